@@ -1,0 +1,323 @@
+"""CPU oracle for the DSS2 hot path - TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+A plain-PyTorch (CPU, fp32 or fp64) restatement of the reference algorithm on the north-star path:
+PyG-style batching, the EdgeAggregation + TAGConv "PowerFlowNet" models and the physics-informed
+WLS loss.  Only `tests/`, `__graft_entry__.smoke()` and the `cpu_baseline` / `--impl reference`
+legs of `bench.py` may import this file; the product package never does.
+
+Every function cites the reference lines it follows (paths relative to the reference root).  The
+PyG pieces (`MessagePassing.propagate`, `TAGConv`, `gcn_norm`, `scatter`, `Batch.from_data_list`)
+restate torch_geometric's published semantics, because torch_geometric is an un-vendored,
+un-pinned dependency (reference README.md:31) that is not installable here.
+
+How it is pinned:
+  * `get_pflow` / bus injections: against the pandapower-solved columns of the reference's own
+    `data/cigre14` pickles (fixtures in tests/golden/, test_oracle_golden.py).
+  * everything else: against outputs of the reference's own `networks.py` / `data.py` executed
+    verbatim in the build container over `oracle/pyg_shim` (tests/golden/make_golden.py wrote them).
+  * against real PyG: PARITY UNPINNED (no PyG available, the reference holds no tests).
+
+Functional style on purpose: models are evaluated from a `state_dict` with the reference's
+parameter names, so the same weights drive the reference, this oracle and the CUDA path.
+"""
+import math
+
+import torch
+
+# --------------------------------------------------------------------------------------------
+# batching  (PyG Batch.from_data_list as used by dss2_run.py:68-69,134)
+# --------------------------------------------------------------------------------------------
+
+
+def collate(graphs):
+    """Disjoint-union batch of `graphs` = list of dicts {x[N,11], edge_index[2,E] i64, edge_attr[E,13], y[N,2]}.
+
+    PyG semantics: features concatenated graph-major on dim 0, `edge_index` concatenated on dim 1
+    with the running node count added, per-graph edge order preserved; `batch[n]` = graph id of
+    node n; `ptr` = exclusive prefix sum of node counts (length B+1)."""
+    xs, eas, ys, eis, bvec, ptr = [], [], [], [], [], [0]
+    for g, gr in enumerate(graphs):
+        n = gr["x"].shape[0]
+        xs.append(gr["x"])
+        eas.append(gr["edge_attr"])
+        ys.append(gr["y"])
+        eis.append(gr["edge_index"] + ptr[-1])
+        bvec.append(torch.full((n,), g, dtype=torch.long))
+        ptr.append(ptr[-1] + n)
+    return {
+        "x": torch.cat(xs, 0), "edge_attr": torch.cat(eas, 0), "y": torch.cat(ys, 0),
+        "edge_index": torch.cat(eis, 1), "batch": torch.cat(bvec, 0),
+        "ptr": torch.tensor(ptr, dtype=torch.long),
+    }
+
+
+# --------------------------------------------------------------------------------------------
+# graph helpers
+# --------------------------------------------------------------------------------------------
+
+
+def segment_sum(values, index, num_rows):
+    """PyG `scatter(..., reduce='sum')`: zeros(num_rows, ...).scatter_add_ along dim 0."""
+    shape = (num_rows,) + tuple(values.shape[1:])
+    idx = index.view((-1,) + (1,) * (values.dim() - 1)).expand_as(values)
+    return values.new_zeros(shape).scatter_add_(0, idx, values)
+
+
+def needs_reverse_edges(edge_index):
+    """networks.py:236-238 `is_directed`: looks only at edge 0 = (s0 -> t0) and reports "directed"
+    when s0 does not occur among the targets of edges that leave t0."""
+    s0, t0 = edge_index[0, 0], edge_index[1, 0]
+    targets_of_t0 = edge_index[1, edge_index[0] == t0]
+    return not bool((targets_of_t0 == s0).any())
+
+
+def undirect(edge_index, edge_attr):
+    """networks.py:240-258: append every edge reversed after all forward edges; the reversed copy
+    of the attributes flips the sign of columns 0 and 2 (normalised P and Q flow) only (:252)."""
+    if not needs_reverse_edges(edge_index):
+        return edge_index, edge_attr
+    both = torch.cat([edge_index, edge_index.flip(0)], dim=1)
+    sign = edge_attr.new_ones(edge_attr.shape[1])
+    sign[0] = -1.0
+    sign[2] = -1.0
+    # multiplying by -1/+1 is exact and gives -0.0 for masked zeros exactly like unary minus
+    return both, torch.cat([edge_attr, edge_attr * sign], dim=0)
+
+
+def gcn_weights(edge_index, num_nodes, dtype):
+    """PyG gcn_norm(add_self_loops=False) as TAGConv calls it: in-degree by target,
+    w_e = deg[src]^-1/2 * deg[dst]^-1/2, infinities zeroed."""
+    src, dst = edge_index[0], edge_index[1]
+    deg = segment_sum(torch.ones(src.numel(), dtype=dtype), dst, num_nodes)
+    dis = deg.pow(-0.5)
+    dis = torch.where(torch.isinf(dis), torch.zeros_like(dis), dis)
+    return dis[src] * dis[dst]
+
+
+# --------------------------------------------------------------------------------------------
+# layers  (networks.py:159-209 EdgeAggregation; PyG TAGConv; networks.py:268-269 dropout/relu)
+# --------------------------------------------------------------------------------------------
+
+
+def edge_aggregation(x, edge_index, edge_attr, w1, b1, w2, b2):
+    """networks.py:176-181 + :206 with aggr='add' (:164): message MLP on [x_target | x_source | a_e],
+    summed into the target node.  The degree norm of :196-200 never reaches `message` and is omitted."""
+    src, dst = edge_index[0], edge_index[1]
+    feats = torch.cat([x.index_select(0, dst), x.index_select(0, src), edge_attr], dim=-1)
+    hidden = torch.relu(torch.addmm(b1, feats, w1.t()))
+    msg = torch.addmm(b2, hidden, w2.t())
+    return segment_sum(msg, dst, x.shape[0])
+
+
+def tag_conv(x, edge_index, weights, bias, edge_w=None):
+    """PyG TAGConv.forward: out = sum_k (A_hat^k x) W_k^T + b with A_hat from gcn_weights, hop by hop.
+    `edge_w` may carry precomputed gcn weights; PyG itself recomputes them in every layer."""
+    if edge_w is None:
+        edge_w = gcn_weights(edge_index, x.shape[0], x.dtype)
+    src, dst = edge_index[0], edge_index[1]
+    out = x @ weights[0].t()
+    for wk in weights[1:]:
+        x = segment_sum(edge_w.unsqueeze(1) * x.index_select(0, src), dst, x.shape[0])
+        out = out + x @ wk.t()
+    return out + bias
+
+
+def dropout_relu(x, p, mask=None, generator=None):
+    """networks.py:268-269: a freshly built nn.Dropout is always in training mode, so the mask is
+    applied in eval too.  x * (mask / (1 - p)) is torch's CPU formulation.  `mask` (0/1, same shape)
+    injects a recorded mask; otherwise one is drawn (p=0 -> identity)."""
+    if p > 0.0:
+        if mask is None:
+            mask = torch.empty_like(x).bernoulli_(1.0 - p, generator=generator)
+        x = x * (mask.to(x.dtype) / (1.0 - p))
+    return torch.relu(x)
+
+
+# --------------------------------------------------------------------------------------------
+# models, evaluated from a state_dict with the reference parameter names
+# --------------------------------------------------------------------------------------------
+
+
+def _layer_params(sd, prefix):
+    k = 0
+    ws = []
+    while f"{prefix}lins.{k}.weight" in sd:
+        ws.append(sd[f"{prefix}lins.{k}.weight"])
+        k += 1
+    return ws, sd[f"{prefix}bias"]
+
+
+def mpn_forward(sd, prefix, x, edge_index, edge_attr, p_drop, skip, masks=None, generator=None):
+    """networks.py:260-273 (MPN) and :323-338 (SkipMPN, `skip=True` adds the input back, :336).
+    `masks`: optional list with one 0/1 tensor per hidden TAG layer."""
+    x_in = x
+    ei2, ea2 = undirect(edge_index, edge_attr)
+    x = edge_aggregation(x, ei2, ea2,
+                         sd[f"{prefix}edge_aggr.edge_aggr.0.weight"], sd[f"{prefix}edge_aggr.edge_aggr.0.bias"],
+                         sd[f"{prefix}edge_aggr.edge_aggr.2.weight"], sd[f"{prefix}edge_aggr.edge_aggr.2.bias"])
+    n_layers = 0
+    while f"{prefix}convs.{n_layers}.bias" in sd:
+        n_layers += 1
+    for layer in range(n_layers):
+        ws, b = _layer_params(sd, f"{prefix}convs.{layer}.")
+        x = tag_conv(x, ei2, ws, b)
+        if layer < n_layers - 1:
+            x = dropout_relu(x, p_drop, None if masks is None else masks[layer], generator)
+    return x_in + x if skip else x
+
+
+def pfn_forward(sd, x, edge_index, edge_attr, p_drop, skip=True, masks=None, generator=None):
+    """networks.py:359-363 (PFN, skip=False) / :384-388 (SkipPFN, skip=True): L stacked sub-nets that
+    all receive the same raw edge attributes; the last one is always a plain MPN (:355,:380)."""
+    n_sub = 0
+    while f"mpns.{n_sub}.convs.0.bias" in sd:
+        n_sub += 1
+    for s in range(n_sub):
+        sub_masks = None if masks is None else masks[s]
+        x = mpn_forward(sd, f"mpns.{s}.", x, edge_index, edge_attr, p_drop,
+                        skip=(skip and s < n_sub - 1), masks=sub_masks, generator=generator)
+    return x
+
+
+def init_state_dict(kind="SkipPFN", dim_featn=8, dim_feate=6, dim_out=2, dim_hid=32, n_gnn_layers=8, K=2, L=5,
+                    seed=0, dtype=torch.float32):
+    """Random parameters with the reference's names/shapes (checkpoint row).  The init
+    distribution (uniform +-1/sqrt(fan_in), TAG bias zero) matches torch/PyG Linear defaults, but parity
+    always goes through state_dict transfer, never seed replay.  kind: MPN | SkipMPN | PFN | SkipPFN."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+
+    def lin(name, fan_out, fan_in, bias):
+        bound = 1.0 / math.sqrt(fan_in)
+        sd[f"{name}.weight"] = ((torch.rand(fan_out, fan_in, generator=g, dtype=torch.float64) * 2 - 1) * bound).to(dtype)
+        if bias:
+            sd[f"{name}.bias"] = ((torch.rand(fan_out, generator=g, dtype=torch.float64) * 2 - 1) * bound).to(dtype)
+
+    def mpn(prefix, d_out):
+        lin(f"{prefix}edge_aggr.edge_aggr.0", dim_hid, 2 * dim_featn + dim_feate, True)
+        lin(f"{prefix}edge_aggr.edge_aggr.2", dim_hid, dim_hid, True)
+        for layer in range(n_gnn_layers):
+            cout = d_out if layer == n_gnn_layers - 1 else dim_hid
+            sd[f"{prefix}convs.{layer}.bias"] = torch.zeros(cout, dtype=dtype)
+            for k in range(K + 1):
+                lin(f"{prefix}convs.{layer}.lins.{k}", cout, dim_hid, False)
+
+    if kind in ("MPN", "SkipMPN"):
+        mpn("", dim_out)
+    else:
+        for s in range(L):
+            mpn(f"mpns.{s}.", dim_out if s == L - 1 else dim_featn)
+    return sd
+
+
+# --------------------------------------------------------------------------------------------
+# physics: branch flows (data.py:328-390) and the WLS loss (data.py:393-459)
+# --------------------------------------------------------------------------------------------
+
+
+def get_pflow(y, edge_index, node_param, edge_param):
+    """data.py:328-390 with phase_shift=True (the only way it is called: angle shift ignored, :362-363).
+
+    y[Nt,2] = (V pu, theta rad); edge_index one-way [2,Et]; node_param[:,0] = vn_kv;
+    edge_param = (G, B, Gs, Bs, closed, phase_shift, imax_or_sn).
+    Returns (loading_lines, loading_trafo, P_from, Q_from, P_to, Q_to, I_from, I_to)."""
+    vn = node_param[:, 0]
+    v_hv, v_lv = vn.max(), vn.min()                     # :334-336, over the whole batch
+    ratio = (v_hv / v_lv).detach()                      # :338
+    frm, to = edge_index[0], edge_index[1]
+    vi, vj = y[:, 0][frm], y[:, 0][to]                  # :355-358
+    delta = y[:, 1][frm] - y[:, 1][to]                  # shift = 0
+    g, b, gs, bs = edge_param[:, 0], edge_param[:, 1], edge_param[:, 2], edge_param[:, 3]
+    is_trafo = torch.ceil(edge_param[:, 5].detach())    # :367 (3 on Oberrhein: quirk kept)
+    rating = edge_param[:, 6].detach()                  # :368
+    cosd, sind = torch.cos(delta), torch.sin(delta)
+    base = v_lv ** 2
+    p_from = (-vi * vj * (g * cosd + b * sind) + (g + gs / 2) * vi ** 2) * base     # :370
+    q_from = (vi * vj * (-g * sind + b * cosd) - (b + bs / 2) * vi ** 2) * base     # :372
+    p_to = (-vi * vj * (g * cosd - b * sind) + (g + gs / 2) * vj ** 2) * base       # :374
+    q_to = (vi * vj * (g * sind + b * cosd) - (b + bs / 2) * vj ** 2) * base        # :376
+    sqrt3 = torch.sqrt(torch.tensor(3.0, dtype=torch.float32)).to(y.dtype)          # :378 fp32 sqrt(3)
+    i_from = torch.complex(p_from, -q_from).abs() / (vi * v_lv * sqrt3)             # :378
+    i_from = i_from / (1.0 - (is_trafo * (1.0 - ratio)))                            # :380
+    i_to = torch.complex(p_to, -q_to).abs() / (vj * v_lv * sqrt3)                   # :383
+    load_lines = ((1.0 - is_trafo) * torch.maximum(i_from, i_to)) / rating          # :387
+    load_trafo = (is_trafo * torch.maximum(i_from * v_hv, i_to * v_lv)) / rating    # :388
+    return load_lines, load_trafo, p_from, q_from, p_to, q_to, i_from, i_to
+
+
+def wls_loss(x, edge_attr, output, x_mean, x_std, edge_mean, edge_std, edge_index, reg_coefs):
+    """data.py:393-459 `gsp_wls_edge`, taking the full 11-/13-column tensors (the caller slices them
+    into input / node_param / edge_input / edge_param, dss2_run.py:140).  The dead dense Laplacian
+    (:422-423) is omitted - it does not influence the result.  `output` is NOT modified in place here
+    (the reference zeroes slack theta inside the caller's tensor, :412-413; the effect on the loss is
+    identical).  Returns the 0-dim loss."""
+    feat, node_param = x[:, :8], x[:, 8:]
+    efeat, edge_param = edge_attr[:, :6], edge_attr[:, 6:]
+    nt = x.shape[0]
+    z, r = feat[:, 0::2], feat[:, 1::2]                               # :397, :403
+    ez, er = efeat[:, 0:4:2], efeat[:, 1:4:2]                         # :398, :405
+    meas = (z * x_std[0::2] + x_mean[0::2]) * (z != 0)                # :402
+    wgt = (r * x_std[1::2] + x_mean[1::2]) * (r != 0)                 # :408
+    emeas = (ez * edge_std[0:4:2] + edge_mean[0:4:2]) * (ez != 0)     # :401
+    ewgt = (er * edge_std[1:4:2] + edge_mean[1:4:2]) * (er != 0)      # :409
+    v = output[:, 0:1] * x_std[:1] + x_mean[:1]                       # :411
+    theta = output[:, 1:] * (1.0 - node_param[:, 1:2])                # :412-413
+    state = torch.cat([v, theta], dim=1)
+    ll, lt, pf, qf, pt, qt, _, _ = get_pflow(state, edge_index, node_param, edge_param)
+    loading = ll + lt                                                 # :417
+    frm, to = edge_index[0], edge_index[1]
+    p_bus = -segment_sum(pt, to, nt) - segment_sum(pf, frm, nt)       # :428
+    q_bus = -segment_sum(qt, to, nt) - segment_sum(qf, frm, nt)       # :429
+    dtheta = (theta[:, 0][frm] - theta[:, 0][to]).abs()               # :431
+    h = torch.cat([v, theta, p_bus[:, None], q_bus[:, None]], dim=1)  # :433
+    h_edge = torch.stack([pf, qf], dim=1)                             # :435
+    lam_n = torch.tensor([reg_coefs["lam_v"], reg_coefs["lam_v"], reg_coefs["lam_p"], reg_coefs["lam_p"]], dtype=x.dtype)
+    lam_e = torch.tensor([reg_coefs["lam_pf"], reg_coefs["lam_pf"]], dtype=x.dtype)
+    j_node = (((meas - h) ** 2 * wgt) * lam_n).sum(1)                 # :446
+    j_edge = (((emeas - h_edge) ** 2 * ewgt) * lam_e).sum(1)          # :447
+    j = j_node.mean() + j_edge.mean()                                 # :450
+    lam = reg_coefs["lam_reg"]
+    j_v = lam * (torch.relu(v - 1.1) + torch.relu(0.9 - v)).mean() ** 2       # :453
+    j_t = lam * torch.relu(dtheta - 0.5).mean() ** 2                          # :454
+    j_l = lam * torch.relu(loading - 1.5).mean() ** 2                         # :455
+    return j + j_v + j_t + j_l
+
+
+# --------------------------------------------------------------------------------------------
+# optimizer (adjacent row a10: torch.optim.Adamax defaults, dss2_run.py:91-92)
+# --------------------------------------------------------------------------------------------
+
+
+def adamax_step(param, grad, exp_avg, exp_inf, step, lr=3e-3, beta1=0.9, beta2=0.999, eps=1e-8):
+    """torch.optim.Adamax single-tensor update (no weight decay); `step` is the 1-based step count.
+    exp_avg = b1*exp_avg + (1-b1)*g ; exp_inf = max(b2*exp_inf, |g| + eps) ;
+    param -= lr / (1 - b1^step) * exp_avg / exp_inf.  Updates in place, returns param."""
+    exp_avg.mul_(beta1).add_(grad, alpha=1 - beta1)
+    torch.maximum(exp_inf * beta2, grad.abs() + eps, out=exp_inf)
+    clr = lr / (1 - beta1 ** step)
+    param.addcdiv_(exp_avg, exp_inf, value=-clr)
+    return param
+
+
+# --------------------------------------------------------------------------------------------
+# one training step on CPU (used as the timed CPU baseline "port")
+# --------------------------------------------------------------------------------------------
+
+
+def train_step(sd, batch, stats, reg_coefs, p_drop, opt_state, kind="SkipPFN", generator=None):
+    """fwd + loss + bwd (autograd) + Adamax on CPU, mirroring dss2_run.py:137-143.  `sd` values must be
+    leaf tensors with requires_grad=True; opt_state = {"step": int, name: (exp_avg, exp_inf)}."""
+    for p in sd.values():
+        p.grad = None
+    out = pfn_forward(sd, batch["x"][:, :8], batch["edge_index"], batch["edge_attr"][:, :6], p_drop,
+                      skip=(kind == "SkipPFN"), generator=generator)
+    loss = wls_loss(batch["x"], batch["edge_attr"], out, stats["x_mean"], stats["x_std"],
+                    stats["edge_mean"], stats["edge_std"], batch["edge_index"], reg_coefs)
+    loss.backward()
+    opt_state["step"] = opt_state.get("step", 0) + 1
+    with torch.no_grad():
+        for name, p in sd.items():
+            if name not in opt_state:
+                opt_state[name] = (torch.zeros_like(p), torch.zeros_like(p))
+            adamax_step(p, p.grad, opt_state[name][0], opt_state[name][1], opt_state["step"])
+    return loss.detach()

@@ -1,0 +1,124 @@
+"""`torch_geometric.nn.conv` subset (oracle shim, test infrastructure).
+
+Implemented from PyG's published semantics: MessagePassing(aggr='add', flow='source_to_target'),
+gcn_norm(add_self_loops=False), TAGConv.  The other conv classes named by reference networks.py:7
+(GCN2Conv, FAConv, GINEConv, GCNConv, ChebConv, GATv2Conv) are outside the hot path
+ and exist only as names so that the reference module imports.
+"""
+import inspect
+
+import torch
+from torch import nn
+
+from ..utils import scatter
+
+
+class MessagePassing(nn.Module):
+    """PyG MessagePassing, the part EdgeAggregation (reference networks.py:159-209) and TAGConv use.
+
+    propagate(edge_index, **kw): for every argument of `message()`: a name ending in `_j` is
+    kw[name[:-2]].index_select(0, edge_index[0]) (source), `_i` is the same at edge_index[1]
+    (target); other names are passed through; kwargs that `message()` does not name are dropped.
+    Aggregation 'add' is scatter(msg, edge_index[1], dim=0, dim_size=N, reduce='sum')."""
+
+    def __init__(self, aggr="add", flow="source_to_target", node_dim=0, **kwargs):
+        super().__init__()
+        if aggr not in ("add", "sum", "mean"):
+            raise NotImplementedError(f"shim supports aggr add/mean, got {aggr}")
+        if flow != "source_to_target":
+            raise NotImplementedError("shim supports flow='source_to_target' only")
+        self.aggr = "sum" if aggr == "add" else aggr
+        self.flow = flow
+        self.node_dim = node_dim
+        self._msg_args = [p for p in inspect.signature(self.message).parameters]
+
+    def propagate(self, edge_index, size=None, **kwargs):
+        src, dst = edge_index[0], edge_index[1]
+        num_nodes = None
+        call = {}
+        for name in self._msg_args:
+            if name.endswith("_j") or name.endswith("_i"):
+                base = kwargs[name[:-2]]
+                if num_nodes is None:
+                    num_nodes = base.size(self.node_dim)
+                call[name] = base.index_select(self.node_dim, src if name.endswith("_j") else dst)
+            else:
+                call[name] = kwargs[name]
+        if num_nodes is None:
+            num_nodes = size[1] if size is not None else int(dst.max()) + 1
+        msg = self.message(**call)
+        out = scatter(msg, dst, dim=self.node_dim, dim_size=num_nodes, reduce=self.aggr)
+        return self.update(out)
+
+    def message(self, x_j):
+        return x_j
+
+    def update(self, inputs):
+        return inputs
+
+
+def gcn_norm(edge_index, edge_weight=None, num_nodes=None, improved=False, add_self_loops=True,
+             flow="source_to_target", dtype=None):
+    """PyG `gcn_norm` for dense-index input.  TAGConv calls it with add_self_loops=False:
+    w = 1; deg = scatter(w, col, N); dis = deg^-1/2 with inf -> 0; w = dis[row] * w * dis[col]."""
+    if add_self_loops:
+        raise NotImplementedError("shim: only the add_self_loops=False path (TAGConv) is restated")
+    if edge_weight is None:
+        edge_weight = torch.ones((edge_index.size(1),), dtype=dtype, device=edge_index.device)
+    row, col = edge_index[0], edge_index[1]
+    idx = col if flow == "source_to_target" else row
+    deg = scatter(edge_weight, idx, dim=0, dim_size=num_nodes, reduce="sum")
+    deg_inv_sqrt = deg.pow_(-0.5)
+    deg_inv_sqrt.masked_fill_(deg_inv_sqrt == float("inf"), 0)
+    edge_weight = deg_inv_sqrt[row] * edge_weight * deg_inv_sqrt[col]
+    return edge_index, edge_weight
+
+
+class TAGConv(MessagePassing):
+    """PyG TAGConv(in, out, K, bias=True, normalize=True):
+    lins = ModuleList[(K+1) x Linear(in, out, bias=False)], bias zeros-initialised;
+    forward: gcn_norm(no self loops); out = lins[0](x); for k=1..K: x = A_hat x; out = out + lins[k](x);
+    out = out + bias.  Used at reference networks.py:230-234."""
+
+    def __init__(self, in_channels, out_channels, K=3, bias=True, normalize=True, **kwargs):
+        kwargs.setdefault("aggr", "add")
+        super().__init__(**kwargs)
+        self.in_channels, self.out_channels, self.K, self.normalize = in_channels, out_channels, K, normalize
+        self.lins = nn.ModuleList([nn.Linear(in_channels, out_channels, bias=False) for _ in range(K + 1)])
+        if bias:
+            self.bias = nn.Parameter(torch.zeros(out_channels))
+        else:
+            self.register_parameter("bias", None)
+
+    def forward(self, x, edge_index, edge_weight=None):
+        if self.normalize:
+            edge_index, edge_weight = gcn_norm(edge_index, edge_weight, x.size(self.node_dim),
+                                               improved=False, add_self_loops=False, flow=self.flow,
+                                               dtype=x.dtype)
+        out = self.lins[0](x)
+        for lin in self.lins[1:]:
+            x = self.propagate(edge_index, x=x, edge_weight=edge_weight)
+            out = out + lin(x)
+        if self.bias is not None:
+            out = out + self.bias
+        return out
+
+    def message(self, x_j, edge_weight):
+        return x_j if edge_weight is None else edge_weight.view(-1, 1) * x_j
+
+
+def _outside_hot_path(name):
+    class _Stub(nn.Module):
+        def __init__(self, *a, **k):
+            raise NotImplementedError(f"torch_geometric.nn.conv.{name}: not restated by the oracle shim "
+                                      "(outside the hot path, SURVEY.md 8f-1)")
+    _Stub.__name__ = name
+    return _Stub
+
+
+GCN2Conv = _outside_hot_path("GCN2Conv")
+FAConv = _outside_hot_path("FAConv")
+GINEConv = _outside_hot_path("GINEConv")
+GCNConv = _outside_hot_path("GCNConv")
+ChebConv = _outside_hot_path("ChebConv")
+GATv2Conv = _outside_hot_path("GATv2Conv")

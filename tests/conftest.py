@@ -1,0 +1,77 @@
+"""Shared test plumbing: the `gpu` marker, import paths, golden-file helpers."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "deep-statistical-solver-for-distribution-system-state-estimation_b200")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+for p in (PKG, os.path.join(ROOT, "oracle"), ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+REG_COEFS = {"mu_v": 1e-1, "mu_theta": 1e-1, "lam_v": 1e-4, "lam_p": 1e-8, "lam_pf": 1e-6, "lam_reg": 1e2}  # dss2_run.py:104-112
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def pytest_collection_modifyitems(config, items):
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+def load_golden(name):
+    return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
+
+
+def golden_model(tag):
+    """Golden model file as (ctor dict, kind, state_dict, grads dict, masks list-of-arrays, raw npz)."""
+    z = load_golden(f"golden_model_{tag}.npz")
+    ctor = {}
+    for k, v in z["ctor"]:
+        ctor[str(k)] = float(v) if str(k) == "dropout_rate" else int(float(v))
+    sd = {k[len("param."):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("param.")}
+    grads = {k[len("grad."):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("grad.") }
+    nt = z["x"].shape[0]
+    nm = int(z["num_masks"])
+    masks = None
+    if nm:
+        bits = np.unpackbits(z["masks"])[: nm * nt * ctor["dim_hid"]].reshape(nm, nt, ctor["dim_hid"])
+        masks = [torch.from_numpy(b.astype(np.float32)) for b in bits]
+    return ctor, str(z["kind"]), sd, grads, masks, z
+
+
+def split_masks(masks, ctor):
+    """Flat list of recorded masks -> per-sub-net lists (n_gnn_layers-1 masks per sub-net)."""
+    if masks is None:
+        return None
+    per = ctor["n_gnn_layers"] - 1
+    return [masks[i * per:(i + 1) * per] for i in range(len(masks) // per)]
+
+
+def assert_fp32_parity(ours, ref32, ref64, what="", rtol=1e-5, noise_mult=2.0):
+    """The fp32 parity criterion used throughout (hard part 1).
+
+    `ref32` is the reference result in fp32, `ref64` the same computation in fp64 (the arbiter).  Two
+    correct fp32 implementations differ by rounding noise that the cancellation-heavy flow equations
+    amplify, so a candidate passes when its distance to the fp64 truth is at most
+    max(rtol * scale, noise_mult * |ref32 - ref64|_max): i.e. within `rtol` relative, or no worse than
+    `noise_mult` times the reference's own fp32 rounding error on that tensor."""
+    ours = torch.as_tensor(ours).double().cpu()
+    ref32 = torch.as_tensor(ref32).double().cpu()
+    ref64 = torch.as_tensor(ref64).double().cpu()
+    scale = float(ref64.abs().max()) if ref64.numel() else 0.0
+    noise = float((ref32 - ref64).abs().max()) if ref64.numel() else 0.0
+    err = float((ours - ref64).abs().max()) if ref64.numel() else 0.0
+    tol = max(rtol * scale, noise_mult * noise)
+    assert err <= tol + 1e-300, f"{what}: err {err:.3e} > tol {tol:.3e} (scale {scale:.3e}, ref32 noise {noise:.3e})"
+    return err, tol

@@ -1,0 +1,188 @@
+"""Generates the golden vectors under tests/golden/ by running the REFERENCE's own code.
+
+Run in the build container only (needs /root/reference, which does not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+It imports the reference's unmodified `data.py` and `networks.py` with `oracle/pyg_shim` standing
+in for torch_geometric (absent from the image), feeds them seeded inputs and stores inputs and
+outputs as .npz.  Tests never import the reference; they compare the oracle (CPU tests) and the
+CUDA path (gpu tests) with these files.
+
+Files written
+  golden_dataset_cigre14.npz  reference data_from_pickles on the first 128 CIGRE-14 scenarios after
+                              np.random.seed(0); loss KATs of gsp_wls_edge on the first 64 graphs
+  golden_model_<tag>.npz      reference model forward + gsp_wls_edge + backward: inputs, recorded
+                              dropout masks, output (before / after the in-place slack masking), loss,
+                              all parameter gradients and the gradient w.r.t. the model output
+"""
+import os
+import pickle
+import sys
+import tempfile
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+PKG = os.path.join(ROOT, "deep-statistical-solver-for-distribution-system-state-estimation_b200")
+sys.path.insert(0, os.path.join(ROOT, "oracle", "pyg_shim"))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, "/root/reference")
+
+import data as ref_data          # noqa: E402  (reference)
+import networks as ref_net       # noqa: E402  (reference)
+from torch_geometric.data import Batch, Data  # noqa: E402  (shim)
+import dss2_oracle as orc        # noqa: E402
+
+sys.path.insert(0, PKG)
+from dss2 import synth           # noqa: E402
+
+REG = {"mu_v": 1e-1, "mu_theta": 1e-1, "lam_v": 1e-4, "lam_p": 1e-8, "lam_pf": 1e-6, "lam_reg": 1e2}  # dss2_run.py:104-112
+CIGRE_MEAS_V, CIGRE_MEAS_PF = np.array([0, 1, 12, 7, 11, 14]), np.array([0, 10])
+
+
+def ref_loss(b, out, stats):
+    xm, xs, em, es = stats
+    return ref_data.gsp_wls_edge(input=b.x[:, :8], edge_input=b.edge_attr[:, :6], output=out, x_mean=xm, x_std=xs,
+                                 edge_mean=em, edge_std=es, edge_index=b.edge_index, reg_coefs=REG,
+                                 num_samples=b.batch[-1] + 1, node_param=b.x[:, 8:], edge_param=b.edge_attr[:, 6:])
+
+
+class RecordingDropout(torch.nn.Module):
+    """Same arithmetic as torch's CPU dropout (x * (bernoulli(1-p) / (1-p))) but keeps the mask."""
+    record = []
+
+    def __init__(self, p=0.5, inplace=False):
+        super().__init__()
+        self.p = p
+
+    def forward(self, x):
+        noise = F.dropout(torch.ones_like(x), self.p, True)
+        RecordingDropout.record.append((noise != 0).numpy().copy())
+        return x * noise
+
+
+def run_model(tag, kind, ctor, batch, stats, sd_seed, torch_seed, dtype=torch.float32):
+    sd = orc.init_state_dict(kind=kind, dim_featn=ctor["dim_featn"], dim_feate=ctor["dim_feate"], dim_out=ctor["dim_out"],
+                             dim_hid=ctor["dim_hid"], n_gnn_layers=ctor["n_gnn_layers"], K=ctor["K"],
+                             L=ctor.get("L", 1), seed=sd_seed)
+    # non-zero TAG biases so that the bias path is exercised
+    g = torch.Generator().manual_seed(sd_seed + 1)
+    for k in sd:
+        if "convs." in k and k.endswith(".bias"):
+            sd[k] = (torch.rand(sd[k].shape, generator=g) - 0.5) * 0.2
+    model = getattr(ref_net, kind)(**ctor)
+    missing = model.load_state_dict(sd, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    model = model.to(dtype)
+    real = torch.nn.Dropout
+    torch.nn.Dropout = RecordingDropout
+    RecordingDropout.record = []
+    try:
+        torch.manual_seed(torch_seed)
+        model.train()
+        x = batch.x.to(dtype)
+        ea = batch.edge_attr.to(dtype)
+        out = model(x[:, :8], batch.edge_index, ea[:, :6])
+    finally:
+        torch.nn.Dropout = real
+    res = {"x": batch.x.numpy(), "edge_index": batch.edge_index.numpy(), "edge_attr": batch.edge_attr.numpy(),
+           "ptr": batch.ptr.numpy(), "out": out.detach().numpy().copy(),
+           "masks": np.packbits(np.stack(RecordingDropout.record).reshape(-1)) if RecordingDropout.record else np.zeros(0, np.uint8),
+           "num_masks": len(RecordingDropout.record),
+           "kind": kind, "ctor": np.array(sorted(ctor.items()), dtype=object).astype(str), "sd_seed": sd_seed,
+           "x_mean": stats[0].numpy(), "x_std": stats[1].numpy(), "edge_mean": stats[2].numpy(), "edge_std": stats[3].numpy()}
+    if ctor["dim_out"] == 2:
+        got = {}
+        out.register_hook(lambda g_: got.__setitem__("g", g_.clone()))   # gradient w.r.t. the pre-masking output
+        bb = Batch(x=x, edge_index=batch.edge_index, edge_attr=ea, y=batch.y)
+        bb.batch = batch.batch
+        loss = ref_loss(bb, out, [s.to(dtype) for s in stats])
+        loss.backward()
+        res["loss"] = np.array(loss.item())
+        res["out_after_loss"] = out.detach().numpy().copy()
+        res["grad_out"] = got["g"].numpy().copy()
+        slack = batch.x[:, 9] == 1.0
+        assert float(np.abs(res["grad_out"][slack.numpy(), 1]).max()) == 0.0
+    else:
+        # models that do not end in (V, theta): a fixed linear functional of the output as the "loss"
+        gw = torch.linspace(-1.0, 1.0, out.numel(), dtype=dtype).reshape(out.shape)
+        (out * gw).sum().backward()
+        res["grad_out"] = gw.numpy()
+    for name, p in model.named_parameters():
+        res["grad." + name] = p.grad.detach().numpy().copy()
+        res["param." + name] = p.detach().numpy().copy()
+    np.savez_compressed(os.path.join(HERE, f"golden_model_{tag}.npz"), **res)
+    print(tag, "out", tuple(out.shape), "loss", res.get("loss"), "masks", res["num_masks"])
+
+
+def main():
+    torch.set_num_threads(1)
+    fix = np.load(os.path.join(HERE, "cigre14_scenarios.npz"), allow_pickle=False)
+    S = fix["nodes"].shape[0]
+
+    # ---- reference data_from_pickles on the same 128 scenarios the fixture holds ----
+    with tempfile.TemporaryDirectory() as tmp:
+        for name in ("nodes", "edges", "labels"):
+            with open(f"/root/reference/data/cigre14/{name}", "rb") as fh:
+                full = pickle.load(fh)
+            with open(os.path.join(tmp, name), "wb") as fh:
+                pickle.dump(full[:S], fh)
+        with open("/root/reference/data/cigre14/noise_param", "rb") as fh:
+            noise = pickle.load(fh)
+        with open(os.path.join(tmp, "noise_param"), "wb") as fh:
+            pickle.dump(noise, fh)
+        np.random.seed(0)
+        ds, xm, xs, em, es = ref_data.data_from_pickles(tmp + "/", 8, 6, 4, 2, CIGRE_MEAS_V, CIGRE_MEAS_PF)
+    stats = (xm, xs, em, es)
+    b64 = Batch.from_data_list(ds[:64])
+    truth = torch.stack([(b64.y[:, 0] - xm[0]) / xs[0], b64.y[:, 1]], 1)
+    kat_truth = ref_loss(b64, truth.clone(), stats).item()
+    kat_zeros = ref_loss(b64, torch.zeros_like(truth), stats).item()
+    pick = [3, 0, 7, 1, 127]
+    bp = Batch.from_data_list([ds[i] for i in pick])
+    np.savez_compressed(
+        os.path.join(HERE, "golden_dataset_cigre14.npz"),
+        x=torch.cat([d.x for d in ds]).numpy(), edge_attr=torch.cat([d.edge_attr for d in ds]).numpy(),
+        y=torch.cat([d.y for d in ds]).numpy(), edge_index=ds[0].edge_index.numpy(),
+        x_mean=xm.numpy(), x_std=xs.numpy(), edge_mean=em.numpy(), edge_std=es.numpy(),
+        kat_loss_truth=np.array(kat_truth), kat_loss_zeros=np.array(kat_zeros),
+        pick=np.array(pick), pick_x=bp.x.numpy(), pick_edge_index=bp.edge_index.numpy(),
+        pick_edge_attr=bp.edge_attr.numpy(), pick_y=bp.y.numpy(), pick_batch=bp.batch.numpy(), pick_ptr=bp.ptr.numpy())
+    print("dataset: KAT truth", kat_truth, "zeros", kat_zeros)
+
+    default = dict(dim_featn=8, dim_feate=6, dim_out=2, dim_hid=32, n_gnn_layers=8, K=2, dropout_rate=0.3, L=5)
+    small = dict(dim_featn=8, dim_feate=6, dim_out=2, dim_hid=32, n_gnn_layers=3, K=2, dropout_rate=0.0, L=2)
+    mpn = dict(dim_featn=8, dim_feate=6, dim_out=2, dim_hid=32, n_gnn_layers=4, K=2, dropout_rate=0.3)
+    skipmpn = dict(dim_featn=8, dim_feate=6, dim_out=8, dim_hid=32, n_gnn_layers=3, K=2, dropout_rate=0.3)
+
+    b4 = Batch.from_data_list(ds[10:14])
+    run_model("skippfn_cigre", "SkipPFN", default, b4, stats, sd_seed=1, torch_seed=11)
+    run_model("pfn_small_cigre", "PFN", small, Batch.from_data_list(ds[20:23]), stats, sd_seed=2, torch_seed=12)
+    run_model("mpn_cigre", "MPN", mpn, Batch.from_data_list(ds[30:35]), stats, sd_seed=3, torch_seed=13)
+    run_model("skipmpn_cigre", "SkipMPN", skipmpn, Batch.from_data_list(ds[40:42]), stats, sd_seed=4, torch_seed=14)
+
+    # ---- Oberrhein: synthetic scenarios from the product generator, reference model + loss on top ----
+    grid = synth.load_grid("ober_sub")
+    store = synth.synthetic_store(grid, 16, seed=1234)
+    graphs = [Data(**store.graph(s)) for s in range(3)]
+    ob = Batch.from_data_list(graphs)
+    ostats = (store.x_mean, store.x_std, store.edge_mean, store.edge_std)
+    run_model("skippfn_ober", "SkipPFN", dict(default, n_gnn_layers=4, L=2), ob, ostats, sd_seed=5, torch_seed=15)
+    # a far-from-solution output so that all three soft-constraint penalties are active
+    torch.manual_seed(99)
+    wild = torch.stack([torch.randn(ob.x.shape[0]) * 3.0, torch.randn(ob.x.shape[0]) * 0.8], 1).requires_grad_(True)
+    loss = ref_loss(ob, wild * 1.0, ostats)
+    loss.backward()
+    np.savez_compressed(os.path.join(HERE, "golden_loss_ober_wild.npz"), x=ob.x.numpy(), edge_index=ob.edge_index.numpy(),
+                        edge_attr=ob.edge_attr.numpy(), output=wild.detach().numpy(), loss=np.array(loss.item()),
+                        grad_out=wild.grad.numpy(), x_mean=ostats[0].numpy(), x_std=ostats[1].numpy(),
+                        edge_mean=ostats[2].numpy(), edge_std=ostats[3].numpy())
+    print("ober wild loss", loss.item())
+
+
+if __name__ == "__main__":
+    main()
