@@ -1,0 +1,496 @@
+// (b2) TAGConv(32 -> cout, K hops) [+ dropout + ReLU] [+ residual], forward and recompute-based backward.
+// Replaces PyG TAGConv.forward + gcn_norm (recomputed per layer in the reference) and the inline
+// Dropout/ReLU of networks.py:268-269, 330-331, plus what autograd derives for them.
+//
+// Design (small-graph / tile path; a tile = a few WHOLE graphs, so hops never leave the CTA):
+//   * persistent CTAs loop over tiles; the tile's node features sit in shared memory as [rows][32] fp32,
+//     one warp lane per hidden feature, so hop gathers are conflict-free and HBM rows are 128-byte lines;
+//   * A_hat^k x is built hop by hop in shared memory walking the CSR-by-destination in PyG scatter
+//     order: segmented sums without atomics;
+//   * the (K+1) 32x32 transforms run on CUDA cores with the weight operand resident in registers
+//     (96 registers per lane for K=2) and the activation operand delivered by warp-broadcast LDS.128,
+//     i.e. 1 shared-memory wavefront per 4 FFMA warp-instructions;
+//   * forward epilogue fuses bias, dropout (counter-based Philox or an injected mask), ReLU, residual and
+//     emits one 32-bit word per node with the sign pattern of the output - all the backward needs;
+//   * backward recomputes A_hat x, A_hat^2 x from the saved layer input and is warp-specialised: half of
+//     the warps produce grad_x by Horner's rule (A_hat is symmetric on the doubled graph),
+//     the other half accumulate grad_W / grad_b in registers across all tiles of the CTA; per-CTA
+//     partial sums are written once and reduced in fixed order by dss2_reduce_partials (deterministic).
+#include "common.cuh"
+
+namespace {
+
+constexpr int FWD_THREADS = 256;
+constexpr int FWD_WARPS = FWD_THREADS / 32;
+constexpr int BWD_THREADS = 512;
+constexpr int BWD_ROLE_WARPS = BWD_THREADS / 64;   // warps per role
+constexpr int MAXK = 3;
+
+struct TagFwdArgs {
+  dss2_graph_t g;
+  const float* x;
+  const float* w;
+  const float* bias;
+  int cout;
+  int act;
+  float scale;          // 1/(1-p)
+  uint32_t keep_thr;    // keep iff rnd < keep_thr
+  int drop_mode;        // 0 none, 1 philox, 2 mask
+  const uint64_t* rng;
+  uint32_t layer_uid;
+  const uint8_t* mask;
+  const float* res;
+  int64_t res_stride;
+  float* y;
+  uint32_t* bits;
+};
+
+struct TagBwdArgs {
+  dss2_graph_t g;
+  const float* x;
+  const float* w;
+  int cout;
+  int act;
+  float scale;
+  const uint32_t* bits;
+  const float* gy;
+  float* gx;
+  float* partials;
+  int64_t partial_stride;
+  int64_t bias_offset;
+};
+
+__host__ __device__ inline int round4(int v) { return (v + 3) & ~3; }
+
+// Tile topology in shared memory: local rowptr, local source ids, degree norm.
+struct TileTopo {
+  int* rowptr;
+  int* col;
+  float* dis;
+};
+
+__device__ __forceinline__ void load_topo(const dss2_graph_t& g, const TileRange& r, TileTopo s, int tid, int nthreads) {
+  const int nT = r.n1 - r.n0, nZ = r.z1 - r.z0;
+  for (int i = tid; i <= nT; i += nthreads) s.rowptr[i] = g.rowptr[r.n0 + i] - r.z0;
+  for (int i = tid; i < nT; i += nthreads) s.dis[i] = g.dis[r.n0 + i];
+  for (int i = tid; i < nZ; i += nthreads) s.col[i] = g.col[r.z0 + i] - r.n0;
+}
+
+// dst[row][lane] = sum_{e in row} dis[row] * dis[src] * src_feat[src][lane]   (one warp per row)
+__device__ __forceinline__ float hop_row(const TileTopo& s, const float* __restrict__ src, int row, int lane) {
+  const int beg = s.rowptr[row], end = s.rowptr[row + 1];
+  const float dn = s.dis[row];
+  float acc = 0.0f;
+  for (int z = beg; z < end; ++z) {
+    const int c = s.col[z];
+    acc = fmaf(dn * s.dis[c], src[c * HID + lane], acc);
+  }
+  return acc;
+}
+
+// contiguous rows global -> shared, 16 bytes per thread per step
+__device__ __forceinline__ void load_rows32(float* dst, const float* __restrict__ src, int nrows, int tid, int nthreads) {
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+  float4* d4 = reinterpret_cast<float4*>(dst);
+  for (int i = tid; i < nrows * (HID / 4); i += nthreads) d4[i] = ldg_stream4(s4 + i);
+}
+
+// -------------------------------------------------------------------------------------------------
+// forward
+// -------------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(FWD_THREADS, 2) k_tag_fwd(TagFwdArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const dss2_graph_t& g = a.g;
+  const int TR = round4(g.max_tile_nodes);
+  float* X = smem;                                   // [K+1][TR][32]
+  TileTopo topo;
+  topo.rowptr = reinterpret_cast<int*>(X + (K + 1) * TR * HID);
+  topo.dis = reinterpret_cast<float*>(topo.rowptr + TR + 4);
+  topo.col = reinterpret_cast<int*>(topo.dis + TR);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cout = a.cout;
+
+  // weight operand: lane c keeps row c of every W_k (96 registers for K = 2)
+  float W[K + 1][HID];
+#pragma unroll
+  for (int k = 0; k <= K; ++k) {
+#pragma unroll
+    for (int j4 = 0; j4 < HID / 4; ++j4) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (lane < cout) v = *reinterpret_cast<const float4*>(a.w + ((size_t)k * cout + lane) * HID + 4 * j4);
+      W[k][4 * j4 + 0] = v.x;
+      W[k][4 * j4 + 1] = v.y;
+      W[k][4 * j4 + 2] = v.z;
+      W[k][4 * j4 + 3] = v.w;
+    }
+  }
+  const float bias = lane < cout ? a.bias[lane] : 0.0f;
+  uint2 key = make_uint2(0u, 0u);
+  uint32_t step_lo = 0;
+  if (a.drop_mode == 1) {
+    uint64_t seed = a.rng[0], step = a.rng[1];
+    key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32) ^ (a.layer_uid * 0x9E3779B9u) ^ (uint32_t)(step >> 32));
+    step_lo = (uint32_t)step;
+  }
+
+  for (int t = blockIdx.x; t < g.num_tiles; t += gridDim.x) {
+    const TileRange r = tile_range(g, t);
+    const int nT = r.n1 - r.n0;
+    load_rows32(X, a.x + (size_t)r.n0 * HID, nT, tid, FWD_THREADS);
+    load_topo(g, r, topo, tid, FWD_THREADS);
+    __syncthreads();
+    // hops 1..K-1 need every row of the previous hop -> block barrier; the last hop is fused below
+#pragma unroll
+    for (int k = 1; k < K; ++k) {
+      for (int row = warp; row < nT; row += FWD_WARPS) X[(k * TR + row) * HID + lane] = hop_row(topo, X + (k - 1) * TR * HID, row, lane);
+      __syncthreads();
+    }
+    const int nblk = (nT + 3) >> 2;
+    for (int blk = warp; blk < nblk; blk += FWD_WARPS) {
+      const int r0 = blk * 4;
+      if (K >= 1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (r0 + i < nT) X[(K * TR + r0 + i) * HID + lane] = hop_row(topo, X + (K - 1) * TR * HID, r0 + i, lane);
+        __syncwarp();
+      }
+      float acc[4] = {bias, bias, bias, bias};
+#pragma unroll
+      for (int k = 0; k <= K; ++k) {
+        const float* Xk = X + (k * TR + r0) * HID;
+#pragma unroll
+        for (int j4 = 0; j4 < HID / 4; ++j4) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 v = *reinterpret_cast<const float4*>(Xk + i * HID + 4 * j4);   // warp-broadcast
+            acc[i] = fmaf(v.x, W[k][4 * j4 + 0], acc[i]);
+            acc[i] = fmaf(v.y, W[k][4 * j4 + 1], acc[i]);
+            acc[i] = fmaf(v.z, W[k][4 * j4 + 2], acc[i]);
+            acc[i] = fmaf(v.w, W[k][4 * j4 + 3], acc[i]);
+          }
+        }
+      }
+      // epilogue: dropout -> ReLU -> sign word -> residual -> store (a row is one 128-byte line)
+      uint32_t rnd[4] = {0u, 0u, 0u, 0u};
+      if (a.act && a.drop_mode == 1) {
+        uint4 q = philox4x32_10(make_uint4((uint32_t)t, (uint32_t)blk, (uint32_t)lane, step_lo), key);
+        rnd[0] = q.x;
+        rnd[1] = q.y;
+        rnd[2] = q.z;
+        rnd[3] = q.w;
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int row = r0 + i;
+        if (row >= nT) break;   // warp-uniform
+        const size_t n = (size_t)r.n0 + row;
+        float v = acc[i];
+        if (a.act) {
+          bool keep = true;
+          if (a.drop_mode == 1) keep = rnd[i] < a.keep_thr;
+          else if (a.drop_mode == 2) keep = a.mask[n * HID + lane] != 0;
+          if (a.drop_mode != 0) v = keep ? v * a.scale : 0.0f;
+          v = fmaxf(v, 0.0f);
+          const uint32_t word = __ballot_sync(0xffffffffu, v > 0.0f);
+          if (lane == 0 && a.bits) a.bits[n] = word;
+        }
+        if (lane < cout) {
+          if (a.res) v += a.res[n * a.res_stride + lane];
+          a.y[n * cout + lane] = v;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// backward
+// -------------------------------------------------------------------------------------------------
+template <int K, int CP>   // CP: cout padded to {2, 8, 32}; padded columns carry zeros
+__global__ void __launch_bounds__(BWD_THREADS, 1) k_tag_bwd(TagBwdArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  const dss2_graph_t& g = a.g;
+  const int TR = round4(g.max_tile_nodes);
+  float* X = smem;                          // [K+1][TR][32]  x, A x, A^2 x   (W role recomputes hops)
+  float* G = X + (K + 1) * TR * HID;        // [TR][32]       grad wrt pre-activation output, zero padded
+  float* H = G + TR * HID;                  // [2][TR][32]    Horner ping-pong (X role)
+  TileTopo topo;
+  topo.rowptr = reinterpret_cast<int*>(H + 2 * TR * HID);
+  topo.dis = reinterpret_cast<float*>(topo.rowptr + TR + 4);
+  topo.col = reinterpret_cast<int*>(topo.dis + TR);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool x_role = warp < BWD_ROLE_WARPS;
+  const int rw = x_role ? warp : warp - BWD_ROLE_WARPS;   // warp index inside the role
+  const int cout = a.cout;
+
+  // X role: lane j keeps column j of every W_k (W_k[c][j], c < CP).  W role: lane j accumulates
+  // grad_W_k[c][j] for all c, plus grad_b[c = lane].
+  float R[K + 1][CP];
+#pragma unroll
+  for (int k = 0; k <= K; ++k)
+#pragma unroll
+    for (int c = 0; c < CP; ++c) R[k][c] = (x_role && c < cout) ? a.w[((size_t)k * cout + c) * HID + lane] : 0.0f;
+  float gb = 0.0f;
+
+  for (int t = blockIdx.x; t < g.num_tiles; t += gridDim.x) {
+    const TileRange r = tile_range(g, t);
+    const int nT = r.n1 - r.n0;
+    load_rows32(X, a.x + (size_t)r.n0 * HID, nT, tid, BWD_THREADS);
+    load_topo(g, r, topo, tid, BWD_THREADS);
+    // grad tile: g_out = grad_y * [y > 0] / (1-p)   (ReLU'(0) = 0; dropped units have y = 0)
+    for (int i = tid; i < nT * HID; i += BWD_THREADS) {
+      const int row = i >> 5, c = i & 31;
+      float v = 0.0f;
+      if (c < cout) {
+        v = a.gy[((size_t)r.n0 + row) * cout + c];
+        if (a.act) v = ((a.bits[(size_t)r.n0 + row] >> c) & 1u) ? v * a.scale : 0.0f;
+      }
+      G[i] = v;
+    }
+    __syncthreads();
+
+    if (x_role) {
+      // grad_x = G W_0 + A (G W_1 + A (G W_2)): Horner over hops, all rows of a stage before the next
+#pragma unroll
+      for (int k = K; k >= 0; --k) {
+        float* out = H + ((K - k) & 1) * TR * HID;
+        const float* prev = H + ((K - k + 1) & 1) * TR * HID;
+        for (int row = rw; row < nT; row += BWD_ROLE_WARPS) {
+          float acc = (k < K) ? hop_row(topo, prev, row, lane) : 0.0f;
+          const float* grow = G + row * HID;
+#pragma unroll
+          for (int c4 = 0; c4 < (CP + 3) / 4; ++c4) {
+            if (CP >= 4) {
+              const float4 v = *reinterpret_cast<const float4*>(grow + 4 * c4);
+              acc = fmaf(v.x, R[k][4 * c4 + 0], acc);
+              acc = fmaf(v.y, R[k][4 * c4 + 1], acc);
+              acc = fmaf(v.z, R[k][4 * c4 + 2], acc);
+              acc = fmaf(v.w, R[k][4 * c4 + 3], acc);
+            } else {
+#pragma unroll
+              for (int c = 0; c < CP; ++c) acc = fmaf(grow[c], R[k][c], acc);
+            }
+          }
+          if (k > 0) out[row * HID + lane] = acc;
+          else a.gx[((size_t)r.n0 + row) * HID + lane] = acc;
+        }
+        if (k > 0) named_bar_sync(1, BWD_THREADS / 2);
+      }
+    } else {
+      // recompute A^k x, then rank-1 updates of grad_W held in registers
+#pragma unroll
+      for (int k = 1; k <= K; ++k) {
+        for (int row = rw; row < nT; row += BWD_ROLE_WARPS) X[(k * TR + row) * HID + lane] = hop_row(topo, X + (k - 1) * TR * HID, row, lane);
+        named_bar_sync(2, BWD_THREADS / 2);
+      }
+      for (int row = rw; row < nT; row += BWD_ROLE_WARPS) {
+        float xk[K + 1];
+#pragma unroll
+        for (int k = 0; k <= K; ++k) xk[k] = X[(k * TR + row) * HID + lane];
+        const float* grow = G + row * HID;
+        gb += grow[lane];
+#pragma unroll
+        for (int c4 = 0; c4 < (CP + 3) / 4; ++c4) {
+          if (CP >= 4) {
+            const float4 v = *reinterpret_cast<const float4*>(grow + 4 * c4);
+#pragma unroll
+            for (int k = 0; k <= K; ++k) {
+              R[k][4 * c4 + 0] = fmaf(v.x, xk[k], R[k][4 * c4 + 0]);
+              R[k][4 * c4 + 1] = fmaf(v.y, xk[k], R[k][4 * c4 + 1]);
+              R[k][4 * c4 + 2] = fmaf(v.z, xk[k], R[k][4 * c4 + 2]);
+              R[k][4 * c4 + 3] = fmaf(v.w, xk[k], R[k][4 * c4 + 3]);
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < CP; ++c)
+#pragma unroll
+              for (int k = 0; k <= K; ++k) R[k][c] = fmaf(grow[c], xk[k], R[k][c]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // cross-warp reduction of the W role's accumulators through shared memory, one partial per CTA
+  float* red = smem;   // [ROLE_WARPS][(K+1)*CP + 1][32]
+  constexpr int PER = (K + 1) * CP + 1;
+  if (!x_role) {
+    float* mine = red + (size_t)rw * PER * HID;
+#pragma unroll
+    for (int k = 0; k <= K; ++k)
+#pragma unroll
+      for (int c = 0; c < CP; ++c) mine[(k * CP + c) * HID + lane] = R[k][c];
+    mine[(K + 1) * CP * HID + lane] = gb;
+  }
+  __syncthreads();
+  float* part = a.partials + (size_t)blockIdx.x * a.partial_stride;
+  const int nW = (K + 1) * cout * HID;
+  for (int i = tid; i < nW + cout; i += BWD_THREADS) {
+    int src;
+    if (i < nW) {
+      const int k = i / (cout * HID), rem = i - k * cout * HID;   // rem = c*32 + j
+      src = (k * CP) * HID + rem;
+    } else {
+      src = (K + 1) * CP * HID + (i - nW);
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int w8 = 0; w8 < BWD_ROLE_WARPS; ++w8) s += red[(size_t)w8 * PER * HID + src];
+    if (i < nW) part[i] = s;
+    else part[a.bias_offset + (i - nW)] = s;
+  }
+}
+
+__global__ void k_reduce_partials(const float* __restrict__ partials, int64_t stride, int num, int64_t count, float* grad, int accumulate) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+    float s = 0.0f;
+    int c = 0;
+    for (; c + 4 <= num; c += 4) {
+      float v0 = partials[(size_t)c * stride + i], v1 = partials[(size_t)(c + 1) * stride + i];
+      float v2 = partials[(size_t)(c + 2) * stride + i], v3 = partials[(size_t)(c + 3) * stride + i];
+      s += v0;
+      s += v1;
+      s += v2;
+      s += v3;
+    }
+    for (; c < num; ++c) s += partials[(size_t)c * stride + i];
+    grad[i] = accumulate ? grad[i] + s : s;
+  }
+}
+
+size_t topo_bytes(const dss2_graph_t* g) {
+  const int TR = round4(g->max_tile_nodes);
+  return (size_t)(TR + 4) * 4 + (size_t)TR * 4 + (size_t)(g->max_tile_nnz + 4) * 4;
+}
+size_t fwd_smem(const dss2_graph_t* g, int K) { return (size_t)(K + 1) * round4(g->max_tile_nodes) * HID * 4 + topo_bytes(g); }
+size_t bwd_smem(const dss2_graph_t* g, int K, int CP) {
+  size_t tile = (size_t)(K + 4) * round4(g->max_tile_nodes) * HID * 4 + topo_bytes(g);
+  size_t red = (size_t)BWD_ROLE_WARPS * ((K + 1) * CP + 1) * HID * 4;
+  return tile > red ? tile : red;
+}
+
+template <typename Kern>
+int set_smem(Kern kern, size_t bytes) {
+  if (bytes > 48 * 1024) DSS2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return 0;
+}
+
+template <int K>
+int launch_fwd(const TagFwdArgs& a, int grid, size_t smem, cudaStream_t s) {
+  if (set_smem(k_tag_fwd<K>, smem)) return -2;
+  k_tag_fwd<K><<<grid, FWD_THREADS, smem, s>>>(a);
+  DSS2_LAUNCH_CHECK();
+  return 0;
+}
+template <int K, int CP>
+int launch_bwd(const TagBwdArgs& a, int grid, size_t smem, cudaStream_t s) {
+  if (set_smem(k_tag_bwd<K, CP>, smem)) return -2;
+  k_tag_bwd<K, CP><<<grid, BWD_THREADS, smem, s>>>(a);
+  DSS2_LAUNCH_CHECK();
+  return 0;
+}
+template <int K>
+int launch_bwd_cp(const TagBwdArgs& a, int cp, int grid, size_t smem, cudaStream_t s) {
+  if (cp == 2) return launch_bwd<K, 2>(a, grid, smem, s);
+  if (cp == 8) return launch_bwd<K, 8>(a, grid, smem, s);
+  return launch_bwd<K, 32>(a, grid, smem, s);
+}
+inline int pad_cout(int cout) { return cout <= 2 ? 2 : (cout <= 8 ? 8 : 32); }
+
+}  // namespace
+
+extern "C" int dss2_num_partials(void) { return dss2_sm_count(); }
+
+extern "C" int dss2_tag_fwd(const dss2_graph_t* g, const float* x, const float* w, const float* bias, int cout, int K, int act,
+                            float p_drop, int drop_mode, const uint64_t* rng_state, uint32_t layer_uid, const uint8_t* mask,
+                            const float* res, int64_t res_stride, float* y, uint32_t* act_bits, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DSS2_CHECK_ARG(g && x && w && bias && y, "dss2_tag_fwd: null argument");
+  DSS2_CHECK_ARG(cout >= 1 && cout <= HID, "dss2_tag_fwd: cout %d outside 1..%d", cout, HID);
+  DSS2_CHECK_ARG(K >= 1 && K <= MAXK, "dss2_tag_fwd: K %d outside 1..%d", K, MAXK);
+  DSS2_CHECK_ARG(p_drop >= 0.0f && p_drop < 1.0f, "dss2_tag_fwd: dropout p %f outside [0,1)", p_drop);
+  DSS2_CHECK_ARG(!(act && drop_mode == 1) || rng_state, "dss2_tag_fwd: philox dropout needs rng_state");
+  DSS2_CHECK_ARG(!(act && drop_mode == 2) || mask, "dss2_tag_fwd: mask dropout needs a mask");
+  DSS2_CHECK_ARG(g->num_tiles > 0, "dss2_tag_fwd: graph has no shared-memory tiling (a graph exceeds %d nodes); "
+                 "the large-graph layer path is not built yet", DSS2_TILE_CAP);
+  if (g->num_nodes == 0) return 0;
+  TagFwdArgs a;
+  a.g = *g;
+  a.x = x;
+  a.w = w;
+  a.bias = bias;
+  a.cout = cout;
+  a.act = act;
+  if (p_drop == 0.0f) drop_mode = 0;
+  a.drop_mode = act ? drop_mode : 0;
+  a.scale = 1.0f / (float)(1.0 - (double)p_drop);
+  double thr = (1.0 - (double)p_drop) * 4294967296.0;
+  a.keep_thr = thr >= 4294967295.0 ? 0xffffffffu : (uint32_t)thr;
+  a.rng = rng_state;
+  a.layer_uid = layer_uid;
+  a.mask = mask;
+  a.res = res;
+  a.res_stride = res_stride;
+  a.y = y;
+  a.bits = act_bits;
+  size_t smem = fwd_smem(g, K);
+  DSS2_CHECK_ARG(smem <= 227 * 1024, "dss2_tag_fwd: tile needs %zu bytes of shared memory", smem);
+  int grid = max(1, min(g->num_tiles, 2 * dss2_sm_count()));
+  switch (K) {
+    case 1: return launch_fwd<1>(a, grid, smem, stream);
+    case 2: return launch_fwd<2>(a, grid, smem, stream);
+    default: return launch_fwd<3>(a, grid, smem, stream);
+  }
+}
+
+extern "C" int dss2_tag_bwd(const dss2_graph_t* g, const float* x, const float* w, int cout, int K, int act, float p_drop,
+                            const uint32_t* act_bits, const float* grad_y, float* grad_x, float* partials, int64_t partial_stride,
+                            int64_t bias_offset, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DSS2_CHECK_ARG(g && x && w && grad_y && grad_x && partials, "dss2_tag_bwd: null argument");
+  DSS2_CHECK_ARG(cout >= 1 && cout <= HID, "dss2_tag_bwd: cout %d outside 1..%d", cout, HID);
+  DSS2_CHECK_ARG(K >= 1 && K <= MAXK, "dss2_tag_bwd: K %d outside 1..%d", K, MAXK);
+  DSS2_CHECK_ARG(!act || act_bits, "dss2_tag_bwd: activation layers need act_bits from the forward");
+  DSS2_CHECK_ARG(partial_stride >= (int64_t)(K + 1) * cout * HID + cout, "dss2_tag_bwd: partial_stride too small");
+  DSS2_CHECK_ARG(bias_offset >= (int64_t)(K + 1) * cout * HID || bias_offset <= -(int64_t)cout, "dss2_tag_bwd: bias_offset overlaps grad_W");
+  DSS2_CHECK_ARG(g->num_tiles > 0, "dss2_tag_bwd: graph has no shared-memory tiling; large-graph path not built yet");
+  TagBwdArgs a;
+  a.g = *g;
+  a.x = x;
+  a.w = w;
+  a.cout = cout;
+  a.act = act;
+  a.scale = 1.0f / (float)(1.0 - (double)p_drop);
+  a.bits = act_bits;
+  a.gy = grad_y;
+  a.gx = grad_x;
+  a.partials = partials;
+  a.partial_stride = partial_stride;
+  a.bias_offset = bias_offset;
+  const int cp = pad_cout(cout);
+  size_t smem = bwd_smem(g, K, cp);
+  DSS2_CHECK_ARG(smem <= 227 * 1024, "dss2_tag_bwd: tile needs %zu bytes of shared memory", smem);
+  // exactly dss2_num_partials() CTAs so that every partial row is written (idle CTAs write zeros)
+  int grid = dss2_sm_count();
+  switch (K) {
+    case 1: return launch_bwd_cp<1>(a, cp, grid, smem, stream);
+    case 2: return launch_bwd_cp<2>(a, cp, grid, smem, stream);
+    default: return launch_bwd_cp<3>(a, cp, grid, smem, stream);
+  }
+}
+
+extern "C" int dss2_reduce_partials(const float* partials, int64_t partial_stride, int num_partials, int64_t count, float* grad,
+                                    int accumulate, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DSS2_CHECK_ARG(partials && grad && num_partials >= 1 && count >= 0, "dss2_reduce_partials: bad argument");
+  if (count == 0) return 0;
+  int grid = (int)max((int64_t)1, min((int64_t)148 * 8, (count + 127) / 128));
+  k_reduce_partials<<<grid, 128, 0, stream>>>(partials, partial_stride, num_partials, count, grad, accumulate);
+  DSS2_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,340 @@
+// (c) Fused branch-flow + WLS loss, forward and backward.  Replaces data.py:328-390, 393-459 + autograd.
+//
+// One shared-memory tile = a few whole scenarios (graphs never share a branch), so bus voltages,
+// branch flows, bus injections and every adjoint live in shared memory; HBM sees x, edge_attr,
+// edge_index and the model output once per pass, and writes grad_out once.  No per-branch tensor ever
+// reaches HBM and no floating-point atomics are used: bus sums walk the CSR by destination in the
+// order of PyG's scatter.  The three soft-constraint penalties are squares of batch means
+// (data.py:453-455), so the gradient needs batch-global sums first: pass 1 (k_wls<false>) produces
+// them (last-CTA-done reduction in fixed order, fp64), pass 2 (k_wls<true>) recomputes the cheap flow
+// arithmetic and applies the adjoints.
+//
+// Compiled with -fmad=false: see wls_math.cuh.
+#include "common.cuh"
+#include "wls_math.cuh"
+
+namespace {
+
+constexpr int WLS_THREADS = 256;
+enum { S_JN = 0, S_JE, S_V, S_TH, S_LOAD, S_N = 5 };
+
+struct WlsArgs {
+  dss2_graph_t g;
+  const float* x;
+  int64_t xs;
+  const float* ea;
+  int64_t eas;
+  float* out;
+  const float* stats;
+  WlsCoefs k;
+  const float* vminmax;
+  int mask_inplace;
+  float* loss;
+  const float* grad_loss;
+  float* grad_out;
+  double* partial;     // [grid][S_N]
+  unsigned* counter;
+  double* sums;        // [S_N]
+};
+
+__device__ __forceinline__ WlsBranchIn load_branch(const float* row, const float* s_v, const float* s_th, int i, int j) {
+  WlsBranchIn in;
+  in.vi = s_v[i];
+  in.vj = s_v[j];
+  in.thi = s_th[i];
+  in.thj = s_th[j];
+  in.G = row[6];
+  in.B = row[7];
+  in.Gs = row[8];
+  in.Bs = row[9];
+  in.shift = row[11];
+  in.rating = row[12];
+  return in;
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(WLS_THREADS) k_wls(WlsArgs a) {
+  extern __shared__ float smem[];
+  const dss2_graph_t& g = a.g;
+  const int T = g.max_tile_nodes, E = g.max_tile_edges;
+  float* s_v = smem;
+  float* s_th = s_v + T;
+  float* s_ap = s_th + T;
+  float* s_aq = s_ap + T;
+  float* s_gv = s_aq + T;
+  float* s_gth = s_gv + T;
+  float* s_pf = s_gth + T;   // bwd: reused as cvi
+  float* s_qf = s_pf + E;    // bwd: reused as cvj
+  float* s_pt = s_qf + E;    // bwd: reused as cdel
+  float* s_qt = s_pt + E;
+  __shared__ WlsStats st;
+  __shared__ double s_red[S_N][WLS_THREADS / 32];
+  __shared__ bool s_last;
+
+  const int tid = threadIdx.x;
+  if (tid < 28) ((float*)&st)[tid] = a.stats[tid];
+  const WlsGrid grid = wls_grid(a.vminmax[0], a.vminmax[1]);
+  const WlsCoefs k = a.k;
+  const int64_t Nt = g.num_nodes, Et = g.num_edges;
+  const int64_t* ei = g.edge_index;
+  __syncthreads();
+
+  double acc[S_N] = {0, 0, 0, 0, 0};
+  float cN = 0.f, cE = 0.f, mv = 0.f, mth = 0.f, ml = 0.f;
+  if (BWD) {
+    float gl = a.grad_loss ? a.grad_loss[0] : 1.0f;
+    cN = gl / (float)Nt;
+    cE = gl / (float)Et;
+    mv = (float)(a.sums[S_V] / (double)Nt);
+    mth = (float)(a.sums[S_TH] / (double)Et);
+    ml = (float)(a.sums[S_LOAD] / (double)Et);
+  }
+
+  for (int t = blockIdx.x; t < g.num_tiles; t += gridDim.x) {
+    const TileRange r = tile_range(g, t);
+    const int nT = r.n1 - r.n0, nE = (int)(r.e1 - r.e0);
+    // pass A: bus state
+    for (int ln = tid; ln < nT; ln += WLS_THREADS) {
+      int64_t n = r.n0 + ln;
+      float o0 = a.out[2 * n], o1 = a.out[2 * n + 1];
+      float slack = a.x[n * a.xs + 9];
+      float th = o1 * (1.0f - slack);
+      s_v[ln] = o0 * st.xs[0] + st.xm[0];
+      s_th[ln] = th;
+      if (!BWD && a.mask_inplace) a.out[2 * n + 1] = th;
+    }
+    __syncthreads();
+    // pass B: branch flows
+    for (int le = tid; le < nE; le += WLS_THREADS) {
+      int64_t e = r.e0 + le;
+      int i = (int)(ei[e] - r.n0), j = (int)(ei[Et + e] - r.n0);
+      const float* row = a.ea + e * a.eas;
+      WlsBranchIn in = load_branch(row, s_v, s_th, i, j);
+      WlsBranch b;
+      wls_branch_forward(in, grid, b);
+      s_pf[le] = b.pf;
+      s_qf[le] = b.qf;
+      s_pt[le] = b.pt;
+      s_qt[le] = b.qt;
+      if (!BWD) {
+        float eZ0 = wls_unnorm(row[0], st.es[0], st.em[0]), eR0 = wls_unnorm(row[1], st.es[1], st.em[1]);
+        float eZ1 = wls_unnorm(row[2], st.es[2], st.em[2]), eR1 = wls_unnorm(row[3], st.es[3], st.em[3]);
+        acc[S_JE] += (double)wls_branch_residual(eZ0, eR0, eZ1, eR1, b.pf, b.qf, k);
+        acc[S_TH] += (double)fmaxf(fabsf(b.delta) - 0.5f, 0.0f);
+        acc[S_LOAD] += (double)fmaxf(b.loading - 1.5f, 0.0f);
+      }
+    }
+    __syncthreads();
+    // pass C: bus injections (data.py:428-429) in PyG scatter order, residuals / adjoints
+    for (int ln = tid; ln < nT; ln += WLS_THREADS) {
+      int64_t n = r.n0 + ln;
+      float sp_to = 0.f, sq_to = 0.f, sp_fr = 0.f, sq_fr = 0.f;
+      for (int z = g.rowptr[n]; z < g.rowptr[n + 1]; ++z) {
+        uint32_t id = g.eid[z];
+        int le = (int)((int64_t)(id & 0x7fffffffu) - r.e0);
+        if (id >> 31) {
+          sp_fr += s_pf[le];
+          sq_fr += s_qf[le];
+        } else {
+          sp_to += s_pt[le];
+          sq_to += s_qt[le];
+        }
+      }
+      float p_bus = -sp_to - sp_fr, q_bus = -sq_to - sq_fr;
+      WlsBus b;
+      wls_bus_load(a.x + n * a.xs, a.out[2 * n], a.out[2 * n + 1], st, b);
+      b.v = s_v[ln];
+      b.th = s_th[ln];
+      if (!BWD) {
+        acc[S_JN] += (double)wls_bus_residual(b, p_bus, q_bus, k);
+        acc[S_V] += (double)wls_bus_vband(b);
+      } else {
+        s_ap[ln] = -2.0f * k.lam_p * b.R[2] * (b.Z[2] - p_bus) * cN;
+        s_aq[ln] = -2.0f * k.lam_p * b.R[3] * (b.Z[3] - q_bus) * cN;
+        float band = (b.v - 1.1f > 0.0f ? 1.0f : 0.0f) - (0.9f - b.v > 0.0f ? 1.0f : 0.0f);
+        s_gv[ln] = -2.0f * k.lam_v * b.R[0] * (b.Z[0] - b.v) * cN + 2.0f * k.lam_reg * mv * cN * band;
+        s_gth[ln] = -2.0f * k.lam_v * b.R[1] * (b.Z[1] - b.th) * cN;
+      }
+    }
+    if (BWD) {
+      __syncthreads();
+      // pass D: branch adjoints -> (dV_i, dV_j, d delta) per branch, kept in shared memory
+      for (int le = tid; le < nE; le += WLS_THREADS) {
+        int64_t e = r.e0 + le;
+        int i = (int)(ei[e] - r.n0), j = (int)(ei[Et + e] - r.n0);
+        const float* row = a.ea + e * a.eas;
+        WlsBranchIn in = load_branch(row, s_v, s_th, i, j);
+        WlsBranch b;
+        wls_branch_forward(in, grid, b);
+        float eZ0 = wls_unnorm(row[0], st.es[0], st.em[0]), eR0 = wls_unnorm(row[1], st.es[1], st.em[1]);
+        float eZ1 = wls_unnorm(row[2], st.es[2], st.em[2]), eR1 = wls_unnorm(row[3], st.es[3], st.em[3]);
+        float dpf = -s_ap[i] - 2.0f * k.lam_pf * eR0 * (eZ0 - b.pf) * cE;
+        float dqf = -s_aq[i] - 2.0f * k.lam_pf * eR1 * (eZ1 - b.qf) * cE;
+        float dpt = -s_ap[j], dqt = -s_aq[j];
+        float ad = fabsf(b.delta);
+        float ddelta = (ad - 0.5f > 0.0f) ? 2.0f * k.lam_reg * mth * cE * (b.delta > 0.0f ? 1.0f : -1.0f) : 0.0f;
+        float dload = (b.loading - 1.5f > 0.0f) ? 2.0f * k.lam_reg * ml * cE : 0.0f;
+        float dvi, dvj, ddel;
+        wls_branch_backward(in, grid, b, dpf, dqf, dpt, dqt, ddelta, dload, dvi, dvj, ddel);
+        s_pf[le] = dvi;
+        s_qf[le] = dvj;
+        s_pt[le] = ddel;
+      }
+      __syncthreads();
+      // pass E: gather branch adjoints into the bus, chain through un-normalisation and slack mask
+      for (int ln = tid; ln < nT; ln += WLS_THREADS) {
+        int64_t n = r.n0 + ln;
+        float gv = s_gv[ln], gth = s_gth[ln];
+        for (int z = g.rowptr[n]; z < g.rowptr[n + 1]; ++z) {
+          uint32_t id = g.eid[z];
+          int le = (int)((int64_t)(id & 0x7fffffffu) - r.e0);
+          if (id >> 31) {  // this bus is the branch's "from" end
+            gv += s_pf[le];
+            gth += s_pt[le];
+          } else {
+            gv += s_qf[le];
+            gth -= s_pt[le];
+          }
+        }
+        float slack = a.x[n * a.xs + 9];
+        a.grad_out[2 * n] = gv * st.xs[0];
+        a.grad_out[2 * n + 1] = gth * (1.0f - slack);
+      }
+    }
+    __syncthreads();
+  }
+
+  if (!BWD) {
+    // block reduction (fp64) -> per-CTA partial -> the last CTA to finish adds the partials in CTA order
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int q = 0; q < S_N; ++q) {
+      double v = warp_sum(acc[q]);
+      if (lane == 0) s_red[q][warp] = v;
+    }
+    __syncthreads();
+    if (tid < S_N) {
+      double v = 0;
+      for (int w = 0; w < WLS_THREADS / 32; ++w) v += s_red[tid][w];
+      a.partial[(size_t)blockIdx.x * S_N + tid] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(a.counter, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      if (tid < S_N) {
+        double v = 0;
+        for (unsigned c = 0; c < gridDim.x; ++c) v += ((volatile double*)a.partial)[(size_t)c * S_N + tid];
+        a.sums[tid] = v;
+        s_red[tid][0] = v;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        double n = (double)Nt, e = (double)Et;
+        double jv = s_red[S_V][0] / n, jt = s_red[S_TH][0] / e, jl = s_red[S_LOAD][0] / e;
+        double lam = (double)k.lam_reg;
+        a.loss[0] = (float)(s_red[S_JN][0] / n + s_red[S_JE][0] / e + lam * jv * jv + lam * jt * jt + lam * jl * jl);
+        *a.counter = 0;  // ready for the next launch / graph replay
+      }
+    }
+  }
+}
+
+// get_pflow as a plain per-branch kernel (evaluation path, dss2_run.py:193-194): outputs are API tensors.
+__global__ void k_pflow(const int64_t* __restrict__ ei, int64_t Et, const float* __restrict__ y, int64_t ys,
+                        const float* __restrict__ ep, int64_t eps_, const float* __restrict__ vminmax, float* out8) {
+  const WlsGrid grid = wls_grid(vminmax[0], vminmax[1]);
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < Et; e += (int64_t)gridDim.x * blockDim.x) {
+    int64_t i = ei[e], j = ei[Et + e];
+    const float* row = ep + e * eps_;
+    WlsBranchIn in;
+    in.vi = y[i * ys];
+    in.thi = y[i * ys + 1];
+    in.vj = y[j * ys];
+    in.thj = y[j * ys + 1];
+    in.G = row[0];
+    in.B = row[1];
+    in.Gs = row[2];
+    in.Bs = row[3];
+    in.shift = row[5];
+    in.rating = row[6];
+    WlsBranch b;
+    wls_branch_forward(in, grid, b);
+    out8[e] = b.ll;
+    out8[Et + e] = b.lt;
+    out8[2 * Et + e] = b.pf;
+    out8[3 * Et + e] = b.qf;
+    out8[4 * Et + e] = b.pt;
+    out8[5 * Et + e] = b.qt;
+    out8[6 * Et + e] = b.i_f;
+    out8[7 * Et + e] = b.i_t;
+  }
+}
+
+int wls_grid_size(const dss2_graph_t* g) { return max(1, min(g->num_tiles, dss2_sm_count() * 8)); }
+size_t wls_smem(const dss2_graph_t* g) { return (size_t)(6 * g->max_tile_nodes + 4 * g->max_tile_edges) * sizeof(float); }
+
+}  // namespace
+
+extern "C" size_t dss2_wls_workspace_bytes(const dss2_graph_t* g) {
+  (void)g;
+  return (size_t)(dss2_sm_count() * 8) * S_N * sizeof(double) + 256 + 16 * sizeof(double);
+}
+
+extern "C" int dss2_wls_fwd_bwd(const dss2_graph_t* g, const float* x, int64_t x_stride, const float* edge_attr,
+                                int64_t ea_stride, float* output, const float* stats, float lam_v, float lam_p, float lam_pf,
+                                float lam_reg, const float* vminmax, int mask_inplace, float* loss, const float* grad_loss,
+                                float* grad_out, void* ws, size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DSS2_CHECK_ARG(g && x && edge_attr && output && stats && vminmax && loss && ws, "dss2_wls_fwd_bwd: null argument");
+  DSS2_CHECK_ARG(g->undirected == 1, "dss2_wls_fwd_bwd: needs a graph built from the one-way edge list with undirect=1");
+  DSS2_CHECK_ARG(g->num_tiles > 0, "dss2_wls_fwd_bwd: graph has no shared-memory tiling (a scenario exceeds %d buses); "
+                 "the large-graph loss path is not built yet", DSS2_TILE_CAP);
+  DSS2_CHECK_ARG(ws_bytes >= dss2_wls_workspace_bytes(g), "dss2_wls_fwd_bwd: workspace too small");
+  DSS2_CHECK_ARG(x_stride >= 11 && ea_stride >= 13, "dss2_wls_fwd_bwd: x needs 11 columns and edge_attr 13");
+  WlsArgs a;
+  a.g = *g;
+  a.x = x;
+  a.xs = x_stride;
+  a.ea = edge_attr;
+  a.eas = ea_stride;
+  a.out = output;
+  a.stats = stats;
+  a.k = WlsCoefs{lam_v, lam_p, lam_pf, lam_reg};
+  a.vminmax = vminmax;
+  a.mask_inplace = mask_inplace;
+  a.loss = loss;
+  a.grad_loss = grad_loss;
+  a.grad_out = grad_out;
+  int grid = wls_grid_size(g);
+  char* base = (char*)ws;
+  a.counter = (unsigned*)base;                       // zero-initialised by the caller once; self-resetting
+  a.sums = (double*)(base + 256);
+  a.partial = a.sums + 16;
+  size_t smem = wls_smem(g);
+  DSS2_CHECK_ARG(smem <= 200 * 1024, "dss2_wls_fwd_bwd: tile needs %zu bytes of shared memory", smem);
+  if (smem > 48 * 1024) {
+    DSS2_CUDA(cudaFuncSetAttribute(k_wls<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DSS2_CUDA(cudaFuncSetAttribute(k_wls<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  k_wls<false><<<grid, WLS_THREADS, smem, stream>>>(a);
+  DSS2_LAUNCH_CHECK();
+  if (grad_out) {
+    k_wls<true><<<grid, WLS_THREADS, smem, stream>>>(a);
+    DSS2_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+extern "C" int dss2_pflow(const int64_t* edge_index, int64_t Et, const float* y, int64_t y_stride, const float* edge_param,
+                          int64_t ep_stride, const float* vminmax, float* out8, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DSS2_CHECK_ARG(edge_index && y && edge_param && vminmax && out8, "dss2_pflow: null argument");
+  if (Et == 0) return 0;
+  int grid = (int)max((int64_t)1, min((int64_t)148 * 8, (Et + 255) / 256));
+  k_pflow<<<grid, 256, 0, stream>>>(edge_index, Et, y, y_stride, edge_param, ep_stride, vminmax, out8);
+  DSS2_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,147 @@
+"""Drop-in for the reference's `networks` module (reference networks.py), B200-native underneath.
+
+Same class names, constructor keywords, `forward(x, edge_index, edge_attr)` signature and parameter names /
+shapes (so reference checkpoints load both ways, dss2_run.py:95-101,240-247) - but a forward / backward is a
+sequence of hand-written sm_100a kernels (libdss2_b200.so): one fused kernel per EdgeAggregation and per
+TAGConv(+Dropout+ReLU) layer over a batch structure that is built once per batch instead of once per layer.
+
+Hot path (BASELINE.json north_star): EdgeAggregation, MPN, SkipMPN, PFN, SkipPFN.
+Reference behaviours kept on purpose: dropout is active in eval() too
+(networks.py:268 builds a fresh nn.Dropout inside forward); the degree norm computed in
+EdgeAggregation.forward (networks.py:196-200) never reaches `message` and is not applied; all sub-nets of a
+PFN receive the same raw edge attributes; reversed edges negate attribute columns 0 and 2 (networks.py:252).
+There is no CPU fallback: without a CUDA device or the built library, forward raises.
+The other models of the reference module (gnn_dsse, GINE_DSSE, GAT_DSSE: GCN2/FA/GINE/GATv2 stacks) are the
+next row of the scope table; their names exist so that `from networks import ...` works.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from dss2 import ops
+from dss2.ops import PFNSpec
+
+
+class TAGConv(nn.Module):
+    """Parameter container with PyG TAGConv's names: lins.{0..K}.weight [out, in] (no bias), bias [out]
+    (zero-initialised).  Inside MPN the fused layer kernel consumes the parameters directly; called on its
+    own it evaluates sum_k (A_hat^k x) W_k^T + b on the un-directed version of `edge_index`."""
+
+    def __init__(self, in_channels, out_channels, K=3, bias=True):
+        super().__init__()
+        self.in_channels, self.out_channels, self.K = in_channels, out_channels, K
+        self.lins = nn.ModuleList([nn.Linear(in_channels, out_channels, bias=False) for _ in range(K + 1)])
+        self.bias = nn.Parameter(torch.zeros(out_channels))
+
+    def forward(self, x, edge_index):
+        return ops.tag_conv(x, edge_index, [lin.weight for lin in self.lins], self.bias)
+
+
+class EdgeAggregation(nn.Module):
+    """networks.py:159-209: out[i] = sum over edges (j -> i) of MLP([x_i | x_j | a_ji]), aggr='add'.
+    Takes the ONE-WAY edge list of the reference's data and applies MPN's un-directing (reversed edges with
+    attribute columns 0 and 2 negated) inside the kernel."""
+
+    def __init__(self, dim_featn, dim_feate, dim_hid, dim_out):
+        super().__init__()
+        self.dim_featn, self.dim_feate, self.dim_out = dim_featn, dim_feate, dim_out
+        self.edge_aggr = nn.Sequential(nn.Linear(dim_featn * 2 + dim_feate, dim_hid), nn.ReLU(), nn.Linear(dim_hid, dim_out))
+
+    def forward(self, x, edge_index, edge_attr):
+        return ops.edge_aggregation(x, edge_index, edge_attr, self.edge_aggr[0].weight, self.edge_aggr[0].bias,
+                                    self.edge_aggr[2].weight, self.edge_aggr[2].bias)
+
+
+class _Stack(nn.Module):
+    """Shared machinery of MPN / SkipMPN / PFN / SkipPFN: spec, flat parameter pack, fused launch sequence."""
+    _dss2_masks = None        # test hook: [sub-net][layer] 0/1 masks consumed by the next forward (exact torch parity)
+    _dss2_rng_state = None    # optional device int64 {seed, step} for the in-kernel Philox dropout
+
+    def _spec(self):
+        raise NotImplementedError
+
+    def _machinery(self):
+        m = self.__dict__.get("_dss2_machinery")
+        if m is None:
+            spec = self._spec()
+            m = (ops.PFNRunner(spec), ops.ParamPack(spec))
+            self.__dict__["_dss2_machinery"] = m
+        return m
+
+    def forward(self, x, edge_index, edge_attr):
+        runner, pack = self._machinery()
+        masks, self._dss2_masks = self._dss2_masks, None
+        return ops.pfn_apply(runner, pack, dict(self.named_parameters()), x, edge_index, edge_attr, masks=masks,
+                             rng_state=self._dss2_rng_state)
+
+
+def _build_mpn(self, dim_featn, dim_feate, dim_out, dim_hid, n_gnn_layers, K, dropout_rate):
+    self.dim_featn, self.dim_feate, self.dim_out, self.dim_hid = dim_featn, dim_feate, dim_out, dim_hid
+    self.n_gnn_layers, self.K, self.dropout_rate = n_gnn_layers, K, dropout_rate
+    self.edge_aggr = EdgeAggregation(dim_featn, dim_feate, dim_hid, dim_hid)
+    self.convs = nn.ModuleList()
+    for l in range(n_gnn_layers):
+        self.convs.append(TAGConv(dim_hid, dim_out if l == n_gnn_layers - 1 else dim_hid, K=K))
+
+
+class MPN(_Stack):
+    """networks.py:212-273: EdgeAggregation, then n_gnn_layers TAGConv(K) with Dropout+ReLU between them."""
+    _skip = False
+
+    def __init__(self, dim_featn, dim_feate, dim_out, dim_hid, n_gnn_layers, K, dropout_rate):
+        super().__init__()
+        _build_mpn(self, dim_featn, dim_feate, dim_out, dim_hid, n_gnn_layers, K, dropout_rate)
+
+    def _spec(self):
+        return PFNSpec(fn=self.dim_featn, fe=self.dim_feate, dim_out=self.dim_out, n_layers=self.n_gnn_layers, K=self.K, L=1,
+                       p_drop=float(self.dropout_rate), skip=(self._skip,), prefix_fmt="", hid=self.dim_hid)
+
+
+class SkipMPN(MPN):
+    """networks.py:275-338: MPN whose input is added to its output (needs dim_out == dim_featn)."""
+    _skip = True
+
+
+def _build_pfn(self, sub_cls, dim_featn, dim_feate, dim_out, dim_hid, n_gnn_layers, K, dropout_rate, L):
+    self.dim_featn, self.dim_feate, self.dim_out, self.dim_hid = dim_featn, dim_feate, dim_out, dim_hid
+    self.n_gnn_layers, self.K, self.dropout_rate, self.L = n_gnn_layers, K, dropout_rate, L
+    self.mpns = nn.ModuleList()
+    for l in range(L):
+        if l == L - 1:   # the last sub-net is always a plain MPN onto dim_out (networks.py:355,380)
+            self.mpns.append(MPN(dim_featn, dim_feate, dim_out, dim_hid, n_gnn_layers, K, dropout_rate))
+        else:
+            self.mpns.append(sub_cls(dim_featn, dim_feate, dim_featn, dim_hid, n_gnn_layers, K, dropout_rate))
+
+
+class PFN(_Stack):
+    """networks.py:340-363: L stacked MPNs, every one fed the same raw edge attributes."""
+    _sub = MPN
+
+    def __init__(self, dim_featn, dim_feate, dim_out, dim_hid, n_gnn_layers, K, dropout_rate, L):
+        super().__init__()
+        _build_pfn(self, self._sub, dim_featn, dim_feate, dim_out, dim_hid, n_gnn_layers, K, dropout_rate, L)
+
+    def _spec(self):
+        skip = tuple((self._sub is SkipMPN) and s < self.L - 1 for s in range(self.L))
+        return PFNSpec(fn=self.dim_featn, fe=self.dim_feate, dim_out=self.dim_out, n_layers=self.n_gnn_layers, K=self.K, L=self.L,
+                       p_drop=float(self.dropout_rate), skip=skip, prefix_fmt="mpns.{s}.", hid=self.dim_hid)
+
+
+class SkipPFN(PFN):
+    """networks.py:365-388: PFN whose first L-1 sub-nets are SkipMPNs."""
+    _sub = SkipMPN
+
+
+def _next_row(name, where):
+    class _Pending(nn.Module):
+        def __init__(self, *args, **kwargs):
+            raise NotImplementedError(f"{name} ({where}) is outside the B200 hot path built so far (SURVEY.md 8f-1: "
+                                      "GATv2 / GINE / GCN2 / FA layers are the next row); use MPN / SkipMPN / PFN / SkipPFN")
+    _Pending.__name__ = name
+    return _Pending
+
+
+gnn_dsse = _next_row("gnn_dsse", "networks.py:11-69")
+GINE_DSSE = _next_row("GINE_DSSE", "networks.py:71-111")
+GAT_DSSE = _next_row("GAT_DSSE", "networks.py:113-156")

@@ -1,0 +1,186 @@
+/*
+ * dss2_b200.h - C ABI of the B200-native DSS2 hot path (libdss2_b200.so).
+ *
+ * The reference (TU-Delft-AI-Energy-Lab/Deep-Statistical-Solver-for-Distribution-System-State-Estimation)
+ * is pure Python and has no FFI; its hot path is reached through the Python surface that
+ * dss2_run.py touches.  This header is the boundary the Python host mirror
+ * (`networks.py`, `data.py` in the package directory) binds with ctypes; every entry point names the
+ * reference code it replaces.  See INTEGRATION.md for the reference-side binding.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer owned by the caller unless it is marked
+ *     "host"; kernels never allocate or free; all work is enqueued on `stream` (a cudaStream_t passed
+ *     as void*) and is safe to capture in a CUDA graph unless stated otherwise;
+ *   - return value 0 = success, negative = error (dss2_last_error() gives the thread-local message);
+ *   - fp32 features, int64 indices at the API (as PyG), int32 kernel-private CSR;
+ *   - hidden width is 32 (one warp lane per hidden feature); other widths are rejected loudly.
+ */
+#ifndef DSS2_B200_H
+#define DSS2_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSS2_HID 32            /* hidden width the layer kernels are specialised for */
+#define DSS2_TILE_CAP 256      /* max nodes of a shared-memory tile (whole graphs) */
+
+const char* dss2_last_error(void);
+int dss2_version(void);
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches claim) */
+int64_t dss2_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Graph structure of one batch (kernel-private; built once per batch topology).
+ * Replaces: MPN.is_directed / undirect_graph (networks.py:236-258, redone in each of the 5 sub-nets),
+ *           PyG gcn_norm inside every TAGConv.forward (recomputed 40x per forward),
+ *           PyG degree (networks.py:197, dead).
+ * The doubled graph (forward edges then reversed edges, networks.py:245-248) is stored as CSR by
+ * destination; within a row entries are ordered by doubled edge id, i.e. the order in which PyG's
+ * sequential scatter_add_ visits them.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct dss2_graph {
+  int64_t num_nodes;        /* Nt */
+  int64_t num_edges;        /* Et one-way edges as given at the API */
+  int64_t nnz;              /* CSR entries: 2*Et if reversed edges were appended, else Et */
+  int32_t num_graphs;       /* B segments (graphs) */
+  int32_t undirected;       /* 1: reversed edges appended (input was one-way) */
+  int32_t graphs_per_tile;  /* G; 0 = no shared-memory tiling possible (graph larger than a tile) */
+  int32_t num_tiles;
+  int32_t max_tile_nodes;
+  int32_t max_tile_nnz;
+  int32_t max_tile_edges;   /* one-way edges */
+  int32_t reserved;
+  const int64_t* edge_index;/* [2,Et] caller's tensor */
+  const int64_t* ptr;       /* [B+1] node offset of every graph (caller's or builder's) */
+  int64_t* eptr;            /* [B+1] one-way edge offset of every graph */
+  int32_t* rowptr;          /* [Nt+1] */
+  int32_t* col;             /* [nnz] source node */
+  uint32_t* eid;            /* [nnz] original edge id | reversed << 31 */
+  float* dis;               /* [Nt] in-degree^-1/2 on the doubled graph, 0 where degree is 0 */
+} dss2_graph_t;
+
+/* Bytes of device workspace dss2_graph_build needs for (Nt, Et, B). */
+size_t dss2_graph_workspace_bytes(int64_t num_nodes, int64_t num_edges, int32_t num_graphs);
+
+/* Builds the structure into `g` (host struct).  `ws` must stay alive as long as `g` is used: all
+ * arrays of `g` except edge_index/ptr point into it.  undirect: 1 append reversed edges, 0 do not,
+ * -1 decide like MPN.is_directed (networks.py:236-238).  tile_cap: max nodes per tile (<= DSS2_TILE_CAP).
+ * Synchronises `stream` (reads sizes back); not graph-capturable. */
+int dss2_graph_build(dss2_graph_t* g, const int64_t* edge_index, int64_t num_edges, int64_t num_nodes,
+                     const int64_t* ptr, int32_t num_graphs, int undirect, int tile_cap,
+                     void* ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (a) Batch packer.  Replaces PyG DataLoader -> Batch.from_data_list (dss2_run.py:18,68-69,134).
+ * Scenario-major store: scenario s owns node rows node_off[s]..node_off[s+1] of x_all[.,11] / y_all[.,2]
+ * and edge rows edge_off[s]..edge_off[s+1] of ea_all[.,13] / columns of ei_all[2,E_all] (local ids).
+ * Output is PyG's disjoint-union batch, bit-exact: x, edge_index (+node offset), edge_attr, y,
+ * batch, ptr, plus eptr (edge offsets) and vminmax = {min, max} of vn_kv = x[:,8] (data.py:334-336).
+ * Any of y/batch may be NULL.  ptr/eptr ([B+1]) are produced by an on-device scan of the selected sizes.
+ * ---------------------------------------------------------------------------------------------- */
+int dss2_pack_batch(const float* x_all, const float* ea_all, const float* y_all, const int64_t* ei_all,
+                    int64_t ei_all_cols, const int64_t* node_off, const int64_t* edge_off,
+                    const int64_t* scen_ids, int32_t num_graphs,
+                    float* x, int64_t* edge_index, int64_t edge_index_cols, float* edge_attr, float* y,
+                    int64_t* batch, int64_t* ptr, int64_t* eptr, float* vminmax, void* stream);
+
+/* vminmax[0] = min, [1] = max of column `col` of x (row stride `stride` floats). */
+int dss2_col_minmax(const float* x, int64_t stride, int col, int64_t n, float* vminmax, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (b1) EdgeAggregation.  Replaces networks.py:159-209 (+ its autograd):
+ *   out[n] = sum_{e: dst(e)=n} ( W2 relu(W1 [x_n | x_src(e) | a_e] + b1) + b2 )   on the doubled graph,
+ * reversed edges using a_e with columns 0 and 2 negated (networks.py:252).
+ * x: [Nt, fn] with row stride x_stride floats (fn <= 8); edge_attr: [Et, fe] row stride ea_stride (fe <= 8).
+ * w1 [32, 2*fn+fe], b1 [32], w2 [32,32], b2 [32] row-major as torch Linear.  out [Nt,32].
+ * ---------------------------------------------------------------------------------------------- */
+int dss2_edgeagg_fwd(const dss2_graph_t* g, const float* x, int64_t x_stride, int fn,
+                     const float* edge_attr, int64_t ea_stride, int fe,
+                     const float* w1, const float* b1, const float* w2, const float* b2,
+                     float* out, void* stream);
+
+/* Backward.  grad_out [Nt,32].  grad_x [Nt,fn] (dense, stride fn) may be NULL; if `skip_grad`
+ * (row stride skip_stride) is given it is added into grad_x (the SkipMPN residual path, networks.py:336).
+ * Weight gradients are written as per-CTA partial sums: partials[cta][edgeagg_param_count] with
+ * layout (w1, b1, w2, b2); *num_partials CTAs were used.  Reduce with dss2_reduce_partials. */
+int dss2_edgeagg_bwd(const dss2_graph_t* g, const float* x, int64_t x_stride, int fn,
+                     const float* edge_attr, int64_t ea_stride, int fe,
+                     const float* w1, const float* b1, const float* w2, const float* b2,
+                     const float* grad_out, const float* skip_grad, int64_t skip_stride,
+                     float* grad_x, float* partials, int64_t partial_stride, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (b2) TAGConv(32 -> cout, K) [+ Dropout + ReLU] [+ residual].  Replaces PyG TAGConv.forward with
+ * gcn_norm(add_self_loops=False) and the inline Dropout/ReLU of networks.py:268-269 (+ autograd):
+ *   out = sum_{k=0..K} (A_hat^k x) W_k^T + b ;  y = relu(dropout_p(out)) if act else out ; y += res
+ * w: K+1 matrices [cout,32] contiguous ([K+1,cout,32]); bias [cout]; y [Nt,cout].
+ * Dropout: mode 0 none; 1 counter-based Philox keyed by (seed, layer_uid, node, feature) with the
+ * seed/step pair read from DEVICE memory rng_state[2] (graph-replay safe); 2 caller-supplied mask
+ * (uint8 [Nt,32], 1 = keep) for exact parity with a recorded torch mask.
+ * act_bits [Nt] (out, may be NULL when !act): bit c = y[n][c] > 0, all the backward needs.
+ * res: optional [Nt,cout] residual input with row stride res_stride (SkipMPN, networks.py:336).
+ * ---------------------------------------------------------------------------------------------- */
+int dss2_tag_fwd(const dss2_graph_t* g, const float* x, const float* w, const float* bias, int cout, int K,
+                 int act, float p_drop, int drop_mode, const uint64_t* rng_state, uint32_t layer_uid,
+                 const uint8_t* mask, const float* res, int64_t res_stride,
+                 float* y, uint32_t* act_bits, void* stream);
+
+/* Backward with recomputation of A_hat^k x from the saved layer input x.
+ * grad_y [Nt,cout]; act_bits as written by the forward (NULL when !act); grad_x [Nt,32].
+ * Per-CTA partial sums: row c of the partials buffer starts at partials + c*partial_stride; grad_W
+ * ([K+1,cout,32]) is written at offset 0 of the row and grad_bias ([cout]) at offset `bias_offset`
+ * (signed: in the flat parameter layout the bias precedes the weights). */
+int dss2_tag_bwd(const dss2_graph_t* g, const float* x, const float* w, int cout, int K,
+                 int act, float p_drop, const uint32_t* act_bits, const float* grad_y,
+                 float* grad_x, float* partials, int64_t partial_stride, int64_t bias_offset,
+                 void* stream);
+
+/* Number of CTAs (= rows of a partials buffer) the layer backward kernels use on this device. */
+int dss2_num_partials(void);
+
+/* grad[i] = sum_{c < num_partials} partials[c*partial_stride + i], i < count; deterministic order.
+ * accumulate != 0 adds into grad instead of overwriting. */
+int dss2_reduce_partials(const float* partials, int64_t partial_stride, int num_partials, int64_t count,
+                         float* grad, int accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (c) Branch flows + WLS loss, fused forward and backward.  Replaces data.py:328-390 (get_pflow) and
+ * data.py:393-459 (gsp_wls_edge) + autograd.  x [Nt,11] (stride x_stride), edge_attr [Et,13]
+ * (stride ea_stride), output [Nt,2] (dense).  stats = {x_mean[8], x_std[8], edge_mean[6], edge_std[6]}
+ * (device, 28 floats).  coefs = {lam_v, lam_p, lam_pf, lam_reg} by value.  vminmax: device {V_lv, V_hv}.
+ * mask_inplace != 0 reproduces the reference's in-place zeroing of slack theta in `output`
+ * (data.py:412-413).  loss: device scalar.  grad_out [Nt,2] may be NULL (forward only);
+ * grad_loss: device scalar upstream gradient or NULL (= 1).  ws: dss2_wls_workspace_bytes(g).
+ * ---------------------------------------------------------------------------------------------- */
+size_t dss2_wls_workspace_bytes(const dss2_graph_t* g);
+int dss2_wls_fwd_bwd(const dss2_graph_t* g, const float* x, int64_t x_stride, const float* edge_attr,
+                     int64_t ea_stride, float* output, const float* stats, float lam_v, float lam_p,
+                     float lam_pf, float lam_reg, const float* vminmax, int mask_inplace,
+                     float* loss, const float* grad_loss, float* grad_out, void* ws, size_t ws_bytes,
+                     void* stream);
+
+/* get_pflow (data.py:328-390, phase_shift=True): y [Nt,2] (V pu, theta rad, row stride y_stride);
+ * node vn_kv via vminmax; edge_param columns (G,B,Gs,Bs,closed,shift,imax) = edge_attr[:,6:13] given
+ * as pointer to column 0 of the parameter block with row stride ep_stride.
+ * out8 [8,Et]: loading_lines, loading_trafo, P_from, Q_from, P_to, Q_to, I_from, I_to. */
+int dss2_pflow(const int64_t* edge_index, int64_t num_edges, const float* y, int64_t y_stride,
+               const float* edge_param, int64_t ep_stride, const float* vminmax, float* out8, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Adjacent: flat-buffer Adamax (torch.optim.Adamax defaults, dss2_run.py:91-92,143).
+ * step_state: device {uint64 seed, uint64 step}; the kernel uses step+1 for bias correction and, when
+ * bump != 0, increments it (so a captured graph advances its own clock).  grad_scale multiplies the
+ * gradient first (1/world_size after a sum all-reduce).
+ * ---------------------------------------------------------------------------------------------- */
+int dss2_adamax_step(float* param, const float* grad, float* exp_avg, float* exp_inf, int64_t count,
+                     float lr, float beta1, float beta2, float eps, float grad_scale,
+                     uint64_t* step_state, int bump, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSS2_B200_H */
