@@ -1,0 +1,148 @@
+"""Device-resident training step: packer -> SkipPFN forward -> fused WLS loss fwd+bwd -> backward -> (all-reduce) ->
+flat Adamax, launched straight through the C ABI over static buffers and replayed as ONE CUDA graph.
+
+This is the throughput path (what `bench.py` measures); it issues exactly the same kernels as the drop-in
+`networks` / `data` modules but skips autograd and per-step allocation.  It mirrors one iteration of the
+reference's training loop (dss2_run.py:134-144): `optimizer.zero_grad(); out = model(...); loss = gsp_wls_edge(...);
+loss.backward(); optimizer.step()` with Adamax(lr=3e-3) (dss2_run.py:91-92) and the always-on dropout
+(networks.py:268) drawn in-kernel from a counter-based generator keyed by (seed, step).
+
+Data parallelism: every rank owns a shard of the scenarios and packs its own batch; the only
+exchange is one sum all-reduce of the flat fp32 gradient (~484 KB for the default SkipPFN) per step, followed by
+the identical Adamax update on every rank with the gradient scaled by 1/world_size ("mean of per-shard
+gradients", i.e. DDP semantics - the loss's squared batch means make sharding inexact w.r.t. one large batch).
+"""
+import torch
+
+from . import _lib
+from .batching import launch_pack
+from .graph import BatchGraph
+from .ops import ParamPack, PFNRunner, PFNSpec
+
+
+def default_spec(p_drop=0.3, L=5, n_layers=8, K=2, dim_out=2, fn=8, fe=6):
+    """SkipPFN(8, 6, 2, 32, 8, 2, 0.3, 5): dss2_run.py:72-82,88."""
+    return PFNSpec(fn=fn, fe=fe, dim_out=dim_out, n_layers=n_layers, K=K, L=L, p_drop=p_drop,
+                   skip=tuple(s < L - 1 for s in range(L)), prefix_fmt="mpns.{s}.")
+
+
+class GraphedTrainer:
+    def __init__(self, store, batch_graphs, spec=None, reg_coefs=None, lr=3e-3, seed=0, init_state_dict=None,
+                 process_group=None, world_size=1, use_cuda_graph=True):
+        self.lib = _lib.load()
+        self.spec = spec or default_spec()
+        self.store = store
+        self.B = int(batch_graphs)
+        self.dev = store.x.device
+        if self.dev.type != "cuda":
+            raise _lib.Dss2Error("GraphedTrainer needs a CUDA-resident ScenarioStore")
+        if store.x.size(0) != store.num_scenarios * store.max_nodes:
+            raise _lib.Dss2Error("GraphedTrainer needs a uniform-topology store (static batch shapes)")
+        self.pg, self.world = process_group, int(world_size)
+        self.lr = float(lr)
+        rc = reg_coefs or {"lam_v": 1e-4, "lam_p": 1e-8, "lam_pf": 1e-6, "lam_reg": 1e2}   # dss2_run.py:104-112
+        self.coefs = (float(rc["lam_v"]), float(rc["lam_p"]), float(rc["lam_pf"]), float(rc["lam_reg"]))
+        self.runner = PFNRunner(self.spec)
+        n, e = store.max_nodes, store.max_edges
+        self.nt, self.et = self.B * n, self.B * e
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        i64 = dict(dtype=torch.long, device=self.dev)
+        with torch.cuda.device(self.dev):
+            # parameters: same init distribution as the reference modules, one flat buffer
+            self.flat = torch.zeros(self.runner.flat_size, **f32)
+            self._init_params(seed, init_state_dict)
+            self.flat_grad = torch.zeros_like(self.flat)
+            self.exp_avg = torch.zeros_like(self.flat)
+            self.exp_inf = torch.zeros_like(self.flat)
+            self.step_state = torch.tensor([seed * 2654435761 % (2 ** 62) + 12345, 0], **i64)   # {philox seed, step}
+            # static batch buffers
+            self.ids = torch.zeros(self.B, **i64)
+            self.batch = {
+                "x": torch.empty(self.nt, 11, **f32), "edge_attr": torch.empty(self.et, 13, **f32), "y": torch.empty(self.nt, 2, **f32),
+                "edge_index": torch.empty(2, self.et, **i64), "batch": torch.empty(self.nt, **i64),
+                "ptr": torch.empty(self.B + 1, **i64), "eptr": torch.empty(self.B + 1, **i64), "vminmax": torch.empty(2, **f32),
+            }
+            self.stats = torch.cat([store.x_mean, store.x_std, store.edge_mean, store.edge_std]).to(**f32).contiguous()
+            self.loss = torch.zeros((), **f32)
+            self.grad_out = torch.empty(self.nt, 2, **f32)
+            self.bufs = self.runner.alloc(self.nt, self.dev, need_grad=True)
+            # structure: one eager pack, then build once (uniform topology: identical for every batch)
+            self.ids.copy_(torch.arange(self.B, device=self.dev) % store.num_scenarios)
+            launch_pack(store, self.ids, self.batch, self.nt, self.et)
+            self.graph = BatchGraph(self.batch["edge_index"], self.nt, ptr=self.batch["ptr"], undirect=1)
+            if self.graph.c.num_tiles == 0:
+                raise _lib.Dss2Error("GraphedTrainer: graphs exceed the shared-memory tile; large-graph path not built yet")
+            self.wls_ws = self.graph.wls_workspace()
+        self.cuda_graph = None
+        self.launches_per_step = None
+        self.use_cuda_graph = use_cuda_graph
+
+    # ---- parameters ----
+    def _init_params(self, seed, sd):
+        table = self.runner.table
+        if sd is None:
+            import math
+            g = torch.Generator().manual_seed(seed)
+            sd = {}
+            for name, shape in self.spec.param_names():
+                if "convs." in name and name.endswith(".bias"):
+                    sd[name] = torch.zeros(shape)                      # PyG TAGConv bias: zeros
+                else:
+                    bound = 1.0 / math.sqrt(shape[-1] if len(shape) > 1 else self._fan_in(name))
+                    sd[name] = (torch.rand(shape, generator=g) * 2 - 1) * bound
+        for name, (off, n) in table.items():
+            self.flat[off:off + n].copy_(sd[name].reshape(-1).to(self.flat))
+
+    def _fan_in(self, name):
+        return 2 * self.spec.fn + self.spec.fe if "edge_aggr.0" in name else self.spec.hid
+
+    def state_dict(self):
+        return {name: self.flat[off:off + n].view(shape).clone()
+                for (name, shape), (off, n) in zip(self.spec.param_names(), self.runner.table.values())}
+
+    # ---- one step ----
+    def _enqueue(self, with_optimizer=True):
+        lib, st = self.lib, _lib.stream()
+        b = self.batch
+        launch_pack(self.store, self.ids, b, self.nt, self.et)
+        out = self.runner.forward(self.graph, b["x"], 11, b["edge_attr"], 13, self.flat, self.bufs,
+                                  drop_mode=1 if self.spec.p_drop > 0 else 0, rng_state=self.step_state)
+        _lib.check(lib.dss2_wls_fwd_bwd(self.graph.ref, _lib.ptr(b["x"]), 11, _lib.ptr(b["edge_attr"]), 13, _lib.ptr(out),
+                                        _lib.ptr(self.stats), *self.coefs, _lib.ptr(b["vminmax"]), 1, _lib.ptr(self.loss), None,
+                                        _lib.ptr(self.grad_out), _lib.ptr(self.wls_ws), self.wls_ws.numel(), st), "dss2_wls_fwd_bwd")
+        self.runner.backward(self.graph, b["x"], 11, b["edge_attr"], 13, self.flat, self.bufs, self.grad_out, self.flat_grad)
+        if self.world > 1:
+            torch.distributed.all_reduce(self.flat_grad, group=self.pg)
+        if with_optimizer:
+            _lib.check(lib.dss2_adamax_step(_lib.ptr(self.flat), _lib.ptr(self.flat_grad), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_inf),
+                                            self.flat.numel(), self.lr, 0.9, 0.999, 1e-8, 1.0 / self.world, _lib.ptr(self.step_state), 1,
+                                            st), "dss2_adamax_step")
+
+    def capture(self):
+        """Warm up eagerly (also counts the launches of one step), then capture the step into a CUDA graph."""
+        with torch.cuda.device(self.dev):
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    before = _lib.launch_count()
+                    self._enqueue()
+                    self.launches_per_step = _lib.launch_count() - before + (1 if self.world > 1 else 0)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            if self.use_cuda_graph:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._enqueue()
+                self.cuda_graph = g
+        return self
+
+    def step(self, ids=None):
+        """Enqueue one training step for scenario ids (device or pinned-host int64 [B]); returns the device loss scalar."""
+        if ids is not None:
+            self.ids.copy_(ids, non_blocking=True)
+        if self.cuda_graph is not None:
+            self.cuda_graph.replay()
+        else:
+            self._enqueue()
+        return self.loss
