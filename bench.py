@@ -178,11 +178,13 @@ def main():
     sampler = ClockSampler(local)
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.profiler.start()      # lets `ncu --profile-from-start off` see exactly the timed steps
     ev0.record()
     for i in range(K):
         trainer.step(ids_host[W + i])
     ev1.record()
     barrier()
+    torch.cuda.profiler.stop()
     sampler.stop_flag.set()
     sampler.join()
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))

@@ -104,6 +104,14 @@ __global__ void k_sort_rows(int64_t Nt, const int* __restrict__ rowptr, int* col
   }
 }
 
+// gcn_norm edge weight per CSR entry: dis[src] * 1 * dis[dst]
+__global__ void k_entry_weights(int64_t Nt, const int* __restrict__ rowptr, const int* __restrict__ col, const float* __restrict__ dis, float* w) {
+  for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < Nt; n += (int64_t)gridDim.x * blockDim.x) {
+    const float dn = dis[n];
+    for (int z = rowptr[n]; z < rowptr[n + 1]; ++z) w[z] = dis[col[z]] * dn;
+  }
+}
+
 __device__ __forceinline__ int graph_of(const int64_t* ptr, int B, int64_t node) {
   int lo = 0, hi = B;  // largest g with ptr[g] <= node
   while (hi - lo > 1) {
@@ -150,7 +158,7 @@ __global__ void k_tile_stats(dss2_graph_t g, int* stats) {
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct WsLayout {
-  size_t rowptr, col, eid, dis, eptr, cursor, stats, cub, total, cub_bytes;
+  size_t rowptr, col, eid, dis, w, eptr, cursor, stats, cub, total, cub_bytes;
 };
 WsLayout ws_layout(int64_t Nt, int64_t Et, int32_t B) {
   WsLayout L;
@@ -160,6 +168,7 @@ WsLayout ws_layout(int64_t Nt, int64_t Et, int32_t B) {
   L.col = take((size_t)(2 * Et + 1) * 4);
   L.eid = take((size_t)(2 * Et + 1) * 4);
   L.dis = take((size_t)(Nt + 1) * 4);
+  L.w = take((size_t)(2 * Et + 1) * 4);
   L.eptr = take((size_t)(B + 1) * 8);
   L.cursor = take((size_t)(Nt + 1) * 4);
   L.stats = take(ST_COUNT * 4);
@@ -196,6 +205,7 @@ extern "C" int dss2_graph_build(dss2_graph_t* g, const int64_t* edge_index, int6
   g->col = (int32_t*)(base + L.col);
   g->eid = (uint32_t*)(base + L.eid);
   g->dis = (float*)(base + L.dis);
+  g->w = (float*)(base + L.w);
   g->eptr = (int64_t*)(base + L.eptr);
   int* cursor = (int*)(base + L.cursor);
   int* stats = (int*)(base + L.stats);
@@ -233,6 +243,8 @@ extern "C" int dss2_graph_build(dss2_graph_t* g, const int64_t* edge_index, int6
   }
   if (Nt > 0) {
     k_sort_rows<<<grid_for(Nt, T), T, 0, stream>>>(Nt, g->rowptr, g->col, g->eid, g->dis);
+    DSS2_LAUNCH_CHECK();
+    k_entry_weights<<<grid_for(Nt, T), T, 0, stream>>>(Nt, g->rowptr, g->col, g->dis, g->w);
     DSS2_LAUNCH_CHECK();
   }
   k_eptr<<<(B + 1 + T - 1) / T, T, 0, stream>>>(edge_index, Et, ptr, B, g->eptr, stats);

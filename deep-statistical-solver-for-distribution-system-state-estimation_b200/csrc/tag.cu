@@ -62,30 +62,48 @@ struct TagBwdArgs {
 
 __host__ __device__ inline int round4(int v) { return (v + 3) & ~3; }
 
-// Tile topology in shared memory: local rowptr, local source ids, degree norm.
+// Tile topology in shared memory: local rowptr and one packed (source row offset, gcn weight) pair per CSR entry.
 struct TileTopo {
   int* rowptr;
-  int* col;
-  float* dis;
+  int2* cw;     // .x = local source node * 32 (float offset of its feature row), .y = weight bits
 };
 
 __device__ __forceinline__ void load_topo(const dss2_graph_t& g, const TileRange& r, TileTopo s, int tid, int nthreads) {
   const int nT = r.n1 - r.n0, nZ = r.z1 - r.z0;
   for (int i = tid; i <= nT; i += nthreads) s.rowptr[i] = g.rowptr[r.n0 + i] - r.z0;
-  for (int i = tid; i < nT; i += nthreads) s.dis[i] = g.dis[r.n0 + i];
-  for (int i = tid; i < nZ; i += nthreads) s.col[i] = g.col[r.z0 + i] - r.n0;
+  for (int i = tid; i < nZ; i += nthreads) s.cw[i] = make_int2((g.col[r.z0 + i] - r.n0) * HID, __float_as_int(g.w[r.z0 + i]));
 }
 
-// dst[row][lane] = sum_{e in row} dis[row] * dis[src] * src_feat[src][lane]   (one warp per row)
-__device__ __forceinline__ float hop_row(const TileTopo& s, const float* __restrict__ src, int row, int lane) {
-  const int beg = s.rowptr[row], end = s.rowptr[row + 1];
-  const float dn = s.dis[row];
-  float acc = 0.0f;
-  for (int z = beg; z < end; ++z) {
-    const int c = s.col[z];
-    acc = fmaf(dn * s.dis[c], src[c * HID + lane], acc);
+// acc[i] += sum_{e in row r0+i} w_e * src[col_e][lane] for R consecutive rows handled by one warp.
+// Degrees are tiny (<= 3 on the feeders): the first 4 entries of each row are fully unrolled and predicated on the
+// warp-uniform degree, so the R rows' loads interleave and no divergence bookkeeping is emitted; longer rows fall through
+// to a plain loop.  Entries are visited in CSR order = PyG scatter order.
+template <int R>
+__device__ __forceinline__ void hop_rows(const TileTopo& s, const float* __restrict__ src, int r0, int nT, int lane, float (&acc)[R]) {
+  int beg[R], deg[R];
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+    const bool valid = r0 + i < nT;
+    beg[i] = valid ? s.rowptr[r0 + i] : 0;
+    deg[i] = valid ? s.rowptr[r0 + i + 1] - beg[i] : 0;
   }
-  return acc;
+#pragma unroll
+  for (int d = 0; d < 4; ++d) {
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      if (d < deg[i]) {
+        const int2 cw = s.cw[beg[i] + d];
+        acc[i] = fmaf(__int_as_float(cw.y), src[cw.x + lane], acc[i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+    for (int z = beg[i] + 4; z < beg[i] + deg[i]; ++z) {
+      const int2 cw = s.cw[z];
+      acc[i] = fmaf(__int_as_float(cw.y), src[cw.x + lane], acc[i]);
+    }
+  }
 }
 
 // contiguous rows global -> shared, 16 bytes per thread per step
@@ -105,9 +123,8 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) k_tag_fwd(TagFwdArgs a) {
   const int TR = round4(g.max_tile_nodes);
   float* X = smem;                                   // [K+1][TR][32]
   TileTopo topo;
-  topo.rowptr = reinterpret_cast<int*>(X + (K + 1) * TR * HID);
-  topo.dis = reinterpret_cast<float*>(topo.rowptr + TR + 4);
-  topo.col = reinterpret_cast<int*>(topo.dis + TR);
+  topo.cw = reinterpret_cast<int2*>(X + (K + 1) * TR * HID);
+  topo.rowptr = reinterpret_cast<int*>(topo.cw + g.max_tile_nnz + 2);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int cout = a.cout;
@@ -142,34 +159,44 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) k_tag_fwd(TagFwdArgs a) {
     load_topo(g, r, topo, tid, FWD_THREADS);
     __syncthreads();
     // hops 1..K-1 need every row of the previous hop -> block barrier; the last hop is fused below
+    const int nblk = (nT + 3) >> 2;
 #pragma unroll
     for (int k = 1; k < K; ++k) {
-      for (int row = warp; row < nT; row += FWD_WARPS) X[(k * TR + row) * HID + lane] = hop_row(topo, X + (k - 1) * TR * HID, row, lane);
+      for (int blk = warp; blk < nblk; blk += FWD_WARPS) {
+        float h[4] = {0.f, 0.f, 0.f, 0.f};
+        hop_rows<4>(topo, X + (k - 1) * TR * HID, blk * 4, nT, lane, h);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) X[(k * TR + blk * 4 + i) * HID + lane] = h[i];
+      }
       __syncthreads();
     }
-    const int nblk = (nT + 3) >> 2;
     for (int blk = warp; blk < nblk; blk += FWD_WARPS) {
       const int r0 = blk * 4;
-      if (K >= 1) {
+      {
+        float h[4] = {0.f, 0.f, 0.f, 0.f};
+        hop_rows<4>(topo, X + (K - 1) * TR * HID, r0, nT, lane, h);
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (r0 + i < nT) X[(K * TR + r0 + i) * HID + lane] = hop_row(topo, X + (K - 1) * TR * HID, r0 + i, lane);
+        for (int i = 0; i < 4; ++i) X[(K * TR + r0 + i) * HID + lane] = h[i];
         __syncwarp();
       }
+      // 4 rows x (K+1)*32 inputs: the 4 accumulators are independent, FFMAs are issued row-interleaved
       float acc[4] = {bias, bias, bias, bias};
 #pragma unroll
       for (int k = 0; k <= K; ++k) {
         const float* Xk = X + (k * TR + r0) * HID;
 #pragma unroll
         for (int j4 = 0; j4 < HID / 4; ++j4) {
+          float4 v[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 v = *reinterpret_cast<const float4*>(Xk + i * HID + 4 * j4);   // warp-broadcast
-            acc[i] = fmaf(v.x, W[k][4 * j4 + 0], acc[i]);
-            acc[i] = fmaf(v.y, W[k][4 * j4 + 1], acc[i]);
-            acc[i] = fmaf(v.z, W[k][4 * j4 + 2], acc[i]);
-            acc[i] = fmaf(v.w, W[k][4 * j4 + 3], acc[i]);
-          }
+          for (int i = 0; i < 4; ++i) v[i] = *reinterpret_cast<const float4*>(Xk + i * HID + 4 * j4);   // warp-broadcast
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[i] = fmaf(v[i].x, W[k][4 * j4 + 0], acc[i]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[i] = fmaf(v[i].y, W[k][4 * j4 + 1], acc[i]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[i] = fmaf(v[i].z, W[k][4 * j4 + 2], acc[i]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[i] = fmaf(v[i].w, W[k][4 * j4 + 3], acc[i]);
         }
       }
       // epilogue: dropout -> ReLU -> sign word -> residual -> store (a row is one 128-byte line)
@@ -218,9 +245,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_tag_bwd(TagBwdArgs a) {
   float* G = X + (K + 1) * TR * HID;        // [TR][32]       grad wrt pre-activation output, zero padded
   float* H = G + TR * HID;                  // [2][TR][32]    Horner ping-pong (X role)
   TileTopo topo;
-  topo.rowptr = reinterpret_cast<int*>(H + 2 * TR * HID);
-  topo.dis = reinterpret_cast<float*>(topo.rowptr + TR + 4);
-  topo.col = reinterpret_cast<int*>(topo.dis + TR);
+  topo.cw = reinterpret_cast<int2*>(H + 2 * TR * HID);
+  topo.rowptr = reinterpret_cast<int*>(topo.cw + g.max_tile_nnz + 2);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool x_role = warp < BWD_ROLE_WARPS;
@@ -253,30 +279,46 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_tag_bwd(TagBwdArgs a) {
     }
     __syncthreads();
 
+    const int nblk = (nT + 3) >> 2;
     if (x_role) {
-      // grad_x = G W_0 + A (G W_1 + A (G W_2)): Horner over hops, all rows of a stage before the next
+      // grad_x = G W_0 + A (G W_1 + A (G W_2)): Horner over hops, all rows of a stage before the next; 4 rows per warp pass
 #pragma unroll
       for (int k = K; k >= 0; --k) {
         float* out = H + ((K - k) & 1) * TR * HID;
         const float* prev = H + ((K - k + 1) & 1) * TR * HID;
-        for (int row = rw; row < nT; row += BWD_ROLE_WARPS) {
-          float acc = (k < K) ? hop_row(topo, prev, row, lane) : 0.0f;
-          const float* grow = G + row * HID;
+        for (int blk = rw; blk < nblk; blk += BWD_ROLE_WARPS) {
+          const int r0 = blk * 4;
+          float acc[4] = {0.f, 0.f, 0.f, 0.f};
+          if (k < K) hop_rows<4>(topo, prev, r0, nT, lane, acc);
+          const float* grow = G + r0 * HID;
+          if (CP >= 4) {
 #pragma unroll
-          for (int c4 = 0; c4 < (CP + 3) / 4; ++c4) {
-            if (CP >= 4) {
-              const float4 v = *reinterpret_cast<const float4*>(grow + 4 * c4);
-              acc = fmaf(v.x, R[k][4 * c4 + 0], acc);
-              acc = fmaf(v.y, R[k][4 * c4 + 1], acc);
-              acc = fmaf(v.z, R[k][4 * c4 + 2], acc);
-              acc = fmaf(v.w, R[k][4 * c4 + 3], acc);
-            } else {
+            for (int c4 = 0; c4 < CP / 4; ++c4) {
+              float4 v[4];
 #pragma unroll
-              for (int c = 0; c < CP; ++c) acc = fmaf(grow[c], R[k][c], acc);
+              for (int i = 0; i < 4; ++i) v[i] = *reinterpret_cast<const float4*>(grow + i * HID + 4 * c4);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) acc[i] = fmaf(v[i].x, R[k][4 * c4 + 0], acc[i]);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) acc[i] = fmaf(v[i].y, R[k][4 * c4 + 1], acc[i]);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) acc[i] = fmaf(v[i].z, R[k][4 * c4 + 2], acc[i]);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) acc[i] = fmaf(v[i].w, R[k][4 * c4 + 3], acc[i]);
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < CP; ++c)
+#pragma unroll
+              for (int i = 0; i < 4; ++i) acc[i] = fmaf(grow[i * HID + c], R[k][c], acc[i]);
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (r0 + i < nT) {
+              if (k > 0) out[(r0 + i) * HID + lane] = acc[i];
+              else a.gx[((size_t)r.n0 + r0 + i) * HID + lane] = acc[i];
             }
           }
-          if (k > 0) out[row * HID + lane] = acc;
-          else a.gx[((size_t)r.n0 + row) * HID + lane] = acc;
         }
         if (k > 0) named_bar_sync(1, BWD_THREADS / 2);
       }
@@ -284,7 +326,12 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_tag_bwd(TagBwdArgs a) {
       // recompute A^k x, then rank-1 updates of grad_W held in registers
 #pragma unroll
       for (int k = 1; k <= K; ++k) {
-        for (int row = rw; row < nT; row += BWD_ROLE_WARPS) X[(k * TR + row) * HID + lane] = hop_row(topo, X + (k - 1) * TR * HID, row, lane);
+        for (int blk = rw; blk < nblk; blk += BWD_ROLE_WARPS) {
+          float h[4] = {0.f, 0.f, 0.f, 0.f};
+          hop_rows<4>(topo, X + (k - 1) * TR * HID, blk * 4, nT, lane, h);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) X[(k * TR + blk * 4 + i) * HID + lane] = h[i];
+        }
         named_bar_sync(2, BWD_THREADS / 2);
       }
       for (int row = rw; row < nT; row += BWD_ROLE_WARPS) {
@@ -293,9 +340,9 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_tag_bwd(TagBwdArgs a) {
         for (int k = 0; k <= K; ++k) xk[k] = X[(k * TR + row) * HID + lane];
         const float* grow = G + row * HID;
         gb += grow[lane];
+        if (CP >= 4) {
 #pragma unroll
-        for (int c4 = 0; c4 < (CP + 3) / 4; ++c4) {
-          if (CP >= 4) {
+          for (int c4 = 0; c4 < CP / 4; ++c4) {
             const float4 v = *reinterpret_cast<const float4*>(grow + 4 * c4);
 #pragma unroll
             for (int k = 0; k <= K; ++k) {
@@ -304,12 +351,12 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_tag_bwd(TagBwdArgs a) {
               R[k][4 * c4 + 2] = fmaf(v.z, xk[k], R[k][4 * c4 + 2]);
               R[k][4 * c4 + 3] = fmaf(v.w, xk[k], R[k][4 * c4 + 3]);
             }
-          } else {
-#pragma unroll
-            for (int c = 0; c < CP; ++c)
-#pragma unroll
-              for (int k = 0; k <= K; ++k) R[k][c] = fmaf(grow[c], xk[k], R[k][c]);
           }
+        } else {
+#pragma unroll
+          for (int c = 0; c < CP; ++c)
+#pragma unroll
+            for (int k = 0; k <= K; ++k) R[k][c] = fmaf(grow[c], xk[k], R[k][c]);
         }
       }
     }
@@ -365,7 +412,7 @@ __global__ void k_reduce_partials(const float* __restrict__ partials, int64_t st
 
 size_t topo_bytes(const dss2_graph_t* g) {
   const int TR = round4(g->max_tile_nodes);
-  return (size_t)(TR + 4) * 4 + (size_t)TR * 4 + (size_t)(g->max_tile_nnz + 4) * 4;
+  return (size_t)(g->max_tile_nnz + 2) * 8 + (size_t)(TR + 8) * 4;
 }
 size_t fwd_smem(const dss2_graph_t* g, int K) { return (size_t)(K + 1) * round4(g->max_tile_nodes) * HID * 4 + topo_bytes(g); }
 size_t bwd_smem(const dss2_graph_t* g, int K, int CP) {

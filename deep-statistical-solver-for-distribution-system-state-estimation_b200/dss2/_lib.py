@@ -23,7 +23,7 @@ class GraphStruct(Structure):
         ("num_graphs", c_int32), ("undirected", c_int32), ("graphs_per_tile", c_int32), ("num_tiles", c_int32),
         ("max_tile_nodes", c_int32), ("max_tile_nnz", c_int32), ("max_tile_edges", c_int32), ("reserved", c_int32),
         ("edge_index", c_void_p), ("ptr", c_void_p), ("eptr", c_void_p), ("rowptr", c_void_p), ("col", c_void_p),
-        ("eid", c_void_p), ("dis", c_void_p),
+        ("eid", c_void_p), ("dis", c_void_p), ("w", c_void_p),
     ]
 
 

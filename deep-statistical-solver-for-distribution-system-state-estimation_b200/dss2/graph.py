@@ -65,7 +65,7 @@ class BatchGraph:
         return {
             "rowptr": view(c.rowptr, c.num_nodes + 1, torch.int32), "col": view(c.col, c.nnz, torch.int32),
             "eid": view(c.eid, c.nnz, torch.int32), "dis": view(c.dis, c.num_nodes, torch.float32),
-            "eptr": view(c.eptr, c.num_graphs + 1, torch.int64),
+            "eptr": view(c.eptr, c.num_graphs + 1, torch.int64), "w": view(c.w, c.nnz, torch.float32),
         }
 
 

@@ -61,6 +61,7 @@ typedef struct dss2_graph {
   int32_t* col;             /* [nnz] source node */
   uint32_t* eid;            /* [nnz] original edge id | reversed << 31 */
   float* dis;               /* [Nt] in-degree^-1/2 on the doubled graph, 0 where degree is 0 */
+  float* w;                 /* [nnz] gcn_norm weight of the entry: dis[src] * dis[dst] */
 } dss2_graph_t;
 
 /* Bytes of device workspace dss2_graph_build needs for (Nt, Et, B). */
