@@ -1,0 +1,124 @@
+// tcgen05 / TMEM helpers for the 32x32 feature transforms (sm_100a).
+//
+// The transforms are evaluated as 3xTF32: x = x_hi + x_lo with x_hi = round-to-nearest TF32(x) and x_lo = x - x_hi (exact in
+// fp32, read by the tensor core as TF32), and x.w ~= x_hi.w_hi + x_lo.w_hi + x_hi.w_lo with fp32 accumulation in TMEM.  The
+// dropped terms are <= 2^-21 relative, i.e. fp32-equivalent accuracy (plain TF32 would be ~1e-3 and break 1e-5 parity).
+//
+// Operand tiles live in shared memory as [rows][32 fp32] = 128-byte rows, K-major, SWIZZLE_128B: 16-byte chunk c of row r
+// is stored at chunk (c ^ (r & 7)); an 8-row group is 1024 bytes (SBO), the tile base is 1024-byte aligned.  One
+// tcgen05.mma.kind::tf32 consumes K = 8 elements = 32 bytes, so a 32-wide row is 4 MMAs whose descriptors advance by 32 bytes.
+// Descriptor bit layouts follow cute/arch/mma_sm100_desc.hpp (CUTLASS, vendored in the image).
+#pragma once
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace tc {
+
+constexpr uint32_t ROW_BYTES = 128;          // 32 fp32
+constexpr uint32_t SBO_BYTES = 1024;         // 8 rows
+constexpr uint32_t KSTEP_BYTES = 32;         // 8 tf32
+
+// byte offset of element (row, col j) inside a swizzled [rows][32] tile
+__device__ __forceinline__ uint32_t swz_off(uint32_t row, uint32_t j) {
+  return row * ROW_BYTES + ((((j >> 2) ^ (row & 7u)) << 4) | ((j & 3u) << 2));
+}
+// same, as "row code" ^ (4*j): code = row*128 | (row&7)<<4
+__device__ __forceinline__ uint32_t row_code(uint32_t row) { return (row << 7) | ((row & 7u) << 4); }
+
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// shared-memory matrix descriptor: K-major, SWIZZLE_128B, version 1 (Blackwell)
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);            // start address, bits [0,14)
+  d |= (uint64_t)1u << 16;                                 // leading byte offset (unused for swizzled K-major) = 1
+  d |= (uint64_t)((SBO_BYTES >> 4) & 0x3FFFu) << 32;       // stride byte offset, bits [32,46)
+  d |= (uint64_t)1u << 46;                                 // version = 1
+  d |= (uint64_t)2u << 61;                                 // layout type = SWIZZLE_128B
+  return d;
+}
+
+// instruction descriptor: D fp32, A/B tf32, both K-major, M x N
+__host__ __device__ constexpr uint32_t idesc_tf32(uint32_t M, uint32_t N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {   // one full warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {     // the same warp
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] * B[smem]^T, issued by ONE thread
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier when all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// 32 consecutive fp32 columns of this thread's TMEM lane (lane = 32*(warp%4) + laneid)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// split 4 consecutive values and store hi / lo chunks (16 bytes each) at byte offset `off` of the two tiles
+__device__ __forceinline__ void split_store4(const float4 v, char* hi_tile, char* lo_tile, uint32_t off) {
+  float4 h, l;
+  h.x = tf32_rna(v.x);
+  h.y = tf32_rna(v.y);
+  h.z = tf32_rna(v.z);
+  h.w = tf32_rna(v.w);
+  l.x = v.x - h.x;
+  l.y = v.y - h.y;
+  l.z = v.z - h.z;
+  l.w = v.w - h.w;
+  *reinterpret_cast<float4*>(hi_tile + off) = h;
+  *reinterpret_cast<float4*>(lo_tile + off) = l;
+}
+
+// Issue the 3xTF32 product of one [128 x 32] activation block pair (hi, lo) with one [32 x 32] weight block pair into
+// 32 TMEM columns.  `first` = this is the first product of the accumulation chain.
+__device__ __forceinline__ void issue_block(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, uint32_t idesc,
+                                            bool first) {
+#pragma unroll
+  for (uint32_t kk = 0; kk < ROW_BYTES / KSTEP_BYTES; ++kk) {
+    const uint32_t o = kk * KSTEP_BYTES;
+    // small terms first
+    mma_tf32(d_tmem, smem_desc_sw128(a_lo + o), smem_desc_sw128(b_hi + o), idesc, (first && kk == 0) ? 0u : 1u);
+    mma_tf32(d_tmem, smem_desc_sw128(a_hi + o), smem_desc_sw128(b_lo + o), idesc, 1u);
+    mma_tf32(d_tmem, smem_desc_sw128(a_hi + o), smem_desc_sw128(b_hi + o), idesc, 1u);
+  }
+}
+
+}  // namespace tc

@@ -3,6 +3,7 @@
 modules.  All arithmetic happens in libdss2_b200.so; torch supplies device memory and streams.
 """
 import ctypes
+import os
 from dataclasses import dataclass
 
 import torch
@@ -11,6 +12,9 @@ from . import _lib
 from .graph import BatchGraph, graph_for
 
 HID = _lib.HID
+# which forward TAG-layer kernel the runner launches: "tc" = tcgen05 3xTF32 transforms (falls back to the CUDA-core kernel
+# where unsupported: K = 3 or a tile that does not fit), "ffma" = CUDA-core kernel.  Both are CUDA; there is no CPU path.
+TAG_FWD_IMPL = os.environ.get("DSS2_TAG_FWD", "ffma")
 
 
 def _align4(n):
@@ -113,6 +117,7 @@ class PFNRunner:
         masks: optional [L][n_layers-1] uint8 [Nt,32] tensors (drop_mode 2).  Returns bufs['outs'][-1]."""
         sp, lib, st = self.spec, self.lib, _lib.stream()
         g = graph.ref
+        use_tc = TAG_FWD_IMPL == "tc" and bool(lib.dss2_tag_fwd_tc_supported(g, sp.K))
         for s in range(sp.L):
             pre = sp.prefix_fmt.format(s=s)
             xin, xs = (x, x_stride) if s == 0 else (bufs["outs"][s - 1], sp.fn)
@@ -129,10 +134,11 @@ class PFNRunner:
                 if not last and drop_mode == 2:
                     mask = masks[s][l]
                 res, rs = (xin, xs) if (last and sp.skip[s]) else (None, 0)
-                _lib.check(lib.dss2_tag_fwd(g, _lib.ptr(bufs["acts"][s, l]), self._p(flat, pre + f"convs.{l}.lins.0.weight"),
-                                            self._p(flat, pre + f"convs.{l}.bias"), cout, sp.K, 0 if last else 1, sp.p_drop, mode,
-                                            _lib.ptr(rng_state), s * sp.n_layers + l, _lib.ptr(mask), _lib.ptr(res), rs,
-                                            _lib.ptr(y), None if last else _lib.ptr(bufs["bits"][s, l]), st), "dss2_tag_fwd")
+                fwd = lib.dss2_tag_fwd_tc if use_tc else lib.dss2_tag_fwd
+                _lib.check(fwd(g, _lib.ptr(bufs["acts"][s, l]), self._p(flat, pre + f"convs.{l}.lins.0.weight"),
+                               self._p(flat, pre + f"convs.{l}.bias"), cout, sp.K, 0 if last else 1, sp.p_drop, mode,
+                               _lib.ptr(rng_state), s * sp.n_layers + l, _lib.ptr(mask), _lib.ptr(res), rs,
+                               _lib.ptr(y), None if last else _lib.ptr(bufs["bits"][s, l]), st), "dss2_tag_fwd")
         return bufs["outs"][-1]
 
     # ---- backward ----

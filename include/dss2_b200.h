@@ -130,6 +130,18 @@ int dss2_tag_fwd(const dss2_graph_t* g, const float* x, const float* w, const fl
                  const uint8_t* mask, const float* res, int64_t res_stride,
                  float* y, uint32_t* act_bits, void* stream);
 
+/* Same contract as dss2_tag_fwd, with the (K+1) 32x32 transforms on the 5th-generation tensor cores (tcgen05.mma kind::tf32,
+ * 3xTF32 split = fp32-equivalent accuracy, accumulators in TMEM) and a thread-per-row epilogue.  The dropout stream differs
+ * from dss2_tag_fwd's (both are functions of (seed, step, layer, node) only).  dss2_tag_fwd_tc_supported() != 0 when the
+ * graph is tiled, K <= 2 and a tile fits the 227 KB of shared memory; otherwise use dss2_tag_fwd. */
+int dss2_tag_fwd_tc_supported(const dss2_graph_t* g, int K);
+int dss2_tag_fwd_tc(const dss2_graph_t* g, const float* x, const float* w, const float* bias, int cout, int K,
+                    int act, float p_drop, int drop_mode, const uint64_t* rng_state, uint32_t layer_uid,
+                    const uint8_t* mask, const float* res, int64_t res_stride,
+                    float* y, uint32_t* act_bits, void* stream);
+/* D[128,32] = A[128,32] * B[32,32]^T through the tensor-core operand / descriptor / TMEM path (bring-up and regression test). */
+int dss2_tc_selftest(const float* A, const float* B, float* D, void* stream);
+
 /* Backward with recomputation of A_hat^k x from the saved layer input x.
  * grad_y [Nt,cout]; act_bits as written by the forward (NULL when !act); grad_x [Nt,32].
  * Per-CTA partial sums: row c of the partials buffer starts at partials + c*partial_stride; grad_W
