@@ -43,9 +43,54 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 
-// instruction descriptor: D fp32, A/B tf32, both K-major, M x N
-__host__ __device__ constexpr uint32_t idesc_tf32(uint32_t M, uint32_t N) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+// MN-major TF32 operands must use the SWIZZLE_128B_BASE32B layout (CUTLASS: "for mn-major tf32 operands, SW128_32B is the only
+// available smem layout"): a [k rows][32 fp32] tile with 128-byte rows whose 32-byte chunk p of row r is stored at chunk
+// p ^ (r & 3) (Swizzle<2,5,2>); the atom is 4 rows = 512 bytes (SBO).  The contraction index is the tile row: one MMA (K = 8)
+// consumes 8 rows = 1024 bytes, so K-steps advance the start address by 1024; M/N extents beyond one 32-element row continue in
+// the next tile, `lbo_bytes` further on.
+__device__ __forceinline__ uint32_t swz32_off(uint32_t row, uint32_t j) {
+  return row * ROW_BYTES + ((((j >> 3) ^ (row & 3u)) << 5) | ((j & 7u) << 2));
+}
+__device__ __forceinline__ uint64_t smem_desc_mn32(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)(512u >> 4) << 32;
+  d |= (uint64_t)1u << 46;
+  d |= (uint64_t)1u << 61;   // layout type 1 = SWIZZLE_128B_BASE32B
+  return d;
+}
+
+// ---- no-swizzle ("interleaved") core-matrix tiles ----
+// A tile is a grid of 128-byte core matrices, each 8 rows x 4 fp32 (row i of the core at byte 16*i): element (r, c) of a tile with
+// Q column groups lives at (r/8)*(Q*128) + (c/4)*128 + (r%8)*16 + (c%4)*4.  The SAME bytes are a valid K-major operand
+// (rows = M/N index, columns = contraction) and a valid MN-major operand (columns = M/N index, rows = contraction): that is what
+// lets one set of tiles feed both GEMMs of the backward (grad_x = G W and grad_W = G^T X).
+__device__ __forceinline__ uint32_t core_off(uint32_t r, uint32_t c, uint32_t q_groups) {
+  return (r >> 3) * (q_groups * 128u) + (c >> 2) * 128u + ((r & 7u) << 4) + ((c & 3u) << 2);
+}
+// K-major use: LBO = distance between the two core matrices one MMA (K = 8) spans = 128 B; SBO = distance between 8-row groups
+__device__ __forceinline__ uint64_t smem_desc_core_k(uint32_t smem_addr, uint32_t row_group_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+  d |= (uint64_t)(128u >> 4) << 16;
+  d |= (uint64_t)((row_group_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1u << 46;
+  return d;   // layout type 0 = no swizzle
+}
+// MN-major use: SBO = distance between groups of 4 M/N elements = 128 B; LBO = distance between 8-row contraction blocks
+__device__ __forceinline__ uint64_t smem_desc_core_mn(uint32_t smem_addr, uint32_t row_group_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((row_group_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)(128u >> 4) << 32;
+  d |= (uint64_t)1u << 46;
+  return d;
+}
+
+// instruction descriptor: D fp32, A/B tf32, M x N; a_mn / b_mn = 1 selects an MN-major operand (0 = K-major)
+__host__ __device__ constexpr uint32_t idesc_tf32(uint32_t M, uint32_t N, uint32_t a_mn = 0, uint32_t b_mn = 0) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (a_mn << 15) | (b_mn << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {   // one full warp

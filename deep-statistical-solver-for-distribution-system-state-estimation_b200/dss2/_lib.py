@@ -43,6 +43,7 @@ _SIGNATURES = {
     "dss2_tag_fwd_tc_supported": (c_int, [_G, c_int]),
     "dss2_tag_fwd_tc": (c_int, [_G, _P, _P, _P, c_int, c_int, c_int, c_float, c_int, _P, c_uint32, _P, _P, c_int64, _P, _P, _P]),
     "dss2_tc_selftest": (c_int, [_P, _P, _P, _P]),
+    "dss2_tc_selftest_mn": (c_int, [_P, _P, _P, _P]),
     "dss2_tag_bwd": (c_int, [_G, _P, _P, c_int, c_int, c_int, c_float, _P, _P, _P, _P, c_int64, c_int64, _P]),
     "dss2_num_partials": (c_int, []),
     "dss2_reduce_partials": (c_int, [_P, c_int64, c_int, c_int64, _P, c_int, _P]),

@@ -141,6 +141,9 @@ int dss2_tag_fwd_tc(const dss2_graph_t* g, const float* x, const float* w, const
                     float* y, uint32_t* act_bits, void* stream);
 /* D[128,32] = A[128,32] * B[32,32]^T through the tensor-core operand / descriptor / TMEM path (bring-up and regression test). */
 int dss2_tc_selftest(const float* A, const float* B, float* D, void* stream);
+/* D[32*t + j, n] = sum_r A[t][r][j] * B[r][n], A = [4,64,32], B = [64,32]: MN-major TF32 operands (SWIZZLE_128B_BASE32B), the
+ * weight-gradient GEMM shape (contraction over node rows). */
+int dss2_tc_selftest_mn(const float* A, const float* B, float* D, void* stream);
 
 /* Backward with recomputation of A_hat^k x from the saved layer input x.
  * grad_y [Nt,cout]; act_bits as written by the forward (NULL when !act); grad_x [Nt,32].

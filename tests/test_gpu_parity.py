@@ -513,6 +513,20 @@ def test_tc_selftest_3xtf32_gemm(env):
     assert torch.equal(D, A2)
 
 
+def test_tc_selftest_mn_major_operands(env):
+    """MN-major TF32 operands (SWIZZLE_128B_BASE32B tiles; the weight-gradient GEMM): D[32*t + j, n] = sum_r A[t, r, j] * B[r, n]."""
+    lib, P = env["lib"].load(), env["lib"].ptr
+    g = torch.Generator(device="cuda").manual_seed(4)
+    A = torch.randn(4, 64, 32, device="cuda", generator=g)
+    B = torch.randn(64, 32, device="cuda", generator=g)
+    D = torch.zeros(128, 32, device="cuda")
+    env["lib"].check(lib.dss2_tc_selftest_mn(P(A), P(B), P(D), env["lib"].stream()), "selftest_mn")
+    torch.cuda.synchronize()
+    ref = torch.einsum("trj,rn->tjn", A.double(), B.double()).reshape(128, 32)
+    err = float((D.double() - ref).abs().max()) / float(ref.abs().max())
+    assert err < 2e-6, err
+
+
 def _tag_fwd_direct(env, fn_name, graph, x, w, bias, cout, K, act, p, mode, rng, uid, mask, res, res_stride):
     lib, P = env["lib"].load(), env["lib"].ptr
     nt = x.size(0)
