@@ -304,7 +304,7 @@ def main():
             "metric": "train scenarios/s", "value": value, "unit": "scenarios/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "nodes_per_step_per_gpu": nt, "edges_per_step_per_gpu": et,
-                       "resident_scenarios_per_gpu": args.scenarios, "cuda_graph": not args.no_graph, "tag_fwd_impl": __import__("dss2.ops", fromlist=["x"]).TAG_FWD_IMPL,
+                       "resident_scenarios_per_gpu": args.scenarios, "cuda_graph": not args.no_graph, "tag_fwd_impl": __import__("dss2.ops", fromlist=["x"]).TAG_IMPL,
                        "l2": "per-step working set (saved activations 1.47 GB + 110 MB scenario store) exceeds the 126 MB L2; no flush needed",
                        "parallelism": f"dp{world}" if world > 1 else "single"},
             "e2e": e2e, "gpu_launches": int(trainer.launches_per_step) * K, "launches_per_step": int(trainer.launches_per_step),

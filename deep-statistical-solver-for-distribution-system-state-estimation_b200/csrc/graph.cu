@@ -146,6 +146,28 @@ __global__ void k_check_edges(const int64_t* __restrict__ ei, int64_t Et, const 
   }
 }
 
+// ELL view of the first 4 entries of every row, with sources numbered relative to the row's tile (thread-per-row kernels)
+__global__ void k_build_ell(dss2_graph_t g) {
+  int t = blockIdx.x;
+  if (t >= g.num_tiles) return;
+  TileRange r = tile_range(g, t);
+  for (int n = r.n0 + threadIdx.x; n < r.n1; n += blockDim.x) {
+    const int beg = g.rowptr[n], deg = g.rowptr[n + 1] - beg;
+    uint32_t cols = 0;
+    float w[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int d = 0; d < 4; ++d) {
+      int local = n - r.n0;          // padding points at the row itself with weight 0
+      if (d < deg) {
+        local = g.col[beg + d] - r.n0;
+        w[d] = g.w[beg + d];
+      }
+      cols |= (uint32_t)(local & 0xff) << (8 * d);
+    }
+    reinterpret_cast<float4*>(g.ell_w)[n] = make_float4(w[0], w[1], w[2], w[3]);
+    reinterpret_cast<uint2*>(g.ell_ci)[n] = make_uint2(cols, (uint32_t)deg);
+  }
+}
+
 __global__ void k_tile_stats(dss2_graph_t g, int* stats) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= g.num_tiles) return;
@@ -158,7 +180,7 @@ __global__ void k_tile_stats(dss2_graph_t g, int* stats) {
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct WsLayout {
-  size_t rowptr, col, eid, dis, w, eptr, cursor, stats, cub, total, cub_bytes;
+  size_t rowptr, col, eid, dis, w, ell_w, ell_ci, eptr, cursor, stats, cub, total, cub_bytes;
 };
 WsLayout ws_layout(int64_t Nt, int64_t Et, int32_t B) {
   WsLayout L;
@@ -169,6 +191,8 @@ WsLayout ws_layout(int64_t Nt, int64_t Et, int32_t B) {
   L.eid = take((size_t)(2 * Et + 1) * 4);
   L.dis = take((size_t)(Nt + 1) * 4);
   L.w = take((size_t)(2 * Et + 1) * 4);
+  L.ell_w = take((size_t)(Nt + 1) * 16);
+  L.ell_ci = take((size_t)(Nt + 1) * 8);
   L.eptr = take((size_t)(B + 1) * 8);
   L.cursor = take((size_t)(Nt + 1) * 4);
   L.stats = take(ST_COUNT * 4);
@@ -206,6 +230,8 @@ extern "C" int dss2_graph_build(dss2_graph_t* g, const int64_t* edge_index, int6
   g->eid = (uint32_t*)(base + L.eid);
   g->dis = (float*)(base + L.dis);
   g->w = (float*)(base + L.w);
+  g->ell_w = (float*)(base + L.ell_w);
+  g->ell_ci = (uint32_t*)(base + L.ell_ci);
   g->eptr = (int64_t*)(base + L.eptr);
   int* cursor = (int*)(base + L.cursor);
   int* stats = (int*)(base + L.stats);
@@ -272,6 +298,8 @@ extern "C" int dss2_graph_build(dss2_graph_t* g, const int64_t* edge_index, int6
   g->max_tile_nodes = h_stats[ST_MAX_TILE_NODES];
   g->max_tile_nnz = h_stats[ST_MAX_TILE_NNZ];
   g->max_tile_edges = h_stats[ST_MAX_TILE_EDGES];
+  k_build_ell<<<g->num_tiles, 128, 0, stream>>>(*g);
+  DSS2_LAUNCH_CHECK();
   return 0;
 }
 

@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_tag_fwd_tc(TagTcArgs a) {
           const uint32_t off = tc::row_code((uint32_t)(blk * 4 + i)) ^ lane4;
           const float hi = tc::tf32_rna(h[i]);
           *reinterpret_cast<float*>(a_hi(k) + off) = hi;
-          *reinterpret_cast<float*>(a_lo(k) + off) = h[i] - hi;
+          *reinterpret_cast<float*>(a_lo(k) + off) = tc::tf32_rna(h[i] - hi);
         }
       }
       if (k < K) __syncthreads();

@@ -1,0 +1,618 @@
+// (b2) TAG layer on tcgen05, second generation: forward, backward-to-input and weight gradients.
+//
+// ncu on the first tensor-core kernel (profiles/r1c) showed the remaining cost was CUDA-core instruction issue and latency: a
+// warp-per-row / lane-per-feature layout spends one warp instruction per 32 floats of ONE row.  Here every CUDA-core stage is
+// thread-per-row: a thread owns one node row (32 fp32 in registers), so one warp instruction advances 32 rows.  That cuts the
+// non-GEMM work ~4x (gathers are LDS.128 of whole neighbour rows, the epilogue needs no ballots or broadcasts), and the three
+// 32x32 transforms stay on the tensor core (3xTF32, accumulators in TMEM).
+//
+//   k_tag_tc2<FWD>  y = sum_k (A^k x) W_k^T + b, dropout, ReLU, sign word, residual                 (replaces k_tag_fwd / k_tag_fwd_tc)
+//   k_tag_tc2<BGX>  grad_x = sum_k (A^k g) W_k with g = grad_y * [y>0]/(1-p): hops commute with the right-multiplication and A is
+//                   symmetric on the doubled graph, so the backward-to-input is the SAME kernel with transposed weights; it also
+//                   stores A g and A^2 g for the weight-gradient kernel
+//   k_tag_gw        grad_W_k = (A^k g)^T x, grad_b = sum g: one streaming MN-major GEMM over 64-row chunks (contraction over node
+//                   rows), accumulated in TMEM across the whole persistent CTA; no hop recomputation on x at all
+//
+// Tiles are <= 128 node rows of whole graphs (graph built with tile_cap = 128).  Operand tiles of hop level k live in one of two
+// rotating shared-memory buffers (level k+2 reuses the buffer of level k once its MMAs have committed), so a CTA needs ~90 KB and
+// two CTAs share an SM; the next tile's rows are prefetched into registers while the current tile is processed.
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace {
+
+constexpr int T2 = 128;                          // rows per tile = threads per CTA
+constexpr uint32_t LV_TILE = T2 * tc::ROW_BYTES; // 16 KB: one operand tile (hi or lo) of one hop level
+constexpr uint32_t W_TILE = 32 * tc::ROW_BYTES;  // 4 KB
+enum { MODE_FWD = 0, MODE_BGX = 1 };
+
+struct Tc2Args {
+  dss2_graph_t g;
+  const float* in;          // FWD: x [Nt,32].  BGX: grad_y [Nt,cout]
+  const uint32_t* in_bits;  // BGX: sign words of the forward output (NULL when the layer had no activation)
+  const float* w;           // [K+1][cout][32]
+  const float* bias;        // FWD
+  int cout;
+  int act;                  // FWD: apply dropout + ReLU
+  float scale;              // 1/(1-p)
+  uint32_t keep_thr16;
+  int drop_mode;
+  const uint64_t* rng;
+  uint32_t layer_uid;
+  const uint8_t* mask;
+  const float* res;
+  int64_t res_stride;
+  float* out;               // FWD: y [Nt,cout].  BGX: grad_x [Nt,32]
+  uint32_t* out_bits;       // FWD
+  float* lvl_out;           // BGX: [K][Nt,32] hop levels 1..K of g (for k_tag_gw)
+};
+
+__device__ __forceinline__ char* align1024(char* p) {
+  const uint32_t a = smem_u32(p);
+  return p + (((a + 1023u) & ~1023u) - a);
+}
+
+// 32 Bernoulli(keep) decisions for one node row (same generator as tag_tc.cu)
+__device__ __forceinline__ uint32_t keep_word(uint2 key, uint32_t tile, uint32_t row, uint32_t step_lo, uint32_t thr16) {
+  uint32_t word = 0;
+#pragma unroll
+  for (uint32_t q = 0; q < 4; ++q) {
+    const uint4 r = philox4x32_10(make_uint4(tile, row, q, step_lo), key);
+    const uint32_t u[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (uint32_t i = 0; i < 4; ++i) {
+      word |= ((u[i] & 0xffffu) < thr16 ? 1u : 0u) << (q * 8 + 2 * i);
+      word |= ((u[i] >> 16) < thr16 ? 1u : 0u) << (q * 8 + 2 * i + 1);
+    }
+  }
+  return word;
+}
+
+// this thread's row (32 fp32 in registers) -> hi / lo operand tiles, K-major SWIZZLE_128B
+__device__ __forceinline__ void store_row_sw128(const float (&v)[32], char* hi, char* lo, uint32_t row) {
+  const uint32_t code = tc::row_code(row);
+#pragma unroll
+  for (uint32_t q = 0; q < 8; ++q)
+    tc::split_store4(make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]), hi, lo, code ^ (q << 4));
+}
+
+// h += w * (hi + lo)[src row]: one neighbour, whole row
+__device__ __forceinline__ void gather_row(float (&h)[32], const char* hi, const char* lo, uint32_t src, float w) {
+  const uint32_t code = tc::row_code(src);
+#pragma unroll
+  for (uint32_t q = 0; q < 8; ++q) {
+    const float4 a = *reinterpret_cast<const float4*>(hi + (code ^ (q << 4)));
+    const float4 b = *reinterpret_cast<const float4*>(lo + (code ^ (q << 4)));
+    h[4 * q + 0] = fmaf(w, a.x + b.x, h[4 * q + 0]);
+    h[4 * q + 1] = fmaf(w, a.y + b.y, h[4 * q + 1]);
+    h[4 * q + 2] = fmaf(w, a.z + b.z, h[4 * q + 2]);
+    h[4 * q + 3] = fmaf(w, a.w + b.w, h[4 * q + 3]);
+  }
+}
+
+struct RowTopo {
+  float4 w;        // weights of the first 4 entries
+  uint32_t cols;   // 4 x 8-bit tile-local sources
+  uint32_t deg;
+};
+__device__ __forceinline__ RowTopo load_row_topo(const dss2_graph_t& g, size_t n) {
+  RowTopo t;
+  t.w = reinterpret_cast<const float4*>(g.ell_w)[n];
+  const uint2 ci = reinterpret_cast<const uint2*>(g.ell_ci)[n];
+  t.cols = ci.x;
+  t.deg = ci.y;
+  return t;
+}
+
+// one hop for this thread's row: entries in CSR order = PyG scatter order
+__device__ __forceinline__ void hop_thread(float (&h)[32], const dss2_graph_t& g, const RowTopo& tp, const char* hi, const char* lo, size_t n,
+                                           int n0) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) h[i] = 0.0f;
+  const float wv[4] = {tp.w.x, tp.w.y, tp.w.z, tp.w.w};
+#pragma unroll
+  for (uint32_t d = 0; d < 4; ++d)
+    if (d < tp.deg) gather_row(h, hi, lo, (tp.cols >> (8 * d)) & 0xffu, wv[d]);
+  if (tp.deg > 4) {   // rare: hub nodes
+    const int beg = g.rowptr[n];
+    for (int z = beg + 4; z < beg + (int)tp.deg; ++z) gather_row(h, hi, lo, (uint32_t)(g.col[z] - n0), g.w[z]);
+  }
+}
+
+template <int MODE, int K>
+__global__ void __launch_bounds__(T2, 2) k_tag_tc2(Tc2Args a) {
+  extern __shared__ char raw[];
+  const dss2_graph_t& g = a.g;
+  char* base = align1024(raw);
+  char* Wt = base;                                  // [(K+1)][hi,lo] x 4 KB weight operand tiles
+  char* Lv = Wt + (K + 1) * 2 * W_TILE;             // [2 buffers][hi,lo] x 16 KB level tiles
+  char* tail = Lv + 4 * LV_TILE;
+  float* bias_s = reinterpret_cast<float*>(tail);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 128);   // [2]: "MMAs reading buffer b have completed"
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(tail + 144);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int cout = a.cout;
+  auto lv_hi = [&](int b) { return Lv + (size_t)(2 * b) * LV_TILE; };
+  auto lv_lo = [&](int b) { return Lv + (size_t)(2 * b + 1) * LV_TILE; };
+
+  // ---- one-time setup ----
+  if (warp == 0) tc::tmem_alloc(tslot, 32);
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_mbar_init();
+  }
+  // weight operand B[n][kk] (K-major rows n): FWD n = output feature c, kk = input feature j: W_k[c][j];
+  //                                           BGX n = input feature j, kk = output feature c: W_k[c][j] transposed
+  for (int idx = tid; idx < (K + 1) * 32 * 32; idx += T2) {
+    const int k = idx >> 10, nrow = (idx >> 5) & 31, kk = idx & 31;
+    const int c = MODE == MODE_FWD ? nrow : kk, j = MODE == MODE_FWD ? kk : nrow;
+    const float v = c < cout ? a.w[((size_t)k * cout + c) * HID + j] : 0.0f;
+    const float hi = tc::tf32_rna(v);
+    const uint32_t off = tc::swz_off((uint32_t)nrow, (uint32_t)kk);
+    *reinterpret_cast<float*>(Wt + (size_t)(2 * k) * W_TILE + off) = hi;
+    *reinterpret_cast<float*>(Wt + (size_t)(2 * k + 1) * W_TILE + off) = tc::tf32_rna(v - hi);
+  }
+  if (tid < 32) bias_s[tid] = (MODE == MODE_FWD && tid < cout) ? a.bias[tid] : 0.0f;
+  uint2 key = make_uint2(0u, 0u);
+  uint32_t step_lo = 0;
+  if (MODE == MODE_FWD && a.drop_mode == 1) {
+    const uint64_t seed = a.rng[0], step = a.rng[1];
+    key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32) ^ (a.layer_uid * 0x9E3779B9u) ^ (uint32_t)(step >> 32));
+    step_lo = (uint32_t)step;
+  }
+  fence_proxy_async();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = *tslot;
+  const uint32_t idesc = tc::idesc_tf32(128, 32);
+  uint32_t par[2] = {0u, 0u};
+
+  // row loader: this thread's input row of tile t (zero padded), FWD: x row; BGX: masked grad_y row
+  float xr[32];
+  RowTopo tp;
+  tp.deg = 0;
+  tp.cols = 0;
+  tp.w = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto load_row = [&](int t) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) xr[i] = 0.0f;
+    if (t >= g.num_tiles) return;
+    const TileRange r = tile_range(g, t);
+    if (tid >= r.n1 - r.n0) return;
+    const size_t n = (size_t)r.n0 + tid;
+    if (MODE == MODE_FWD || cout == 32) {
+      const float4* src = reinterpret_cast<const float4*>(a.in + n * 32);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 v = ldg_stream4(src + q);
+        xr[4 * q] = v.x;
+        xr[4 * q + 1] = v.y;
+        xr[4 * q + 2] = v.z;
+        xr[4 * q + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 32; ++c)
+        if (c < cout) xr[c] = a.in[n * cout + c];
+    }
+    if (MODE == MODE_BGX && a.in_bits) {
+      const uint32_t word = a.in_bits[n];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) xr[c] = ((word >> c) & 1u) ? xr[c] * a.scale : 0.0f;
+    }
+  };
+
+  load_row(blockIdx.x);
+  for (int t = blockIdx.x; t < g.num_tiles; t += gridDim.x) {
+    const TileRange r = tile_range(g, t);
+    const int nT = r.n1 - r.n0;
+    const bool live = tid < nT;
+    const size_t n = (size_t)r.n0 + tid;
+    if (live) tp = load_row_topo(g, n);
+    // ---- level 0 ----
+    store_row_sw128(xr, lv_hi(0), lv_lo(0), (uint32_t)tid);      // dead rows store zeros: keeps the MMA input finite
+    load_row(t + gridDim.x);                                     // prefetch the next tile's row into the same registers
+    fence_proxy_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      tc::fence_after_sync();
+      tc::issue_block(tmem, smem_u32(lv_hi(0)), smem_u32(lv_lo(0)), smem_u32(Wt), smem_u32(Wt + W_TILE), idesc, true);
+      tc::mma_commit(&bars[0]);
+    }
+    // ---- levels 1..K ----
+#pragma unroll
+    for (int k = 1; k <= K; ++k) {
+      const int b = k & 1, pb = (k - 1) & 1;
+      float h[32];
+      if (live) hop_thread(h, g, tp, lv_hi(pb), lv_lo(pb), n, r.n0);
+      else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) h[i] = 0.0f;
+      }
+      if (k >= 2) {   // buffer b still feeds the MMAs of level k-2
+        mbar_wait(&bars[b], par[b]);
+        par[b] ^= 1u;
+      }
+      store_row_sw128(h, lv_hi(b), lv_lo(b), (uint32_t)tid);
+      if (MODE == MODE_BGX && a.lvl_out && live) {
+        float4* dst = reinterpret_cast<float4*>(a.lvl_out + ((size_t)(k - 1) * g.num_nodes + n) * 32);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) dst[q] = make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
+      }
+      fence_proxy_async();
+      tc::fence_before_sync();
+      __syncthreads();
+      if (tid == 0) {
+        tc::fence_after_sync();
+        tc::issue_block(tmem, smem_u32(lv_hi(b)), smem_u32(lv_lo(b)), smem_u32(Wt + (size_t)(2 * k) * W_TILE),
+                        smem_u32(Wt + (size_t)(2 * k + 1) * W_TILE), idesc, false);
+        tc::mma_commit(&bars[b]);
+      }
+    }
+    // ---- all MMAs of the tile complete when the last two commits have arrived ----
+    if (K >= 1) {
+      const int b2 = (K - 1) & 1;
+      mbar_wait(&bars[b2], par[b2]);
+      par[b2] ^= 1u;
+    }
+    {
+      const int b1 = K & 1;
+      mbar_wait(&bars[b1], par[b1]);
+      par[b1] ^= 1u;
+    }
+    tc::fence_after_sync();
+    float v[32];
+    tc::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16), v);
+    if (live) {
+      if (MODE == MODE_FWD) {
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 bq = *reinterpret_cast<const float4*>(bias_s + 4 * c4);
+          v[4 * c4 + 0] += bq.x;
+          v[4 * c4 + 1] += bq.y;
+          v[4 * c4 + 2] += bq.z;
+          v[4 * c4 + 3] += bq.w;
+        }
+        if (a.act) {
+          uint32_t keep = 0xffffffffu;
+          if (a.drop_mode == 1) {
+            keep = keep_word(key, (uint32_t)t, (uint32_t)tid, step_lo, a.keep_thr16);
+          } else if (a.drop_mode == 2) {
+            const uint4* mp = reinterpret_cast<const uint4*>(a.mask + n * HID);
+            const uint4 m0 = mp[0], m1 = mp[1];
+            const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+            keep = 0u;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) keep |= (((mw[c >> 2] >> ((c & 3) * 8)) & 0xffu) != 0u ? 1u : 0u) << c;
+          }
+          uint32_t word = 0u;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            float xv = v[c];
+            if (a.drop_mode != 0) xv = ((keep >> c) & 1u) ? xv * a.scale : 0.0f;
+            xv = fmaxf(xv, 0.0f);
+            word |= (xv > 0.0f ? 1u : 0u) << c;
+            v[c] = xv;
+          }
+          if (a.out_bits) a.out_bits[n] = word;
+        }
+        if (a.res) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if (c < cout) v[c] += a.res[n * a.res_stride + c];
+        }
+      }
+      const int ow = MODE == MODE_FWD ? cout : 32;
+      if (ow == 32) {
+        float4* dst = reinterpret_cast<float4*>(a.out + n * 32);
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) dst[c4] = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+      } else if (ow == 8) {
+        float4* dst = reinterpret_cast<float4*>(a.out + n * 8);
+        dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+        dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+      } else if (ow == 2) {
+        *reinterpret_cast<float2*>(a.out + n * 2) = make_float2(v[0], v[1]);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+          if (c < ow) a.out[n * ow + c] = v[c];
+      }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+  }
+  if (warp == 0) tc::tmem_dealloc(tmem, 32);
+}
+
+// -------------------------------------------------------------------------------------------------
+// weight gradients: D[32*k + c, j] = sum_r G_k[r][c] * x[r][j]  (k <= K), D[c, 32] = sum_r G_0[r][c]  (bias gradient, ones column)
+// -------------------------------------------------------------------------------------------------
+constexpr int GW_ROWS = 64;                       // node rows per chunk (contraction block)
+constexpr uint32_t GW_TILE = GW_ROWS * tc::ROW_BYTES;   // 8 KB
+
+struct GwArgs {
+  int64_t num_nodes;
+  const float* x;          // layer input [Nt,32]
+  const float* gy;         // grad wrt layer output [Nt,cout]
+  const uint32_t* bits;    // sign words or NULL
+  const float* lvl;        // [K][Nt,32] = A g, A^2 g from k_tag_tc2<BGX>
+  int cout;
+  float scale;
+  float* partials;         // row = blockIdx.x
+  int64_t partial_stride;
+  int64_t bias_offset;
+};
+
+template <int K>
+__global__ void __launch_bounds__(128, 2) k_tag_gw(GwArgs a) {
+  extern __shared__ char raw[];
+  char* base = align1024(raw);
+  // A side (MN-major, M = 32*level + c): [hi: G_0..G_K, pad][lo: G_0..G_K, pad] each tile 8 KB, LBO = 8 KB; with K = 2 the M = 128
+  // extent covers 3 levels + 1 block that aliases the next tile (ignored rows 96..127)
+  char* Ah = base;
+  char* Al = Ah + 4 * GW_TILE;
+  // B side (MN-major, N = 48: 32 input features + the ones column): [x.hi][ones][x.lo][zeros]
+  char* Bh = Al + 4 * GW_TILE;
+  char* Bones = Bh + GW_TILE;
+  char* Bl = Bones + GW_TILE;
+  char* Bzero = Bl + GW_TILE;
+  char* tail = Bzero + GW_TILE;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(tail);
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(tail + 16);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int row = tid & (GW_ROWS - 1), half = tid >> 6;   // two threads per chunk row: half 0 -> x and G_0, half 1 -> G_1, G_2
+  const int cout = a.cout;
+
+  if (warp == 0) tc::tmem_alloc(tslot, 64);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  // constant tiles: ones column (feature 0 of the second N block) / zeros, and the unused 4th A block
+  for (int idx = tid; idx < GW_ROWS * 32; idx += 128) {
+    const uint32_t r = idx >> 5, j = idx & 31;
+    *reinterpret_cast<float*>(Bones + tc::swz32_off(r, j)) = j == 0 ? 1.0f : 0.0f;
+    *reinterpret_cast<float*>(Bzero + tc::swz32_off(r, j)) = 0.0f;
+    if (K < 3) {
+      *reinterpret_cast<float*>(Ah + 3 * GW_TILE + tc::swz32_off(r, j)) = 0.0f;
+      *reinterpret_cast<float*>(Al + 3 * GW_TILE + tc::swz32_off(r, j)) = 0.0f;
+      if (K < 2) {
+        *reinterpret_cast<float*>(Ah + 2 * GW_TILE + tc::swz32_off(r, j)) = 0.0f;
+        *reinterpret_cast<float*>(Al + 2 * GW_TILE + tc::swz32_off(r, j)) = 0.0f;
+      }
+    }
+  }
+  fence_proxy_async();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = *tslot;
+  const uint32_t idesc = tc::idesc_tf32(128, 48, 1, 1);
+  uint32_t par = 0;
+
+  const int64_t num_chunks = (a.num_nodes + GW_ROWS - 1) / GW_ROWS;
+  float r0[32], r1[32];   // half 0: x row, masked grad row.  half 1: level-1 row, level-2 row
+  auto load_chunk = [&](int64_t ch) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) r0[i] = r1[i] = 0.0f;
+    const int64_t n = ch * GW_ROWS + row;
+    if (ch >= num_chunks || n >= a.num_nodes) return;
+    const float* p0 = half == 0 ? a.x + n * 32 : a.lvl + n * 32;
+    const float* p1 = half == 0 ? nullptr : (K >= 2 ? a.lvl + (a.num_nodes + n) * 32 : nullptr);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 v = ldg_stream4(reinterpret_cast<const float4*>(p0) + q);
+      r0[4 * q] = v.x;
+      r0[4 * q + 1] = v.y;
+      r0[4 * q + 2] = v.z;
+      r0[4 * q + 3] = v.w;
+    }
+    if (half == 0) {
+      if (cout == 32) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 v = ldg_stream4(reinterpret_cast<const float4*>(a.gy + n * 32) + q);
+          r1[4 * q] = v.x;
+          r1[4 * q + 1] = v.y;
+          r1[4 * q + 2] = v.z;
+          r1[4 * q + 3] = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+          if (c < cout) r1[c] = a.gy[n * cout + c];
+      }
+      if (a.bits) {
+        const uint32_t word = a.bits[n];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) r1[c] = ((word >> c) & 1u) ? r1[c] * a.scale : 0.0f;
+      }
+    } else if (p1) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 v = ldg_stream4(reinterpret_cast<const float4*>(p1) + q);
+        r1[4 * q] = v.x;
+        r1[4 * q + 1] = v.y;
+        r1[4 * q + 2] = v.z;
+        r1[4 * q + 3] = v.w;
+      }
+    }
+  };
+  auto store_row32 = [&](const float (&v)[32], char* hi, char* lo) {
+#pragma unroll
+    for (uint32_t q = 0; q < 8; ++q)
+      tc::split_store4(make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]), hi, lo, tc::swz32_off((uint32_t)row, 4 * q));
+  };
+
+  bool first = true;
+  load_chunk(blockIdx.x);
+  for (int64_t ch = blockIdx.x; ch < num_chunks; ch += gridDim.x) {
+    if (!first) {   // the previous chunk's MMAs still read the tiles
+      mbar_wait(bar, par);
+      par ^= 1u;
+    }
+    if (half == 0) {
+      store_row32(r0, Bh, Bl);                         // x
+      store_row32(r1, Ah, Al);                         // G_0
+    } else {
+      store_row32(r0, Ah + GW_TILE, Al + GW_TILE);     // G_1
+      if (K >= 2) store_row32(r1, Ah + 2 * GW_TILE, Al + 2 * GW_TILE);   // G_2
+    }
+    load_chunk(ch + gridDim.x);
+    fence_proxy_async();
+    tc::fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      tc::fence_after_sync();
+#pragma unroll
+      for (uint32_t ks = 0; ks < GW_ROWS / 8; ++ks) {
+        const uint32_t o = ks * 1024;
+        tc::mma_tf32(tmem, tc::smem_desc_mn32(smem_u32(Al) + o, GW_TILE), tc::smem_desc_mn32(smem_u32(Bl) + o, GW_TILE), idesc,
+                     (first && ks == 0) ? 0u : 1u);
+        tc::mma_tf32(tmem, tc::smem_desc_mn32(smem_u32(Al) + o, GW_TILE), tc::smem_desc_mn32(smem_u32(Bh) + o, GW_TILE), idesc, 1u);
+        tc::mma_tf32(tmem, tc::smem_desc_mn32(smem_u32(Ah) + o, GW_TILE), tc::smem_desc_mn32(smem_u32(Bl) + o, GW_TILE), idesc, 1u);
+        tc::mma_tf32(tmem, tc::smem_desc_mn32(smem_u32(Ah) + o, GW_TILE), tc::smem_desc_mn32(smem_u32(Bh) + o, GW_TILE), idesc, 1u);
+      }
+      tc::mma_commit(bar);
+    }
+    first = false;
+  }
+  // ---- write this CTA's partial sums ----
+  float* part = a.partials + (size_t)blockIdx.x * a.partial_stride;
+  const int m = tid;                 // TMEM lane = 32*level + c
+  const int k = m >> 5, c = m & 31;
+  if (!first) {
+    mbar_wait(bar, par);
+    tc::fence_after_sync();
+    float v[32];
+    tc::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16), v);
+    float vb[32];
+    tc::tmem_ld32(tmem + 32 + ((uint32_t)(warp * 32) << 16), vb);    // column 32 = bias gradient (level 0 lanes)
+    if (k <= K && c < cout) {
+      float4* dst = reinterpret_cast<float4*>(part + ((size_t)k * cout + c) * 32);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      if (k == 0) part[a.bias_offset + c] = vb[0];
+    }
+  } else if (k <= K && c < cout) {   // a CTA without chunks contributes zeros
+#pragma unroll
+    for (int j = 0; j < 32; ++j) part[((size_t)k * cout + c) * 32 + j] = 0.0f;
+    if (k == 0) part[a.bias_offset + c] = 0.0f;
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 64);
+}
+
+size_t tc2_smem(int K) { return 1024 + (size_t)(K + 1) * 2 * W_TILE + 4 * LV_TILE + 256; }
+size_t gw_smem() { return 1024 + 12 * GW_TILE + 64; }
+
+int tc2_supported(const dss2_graph_t* g, int K) {
+  return g && g->num_tiles > 0 && g->max_tile_nodes <= T2 && K >= 1 && K <= 2 && g->ell_w && g->ell_ci;
+}
+
+template <int MODE>
+int launch_tc2(const Tc2Args& a, int K, cudaStream_t stream) {
+  const size_t smem = tc2_smem(K);
+  const int grid = max(1, min(a.g.num_tiles, 2 * dss2_sm_count()));
+  if (K == 1) {
+    DSS2_CUDA(cudaFuncSetAttribute(k_tag_tc2<MODE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_tag_tc2<MODE, 1><<<grid, T2, smem, stream>>>(a);
+  } else {
+    DSS2_CUDA(cudaFuncSetAttribute(k_tag_tc2<MODE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_tag_tc2<MODE, 2><<<grid, T2, smem, stream>>>(a);
+  }
+  DSS2_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int dss2_tag_tc2_supported(const dss2_graph_t* g, int K) { return tc2_supported(g, K); }
+
+extern "C" int dss2_tag_fwd_tc2(const dss2_graph_t* g, const float* x, const float* w, const float* bias, int cout, int K, int act,
+                                float p_drop, int drop_mode, const uint64_t* rng_state, uint32_t layer_uid, const uint8_t* mask,
+                                const float* res, int64_t res_stride, float* y, uint32_t* act_bits, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DSS2_CHECK_ARG(g && x && w && bias && y, "dss2_tag_fwd_tc2: null argument");
+  DSS2_CHECK_ARG(cout >= 1 && cout <= HID, "dss2_tag_fwd_tc2: cout %d outside 1..%d", cout, HID);
+  DSS2_CHECK_ARG(tc2_supported(g, K), "dss2_tag_fwd_tc2: needs a graph tiled with tile_cap <= 128 and K in 1..2");
+  DSS2_CHECK_ARG(p_drop >= 0.0f && p_drop < 1.0f, "dss2_tag_fwd_tc2: dropout p %f outside [0,1)", p_drop);
+  DSS2_CHECK_ARG(!(act && drop_mode == 1) || rng_state, "dss2_tag_fwd_tc2: philox dropout needs rng_state");
+  DSS2_CHECK_ARG(!(act && drop_mode == 2) || mask, "dss2_tag_fwd_tc2: mask dropout needs a mask");
+  if (g->num_nodes == 0) return 0;
+  Tc2Args a = {};
+  a.g = *g;
+  a.in = x;
+  a.w = w;
+  a.bias = bias;
+  a.cout = cout;
+  a.act = act;
+  if (p_drop == 0.0f) drop_mode = 0;
+  a.drop_mode = act ? drop_mode : 0;
+  a.scale = 1.0f / (float)(1.0 - (double)p_drop);
+  double thr = (1.0 - (double)p_drop) * 65536.0 + 0.5;
+  a.keep_thr16 = thr >= 65536.0 ? 65536u : (uint32_t)thr;
+  a.rng = rng_state;
+  a.layer_uid = layer_uid;
+  a.mask = mask;
+  a.res = res;
+  a.res_stride = res_stride;
+  a.out = y;
+  a.out_bits = act_bits;
+  return launch_tc2<MODE_FWD>(a, K, stream);
+}
+
+extern "C" size_t dss2_tag_bwd_tc2_workspace_bytes(int64_t num_nodes, int K) { return (size_t)K * num_nodes * HID * sizeof(float) + 256; }
+
+extern "C" int dss2_tag_bwd_tc2(const dss2_graph_t* g, const float* x, const float* w, int cout, int K, int act, float p_drop,
+                                const uint32_t* act_bits, const float* grad_y, float* grad_x, float* partials, int64_t partial_stride,
+                                int64_t bias_offset, void* ws, size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DSS2_CHECK_ARG(g && x && w && grad_y && grad_x && partials && ws, "dss2_tag_bwd_tc2: null argument");
+  DSS2_CHECK_ARG(cout >= 1 && cout <= HID, "dss2_tag_bwd_tc2: cout %d outside 1..%d", cout, HID);
+  DSS2_CHECK_ARG(tc2_supported(g, K), "dss2_tag_bwd_tc2: needs a graph tiled with tile_cap <= 128 and K in 1..2");
+  DSS2_CHECK_ARG(!act || act_bits, "dss2_tag_bwd_tc2: activation layers need act_bits from the forward");
+  DSS2_CHECK_ARG(ws_bytes >= dss2_tag_bwd_tc2_workspace_bytes(g->num_nodes, K), "dss2_tag_bwd_tc2: workspace too small");
+  DSS2_CHECK_ARG(partial_stride >= (int64_t)(K + 1) * cout * HID + cout, "dss2_tag_bwd_tc2: partial_stride too small");
+  if (g->num_nodes == 0) return 0;
+  const float scale = 1.0f / (float)(1.0 - (double)p_drop);
+  Tc2Args a = {};
+  a.g = *g;
+  a.in = grad_y;
+  a.in_bits = act ? act_bits : nullptr;
+  a.w = w;
+  a.cout = cout;
+  a.scale = scale;
+  a.out = grad_x;
+  a.lvl_out = (float*)ws;
+  int rc = launch_tc2<MODE_BGX>(a, K, stream);
+  if (rc) return rc;
+  GwArgs b;
+  b.num_nodes = g->num_nodes;
+  b.x = x;
+  b.gy = grad_y;
+  b.bits = act ? act_bits : nullptr;
+  b.lvl = (const float*)ws;
+  b.cout = cout;
+  b.scale = scale;
+  b.partials = partials;
+  b.partial_stride = partial_stride;
+  b.bias_offset = bias_offset;
+  const size_t smem = gw_smem();
+  const int grid = dss2_sm_count();    // = dss2_num_partials(): every partial row is written
+  if (K == 1) {
+    DSS2_CUDA(cudaFuncSetAttribute(k_tag_gw<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_tag_gw<1><<<grid, 128, smem, stream>>>(b);
+  } else {
+    DSS2_CUDA(cudaFuncSetAttribute(k_tag_gw<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_tag_gw<2><<<grid, 128, smem, stream>>>(b);
+  }
+  DSS2_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,8 +1,8 @@
 // tcgen05 / TMEM helpers for the 32x32 feature transforms (sm_100a).
 //
 // The transforms are evaluated as 3xTF32: x = x_hi + x_lo with x_hi = round-to-nearest TF32(x) and x_lo = x - x_hi (exact in
-// fp32, read by the tensor core as TF32), and x.w ~= x_hi.w_hi + x_lo.w_hi + x_hi.w_lo with fp32 accumulation in TMEM.  The
-// dropped terms are <= 2^-21 relative, i.e. fp32-equivalent accuracy (plain TF32 would be ~1e-3 and break 1e-5 parity).
+// fp32, then itself rounded to TF32), and x.w ~= x_hi.w_hi + x_lo.w_hi + x_hi.w_lo with fp32 accumulation in TMEM.  The
+// dropped terms are <= 2^-22 relative, i.e. fp32-equivalent accuracy (plain TF32 would be ~1e-3 and break 1e-5 parity).
 //
 // Operand tiles live in shared memory as [rows][32 fp32] = 128-byte rows, K-major, SWIZZLE_128B: 16-byte chunk c of row r
 // is stored at chunk (c ^ (r & 7)); an 8-row group is 1024 bytes (SBO), the tile base is 1024-byte aligned.  One
@@ -144,10 +144,12 @@ __device__ __forceinline__ void split_store4(const float4 v, char* hi_tile, char
   h.y = tf32_rna(v.y);
   h.z = tf32_rna(v.z);
   h.w = tf32_rna(v.w);
-  l.x = v.x - h.x;
-  l.y = v.y - h.y;
-  l.z = v.z - h.z;
-  l.w = v.w - h.w;
+  // the residual is rounded to TF32 as well: the tensor core would otherwise TRUNCATE it (biased, errors add coherently in long
+  // sums); rounded, the representation error is <= 2^-22 |x| and unbiased
+  l.x = tf32_rna(v.x - h.x);
+  l.y = tf32_rna(v.y - h.y);
+  l.z = tf32_rna(v.z - h.z);
+  l.w = tf32_rna(v.w - h.w);
   *reinterpret_cast<float4*>(hi_tile + off) = h;
   *reinterpret_cast<float4*>(lo_tile + off) = l;
 }
@@ -159,8 +161,10 @@ __device__ __forceinline__ void issue_block(uint32_t d_tmem, uint32_t a_hi, uint
 #pragma unroll
   for (uint32_t kk = 0; kk < ROW_BYTES / KSTEP_BYTES; ++kk) {
     const uint32_t o = kk * KSTEP_BYTES;
-    // small terms first
-    mma_tf32(d_tmem, smem_desc_sw128(a_lo + o), smem_desc_sw128(b_hi + o), idesc, (first && kk == 0) ? 0u : 1u);
+    // small terms first; the lo.lo term (2^-22) is kept too - MMA issue is nowhere near the bottleneck and it leaves the operand
+    // representation (2^-23 per operand, unbiased) as the only error source
+    mma_tf32(d_tmem, smem_desc_sw128(a_lo + o), smem_desc_sw128(b_lo + o), idesc, (first && kk == 0) ? 0u : 1u);
+    mma_tf32(d_tmem, smem_desc_sw128(a_lo + o), smem_desc_sw128(b_hi + o), idesc, 1u);
     mma_tf32(d_tmem, smem_desc_sw128(a_hi + o), smem_desc_sw128(b_lo + o), idesc, 1u);
     mma_tf32(d_tmem, smem_desc_sw128(a_hi + o), smem_desc_sw128(b_hi + o), idesc, 1u);
   }

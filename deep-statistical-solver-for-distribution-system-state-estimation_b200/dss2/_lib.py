@@ -23,7 +23,7 @@ class GraphStruct(Structure):
         ("num_graphs", c_int32), ("undirected", c_int32), ("graphs_per_tile", c_int32), ("num_tiles", c_int32),
         ("max_tile_nodes", c_int32), ("max_tile_nnz", c_int32), ("max_tile_edges", c_int32), ("reserved", c_int32),
         ("edge_index", c_void_p), ("ptr", c_void_p), ("eptr", c_void_p), ("rowptr", c_void_p), ("col", c_void_p),
-        ("eid", c_void_p), ("dis", c_void_p), ("w", c_void_p),
+        ("eid", c_void_p), ("dis", c_void_p), ("w", c_void_p), ("ell_w", c_void_p), ("ell_ci", c_void_p),
     ]
 
 
@@ -42,6 +42,10 @@ _SIGNATURES = {
     "dss2_tag_fwd": (c_int, [_G, _P, _P, _P, c_int, c_int, c_int, c_float, c_int, _P, c_uint32, _P, _P, c_int64, _P, _P, _P]),
     "dss2_tag_fwd_tc_supported": (c_int, [_G, c_int]),
     "dss2_tag_fwd_tc": (c_int, [_G, _P, _P, _P, c_int, c_int, c_int, c_float, c_int, _P, c_uint32, _P, _P, c_int64, _P, _P, _P]),
+    "dss2_tag_tc2_supported": (c_int, [_G, c_int]),
+    "dss2_tag_fwd_tc2": (c_int, [_G, _P, _P, _P, c_int, c_int, c_int, c_float, c_int, _P, c_uint32, _P, _P, c_int64, _P, _P, _P]),
+    "dss2_tag_bwd_tc2_workspace_bytes": (c_size_t, [c_int64, c_int]),
+    "dss2_tag_bwd_tc2": (c_int, [_G, _P, _P, c_int, c_int, c_int, c_float, _P, _P, _P, _P, c_int64, c_int64, _P, c_size_t, _P]),
     "dss2_tc_selftest": (c_int, [_P, _P, _P, _P]),
     "dss2_tc_selftest_mn": (c_int, [_P, _P, _P, _P]),
     "dss2_tag_bwd": (c_int, [_G, _P, _P, c_int, c_int, c_int, c_float, _P, _P, _P, _P, c_int64, c_int64, _P]),

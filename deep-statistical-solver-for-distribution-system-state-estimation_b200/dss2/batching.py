@@ -90,6 +90,11 @@ def launch_pack(store, ids, out, num_nodes, num_edges):
     _lib.check(rc, "dss2_pack_batch")
 
 
+def _tile_cap():
+    from . import ops
+    return ops.tile_cap()
+
+
 def pack_batch(store, ids, graph_cache=None):
     """Fresh Batch for scenario ids (sequence or tensor).  Sizes come from the host copy of the offsets."""
     _lib.load()
@@ -116,15 +121,15 @@ def pack_batch(store, ids, graph_cache=None):
         # structure: identical for every batch drawn from a uniform-topology store with the same graph count
         key = None
         if graph_cache is not None and _uniform(store):
-            key = (b, store.max_nodes, store.max_edges)
+            key = (b, store.max_nodes, store.max_edges, _tile_cap())
         g = graph_cache.get(key) if key is not None else None
         if g is None:
             if key is not None:
                 # a cached structure must not alias this batch's tensors: it keeps private copies
-                g = BatchGraph(batch.edge_index.clone(), nt, ptr=batch.ptr.clone())
+                g = BatchGraph(batch.edge_index.clone(), nt, ptr=batch.ptr.clone(), tile_cap=_tile_cap())
                 graph_cache[key] = g
             else:
-                g = BatchGraph(batch.edge_index, nt, ptr=batch.ptr)
+                g = BatchGraph(batch.edge_index, nt, ptr=batch.ptr, tile_cap=_tile_cap())
     batch.edge_index._dss2_graph = g
     batch.edge_index._dss2_graph_version = batch.edge_index._version
     return batch

@@ -24,6 +24,7 @@ class BatchGraph:
             raise ValueError("edge_index must be int64 [2, E]")
         self.edge_index = edge_index.contiguous()
         self.num_nodes = int(num_nodes)
+        self.tile_cap = int(tile_cap)
         self.num_edges = int(edge_index.size(1))
         if ptr is None:
             ptr = discover_segments(self.edge_index, self.num_nodes)

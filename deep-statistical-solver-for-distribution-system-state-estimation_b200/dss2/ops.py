@@ -12,9 +12,16 @@ from . import _lib
 from .graph import BatchGraph, graph_for
 
 HID = _lib.HID
-# which forward TAG-layer kernel the runner launches: "tc" = tcgen05 3xTF32 transforms (falls back to the CUDA-core kernel
-# where unsupported: K = 3 or a tile that does not fit), "ffma" = CUDA-core kernel.  Both are CUDA; there is no CPU path.
-TAG_FWD_IMPL = os.environ.get("DSS2_TAG_FWD", "ffma")
+# which TAG-layer kernels the runner launches (all are CUDA; there is no CPU path):
+#   "ffma": CUDA-core forward and backward (tag.cu)
+#   "tc"  : first tcgen05 forward (tag_tc.cu), CUDA-core backward
+#   "tc2" : second-generation tcgen05 forward AND backward (tag_tc2.cu); needs graphs tiled with tile_cap 128
+# Unsupported shapes (K = 3, oversize tiles) fall back to the CUDA-core kernels.
+TAG_IMPL = os.environ.get("DSS2_TAG_IMPL", "tc2")
+
+
+def tile_cap():
+    return 128 if TAG_IMPL == "tc2" else _lib.TILE_CAP
 
 
 def _align4(n):
@@ -105,6 +112,7 @@ class PFNRunner:
             b["g32"] = [torch.empty(num_nodes, HID, **f32) for _ in range(2)]
             b["gsub"] = [torch.empty(num_nodes, sp.fn, **f32) for _ in range(2)]
             b["partials"] = torch.zeros(self.num_partials, self.flat_size, **f32)
+            b["lvl"] = torch.empty(self.lib.dss2_tag_bwd_tc2_workspace_bytes(num_nodes, sp.K) // 4, **f32)
         return b
 
     def _p(self, flat, name):
@@ -117,7 +125,8 @@ class PFNRunner:
         masks: optional [L][n_layers-1] uint8 [Nt,32] tensors (drop_mode 2).  Returns bufs['outs'][-1]."""
         sp, lib, st = self.spec, self.lib, _lib.stream()
         g = graph.ref
-        use_tc = TAG_FWD_IMPL == "tc" and bool(lib.dss2_tag_fwd_tc_supported(g, sp.K))
+        use_tc = TAG_IMPL == "tc" and bool(lib.dss2_tag_fwd_tc_supported(g, sp.K))
+        use_tc2 = TAG_IMPL == "tc2" and bool(lib.dss2_tag_tc2_supported(g, sp.K))
         for s in range(sp.L):
             pre = sp.prefix_fmt.format(s=s)
             xin, xs = (x, x_stride) if s == 0 else (bufs["outs"][s - 1], sp.fn)
@@ -134,7 +143,7 @@ class PFNRunner:
                 if not last and drop_mode == 2:
                     mask = masks[s][l]
                 res, rs = (xin, xs) if (last and sp.skip[s]) else (None, 0)
-                fwd = lib.dss2_tag_fwd_tc if use_tc else lib.dss2_tag_fwd
+                fwd = lib.dss2_tag_fwd_tc2 if use_tc2 else (lib.dss2_tag_fwd_tc if use_tc else lib.dss2_tag_fwd)
                 _lib.check(fwd(g, _lib.ptr(bufs["acts"][s, l]), self._p(flat, pre + f"convs.{l}.lins.0.weight"),
                                self._p(flat, pre + f"convs.{l}.bias"), cout, sp.K, 0 if last else 1, sp.p_drop, mode,
                                _lib.ptr(rng_state), s * sp.n_layers + l, _lib.ptr(mask), _lib.ptr(res), rs,
@@ -152,6 +161,7 @@ class PFNRunner:
         def pp(name):
             return ctypes.c_void_p(part.data_ptr() + 4 * self.table[name][0])
 
+        use_tc2 = TAG_IMPL == "tc2" and bool(lib.dss2_tag_tc2_supported(g, sp.K))
         gy = grad_out
         for s in reversed(range(sp.L)):
             pre = sp.prefix_fmt.format(s=s)
@@ -162,10 +172,13 @@ class PFNRunner:
                 cout = sp.out_dim(s) if last else HID
                 gx = bufs["g32"][l & 1]
                 w_off, b_off = self.table[pre + f"convs.{l}.lins.0.weight"][0], self.table[pre + f"convs.{l}.bias"][0]
-                _lib.check(lib.dss2_tag_bwd(g, _lib.ptr(bufs["acts"][s, l]), self._p(flat, pre + f"convs.{l}.lins.0.weight"), cout, sp.K,
-                                            0 if last else 1, sp.p_drop, None if last else _lib.ptr(bufs["bits"][s, l]),
-                                            _lib.ptr(gy), _lib.ptr(gx), pp(pre + f"convs.{l}.lins.0.weight"), pstride,
-                                            b_off - w_off, st), "dss2_tag_bwd")
+                common = (g, _lib.ptr(bufs["acts"][s, l]), self._p(flat, pre + f"convs.{l}.lins.0.weight"), cout, sp.K,
+                          0 if last else 1, sp.p_drop, None if last else _lib.ptr(bufs["bits"][s, l]),
+                          _lib.ptr(gy), _lib.ptr(gx), pp(pre + f"convs.{l}.lins.0.weight"), pstride, b_off - w_off)
+                if use_tc2:
+                    _lib.check(lib.dss2_tag_bwd_tc2(*common, _lib.ptr(bufs["lvl"]), bufs["lvl"].numel() * 4, st), "dss2_tag_bwd_tc2")
+                else:
+                    _lib.check(lib.dss2_tag_bwd(*common, st), "dss2_tag_bwd")
                 gy = gx
             need_gx = s > 0
             gprev = bufs["gsub"][s & 1] if need_gx else None
@@ -258,10 +271,11 @@ def stage_rows(t):
 def resolve_graph(edge_index, num_nodes):
     """BatchGraph for `edge_index` (CPU or CUDA).  Cached on the tensor object, keyed by its version."""
     cached = getattr(edge_index, "_dss2_graph", None)
-    if cached is not None and cached.num_nodes == num_nodes and getattr(edge_index, "_dss2_graph_version", None) == edge_index._version:
+    if (cached is not None and cached.num_nodes == num_nodes and getattr(edge_index, "_dss2_graph_version", None) == edge_index._version
+            and cached.tile_cap <= tile_cap()):
         return cached
     ei = edge_index if edge_index.device.type == "cuda" else edge_index.cuda(non_blocking=True)
-    g = BatchGraph(ei.long(), num_nodes, ptr=getattr(edge_index, "_dss2_ptr", None))
+    g = BatchGraph(ei.long(), num_nodes, ptr=getattr(edge_index, "_dss2_ptr", None), tile_cap=tile_cap())
     try:
         edge_index._dss2_graph = g
         edge_index._dss2_graph_version = edge_index._version

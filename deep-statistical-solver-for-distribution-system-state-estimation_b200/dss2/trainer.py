@@ -69,7 +69,8 @@ class GraphedTrainer:
             # structure: one eager pack, then build once (uniform topology: identical for every batch)
             self.ids.copy_(torch.arange(self.B, device=self.dev) % store.num_scenarios)
             launch_pack(store, self.ids, self.batch, self.nt, self.et)
-            self.graph = BatchGraph(self.batch["edge_index"], self.nt, ptr=self.batch["ptr"], undirect=1)
+            from .ops import tile_cap
+            self.graph = BatchGraph(self.batch["edge_index"], self.nt, ptr=self.batch["ptr"], undirect=1, tile_cap=tile_cap())
             if self.graph.c.num_tiles == 0:
                 raise _lib.Dss2Error("GraphedTrainer: graphs exceed the shared-memory tile; large-graph path not built yet")
             self.wls_ws = self.graph.wls_workspace()

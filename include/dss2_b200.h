@@ -62,6 +62,8 @@ typedef struct dss2_graph {
   uint32_t* eid;            /* [nnz] original edge id | reversed << 31 */
   float* dis;               /* [Nt] in-degree^-1/2 on the doubled graph, 0 where degree is 0 */
   float* w;                 /* [nnz] gcn_norm weight of the entry: dis[src] * dis[dst] */
+  float* ell_w;             /* [Nt][4] weights of the first 4 entries of every row (0 = padding): thread-per-row kernels */
+  uint32_t* ell_ci;         /* [Nt][2] .x = 4 x 8-bit tile-local source rows of those entries, .y = row degree */
 } dss2_graph_t;
 
 /* Bytes of device workspace dss2_graph_build needs for (Nt, Et, B). */
@@ -139,6 +141,21 @@ int dss2_tag_fwd_tc(const dss2_graph_t* g, const float* x, const float* w, const
                     int act, float p_drop, int drop_mode, const uint64_t* rng_state, uint32_t layer_uid,
                     const uint8_t* mask, const float* res, int64_t res_stride,
                     float* y, uint32_t* act_bits, void* stream);
+/* Second-generation tensor-core layer kernels (thread-per-row CUDA-core stages, rotating level buffers, 2 CTAs/SM); need a graph
+ * built with tile_cap <= 128 and K <= 2.  Forward: same contract as dss2_tag_fwd.  Backward: same contract as dss2_tag_bwd plus a
+ * workspace of dss2_tag_bwd_tc2_workspace_bytes() for the hop levels of the masked output gradient; it runs the backward-to-input as
+ * the forward kernel with transposed weights (grad_x = sum_k (A^k g) W_k) and the weight gradients as one streaming MN-major GEMM
+ * (grad_W_k = (A^k g)^T x), with no hop recomputation on x. */
+int dss2_tag_tc2_supported(const dss2_graph_t* g, int K);
+int dss2_tag_fwd_tc2(const dss2_graph_t* g, const float* x, const float* w, const float* bias, int cout, int K,
+                     int act, float p_drop, int drop_mode, const uint64_t* rng_state, uint32_t layer_uid,
+                     const uint8_t* mask, const float* res, int64_t res_stride,
+                     float* y, uint32_t* act_bits, void* stream);
+size_t dss2_tag_bwd_tc2_workspace_bytes(int64_t num_nodes, int K);
+int dss2_tag_bwd_tc2(const dss2_graph_t* g, const float* x, const float* w, int cout, int K,
+                     int act, float p_drop, const uint32_t* act_bits, const float* grad_y,
+                     float* grad_x, float* partials, int64_t partial_stride, int64_t bias_offset,
+                     void* ws, size_t ws_bytes, void* stream);
 /* D[128,32] = A[128,32] * B[32,32]^T through the tensor-core operand / descriptor / TMEM path (bring-up and regression test). */
 int dss2_tc_selftest(const float* A, const float* B, float* D, void* stream);
 /* D[32*t + j, n] = sum_r A[t][r][j] * B[r][n], A = [4,64,32], B = [64,32]: MN-major TF32 operands (SWIZZLE_128B_BASE32B), the
