@@ -203,17 +203,25 @@ __global__ void __launch_bounds__(T2, 2) k_tag_tc2(Tc2Args a) {
       for (int c = 0; c < 32; ++c) xr[c] = ((word >> c) & 1u) ? xr[c] * a.scale : 0.0f;
     }
   };
+  RowTopo tp_next = tp;
+  auto load_topo = [&](int t) {
+    if (t >= g.num_tiles) return;
+    const TileRange r = tile_range(g, t);
+    if (tid < r.n1 - r.n0) tp_next = load_row_topo(g, (size_t)r.n0 + tid);
+  };
 
   load_row(blockIdx.x);
+  load_topo(blockIdx.x);
   for (int t = blockIdx.x; t < g.num_tiles; t += gridDim.x) {
     const TileRange r = tile_range(g, t);
     const int nT = r.n1 - r.n0;
     const bool live = tid < nT;
     const size_t n = (size_t)r.n0 + tid;
-    if (live) tp = load_row_topo(g, n);
+    tp = tp_next;
     // ---- level 0 ----
     store_row_sw128(xr, lv_hi(0), lv_lo(0), (uint32_t)tid);      // dead rows store zeros: keeps the MMA input finite
-    load_row(t + gridDim.x);                                     // prefetch the next tile's row into the same registers
+    load_row(t + gridDim.x);                                     // prefetch the next tile's row (same registers) and topology
+    load_topo(t + gridDim.x);
     fence_proxy_async();
     tc::fence_before_sync();
     __syncthreads();
@@ -348,12 +356,15 @@ struct GwArgs {
   int64_t bias_offset;
 };
 
+constexpr int GW_STAGES = 3;
+constexpr uint32_t GW_STAGE_BYTES = 4 * GW_TILE + 256;   // x, grad_y, A g, A^2 g rows + sign words of one 64-row chunk
+
 template <int K>
-__global__ void __launch_bounds__(128, 2) k_tag_gw(GwArgs a) {
+__global__ void __launch_bounds__(128, 1) k_tag_gw(GwArgs a) {
   extern __shared__ char raw[];
   char* base = align1024(raw);
   // A side (MN-major, M = 32*level + c): [hi: G_0..G_K, pad][lo: G_0..G_K, pad] each tile 8 KB, LBO = 8 KB; with K = 2 the M = 128
-  // extent covers 3 levels + 1 block that aliases the next tile (ignored rows 96..127)
+  // extent covers 3 levels + 1 zero block (rows 96..127 of D are ignored)
   char* Ah = base;
   char* Al = Ah + 4 * GW_TILE;
   // B side (MN-major, N = 48: 32 input features + the ones column): [x.hi][ones][x.lo][zeros]
@@ -361,30 +372,28 @@ __global__ void __launch_bounds__(128, 2) k_tag_gw(GwArgs a) {
   char* Bones = Bh + GW_TILE;
   char* Bl = Bones + GW_TILE;
   char* Bzero = Bl + GW_TILE;
-  char* tail = Bzero + GW_TILE;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(tail);
-  uint32_t* tslot = reinterpret_cast<uint32_t*>(tail + 16);
+  char* stage0 = Bzero + GW_TILE;                        // raw rows landed by the TMA engine, GW_STAGES deep
+  char* tail = stage0 + GW_STAGES * GW_STAGE_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(tail);    // [GW_STAGES] "chunk has landed"
+  uint64_t* bar = full + GW_STAGES;                      // "MMAs of the previous chunk have completed"
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(bar + 1);
   const int tid = threadIdx.x, warp = tid >> 5;
   const int row = tid & (GW_ROWS - 1), half = tid >> 6;   // two threads per chunk row: half 0 -> x and G_0, half 1 -> G_1, G_2
   const int cout = a.cout;
 
   if (warp == 0) tc::tmem_alloc(tslot, 64);
   if (tid == 0) {
+    for (int s = 0; s < GW_STAGES; ++s) mbar_init(&full[s], 1);
     mbar_init(bar, 1);
     fence_mbar_init();
   }
-  // constant tiles: ones column (feature 0 of the second N block) / zeros, and the unused 4th A block
-  for (int idx = tid; idx < GW_ROWS * 32; idx += 128) {
+  for (int idx = tid; idx < GW_ROWS * 32; idx += 128) {   // constant tiles
     const uint32_t r = idx >> 5, j = idx & 31;
     *reinterpret_cast<float*>(Bones + tc::swz32_off(r, j)) = j == 0 ? 1.0f : 0.0f;
     *reinterpret_cast<float*>(Bzero + tc::swz32_off(r, j)) = 0.0f;
-    if (K < 3) {
-      *reinterpret_cast<float*>(Ah + 3 * GW_TILE + tc::swz32_off(r, j)) = 0.0f;
-      *reinterpret_cast<float*>(Al + 3 * GW_TILE + tc::swz32_off(r, j)) = 0.0f;
-      if (K < 2) {
-        *reinterpret_cast<float*>(Ah + 2 * GW_TILE + tc::swz32_off(r, j)) = 0.0f;
-        *reinterpret_cast<float*>(Al + 2 * GW_TILE + tc::swz32_off(r, j)) = 0.0f;
-      }
+    for (int blk = K + 1; blk < 4; ++blk) {
+      *reinterpret_cast<float*>(Ah + blk * GW_TILE + tc::swz32_off(r, j)) = 0.0f;
+      *reinterpret_cast<float*>(Al + blk * GW_TILE + tc::swz32_off(r, j)) = 0.0f;
     }
   }
   fence_proxy_async();
@@ -393,56 +402,26 @@ __global__ void __launch_bounds__(128, 2) k_tag_gw(GwArgs a) {
   tc::fence_after_sync();
   const uint32_t tmem = *tslot;
   const uint32_t idesc = tc::idesc_tf32(128, 48, 1, 1);
-  uint32_t par = 0;
 
   const int64_t num_chunks = (a.num_nodes + GW_ROWS - 1) / GW_ROWS;
-  float r0[32], r1[32];   // half 0: x row, masked grad row.  half 1: level-1 row, level-2 row
-  auto load_chunk = [&](int64_t ch) {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) r0[i] = r1[i] = 0.0f;
-    const int64_t n = ch * GW_ROWS + row;
-    if (ch >= num_chunks || n >= a.num_nodes) return;
-    const float* p0 = half == 0 ? a.x + n * 32 : a.lvl + n * 32;
-    const float* p1 = half == 0 ? nullptr : (K >= 2 ? a.lvl + (a.num_nodes + n) * 32 : nullptr);
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const float4 v = ldg_stream4(reinterpret_cast<const float4*>(p0) + q);
-      r0[4 * q] = v.x;
-      r0[4 * q + 1] = v.y;
-      r0[4 * q + 2] = v.z;
-      r0[4 * q + 3] = v.w;
-    }
-    if (half == 0) {
-      if (cout == 32) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 v = ldg_stream4(reinterpret_cast<const float4*>(a.gy + n * 32) + q);
-          r1[4 * q] = v.x;
-          r1[4 * q + 1] = v.y;
-          r1[4 * q + 2] = v.z;
-          r1[4 * q + 3] = v.w;
-        }
-      } else {
-#pragma unroll
-        for (int c = 0; c < 32; ++c)
-          if (c < cout) r1[c] = a.gy[n * cout + c];
-      }
-      if (a.bits) {
-        const uint32_t word = a.bits[n];
-#pragma unroll
-        for (int c = 0; c < 32; ++c) r1[c] = ((word >> c) & 1u) ? r1[c] * a.scale : 0.0f;
-      }
-    } else if (p1) {
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float4 v = ldg_stream4(reinterpret_cast<const float4*>(p1) + q);
-        r1[4 * q] = v.x;
-        r1[4 * q + 1] = v.y;
-        r1[4 * q + 2] = v.z;
-        r1[4 * q + 3] = v.w;
-      }
-    }
+  const int64_t full_chunks = a.num_nodes / GW_ROWS;       // only whole chunks go through the bulk-copy engine
+  const uint32_t gy_bytes = (uint32_t)(GW_ROWS * cout * 4);
+  const uint32_t tx = GW_TILE * (K >= 2 ? 3 : 2) + gy_bytes + (a.bits ? 256u : 0u);
+  // producer (thread 0): land chunk `ch` in stage `s`
+  auto issue = [&](int64_t ch, int s) {
+    if (ch >= full_chunks) return;
+    char* st = stage0 + (size_t)s * GW_STAGE_BYTES;
+    const int64_t n = ch * GW_ROWS;
+    mbar_expect_tx(&full[s], tx);
+    bulk_g2s(st, a.x + n * 32, GW_TILE, &full[s]);
+    bulk_g2s(st + GW_TILE, a.gy + n * cout, gy_bytes, &full[s]);
+    bulk_g2s(st + 2 * GW_TILE, a.lvl + n * 32, GW_TILE, &full[s]);
+    if (K >= 2) bulk_g2s(st + 3 * GW_TILE, a.lvl + (a.num_nodes + n) * 32, GW_TILE, &full[s]);
+    if (a.bits) bulk_g2s(st + 4 * GW_TILE, a.bits + n, 256, &full[s]);
   };
+  if (tid == 0)
+    for (int i = 0; i < GW_STAGES; ++i) issue(blockIdx.x + (int64_t)i * gridDim.x, i);
+
   auto store_row32 = [&](const float (&v)[32], char* hi, char* lo) {
 #pragma unroll
     for (uint32_t q = 0; q < 8; ++q)
@@ -450,9 +429,77 @@ __global__ void __launch_bounds__(128, 2) k_tag_gw(GwArgs a) {
   };
 
   bool first = true;
-  load_chunk(blockIdx.x);
-  for (int64_t ch = blockIdx.x; ch < num_chunks; ch += gridDim.x) {
-    if (!first) {   // the previous chunk's MMAs still read the tiles
+  uint32_t par = 0;
+  int it = 0;
+  for (int64_t ch = blockIdx.x; ch < num_chunks; ch += gridDim.x, ++it) {
+    const int s = it % GW_STAGES;
+    float r0[32], r1[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) r0[i] = r1[i] = 0.0f;
+    uint32_t word = 0xffffffffu;
+    if (ch < full_chunks) {
+      mbar_wait(&full[s], (uint32_t)((it / GW_STAGES) & 1));
+      const char* st = stage0 + (size_t)s * GW_STAGE_BYTES;
+      const float4* p0 = reinterpret_cast<const float4*>(st + (half == 0 ? 0 : 2 * GW_TILE)) + row * 8;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 v = p0[q];
+        r0[4 * q] = v.x;
+        r0[4 * q + 1] = v.y;
+        r0[4 * q + 2] = v.z;
+        r0[4 * q + 3] = v.w;
+      }
+      if (half == 0) {
+        const float* gp = reinterpret_cast<const float*>(st + GW_TILE) + row * cout;
+        if (cout == 32) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 v = reinterpret_cast<const float4*>(gp)[q];
+            r1[4 * q] = v.x;
+            r1[4 * q + 1] = v.y;
+            r1[4 * q + 2] = v.z;
+            r1[4 * q + 3] = v.w;
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if (c < cout) r1[c] = gp[c];
+        }
+        if (a.bits) word = reinterpret_cast<const uint32_t*>(st + 4 * GW_TILE)[row];
+      } else if (K >= 2) {
+        const float4* p1 = reinterpret_cast<const float4*>(st + 3 * GW_TILE) + row * 8;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 v = p1[q];
+          r1[4 * q] = v.x;
+          r1[4 * q + 1] = v.y;
+          r1[4 * q + 2] = v.z;
+          r1[4 * q + 3] = v.w;
+        }
+      }
+    } else {   // the one ragged chunk at the end of the batch: plain bounded loads
+      const int64_t n = ch * GW_ROWS + row;
+      if (n < a.num_nodes) {
+        const float* p0 = half == 0 ? a.x + n * 32 : a.lvl + n * 32;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) r0[c] = p0[c];
+        if (half == 0) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if (c < cout) r1[c] = a.gy[n * cout + c];
+          if (a.bits) word = a.bits[n];
+        } else if (K >= 2) {
+          const float* p1 = a.lvl + (a.num_nodes + n) * 32;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) r1[c] = p1[c];
+        }
+      }
+    }
+    if (half == 0 && a.bits) {
+#pragma unroll
+      for (int c = 0; c < 32; ++c) r1[c] = ((word >> c) & 1u) ? r1[c] * a.scale : 0.0f;
+    }
+    if (!first) {   // the previous chunk's MMAs still read the operand tiles
       mbar_wait(bar, par);
       par ^= 1u;
     }
@@ -463,10 +510,9 @@ __global__ void __launch_bounds__(128, 2) k_tag_gw(GwArgs a) {
       store_row32(r0, Ah + GW_TILE, Al + GW_TILE);     // G_1
       if (K >= 2) store_row32(r1, Ah + 2 * GW_TILE, Al + 2 * GW_TILE);   // G_2
     }
-    load_chunk(ch + gridDim.x);
     fence_proxy_async();
     tc::fence_before_sync();
-    __syncthreads();
+    __syncthreads();          // operand tiles complete; staging slot s has been consumed by every thread
     if (tid == 0) {
       tc::fence_after_sync();
 #pragma unroll
@@ -479,6 +525,7 @@ __global__ void __launch_bounds__(128, 2) k_tag_gw(GwArgs a) {
         tc::mma_tf32(tmem, tc::smem_desc_mn32(smem_u32(Ah) + o, GW_TILE), tc::smem_desc_mn32(smem_u32(Bh) + o, GW_TILE), idesc, 1u);
       }
       tc::mma_commit(bar);
+      issue(ch + (int64_t)GW_STAGES * gridDim.x, s);   // refill the slot that was just drained
     }
     first = false;
   }
@@ -510,7 +557,7 @@ __global__ void __launch_bounds__(128, 2) k_tag_gw(GwArgs a) {
 }
 
 size_t tc2_smem(int K) { return 1024 + (size_t)(K + 1) * 2 * W_TILE + 4 * LV_TILE + 256; }
-size_t gw_smem() { return 1024 + 12 * GW_TILE + 64; }
+size_t gw_smem() { return 1024 + 12 * GW_TILE + GW_STAGES * GW_STAGE_BYTES + 128; }
 
 int tc2_supported(const dss2_graph_t* g, int K) {
   return g && g->num_tiles > 0 && g->max_tile_nodes <= T2 && K >= 1 && K <= 2 && g->ell_w && g->ell_ci;
@@ -580,6 +627,8 @@ extern "C" int dss2_tag_bwd_tc2(const dss2_graph_t* g, const float* x, const flo
   DSS2_CHECK_ARG(!act || act_bits, "dss2_tag_bwd_tc2: activation layers need act_bits from the forward");
   DSS2_CHECK_ARG(ws_bytes >= dss2_tag_bwd_tc2_workspace_bytes(g->num_nodes, K), "dss2_tag_bwd_tc2: workspace too small");
   DSS2_CHECK_ARG(partial_stride >= (int64_t)(K + 1) * cout * HID + cout, "dss2_tag_bwd_tc2: partial_stride too small");
+  DSS2_CHECK_ARG((((uintptr_t)x | (uintptr_t)grad_y | (uintptr_t)ws | (uintptr_t)act_bits | (uintptr_t)grad_x | (uintptr_t)partials) & 15) == 0,
+                 "dss2_tag_bwd_tc2: x, grad_y, grad_x, act_bits, partials and ws must be 16-byte aligned (bulk-copy / 128-bit access)");
   if (g->num_nodes == 0) return 0;
   const float scale = 1.0f / (float)(1.0 - (double)p_drop);
   Tc2Args a = {};

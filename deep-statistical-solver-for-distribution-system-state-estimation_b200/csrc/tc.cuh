@@ -26,11 +26,10 @@ __device__ __forceinline__ uint32_t swz_off(uint32_t row, uint32_t j) {
 // same, as "row code" ^ (4*j): code = row*128 | (row&7)<<4
 __device__ __forceinline__ uint32_t row_code(uint32_t row) { return (row << 7) | ((row & 7u) << 4); }
 
-__device__ __forceinline__ float tf32_rna(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
+// round-to-nearest (ties away from zero) to TF32 = add half a TF32 ulp to the magnitude and truncate.  cvt.rna.tf32.f32 does the same
+// plus NaN/Inf special-casing, which ptxas expands to ~5 instructions on sm_100a (ncu: LOP3/FSETP/SEL made up 40% of the kernel);
+// activations and weights here are finite, so the two-instruction integer form is used.
+__device__ __forceinline__ float tf32_rna(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
 
 // shared-memory matrix descriptor: K-major, SWIZZLE_128B, version 1 (Blackwell)
 __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr) {

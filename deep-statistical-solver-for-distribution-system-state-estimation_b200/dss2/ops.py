@@ -105,7 +105,8 @@ class PFNRunner:
         f32 = dict(dtype=torch.float32, device=device)
         b = {
             "acts": torch.empty(sp.L, sp.n_layers, num_nodes, HID, **f32),    # [s][l] = input of TAG layer l
-            "bits": torch.empty(sp.L, max(sp.n_layers - 1, 1), num_nodes, dtype=torch.int32, device=device),
+            # one sign word per node; rows padded to 64 words so every [s, l] slice starts 256-byte aligned (bulk-copy source)
+            "bits": torch.empty(sp.L, max(sp.n_layers - 1, 1), (num_nodes + 63) // 64 * 64, dtype=torch.int32, device=device),
             "outs": [torch.empty(num_nodes, sp.out_dim(s), **f32) for s in range(sp.L)],
         }
         if need_grad:

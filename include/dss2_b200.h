@@ -145,7 +145,7 @@ int dss2_tag_fwd_tc(const dss2_graph_t* g, const float* x, const float* w, const
  * built with tile_cap <= 128 and K <= 2.  Forward: same contract as dss2_tag_fwd.  Backward: same contract as dss2_tag_bwd plus a
  * workspace of dss2_tag_bwd_tc2_workspace_bytes() for the hop levels of the masked output gradient; it runs the backward-to-input as
  * the forward kernel with transposed weights (grad_x = sum_k (A^k g) W_k) and the weight gradients as one streaming MN-major GEMM
- * (grad_W_k = (A^k g)^T x), with no hop recomputation on x. */
+ * (grad_W_k = (A^k g)^T x), with no hop recomputation on x.  Pointers must be 16-byte aligned (TMA bulk copies, 128-bit accesses). */
 int dss2_tag_tc2_supported(const dss2_graph_t* g, int K);
 int dss2_tag_fwd_tc2(const dss2_graph_t* g, const float* x, const float* w, const float* bias, int cout, int K,
                      int act, float p_drop, int drop_mode, const uint64_t* rng_state, uint32_t layer_uid,

@@ -633,7 +633,8 @@ def _tie_aware_model_check(env, tag, impl):
         if loss_i is not None:
             assert_fp32_parity(loss_i, z["loss"], l64, f"loss ({impl})")
         nl = ctor["n_gnn_layers"] - 1
-        differ = (b_cc["bits"][:, :nl] != b_i["bits"][:, :nl]).nonzero().tolist() if nl > 0 else []
+        nn_ = x.size(0)
+        differ = (b_cc["bits"][:, :nl, :nn_] != b_i["bits"][:, :nl, :nn_]).nonzero().tolist() if nl > 0 else []
         for s_, l_, n_ in differ:
             wa, wb = int(b_cc["bits"][s_, l_, n_]) & 0xFFFFFFFF, int(b_i["bits"][s_, l_, n_]) & 0xFFFFFFFF
             for c in range(32):
