@@ -68,25 +68,30 @@ __device__ __forceinline__ uint32_t keep_word(uint2 key, uint32_t tile, uint32_t
   return word;
 }
 
-// this thread's row (32 fp32 in registers) -> hi / lo operand tiles, K-major SWIZZLE_128B
-__device__ __forceinline__ void store_row_sw128(const float (&v)[32], char* hi, char* lo, uint32_t row) {
+// Thread mapping of the layer kernel: 256 threads per tile, thread = (row, half): row = tid & 127 (= its TMEM lane), half = tid >> 7
+// owns features [16*half, 16*half + 16).  Two threads per row double the number of busy warps on grids whose tile holds a single
+// graph (Oberrhein: 70 of 128 rows) and halve every per-thread dependency chain.
+constexpr int TC2_WORKERS = 256;                 // 8 worker warps
+constexpr int TC2_THREADS = TC2_WORKERS + 32;    // + 1 issuer warp (one elected lane issues every tcgen05.mma)
+constexpr int HF = 16;
+
+__device__ __forceinline__ void store_half_sw128(const float (&v)[HF], char* pt, char* lt, uint32_t row, uint32_t half) {
   const uint32_t code = tc::row_code(row);
 #pragma unroll
-  for (uint32_t q = 0; q < 8; ++q)
-    tc::split_store4(make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]), hi, lo, code ^ (q << 4));
+  for (uint32_t q = 0; q < 4; ++q)
+    tc::plain_store4(make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]), pt, lt, code ^ ((half * 4 + q) << 4));
 }
 
-// h += w * (hi + lo)[src row]: one neighbour, whole row
-__device__ __forceinline__ void gather_row(float (&h)[32], const char* hi, const char* lo, uint32_t src, float w) {
+// h += w * plain[src row][16*half ...]: one neighbour, exact fp32 values from the plain tile
+__device__ __forceinline__ void gather_half(float (&h)[HF], const char* pt, uint32_t src, float w, uint32_t half) {
   const uint32_t code = tc::row_code(src);
 #pragma unroll
-  for (uint32_t q = 0; q < 8; ++q) {
-    const float4 a = *reinterpret_cast<const float4*>(hi + (code ^ (q << 4)));
-    const float4 b = *reinterpret_cast<const float4*>(lo + (code ^ (q << 4)));
-    h[4 * q + 0] = fmaf(w, a.x + b.x, h[4 * q + 0]);
-    h[4 * q + 1] = fmaf(w, a.y + b.y, h[4 * q + 1]);
-    h[4 * q + 2] = fmaf(w, a.z + b.z, h[4 * q + 2]);
-    h[4 * q + 3] = fmaf(w, a.w + b.w, h[4 * q + 3]);
+  for (uint32_t q = 0; q < 4; ++q) {
+    const float4 a = *reinterpret_cast<const float4*>(pt + (code ^ ((half * 4 + q) << 4)));
+    h[4 * q + 0] = fmaf(w, a.x, h[4 * q + 0]);
+    h[4 * q + 1] = fmaf(w, a.y, h[4 * q + 1]);
+    h[4 * q + 2] = fmaf(w, a.z, h[4 * q + 2]);
+    h[4 * q + 3] = fmaf(w, a.w, h[4 * q + 3]);
   }
 }
 
@@ -104,54 +109,88 @@ __device__ __forceinline__ RowTopo load_row_topo(const dss2_graph_t& g, size_t n
   return t;
 }
 
-// one hop for this thread's row: entries in CSR order = PyG scatter order
-__device__ __forceinline__ void hop_thread(float (&h)[32], const dss2_graph_t& g, const RowTopo& tp, const char* hi, const char* lo, size_t n,
-                                           int n0) {
+// one hop for this thread's half row: entries in CSR order = PyG scatter order
+__device__ __forceinline__ void hop_thread(float (&h)[HF], const dss2_graph_t& g, const RowTopo& tp, const char* pt, size_t n, int n0,
+                                           uint32_t half) {
 #pragma unroll
-  for (int i = 0; i < 32; ++i) h[i] = 0.0f;
+  for (int i = 0; i < HF; ++i) h[i] = 0.0f;
   const float wv[4] = {tp.w.x, tp.w.y, tp.w.z, tp.w.w};
 #pragma unroll
   for (uint32_t d = 0; d < 4; ++d)
-    if (d < tp.deg) gather_row(h, hi, lo, (tp.cols >> (8 * d)) & 0xffu, wv[d]);
+    if (d < tp.deg) gather_half(h, pt, (tp.cols >> (8 * d)) & 0xffu, wv[d], half);
   if (tp.deg > 4) {   // rare: hub nodes
     const int beg = g.rowptr[n];
-    for (int z = beg + 4; z < beg + (int)tp.deg; ++z) gather_row(h, hi, lo, (uint32_t)(g.col[z] - n0), g.w[z]);
+    for (int z = beg + 4; z < beg + (int)tp.deg; ++z) gather_half(h, pt, (uint32_t)(g.col[z] - n0), g.w[z], half);
   }
 }
 
+// 16 Bernoulli(keep) decisions: features [16*half, 16*half+16) of one node row
+__device__ __forceinline__ uint32_t keep_half(uint2 key, uint32_t tile, uint32_t row, uint32_t half, uint32_t step_lo, uint32_t thr16) {
+  uint32_t word = 0;
+#pragma unroll
+  for (uint32_t q = 0; q < 2; ++q) {
+    const uint4 r = philox4x32_10(make_uint4(tile, row, half * 2 + q, step_lo), key);
+    const uint32_t u[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (uint32_t i = 0; i < 4; ++i) {
+      word |= ((u[i] & 0xffffu) < thr16 ? 1u : 0u) << (q * 8 + 2 * i);
+      word |= ((u[i] >> 16) < thr16 ? 1u : 0u) << (q * 8 + 2 * i + 1);
+    }
+  }
+  return word;
+}
+
+struct TileNodes {
+  int n0, n1;
+};
+__device__ __forceinline__ TileNodes tile_nodes(const dss2_graph_t& g, int t) {
+  TileNodes r;
+  r.n0 = r.n1 = 0;
+  if (t < g.num_tiles) {
+    const int g0 = t * g.graphs_per_tile, g1 = min(g0 + g.graphs_per_tile, g.num_graphs);
+    r.n0 = (int)g.ptr[g0];
+    r.n1 = (int)g.ptr[g1];
+  }
+  return r;
+}
+
 template <int MODE, int K>
-__global__ void __launch_bounds__(T2, 2) k_tag_tc2(Tc2Args a) {
+__global__ void __launch_bounds__(TC2_THREADS, 2) k_tag_tc2(Tc2Args a) {
   extern __shared__ char raw[];
   const dss2_graph_t& g = a.g;
   char* base = align1024(raw);
-  char* Wt = base;                                  // [(K+1)][hi,lo] x 4 KB weight operand tiles
-  char* Lv = Wt + (K + 1) * 2 * W_TILE;             // [2 buffers][hi,lo] x 16 KB level tiles
+  char* Wt = base;                                  // [(K+1)] x 8 KB: rows 0-31 plain W_k, rows 32-63 residual -> one N = 64 operand
+  char* Lv = Wt + (K + 1) * 2 * W_TILE;             // [2 buffers][plain, residual] x 16 KB level tiles
   char* tail = Lv + 4 * LV_TILE;
   float* bias_s = reinterpret_cast<float*>(tail);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 128);   // [2]: "MMAs reading buffer b have completed"
-  uint32_t* tslot = reinterpret_cast<uint32_t*>(tail + 144);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 128);   // [2]: "MMAs reading buffer b have completed"   (tcgen05.commit)
+  uint64_t* full = bars + 2;                                  // [2]: "all workers have written buffer b"       (256 arrivals)
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(full + 2);
   const int tid = threadIdx.x, warp = tid >> 5;
+  const bool issuer = warp == TC2_WORKERS / 32;
+  const uint32_t row = tid & 127, half = (tid >> 7) & 1;
   const int cout = a.cout;
-  auto lv_hi = [&](int b) { return Lv + (size_t)(2 * b) * LV_TILE; };
-  auto lv_lo = [&](int b) { return Lv + (size_t)(2 * b + 1) * LV_TILE; };
+  auto lv_p = [&](int b) { return Lv + (size_t)(2 * b) * LV_TILE; };
+  auto lv_l = [&](int b) { return Lv + (size_t)(2 * b + 1) * LV_TILE; };
 
   // ---- one-time setup ----
-  if (warp == 0) tc::tmem_alloc(tslot, 32);
+  if (warp == 0) tc::tmem_alloc(tslot, 64);
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
+    mbar_init(&full[0], TC2_WORKERS);
+    mbar_init(&full[1], TC2_WORKERS);
     fence_mbar_init();
   }
   // weight operand B[n][kk] (K-major rows n): FWD n = output feature c, kk = input feature j: W_k[c][j];
   //                                           BGX n = input feature j, kk = output feature c: W_k[c][j] transposed
-  for (int idx = tid; idx < (K + 1) * 32 * 32; idx += T2) {
+  for (int idx = tid; idx < (K + 1) * 32 * 32; idx += TC2_THREADS) {
     const int k = idx >> 10, nrow = (idx >> 5) & 31, kk = idx & 31;
     const int c = MODE == MODE_FWD ? nrow : kk, j = MODE == MODE_FWD ? kk : nrow;
     const float v = c < cout ? a.w[((size_t)k * cout + c) * HID + j] : 0.0f;
-    const float hi = tc::tf32_rna(v);
     const uint32_t off = tc::swz_off((uint32_t)nrow, (uint32_t)kk);
-    *reinterpret_cast<float*>(Wt + (size_t)(2 * k) * W_TILE + off) = hi;
-    *reinterpret_cast<float*>(Wt + (size_t)(2 * k + 1) * W_TILE + off) = tc::tf32_rna(v - hi);
+    *reinterpret_cast<float*>(Wt + (size_t)(2 * k) * W_TILE + off) = v;
+    *reinterpret_cast<float*>(Wt + (size_t)(2 * k + 1) * W_TILE + off) = tc::tf32_residual(v);
   }
   if (tid < 32) bias_s[tid] = (MODE == MODE_FWD && tid < cout) ? a.bias[tid] : 0.0f;
   uint2 key = make_uint2(0u, 0u);
@@ -166,175 +205,191 @@ __global__ void __launch_bounds__(T2, 2) k_tag_tc2(Tc2Args a) {
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = *tslot;
-  const uint32_t idesc = tc::idesc_tf32(128, 32);
-  uint32_t par[2] = {0u, 0u};
 
-  // row loader: this thread's input row of tile t (zero padded), FWD: x row; BGX: masked grad_y row
-  float xr[32];
-  RowTopo tp;
-  tp.deg = 0;
-  tp.cols = 0;
-  tp.w = make_float4(0.f, 0.f, 0.f, 0.f);
-  auto load_row = [&](int t) {
+  if (issuer) {
+    // ===== MMA issuer warp: D[:, 0:32] += A W_plain^T, D[:, 32:64] += A W_resid^T for A in {plain, residual} of every level =====
+    const uint32_t idesc = tc::idesc_tf32(128, 64);
+    uint32_t fpar[2] = {0u, 0u};
+    for (int t = blockIdx.x; t < g.num_tiles; t += gridDim.x) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) xr[i] = 0.0f;
-    if (t >= g.num_tiles) return;
-    const TileRange r = tile_range(g, t);
-    if (tid >= r.n1 - r.n0) return;
-    const size_t n = (size_t)r.n0 + tid;
-    if (MODE == MODE_FWD || cout == 32) {
-      const float4* src = reinterpret_cast<const float4*>(a.in + n * 32);
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float4 v = ldg_stream4(src + q);
-        xr[4 * q] = v.x;
-        xr[4 * q + 1] = v.y;
-        xr[4 * q + 2] = v.z;
-        xr[4 * q + 3] = v.w;
-      }
-    } else {
-#pragma unroll
-      for (int c = 0; c < 32; ++c)
-        if (c < cout) xr[c] = a.in[n * cout + c];
-    }
-    if (MODE == MODE_BGX && a.in_bits) {
-      const uint32_t word = a.in_bits[n];
-#pragma unroll
-      for (int c = 0; c < 32; ++c) xr[c] = ((word >> c) & 1u) ? xr[c] * a.scale : 0.0f;
-    }
-  };
-  RowTopo tp_next = tp;
-  auto load_topo = [&](int t) {
-    if (t >= g.num_tiles) return;
-    const TileRange r = tile_range(g, t);
-    if (tid < r.n1 - r.n0) tp_next = load_row_topo(g, (size_t)r.n0 + tid);
-  };
-
-  load_row(blockIdx.x);
-  load_topo(blockIdx.x);
-  for (int t = blockIdx.x; t < g.num_tiles; t += gridDim.x) {
-    const TileRange r = tile_range(g, t);
-    const int nT = r.n1 - r.n0;
-    const bool live = tid < nT;
-    const size_t n = (size_t)r.n0 + tid;
-    tp = tp_next;
-    // ---- level 0 ----
-    store_row_sw128(xr, lv_hi(0), lv_lo(0), (uint32_t)tid);      // dead rows store zeros: keeps the MMA input finite
-    load_row(t + gridDim.x);                                     // prefetch the next tile's row (same registers) and topology
-    load_topo(t + gridDim.x);
-    fence_proxy_async();
-    tc::fence_before_sync();
-    __syncthreads();
-    if (tid == 0) {
-      tc::fence_after_sync();
-      tc::issue_block(tmem, smem_u32(lv_hi(0)), smem_u32(lv_lo(0)), smem_u32(Wt), smem_u32(Wt + W_TILE), idesc, true);
-      tc::mma_commit(&bars[0]);
-    }
-    // ---- levels 1..K ----
-#pragma unroll
-    for (int k = 1; k <= K; ++k) {
-      const int b = k & 1, pb = (k - 1) & 1;
-      float h[32];
-      if (live) hop_thread(h, g, tp, lv_hi(pb), lv_lo(pb), n, r.n0);
-      else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) h[i] = 0.0f;
-      }
-      if (k >= 2) {   // buffer b still feeds the MMAs of level k-2
-        mbar_wait(&bars[b], par[b]);
-        par[b] ^= 1u;
-      }
-      store_row_sw128(h, lv_hi(b), lv_lo(b), (uint32_t)tid);
-      if (MODE == MODE_BGX && a.lvl_out && live) {
-        float4* dst = reinterpret_cast<float4*>(a.lvl_out + ((size_t)(k - 1) * g.num_nodes + n) * 32);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) dst[q] = make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
-      }
-      fence_proxy_async();
-      tc::fence_before_sync();
-      __syncthreads();
-      if (tid == 0) {
+      for (int k = 0; k <= K; ++k) {
+        const int b = k & 1;
+        mbar_wait(&full[b], fpar[b]);
+        fpar[b] ^= 1u;
         tc::fence_after_sync();
-        tc::issue_block(tmem, smem_u32(lv_hi(b)), smem_u32(lv_lo(b)), smem_u32(Wt + (size_t)(2 * k) * W_TILE),
-                        smem_u32(Wt + (size_t)(2 * k + 1) * W_TILE), idesc, false);
-        tc::mma_commit(&bars[b]);
+        if ((tid & 31) == 0) {
+          const uint64_t dP = tc::smem_desc_sw128(smem_u32(lv_p(b))), dL = tc::smem_desc_sw128(smem_u32(lv_l(b)));
+          const uint64_t dW = tc::smem_desc_sw128(smem_u32(Wt + (size_t)(2 * k) * W_TILE));
+#pragma unroll
+          for (uint32_t kk = 0; kk < 4; ++kk) {
+            const uint32_t o = kk * tc::KSTEP_BYTES;
+            tc::mma_tf32(tmem, tc::desc_advance(dL, o), tc::desc_advance(dW, o), idesc, (k == 0 && kk == 0) ? 0u : 1u);
+            tc::mma_tf32(tmem, tc::desc_advance(dP, o), tc::desc_advance(dW, o), idesc, 1u);
+          }
+          tc::mma_commit(&bars[b]);
+        }
+        __syncwarp();
       }
     }
-    // ---- all MMAs of the tile complete when the last two commits have arrived ----
-    if (K >= 1) {
-      const int b2 = (K - 1) & 1;
-      mbar_wait(&bars[b2], par[b2]);
-      par[b2] ^= 1u;
-    }
-    {
-      const int b1 = K & 1;
-      mbar_wait(&bars[b1], par[b1]);
-      par[b1] ^= 1u;
-    }
-    tc::fence_after_sync();
-    float v[32];
-    tc::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16), v);
-    if (live) {
-      if (MODE == MODE_FWD) {
+  } else {
+    // ===== worker warps: thread = (row, half) =====
+    uint32_t par[2] = {0u, 0u};
+    // software pipeline over this CTA's tiles: node range two tiles ahead, rows + topology one tile ahead (all in registers)
+    float xr[HF];
+    RowTopo tp_next;
+    tp_next.deg = 0;
+    tp_next.cols = 0;
+    tp_next.w = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto load_row = [&](const TileNodes& tn) {   // this thread's half row of the tile, zero padded; BGX: masked grad_y
 #pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) {
-          const float4 bq = *reinterpret_cast<const float4*>(bias_s + 4 * c4);
-          v[4 * c4 + 0] += bq.x;
-          v[4 * c4 + 1] += bq.y;
-          v[4 * c4 + 2] += bq.z;
-          v[4 * c4 + 3] += bq.w;
+      for (int i = 0; i < HF; ++i) xr[i] = 0.0f;
+      if ((int)row >= tn.n1 - tn.n0) return;
+      const size_t n = (size_t)tn.n0 + row;
+      tp_next = load_row_topo(g, n);
+      if (MODE == MODE_FWD || cout == 32) {
+        const float4* src = reinterpret_cast<const float4*>(a.in + n * 32 + half * HF);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 v = ldg_stream4(src + q);
+          xr[4 * q] = v.x;
+          xr[4 * q + 1] = v.y;
+          xr[4 * q + 2] = v.z;
+          xr[4 * q + 3] = v.w;
         }
-        if (a.act) {
-          uint32_t keep = 0xffffffffu;
-          if (a.drop_mode == 1) {
-            keep = keep_word(key, (uint32_t)t, (uint32_t)tid, step_lo, a.keep_thr16);
-          } else if (a.drop_mode == 2) {
-            const uint4* mp = reinterpret_cast<const uint4*>(a.mask + n * HID);
-            const uint4 m0 = mp[0], m1 = mp[1];
-            const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-            keep = 0u;
-#pragma unroll
-            for (int c = 0; c < 32; ++c) keep |= (((mw[c >> 2] >> ((c & 3) * 8)) & 0xffu) != 0u ? 1u : 0u) << c;
-          }
-          uint32_t word = 0u;
-#pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            float xv = v[c];
-            if (a.drop_mode != 0) xv = ((keep >> c) & 1u) ? xv * a.scale : 0.0f;
-            xv = fmaxf(xv, 0.0f);
-            word |= (xv > 0.0f ? 1u : 0u) << c;
-            v[c] = xv;
-          }
-          if (a.out_bits) a.out_bits[n] = word;
-        }
-        if (a.res) {
-#pragma unroll
-          for (int c = 0; c < 32; ++c)
-            if (c < cout) v[c] += a.res[n * a.res_stride + c];
-        }
-      }
-      const int ow = MODE == MODE_FWD ? cout : 32;
-      if (ow == 32) {
-        float4* dst = reinterpret_cast<float4*>(a.out + n * 32);
-#pragma unroll
-        for (int c4 = 0; c4 < 8; ++c4) dst[c4] = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
-      } else if (ow == 8) {
-        float4* dst = reinterpret_cast<float4*>(a.out + n * 8);
-        dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-        dst[1] = make_float4(v[4], v[5], v[6], v[7]);
-      } else if (ow == 2) {
-        *reinterpret_cast<float2*>(a.out + n * 2) = make_float2(v[0], v[1]);
       } else {
 #pragma unroll
-        for (int c = 0; c < 32; ++c)
-          if (c < ow) a.out[n * ow + c] = v[c];
+        for (int c = 0; c < HF; ++c)
+          if ((int)(half * HF) + c < cout) xr[c] = a.in[n * cout + half * HF + c];
+      }
+      if (MODE == MODE_BGX && a.in_bits) {
+        const uint32_t word = a.in_bits[n] >> (half * HF);
+#pragma unroll
+        for (int c = 0; c < HF; ++c) xr[c] = ((word >> c) & 1u) ? xr[c] * a.scale : 0.0f;
+      }
+    };
+    auto publish = [&](int b) {   // my part of buffer b is written: make it visible to the tensor core, tell the issuer, meet the workers
+      fence_proxy_async();
+      tc::mbar_arrive(&full[b]);
+      named_bar_sync(1, TC2_WORKERS);
+    };
+
+    TileNodes cur = tile_nodes(g, blockIdx.x);
+    TileNodes nxt = tile_nodes(g, blockIdx.x + gridDim.x);
+    load_row(cur);
+    for (int t = blockIdx.x; t < g.num_tiles; t += gridDim.x) {
+      const int nT = cur.n1 - cur.n0, n0 = cur.n0;
+      const bool live = (int)row < nT;
+      const size_t n = (size_t)n0 + row;
+      const RowTopo tp = tp_next;
+      // ---- level 0 (buffer 0 is free: the previous tile's epilogue waited for its last MMAs) ----
+      store_half_sw128(xr, lv_p(0), lv_l(0), row, half);          // dead rows store zeros: keeps the MMA input finite
+      cur = nxt;
+      load_row(cur);                                               // prefetch next tile: rows (same registers) + topology
+      nxt = tile_nodes(g, t + 2 * gridDim.x);                      // and the node range of the tile after it
+      publish(0);
+      // ---- levels 1..K ----
+#pragma unroll
+      for (int k = 1; k <= K; ++k) {
+        const int b = k & 1, pb = (k - 1) & 1;
+        float h[HF];
+        if (live) hop_thread(h, g, tp, lv_p(pb), n, n0, half);
+        else {
+#pragma unroll
+          for (int i = 0; i < HF; ++i) h[i] = 0.0f;
+        }
+        if (k >= 2) {   // buffer b still feeds the MMAs of level k-2
+          mbar_wait(&bars[b], par[b]);
+          par[b] ^= 1u;
+        }
+        store_half_sw128(h, lv_p(b), lv_l(b), row, half);
+        if (MODE == MODE_BGX && a.lvl_out && live) {
+          float4* dst = reinterpret_cast<float4*>(a.lvl_out + ((size_t)(k - 1) * g.num_nodes + n) * 32 + half * HF);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) dst[q] = make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
+        }
+        publish(b);
+      }
+      // ---- all MMAs of the tile complete when the last two commits have arrived ----
+      if (K >= 1) {
+        const int b2 = (K - 1) & 1;
+        mbar_wait(&bars[b2], par[b2]);
+        par[b2] ^= 1u;
+      }
+      {
+        const int b1 = K & 1;
+        mbar_wait(&bars[b1], par[b1]);
+        par[b1] ^= 1u;
+      }
+      tc::fence_after_sync();
+      float v[HF], v2[HF];
+      const uint32_t taddr = tmem + half * HF + ((uint32_t)((warp & 3) * 32) << 16);
+      tc::tmem_ld16(taddr, v);
+      tc::tmem_ld16(taddr + 32, v2);
+      tc::fence_before_sync();        // orders these TMEM reads before the next tile's "buffer written" arrival -> issuer -> overwrite of D
+#pragma unroll
+      for (int c = 0; c < HF; ++c) v[c] += v2[c];
+      if (live) {
+        if (MODE == MODE_FWD) {
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            const float4 bq = *reinterpret_cast<const float4*>(bias_s + half * HF + 4 * c4);
+            v[4 * c4 + 0] += bq.x;
+            v[4 * c4 + 1] += bq.y;
+            v[4 * c4 + 2] += bq.z;
+            v[4 * c4 + 3] += bq.w;
+          }
+          if (a.act) {
+            uint32_t keep = 0xffffu;
+            if (a.drop_mode == 1) {
+              keep = keep_half(key, (uint32_t)t, row, half, step_lo, a.keep_thr16);
+            } else if (a.drop_mode == 2) {
+              const uint4 m0 = *reinterpret_cast<const uint4*>(a.mask + n * HID + half * HF);
+              const uint32_t mw[4] = {m0.x, m0.y, m0.z, m0.w};
+              keep = 0u;
+#pragma unroll
+              for (int c = 0; c < HF; ++c) keep |= (((mw[c >> 2] >> ((c & 3) * 8)) & 0xffu) != 0u ? 1u : 0u) << c;
+            }
+            uint32_t word = 0u;
+#pragma unroll
+            for (int c = 0; c < HF; ++c) {
+              float xv = v[c];
+              if (a.drop_mode != 0) xv = ((keep >> c) & 1u) ? xv * a.scale : 0.0f;
+              xv = fmaxf(xv, 0.0f);
+              word |= (xv > 0.0f ? 1u : 0u) << c;
+              v[c] = xv;
+            }
+            if (a.out_bits) reinterpret_cast<uint16_t*>(a.out_bits)[2 * n + half] = (uint16_t)word;   // little endian halves
+          }
+          if (a.res) {
+#pragma unroll
+            for (int c = 0; c < HF; ++c)
+              if ((int)(half * HF) + c < cout) v[c] += a.res[n * a.res_stride + half * HF + c];
+          }
+        }
+        const int ow = MODE == MODE_FWD ? cout : 32;
+        if (ow == 32) {
+          float4* dst = reinterpret_cast<float4*>(a.out + n * 32 + half * HF);
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) dst[c4] = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+        } else if (ow == 8) {
+          if (half == 0) {
+            float4* dst = reinterpret_cast<float4*>(a.out + n * 8);
+            dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+            dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+          }
+        } else if (ow == 2) {
+          if (half == 0) *reinterpret_cast<float2*>(a.out + n * 2) = make_float2(v[0], v[1]);
+        } else {
+#pragma unroll
+          for (int c = 0; c < HF; ++c)
+            if ((int)(half * HF) + c < ow) a.out[n * ow + half * HF + c] = v[c];
+        }
       }
     }
-    tc::fence_before_sync();
-    __syncthreads();
-    tc::fence_after_sync();
   }
-  if (warp == 0) tc::tmem_dealloc(tmem, 32);
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 64);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -515,14 +570,15 @@ __global__ void __launch_bounds__(128, 1) k_tag_gw(GwArgs a) {
     __syncthreads();          // operand tiles complete; staging slot s has been consumed by every thread
     if (tid == 0) {
       tc::fence_after_sync();
+      const uint64_t dAh = tc::smem_desc_mn32(smem_u32(Ah), GW_TILE), dAl = tc::smem_desc_mn32(smem_u32(Al), GW_TILE);
+      const uint64_t dBh = tc::smem_desc_mn32(smem_u32(Bh), GW_TILE), dBl = tc::smem_desc_mn32(smem_u32(Bl), GW_TILE);
 #pragma unroll
       for (uint32_t ks = 0; ks < GW_ROWS / 8; ++ks) {
         const uint32_t o = ks * 1024;
-        tc::mma_tf32(tmem, tc::smem_desc_mn32(smem_u32(Al) + o, GW_TILE), tc::smem_desc_mn32(smem_u32(Bl) + o, GW_TILE), idesc,
-                     (first && ks == 0) ? 0u : 1u);
-        tc::mma_tf32(tmem, tc::smem_desc_mn32(smem_u32(Al) + o, GW_TILE), tc::smem_desc_mn32(smem_u32(Bh) + o, GW_TILE), idesc, 1u);
-        tc::mma_tf32(tmem, tc::smem_desc_mn32(smem_u32(Ah) + o, GW_TILE), tc::smem_desc_mn32(smem_u32(Bl) + o, GW_TILE), idesc, 1u);
-        tc::mma_tf32(tmem, tc::smem_desc_mn32(smem_u32(Ah) + o, GW_TILE), tc::smem_desc_mn32(smem_u32(Bh) + o, GW_TILE), idesc, 1u);
+        tc::mma_tf32(tmem, tc::desc_advance(dAl, o), tc::desc_advance(dBl, o), idesc, (first && ks == 0) ? 0u : 1u);
+        tc::mma_tf32(tmem, tc::desc_advance(dAl, o), tc::desc_advance(dBh, o), idesc, 1u);
+        tc::mma_tf32(tmem, tc::desc_advance(dAh, o), tc::desc_advance(dBl, o), idesc, 1u);
+        tc::mma_tf32(tmem, tc::desc_advance(dAh, o), tc::desc_advance(dBh, o), idesc, 1u);
       }
       tc::mma_commit(bar);
       issue(ch + (int64_t)GW_STAGES * gridDim.x, s);   // refill the slot that was just drained
@@ -556,7 +612,7 @@ __global__ void __launch_bounds__(128, 1) k_tag_gw(GwArgs a) {
   if (warp == 0) tc::tmem_dealloc(tmem, 64);
 }
 
-size_t tc2_smem(int K) { return 1024 + (size_t)(K + 1) * 2 * W_TILE + 4 * LV_TILE + 256; }
+size_t tc2_smem(int K) { return 1024 + (size_t)(K + 1) * 2 * W_TILE + 4 * LV_TILE + 256; }   // ~89 KB: two CTAs per SM
 size_t gw_smem() { return 1024 + 12 * GW_TILE + GW_STAGES * GW_STAGE_BYTES + 128; }
 
 int tc2_supported(const dss2_graph_t* g, int K) {
@@ -569,10 +625,10 @@ int launch_tc2(const Tc2Args& a, int K, cudaStream_t stream) {
   const int grid = max(1, min(a.g.num_tiles, 2 * dss2_sm_count()));
   if (K == 1) {
     DSS2_CUDA(cudaFuncSetAttribute(k_tag_tc2<MODE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_tag_tc2<MODE, 1><<<grid, T2, smem, stream>>>(a);
+    k_tag_tc2<MODE, 1><<<grid, TC2_THREADS, smem, stream>>>(a);
   } else {
     DSS2_CUDA(cudaFuncSetAttribute(k_tag_tc2<MODE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_tag_tc2<MODE, 2><<<grid, T2, smem, stream>>>(a);
+    k_tag_tc2<MODE, 2><<<grid, TC2_THREADS, smem, stream>>>(a);
   }
   DSS2_LAUNCH_CHECK();
   return 0;

@@ -153,6 +153,52 @@ __device__ __forceinline__ void split_store4(const float4 v, char* hi_tile, char
   *reinterpret_cast<float4*>(lo_tile + off) = l;
 }
 
+// ---- "plain + residual" operand pair ----
+// The tensor core reads only the top 19 bits of an fp32 word (TF32 = truncation), so the PLAIN fp32 tile can serve as the high
+// operand: hi = trunc_tf32(x) implicitly.  The residual tile holds lo = rna_tf32(x - trunc_tf32(x)) (|lo| < 2^-10 |x|, rounded to 11
+// bits: unbiased error <= 2^-21 |x|).  Benefits: hops gather the exact fp32 row from ONE tile, and the split costs 4 instructions.
+__device__ __forceinline__ float tf32_residual(float x) { return tf32_rna(x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u)); }
+__device__ __forceinline__ void plain_store4(const float4 v, char* p_tile, char* l_tile, uint32_t off) {
+  *reinterpret_cast<float4*>(p_tile + off) = v;
+  *reinterpret_cast<float4*>(l_tile + off) = make_float4(tf32_residual(v.x), tf32_residual(v.y), tf32_residual(v.z), tf32_residual(v.w));
+}
+
+// arrive (count 1) on a CTA-local mbarrier
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// advance the start-address field of a descriptor by `bytes` (multiple of 16, no carry out of the 14-bit field for our tile sizes)
+__device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) { return desc + (uint64_t)(bytes >> 4); }
+
+// 16 columns (half a row) of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// 4-term product of one [128 x 32] activation tile pair with one [32 x 32] weight tile pair from PRE-BUILT descriptors
+__device__ __forceinline__ void issue_block_desc(uint32_t d_tmem, uint64_t a_hi, uint64_t a_lo, uint64_t b_hi, uint64_t b_lo, uint32_t idesc,
+                                                 bool first) {
+#pragma unroll
+  for (uint32_t kk = 0; kk < ROW_BYTES / KSTEP_BYTES; ++kk) {
+    const uint32_t o = kk * KSTEP_BYTES;
+    mma_tf32(d_tmem, desc_advance(a_lo, o), desc_advance(b_lo, o), idesc, (first && kk == 0) ? 0u : 1u);
+    mma_tf32(d_tmem, desc_advance(a_lo, o), desc_advance(b_hi, o), idesc, 1u);
+    mma_tf32(d_tmem, desc_advance(a_hi, o), desc_advance(b_lo, o), idesc, 1u);
+    mma_tf32(d_tmem, desc_advance(a_hi, o), desc_advance(b_hi, o), idesc, 1u);
+  }
+}
+
 // Issue the 3xTF32 product of one [128 x 32] activation block pair (hi, lo) with one [32 x 32] weight block pair into
 // 32 TMEM columns.  `first` = this is the first product of the accumulation chain.
 __device__ __forceinline__ void issue_block(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, uint32_t idesc,
