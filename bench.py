@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--same-shards", action="store_true", help="every rank uses rank 0's scenarios and ids (multi-GPU == single-GPU check)")
     return ap.parse_args()
 
 
@@ -164,11 +165,12 @@ def main():
         return float(t.item())
 
     grid = synth.load_grid(CASE)
-    store = synth.synthetic_store(grid, args.scenarios, seed=1234 + rank, device=dev)
+    shard = 0 if args.same_shards else rank
+    store = synth.synthetic_store(grid, args.scenarios, seed=1234 + shard, device=dev)
     n, e = store.max_nodes, store.max_edges
     trainer = GraphedTrainer(store, B, spec=default_spec(), reg_coefs=REG, seed=0, process_group=pg, world_size=world,
                              use_cuda_graph=not args.no_graph).capture()
-    gen = torch.Generator().manual_seed(99 + rank)
+    gen = torch.Generator().manual_seed(99 + shard)
     ids_host = torch.randint(0, args.scenarios, (W + K, B), generator=gen).pin_memory()
 
     # ---- device-resident throughput: scenarios already in HBM, ids copied per step (32 KB) ----
@@ -191,25 +193,39 @@ def main():
     loss_end = float(trainer.loss.item())
     value = world * B * K / (ms_total / 1e3)
 
-    # ---- dominant kernel, timed live on the launching stream: TAG-layer backward (hidden layer, 32 -> 32, K=2) ----
+    # ---- layer kernels timed live on the launching stream (hidden layer 32 -> 32, K = 2, the shapes of 35 of the 40 TAG layers) ----
     lib, P = _lib.load(), _lib.ptr
+    from dss2 import ops as _ops
     sp, run, bufs = trainer.spec, trainer.runner, trainer.bufs
     nt, et = trainer.nt, trainer.et
     name_w, name_b = "mpns.0.convs.3.lins.0.weight", "mpns.0.convs.3.bias"
     w_off, b_off = run.table[name_w][0], run.table[name_b][0]
+    part_w = ctypes.c_void_p(bufs["partials"].data_ptr() + 4 * w_off)
+    gref, st_ = trainer.graph.ref, _lib.stream
+    x_l, y_l, bits_l = bufs["acts"][0, 3], bufs["acts"][0, 4], bufs["bits"][0, 3]
+    gy_l, gx_l, lvl = bufs["g32"][0], bufs["g32"][1], bufs["lvl"]
+    wp, bp = run._p(trainer.flat, name_w), run._p(trainer.flat, name_b)
+    tc2 = _ops.TAG_IMPL == "tc2" and bool(lib.dss2_tag_tc2_supported(gref, sp.K))
+    kernels = {}
+    if tc2:
+        kernels["k_tag_tc2<BGX> (TAG backward-to-input, tcgen05)"] = (lambda: _lib.check(lib.dss2_tag_bwd_tc2_gx(
+            gref, wp, 32, sp.K, 1, sp.p_drop, P(bits_l), P(gy_l), P(gx_l), P(lvl), lvl.numel() * 4, st_()), "gx"),
+            nt * (128 + 128 + 4 + 24), "grad_y + sign word + ELL topology in, grad_x out; excludes the 256 B/node hop-level spill it writes for k_tag_gw")
+        kernels["k_tag_tc2<FWD> (TAG forward, tcgen05)"] = (lambda: _lib.check(lib.dss2_tag_fwd_tc2(
+            gref, P(x_l), wp, bp, 32, sp.K, 1, sp.p_drop, 1, P(trainer.step_state), 3, None, None, 0, P(y_l), P(bits_l), st_()), "fwd"),
+            nt * (128 + 128 + 4 + 24), "x + ELL topology in, y + sign word out")
+        kernels["k_tag_gw (TAG weight gradients, tcgen05 MN-major, TMA ring)"] = (lambda: _lib.check(lib.dss2_tag_bwd_tc2_gw(
+            nt, P(x_l), 32, sp.K, 1, sp.p_drop, P(bits_l), P(gy_l), part_w, run.flat_size, b_off - w_off, P(lvl), lvl.numel() * 4, st_()), "gw"),
+            nt * (128 + 128 + 4), "x + grad_y + sign word in; excludes the 256 B/node hop levels it re-reads")
+    else:
+        kernels["k_tag_bwd<2,32> (TAG backward, CUDA cores)"] = (lambda: _lib.check(lib.dss2_tag_bwd(
+            gref, P(x_l), wp, 32, sp.K, 1, sp.p_drop, P(bits_l), P(gy_l), P(gx_l), part_w, run.flat_size, b_off - w_off, st_()), "bwd"),
+            nt * (3 * 128 + 4) + 4 * (nt + 1) + 16 * et, "x, grad_y in, grad_x out, sign word, CSR")
+        kernels["k_tag_fwd<2> (TAG forward, CUDA cores)"] = (lambda: _lib.check(lib.dss2_tag_fwd(
+            gref, P(x_l), wp, bp, 32, sp.K, 1, sp.p_drop, 1, P(trainer.step_state), 3, None, None, 0, P(y_l), P(bits_l), st_()), "fwd"),
+            nt * (2 * 128 + 4) + 4 * (nt + 1) + 16 * et, "x in, y out, sign word, CSR")
 
-    def launch_dom():
-        _lib.check(lib.dss2_tag_bwd(trainer.graph.ref, P(bufs["acts"][0, 3]), run._p(trainer.flat, name_w), 32, sp.K, 1, sp.p_drop,
-                                    P(bufs["bits"][0, 3]), P(bufs["g32"][0]), P(bufs["g32"][1]),
-                                    ctypes.c_void_p(bufs["partials"].data_ptr() + 4 * w_off), run.flat_size, b_off - w_off,
-                                    _lib.stream()), "dss2_tag_bwd")
-
-    def launch_fwd():
-        _lib.check(lib.dss2_tag_fwd(trainer.graph.ref, P(bufs["acts"][0, 3]), run._p(trainer.flat, name_w), run._p(trainer.flat, name_b), 32,
-                                    sp.K, 1, sp.p_drop, 1, P(trainer.step_state), 3, None, None, 0, P(bufs["acts"][0, 4]), P(bufs["bits"][0, 3]),
-                                    _lib.stream()), "dss2_tag_fwd")
-
-    def time_kernel(fn, reps=40):
+    def time_kernel(fn, reps=30):
         flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # 256 MB > 126 MB L2
         durs = []
         for _ in range(3):
@@ -224,35 +240,27 @@ def main():
             durs.append(a.elapsed_time(b))
         return statistics.mean(durs) * 1e-3
 
-    def launch_fwd_tc():
-        _lib.check(lib.dss2_tag_fwd_tc(trainer.graph.ref, P(bufs["acts"][0, 3]), run._p(trainer.flat, name_w), run._p(trainer.flat, name_b), 32,
-                                       sp.K, 1, sp.p_drop, 1, P(trainer.step_state), 3, None, None, 0, P(bufs["acts"][0, 4]), P(bufs["bits"][0, 3]),
-                                       _lib.stream()), "dss2_tag_fwd_tc")
-
-    t_bwd = time_kernel(launch_dom)
-    t_fwd = time_kernel(launch_fwd)
-    t_fwd_tc = time_kernel(launch_fwd_tc) if lib.dss2_tag_fwd_tc_supported(trainer.graph.ref, sp.K) else None
-    # algorithmic bytes per launch: x, grad_y in, grad_x out (32 fp32 each), sign word, CSR (rowptr, col, dis)
-    bytes_bwd = nt * (3 * 128 + 4) + 4 * (nt + 1) + 4 * (2 * et) + 4 * nt
-    bytes_fwd = nt * (2 * 128 + 4) + 4 * (nt + 1) + 4 * (2 * et) + 4 * nt
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    traffic = None
+    traffic_tab = {}
     tpath = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("tag_bwd_dram_bytes_per_launch")
-    ach = bytes_bwd / t_bwd / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_tag_bwd<K=2,cout=32> (TAG layer backward, recompute)", "achieved": ach, "peak": peak,
-                "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "peak_source": peak_src, "us_per_launch": t_bwd * 1e6,
-                "algorithmic_bytes_per_launch": bytes_bwd,
-                "note": "fp32 CUDA-core FFMA bound at this fusion level (AI ~37 flop/B, SURVEY 8d); HBM fraction reported as the contract asks",
-                "tag_fwd": {"achieved": bytes_fwd / t_fwd / 1e9, "frac": bytes_fwd / t_fwd / 1e9 / peak, "us_per_launch": t_fwd * 1e6,
-                            "algorithmic_bytes_per_launch": bytes_fwd},
-                "tag_fwd_tcgen05": None if t_fwd_tc is None else {"achieved": bytes_fwd / t_fwd_tc / 1e9, "frac": bytes_fwd / t_fwd_tc / 1e9 / peak,
-                                                                    "us_per_launch": t_fwd_tc * 1e6}}
+        traffic_tab = json.load(open(tpath))
+    timed = []
+    for kname, (fn, nbytes, what) in kernels.items():
+        t = time_kernel(fn)
+        timed.append({"kernel": kname, "us_per_launch": t * 1e6, "algorithmic_bytes_per_launch": nbytes, "bytes_counted": what,
+                      "achieved": nbytes / t / 1e9, "frac": nbytes / t / 1e9 / peak, "traffic": traffic_tab.get(kname.split(" ")[0])})
+    dom = max(timed, key=lambda r: r["us_per_launch"])
+    roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": peak, "unit": "GB/s", "frac": dom["frac"],
+                "traffic": dom["traffic"], "peak_source": peak_src, "us_per_launch": dom["us_per_launch"],
+                "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"], "bytes_counted": dom["bytes_counted"],
+                "note": "layer kernels are bound by the per-tile dependency chain (shared-memory gathers, barriers, tcgen05 issue), not by HBM: "
+                        "see DESIGN.md section 4 and profiles/",
+                "all_layer_kernels": timed}
 
     # ---- end to end through the host-buffer API: pinned host scenarios -> H2D -> step -> D2H loss, all inside the timed region ----
     e2e = None
@@ -310,9 +318,14 @@ def main():
             "e2e": e2e, "gpu_launches": int(trainer.launches_per_step) * K, "launches_per_step": int(trainer.launches_per_step),
             "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.result(), "final_loss": loss_end,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # a process group that has collectives captured in live CUDA graphs can hang in destroy_process_group(): leave together, hard
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -673,39 +673,49 @@ extern "C" int dss2_tag_fwd_tc2(const dss2_graph_t* g, const float* x, const flo
 
 extern "C" size_t dss2_tag_bwd_tc2_workspace_bytes(int64_t num_nodes, int K) { return (size_t)K * num_nodes * HID * sizeof(float) + 256; }
 
-extern "C" int dss2_tag_bwd_tc2(const dss2_graph_t* g, const float* x, const float* w, int cout, int K, int act, float p_drop,
-                                const uint32_t* act_bits, const float* grad_y, float* grad_x, float* partials, int64_t partial_stride,
-                                int64_t bias_offset, void* ws, size_t ws_bytes, void* stream_) {
+// the two halves of the backward, individually launchable (bench.py times them separately; dss2_tag_bwd_tc2 = both)
+extern "C" int dss2_tag_bwd_tc2_gx(const dss2_graph_t* g, const float* w, int cout, int K, int act, float p_drop, const uint32_t* act_bits,
+                                   const float* grad_y, float* grad_x, void* ws, size_t ws_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  DSS2_CHECK_ARG(g && x && w && grad_y && grad_x && partials && ws, "dss2_tag_bwd_tc2: null argument");
-  DSS2_CHECK_ARG(cout >= 1 && cout <= HID, "dss2_tag_bwd_tc2: cout %d outside 1..%d", cout, HID);
-  DSS2_CHECK_ARG(tc2_supported(g, K), "dss2_tag_bwd_tc2: needs a graph tiled with tile_cap <= 128 and K in 1..2");
-  DSS2_CHECK_ARG(!act || act_bits, "dss2_tag_bwd_tc2: activation layers need act_bits from the forward");
-  DSS2_CHECK_ARG(ws_bytes >= dss2_tag_bwd_tc2_workspace_bytes(g->num_nodes, K), "dss2_tag_bwd_tc2: workspace too small");
-  DSS2_CHECK_ARG(partial_stride >= (int64_t)(K + 1) * cout * HID + cout, "dss2_tag_bwd_tc2: partial_stride too small");
-  DSS2_CHECK_ARG((((uintptr_t)x | (uintptr_t)grad_y | (uintptr_t)ws | (uintptr_t)act_bits | (uintptr_t)grad_x | (uintptr_t)partials) & 15) == 0,
-                 "dss2_tag_bwd_tc2: x, grad_y, grad_x, act_bits, partials and ws must be 16-byte aligned (bulk-copy / 128-bit access)");
+  DSS2_CHECK_ARG(g && w && grad_y && grad_x && ws, "dss2_tag_bwd_tc2_gx: null argument");
+  DSS2_CHECK_ARG(cout >= 1 && cout <= HID, "dss2_tag_bwd_tc2_gx: cout %d outside 1..%d", cout, HID);
+  DSS2_CHECK_ARG(tc2_supported(g, K), "dss2_tag_bwd_tc2_gx: needs a graph tiled with tile_cap <= 128 and K in 1..2");
+  DSS2_CHECK_ARG(!act || act_bits, "dss2_tag_bwd_tc2_gx: activation layers need act_bits from the forward");
+  DSS2_CHECK_ARG(ws_bytes >= dss2_tag_bwd_tc2_workspace_bytes(g->num_nodes, K), "dss2_tag_bwd_tc2_gx: workspace too small");
+  DSS2_CHECK_ARG((((uintptr_t)grad_y | (uintptr_t)ws | (uintptr_t)grad_x) & 15) == 0, "dss2_tag_bwd_tc2_gx: pointers must be 16-byte aligned");
   if (g->num_nodes == 0) return 0;
-  const float scale = 1.0f / (float)(1.0 - (double)p_drop);
   Tc2Args a = {};
   a.g = *g;
   a.in = grad_y;
   a.in_bits = act ? act_bits : nullptr;
   a.w = w;
   a.cout = cout;
-  a.scale = scale;
+  a.scale = 1.0f / (float)(1.0 - (double)p_drop);
   a.out = grad_x;
   a.lvl_out = (float*)ws;
-  int rc = launch_tc2<MODE_BGX>(a, K, stream);
-  if (rc) return rc;
+  return launch_tc2<MODE_BGX>(a, K, stream);
+}
+
+extern "C" int dss2_tag_bwd_tc2_gw(int64_t num_nodes, const float* x, int cout, int K, int act, float p_drop, const uint32_t* act_bits,
+                                   const float* grad_y, float* partials, int64_t partial_stride, int64_t bias_offset, const void* ws,
+                                   size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DSS2_CHECK_ARG(x && grad_y && partials && ws, "dss2_tag_bwd_tc2_gw: null argument");
+  DSS2_CHECK_ARG(cout >= 1 && cout <= HID && K >= 1 && K <= 2, "dss2_tag_bwd_tc2_gw: cout %d / K %d unsupported", cout, K);
+  DSS2_CHECK_ARG(!act || act_bits, "dss2_tag_bwd_tc2_gw: activation layers need act_bits from the forward");
+  DSS2_CHECK_ARG(ws_bytes >= dss2_tag_bwd_tc2_workspace_bytes(num_nodes, K), "dss2_tag_bwd_tc2_gw: workspace too small");
+  DSS2_CHECK_ARG(partial_stride >= (int64_t)(K + 1) * cout * HID + cout, "dss2_tag_bwd_tc2_gw: partial_stride too small");
+  DSS2_CHECK_ARG((((uintptr_t)x | (uintptr_t)grad_y | (uintptr_t)ws | (uintptr_t)act_bits | (uintptr_t)partials) & 15) == 0,
+                 "dss2_tag_bwd_tc2_gw: x, grad_y, act_bits, partials and ws must be 16-byte aligned (bulk-copy sources / 128-bit stores)");
+  if (num_nodes == 0) return 0;
   GwArgs b;
-  b.num_nodes = g->num_nodes;
+  b.num_nodes = num_nodes;
   b.x = x;
   b.gy = grad_y;
   b.bits = act ? act_bits : nullptr;
   b.lvl = (const float*)ws;
   b.cout = cout;
-  b.scale = scale;
+  b.scale = 1.0f / (float)(1.0 - (double)p_drop);
   b.partials = partials;
   b.partial_stride = partial_stride;
   b.bias_offset = bias_offset;
@@ -720,4 +730,13 @@ extern "C" int dss2_tag_bwd_tc2(const dss2_graph_t* g, const float* x, const flo
   }
   DSS2_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int dss2_tag_bwd_tc2(const dss2_graph_t* g, const float* x, const float* w, int cout, int K, int act, float p_drop,
+                                const uint32_t* act_bits, const float* grad_y, float* grad_x, float* partials, int64_t partial_stride,
+                                int64_t bias_offset, void* ws, size_t ws_bytes, void* stream_) {
+  DSS2_CHECK_ARG(g, "dss2_tag_bwd_tc2: null graph");
+  int rc = dss2_tag_bwd_tc2_gx(g, w, cout, K, act, p_drop, act_bits, grad_y, grad_x, ws, ws_bytes, stream_);
+  if (rc) return rc;
+  return dss2_tag_bwd_tc2_gw(g->num_nodes, x, cout, K, act, p_drop, act_bits, grad_y, partials, partial_stride, bias_offset, ws, ws_bytes, stream_);
 }

@@ -156,6 +156,13 @@ int dss2_tag_bwd_tc2(const dss2_graph_t* g, const float* x, const float* w, int 
                      int act, float p_drop, const uint32_t* act_bits, const float* grad_y,
                      float* grad_x, float* partials, int64_t partial_stride, int64_t bias_offset,
                      void* ws, size_t ws_bytes, void* stream);
+/* Its two launches on their own: _gx writes grad_x and the hop levels of the masked output gradient into ws; _gw consumes x,
+ * grad_y (+act_bits) and ws and writes the per-CTA partial sums of grad_W / grad_b. */
+int dss2_tag_bwd_tc2_gx(const dss2_graph_t* g, const float* w, int cout, int K, int act, float p_drop,
+                        const uint32_t* act_bits, const float* grad_y, float* grad_x, void* ws, size_t ws_bytes, void* stream);
+int dss2_tag_bwd_tc2_gw(int64_t num_nodes, const float* x, int cout, int K, int act, float p_drop,
+                        const uint32_t* act_bits, const float* grad_y, float* partials, int64_t partial_stride,
+                        int64_t bias_offset, const void* ws, size_t ws_bytes, void* stream);
 /* D[128,32] = A[128,32] * B[32,32]^T through the tensor-core operand / descriptor / TMEM path (bring-up and regression test). */
 int dss2_tc_selftest(const float* A, const float* B, float* D, void* stream);
 /* D[32*t + j, n] = sum_r A[t][r][j] * B[r][n], A = [4,64,32], B = [64,32]: MN-major TF32 operands (SWIZZLE_128B_BASE32B), the
