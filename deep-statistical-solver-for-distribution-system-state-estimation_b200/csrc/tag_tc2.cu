@@ -422,18 +422,19 @@ __global__ void __launch_bounds__(128, 1) k_tag_gw(GwArgs a) {
   // extent covers 3 levels + 1 zero block (rows 96..127 of D are ignored)
   char* Ah = base;
   char* Al = Ah + 4 * GW_TILE;
-  // B side (MN-major, N = 48: 32 input features + the ones column): [x.hi][ones][x.lo][zeros]
+  // B side (MN-major, N = 32 input features): [x.hi][x.lo]
   char* Bh = Al + 4 * GW_TILE;
-  char* Bones = Bh + GW_TILE;
-  char* Bl = Bones + GW_TILE;
-  char* Bzero = Bl + GW_TILE;
-  char* stage0 = Bzero + GW_TILE;                        // raw rows landed by the TMA engine, GW_STAGES deep
+  char* Bl = Bh + GW_TILE;
+  char* stage0 = Bl + GW_TILE;                           // raw rows landed by the TMA engine, GW_STAGES deep
   char* tail = stage0 + GW_STAGES * GW_STAGE_BYTES;
   uint64_t* full = reinterpret_cast<uint64_t*>(tail);    // [GW_STAGES] "chunk has landed"
   uint64_t* bar = full + GW_STAGES;                      // "MMAs of the previous chunk have completed"
   uint32_t* tslot = reinterpret_cast<uint32_t*>(bar + 1);
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int row = tid & (GW_ROWS - 1), half = tid >> 6;   // two threads per chunk row: half 0 -> x and G_0, half 1 -> G_1, G_2
+  // thread = (16-byte column chunk cq, row group rs): it converts chunk cq of rows rs, rs+16, rs+32, rs+48 of all four arrays.
+  // Eight consecutive threads read one staged row (128 contiguous bytes) and write the eight swizzled chunks of one operand row:
+  // both accesses are bank-conflict free (ncu on the thread-per-row version: 78 % of the shared-memory wavefronts were conflicts).
+  const uint32_t cq = tid & 7, rs = tid >> 3;
   const int cout = a.cout;
 
   if (warp == 0) tc::tmem_alloc(tslot, 64);
@@ -442,10 +443,8 @@ __global__ void __launch_bounds__(128, 1) k_tag_gw(GwArgs a) {
     mbar_init(bar, 1);
     fence_mbar_init();
   }
-  for (int idx = tid; idx < GW_ROWS * 32; idx += 128) {   // constant tiles
+  for (int idx = tid; idx < GW_ROWS * 32; idx += 128) {   // unused A blocks (M rows beyond the K+1 levels) read as zeros
     const uint32_t r = idx >> 5, j = idx & 31;
-    *reinterpret_cast<float*>(Bones + tc::swz32_off(r, j)) = j == 0 ? 1.0f : 0.0f;
-    *reinterpret_cast<float*>(Bzero + tc::swz32_off(r, j)) = 0.0f;
     for (int blk = K + 1; blk < 4; ++blk) {
       *reinterpret_cast<float*>(Ah + blk * GW_TILE + tc::swz32_off(r, j)) = 0.0f;
       *reinterpret_cast<float*>(Al + blk * GW_TILE + tc::swz32_off(r, j)) = 0.0f;
@@ -456,7 +455,7 @@ __global__ void __launch_bounds__(128, 1) k_tag_gw(GwArgs a) {
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = *tslot;
-  const uint32_t idesc = tc::idesc_tf32(128, 48, 1, 1);
+  const uint32_t idesc = tc::idesc_tf32(128, 32, 1, 1);
 
   const int64_t num_chunks = (a.num_nodes + GW_ROWS - 1) / GW_ROWS;
   const int64_t full_chunks = a.num_nodes / GW_ROWS;       // only whole chunks go through the bulk-copy engine
@@ -477,93 +476,75 @@ __global__ void __launch_bounds__(128, 1) k_tag_gw(GwArgs a) {
   if (tid == 0)
     for (int i = 0; i < GW_STAGES; ++i) issue(blockIdx.x + (int64_t)i * gridDim.x, i);
 
-  auto store_row32 = [&](const float (&v)[32], char* hi, char* lo) {
-#pragma unroll
-    for (uint32_t q = 0; q < 8; ++q)
-      tc::split_store4(make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]), hi, lo, tc::swz32_off((uint32_t)row, 4 * q));
-  };
+  // grad_b = column sums of the masked output gradient: accumulated exactly in fp32 registers by the threads that convert those
+  // columns (a ones-column in the GEMM would inherit the 2^-23 TF32-pair representation error, visible in this cancelling sum)
+  float gb[4] = {0.f, 0.f, 0.f, 0.f};
 
   bool first = true;
   uint32_t par = 0;
   int it = 0;
   for (int64_t ch = blockIdx.x; ch < num_chunks; ch += gridDim.x, ++it) {
     const int s = it % GW_STAGES;
-    float r0[32], r1[32];
+    const bool staged = ch < full_chunks;
+    const char* st = stage0 + (size_t)s * GW_STAGE_BYTES;
+    if (staged) mbar_wait(&full[s], (uint32_t)((it / GW_STAGES) & 1));
+    float4 vx[4], vg[4], v1[4], v2[4];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) r0[i] = r1[i] = 0.0f;
-    uint32_t word = 0xffffffffu;
-    if (ch < full_chunks) {
-      mbar_wait(&full[s], (uint32_t)((it / GW_STAGES) & 1));
-      const char* st = stage0 + (size_t)s * GW_STAGE_BYTES;
-      const float4* p0 = reinterpret_cast<const float4*>(st + (half == 0 ? 0 : 2 * GW_TILE)) + row * 8;
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float4 v = p0[q];
-        r0[4 * q] = v.x;
-        r0[4 * q + 1] = v.y;
-        r0[4 * q + 2] = v.z;
-        r0[4 * q + 3] = v.w;
-      }
-      if (half == 0) {
-        const float* gp = reinterpret_cast<const float*>(st + GW_TILE) + row * cout;
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t r = rs + 16 * i;
+      const int64_t n = ch * GW_ROWS + r;
+      const bool inb = n < a.num_nodes;
+      vx[i] = vg[i] = v1[i] = v2[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      uint32_t word = 0xffffffffu;
+      if (staged) {
+        vx[i] = *reinterpret_cast<const float4*>(st + r * 128 + cq * 16);
+        v1[i] = *reinterpret_cast<const float4*>(st + 2 * GW_TILE + r * 128 + cq * 16);
+        if (K >= 2) v2[i] = *reinterpret_cast<const float4*>(st + 3 * GW_TILE + r * 128 + cq * 16);
         if (cout == 32) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 v = reinterpret_cast<const float4*>(gp)[q];
-            r1[4 * q] = v.x;
-            r1[4 * q + 1] = v.y;
-            r1[4 * q + 2] = v.z;
-            r1[4 * q + 3] = v.w;
-          }
+          vg[i] = *reinterpret_cast<const float4*>(st + GW_TILE + r * 128 + cq * 16);
         } else {
+          const float* gp = reinterpret_cast<const float*>(st + GW_TILE) + r * cout;
+          float t4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int c = 0; c < 32; ++c)
-            if (c < cout) r1[c] = gp[c];
+          for (int e = 0; e < 4; ++e)
+            if ((int)(cq * 4 + e) < cout) t4[e] = gp[cq * 4 + e];
+          vg[i] = make_float4(t4[0], t4[1], t4[2], t4[3]);
         }
-        if (a.bits) word = reinterpret_cast<const uint32_t*>(st + 4 * GW_TILE)[row];
-      } else if (K >= 2) {
-        const float4* p1 = reinterpret_cast<const float4*>(st + 3 * GW_TILE) + row * 8;
+        if (a.bits) word = reinterpret_cast<const uint32_t*>(st + 4 * GW_TILE)[r];
+      } else if (inb) {   // the one ragged chunk at the end of the batch: plain bounded loads
+        vx[i] = *reinterpret_cast<const float4*>(a.x + n * 32 + cq * 4);
+        v1[i] = *reinterpret_cast<const float4*>(a.lvl + n * 32 + cq * 4);
+        if (K >= 2) v2[i] = *reinterpret_cast<const float4*>(a.lvl + (a.num_nodes + n) * 32 + cq * 4);
+        float t4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 v = p1[q];
-          r1[4 * q] = v.x;
-          r1[4 * q + 1] = v.y;
-          r1[4 * q + 2] = v.z;
-          r1[4 * q + 3] = v.w;
-        }
+        for (int e = 0; e < 4; ++e)
+          if ((int)(cq * 4 + e) < cout) t4[e] = a.gy[n * cout + cq * 4 + e];
+        vg[i] = make_float4(t4[0], t4[1], t4[2], t4[3]);
+        if (a.bits) word = a.bits[n];
       }
-    } else {   // the one ragged chunk at the end of the batch: plain bounded loads
-      const int64_t n = ch * GW_ROWS + row;
-      if (n < a.num_nodes) {
-        const float* p0 = half == 0 ? a.x + n * 32 : a.lvl + n * 32;
-#pragma unroll
-        for (int c = 0; c < 32; ++c) r0[c] = p0[c];
-        if (half == 0) {
-#pragma unroll
-          for (int c = 0; c < 32; ++c)
-            if (c < cout) r1[c] = a.gy[n * cout + c];
-          if (a.bits) word = a.bits[n];
-        } else if (K >= 2) {
-          const float* p1 = a.lvl + (a.num_nodes + n) * 32;
-#pragma unroll
-          for (int c = 0; c < 32; ++c) r1[c] = p1[c];
-        }
+      if (a.bits) {
+        const uint32_t w4 = word >> (cq * 4);
+        vg[i].x = (w4 & 1u) ? vg[i].x * a.scale : 0.0f;
+        vg[i].y = (w4 & 2u) ? vg[i].y * a.scale : 0.0f;
+        vg[i].z = (w4 & 4u) ? vg[i].z * a.scale : 0.0f;
+        vg[i].w = (w4 & 8u) ? vg[i].w * a.scale : 0.0f;
       }
-    }
-    if (half == 0 && a.bits) {
-#pragma unroll
-      for (int c = 0; c < 32; ++c) r1[c] = ((word >> c) & 1u) ? r1[c] * a.scale : 0.0f;
+      gb[0] += vg[i].x;
+      gb[1] += vg[i].y;
+      gb[2] += vg[i].z;
+      gb[3] += vg[i].w;
     }
     if (!first) {   // the previous chunk's MMAs still read the operand tiles
       mbar_wait(bar, par);
       par ^= 1u;
     }
-    if (half == 0) {
-      store_row32(r0, Bh, Bl);                         // x
-      store_row32(r1, Ah, Al);                         // G_0
-    } else {
-      store_row32(r0, Ah + GW_TILE, Al + GW_TILE);     // G_1
-      if (K >= 2) store_row32(r1, Ah + 2 * GW_TILE, Al + 2 * GW_TILE);   // G_2
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t off = tc::swz32_off(rs + 16 * i, cq * 4);
+      tc::split_store4(vx[i], Bh, Bl, off);                                   // x
+      tc::split_store4(vg[i], Ah, Al, off);                                   // G_0
+      tc::split_store4(v1[i], Ah + GW_TILE, Al + GW_TILE, off);               // G_1
+      if (K >= 2) tc::split_store4(v2[i], Ah + 2 * GW_TILE, Al + 2 * GW_TILE, off);   // G_2
     }
     fence_proxy_async();
     tc::fence_before_sync();
@@ -594,18 +575,25 @@ __global__ void __launch_bounds__(128, 1) k_tag_gw(GwArgs a) {
     tc::fence_after_sync();
     float v[32];
     tc::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16), v);
-    float vb[32];
-    tc::tmem_ld32(tmem + 32 + ((uint32_t)(warp * 32) << 16), vb);    // column 32 = bias gradient (level 0 lanes)
     if (k <= K && c < cout) {
       float4* dst = reinterpret_cast<float4*>(part + ((size_t)k * cout + c) * 32);
 #pragma unroll
       for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-      if (k == 0) part[a.bias_offset + c] = vb[0];
     }
   } else if (k <= K && c < cout) {   // a CTA without chunks contributes zeros
 #pragma unroll
     for (int j = 0; j < 32; ++j) part[((size_t)k * cout + c) * 32 + j] = 0.0f;
-    if (k == 0) part[a.bias_offset + c] = 0.0f;
+  }
+  // bias gradient: 16 row-group partials per column -> shared memory -> 32 column sums in fixed order
+  float* red = reinterpret_cast<float*>(stage0);
+  __syncthreads();
+#pragma unroll
+  for (int e = 0; e < 4; ++e) red[rs * 33 + cq * 4 + e] = gb[e];
+  __syncthreads();
+  if (tid < 32 && tid < cout) {
+    float sum = 0.0f;
+    for (int r = 0; r < 16; ++r) sum += red[r * 33 + tid];
+    part[a.bias_offset + tid] = sum;
   }
   tc::fence_before_sync();
   __syncthreads();
@@ -613,7 +601,7 @@ __global__ void __launch_bounds__(128, 1) k_tag_gw(GwArgs a) {
 }
 
 size_t tc2_smem(int K) { return 1024 + (size_t)(K + 1) * 2 * W_TILE + 4 * LV_TILE + 256; }   // ~89 KB: two CTAs per SM
-size_t gw_smem() { return 1024 + 12 * GW_TILE + GW_STAGES * GW_STAGE_BYTES + 128; }
+size_t gw_smem() { return 1024 + 10 * GW_TILE + GW_STAGES * GW_STAGE_BYTES + 128; }
 
 int tc2_supported(const dss2_graph_t* g, int K) {
   return g && g->num_tiles > 0 && g->max_tile_nodes <= T2 && K >= 1 && K <= 2 && g->ell_w && g->ell_ci;
