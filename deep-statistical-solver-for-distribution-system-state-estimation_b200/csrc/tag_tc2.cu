@@ -21,8 +21,7 @@
 
 namespace {
 
-constexpr int T2 = 128;                          // rows per tile = threads per CTA
-constexpr uint32_t LV_TILE = T2 * tc::ROW_BYTES; // 16 KB: one operand tile (hi or lo) of one hop level
+constexpr int T2_MAX = 256;                      // rows per tile (2 MMA blocks of 128)
 constexpr uint32_t W_TILE = 32 * tc::ROW_BYTES;  // 4 KB
 enum { MODE_FWD = 0, MODE_BGX = 1 };
 
@@ -71,8 +70,8 @@ __device__ __forceinline__ uint32_t keep_word(uint2 key, uint32_t tile, uint32_t
 // Thread mapping of the layer kernel: 256 threads per tile, thread = (row, half): row = tid & 127 (= its TMEM lane), half = tid >> 7
 // owns features [16*half, 16*half + 16).  Two threads per row double the number of busy warps on grids whose tile holds a single
 // graph (Oberrhein: 70 of 128 rows) and halve every per-thread dependency chain.
-constexpr int TC2_WORKERS = 256;                 // 8 worker warps
-constexpr int TC2_THREADS = TC2_WORKERS + 32;    // + 1 issuer warp (one elected lane issues every tcgen05.mma)
+// NB = MMA blocks (128 rows each) per tile: NB = 2 packs e.g. 3 Oberrhein graphs (210 rows) or 17 CIGRE graphs (255 rows) into one
+// tile, so that more live rows share one pass through the per-tile dependency chain; workers = 256 per block + 1 issuer warp.
 constexpr int HF = 16;
 
 __device__ __forceinline__ void store_half_sw128(const float (&v)[HF], char* pt, char* lt, uint32_t row, uint32_t half) {
@@ -154,13 +153,17 @@ __device__ __forceinline__ TileNodes tile_nodes(const dss2_graph_t& g, int t) {
   return r;
 }
 
-template <int MODE, int K>
-__global__ void __launch_bounds__(TC2_THREADS, 2) k_tag_tc2(Tc2Args a) {
+template <int MODE, int K, int NB>
+__global__ void __launch_bounds__(256 * NB + 32, 3 - NB) k_tag_tc2(Tc2Args a) {
+  constexpr int TC2_WORKERS = 256 * NB;
+  constexpr int TC2_THREADS = TC2_WORKERS + 32;
+  constexpr int ROWS = 128 * NB;
+  constexpr uint32_t LV_TILE = ROWS * tc::ROW_BYTES;   // one operand tile (plain or residual) of one hop level
   extern __shared__ char raw[];
   const dss2_graph_t& g = a.g;
   char* base = align1024(raw);
   char* Wt = base;                                  // [(K+1)] x 8 KB: rows 0-31 plain W_k, rows 32-63 residual -> one N = 64 operand
-  char* Lv = Wt + (K + 1) * 2 * W_TILE;             // [2 buffers][plain, residual] x 16 KB level tiles
+  char* Lv = Wt + (K + 1) * 2 * W_TILE;             // [2 buffers][plain, residual] level tiles
   char* tail = Lv + 4 * LV_TILE;
   float* bias_s = reinterpret_cast<float*>(tail);
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 128);   // [2]: "MMAs reading buffer b have completed"   (tcgen05.commit)
@@ -168,13 +171,14 @@ __global__ void __launch_bounds__(TC2_THREADS, 2) k_tag_tc2(Tc2Args a) {
   uint32_t* tslot = reinterpret_cast<uint32_t*>(full + 2);
   const int tid = threadIdx.x, warp = tid >> 5;
   const bool issuer = warp == TC2_WORKERS / 32;
-  const uint32_t row = tid & 127, half = (tid >> 7) & 1;
+  // worker tid = half * ROWS + row: warp % 4 == (row / 32) % 4 = the TMEM lane quarter this warp may read
+  const uint32_t row = (uint32_t)tid % ROWS, half = ((uint32_t)tid / ROWS) & 1u;
   const int cout = a.cout;
   auto lv_p = [&](int b) { return Lv + (size_t)(2 * b) * LV_TILE; };
   auto lv_l = [&](int b) { return Lv + (size_t)(2 * b + 1) * LV_TILE; };
 
   // ---- one-time setup ----
-  if (warp == 0) tc::tmem_alloc(tslot, 64);
+  if (warp == 0) tc::tmem_alloc(tslot, 64 * NB);
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
@@ -211,6 +215,8 @@ __global__ void __launch_bounds__(TC2_THREADS, 2) k_tag_tc2(Tc2Args a) {
     const uint32_t idesc = tc::idesc_tf32(128, 64);
     uint32_t fpar[2] = {0u, 0u};
     for (int t = blockIdx.x; t < g.num_tiles; t += gridDim.x) {
+      const TileNodes tn = tile_nodes(g, t);
+      const int nmb = (NB == 2 && tn.n1 - tn.n0 > 128) ? 2 : 1;
 #pragma unroll
       for (int k = 0; k <= K; ++k) {
         const int b = k & 1;
@@ -218,13 +224,16 @@ __global__ void __launch_bounds__(TC2_THREADS, 2) k_tag_tc2(Tc2Args a) {
         fpar[b] ^= 1u;
         tc::fence_after_sync();
         if ((tid & 31) == 0) {
-          const uint64_t dP = tc::smem_desc_sw128(smem_u32(lv_p(b))), dL = tc::smem_desc_sw128(smem_u32(lv_l(b)));
           const uint64_t dW = tc::smem_desc_sw128(smem_u32(Wt + (size_t)(2 * k) * W_TILE));
+          for (int mb = 0; mb < nmb; ++mb) {
+            const uint64_t dP = tc::smem_desc_sw128(smem_u32(lv_p(b)) + mb * 128 * tc::ROW_BYTES);
+            const uint64_t dL = tc::smem_desc_sw128(smem_u32(lv_l(b)) + mb * 128 * tc::ROW_BYTES);
 #pragma unroll
-          for (uint32_t kk = 0; kk < 4; ++kk) {
-            const uint32_t o = kk * tc::KSTEP_BYTES;
-            tc::mma_tf32(tmem, tc::desc_advance(dL, o), tc::desc_advance(dW, o), idesc, (k == 0 && kk == 0) ? 0u : 1u);
-            tc::mma_tf32(tmem, tc::desc_advance(dP, o), tc::desc_advance(dW, o), idesc, 1u);
+            for (uint32_t kk = 0; kk < 4; ++kk) {
+              const uint32_t o = kk * tc::KSTEP_BYTES;
+              tc::mma_tf32(tmem + mb * 64, tc::desc_advance(dL, o), tc::desc_advance(dW, o), idesc, (k == 0 && kk == 0) ? 0u : 1u);
+              tc::mma_tf32(tmem + mb * 64, tc::desc_advance(dP, o), tc::desc_advance(dW, o), idesc, 1u);
+            }
           }
           tc::mma_commit(&bars[b]);
         }
@@ -322,7 +331,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 2) k_tag_tc2(Tc2Args a) {
       }
       tc::fence_after_sync();
       float v[HF], v2[HF];
-      const uint32_t taddr = tmem + half * HF + ((uint32_t)((warp & 3) * 32) << 16);
+      const uint32_t taddr = tmem + (row >> 7) * 64 + half * HF + ((uint32_t)((warp & 3) * 32) << 16);
       tc::tmem_ld16(taddr, v);
       tc::tmem_ld16(taddr + 32, v2);
       tc::fence_before_sync();        // orders these TMEM reads before the next tile's "buffer written" arrival -> issuer -> overwrite of D
@@ -389,7 +398,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 2) k_tag_tc2(Tc2Args a) {
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem, 64);
+  if (warp == 0) tc::tmem_dealloc(tmem, 64 * NB);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -600,26 +609,27 @@ __global__ void __launch_bounds__(128, 1) k_tag_gw(GwArgs a) {
   if (warp == 0) tc::tmem_dealloc(tmem, 64);
 }
 
-size_t tc2_smem(int K) { return 1024 + (size_t)(K + 1) * 2 * W_TILE + 4 * LV_TILE + 256; }   // ~89 KB: two CTAs per SM
+size_t tc2_smem(int K, int nb) { return 1024 + (size_t)(K + 1) * 2 * W_TILE + 4 * (size_t)nb * 128 * tc::ROW_BYTES + 256; }   // 89 KB (2 CTAs/SM) or 153 KB
 size_t gw_smem() { return 1024 + 10 * GW_TILE + GW_STAGES * GW_STAGE_BYTES + 128; }
 
 int tc2_supported(const dss2_graph_t* g, int K) {
-  return g && g->num_tiles > 0 && g->max_tile_nodes <= T2 && K >= 1 && K <= 2 && g->ell_w && g->ell_ci;
+  return g && g->num_tiles > 0 && g->max_tile_nodes <= T2_MAX && K >= 1 && K <= 2 && g->ell_w && g->ell_ci;
 }
 
-template <int MODE>
-int launch_tc2(const Tc2Args& a, int K, cudaStream_t stream) {
-  const size_t smem = tc2_smem(K);
-  const int grid = max(1, min(a.g.num_tiles, 2 * dss2_sm_count()));
-  if (K == 1) {
-    DSS2_CUDA(cudaFuncSetAttribute(k_tag_tc2<MODE, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_tag_tc2<MODE, 1><<<grid, TC2_THREADS, smem, stream>>>(a);
-  } else {
-    DSS2_CUDA(cudaFuncSetAttribute(k_tag_tc2<MODE, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_tag_tc2<MODE, 2><<<grid, TC2_THREADS, smem, stream>>>(a);
-  }
+template <int MODE, int K, int NB>
+int launch_tc2_inst(const Tc2Args& a, cudaStream_t stream) {
+  const size_t smem = tc2_smem(K, NB);
+  const int grid = max(1, min(a.g.num_tiles, (3 - NB) * dss2_sm_count()));
+  DSS2_CUDA(cudaFuncSetAttribute(k_tag_tc2<MODE, K, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_tag_tc2<MODE, K, NB><<<grid, 256 * NB + 32, smem, stream>>>(a);
   DSS2_LAUNCH_CHECK();
   return 0;
+}
+template <int MODE>
+int launch_tc2(const Tc2Args& a, int K, cudaStream_t stream) {
+  const bool two = a.g.max_tile_nodes > 128;
+  if (K == 1) return two ? launch_tc2_inst<MODE, 1, 2>(a, stream) : launch_tc2_inst<MODE, 1, 1>(a, stream);
+  return two ? launch_tc2_inst<MODE, 2, 2>(a, stream) : launch_tc2_inst<MODE, 2, 1>(a, stream);
 }
 
 }  // namespace
@@ -632,7 +642,7 @@ extern "C" int dss2_tag_fwd_tc2(const dss2_graph_t* g, const float* x, const flo
   cudaStream_t stream = (cudaStream_t)stream_;
   DSS2_CHECK_ARG(g && x && w && bias && y, "dss2_tag_fwd_tc2: null argument");
   DSS2_CHECK_ARG(cout >= 1 && cout <= HID, "dss2_tag_fwd_tc2: cout %d outside 1..%d", cout, HID);
-  DSS2_CHECK_ARG(tc2_supported(g, K), "dss2_tag_fwd_tc2: needs a graph tiled with tile_cap <= 128 and K in 1..2");
+  DSS2_CHECK_ARG(tc2_supported(g, K), "dss2_tag_fwd_tc2: needs a tiled graph (tile_cap <= 256) and K in 1..2");
   DSS2_CHECK_ARG(p_drop >= 0.0f && p_drop < 1.0f, "dss2_tag_fwd_tc2: dropout p %f outside [0,1)", p_drop);
   DSS2_CHECK_ARG(!(act && drop_mode == 1) || rng_state, "dss2_tag_fwd_tc2: philox dropout needs rng_state");
   DSS2_CHECK_ARG(!(act && drop_mode == 2) || mask, "dss2_tag_fwd_tc2: mask dropout needs a mask");
@@ -667,7 +677,7 @@ extern "C" int dss2_tag_bwd_tc2_gx(const dss2_graph_t* g, const float* w, int co
   cudaStream_t stream = (cudaStream_t)stream_;
   DSS2_CHECK_ARG(g && w && grad_y && grad_x && ws, "dss2_tag_bwd_tc2_gx: null argument");
   DSS2_CHECK_ARG(cout >= 1 && cout <= HID, "dss2_tag_bwd_tc2_gx: cout %d outside 1..%d", cout, HID);
-  DSS2_CHECK_ARG(tc2_supported(g, K), "dss2_tag_bwd_tc2_gx: needs a graph tiled with tile_cap <= 128 and K in 1..2");
+  DSS2_CHECK_ARG(tc2_supported(g, K), "dss2_tag_bwd_tc2_gx: needs a tiled graph (tile_cap <= 256) and K in 1..2");
   DSS2_CHECK_ARG(!act || act_bits, "dss2_tag_bwd_tc2_gx: activation layers need act_bits from the forward");
   DSS2_CHECK_ARG(ws_bytes >= dss2_tag_bwd_tc2_workspace_bytes(g->num_nodes, K), "dss2_tag_bwd_tc2_gx: workspace too small");
   DSS2_CHECK_ARG((((uintptr_t)grad_y | (uintptr_t)ws | (uintptr_t)grad_x) & 15) == 0, "dss2_tag_bwd_tc2_gx: pointers must be 16-byte aligned");

@@ -15,13 +15,14 @@ HID = _lib.HID
 # which TAG-layer kernels the runner launches (all are CUDA; there is no CPU path):
 #   "ffma": CUDA-core forward and backward (tag.cu)
 #   "tc"  : first tcgen05 forward (tag_tc.cu), CUDA-core backward
-#   "tc2" : second-generation tcgen05 forward AND backward (tag_tc2.cu); needs graphs tiled with tile_cap 128
+#   "tc2" : second-generation tcgen05 forward AND backward (tag_tc2.cu); tiles of up to 256 rows (two MMA blocks)
 # Unsupported shapes (K = 3, oversize tiles) fall back to the CUDA-core kernels.
 TAG_IMPL = os.environ.get("DSS2_TAG_IMPL", "tc2")
 
 
 def tile_cap():
-    return 128 if TAG_IMPL == "tc2" else _lib.TILE_CAP
+    """Max node rows of a shared-memory tile the batch structure is built for (all layer kernels accept up to 256)."""
+    return int(os.environ.get("DSS2_TILE_CAP", _lib.TILE_CAP))
 
 
 def _align4(n):
