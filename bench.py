@@ -214,8 +214,14 @@ def main():
         kernels["k_tag_tc2<FWD> (TAG forward, tcgen05)"] = (lambda: _lib.check(lib.dss2_tag_fwd_tc2(
             gref, P(x_l), wp, bp, 32, sp.K, 1, sp.p_drop, 1, P(trainer.step_state), 3, None, None, 0, P(y_l), P(bits_l), st_()), "fwd"),
             nt * (128 + 128 + 4 + 24), "x + ELL topology in, y + sign word out")
-        kernels["k_tag_gw (TAG weight gradients, tcgen05 MN-major, TMA ring)"] = (lambda: _lib.check(lib.dss2_tag_bwd_tc2_gw(
-            nt, P(x_l), 32, sp.K, 1, sp.p_drop, P(bits_l), P(gy_l), part_w, run.flat_size, b_off - w_off, P(lvl), lvl.numel() * 4, st_()), "gw"),
+        in_step = " [in the step]"
+        kernels["k_tag_gw (TAG weight gradients, tcgen05 MN-major, TMA ring)" + (in_step if _ops.GW_IMPL == "tc" else " [alternative]")] = (
+            lambda: _lib.check(lib.dss2_tag_bwd_tc2_gw(
+                nt, P(x_l), 32, sp.K, 1, sp.p_drop, P(bits_l), P(gy_l), part_w, run.flat_size, b_off - w_off, P(lvl), lvl.numel() * 4, st_()), "gw"),
+            nt * (128 + 128 + 4), "x + grad_y + sign word in; excludes the 256 B/node hop levels it re-reads")
+        kernels["k_tag_gw_ffma (TAG weight gradients, exact fp32 FFMA, TMA ring)" + (in_step if _ops.GW_IMPL != "tc" else " [alternative]")] = (
+            lambda: _lib.check(lib.dss2_tag_gw_ffma(
+                nt, P(x_l), 32, sp.K, 1, sp.p_drop, P(bits_l), P(gy_l), part_w, run.flat_size, b_off - w_off, P(lvl), lvl.numel() * 4, st_()), "gwf"),
             nt * (128 + 128 + 4), "x + grad_y + sign word in; excludes the 256 B/node hop levels it re-reads")
     else:
         kernels["k_tag_bwd<2,32> (TAG backward, CUDA cores)"] = (lambda: _lib.check(lib.dss2_tag_bwd(
@@ -254,7 +260,7 @@ def main():
         t = time_kernel(fn)
         timed.append({"kernel": kname, "us_per_launch": t * 1e6, "algorithmic_bytes_per_launch": nbytes, "bytes_counted": what,
                       "achieved": nbytes / t / 1e9, "frac": nbytes / t / 1e9 / peak, "traffic": traffic_tab.get(kname.split(" ")[0])})
-    dom = max(timed, key=lambda r: r["us_per_launch"])
+    dom = max((r for r in timed if "[alternative]" not in r["kernel"]), key=lambda r: r["us_per_launch"])
     roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": peak, "unit": "GB/s", "frac": dom["frac"],
                 "traffic": dom["traffic"], "peak_source": peak_src, "us_per_launch": dom["us_per_launch"],
                 "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"], "bytes_counted": dom["bytes_counted"],

@@ -43,6 +43,11 @@ int dss2_sm_count();
     dss2_count_launch(1);                                                                        \
   } while (0)
 
+// large-graph (num_tiles == 0) variants, implemented next to their tiled counterparts
+#define DSS2_NEED_SCRATCH(g, who)                                                                                        \
+  DSS2_CHECK_ARG((g)->scratch && (g)->scratch_bytes >= dss2_generic_scratch_bytes((g)->num_nodes),                        \
+                 "%s: graph larger than a tile needs g->scratch of dss2_generic_scratch_bytes() bytes", who)
+
 // ---------------------------------------------------------------------------------------------
 // device: small utilities
 // ---------------------------------------------------------------------------------------------

@@ -341,6 +341,180 @@ __global__ void __launch_bounds__(EA_THREADS, 1) k_edgeagg_bwd(EaArgs a) {
   }
 }
 
+// -------------------------------------------------------------------------------------------------
+// large-graph path: same arithmetic, P / Q / grad_S live in global scratch ([3][Nt,32]) and every phase is its own launch
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_x8(const EaArgs& a, int64_t n, float (&xv)[FP]) {
+#pragma unroll
+  for (int i = 0; i < FP; ++i) xv[i] = i < a.fn ? a.x[n * a.xs + i] : 0.0f;
+}
+__device__ __forceinline__ void load_a8(const EaArgs& a, uint32_t id, float (&av)[FP]) {
+  const int64_t e = id & 0x7fffffffu;
+  const float sgn = (id >> 31) ? -1.0f : 1.0f;
+#pragma unroll
+  for (int i = 0; i < FP; ++i) av[i] = i < a.fe ? a.ea[e * a.eas + i] : 0.0f;
+  av[0] *= sgn;
+  av[2] *= sgn;
+}
+__device__ __forceinline__ float dot8(const float (&w)[FP], const float (&v)[FP]) {
+  float t = 0.0f;
+#pragma unroll
+  for (int i = 0; i < FP; ++i) t = fmaf(w[i], v[i], t);
+  return t;
+}
+// out[lane] = sum_h M[h] * shfl(vec, h): matrix row/column in registers, vector spread over the lanes
+__device__ __forceinline__ float matvec_shfl(const float (&M)[HID], float vec) {
+  float acc = 0.0f;
+#pragma unroll
+  for (int h = 0; h < HID; ++h) acc = fmaf(M[h], __shfl_sync(0xffffffffu, vec, h), acc);
+  return acc;
+}
+
+// phase 1: P = W1a x + b1, Q = W1b x  [, grad_S = W2^T grad_out]
+__global__ void __launch_bounds__(EA_THREADS) k_ea_nodes_g(EaArgs a, float* P, float* Q, float* GS) {
+  const dss2_graph_t& g = a.g;
+  const int lane = threadIdx.x & 31;
+  const W1Row w1 = load_w1(a, lane);
+  float W2col[HID];
+  if (GS) {
+#pragma unroll
+    for (int o = 0; o < HID; ++o) W2col[o] = a.w2[o * HID + lane];
+  }
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t n = warp; n < g.num_nodes; n += nwarps) {
+    float xv[FP];
+    load_x8(a, n, xv);
+    P[n * HID + lane] = w1.bias + dot8(w1.a, xv);
+    Q[n * HID + lane] = dot8(w1.b, xv);
+    if (GS) GS[n * HID + lane] = matvec_shfl(W2col, a.gout[n * HID + lane]);
+  }
+}
+
+// phase 2 forward: out[n] = W2 * sum_e relu(P[n] + Q[src] + W1c a_e) + deg * b2
+__global__ void __launch_bounds__(EA_THREADS) k_ea_fwd_g(EaArgs a, const float* __restrict__ P, const float* __restrict__ Q) {
+  const dss2_graph_t& g = a.g;
+  const int lane = threadIdx.x & 31;
+  const W1Row w1 = load_w1(a, lane);
+  float W2row[HID];
+#pragma unroll
+  for (int h = 0; h < HID; ++h) W2row[h] = a.w2[lane * HID + h];
+  const float b2 = a.b2[lane];
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t n = warp; n < g.num_nodes; n += nwarps) {
+    const int beg = g.rowptr[n], end = g.rowptr[n + 1];
+    const float p = P[n * HID + lane];
+    float S = 0.0f;
+    for (int z = beg; z < end; ++z) {
+      float av[FP];
+      load_a8(a, g.eid[z], av);
+      S += fmaxf(p + Q[(size_t)g.col[z] * HID + lane] + dot8(w1.c, av), 0.0f);
+    }
+    a.out[n * HID + lane] = fmaf((float)(end - beg), b2, matvec_shfl(W2row, S));
+  }
+}
+
+// phase 2 backward: identical to the tile kernel's edge loop, with global gathers
+__global__ void __launch_bounds__(EA_THREADS, 1) k_ea_bwd_g(EaArgs a, const float* __restrict__ P, const float* __restrict__ Q,
+                                                            const float* __restrict__ GS) {
+  extern __shared__ __align__(16) float smem[];
+  const dss2_graph_t& g = a.g;
+  const int tid = threadIdx.x, lane = tid & 31, warp_in_block = tid >> 5;
+  const int fn = a.fn, fe = a.fe, ld = 2 * fn + fe;
+  const W1Row w1 = load_w1(a, lane);
+  float gW1a[FP], gW1b[FP], gW1c[FP], gb1 = 0.0f, gb2 = 0.0f, gW2[HID];
+#pragma unroll
+  for (int i = 0; i < FP; ++i) gW1a[i] = gW1b[i] = gW1c[i] = 0.0f;
+#pragma unroll
+  for (int o = 0; o < HID; ++o) gW2[o] = 0.0f;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + tid) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t n = warp; n < g.num_nodes; n += nwarps) {
+    const int beg = g.rowptr[n], end = g.rowptr[n + 1];
+    const float p = P[n * HID + lane], q = Q[n * HID + lane], gs = GS[n * HID + lane], go = a.gout[n * HID + lane];
+    float S = 0.0f, gP = 0.0f, gQ = 0.0f;
+    for (int z = beg; z < end; ++z) {
+      const int64_t c = g.col[z];
+      float av[FP];
+      load_a8(a, g.eid[z], av);
+      const float pre_in = p + Q[c * HID + lane] + dot8(w1.c, av);
+      S += fmaxf(pre_in, 0.0f);
+      const float gp = pre_in > 0.0f ? gs : 0.0f;
+      gP += gp;
+#pragma unroll
+      for (int i = 0; i < FP; ++i) gW1c[i] = fmaf(gp, av[i], gW1c[i]);
+      av[0] = -av[0];   // twin edge (n -> c): columns 0 and 2 flipped once more
+      av[2] = -av[2];
+      const float pre_tw = P[c * HID + lane] + q + dot8(w1.c, av);
+      gQ += pre_tw > 0.0f ? GS[c * HID + lane] : 0.0f;
+    }
+    gb1 += gP;
+    gb2 = fmaf((float)(end - beg), go, gb2);
+    float xv[FP];
+    load_x8(a, n, xv);
+#pragma unroll
+    for (int i = 0; i < FP; ++i) {
+      gW1a[i] = fmaf(gP, xv[i], gW1a[i]);
+      gW1b[i] = fmaf(gQ, xv[i], gW1b[i]);
+    }
+#pragma unroll
+    for (int o = 0; o < HID; ++o) gW2[o] = fmaf(__shfl_sync(0xffffffffu, go, o), S, gW2[o]);
+    if (a.gx) {
+      float mine = 0.0f;
+#pragma unroll
+      for (int i = 0; i < FP; ++i) {
+        const float v = warp_sum(fmaf(w1.a[i], gP, w1.b[i] * gQ));
+        if (lane == i) mine = v;
+      }
+      if (lane < fn) {
+        if (a.skip) mine += a.skip[n * a.skip_stride + lane];
+        a.gx[n * fn + lane] = mine;
+      }
+    }
+  }
+  // per-CTA partial (same layout and reduction as k_edgeagg_bwd)
+  constexpr int PER = 3 * FP + 2 + HID;
+  float* red = smem;
+  {
+    float* mine = red + (size_t)warp_in_block * PER * HID;
+#pragma unroll
+    for (int i = 0; i < FP; ++i) {
+      mine[(i)*HID + lane] = gW1a[i];
+      mine[(FP + i) * HID + lane] = gW1b[i];
+      mine[(2 * FP + i) * HID + lane] = gW1c[i];
+    }
+    mine[(3 * FP) * HID + lane] = gb1;
+    mine[(3 * FP + 1) * HID + lane] = gb2;
+#pragma unroll
+    for (int o = 0; o < HID; ++o) mine[(3 * FP + 2 + o) * HID + lane] = gW2[o];
+  }
+  __syncthreads();
+  float* part = a.partials + (size_t)blockIdx.x * a.partial_stride;
+  const int n_w1 = HID * ld, off_b1 = n_w1, off_w2 = n_w1 + HID, off_b2 = off_w2 + HID * HID, total = off_b2 + HID;
+  for (int i = tid; i < total; i += EA_THREADS) {
+    int slot, ln;
+    if (i < n_w1) {
+      const int h = i / ld, c = i - h * ld;
+      slot = c < fn ? c : (c < 2 * fn ? FP + (c - fn) : 2 * FP + (c - 2 * fn));
+      ln = h;
+    } else if (i < off_w2) {
+      slot = 3 * FP;
+      ln = i - off_b1;
+    } else if (i < off_b2) {
+      const int o = (i - off_w2) / HID, h = (i - off_w2) - o * HID;
+      slot = 3 * FP + 2 + o;
+      ln = h;
+    } else {
+      slot = 3 * FP + 1;
+      ln = i - off_b2;
+    }
+    float sum = 0.0f;
+#pragma unroll
+    for (int w8 = 0; w8 < EA_WARPS; ++w8) sum += red[((size_t)w8 * PER + slot) * HID + ln];
+    part[i] = sum;
+  }
+}
+
+inline int ea_gen_grid(int64_t rows) { return (int)max((int64_t)1, min((int64_t)dss2_sm_count() * 8, (rows + EA_WARPS - 1) / EA_WARPS)); }
+
 size_t ea_smem(const dss2_graph_t* g, int bufs) {
   const int TR = round4(g->max_tile_nodes), ER = round4(g->max_tile_edges);
   size_t tile = (size_t)bufs * TR * HID * 4 + (size_t)TR * FP * 4 + (size_t)ER * FP * 4 + (size_t)(TR + 4) * 4 +
@@ -352,8 +526,6 @@ int check_common(const char* who, const dss2_graph_t* g, const float* x, int fn,
                  const float* b1, const float* w2, const float* b2) {
   DSS2_CHECK_ARG(g && x && ea && w1 && b1 && w2 && b2, "%s: null argument", who);
   DSS2_CHECK_ARG(fn >= 1 && fn <= FP && fe >= 1 && fe <= FP, "%s: feature counts (%d node, %d edge) outside 1..%d", who, fn, fe, FP);
-  DSS2_CHECK_ARG(g->num_tiles > 0, "%s: graph has no shared-memory tiling (a graph exceeds %d nodes); large-graph path not built yet",
-                 who, DSS2_TILE_CAP);
   return 0;
 }
 
@@ -378,6 +550,17 @@ extern "C" int dss2_edgeagg_fwd(const dss2_graph_t* g, const float* x, int64_t x
   a.w2 = w2;
   a.b2 = b2;
   a.out = out;
+  if (g->num_nodes == 0) return 0;
+  if (g->num_tiles == 0) {   // large-graph path
+    DSS2_NEED_SCRATCH(g, "dss2_edgeagg_fwd");
+    float* P = g->scratch;
+    float* Q = P + (size_t)g->num_nodes * HID;
+    k_ea_nodes_g<<<ea_gen_grid(g->num_nodes), EA_THREADS, 0, stream>>>(a, P, Q, nullptr);
+    DSS2_LAUNCH_CHECK();
+    k_ea_fwd_g<<<ea_gen_grid(g->num_nodes), EA_THREADS, 0, stream>>>(a, P, Q);
+    DSS2_LAUNCH_CHECK();
+    return 0;
+  }
   size_t smem = ea_smem(g, 2);
   DSS2_CHECK_ARG(smem <= 113 * 1024, "dss2_edgeagg_fwd: tile needs %zu bytes of shared memory", smem);
   if (smem > 48 * 1024) DSS2_CUDA(cudaFuncSetAttribute(k_edgeagg_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -413,6 +596,22 @@ extern "C" int dss2_edgeagg_bwd(const dss2_graph_t* g, const float* x, int64_t x
   a.gx = grad_x;
   a.partials = partials;
   a.partial_stride = partial_stride;
+  DSS2_CHECK_ARG(g->undirected == 1, "dss2_edgeagg_bwd: needs the one-way edge list of the reference's data (reversed twins are derived, "
+                 "not looked up); edge lists that already hold both directions are forward-only");
+  if (g->num_tiles == 0) {   // large-graph path
+    DSS2_NEED_SCRATCH(g, "dss2_edgeagg_bwd");
+    const int64_t Nt = g->num_nodes;
+    float* P = g->scratch;
+    float* Q = P + (size_t)Nt * HID;
+    float* GS = Q + (size_t)Nt * HID;
+    k_ea_nodes_g<<<ea_gen_grid(Nt), EA_THREADS, 0, stream>>>(a, P, Q, GS);
+    DSS2_LAUNCH_CHECK();
+    const size_t red_bytes = (size_t)EA_WARPS * (3 * FP + 2 + HID) * HID * 4;
+    DSS2_CUDA(cudaFuncSetAttribute(k_ea_bwd_g, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)red_bytes));
+    k_ea_bwd_g<<<dss2_sm_count(), EA_THREADS, red_bytes, stream>>>(a, P, Q, GS);
+    DSS2_LAUNCH_CHECK();
+    return 0;
+  }
   size_t smem = ea_smem(g, 4);
   size_t red = (size_t)EA_WARPS * (3 * FP + 2 + HID) * HID * 4;
   if (red > smem) smem = red;

@@ -207,6 +207,8 @@ inline int grid_for(int64_t n, int threads) { return (int)max((int64_t)1, min((i
 
 }  // namespace
 
+extern "C" size_t dss2_generic_scratch_bytes(int64_t Nt) { return ((size_t)4 * Nt * HID + 16384) * sizeof(float); }
+
 extern "C" size_t dss2_graph_workspace_bytes(int64_t Nt, int64_t Et, int32_t B) { return ws_layout(Nt, Et, B).total; }
 
 extern "C" int dss2_graph_build(dss2_graph_t* g, const int64_t* edge_index, int64_t Et, int64_t Nt, const int64_t* ptr,

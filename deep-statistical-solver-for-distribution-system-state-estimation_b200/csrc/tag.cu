@@ -393,6 +393,167 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_tag_bwd(TagBwdArgs a) {
   }
 }
 
+// -------------------------------------------------------------------------------------------------
+// large-graph path (a graph does not fit a tile): hops are separate SpMM launches over the global CSR, the transform streams rows.
+//   forward : L1 = A x, L2 = A L1 (scratch) ; y = sum_k L_k W_k^T + b [+ dropout, ReLU, sign word, residual]
+//   backward: G0 = grad_y * [y>0]/(1-p), G1 = A G0, G2 = A G1 ; grad_x = sum_k G_k W_k (same transform kernel, transposed weights) ;
+//             grad_W_k = G_k^T x, grad_b via the row-streaming tcgen05 kernel k_tag_gw (tag_tc2.cu) - it never needed tiles
+// -------------------------------------------------------------------------------------------------
+constexpr int GEN_THREADS = 256;
+
+__global__ void __launch_bounds__(GEN_THREADS) k_hop_generic(const int* __restrict__ rowptr, const int* __restrict__ col,
+                                                             const float* __restrict__ w, const float* __restrict__ X, float* __restrict__ Y,
+                                                             int64_t Nt) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t n = warp; n < Nt; n += nwarps) {
+    float acc = 0.0f;
+    for (int z = rowptr[n]; z < rowptr[n + 1]; ++z) acc = fmaf(w[z], X[(size_t)col[z] * HID + lane], acc);   // CSR order = PyG scatter order
+    Y[(size_t)n * HID + lane] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(GEN_THREADS) k_mask_grad(const float* __restrict__ gy, const uint32_t* __restrict__ bits, int cout,
+                                                           float scale, float* __restrict__ G0, int64_t Nt) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < Nt * HID; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = i >> 5;
+    const int c = (int)(i & 31);
+    float v = c < cout ? gy[n * cout + c] : 0.0f;
+    if (bits) v = ((bits[n] >> c) & 1u) ? v * scale : 0.0f;
+    G0[i] = v;
+  }
+}
+
+// WT[k][j][c] = W[k][c][j] for c < cout, 0 beyond: the transform kernel then yields grad_x from the hop levels of the gradient
+__global__ void k_transpose_w(const float* __restrict__ W, int cout, int K, float* __restrict__ WT) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (K + 1) * HID * HID; i += gridDim.x * blockDim.x) {
+    const int k = i / (HID * HID), j = (i / HID) % HID, c = i % HID;
+    WT[i] = c < cout ? W[((size_t)k * cout + c) * HID + j] : 0.0f;
+  }
+}
+
+struct DenseArgs {
+  const float* L[MAXK + 1];   // hop levels [Nt,32]
+  const float* w;             // [K+1][cout][32]
+  const float* bias;          // may be NULL
+  int cout, act, drop_mode;
+  float scale;
+  uint32_t keep_thr;
+  const uint64_t* rng;
+  uint32_t layer_uid;
+  const uint8_t* mask;
+  const float* res;
+  int64_t res_stride;
+  float* y;
+  uint32_t* bits;
+  int64_t Nt;
+};
+
+template <int K>
+__global__ void __launch_bounds__(GEN_THREADS, 2) k_dense_tag(DenseArgs a) {
+  __shared__ __align__(16) float stage[GEN_THREADS / 32][K + 1][4][HID];   // per warp: 4 rows of every level
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int cout = a.cout;
+  float W[K + 1][HID];
+#pragma unroll
+  for (int k = 0; k <= K; ++k)
+#pragma unroll
+    for (int j4 = 0; j4 < HID / 4; ++j4) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (lane < cout) v = *reinterpret_cast<const float4*>(a.w + ((size_t)k * cout + lane) * HID + 4 * j4);
+      W[k][4 * j4 + 0] = v.x;
+      W[k][4 * j4 + 1] = v.y;
+      W[k][4 * j4 + 2] = v.z;
+      W[k][4 * j4 + 3] = v.w;
+    }
+  const float bias = (a.bias && lane < cout) ? a.bias[lane] : 0.0f;
+  uint2 key = make_uint2(0u, 0u);
+  uint32_t step_lo = 0;
+  if (a.drop_mode == 1) {
+    const uint64_t seed = a.rng[0], step = a.rng[1];
+    key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32) ^ (a.layer_uid * 0x9E3779B9u) ^ (uint32_t)(step >> 32));
+    step_lo = (uint32_t)step;
+  }
+  const int64_t nblk = (a.Nt + 3) >> 2;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t blk = warp; blk < nblk; blk += nwarps) {
+    const int64_t r0 = blk * 4;
+#pragma unroll
+    for (int k = 0; k <= K; ++k)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) stage[wib][k][i][lane] = (r0 + i < a.Nt) ? a.L[k][(size_t)(r0 + i) * HID + lane] : 0.0f;
+    __syncwarp();
+    float acc[4] = {bias, bias, bias, bias};
+#pragma unroll
+    for (int k = 0; k <= K; ++k)
+#pragma unroll
+      for (int j4 = 0; j4 < HID / 4; ++j4) {
+        float4 v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = *reinterpret_cast<const float4*>(&stage[wib][k][i][4 * j4]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i] = fmaf(v[i].x, W[k][4 * j4 + 0], acc[i]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i] = fmaf(v[i].y, W[k][4 * j4 + 1], acc[i]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i] = fmaf(v[i].z, W[k][4 * j4 + 2], acc[i]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i] = fmaf(v[i].w, W[k][4 * j4 + 3], acc[i]);
+      }
+    uint32_t rnd[4] = {0u, 0u, 0u, 0u};
+    if (a.act && a.drop_mode == 1) {
+      const uint4 q = philox4x32_10(make_uint4((uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)lane, step_lo), key);
+      rnd[0] = q.x;
+      rnd[1] = q.y;
+      rnd[2] = q.z;
+      rnd[3] = q.w;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int64_t n = r0 + i;
+      if (n >= a.Nt) break;
+      float v = acc[i];
+      if (a.act) {
+        bool keep = true;
+        if (a.drop_mode == 1) keep = rnd[i] < a.keep_thr;
+        else if (a.drop_mode == 2) keep = a.mask[n * HID + lane] != 0;
+        if (a.drop_mode != 0) v = keep ? v * a.scale : 0.0f;
+        v = fmaxf(v, 0.0f);
+        const uint32_t word = __ballot_sync(0xffffffffu, v > 0.0f);
+        if (lane == 0 && a.bits) a.bits[n] = word;
+      }
+      if (lane < cout) {
+        if (a.res) v += a.res[n * a.res_stride + lane];
+        a.y[n * cout + lane] = v;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+inline int gen_grid(int64_t work_items, int per_block) {
+  return (int)max((int64_t)1, min((int64_t)dss2_sm_count() * 8, (work_items + per_block - 1) / per_block));
+}
+
+template <int K>
+int launch_dense(const DenseArgs& a, cudaStream_t s) {
+  k_dense_tag<K><<<gen_grid((a.Nt + 3) / 4, GEN_THREADS / 32), GEN_THREADS, 0, s>>>(a);
+  DSS2_LAUNCH_CHECK();
+  return 0;
+}
+int launch_dense_k(const DenseArgs& a, int K, cudaStream_t s) {
+  switch (K) {
+    case 1: return launch_dense<1>(a, s);
+    case 2: return launch_dense<2>(a, s);
+    default: return launch_dense<3>(a, s);
+  }
+}
+int launch_hop(const dss2_graph_t* g, const float* X, float* Y, cudaStream_t s) {
+  k_hop_generic<<<gen_grid(g->num_nodes, GEN_THREADS / 32), GEN_THREADS, 0, s>>>(g->rowptr, g->col, g->w, X, Y, g->num_nodes);
+  DSS2_LAUNCH_CHECK();
+  return 0;
+}
+
 __global__ void k_reduce_partials(const float* __restrict__ partials, int64_t stride, int num, int64_t count, float* grad, int accumulate) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
     float s = 0.0f;
@@ -463,9 +624,36 @@ extern "C" int dss2_tag_fwd(const dss2_graph_t* g, const float* x, const float* 
   DSS2_CHECK_ARG(p_drop >= 0.0f && p_drop < 1.0f, "dss2_tag_fwd: dropout p %f outside [0,1)", p_drop);
   DSS2_CHECK_ARG(!(act && drop_mode == 1) || rng_state, "dss2_tag_fwd: philox dropout needs rng_state");
   DSS2_CHECK_ARG(!(act && drop_mode == 2) || mask, "dss2_tag_fwd: mask dropout needs a mask");
-  DSS2_CHECK_ARG(g->num_tiles > 0, "dss2_tag_fwd: graph has no shared-memory tiling (a graph exceeds %d nodes); "
-                 "the large-graph layer path is not built yet", DSS2_TILE_CAP);
   if (g->num_nodes == 0) return 0;
+  if (g->num_tiles == 0) {   // large-graph path
+    DSS2_NEED_SCRATCH(g, "dss2_tag_fwd");
+    const int64_t Nt = g->num_nodes;
+    float* lv = g->scratch;
+    DenseArgs d = {};
+    d.L[0] = x;
+    for (int k = 1; k <= K; ++k) {
+      if (launch_hop(g, d.L[k - 1], lv + (size_t)(k - 1) * Nt * HID, stream)) return -3;
+      d.L[k] = lv + (size_t)(k - 1) * Nt * HID;
+    }
+    d.w = w;
+    d.bias = bias;
+    d.cout = cout;
+    d.act = act;
+    if (p_drop == 0.0f) drop_mode = 0;
+    d.drop_mode = act ? drop_mode : 0;
+    d.scale = 1.0f / (float)(1.0 - (double)p_drop);
+    double thr_ = (1.0 - (double)p_drop) * 4294967296.0;
+    d.keep_thr = thr_ >= 4294967295.0 ? 0xffffffffu : (uint32_t)thr_;
+    d.rng = rng_state;
+    d.layer_uid = layer_uid;
+    d.mask = mask;
+    d.res = res;
+    d.res_stride = res_stride;
+    d.y = y;
+    d.bits = act_bits;
+    d.Nt = Nt;
+    return launch_dense_k(d, K, stream);
+  }
   TagFwdArgs a;
   a.g = *g;
   a.x = x;
@@ -505,7 +693,33 @@ extern "C" int dss2_tag_bwd(const dss2_graph_t* g, const float* x, const float* 
   DSS2_CHECK_ARG(!act || act_bits, "dss2_tag_bwd: activation layers need act_bits from the forward");
   DSS2_CHECK_ARG(partial_stride >= (int64_t)(K + 1) * cout * HID + cout, "dss2_tag_bwd: partial_stride too small");
   DSS2_CHECK_ARG(bias_offset >= (int64_t)(K + 1) * cout * HID || bias_offset <= -(int64_t)cout, "dss2_tag_bwd: bias_offset overlaps grad_W");
-  DSS2_CHECK_ARG(g->num_tiles > 0, "dss2_tag_bwd: graph has no shared-memory tiling; large-graph path not built yet");
+  if (g->num_nodes == 0) return 0;
+  if (g->num_tiles == 0) {   // large-graph path: hops on the masked output gradient, then two GEMMs
+    DSS2_NEED_SCRATCH(g, "dss2_tag_bwd");
+    DSS2_CHECK_ARG(K <= 2, "dss2_tag_bwd: the large-graph backward supports K <= 2 (weight-gradient kernel)");
+    const int64_t Nt = g->num_nodes;
+    float* lvl = g->scratch;                         // [K][Nt,32] = A g, A^2 g  (layout k_tag_gw expects)
+    float* G0 = g->scratch + (size_t)K * Nt * HID;   // masked, zero-padded gradient
+    float* WT = G0 + (size_t)Nt * HID;               // transposed weights
+    const float scale = 1.0f / (float)(1.0 - (double)p_drop);
+    k_mask_grad<<<gen_grid(Nt * HID, GEN_THREADS), GEN_THREADS, 0, stream>>>(grad_y, act ? act_bits : nullptr, cout, scale, G0, Nt);
+    DSS2_LAUNCH_CHECK();
+    DenseArgs d = {};
+    d.L[0] = G0;
+    for (int k = 1; k <= K; ++k) {
+      if (launch_hop(g, d.L[k - 1], lvl + (size_t)(k - 1) * Nt * HID, stream)) return -3;
+      d.L[k] = lvl + (size_t)(k - 1) * Nt * HID;
+    }
+    k_transpose_w<<<12, 256, 0, stream>>>(w, cout, K, WT);
+    DSS2_LAUNCH_CHECK();
+    d.w = WT;
+    d.cout = HID;
+    d.y = grad_x;
+    d.Nt = Nt;
+    if (launch_dense_k(d, K, stream)) return -3;
+    return dss2_tag_gw_ffma(Nt, x, cout, K, act, p_drop, act_bits, grad_y, partials, partial_stride, bias_offset, lvl,
+                               dss2_tag_bwd_tc2_workspace_bytes(Nt, K), stream_);
+  }
   TagBwdArgs a;
   a.g = *g;
   a.x = x;

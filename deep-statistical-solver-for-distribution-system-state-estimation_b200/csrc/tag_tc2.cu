@@ -609,6 +609,149 @@ __global__ void __launch_bounds__(128, 1) k_tag_gw(GwArgs a) {
   if (warp == 0) tc::tmem_dealloc(tmem, 64);
 }
 
+// -------------------------------------------------------------------------------------------------
+// The same weight gradients on the fp32 FMA pipe, exact fp32 (no TF32 split, no TMEM accumulation order): a pure streaming
+// kernel - no hops, no dependency chain - so the CUDA cores are not the handicap they are in the layer kernels.  The bulk-copy
+// ring lands raw 64-row chunks; a short pre-pass applies the dropout/ReLU mask to grad_y (and sums the bias gradient); then
+// thread (i = input feature, cg = group of 4 output columns) keeps 4(K+1) accumulators and walks the chunk's rows:
+// per row 1 LDS (x[r][i], conflict free) + (K+1) broadcast LDS.128 + 4(K+1) FFMA.
+// -------------------------------------------------------------------------------------------------
+constexpr int GWF_STAGES = 4;
+constexpr int GWF_THREADS = 256;
+#define GWF_STAGE_BYTES(K) ((uint32_t)((K) + 2) * GW_TILE + 256u)   // x, grad_y, K hop levels, sign words
+template <int K>
+size_t gwf_smem() { return 1024 + GWF_STAGES * GWF_STAGE_BYTES(K) + 2 * GW_TILE + 32 * 33 * 4 + 64; }
+
+template <int K>
+__global__ void __launch_bounds__(GWF_THREADS, 1) k_tag_gw_ffma(GwArgs a) {
+  extern __shared__ char raw[];
+  char* base = align1024(raw);
+  constexpr uint32_t STAGE = GWF_STAGE_BYTES(K);
+  char* stage0 = base;
+  float* G0 = reinterpret_cast<float*>(stage0 + GWF_STAGES * STAGE);   // [2][64][32] masked, scaled grad_y (double buffered)
+  float* red = G0 + 2 * GW_ROWS * 32;                                   // [32][33] bias-gradient partials
+  uint64_t* full = reinterpret_cast<uint64_t*>(red + 32 * 33);
+  const int tid = threadIdx.x;
+  const int cout = a.cout;
+  if (tid == 0) {
+    for (int s = 0; s < GWF_STAGES; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const int64_t num_chunks = (a.num_nodes + GW_ROWS - 1) / GW_ROWS;
+  const int64_t full_chunks = a.num_nodes / GW_ROWS;
+  const uint32_t gy_bytes = (uint32_t)(GW_ROWS * cout * 4);
+  const uint32_t tx = GW_TILE * (K + 1) + gy_bytes + (a.bits ? 256u : 0u);
+  auto issue = [&](int64_t ch, int s) {
+    if (ch >= full_chunks) return;
+    char* st = stage0 + (size_t)s * STAGE;
+    const int64_t n = ch * GW_ROWS;
+    mbar_expect_tx(&full[s], tx);
+    bulk_g2s(st, a.x + n * 32, GW_TILE, &full[s]);
+    bulk_g2s(st + GW_TILE, a.gy + n * cout, gy_bytes, &full[s]);
+#pragma unroll
+    for (int k = 0; k < K; ++k) bulk_g2s(st + (2 + k) * GW_TILE, a.lvl + ((int64_t)k * a.num_nodes + n) * 32, GW_TILE, &full[s]);
+    if (a.bits) bulk_g2s(st + (K + 2) * GW_TILE, a.bits + n, 256, &full[s]);
+  };
+  if (tid == 0)
+    for (int i = 0; i < GWF_STAGES - 1; ++i) issue(blockIdx.x + (int64_t)i * gridDim.x, i);
+
+  const uint32_t cq = tid & 7, rs = tid >> 3;          // pre-pass mapping: 16-byte column chunk, row (and row + 32)
+  const int i_feat = tid & 31, c0 = (tid >> 5) * 4;    // main mapping
+  float gb[4] = {0.f, 0.f, 0.f, 0.f};
+  float acc[K + 1][4];
+#pragma unroll
+  for (int k = 0; k <= K; ++k)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[k][e] = 0.0f;
+
+  int it = 0;
+  for (int64_t ch = blockIdx.x; ch < num_chunks; ch += gridDim.x, ++it) {
+    const int s = it % GWF_STAGES;
+    char* st = stage0 + (size_t)s * STAGE;
+    float* g0 = G0 + (it & 1) * GW_ROWS * 32;
+    if (ch < full_chunks) {
+      mbar_wait(&full[s], (uint32_t)((it / GWF_STAGES) & 1));
+    } else {   // the one ragged chunk at the end of the batch: bounded loads by all threads into the (idle) slot, zero filled
+      const int64_t n0 = ch * GW_ROWS;
+      for (int idx = tid; idx < GW_ROWS * 32; idx += GWF_THREADS) {
+        const int r = idx >> 5, j = idx & 31;
+        const bool inb = n0 + r < a.num_nodes;
+        reinterpret_cast<float*>(st)[idx] = inb ? a.x[(n0 + r) * 32 + j] : 0.0f;
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+          reinterpret_cast<float*>(st + (2 + k) * GW_TILE)[idx] = inb ? a.lvl[((int64_t)k * a.num_nodes + n0 + r) * 32 + j] : 0.0f;
+        if (j < cout) reinterpret_cast<float*>(st + GW_TILE)[r * cout + j] = inb ? a.gy[(n0 + r) * cout + j] : 0.0f;
+        if (a.bits && j == 0) reinterpret_cast<uint32_t*>(st + (K + 2) * GW_TILE)[r] = inb ? a.bits[n0 + r] : 0u;
+      }
+      __syncthreads();
+    }
+    // pre-pass: masked, scaled output gradient -> g0, bias gradient
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const uint32_t r = rs + 32 * h;
+      float4 vg;
+      if (cout == 32) {
+        vg = *reinterpret_cast<const float4*>(st + GW_TILE + r * 128 + cq * 16);
+      } else {
+        const float* gp = reinterpret_cast<const float*>(st + GW_TILE) + r * cout;
+        float t4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if ((int)(cq * 4 + e) < cout) t4[e] = gp[cq * 4 + e];
+        vg = make_float4(t4[0], t4[1], t4[2], t4[3]);
+      }
+      if (a.bits) {
+        const uint32_t w4 = reinterpret_cast<const uint32_t*>(st + (K + 2) * GW_TILE)[r] >> (cq * 4);
+        vg.x = (w4 & 1u) ? vg.x * a.scale : 0.0f;
+        vg.y = (w4 & 2u) ? vg.y * a.scale : 0.0f;
+        vg.z = (w4 & 4u) ? vg.z * a.scale : 0.0f;
+        vg.w = (w4 & 8u) ? vg.w * a.scale : 0.0f;
+      }
+      gb[0] += vg.x;
+      gb[1] += vg.y;
+      gb[2] += vg.z;
+      gb[3] += vg.w;
+      *reinterpret_cast<float4*>(g0 + r * 32 + cq * 4) = vg;
+    }
+    __syncthreads();   // g0 complete; every thread has left the main loop of the previous chunk -> its slot may be refilled
+    if (tid == 0) issue(ch + (int64_t)(GWF_STAGES - 1) * gridDim.x, (it + GWF_STAGES - 1) % GWF_STAGES);
+    const float* xs = reinterpret_cast<const float*>(st) + i_feat;
+#pragma unroll 4
+    for (int r = 0; r < GW_ROWS; ++r) {
+      const float xv = xs[r * 32];
+      const float4 l0 = *reinterpret_cast<const float4*>(g0 + r * 32 + c0);
+      acc[0][0] = fmaf(l0.x, xv, acc[0][0]);
+      acc[0][1] = fmaf(l0.y, xv, acc[0][1]);
+      acc[0][2] = fmaf(l0.z, xv, acc[0][2]);
+      acc[0][3] = fmaf(l0.w, xv, acc[0][3]);
+#pragma unroll
+      for (int k = 1; k <= K; ++k) {
+        const float4 lk = *reinterpret_cast<const float4*>(st + (1 + k) * GW_TILE + r * 128 + c0 * 4);
+        acc[k][0] = fmaf(lk.x, xv, acc[k][0]);
+        acc[k][1] = fmaf(lk.y, xv, acc[k][1]);
+        acc[k][2] = fmaf(lk.z, xv, acc[k][2]);
+        acc[k][3] = fmaf(lk.w, xv, acc[k][3]);
+      }
+    }
+  }
+  // ---- this CTA's partial sums ----
+  float* part = a.partials + (size_t)blockIdx.x * a.partial_stride;
+#pragma unroll
+  for (int k = 0; k <= K; ++k)
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (c0 + e < cout) part[((size_t)k * cout + c0 + e) * 32 + i_feat] = acc[k][e];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) red[rs * 33 + cq * 4 + e] = gb[e];
+  __syncthreads();
+  if (tid < cout) {
+    float sum = 0.0f;
+    for (int r = 0; r < 32; ++r) sum += red[r * 33 + tid];
+    part[a.bias_offset + tid] = sum;
+  }
+}
+
 size_t tc2_smem(int K, int nb) { return 1024 + (size_t)(K + 1) * 2 * W_TILE + 4 * (size_t)nb * 128 * tc::ROW_BYTES + 256; }   // 89 KB (2 CTAs/SM) or 153 KB
 size_t gw_smem() { return 1024 + 10 * GW_TILE + GW_STAGES * GW_STAGE_BYTES + 128; }
 
@@ -726,6 +869,42 @@ extern "C" int dss2_tag_bwd_tc2_gw(int64_t num_nodes, const float* x, int cout, 
     DSS2_CUDA(cudaFuncSetAttribute(k_tag_gw<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_tag_gw<2><<<grid, 128, smem, stream>>>(b);
   }
+  DSS2_LAUNCH_CHECK();
+  return 0;
+}
+
+// exact fp32 variant of the weight-gradient pass (CUDA cores); same contract, K up to 3
+extern "C" int dss2_tag_gw_ffma(int64_t num_nodes, const float* x, int cout, int K, int act, float p_drop, const uint32_t* act_bits,
+                                const float* grad_y, float* partials, int64_t partial_stride, int64_t bias_offset, const void* ws,
+                                size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DSS2_CHECK_ARG(x && grad_y && partials && ws, "dss2_tag_gw_ffma: null argument");
+  DSS2_CHECK_ARG(cout >= 1 && cout <= HID && K >= 1 && K <= 3, "dss2_tag_gw_ffma: cout %d / K %d unsupported", cout, K);
+  DSS2_CHECK_ARG(!act || act_bits, "dss2_tag_gw_ffma: activation layers need act_bits from the forward");
+  DSS2_CHECK_ARG(ws_bytes >= (size_t)K * num_nodes * HID * sizeof(float), "dss2_tag_gw_ffma: workspace too small");
+  DSS2_CHECK_ARG(partial_stride >= (int64_t)(K + 1) * cout * HID + cout, "dss2_tag_gw_ffma: partial_stride too small");
+  DSS2_CHECK_ARG((((uintptr_t)x | (uintptr_t)grad_y | (uintptr_t)ws | (uintptr_t)act_bits) & 15) == 0 && (num_nodes * HID * 4) % 16 == 0,
+                 "dss2_tag_gw_ffma: x, grad_y, act_bits and ws must be 16-byte aligned (bulk-copy sources)");
+  if (num_nodes == 0) return 0;
+  GwArgs b;
+  b.num_nodes = num_nodes;
+  b.x = x;
+  b.gy = grad_y;
+  b.bits = act ? act_bits : nullptr;
+  b.lvl = (const float*)ws;
+  b.cout = cout;
+  b.scale = 1.0f / (float)(1.0 - (double)p_drop);
+  b.partials = partials;
+  b.partial_stride = partial_stride;
+  b.bias_offset = bias_offset;
+  const int grid = dss2_sm_count();    // = dss2_num_partials(): every partial row is written
+#define DSS2_GWF(KK)                                                                                                     \
+  {                                                                                                                      \
+    DSS2_CUDA(cudaFuncSetAttribute(k_tag_gw_ffma<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gwf_smem<KK>())); \
+    k_tag_gw_ffma<KK><<<grid, GWF_THREADS, gwf_smem<KK>(), stream>>>(b);                                                 \
+  }
+  if (K == 1) DSS2_GWF(1) else if (K == 2) DSS2_GWF(2) else DSS2_GWF(3)
+#undef DSS2_GWF
   DSS2_LAUNCH_CHECK();
   return 0;
 }

@@ -242,6 +242,235 @@ __global__ void __launch_bounds__(WLS_THREADS) k_wls(WlsArgs a) {
   }
 }
 
+// -------------------------------------------------------------------------------------------------
+// large-graph path (a scenario with more buses than a tile holds): the same passes A-E as k_wls, one
+// launch per pass, the per-bus / per-branch intermediates in the graph's global scratch
+// (6 Nt + 4 Et floats).  Same arithmetic (wls_math.cuh), same fixed-order fp64 reductions.
+// -------------------------------------------------------------------------------------------------
+struct WlsScratch {
+  float *v, *th, *ap, *aq, *gv, *gth;   // [Nt]
+  float *pf, *qf, *pt, *qt;             // [Et]; backward reuses pf/qf/pt as dV_i / dV_j / d delta
+};
+
+__device__ __forceinline__ void wls_block_partial(double (&acc)[S_N], double* partial_row) {
+  __shared__ double s_red[S_N][WLS_THREADS / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int q = 0; q < S_N; ++q) {
+    double v = warp_sum(acc[q]);
+    if (lane == 0) s_red[q][warp] = v;
+  }
+  __syncthreads();
+  if (tid < S_N) {
+    double v = 0;
+    for (int w = 0; w < WLS_THREADS / 32; ++w) v += s_red[tid][w];
+    partial_row[tid] = v;
+  }
+}
+
+__global__ void __launch_bounds__(WLS_THREADS) k_wls_g_state(WlsArgs a, WlsScratch s) {
+  const float xs0 = a.stats[8], xm0 = a.stats[0];
+  for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < a.g.num_nodes; n += (int64_t)gridDim.x * blockDim.x) {
+    float o0 = a.out[2 * n], o1 = a.out[2 * n + 1];
+    float slack = a.x[n * a.xs + 9];
+    float th = o1 * (1.0f - slack);
+    s.v[n] = o0 * xs0 + xm0;
+    s.th[n] = th;
+    if (a.mask_inplace) a.out[2 * n + 1] = th;
+  }
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(WLS_THREADS) k_wls_g_branch(WlsArgs a, WlsScratch s) {
+  __shared__ WlsStats st;
+  const dss2_graph_t& g = a.g;
+  const int tid = threadIdx.x;
+  if (tid < 28) ((float*)&st)[tid] = a.stats[tid];
+  __syncthreads();
+  const WlsGrid grid = wls_grid(a.vminmax[0], a.vminmax[1]);
+  const WlsCoefs k = a.k;
+  const int64_t Nt = g.num_nodes, Et = g.num_edges;
+  const int64_t* ei = g.edge_index;
+  double acc[S_N] = {0, 0, 0, 0, 0};
+  float cE = 0.f, mth = 0.f, ml = 0.f;
+  if (BWD) {
+    float gl = a.grad_loss ? a.grad_loss[0] : 1.0f;
+    cE = gl / (float)Et;
+    mth = (float)(a.sums[S_TH] / (double)Et);
+    ml = (float)(a.sums[S_LOAD] / (double)Et);
+  }
+  (void)Nt;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + tid; e < Et; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = ei[e], j = ei[Et + e];
+    const float* row = a.ea + e * a.eas;
+    WlsBranchIn in;
+    in.vi = s.v[i];
+    in.vj = s.v[j];
+    in.thi = s.th[i];
+    in.thj = s.th[j];
+    in.G = row[6];
+    in.B = row[7];
+    in.Gs = row[8];
+    in.Bs = row[9];
+    in.shift = row[11];
+    in.rating = row[12];
+    WlsBranch b;
+    wls_branch_forward(in, grid, b);
+    float eZ0 = wls_unnorm(row[0], st.es[0], st.em[0]), eR0 = wls_unnorm(row[1], st.es[1], st.em[1]);
+    float eZ1 = wls_unnorm(row[2], st.es[2], st.em[2]), eR1 = wls_unnorm(row[3], st.es[3], st.em[3]);
+    if (!BWD) {
+      s.pf[e] = b.pf;
+      s.qf[e] = b.qf;
+      s.pt[e] = b.pt;
+      s.qt[e] = b.qt;
+      acc[S_JE] += (double)wls_branch_residual(eZ0, eR0, eZ1, eR1, b.pf, b.qf, k);
+      acc[S_TH] += (double)fmaxf(fabsf(b.delta) - 0.5f, 0.0f);
+      acc[S_LOAD] += (double)fmaxf(b.loading - 1.5f, 0.0f);
+    } else {
+      float dpf = -s.ap[i] - 2.0f * k.lam_pf * eR0 * (eZ0 - b.pf) * cE;
+      float dqf = -s.aq[i] - 2.0f * k.lam_pf * eR1 * (eZ1 - b.qf) * cE;
+      float dpt = -s.ap[j], dqt = -s.aq[j];
+      float ad = fabsf(b.delta);
+      float ddelta = (ad - 0.5f > 0.0f) ? 2.0f * k.lam_reg * mth * cE * (b.delta > 0.0f ? 1.0f : -1.0f) : 0.0f;
+      float dload = (b.loading - 1.5f > 0.0f) ? 2.0f * k.lam_reg * ml * cE : 0.0f;
+      float dvi, dvj, ddel;
+      wls_branch_backward(in, grid, b, dpf, dqf, dpt, dqt, ddelta, dload, dvi, dvj, ddel);
+      s.pf[e] = dvi;
+      s.qf[e] = dvj;
+      s.pt[e] = ddel;
+    }
+  }
+  if (!BWD) wls_block_partial(acc, a.partial + (size_t)blockIdx.x * S_N);
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(WLS_THREADS) k_wls_g_bus(WlsArgs a, WlsScratch s, int partial_base) {
+  __shared__ WlsStats st;
+  const dss2_graph_t& g = a.g;
+  const int tid = threadIdx.x;
+  if (tid < 28) ((float*)&st)[tid] = a.stats[tid];
+  __syncthreads();
+  const WlsCoefs k = a.k;
+  const int64_t Nt = g.num_nodes;
+  double acc[S_N] = {0, 0, 0, 0, 0};
+  float cN = 0.f, mv = 0.f;
+  if (BWD) {
+    float gl = a.grad_loss ? a.grad_loss[0] : 1.0f;
+    cN = gl / (float)Nt;
+    mv = (float)(a.sums[S_V] / (double)Nt);
+  }
+  for (int64_t n = blockIdx.x * (int64_t)blockDim.x + tid; n < Nt; n += (int64_t)gridDim.x * blockDim.x) {
+    float sp_to = 0.f, sq_to = 0.f, sp_fr = 0.f, sq_fr = 0.f;
+    for (int z = g.rowptr[n]; z < g.rowptr[n + 1]; ++z) {
+      const uint32_t id = g.eid[z];
+      const int64_t e = id & 0x7fffffffu;
+      if (id >> 31) {
+        sp_fr += s.pf[e];
+        sq_fr += s.qf[e];
+      } else {
+        sp_to += s.pt[e];
+        sq_to += s.qt[e];
+      }
+    }
+    float p_bus = -sp_to - sp_fr, q_bus = -sq_to - sq_fr;
+    WlsBus b;
+    wls_bus_load(a.x + n * a.xs, a.out[2 * n], a.out[2 * n + 1], st, b);
+    b.v = s.v[n];
+    b.th = s.th[n];
+    if (!BWD) {
+      acc[S_JN] += (double)wls_bus_residual(b, p_bus, q_bus, k);
+      acc[S_V] += (double)wls_bus_vband(b);
+    } else {
+      s.ap[n] = -2.0f * k.lam_p * b.R[2] * (b.Z[2] - p_bus) * cN;
+      s.aq[n] = -2.0f * k.lam_p * b.R[3] * (b.Z[3] - q_bus) * cN;
+      float band = (b.v - 1.1f > 0.0f ? 1.0f : 0.0f) - (0.9f - b.v > 0.0f ? 1.0f : 0.0f);
+      s.gv[n] = -2.0f * k.lam_v * b.R[0] * (b.Z[0] - b.v) * cN + 2.0f * k.lam_reg * mv * cN * band;
+      s.gth[n] = -2.0f * k.lam_v * b.R[1] * (b.Z[1] - b.th) * cN;
+    }
+  }
+  if (!BWD) wls_block_partial(acc, a.partial + (size_t)(partial_base + blockIdx.x) * S_N);
+}
+
+// one CTA: add the per-CTA partials in CTA order (fp64), publish the sums and the loss
+__global__ void k_wls_g_finish(WlsArgs a, int rows) {
+  __shared__ double s_sum[S_N];
+  const int tid = threadIdx.x;
+  if (tid < S_N) {
+    double v = 0;
+    for (int c = 0; c < rows; ++c) v += a.partial[(size_t)c * S_N + tid];
+    a.sums[tid] = v;
+    s_sum[tid] = v;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double n = (double)a.g.num_nodes, e = (double)a.g.num_edges;
+    double jv = s_sum[S_V] / n, jt = s_sum[S_TH] / e, jl = s_sum[S_LOAD] / e;
+    double lam = (double)a.k.lam_reg;
+    a.loss[0] = (float)(s_sum[S_JN] / n + s_sum[S_JE] / e + lam * jv * jv + lam * jt * jt + lam * jl * jl);
+  }
+}
+
+__global__ void __launch_bounds__(WLS_THREADS) k_wls_g_gather(WlsArgs a, WlsScratch s) {
+  const dss2_graph_t& g = a.g;
+  const float xs0 = a.stats[8];
+  for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < g.num_nodes; n += (int64_t)gridDim.x * blockDim.x) {
+    float gv = s.gv[n], gth = s.gth[n];
+    for (int z = g.rowptr[n]; z < g.rowptr[n + 1]; ++z) {
+      const uint32_t id = g.eid[z];
+      const int64_t e = id & 0x7fffffffu;
+      if (id >> 31) {
+        gv += s.pf[e];
+        gth += s.pt[e];
+      } else {
+        gv += s.qf[e];
+        gth -= s.pt[e];
+      }
+    }
+    float slack = a.x[n * a.xs + 9];
+    a.grad_out[2 * n] = gv * xs0;
+    a.grad_out[2 * n + 1] = gth * (1.0f - slack);
+  }
+}
+
+int wls_generic(const WlsArgs& a, bool want_grad, cudaStream_t stream) {
+  const dss2_graph_t* g = &a.g;
+  const int64_t Nt = g->num_nodes, Et = g->num_edges;
+  DSS2_NEED_SCRATCH(g, "dss2_wls_fwd_bwd");
+  DSS2_CHECK_ARG((size_t)(6 * Nt + 4 * Et) * sizeof(float) <= g->scratch_bytes, "dss2_wls_fwd_bwd: graph scratch too small for %lld branches",
+                 (long long)Et);
+  WlsScratch s;
+  s.v = g->scratch;
+  s.th = s.v + Nt;
+  s.ap = s.th + Nt;
+  s.aq = s.ap + Nt;
+  s.gv = s.aq + Nt;
+  s.gth = s.gv + Nt;
+  s.pf = s.gth + Nt;
+  s.qf = s.pf + Et;
+  s.pt = s.qf + Et;
+  s.qt = s.pt + Et;
+  const int half = dss2_sm_count() * 4;   // the partial buffer holds sm*8 rows: branches first, buses after
+  const int gn = (int)max((int64_t)1, min((int64_t)half, (Nt + WLS_THREADS - 1) / WLS_THREADS));
+  const int ge = (int)max((int64_t)1, min((int64_t)half, (Et + WLS_THREADS - 1) / WLS_THREADS));
+  k_wls_g_state<<<gn, WLS_THREADS, 0, stream>>>(a, s);
+  DSS2_LAUNCH_CHECK();
+  k_wls_g_branch<false><<<ge, WLS_THREADS, 0, stream>>>(a, s);
+  DSS2_LAUNCH_CHECK();
+  k_wls_g_bus<false><<<gn, WLS_THREADS, 0, stream>>>(a, s, ge);
+  DSS2_LAUNCH_CHECK();
+  k_wls_g_finish<<<1, 32, 0, stream>>>(a, ge + gn);
+  DSS2_LAUNCH_CHECK();
+  if (want_grad) {
+    k_wls_g_bus<true><<<gn, WLS_THREADS, 0, stream>>>(a, s, 0);
+    DSS2_LAUNCH_CHECK();
+    k_wls_g_branch<true><<<ge, WLS_THREADS, 0, stream>>>(a, s);
+    DSS2_LAUNCH_CHECK();
+    k_wls_g_gather<<<gn, WLS_THREADS, 0, stream>>>(a, s);
+    DSS2_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
 // get_pflow as a plain per-branch kernel (evaluation path, dss2_run.py:193-194): outputs are API tensors.
 __global__ void k_pflow(const int64_t* __restrict__ ei, int64_t Et, const float* __restrict__ y, int64_t ys,
                         const float* __restrict__ ep, int64_t eps_, const float* __restrict__ vminmax, float* out8) {
@@ -290,8 +519,6 @@ extern "C" int dss2_wls_fwd_bwd(const dss2_graph_t* g, const float* x, int64_t x
   cudaStream_t stream = (cudaStream_t)stream_;
   DSS2_CHECK_ARG(g && x && edge_attr && output && stats && vminmax && loss && ws, "dss2_wls_fwd_bwd: null argument");
   DSS2_CHECK_ARG(g->undirected == 1, "dss2_wls_fwd_bwd: needs a graph built from the one-way edge list with undirect=1");
-  DSS2_CHECK_ARG(g->num_tiles > 0, "dss2_wls_fwd_bwd: graph has no shared-memory tiling (a scenario exceeds %d buses); "
-                 "the large-graph loss path is not built yet", DSS2_TILE_CAP);
   DSS2_CHECK_ARG(ws_bytes >= dss2_wls_workspace_bytes(g), "dss2_wls_fwd_bwd: workspace too small");
   DSS2_CHECK_ARG(x_stride >= 11 && ea_stride >= 13, "dss2_wls_fwd_bwd: x needs 11 columns and edge_attr 13");
   WlsArgs a;
@@ -313,6 +540,10 @@ extern "C" int dss2_wls_fwd_bwd(const dss2_graph_t* g, const float* x, int64_t x
   a.counter = (unsigned*)base;                       // zero-initialised by the caller once; self-resetting
   a.sums = (double*)(base + 256);
   a.partial = a.sums + 16;
+  if (g->num_nodes == 0 || g->num_edges == 0) {
+    DSS2_CHECK_ARG(false, "dss2_wls_fwd_bwd: empty batch (the reference's means over buses / branches would be NaN)");
+  }
+  if (g->num_tiles == 0) return wls_generic(a, grad_out != nullptr, stream);
   size_t smem = wls_smem(g);
   DSS2_CHECK_ARG(smem <= 200 * 1024, "dss2_wls_fwd_bwd: tile needs %zu bytes of shared memory", smem);
   if (smem > 48 * 1024) {

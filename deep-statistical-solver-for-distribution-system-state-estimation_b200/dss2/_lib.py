@@ -24,6 +24,7 @@ class GraphStruct(Structure):
         ("max_tile_nodes", c_int32), ("max_tile_nnz", c_int32), ("max_tile_edges", c_int32), ("reserved", c_int32),
         ("edge_index", c_void_p), ("ptr", c_void_p), ("eptr", c_void_p), ("rowptr", c_void_p), ("col", c_void_p),
         ("eid", c_void_p), ("dis", c_void_p), ("w", c_void_p), ("ell_w", c_void_p), ("ell_ci", c_void_p),
+        ("scratch", c_void_p), ("scratch_bytes", c_size_t),
     ]
 
 
@@ -34,6 +35,7 @@ _SIGNATURES = {
     "dss2_version": (c_int, []),
     "dss2_launch_count": (c_int64, []),
     "dss2_graph_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int32]),
+    "dss2_generic_scratch_bytes": (c_size_t, [c_int64]),
     "dss2_graph_build": (c_int, [_G, _P, c_int64, c_int64, _P, c_int32, c_int, c_int, _P, c_size_t, _P]),
     "dss2_pack_batch": (c_int, [_P, _P, _P, _P, c_int64, _P, _P, _P, c_int32, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P]),
     "dss2_col_minmax": (c_int, [_P, c_int64, c_int, c_int64, _P, _P]),
@@ -48,6 +50,7 @@ _SIGNATURES = {
     "dss2_tag_bwd_tc2": (c_int, [_G, _P, _P, c_int, c_int, c_int, c_float, _P, _P, _P, _P, c_int64, c_int64, _P, c_size_t, _P]),
     "dss2_tag_bwd_tc2_gx": (c_int, [_G, _P, c_int, c_int, c_int, c_float, _P, _P, _P, _P, c_size_t, _P]),
     "dss2_tag_bwd_tc2_gw": (c_int, [c_int64, _P, c_int, c_int, c_int, c_float, _P, _P, _P, c_int64, c_int64, _P, c_size_t, _P]),
+    "dss2_tag_gw_ffma": (c_int, [c_int64, _P, c_int, c_int, c_int, c_float, _P, _P, _P, c_int64, c_int64, _P, c_size_t, _P]),
     "dss2_tc_selftest": (c_int, [_P, _P, _P, _P]),
     "dss2_tc_selftest_mn": (c_int, [_P, _P, _P, _P]),
     "dss2_tag_bwd": (c_int, [_G, _P, _P, c_int, c_int, c_int, c_float, _P, _P, _P, _P, c_int64, c_int64, _P]),

@@ -39,6 +39,12 @@ class BatchGraph:
                                       _lib.stream())
         _lib.check(rc, "dss2_graph_build")
         self._wls_ws = None
+        self.scratch = None
+        if self.c.num_tiles == 0:      # a graph exceeds a tile: the large-graph kernels need scratch
+            n = lib.dss2_generic_scratch_bytes(self.num_nodes)
+            self.scratch = torch.empty(n, dtype=torch.uint8, device=edge_index.device)
+            self.c.scratch = self.scratch.data_ptr()
+            self.c.scratch_bytes = n
 
     @property
     def ref(self):

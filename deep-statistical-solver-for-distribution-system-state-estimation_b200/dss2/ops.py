@@ -18,6 +18,9 @@ HID = _lib.HID
 #   "tc2" : second-generation tcgen05 forward AND backward (tag_tc2.cu); tiles of up to 256 rows (two MMA blocks)
 # Unsupported shapes (K = 3, oversize tiles) fall back to the CUDA-core kernels.
 TAG_IMPL = os.environ.get("DSS2_TAG_IMPL", "tc2")
+# weight-gradient pass behind the tc2 backward: "tc" = tcgen05 3xTF32 GEMM (68.7 us on the bench layer), "ffma" = exact fp32 streaming
+# kernel on the CUDA cores (82.5 us; profiles/r1k_bench.json) - the tensor cores are used because they measure faster
+GW_IMPL = os.environ.get("DSS2_GW_IMPL", "tc")
 
 
 def tile_cap():
@@ -177,8 +180,14 @@ class PFNRunner:
                 common = (g, _lib.ptr(bufs["acts"][s, l]), self._p(flat, pre + f"convs.{l}.lins.0.weight"), cout, sp.K,
                           0 if last else 1, sp.p_drop, None if last else _lib.ptr(bufs["bits"][s, l]),
                           _lib.ptr(gy), _lib.ptr(gx), pp(pre + f"convs.{l}.lins.0.weight"), pstride, b_off - w_off)
-                if use_tc2:
+                if use_tc2 and GW_IMPL == "tc":
                     _lib.check(lib.dss2_tag_bwd_tc2(*common, _lib.ptr(bufs["lvl"]), bufs["lvl"].numel() * 4, st), "dss2_tag_bwd_tc2")
+                elif use_tc2:
+                    (_, xl, wl, _, _, actl, _, bitsl, gyl, gxl, partl, _, boff) = common
+                    ws, nws = _lib.ptr(bufs["lvl"]), bufs["lvl"].numel() * 4
+                    _lib.check(lib.dss2_tag_bwd_tc2_gx(g, wl, cout, sp.K, actl, sp.p_drop, bitsl, gyl, gxl, ws, nws, st), "dss2_tag_bwd_tc2_gx")
+                    _lib.check(lib.dss2_tag_gw_ffma(graph.num_nodes, xl, cout, sp.K, actl, sp.p_drop, bitsl, gyl, partl, pstride, boff,
+                                                    ws, nws, st), "dss2_tag_gw_ffma")
                 else:
                     _lib.check(lib.dss2_tag_bwd(*common, st), "dss2_tag_bwd")
                 gy = gx

@@ -71,8 +71,6 @@ class GraphedTrainer:
             launch_pack(store, self.ids, self.batch, self.nt, self.et)
             from .ops import tile_cap
             self.graph = BatchGraph(self.batch["edge_index"], self.nt, ptr=self.batch["ptr"], undirect=1, tile_cap=tile_cap())
-            if self.graph.c.num_tiles == 0:
-                raise _lib.Dss2Error("GraphedTrainer: graphs exceed the shared-memory tile; large-graph path not built yet")
             self.wls_ws = self.graph.wls_workspace()
         self.cuda_graph = None
         self.launches_per_step = None

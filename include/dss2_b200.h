@@ -64,7 +64,14 @@ typedef struct dss2_graph {
   float* w;                 /* [nnz] gcn_norm weight of the entry: dis[src] * dis[dst] */
   float* ell_w;             /* [Nt][4] weights of the first 4 entries of every row (0 = padding): thread-per-row kernels */
   uint32_t* ell_ci;         /* [Nt][2] .x = 4 x 8-bit tile-local source rows of those entries, .y = row degree */
+  float* scratch;           /* caller-provided, only needed when num_tiles == 0 (a graph exceeds a tile): */
+  size_t scratch_bytes;     /*   dss2_generic_scratch_bytes(Nt) bytes of device memory for the large-graph kernels */
 } dss2_graph_t;
+
+/* Large graphs (a graph with more nodes than a tile, e.g. a 10k-bus feeder): num_tiles == 0 after the build and every layer /
+ * loss entry point switches to its global-memory variant (hops as separate SpMM launches, row-streaming transforms, node-centric
+ * loss passes).  Those need scratch: set g->scratch / g->scratch_bytes to a device buffer of this many bytes. */
+size_t dss2_generic_scratch_bytes(int64_t num_nodes);
 
 /* Bytes of device workspace dss2_graph_build needs for (Nt, Et, B). */
 size_t dss2_graph_workspace_bytes(int64_t num_nodes, int64_t num_edges, int32_t num_graphs);
@@ -163,6 +170,11 @@ int dss2_tag_bwd_tc2_gx(const dss2_graph_t* g, const float* w, int cout, int K, 
 int dss2_tag_bwd_tc2_gw(int64_t num_nodes, const float* x, int cout, int K, int act, float p_drop,
                         const uint32_t* act_bits, const float* grad_y, float* partials, int64_t partial_stride,
                         int64_t bias_offset, const void* ws, size_t ws_bytes, void* stream);
+/* The weight-gradient pass of dss2_tag_bwd_tc2_gw in exact fp32 on the CUDA cores (bulk-copy ring + FFMA, K <= 3): same arguments,
+ * same partial layout.  It is a pure streaming pass, and ncu / CUDA events decide which of the two the host uses. */
+int dss2_tag_gw_ffma(int64_t num_nodes, const float* x, int cout, int K, int act, float p_drop, const uint32_t* act_bits,
+                     const float* grad_y, float* partials, int64_t partial_stride, int64_t bias_offset, const void* ws,
+                     size_t ws_bytes, void* stream);
 /* D[128,32] = A[128,32] * B[32,32]^T through the tensor-core operand / descriptor / TMEM path (bring-up and regression test). */
 int dss2_tc_selftest(const float* A, const float* B, float* D, void* stream);
 /* D[32*t + j, n] = sum_r A[t][r][j] * B[r][n], A = [4,64,32], B = [64,32]: MN-major TF32 operands (SWIZZLE_128B_BASE32B), the
