@@ -70,19 +70,19 @@ __device__ __forceinline__ EaSmem carve(float* smem, int TR, int ER, int Z, int 
   return s;
 }
 
-__device__ __forceinline__ void load_tile(const EaArgs& a, const TileRange& r, const EaSmem& s, int tid) {
+__device__ __forceinline__ void load_tile(const EaArgs& a, const TileRange& r, const EaSmem& s, int tid, int nthr) {
   const dss2_graph_t& g = a.g;
   const int nT = r.n1 - r.n0, nE = (int)(r.e1 - r.e0), nZ = r.z1 - r.z0;
-  for (int i = tid; i < nT * FP; i += EA_THREADS) {
+  for (int i = tid; i < nT * FP; i += nthr) {
     const int row = i >> 3, c = i & 7;
     s.xs[i] = c < a.fn ? a.x[((size_t)r.n0 + row) * a.xs + c] : 0.0f;
   }
-  for (int i = tid; i < nE * FP; i += EA_THREADS) {
+  for (int i = tid; i < nE * FP; i += nthr) {
     const int row = i >> 3, c = i & 7;
     s.at[i] = c < a.fe ? a.ea[((size_t)r.e0 + row) * a.eas + c] : 0.0f;
   }
-  for (int i = tid; i <= nT; i += EA_THREADS) s.rowptr[i] = g.rowptr[r.n0 + i] - r.z0;
-  for (int i = tid; i < nZ; i += EA_THREADS) {
+  for (int i = tid; i <= nT; i += nthr) s.rowptr[i] = g.rowptr[r.n0 + i] - r.z0;
+  for (int i = tid; i < nZ; i += nthr) {
     s.col[i] = g.col[r.z0 + i] - r.n0;
     const uint32_t id = g.eid[r.z0 + i];
     s.eid[i] = (uint32_t)((int64_t)(id & 0x7fffffffu) - r.e0) | (id & 0x80000000u);
@@ -136,6 +136,21 @@ __device__ __forceinline__ float edge_term(const W1Row& w, const float* arow, fl
   return t;
 }
 
+// Sum each of 8 per-lane values over the warp with 9 shuffles instead of 40: halve the value set while halving the lane set
+// (xor 16, 8, 4), then two plain butterfly steps.  Lane l ends up with the total of v[l >> 2].
+__device__ __forceinline__ float reduce8_transposed(const float (&v)[FP], int lane) {
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+  float u[4], t[2];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) u[j] = (b4 ? v[4 + j] : v[j]) + __shfl_xor_sync(0xffffffffu, b4 ? v[j] : v[4 + j], 16);
+#pragma unroll
+  for (int j = 0; j < 2; ++j) t[j] = (b3 ? u[2 + j] : u[j]) + __shfl_xor_sync(0xffffffffu, b3 ? u[j] : u[2 + j], 8);
+  float s = (b2 ? t[1] : t[0]) + __shfl_xor_sync(0xffffffffu, b2 ? t[0] : t[1], 4);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  return s;
+}
+
 // out[lane] = sum_h M[lane][h] * vec[h], vec broadcast from shared memory, M row in registers
 __device__ __forceinline__ float matvec32(const float (&Mrow)[HID], const float* vec) {
   float acc = 0.0f;
@@ -150,7 +165,9 @@ __device__ __forceinline__ float matvec32(const float (&Mrow)[HID], const float*
   return acc;
 }
 
-__global__ void __launch_bounds__(EA_THREADS, 2) k_edgeagg_fwd(EaArgs a) {
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_edgeagg_fwd(EaArgs a) {
+  constexpr int NW = NT / 32;
   extern __shared__ __align__(16) float smem[];
   const dss2_graph_t& g = a.g;
   const int TR = round4(g.max_tile_nodes), ER = round4(g.max_tile_edges);
@@ -165,16 +182,16 @@ __global__ void __launch_bounds__(EA_THREADS, 2) k_edgeagg_fwd(EaArgs a) {
   for (int t = blockIdx.x; t < g.num_tiles; t += gridDim.x) {
     const TileRange r = tile_range(g, t);
     const int nT = r.n1 - r.n0;
-    load_tile(a, r, s, tid);
+    load_tile(a, r, s, tid, NT);
     __syncthreads();
-    for (int row = warp; row < nT; row += EA_WARPS) {
+    for (int row = warp; row < nT; row += NW) {
       float p, q;
       node_pq(w1, s.xs + row * FP, p, q);
       s.P[row * HID + lane] = p;
       s.Q[row * HID + lane] = q;
     }
     __syncthreads();
-    for (int row = warp; row < nT; row += EA_WARPS) {
+    for (int row = warp; row < nT; row += NW) {
       const int beg = s.rowptr[row], end = s.rowptr[row + 1];
       const float p = s.P[row * HID + lane];
       float S = 0.0f;
@@ -195,7 +212,9 @@ __global__ void __launch_bounds__(EA_THREADS, 2) k_edgeagg_fwd(EaArgs a) {
 }
 
 // partial layout: w1 [32][ld], b1 [32], w2 [32][32], b2 [32]
-__global__ void __launch_bounds__(EA_THREADS, 1) k_edgeagg_bwd(EaArgs a) {
+template <int NT>
+__global__ void __launch_bounds__(NT, 1) k_edgeagg_bwd(EaArgs a) {
+  constexpr int NW = NT / 32;
   extern __shared__ __align__(16) float smem[];
   const dss2_graph_t& g = a.g;
   const int TR = round4(g.max_tile_nodes), ER = round4(g.max_tile_edges);
@@ -206,9 +225,6 @@ __global__ void __launch_bounds__(EA_THREADS, 1) k_edgeagg_bwd(EaArgs a) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int fn = a.fn, fe = a.fe, ld = 2 * fn + fe;
   const W1Row w1 = load_w1(a, lane);
-  float W2col[HID];   // lane h keeps column h of W2: W2[o][h]
-#pragma unroll
-  for (int o = 0; o < HID; ++o) W2col[o] = a.w2[o * HID + lane];
 
   // accumulators (lane = hidden unit h, except gb2 where lane = output unit o)
   float gW1a[FP], gW1b[FP], gW1c[FP], gb1 = 0.0f, gb2 = 0.0f, gW2[HID];
@@ -220,14 +236,18 @@ __global__ void __launch_bounds__(EA_THREADS, 1) k_edgeagg_bwd(EaArgs a) {
   for (int t = blockIdx.x; t < g.num_tiles; t += gridDim.x) {
     const TileRange r = tile_range(g, t);
     const int nT = r.n1 - r.n0;
-    load_tile(a, r, s, tid);
+    load_tile(a, r, s, tid, NT);
     {
       const float4* src = reinterpret_cast<const float4*>(a.gout + (size_t)r.n0 * HID);
       float4* dst = reinterpret_cast<float4*>(GO);
-      for (int i = tid; i < nT * (HID / 4); i += EA_THREADS) dst[i] = ldg_stream4(src + i);
+      for (int i = tid; i < nT * (HID / 4); i += NT) dst[i] = ldg_stream4(src + i);
     }
     __syncthreads();
-    for (int row = warp; row < nT; row += EA_WARPS) {
+    {
+      float W2col[HID];   // lane h keeps column h of W2: W2[o][h]; only live in this phase (reloaded per tile from L1)
+#pragma unroll
+      for (int o = 0; o < HID; ++o) W2col[o] = __ldg(a.w2 + o * HID + lane);
+    for (int row = warp; row < nT; row += NW) {
       float p, q;
       node_pq(w1, s.xs + row * FP, p, q);
       s.P[row * HID + lane] = p;
@@ -236,8 +256,9 @@ __global__ void __launch_bounds__(EA_THREADS, 1) k_edgeagg_bwd(EaArgs a) {
       GS[row * HID + lane] = matvec32(W2col, GO + row * HID);
       gb2 = fmaf((float)(s.rowptr[row + 1] - s.rowptr[row]), GO[row * HID + lane], gb2);
     }
+    }
     __syncthreads();
-    for (int row = warp; row < nT; row += EA_WARPS) {
+    for (int row = warp; row < nT; row += NW) {
       const int beg = s.rowptr[row], end = s.rowptr[row + 1];
       const float p = s.P[row * HID + lane], q = s.Q[row * HID + lane], gs = GS[row * HID + lane];
       float S = 0.0f, gP = 0.0f, gQ = 0.0f;
@@ -282,16 +303,15 @@ __global__ void __launch_bounds__(EA_THREADS, 1) k_edgeagg_bwd(EaArgs a) {
       }
       // grad_x[row][i] = sum_h W1a[h][i] gP[h] + W1b[h][i] gQ[h]  (+ residual-path gradient)
       if (a.gx) {
-        float mine = 0.0f;
+        float v[FP];
 #pragma unroll
-        for (int i = 0; i < FP; ++i) {
-          const float v = warp_sum(fmaf(w1.a[i], gP, w1.b[i] * gQ));
-          if (lane == i) mine = v;
-        }
-        if (lane < fn) {
+        for (int i = 0; i < FP; ++i) v[i] = fmaf(w1.a[i], gP, w1.b[i] * gQ);
+        float mine = reduce8_transposed(v, lane);   // lane l: total of feature l >> 2
+        const int i = lane >> 2;
+        if ((lane & 3) == 0 && i < fn) {
           const size_t n = (size_t)r.n0 + row;
-          if (a.skip) mine += a.skip[n * a.skip_stride + lane];
-          a.gx[n * fn + lane] = mine;
+          if (a.skip) mine += a.skip[n * a.skip_stride + i];
+          a.gx[n * fn + i] = mine;
         }
       }
     }
@@ -300,7 +320,7 @@ __global__ void __launch_bounds__(EA_THREADS, 1) k_edgeagg_bwd(EaArgs a) {
 
   // per-CTA partial: reduce the 8 warps through shared memory
   constexpr int PER = 3 * FP + 2 + HID;   // gW1a, gW1b, gW1c, gb1, gb2, gW2[32]
-  float* red = smem;                      // [EA_WARPS][PER][32]
+  float* red = smem;                      // [NW][PER][32]
   {
     float* mine = red + (size_t)warp * PER * HID;
 #pragma unroll
@@ -317,7 +337,7 @@ __global__ void __launch_bounds__(EA_THREADS, 1) k_edgeagg_bwd(EaArgs a) {
   __syncthreads();
   float* part = a.partials + (size_t)blockIdx.x * a.partial_stride;
   const int n_w1 = HID * ld, off_b1 = n_w1, off_w2 = n_w1 + HID, off_b2 = off_w2 + HID * HID, total = off_b2 + HID;
-  for (int i = tid; i < total; i += EA_THREADS) {
+  for (int i = tid; i < total; i += NT) {
     int slot, ln;
     if (i < n_w1) {
       const int h = i / ld, c = i - h * ld;
@@ -336,7 +356,7 @@ __global__ void __launch_bounds__(EA_THREADS, 1) k_edgeagg_bwd(EaArgs a) {
     }
     float sum = 0.0f;
 #pragma unroll
-    for (int w8 = 0; w8 < EA_WARPS; ++w8) sum += red[((size_t)w8 * PER + slot) * HID + ln];
+    for (int w8 = 0; w8 < NW; ++w8) sum += red[((size_t)w8 * PER + slot) * HID + ln];
     part[i] = sum;
   }
 }
@@ -458,15 +478,14 @@ __global__ void __launch_bounds__(EA_THREADS, 1) k_ea_bwd_g(EaArgs a, const floa
 #pragma unroll
     for (int o = 0; o < HID; ++o) gW2[o] = fmaf(__shfl_sync(0xffffffffu, go, o), S, gW2[o]);
     if (a.gx) {
-      float mine = 0.0f;
+      float v[FP];
 #pragma unroll
-      for (int i = 0; i < FP; ++i) {
-        const float v = warp_sum(fmaf(w1.a[i], gP, w1.b[i] * gQ));
-        if (lane == i) mine = v;
-      }
-      if (lane < fn) {
-        if (a.skip) mine += a.skip[n * a.skip_stride + lane];
-        a.gx[n * fn + lane] = mine;
+      for (int i = 0; i < FP; ++i) v[i] = fmaf(w1.a[i], gP, w1.b[i] * gQ);
+      float mine = reduce8_transposed(v, lane);
+      const int i = lane >> 2;
+      if ((lane & 3) == 0 && i < fn) {
+        if (a.skip) mine += a.skip[n * a.skip_stride + i];
+        a.gx[n * fn + i] = mine;
       }
     }
   }
@@ -522,6 +541,14 @@ size_t ea_smem(const dss2_graph_t* g, int bufs) {
   return tile;
 }
 
+// threads per CTA of the tile kernels; the environment override exists for measurements
+constexpr int EA_FWD_THREADS = 256, EA_BWD_THREADS = 384;
+int ea_threads(const char* env, int dflt) {
+  const char* v = getenv(env);
+  const int n = v ? atoi(v) : dflt;
+  return (n == 256 || n == 384 || n == 512) ? n : dflt;
+}
+
 int check_common(const char* who, const dss2_graph_t* g, const float* x, int fn, const float* ea, int fe, const float* w1,
                  const float* b1, const float* w2, const float* b2) {
   DSS2_CHECK_ARG(g && x && ea && w1 && b1 && w2 && b2, "%s: null argument", who);
@@ -563,9 +590,15 @@ extern "C" int dss2_edgeagg_fwd(const dss2_graph_t* g, const float* x, int64_t x
   }
   size_t smem = ea_smem(g, 2);
   DSS2_CHECK_ARG(smem <= 113 * 1024, "dss2_edgeagg_fwd: tile needs %zu bytes of shared memory", smem);
-  if (smem > 48 * 1024) DSS2_CUDA(cudaFuncSetAttribute(k_edgeagg_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int grid = max(1, min(g->num_tiles, 2 * dss2_sm_count()));
-  k_edgeagg_fwd<<<grid, EA_THREADS, smem, stream>>>(a);
+#define DSS2_EA_FWD(NT)                                                                                                          \
+  {                                                                                                                              \
+    if (smem > 48 * 1024) DSS2_CUDA(cudaFuncSetAttribute(k_edgeagg_fwd<NT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k_edgeagg_fwd<NT, 2><<<grid, NT, smem, stream>>>(a);                                                                         \
+  }
+  const int nt = ea_threads("DSS2_EA_FWD_THREADS", EA_FWD_THREADS);
+  if (nt == 256) DSS2_EA_FWD(256) else if (nt == 384) DSS2_EA_FWD(384) else DSS2_EA_FWD(512)
+#undef DSS2_EA_FWD
   DSS2_LAUNCH_CHECK();
   return 0;
 }
@@ -612,12 +645,18 @@ extern "C" int dss2_edgeagg_bwd(const dss2_graph_t* g, const float* x, int64_t x
     DSS2_LAUNCH_CHECK();
     return 0;
   }
+  const int nt = ea_threads("DSS2_EA_BWD_THREADS", EA_BWD_THREADS);
   size_t smem = ea_smem(g, 4);
-  size_t red = (size_t)EA_WARPS * (3 * FP + 2 + HID) * HID * 4;
+  size_t red = (size_t)(nt / 32) * (3 * FP + 2 + HID) * HID * 4;
   if (red > smem) smem = red;
   DSS2_CHECK_ARG(smem <= 227 * 1024, "dss2_edgeagg_bwd: tile needs %zu bytes of shared memory", smem);
-  if (smem > 48 * 1024) DSS2_CUDA(cudaFuncSetAttribute(k_edgeagg_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_edgeagg_bwd<<<dss2_sm_count(), EA_THREADS, smem, stream>>>(a);
+#define DSS2_EA_BWD(NT)                                                                                                       \
+  {                                                                                                                           \
+    if (smem > 48 * 1024) DSS2_CUDA(cudaFuncSetAttribute(k_edgeagg_bwd<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k_edgeagg_bwd<NT><<<dss2_sm_count(), NT, smem, stream>>>(a);                                                              \
+  }
+  if (nt == 256) DSS2_EA_BWD(256) else if (nt == 384) DSS2_EA_BWD(384) else DSS2_EA_BWD(512)
+#undef DSS2_EA_BWD
   DSS2_LAUNCH_CHECK();
   return 0;
 }

@@ -422,37 +422,47 @@ struct GwArgs {
 
 constexpr int GW_STAGES = 3;
 constexpr uint32_t GW_STAGE_BYTES = 4 * GW_TILE + 256;   // x, grad_y, A g, A^2 g rows + sign words of one 64-row chunk
+constexpr int GW_CONV = 256;                             // converter threads (8 warps)
+constexpr int GW_THREADS = GW_CONV + 32;                 // + 1 producer / MMA-issuer warp
 
+// Roles (ncu on the one-role version: 4 warps, 12 % issue utilisation, the converting thread 0 also spent ~1.9 k cycles per chunk
+// issuing 32 MMAs while the other warps waited at the barrier):
+//   warp 8, lane 0: lands chunks with bulk copies (3-stage ring), and per chunk - once all converters have arrived on `ready` -
+//                   issues 16 MMAs M128 x N64 x K8: A in {G.lo, G.hi} x B = [x.hi ; x.lo] stacked along N (the two halves of D are
+//                   added in the epilogue), commits to `bar`, refills the ring slot the converters have just drained;
+//   warps 0-7:      thread = (16-byte column chunk cq, row rs and rs + 32): staged rows -> registers -> mask -> hi/lo split; wait
+//                   for the previous chunk's MMAs (`bar`), store the operand tiles, arrive on `ready`.
+// Loads + conversion of chunk i+1 overlap the MMA issue and execution of chunk i; only the tile stores wait for the tensor core.
 template <int K>
-__global__ void __launch_bounds__(128, 1) k_tag_gw(GwArgs a) {
+__global__ void __launch_bounds__(GW_THREADS, 1) k_tag_gw(GwArgs a) {
   extern __shared__ char raw[];
   char* base = align1024(raw);
   // A side (MN-major, M = 32*level + c): [hi: G_0..G_K, pad][lo: G_0..G_K, pad] each tile 8 KB, LBO = 8 KB; with K = 2 the M = 128
   // extent covers 3 levels + 1 zero block (rows 96..127 of D are ignored)
   char* Ah = base;
   char* Al = Ah + 4 * GW_TILE;
-  // B side (MN-major, N = 32 input features): [x.hi][x.lo]
+  // B side (MN-major, N = 64: 32 input features of x.hi, then of x.lo; LBO = 8 KB)
   char* Bh = Al + 4 * GW_TILE;
   char* Bl = Bh + GW_TILE;
   char* stage0 = Bl + GW_TILE;                           // raw rows landed by the TMA engine, GW_STAGES deep
   char* tail = stage0 + GW_STAGES * GW_STAGE_BYTES;
   uint64_t* full = reinterpret_cast<uint64_t*>(tail);    // [GW_STAGES] "chunk has landed"
-  uint64_t* bar = full + GW_STAGES;                      // "MMAs of the previous chunk have completed"
+  uint64_t* ready = full + GW_STAGES;                    // "operand tiles of this chunk are written" (GW_CONV arrivals)
+  uint64_t* bar = ready + 1;                             // "MMAs of this chunk have completed"
   uint32_t* tslot = reinterpret_cast<uint32_t*>(bar + 1);
   const int tid = threadIdx.x, warp = tid >> 5;
-  // thread = (16-byte column chunk cq, row group rs): it converts chunk cq of rows rs, rs+16, rs+32, rs+48 of all four arrays.
-  // Eight consecutive threads read one staged row (128 contiguous bytes) and write the eight swizzled chunks of one operand row:
-  // both accesses are bank-conflict free (ncu on the thread-per-row version: 78 % of the shared-memory wavefronts were conflicts).
-  const uint32_t cq = tid & 7, rs = tid >> 3;
+  const bool issuer = warp == GW_CONV / 32;
+  const uint32_t cq = tid & 7, rs = (tid >> 3) & 31;
   const int cout = a.cout;
 
   if (warp == 0) tc::tmem_alloc(tslot, 64);
   if (tid == 0) {
     for (int s = 0; s < GW_STAGES; ++s) mbar_init(&full[s], 1);
+    mbar_init(ready, GW_CONV);
     mbar_init(bar, 1);
     fence_mbar_init();
   }
-  for (int idx = tid; idx < GW_ROWS * 32; idx += 128) {   // unused A blocks (M rows beyond the K+1 levels) read as zeros
+  for (int idx = tid; idx < GW_ROWS * 32; idx += GW_THREADS) {   // unused A blocks (M rows beyond the K+1 levels) read as zeros
     const uint32_t r = idx >> 5, j = idx & 31;
     for (int blk = K + 1; blk < 4; ++blk) {
       *reinterpret_cast<float*>(Ah + blk * GW_TILE + tc::swz32_off(r, j)) = 0.0f;
@@ -464,144 +474,153 @@ __global__ void __launch_bounds__(128, 1) k_tag_gw(GwArgs a) {
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = *tslot;
-  const uint32_t idesc = tc::idesc_tf32(128, 32, 1, 1);
 
   const int64_t num_chunks = (a.num_nodes + GW_ROWS - 1) / GW_ROWS;
   const int64_t full_chunks = a.num_nodes / GW_ROWS;       // only whole chunks go through the bulk-copy engine
-  const uint32_t gy_bytes = (uint32_t)(GW_ROWS * cout * 4);
-  const uint32_t tx = GW_TILE * (K >= 2 ? 3 : 2) + gy_bytes + (a.bits ? 256u : 0u);
-  // producer (thread 0): land chunk `ch` in stage `s`
-  auto issue = [&](int64_t ch, int s) {
-    if (ch >= full_chunks) return;
-    char* st = stage0 + (size_t)s * GW_STAGE_BYTES;
-    const int64_t n = ch * GW_ROWS;
-    mbar_expect_tx(&full[s], tx);
-    bulk_g2s(st, a.x + n * 32, GW_TILE, &full[s]);
-    bulk_g2s(st + GW_TILE, a.gy + n * cout, gy_bytes, &full[s]);
-    bulk_g2s(st + 2 * GW_TILE, a.lvl + n * 32, GW_TILE, &full[s]);
-    if (K >= 2) bulk_g2s(st + 3 * GW_TILE, a.lvl + (a.num_nodes + n) * 32, GW_TILE, &full[s]);
-    if (a.bits) bulk_g2s(st + 4 * GW_TILE, a.bits + n, 256, &full[s]);
-  };
-  if (tid == 0)
-    for (int i = 0; i < GW_STAGES; ++i) issue(blockIdx.x + (int64_t)i * gridDim.x, i);
-
-  // grad_b = column sums of the masked output gradient: accumulated exactly in fp32 registers by the threads that convert those
-  // columns (a ones-column in the GEMM would inherit the 2^-23 TF32-pair representation error, visible in this cancelling sum)
   float gb[4] = {0.f, 0.f, 0.f, 0.f};
+  bool any = false;
 
-  bool first = true;
-  uint32_t par = 0;
-  int it = 0;
-  for (int64_t ch = blockIdx.x; ch < num_chunks; ch += gridDim.x, ++it) {
-    const int s = it % GW_STAGES;
-    const bool staged = ch < full_chunks;
-    const char* st = stage0 + (size_t)s * GW_STAGE_BYTES;
-    if (staged) mbar_wait(&full[s], (uint32_t)((it / GW_STAGES) & 1));
-    float4 vx[4], vg[4], v1[4], v2[4];
+  if (issuer) {
+    if ((tid & 31) == 0) {
+      const uint32_t gy_bytes = (uint32_t)(GW_ROWS * cout * 4);
+      const uint32_t tx = GW_TILE * (K >= 2 ? 3 : 2) + gy_bytes + (a.bits ? 256u : 0u);
+      auto issue = [&](int64_t ch, int s) {
+        if (ch >= full_chunks) return;
+        char* st = stage0 + (size_t)s * GW_STAGE_BYTES;
+        const int64_t n = ch * GW_ROWS;
+        mbar_expect_tx(&full[s], tx);
+        bulk_g2s(st, a.x + n * 32, GW_TILE, &full[s]);
+        bulk_g2s(st + GW_TILE, a.gy + n * cout, gy_bytes, &full[s]);
+        bulk_g2s(st + 2 * GW_TILE, a.lvl + n * 32, GW_TILE, &full[s]);
+        if (K >= 2) bulk_g2s(st + 3 * GW_TILE, a.lvl + (a.num_nodes + n) * 32, GW_TILE, &full[s]);
+        if (a.bits) bulk_g2s(st + 4 * GW_TILE, a.bits + n, 256, &full[s]);
+      };
+      for (int i = 0; i < GW_STAGES; ++i) issue(blockIdx.x + (int64_t)i * gridDim.x, i);
+      const uint32_t idesc = tc::idesc_tf32(128, 64, 1, 1);
+      const uint64_t dAh = tc::smem_desc_mn32(smem_u32(Ah), GW_TILE), dAl = tc::smem_desc_mn32(smem_u32(Al), GW_TILE);
+      const uint64_t dB = tc::smem_desc_mn32(smem_u32(Bh), GW_TILE);
+      int it = 0;
+      for (int64_t ch = blockIdx.x; ch < num_chunks; ch += gridDim.x, ++it) {
+        mbar_wait(ready, (uint32_t)(it & 1));
+        tc::fence_after_sync();
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const uint32_t r = rs + 16 * i;
-      const int64_t n = ch * GW_ROWS + r;
-      const bool inb = n < a.num_nodes;
-      vx[i] = vg[i] = v1[i] = v2[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      uint32_t word = 0xffffffffu;
-      if (staged) {
-        vx[i] = *reinterpret_cast<const float4*>(st + r * 128 + cq * 16);
-        v1[i] = *reinterpret_cast<const float4*>(st + 2 * GW_TILE + r * 128 + cq * 16);
-        if (K >= 2) v2[i] = *reinterpret_cast<const float4*>(st + 3 * GW_TILE + r * 128 + cq * 16);
-        if (cout == 32) {
-          vg[i] = *reinterpret_cast<const float4*>(st + GW_TILE + r * 128 + cq * 16);
-        } else {
-          const float* gp = reinterpret_cast<const float*>(st + GW_TILE) + r * cout;
+        for (uint32_t ks = 0; ks < GW_ROWS / 8; ++ks) {
+          const uint32_t o = ks * 1024;
+          tc::mma_tf32(tmem, tc::desc_advance(dAl, o), tc::desc_advance(dB, o), idesc, (it == 0 && ks == 0) ? 0u : 1u);
+          tc::mma_tf32(tmem, tc::desc_advance(dAh, o), tc::desc_advance(dB, o), idesc, 1u);
+        }
+        tc::mma_commit(bar);
+        issue(ch + (int64_t)GW_STAGES * gridDim.x, it % GW_STAGES);   // every converter has read this slot before arriving on `ready`
+      }
+    }
+    __syncwarp();
+  } else {
+    uint32_t par = 0;
+    int it = 0;
+    for (int64_t ch = blockIdx.x; ch < num_chunks; ch += gridDim.x, ++it) {
+      const int s = it % GW_STAGES;
+      const bool staged = ch < full_chunks;
+      const char* st = stage0 + (size_t)s * GW_STAGE_BYTES;
+      if (staged) mbar_wait(&full[s], (uint32_t)((it / GW_STAGES) & 1));
+      float4 vx[2], vg[2], v1[2], v2[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const uint32_t r = rs + 32 * i;
+        const int64_t n = ch * GW_ROWS + r;
+        const bool inb = n < a.num_nodes;
+        vx[i] = vg[i] = v1[i] = v2[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        uint32_t word = 0xffffffffu;
+        if (staged) {
+          vx[i] = *reinterpret_cast<const float4*>(st + r * 128 + cq * 16);
+          v1[i] = *reinterpret_cast<const float4*>(st + 2 * GW_TILE + r * 128 + cq * 16);
+          if (K >= 2) v2[i] = *reinterpret_cast<const float4*>(st + 3 * GW_TILE + r * 128 + cq * 16);
+          if (cout == 32) {
+            vg[i] = *reinterpret_cast<const float4*>(st + GW_TILE + r * 128 + cq * 16);
+          } else {
+            const float* gp = reinterpret_cast<const float*>(st + GW_TILE) + r * cout;
+            float t4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if ((int)(cq * 4 + e) < cout) t4[e] = gp[cq * 4 + e];
+            vg[i] = make_float4(t4[0], t4[1], t4[2], t4[3]);
+          }
+          if (a.bits) word = reinterpret_cast<const uint32_t*>(st + 4 * GW_TILE)[r];
+        } else if (inb) {   // the one ragged chunk at the end of the batch: plain bounded loads
+          vx[i] = *reinterpret_cast<const float4*>(a.x + n * 32 + cq * 4);
+          v1[i] = *reinterpret_cast<const float4*>(a.lvl + n * 32 + cq * 4);
+          if (K >= 2) v2[i] = *reinterpret_cast<const float4*>(a.lvl + (a.num_nodes + n) * 32 + cq * 4);
           float t4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int e = 0; e < 4; ++e)
-            if ((int)(cq * 4 + e) < cout) t4[e] = gp[cq * 4 + e];
+            if ((int)(cq * 4 + e) < cout) t4[e] = a.gy[n * cout + cq * 4 + e];
           vg[i] = make_float4(t4[0], t4[1], t4[2], t4[3]);
+          if (a.bits) word = a.bits[n];
         }
-        if (a.bits) word = reinterpret_cast<const uint32_t*>(st + 4 * GW_TILE)[r];
-      } else if (inb) {   // the one ragged chunk at the end of the batch: plain bounded loads
-        vx[i] = *reinterpret_cast<const float4*>(a.x + n * 32 + cq * 4);
-        v1[i] = *reinterpret_cast<const float4*>(a.lvl + n * 32 + cq * 4);
-        if (K >= 2) v2[i] = *reinterpret_cast<const float4*>(a.lvl + (a.num_nodes + n) * 32 + cq * 4);
-        float t4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if ((int)(cq * 4 + e) < cout) t4[e] = a.gy[n * cout + cq * 4 + e];
-        vg[i] = make_float4(t4[0], t4[1], t4[2], t4[3]);
-        if (a.bits) word = a.bits[n];
+        if (a.bits) {
+          const uint32_t w4 = word >> (cq * 4);
+          vg[i].x = (w4 & 1u) ? vg[i].x * a.scale : 0.0f;
+          vg[i].y = (w4 & 2u) ? vg[i].y * a.scale : 0.0f;
+          vg[i].z = (w4 & 4u) ? vg[i].z * a.scale : 0.0f;
+          vg[i].w = (w4 & 8u) ? vg[i].w * a.scale : 0.0f;
+        }
+        // grad_b = column sums of the masked output gradient, exact fp32 on the CUDA cores (a ones-column in the GEMM would inherit
+        // the 2^-23 TF32-pair representation error, visible in this cancelling sum)
+        gb[0] += vg[i].x;
+        gb[1] += vg[i].y;
+        gb[2] += vg[i].z;
+        gb[3] += vg[i].w;
       }
-      if (a.bits) {
-        const uint32_t w4 = word >> (cq * 4);
-        vg[i].x = (w4 & 1u) ? vg[i].x * a.scale : 0.0f;
-        vg[i].y = (w4 & 2u) ? vg[i].y * a.scale : 0.0f;
-        vg[i].z = (w4 & 4u) ? vg[i].z * a.scale : 0.0f;
-        vg[i].w = (w4 & 8u) ? vg[i].w * a.scale : 0.0f;
+      if (any) {   // the previous chunk's MMAs still read the operand tiles
+        mbar_wait(bar, par);
+        par ^= 1u;
       }
-      gb[0] += vg[i].x;
-      gb[1] += vg[i].y;
-      gb[2] += vg[i].z;
-      gb[3] += vg[i].w;
-    }
-    if (!first) {   // the previous chunk's MMAs still read the operand tiles
-      mbar_wait(bar, par);
-      par ^= 1u;
-    }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const uint32_t off = tc::swz32_off(rs + 16 * i, cq * 4);
-      tc::split_store4(vx[i], Bh, Bl, off);                                   // x
-      tc::split_store4(vg[i], Ah, Al, off);                                   // G_0
-      tc::split_store4(v1[i], Ah + GW_TILE, Al + GW_TILE, off);               // G_1
-      if (K >= 2) tc::split_store4(v2[i], Ah + 2 * GW_TILE, Al + 2 * GW_TILE, off);   // G_2
+      for (int i = 0; i < 2; ++i) {
+        const uint32_t off = tc::swz32_off(rs + 32 * i, cq * 4);
+        tc::split_store4(vx[i], Bh, Bl, off);                                   // x
+        tc::split_store4(vg[i], Ah, Al, off);                                   // G_0
+        tc::split_store4(v1[i], Ah + GW_TILE, Al + GW_TILE, off);               // G_1
+        if (K >= 2) tc::split_store4(v2[i], Ah + 2 * GW_TILE, Al + 2 * GW_TILE, off);   // G_2
+      }
+      fence_proxy_async();
+      tc::mbar_arrive(ready);
+      any = true;
     }
-    fence_proxy_async();
-    tc::fence_before_sync();
-    __syncthreads();          // operand tiles complete; staging slot s has been consumed by every thread
-    if (tid == 0) {
+    if (any) {
+      mbar_wait(bar, par);   // the last chunk's MMAs: the accumulator is final
       tc::fence_after_sync();
-      const uint64_t dAh = tc::smem_desc_mn32(smem_u32(Ah), GW_TILE), dAl = tc::smem_desc_mn32(smem_u32(Al), GW_TILE);
-      const uint64_t dBh = tc::smem_desc_mn32(smem_u32(Bh), GW_TILE), dBl = tc::smem_desc_mn32(smem_u32(Bl), GW_TILE);
-#pragma unroll
-      for (uint32_t ks = 0; ks < GW_ROWS / 8; ++ks) {
-        const uint32_t o = ks * 1024;
-        tc::mma_tf32(tmem, tc::desc_advance(dAl, o), tc::desc_advance(dBl, o), idesc, (first && ks == 0) ? 0u : 1u);
-        tc::mma_tf32(tmem, tc::desc_advance(dAl, o), tc::desc_advance(dBh, o), idesc, 1u);
-        tc::mma_tf32(tmem, tc::desc_advance(dAh, o), tc::desc_advance(dBl, o), idesc, 1u);
-        tc::mma_tf32(tmem, tc::desc_advance(dAh, o), tc::desc_advance(dBh, o), idesc, 1u);
-      }
-      tc::mma_commit(bar);
-      issue(ch + (int64_t)GW_STAGES * gridDim.x, s);   // refill the slot that was just drained
     }
-    first = false;
   }
-  // ---- write this CTA's partial sums ----
+  // ---- write this CTA's partial sums: TMEM lane m = 32*level + c; columns 0-31 (x.hi part) + 32-63 (x.lo part) ----
   float* part = a.partials + (size_t)blockIdx.x * a.partial_stride;
-  const int m = tid;                 // TMEM lane = 32*level + c
-  const int k = m >> 5, c = m & 31;
-  if (!first) {
-    mbar_wait(bar, par);
-    tc::fence_after_sync();
-    float v[32];
-    tc::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16), v);
+  if (warp < 4) {
+    const int m = tid, k = m >> 5, c = m & 31;
+    float vh[32], vl[32];
+    if (any) {   // uniform over the converter warps; tcgen05.ld is warp-collective, so every lane takes part
+      tc::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16), vh);
+      tc::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + 32, vl);
+    } else {     // a CTA without chunks contributes zeros
+#pragma unroll
+      for (int j = 0; j < 32; ++j) vh[j] = vl[j] = 0.0f;
+    }
     if (k <= K && c < cout) {
       float4* dst = reinterpret_cast<float4*>(part + ((size_t)k * cout + c) * 32);
 #pragma unroll
-      for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      for (int q = 0; q < 8; ++q)
+        dst[q] = make_float4(vh[4 * q] + vl[4 * q], vh[4 * q + 1] + vl[4 * q + 1], vh[4 * q + 2] + vl[4 * q + 2], vh[4 * q + 3] + vl[4 * q + 3]);
     }
-  } else if (k <= K && c < cout) {   // a CTA without chunks contributes zeros
-#pragma unroll
-    for (int j = 0; j < 32; ++j) part[((size_t)k * cout + c) * 32 + j] = 0.0f;
   }
-  // bias gradient: 16 row-group partials per column -> shared memory -> 32 column sums in fixed order
+  // bias gradient: 32 row-group partials per column -> shared memory -> 32 column sums in fixed order
   float* red = reinterpret_cast<float*>(stage0);
   __syncthreads();
+  if (!issuer) {
 #pragma unroll
-  for (int e = 0; e < 4; ++e) red[rs * 33 + cq * 4 + e] = gb[e];
+    for (int e = 0; e < 4; ++e) red[rs * 33 + cq * 4 + e] = gb[e];
+  }
   __syncthreads();
   if (tid < 32 && tid < cout) {
     float sum = 0.0f;
-    for (int r = 0; r < 16; ++r) sum += red[r * 33 + tid];
+    for (int r = 0; r < 32; ++r) sum += red[r * 33 + tid];
     part[a.bias_offset + tid] = sum;
   }
   tc::fence_before_sync();
@@ -864,10 +883,10 @@ extern "C" int dss2_tag_bwd_tc2_gw(int64_t num_nodes, const float* x, int cout, 
   const int grid = dss2_sm_count();    // = dss2_num_partials(): every partial row is written
   if (K == 1) {
     DSS2_CUDA(cudaFuncSetAttribute(k_tag_gw<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_tag_gw<1><<<grid, 128, smem, stream>>>(b);
+    k_tag_gw<1><<<grid, GW_THREADS, smem, stream>>>(b);
   } else {
     DSS2_CUDA(cudaFuncSetAttribute(k_tag_gw<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_tag_gw<2><<<grid, 128, smem, stream>>>(b);
+    k_tag_gw<2><<<grid, GW_THREADS, smem, stream>>>(b);
   }
   DSS2_LAUNCH_CHECK();
   return 0;
