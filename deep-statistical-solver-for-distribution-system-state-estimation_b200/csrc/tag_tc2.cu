@@ -424,32 +424,33 @@ constexpr int GW_STAGES = 3;
 constexpr uint32_t GW_STAGE_BYTES = 4 * GW_TILE + 256;   // x, grad_y, A g, A^2 g rows + sign words of one 64-row chunk
 constexpr int GW_CONV = 256;                             // converter threads (8 warps)
 constexpr int GW_THREADS = GW_CONV + 32;                 // + 1 producer / MMA-issuer warp
+// one operand buffer: A.hi[K+1 blocks] A.lo[K+1 blocks] B.hi B.lo.  The M = 128 descriptors span 4 blocks: the blocks past the K+1
+// levels alias whatever follows in the buffer (finite or not: they only feed rows of D that are never read).
+__host__ __device__ constexpr uint32_t gw_ops_bytes(int K) { return (uint32_t)(2 * (K + 1) + 2) * GW_TILE; }
 
 // Roles (ncu on the one-role version: 4 warps, 12 % issue utilisation, the converting thread 0 also spent ~1.9 k cycles per chunk
-// issuing 32 MMAs while the other warps waited at the barrier):
-//   warp 8, lane 0: lands chunks with bulk copies (3-stage ring), and per chunk - once all converters have arrived on `ready` -
+// issuing 32 MMAs while the other warps waited at the barrier; on the single-buffer version: 45 % of the converter samples waiting
+// for the previous chunk's MMAs):
+//   warp 8, lane 0: lands chunks with bulk copies (3-stage ring), and per chunk - once all converters have arrived on `ready[b]` -
 //                   issues 16 MMAs M128 x N64 x K8: A in {G.lo, G.hi} x B = [x.hi ; x.lo] stacked along N (the two halves of D are
-//                   added in the epilogue), commits to `bar`, refills the ring slot the converters have just drained;
-//   warps 0-7:      thread = (16-byte column chunk cq, row rs and rs + 32): staged rows -> registers -> mask -> hi/lo split; wait
-//                   for the previous chunk's MMAs (`bar`), store the operand tiles, arrive on `ready`.
-// Loads + conversion of chunk i+1 overlap the MMA issue and execution of chunk i; only the tile stores wait for the tensor core.
+//                   added in the epilogue), commits to `bar[b]`, refills the ring slot the converters have just drained;
+//   warps 0-7:      thread = (16-byte column chunk cq, rows rs and rs + 32): staged rows -> registers -> mask -> hi/lo split; wait
+//                   until the MMAs that last read operand buffer b (two chunks ago) are complete, store the operand tiles, arrive
+//                   on `ready[b]`.
+// The operand tiles are double buffered, so conversion and tile stores of chunk i+1 overlap the MMAs of chunk i.
 template <int K>
 __global__ void __launch_bounds__(GW_THREADS, 1) k_tag_gw(GwArgs a) {
   extern __shared__ char raw[];
   char* base = align1024(raw);
-  // A side (MN-major, M = 32*level + c): [hi: G_0..G_K, pad][lo: G_0..G_K, pad] each tile 8 KB, LBO = 8 KB; with K = 2 the M = 128
-  // extent covers 3 levels + 1 zero block (rows 96..127 of D are ignored)
-  char* Ah = base;
-  char* Al = Ah + 4 * GW_TILE;
-  // B side (MN-major, N = 64: 32 input features of x.hi, then of x.lo; LBO = 8 KB)
-  char* Bh = Al + 4 * GW_TILE;
-  char* Bl = Bh + GW_TILE;
-  char* stage0 = Bl + GW_TILE;                           // raw rows landed by the TMA engine, GW_STAGES deep
+  constexpr uint32_t OPS = gw_ops_bytes(K);
+  constexpr uint32_t A_LO = (K + 1) * GW_TILE, B_HI = 2 * (K + 1) * GW_TILE, B_LO = B_HI + GW_TILE;
+  char* ops = base;
+  char* stage0 = ops + 2 * OPS;                          // raw rows landed by the TMA engine, GW_STAGES deep
   char* tail = stage0 + GW_STAGES * GW_STAGE_BYTES;
   uint64_t* full = reinterpret_cast<uint64_t*>(tail);    // [GW_STAGES] "chunk has landed"
-  uint64_t* ready = full + GW_STAGES;                    // "operand tiles of this chunk are written" (GW_CONV arrivals)
-  uint64_t* bar = ready + 1;                             // "MMAs of this chunk have completed"
-  uint32_t* tslot = reinterpret_cast<uint32_t*>(bar + 1);
+  uint64_t* ready = full + GW_STAGES;                    // [2] "operand buffer b is written" (GW_CONV arrivals)
+  uint64_t* bar = ready + 2;                             // [2] "the MMAs reading operand buffer b have completed"
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(bar + 2);
   const int tid = threadIdx.x, warp = tid >> 5;
   const bool issuer = warp == GW_CONV / 32;
   const uint32_t cq = tid & 7, rs = (tid >> 3) & 31;
@@ -458,18 +459,12 @@ __global__ void __launch_bounds__(GW_THREADS, 1) k_tag_gw(GwArgs a) {
   if (warp == 0) tc::tmem_alloc(tslot, 64);
   if (tid == 0) {
     for (int s = 0; s < GW_STAGES; ++s) mbar_init(&full[s], 1);
-    mbar_init(ready, GW_CONV);
-    mbar_init(bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&ready[b], GW_CONV);
+      mbar_init(&bar[b], 1);
+    }
     fence_mbar_init();
   }
-  for (int idx = tid; idx < GW_ROWS * 32; idx += GW_THREADS) {   // unused A blocks (M rows beyond the K+1 levels) read as zeros
-    const uint32_t r = idx >> 5, j = idx & 31;
-    for (int blk = K + 1; blk < 4; ++blk) {
-      *reinterpret_cast<float*>(Ah + blk * GW_TILE + tc::swz32_off(r, j)) = 0.0f;
-      *reinterpret_cast<float*>(Al + blk * GW_TILE + tc::swz32_off(r, j)) = 0.0f;
-    }
-  }
-  fence_proxy_async();
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
@@ -478,7 +473,7 @@ __global__ void __launch_bounds__(GW_THREADS, 1) k_tag_gw(GwArgs a) {
   const int64_t num_chunks = (a.num_nodes + GW_ROWS - 1) / GW_ROWS;
   const int64_t full_chunks = a.num_nodes / GW_ROWS;       // only whole chunks go through the bulk-copy engine
   float gb[4] = {0.f, 0.f, 0.f, 0.f};
-  bool any = false;
+  int it = 0;                                              // chunks this CTA has processed (same count in every role)
 
   if (issuer) {
     if ((tid & 31) == 0) {
@@ -497,11 +492,12 @@ __global__ void __launch_bounds__(GW_THREADS, 1) k_tag_gw(GwArgs a) {
       };
       for (int i = 0; i < GW_STAGES; ++i) issue(blockIdx.x + (int64_t)i * gridDim.x, i);
       const uint32_t idesc = tc::idesc_tf32(128, 64, 1, 1);
-      const uint64_t dAh = tc::smem_desc_mn32(smem_u32(Ah), GW_TILE), dAl = tc::smem_desc_mn32(smem_u32(Al), GW_TILE);
-      const uint64_t dB = tc::smem_desc_mn32(smem_u32(Bh), GW_TILE);
-      int it = 0;
       for (int64_t ch = blockIdx.x; ch < num_chunks; ch += gridDim.x, ++it) {
-        mbar_wait(ready, (uint32_t)(it & 1));
+        const int b = it & 1;
+        const uint32_t ob = smem_u32(ops + b * OPS);
+        const uint64_t dAh = tc::smem_desc_mn32(ob, GW_TILE), dAl = tc::smem_desc_mn32(ob + A_LO, GW_TILE);
+        const uint64_t dB = tc::smem_desc_mn32(ob + B_HI, GW_TILE);
+        mbar_wait(&ready[b], (uint32_t)((it >> 1) & 1));
         tc::fence_after_sync();
 #pragma unroll
         for (uint32_t ks = 0; ks < GW_ROWS / 8; ++ks) {
@@ -509,16 +505,14 @@ __global__ void __launch_bounds__(GW_THREADS, 1) k_tag_gw(GwArgs a) {
           tc::mma_tf32(tmem, tc::desc_advance(dAl, o), tc::desc_advance(dB, o), idesc, (it == 0 && ks == 0) ? 0u : 1u);
           tc::mma_tf32(tmem, tc::desc_advance(dAh, o), tc::desc_advance(dB, o), idesc, 1u);
         }
-        tc::mma_commit(bar);
+        tc::mma_commit(&bar[b]);
         issue(ch + (int64_t)GW_STAGES * gridDim.x, it % GW_STAGES);   // every converter has read this slot before arriving on `ready`
       }
     }
     __syncwarp();
   } else {
-    uint32_t par = 0;
-    int it = 0;
     for (int64_t ch = blockIdx.x; ch < num_chunks; ch += gridDim.x, ++it) {
-      const int s = it % GW_STAGES;
+      const int s = it % GW_STAGES, b = it & 1;
       const bool staged = ch < full_chunks;
       const char* st = stage0 + (size_t)s * GW_STAGE_BYTES;
       if (staged) mbar_wait(&full[s], (uint32_t)((it / GW_STAGES) & 1));
@@ -570,10 +564,11 @@ __global__ void __launch_bounds__(GW_THREADS, 1) k_tag_gw(GwArgs a) {
         gb[2] += vg[i].z;
         gb[3] += vg[i].w;
       }
-      if (any) {   // the previous chunk's MMAs still read the operand tiles
-        mbar_wait(bar, par);
-        par ^= 1u;
-      }
+      if (it >= 2) mbar_wait(&bar[b], (uint32_t)(((it >> 1) - 1) & 1));   // the MMAs of chunk it-2 read this operand buffer
+      char* Ah = ops + b * OPS;
+      char* Al = Ah + A_LO;
+      char* Bh = Ah + B_HI;
+      char* Bl = Ah + B_LO;
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         const uint32_t off = tc::swz32_off(rs + 32 * i, cq * 4);
@@ -583,11 +578,11 @@ __global__ void __launch_bounds__(GW_THREADS, 1) k_tag_gw(GwArgs a) {
         if (K >= 2) tc::split_store4(v2[i], Ah + 2 * GW_TILE, Al + 2 * GW_TILE, off);   // G_2
       }
       fence_proxy_async();
-      tc::mbar_arrive(ready);
-      any = true;
+      tc::mbar_arrive(&ready[b]);
     }
-    if (any) {
-      mbar_wait(bar, par);   // the last chunk's MMAs: the accumulator is final
+    if (it > 0) {   // the last chunk's commit covers every MMA issued before it: the accumulator is final
+      const int last = it - 1;
+      mbar_wait(&bar[last & 1], (uint32_t)((last >> 1) & 1));
       tc::fence_after_sync();
     }
   }
@@ -596,7 +591,7 @@ __global__ void __launch_bounds__(GW_THREADS, 1) k_tag_gw(GwArgs a) {
   if (warp < 4) {
     const int m = tid, k = m >> 5, c = m & 31;
     float vh[32], vl[32];
-    if (any) {   // uniform over the converter warps; tcgen05.ld is warp-collective, so every lane takes part
+    if (it > 0) {   // uniform over the converter warps; tcgen05.ld is warp-collective, so every lane takes part
       tc::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16), vh);
       tc::tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + 32, vl);
     } else {     // a CTA without chunks contributes zeros
@@ -772,7 +767,7 @@ __global__ void __launch_bounds__(GWF_THREADS, 1) k_tag_gw_ffma(GwArgs a) {
 }
 
 size_t tc2_smem(int K, int nb) { return 1024 + (size_t)(K + 1) * 2 * W_TILE + 4 * (size_t)nb * 128 * tc::ROW_BYTES + 256; }   // 89 KB (2 CTAs/SM) or 153 KB
-size_t gw_smem() { return 1024 + 10 * GW_TILE + GW_STAGES * GW_STAGE_BYTES + 128; }
+size_t gw_smem(int K) { return 1024 + 2 * gw_ops_bytes(K) + GW_STAGES * GW_STAGE_BYTES + 128; }
 
 int tc2_supported(const dss2_graph_t* g, int K) {
   return g && g->num_tiles > 0 && g->max_tile_nodes <= T2_MAX && K >= 1 && K <= 2 && g->ell_w && g->ell_ci;
@@ -879,7 +874,7 @@ extern "C" int dss2_tag_bwd_tc2_gw(int64_t num_nodes, const float* x, int cout, 
   b.partials = partials;
   b.partial_stride = partial_stride;
   b.bias_offset = bias_offset;
-  const size_t smem = gw_smem();
+  const size_t smem = gw_smem(K);
   const int grid = dss2_sm_count();    // = dss2_num_partials(): every partial row is written
   if (K == 1) {
     DSS2_CUDA(cudaFuncSetAttribute(k_tag_gw<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
