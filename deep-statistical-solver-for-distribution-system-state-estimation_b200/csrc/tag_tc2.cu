@@ -422,8 +422,8 @@ struct GwArgs {
 
 constexpr int GW_STAGES = 3;
 constexpr uint32_t GW_STAGE_BYTES = 4 * GW_TILE + 256;   // x, grad_y, A g, A^2 g rows + sign words of one 64-row chunk
-constexpr int GW_CONV = 256;                             // converter threads (8 warps)
-constexpr int GW_THREADS = GW_CONV + 32;                 // + 1 producer / MMA-issuer warp
+constexpr int GW_CONV = 512;                             // converter threads (16 warps): thread = (16-byte column chunk, row of the chunk)
+constexpr int GW_THREADS = GW_CONV + 64;                 // + 1 MMA-issuer warp + 1 bulk-copy producer warp
 // one operand buffer: A.hi[K+1 blocks] A.lo[K+1 blocks] B.hi B.lo.  The M = 128 descriptors span 4 blocks: the blocks past the K+1
 // levels alias whatever follows in the buffer (finite or not: they only feed rows of D that are never read).
 __host__ __device__ constexpr uint32_t gw_ops_bytes(int K) { return (uint32_t)(2 * (K + 1) + 2) * GW_TILE; }
@@ -431,12 +431,14 @@ __host__ __device__ constexpr uint32_t gw_ops_bytes(int K) { return (uint32_t)(2
 // Roles (ncu on the one-role version: 4 warps, 12 % issue utilisation, the converting thread 0 also spent ~1.9 k cycles per chunk
 // issuing 32 MMAs while the other warps waited at the barrier; on the single-buffer version: 45 % of the converter samples waiting
 // for the previous chunk's MMAs):
-//   warp 8, lane 0: lands chunks with bulk copies (3-stage ring), and per chunk - once all converters have arrived on `ready[b]` -
-//                   issues 16 MMAs M128 x N64 x K8: A in {G.lo, G.hi} x B = [x.hi ; x.lo] stacked along N (the two halves of D are
-//                   added in the epilogue), commits to `bar[b]`, refills the ring slot the converters have just drained;
-//   warps 0-7:      thread = (16-byte column chunk cq, rows rs and rs + 32): staged rows -> registers -> mask -> hi/lo split; wait
-//                   until the MMAs that last read operand buffer b (two chunks ago) are complete, store the operand tiles, arrive
-//                   on `ready[b]`.
+//   warp 16, lane 0: per chunk - once all converters have arrived on `ready[b]` - issues 16 MMAs M128 x N64 x K8: A in {G.lo, G.hi}
+//                    x B = [x.hi ; x.lo] stacked along N (the two halves of D are added in the epilogue), commits to `bar[b]`;
+//   warp 17, lane 0: lands chunks with bulk copies (3-stage ring); a slot is refilled as soon as `ready[b]` says that every
+//                    converter has read it (clock64 stamps: issuing 16 MMAs costs ~980 cycles and 5 bulk copies ~430, so the two
+//                    jobs get a thread each);
+//   warps 0-15:      thread = (16-byte column chunk cq, row rs): staged row -> registers -> mask -> hi/lo split; wait until the
+//                    MMAs that last read operand buffer b (two chunks ago) are complete, store the operand tiles, arrive on
+//                    `ready[b]`.
 // The operand tiles are double buffered, so conversion and tile stores of chunk i+1 overlap the MMAs of chunk i.
 template <int K>
 __global__ void __launch_bounds__(GW_THREADS, 1) k_tag_gw(GwArgs a) {
@@ -448,17 +450,21 @@ __global__ void __launch_bounds__(GW_THREADS, 1) k_tag_gw(GwArgs a) {
   char* stage0 = ops + 2 * OPS;                          // raw rows landed by the TMA engine, GW_STAGES deep
   char* tail = stage0 + GW_STAGES * GW_STAGE_BYTES;
   uint64_t* full = reinterpret_cast<uint64_t*>(tail);    // [GW_STAGES] "chunk has landed"
-  uint64_t* ready = full + GW_STAGES;                    // [2] "operand buffer b is written" (GW_CONV arrivals)
+  uint64_t* empty = full + GW_STAGES;                    // [GW_STAGES] "every converter has read the slot" (GW_CONV arrivals)
+  uint64_t* ready = empty + GW_STAGES;                   // [2] "operand buffer b is written" (GW_CONV arrivals)
   uint64_t* bar = ready + 2;                             // [2] "the MMAs reading operand buffer b have completed"
   uint32_t* tslot = reinterpret_cast<uint32_t*>(bar + 2);
   const int tid = threadIdx.x, warp = tid >> 5;
-  const bool issuer = warp == GW_CONV / 32;
-  const uint32_t cq = tid & 7, rs = (tid >> 3) & 31;
+  const bool issuer = warp == GW_CONV / 32, producer = warp == GW_CONV / 32 + 1;
+  const uint32_t cq = tid & 7, rs = (tid >> 3) & 63;
   const int cout = a.cout;
 
   if (warp == 0) tc::tmem_alloc(tslot, 64);
   if (tid == 0) {
-    for (int s = 0; s < GW_STAGES; ++s) mbar_init(&full[s], 1);
+    for (int s = 0; s < GW_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], GW_CONV);
+    }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&ready[b], GW_CONV);
       mbar_init(&bar[b], 1);
@@ -475,7 +481,7 @@ __global__ void __launch_bounds__(GW_THREADS, 1) k_tag_gw(GwArgs a) {
   float gb[4] = {0.f, 0.f, 0.f, 0.f};
   int it = 0;                                              // chunks this CTA has processed (same count in every role)
 
-  if (issuer) {
+  if (producer) {
     if ((tid & 31) == 0) {
       const uint32_t gy_bytes = (uint32_t)(GW_ROWS * cout * 4);
       const uint32_t tx = GW_TILE * (K >= 2 ? 3 : 2) + gy_bytes + (a.bits ? 256u : 0u);
@@ -491,6 +497,15 @@ __global__ void __launch_bounds__(GW_THREADS, 1) k_tag_gw(GwArgs a) {
         if (a.bits) bulk_g2s(st + 4 * GW_TILE, a.bits + n, 256, &full[s]);
       };
       for (int i = 0; i < GW_STAGES; ++i) issue(blockIdx.x + (int64_t)i * gridDim.x, i);
+      for (int64_t ch = blockIdx.x; ch < num_chunks; ch += gridDim.x, ++it) {
+        const int s = it % GW_STAGES;
+        mbar_wait(&empty[s], (uint32_t)((it / GW_STAGES) & 1));      // every converter has read the slot into registers
+        issue(ch + (int64_t)GW_STAGES * gridDim.x, s);
+      }
+    }
+    __syncwarp();
+  } else if (issuer) {
+    if ((tid & 31) == 0) {
       const uint32_t idesc = tc::idesc_tf32(128, 64, 1, 1);
       for (int64_t ch = blockIdx.x; ch < num_chunks; ch += gridDim.x, ++it) {
         const int b = it & 1;
@@ -506,7 +521,6 @@ __global__ void __launch_bounds__(GW_THREADS, 1) k_tag_gw(GwArgs a) {
           tc::mma_tf32(tmem, tc::desc_advance(dAh, o), tc::desc_advance(dB, o), idesc, 1u);
         }
         tc::mma_commit(&bar[b]);
-        issue(ch + (int64_t)GW_STAGES * gridDim.x, it % GW_STAGES);   // every converter has read this slot before arriving on `ready`
       }
     }
     __syncwarp();
@@ -516,67 +530,61 @@ __global__ void __launch_bounds__(GW_THREADS, 1) k_tag_gw(GwArgs a) {
       const bool staged = ch < full_chunks;
       const char* st = stage0 + (size_t)s * GW_STAGE_BYTES;
       if (staged) mbar_wait(&full[s], (uint32_t)((it / GW_STAGES) & 1));
-      float4 vx[2], vg[2], v1[2], v2[2];
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const uint32_t r = rs + 32 * i;
-        const int64_t n = ch * GW_ROWS + r;
-        const bool inb = n < a.num_nodes;
-        vx[i] = vg[i] = v1[i] = v2[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        uint32_t word = 0xffffffffu;
-        if (staged) {
-          vx[i] = *reinterpret_cast<const float4*>(st + r * 128 + cq * 16);
-          v1[i] = *reinterpret_cast<const float4*>(st + 2 * GW_TILE + r * 128 + cq * 16);
-          if (K >= 2) v2[i] = *reinterpret_cast<const float4*>(st + 3 * GW_TILE + r * 128 + cq * 16);
-          if (cout == 32) {
-            vg[i] = *reinterpret_cast<const float4*>(st + GW_TILE + r * 128 + cq * 16);
-          } else {
-            const float* gp = reinterpret_cast<const float*>(st + GW_TILE) + r * cout;
-            float t4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if ((int)(cq * 4 + e) < cout) t4[e] = gp[cq * 4 + e];
-            vg[i] = make_float4(t4[0], t4[1], t4[2], t4[3]);
-          }
-          if (a.bits) word = reinterpret_cast<const uint32_t*>(st + 4 * GW_TILE)[r];
-        } else if (inb) {   // the one ragged chunk at the end of the batch: plain bounded loads
-          vx[i] = *reinterpret_cast<const float4*>(a.x + n * 32 + cq * 4);
-          v1[i] = *reinterpret_cast<const float4*>(a.lvl + n * 32 + cq * 4);
-          if (K >= 2) v2[i] = *reinterpret_cast<const float4*>(a.lvl + (a.num_nodes + n) * 32 + cq * 4);
+      const uint32_t r = rs;
+      const int64_t n = ch * GW_ROWS + r;
+      float4 vx, vg, v1, v2;
+      vx = vg = v1 = v2 = make_float4(0.f, 0.f, 0.f, 0.f);
+      uint32_t word = 0xffffffffu;
+      if (staged) {
+        vx = *reinterpret_cast<const float4*>(st + r * 128 + cq * 16);
+        v1 = *reinterpret_cast<const float4*>(st + 2 * GW_TILE + r * 128 + cq * 16);
+        if (K >= 2) v2 = *reinterpret_cast<const float4*>(st + 3 * GW_TILE + r * 128 + cq * 16);
+        if (cout == 32) {
+          vg = *reinterpret_cast<const float4*>(st + GW_TILE + r * 128 + cq * 16);
+        } else {
+          const float* gp = reinterpret_cast<const float*>(st + GW_TILE) + r * cout;
           float t4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int e = 0; e < 4; ++e)
-            if ((int)(cq * 4 + e) < cout) t4[e] = a.gy[n * cout + cq * 4 + e];
-          vg[i] = make_float4(t4[0], t4[1], t4[2], t4[3]);
-          if (a.bits) word = a.bits[n];
+            if ((int)(cq * 4 + e) < cout) t4[e] = gp[cq * 4 + e];
+          vg = make_float4(t4[0], t4[1], t4[2], t4[3]);
         }
-        if (a.bits) {
-          const uint32_t w4 = word >> (cq * 4);
-          vg[i].x = (w4 & 1u) ? vg[i].x * a.scale : 0.0f;
-          vg[i].y = (w4 & 2u) ? vg[i].y * a.scale : 0.0f;
-          vg[i].z = (w4 & 4u) ? vg[i].z * a.scale : 0.0f;
-          vg[i].w = (w4 & 8u) ? vg[i].w * a.scale : 0.0f;
-        }
-        // grad_b = column sums of the masked output gradient, exact fp32 on the CUDA cores (a ones-column in the GEMM would inherit
-        // the 2^-23 TF32-pair representation error, visible in this cancelling sum)
-        gb[0] += vg[i].x;
-        gb[1] += vg[i].y;
-        gb[2] += vg[i].z;
-        gb[3] += vg[i].w;
+        if (a.bits) word = reinterpret_cast<const uint32_t*>(st + 4 * GW_TILE)[r];
+      } else if (n < a.num_nodes) {   // the one ragged chunk at the end of the batch: plain bounded loads
+        vx = *reinterpret_cast<const float4*>(a.x + n * 32 + cq * 4);
+        v1 = *reinterpret_cast<const float4*>(a.lvl + n * 32 + cq * 4);
+        if (K >= 2) v2 = *reinterpret_cast<const float4*>(a.lvl + (a.num_nodes + n) * 32 + cq * 4);
+        float t4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if ((int)(cq * 4 + e) < cout) t4[e] = a.gy[n * cout + cq * 4 + e];
+        vg = make_float4(t4[0], t4[1], t4[2], t4[3]);
+        if (a.bits) word = a.bits[n];
       }
+      if (a.bits) {
+        const uint32_t w4 = word >> (cq * 4);
+        vg.x = (w4 & 1u) ? vg.x * a.scale : 0.0f;
+        vg.y = (w4 & 2u) ? vg.y * a.scale : 0.0f;
+        vg.z = (w4 & 4u) ? vg.z * a.scale : 0.0f;
+        vg.w = (w4 & 8u) ? vg.w * a.scale : 0.0f;
+      }
+      tc::mbar_arrive(&empty[s]);   // slot s is in registers: the producer may refill it
+      // grad_b = column sums of the masked output gradient, exact fp32 on the CUDA cores (a ones-column in the GEMM would inherit
+      // the 2^-23 TF32-pair representation error, visible in this cancelling sum)
+      gb[0] += vg.x;
+      gb[1] += vg.y;
+      gb[2] += vg.z;
+      gb[3] += vg.w;
       if (it >= 2) mbar_wait(&bar[b], (uint32_t)(((it >> 1) - 1) & 1));   // the MMAs of chunk it-2 read this operand buffer
       char* Ah = ops + b * OPS;
       char* Al = Ah + A_LO;
       char* Bh = Ah + B_HI;
       char* Bl = Ah + B_LO;
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const uint32_t off = tc::swz32_off(rs + 32 * i, cq * 4);
-        tc::split_store4(vx[i], Bh, Bl, off);                                   // x
-        tc::split_store4(vg[i], Ah, Al, off);                                   // G_0
-        tc::split_store4(v1[i], Ah + GW_TILE, Al + GW_TILE, off);               // G_1
-        if (K >= 2) tc::split_store4(v2[i], Ah + 2 * GW_TILE, Al + 2 * GW_TILE, off);   // G_2
-      }
+      const uint32_t off = tc::swz32_off(r, cq * 4);
+      tc::split_store4(vx, Bh, Bl, off);                                      // x
+      tc::split_store4(vg, Ah, Al, off);                                      // G_0
+      tc::split_store4(v1, Ah + GW_TILE, Al + GW_TILE, off);                  // G_1
+      if (K >= 2) tc::split_store4(v2, Ah + 2 * GW_TILE, Al + 2 * GW_TILE, off);   // G_2
       fence_proxy_async();
       tc::mbar_arrive(&ready[b]);
     }
@@ -605,17 +613,17 @@ __global__ void __launch_bounds__(GW_THREADS, 1) k_tag_gw(GwArgs a) {
         dst[q] = make_float4(vh[4 * q] + vl[4 * q], vh[4 * q + 1] + vl[4 * q + 1], vh[4 * q + 2] + vl[4 * q + 2], vh[4 * q + 3] + vl[4 * q + 3]);
     }
   }
-  // bias gradient: 32 row-group partials per column -> shared memory -> 32 column sums in fixed order
+  // bias gradient: 64 row partials per column -> shared memory -> 32 column sums in fixed order
   float* red = reinterpret_cast<float*>(stage0);
   __syncthreads();
-  if (!issuer) {
+  if (tid < GW_CONV) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) red[rs * 33 + cq * 4 + e] = gb[e];
   }
   __syncthreads();
   if (tid < 32 && tid < cout) {
     float sum = 0.0f;
-    for (int r = 0; r < 32; ++r) sum += red[r * 33 + tid];
+    for (int r = 0; r < 64; ++r) sum += red[r * 33 + tid];
     part[a.bias_offset + tid] = sum;
   }
   tc::fence_before_sync();
@@ -767,7 +775,7 @@ __global__ void __launch_bounds__(GWF_THREADS, 1) k_tag_gw_ffma(GwArgs a) {
 }
 
 size_t tc2_smem(int K, int nb) { return 1024 + (size_t)(K + 1) * 2 * W_TILE + 4 * (size_t)nb * 128 * tc::ROW_BYTES + 256; }   // 89 KB (2 CTAs/SM) or 153 KB
-size_t gw_smem(int K) { return 1024 + 2 * gw_ops_bytes(K) + GW_STAGES * GW_STAGE_BYTES + 128; }
+size_t gw_smem(int K) { return 1024 + 2 * gw_ops_bytes(K) + GW_STAGES * GW_STAGE_BYTES + 128; }   // 128: 10 mbarriers + TMEM slot
 
 int tc2_supported(const dss2_graph_t* g, int K) {
   return g && g->num_tiles > 0 && g->max_tile_nodes <= T2_MAX && K >= 1 && K <= 2 && g->ell_w && g->ell_ci;
