@@ -292,10 +292,12 @@ __global__ void __launch_bounds__(256 * NB + 32, 3 - NB) k_tag_tc2(Tc2Args a) {
       const RowTopo tp = tp_next;
       // ---- level 0 (buffer 0 is free: the previous tile's epilogue waited for its last MMAs) ----
       store_half_sw128(xr, lv_p(0), lv_l(0), row, half);          // dead rows store zeros: keeps the MMA input finite
-      cur = nxt;
-      load_row(cur);                                               // prefetch next tile: rows (same registers) + topology
-      nxt = tile_nodes(g, t + 2 * gridDim.x);                      // and the node range of the tile after it
       publish(0);
+      // prefetch AFTER the publish: fence.proxy.async waits for every earlier memory operation of the thread, global loads and
+      // stores included (clock64 stamps: +560 cycles per tile with the loads in front of it, +1300 per level with the spill stores)
+      cur = nxt;
+      load_row(cur);                                               // next tile: rows (same registers) + topology
+      nxt = tile_nodes(g, t + 2 * gridDim.x);                      // and the node range of the tile after it
       // ---- levels 1..K ----
 #pragma unroll
       for (int k = 1; k <= K; ++k) {
@@ -311,13 +313,16 @@ __global__ void __launch_bounds__(256 * NB + 32, 3 - NB) k_tag_tc2(Tc2Args a) {
           par[b] ^= 1u;
         }
         store_half_sw128(h, lv_p(b), lv_l(b), row, half);
-        if (MODE == MODE_BGX && a.lvl_out && live) {
+        publish(b);
+        if (MODE == MODE_BGX && a.lvl_out && live) {   // hop-level spill for the weight-gradient pass (after the publish, see above)
           float4* dst = reinterpret_cast<float4*>(a.lvl_out + ((size_t)(k - 1) * g.num_nodes + n) * 32 + half * HF);
 #pragma unroll
           for (int q = 0; q < 4; ++q) dst[q] = make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
         }
-        publish(b);
       }
+      // dropout keep bits do not depend on the MMAs: generate them while the tensor core finishes
+      uint32_t keep_rng = 0xffffu;
+      if (MODE == MODE_FWD && a.act && a.drop_mode == 1 && live) keep_rng = keep_half(key, (uint32_t)t, row, half, step_lo, a.keep_thr16);
       // ---- all MMAs of the tile complete when the last two commits have arrived ----
       if (K >= 1) {
         const int b2 = (K - 1) & 1;
@@ -350,7 +355,7 @@ __global__ void __launch_bounds__(256 * NB + 32, 3 - NB) k_tag_tc2(Tc2Args a) {
           if (a.act) {
             uint32_t keep = 0xffffu;
             if (a.drop_mode == 1) {
-              keep = keep_half(key, (uint32_t)t, row, half, step_lo, a.keep_thr16);
+              keep = keep_rng;
             } else if (a.drop_mode == 2) {
               const uint4 m0 = *reinterpret_cast<const uint4*>(a.mask + n * HID + half * HF);
               const uint32_t mw[4] = {m0.x, m0.y, m0.z, m0.w};
