@@ -293,11 +293,11 @@ __global__ void __launch_bounds__(256 * NB + 32, 3 - NB) k_tag_tc2(Tc2Args a) {
       // ---- level 0 (buffer 0 is free: the previous tile's epilogue waited for its last MMAs) ----
       store_half_sw128(xr, lv_p(0), lv_l(0), row, half);          // dead rows store zeros: keeps the MMA input finite
       publish(0);
-      // prefetch AFTER the publish: fence.proxy.async waits for every earlier memory operation of the thread, global loads and
-      // stores included (clock64 stamps: +560 cycles per tile with the loads in front of it, +1300 per level with the spill stores)
-      cur = nxt;
-      load_row(cur);                                               // next tile: rows (same registers) + topology
-      nxt = tile_nodes(g, t + 2 * gridDim.x);                      // and the node range of the tile after it
+      if (MODE == MODE_BGX) {   // see the note on the prefetch below: with the spill stores in flight the backward measures best here
+        cur = nxt;
+        load_row(cur);
+        nxt = tile_nodes(g, t + 2 * gridDim.x);
+      }
       // ---- levels 1..K ----
 #pragma unroll
       for (int k = 1; k <= K; ++k) {
@@ -314,11 +314,22 @@ __global__ void __launch_bounds__(256 * NB + 32, 3 - NB) k_tag_tc2(Tc2Args a) {
         }
         store_half_sw128(h, lv_p(b), lv_l(b), row, half);
         publish(b);
-        if (MODE == MODE_BGX && a.lvl_out && live) {   // hop-level spill for the weight-gradient pass (after the publish, see above)
+        // hop-level spill for the weight-gradient pass.  Its stores drain during the next hop; the fence of the next publish still
+        // waits for their tail (measured: cheaper than deferring all spills to the tile end, where they pile up with the output
+        // stores in front of the next tile's first fence: 88 vs 103 us)
+        if (MODE == MODE_BGX && a.lvl_out && live) {
           float4* dst = reinterpret_cast<float4*>(a.lvl_out + ((size_t)(k - 1) * g.num_nodes + n) * 32 + half * HF);
 #pragma unroll
           for (int q = 0; q < 4; ++q) dst[q] = make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
         }
+      }
+      // The prefetch of the next tile sits here, behind the tile's LAST proxy fence: fence.proxy.async waits for every earlier memory
+      // operation of the thread, global ones included (clock64 stamps: a prefetch issued before a publish costs ~2000 cycles of
+      // exposed DRAM latency at that publish).  From here the loads have the whole epilogue to land.
+      if (MODE == MODE_FWD) {
+        cur = nxt;
+        load_row(cur);                                             // next tile: rows (same registers) + topology
+        nxt = tile_nodes(g, t + 2 * gridDim.x);                    // and the node range of the tile after it
       }
       // dropout keep bits do not depend on the MMAs: generate them while the tensor core finishes
       uint32_t keep_rng = 0xffffu;
