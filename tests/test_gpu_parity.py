@@ -838,3 +838,57 @@ def test_model_kernels_with_exact_weight_gradient_pass(env, monkeypatch, tag):
     which measures faster, is the default."""
     monkeypatch.setattr(env["ops"], "GW_IMPL", "ffma")
     _tie_aware_model_check(env, tag, "tc2")
+
+
+# ------------------------------------------------------------------------------------------------ ragged batches of mixed grids
+def _mixed_grid_batch(env):
+    """Scenarios of three grids (15-, 15- and 70-bus graphs, different edge counts) interleaved in one batch."""
+    graphs, stats = [], None
+    for case, k, seed in (("cigre14", 5, 1), ("ober_sub", 3, 2), ("cigre14_reswitched", 4, 3)):
+        st = env["synth"].synthetic_store(env["synth"].load_grid(case), k, seed=seed)
+        if case == "ober_sub":
+            stats = [st.x_mean, st.x_std, st.edge_mean, st.edge_std]
+        graphs += [st.graph(i) for i in range(k)]
+    order = [0, 5, 8, 1, 6, 9, 2, 7, 10, 3, 11, 4]
+    data = [env["batching"].Data(**{k: v.clone() for k, v in graphs[i].items()}) for i in order]
+    store = env["batching"].store_from_graphs(data, "cuda")
+    b = env["batching"].pack_batch(store, list(range(len(order))))
+    return b, [graphs[i] for i in order], stats
+
+
+def _mixed_grid_model_check(env):
+    b, graphs, stats = _mixed_grid_batch(env)
+    ref = orc.collate(graphs)
+    for k in ("x", "edge_index", "edge_attr", "batch", "ptr"):
+        assert torch.equal(getattr(b, k).cpu(), ref[k]), k
+    ctor = dict(dim_featn=8, dim_feate=6, dim_out=2, dim_hid=32, n_gnn_layers=3, K=2, dropout_rate=0.0, L=2)
+    sd = orc.init_state_dict("SkipPFN", n_gnn_layers=3, L=2, seed=21)
+    model = env["networks"].SkipPFN(**ctor)
+    model.load_state_dict(sd, strict=True)
+    model = model.cuda().train()
+    out = model(b.x[:, :8], b.edge_index, b.edge_attr[:, :6])
+    out_before = out.detach().clone()
+    loss = env["data"].gsp_wls_edge(input=b.x[:, :8], edge_input=b.edge_attr[:, :6], output=out, x_mean=stats[0], x_std=stats[1],
+                                    edge_mean=stats[2], edge_std=stats[3], edge_index=b.edge_index, reg_coefs=REG_COEFS, num_samples=None,
+                                    node_param=b.x[:, 8:], edge_param=b.edge_attr[:, 6:])
+    loss.backward()
+    res = {}
+    for dtype in (torch.float32, torch.float64):
+        p = {k: v.to(dtype).clone().requires_grad_(True) for k, v in sd.items()}
+        o = orc.pfn_forward(p, ref["x"].to(dtype)[:, :8], ref["edge_index"], ref["edge_attr"].to(dtype)[:, :6], 0.0, skip=True)
+        l = orc.wls_loss(ref["x"].to(dtype), ref["edge_attr"].to(dtype), o, *[s.to(dtype) for s in stats], ref["edge_index"], REG_COEFS)
+        l.backward()
+        res[dtype] = (o.detach(), l.detach(), {k: v.grad for k, v in p.items()})
+    assert_fp32_parity(out_before, res[torch.float32][0], res[torch.float64][0], "out")
+    assert_fp32_parity(loss.detach(), res[torch.float32][1], res[torch.float64][1], "loss")
+    for name, prm in model.named_parameters():
+        assert_fp32_parity(prm.grad, res[torch.float32][2][name], res[torch.float64][2][name], name, noise_mult=8.0)
+
+
+def test_ragged_mixed_grid_batch_tiled(env):
+    """Tiles hold a varying number of whole graphs of different sizes (ragged ELL / tile ranges), loss with per-batch vn_kv extremes."""
+    _mixed_grid_model_check(env)
+
+
+def test_ragged_mixed_grid_batch_large_graph_path(env, tiny_tiles):
+    _mixed_grid_model_check(env)
