@@ -211,6 +211,72 @@ def init_state_dict(kind="SkipPFN", dim_featn=8, dim_feate=6, dim_out=2, dim_hid
 
 
 # --------------------------------------------------------------------------------------------
+# GAT_DSSE (networks.py:113-156): 7 x (GATv2Conv(8, 8, heads=1, edge_dim=6, add_self_loops, fill 'mean') + LeakyReLU(0.01)),
+# Linear(8, 32), Linear(32, 2).  SURVEY.md 8f-1: the as-shipped default model of dss2_run.py:86.
+# --------------------------------------------------------------------------------------------
+
+
+def gatv2_layer(x, edge_index, edge_attr, w_l, b_l, w_r, b_r, w_e, att, bias, slope=0.2):
+    """One GATv2Conv (heads = 1) on the ONE-WAY edge list the script passes (networks.py:146 gets `data.edge_index` as is).
+    Self loops of the input are dropped, then one loop per node is appended whose attribute is the mean of the attributes of the
+    edges pointing at the node (0 without any).  Segment softmax as PyG: max-shifted exp / (sum + 1e-16)."""
+    n = x.size(0)
+    keep = edge_index[0] != edge_index[1]
+    src, dst, ea = edge_index[0][keep], edge_index[1][keep], edge_attr[keep]
+    cnt = segment_sum(torch.ones(dst.numel(), 1, dtype=x.dtype), dst, n).clamp(min=1)
+    loop_attr = segment_sum(ea, dst, n) / cnt
+    loop = torch.arange(n)
+    src, dst, ea = torch.cat([src, loop]), torch.cat([dst, loop]), torch.cat([ea, loop_attr])
+    x_l = x @ w_l.t() + b_l
+    x_r = x @ w_r.t() + b_r
+    s = torch.nn.functional.leaky_relu(x_r[dst] + x_l[src] + ea @ w_e.t(), slope)
+    score = (s * att.view(1, -1)).sum(-1)
+    smax = torch.full((n,), float("-inf"), dtype=x.dtype).scatter_reduce(0, dst, score.detach(), reduce="amax", include_self=True)
+    ex = (score - smax[dst]).exp()
+    den = segment_sum(ex.view(-1, 1), dst, n).view(-1) + 1e-16
+    alpha = ex / den[dst]
+    return segment_sum(x_l[src] * alpha.view(-1, 1), dst, n) + bias
+
+
+def gat_dsse_forward(sd, x, edge_index, edge_attr, num_layers=8):
+    """GAT_DSSE.forward (networks.py:155-156) from a reference-named state_dict (`model.module_{i}.*`, PyG Sequential naming)."""
+    h = x
+    for l in range(num_layers - 1):
+        p = f"model.module_{2 * l}."
+        h = gatv2_layer(h, edge_index, edge_attr, sd[p + "lin_l.weight"], sd[p + "lin_l.bias"], sd[p + "lin_r.weight"], sd[p + "lin_r.bias"],
+                        sd[p + "lin_edge.weight"], sd[p + "att"], sd[p + "bias"])
+        h = torch.nn.functional.leaky_relu(h, 0.01)
+    i = 2 * (num_layers - 1)
+    h = h @ sd[f"model.module_{i}.weight"].t() + sd[f"model.module_{i}.bias"]
+    return h @ sd[f"model.module_{i + 1}.weight"].t() + sd[f"model.module_{i + 1}.bias"]
+
+
+def init_gat_state_dict(dim_feat=8, dim_dense=32, dim_out=2, num_layers=8, edge_dim=6, seed=0, dtype=torch.float32):
+    """Random GAT_DSSE parameters with the reference's names/shapes; all biases non-zero so every path is exercised."""
+    g = torch.Generator().manual_seed(seed)
+
+    def u(*shape, bound):
+        return ((torch.rand(*shape, generator=g, dtype=torch.float64) * 2 - 1) * bound).to(dtype)
+
+    sd = {}
+    for l in range(num_layers - 1):
+        p = f"model.module_{2 * l}."
+        sd[p + "att"] = u(1, 1, dim_feat, bound=0.8)
+        sd[p + "bias"] = u(dim_feat, bound=0.1)
+        sd[p + "lin_l.weight"] = u(dim_feat, dim_feat, bound=0.6)
+        sd[p + "lin_l.bias"] = u(dim_feat, bound=0.1)
+        sd[p + "lin_r.weight"] = u(dim_feat, dim_feat, bound=0.6)
+        sd[p + "lin_r.bias"] = u(dim_feat, bound=0.1)
+        sd[p + "lin_edge.weight"] = u(dim_feat, edge_dim, bound=0.6)
+    i = 2 * (num_layers - 1)
+    sd[f"model.module_{i}.weight"] = u(dim_dense, dim_feat, bound=1.0 / math.sqrt(dim_feat))
+    sd[f"model.module_{i}.bias"] = u(dim_dense, bound=1.0 / math.sqrt(dim_feat))
+    sd[f"model.module_{i + 1}.weight"] = u(dim_out, dim_dense, bound=1.0 / math.sqrt(dim_dense))
+    sd[f"model.module_{i + 1}.bias"] = u(dim_out, bound=1.0 / math.sqrt(dim_dense))
+    return sd
+
+
+# --------------------------------------------------------------------------------------------
 # physics: branch flows (data.py:328-390) and the WLS loss (data.py:393-459)
 # --------------------------------------------------------------------------------------------
 

@@ -1,16 +1,16 @@
 """`torch_geometric.nn.conv` subset (oracle shim, test infrastructure).
 
 Implemented from PyG's published semantics: MessagePassing(aggr='add', flow='source_to_target'),
-gcn_norm(add_self_loops=False), TAGConv.  The other conv classes named by reference networks.py:7
-(GCN2Conv, FAConv, GINEConv, GCNConv, ChebConv, GATv2Conv) are outside the hot path
- and exist only as names so that the reference module imports.
+gcn_norm(add_self_loops=False), TAGConv, and GATv2Conv (the as-shipped default model of
+dss2_run.py:86).  The other conv classes named by reference networks.py:7 (GCN2Conv, FAConv, GINEConv,
+GCNConv, ChebConv) exist only as names so that the reference module imports.
 """
 import inspect
 
 import torch
 from torch import nn
 
-from ..utils import scatter
+from ..utils import add_self_loops, remove_self_loops, scatter, softmax
 
 
 class MessagePassing(nn.Module):
@@ -121,4 +121,67 @@ FAConv = _outside_hot_path("FAConv")
 GINEConv = _outside_hot_path("GINEConv")
 GCNConv = _outside_hot_path("GCNConv")
 ChebConv = _outside_hot_path("ChebConv")
-GATv2Conv = _outside_hot_path("GATv2Conv")
+
+
+class GATv2Conv(MessagePassing):
+    """PyG GATv2Conv(in, out, heads=1, concat=True, negative_slope=0.2, dropout=0., add_self_loops=True, edge_dim=None,
+    fill_value='mean', bias=True, share_weights=False), as used at reference networks.py:146:
+      lin_l, lin_r = Linear(in, H*C, bias=bias) (glorot weights, zero bias); att [1, H, C] glorot; lin_edge = Linear(edge_dim, H*C,
+      bias=False); bias [H*C] zeros.
+      forward: x_l = lin_l(x), x_r = lin_r(x); remove_self_loops + add_self_loops(fill_value) on (edge_index, edge_attr);
+      per edge (j -> i): s = x_r[i] + x_l[j] + lin_edge(a); alpha = softmax_i(sum_c att * leaky_relu(s, slope)); dropout(alpha);
+      out[i] = sum_j alpha_ij * x_l[j]; concat heads; + bias."""
+
+    def __init__(self, in_channels, out_channels, heads=1, concat=True, negative_slope=0.2, dropout=0.0, add_self_loops=True,
+                 edge_dim=None, fill_value="mean", bias=True, share_weights=False, **kwargs):
+        kwargs.setdefault("aggr", "add")
+        super().__init__(node_dim=0, **kwargs)
+        if share_weights:
+            raise NotImplementedError("shim: share_weights=False only")
+        self.in_channels, self.out_channels, self.heads, self.concat = in_channels, out_channels, heads, concat
+        self.negative_slope, self.dropout, self.add_self_loops_, self.edge_dim, self.fill_value = negative_slope, dropout, add_self_loops, edge_dim, fill_value
+        self.lin_l = nn.Linear(in_channels, heads * out_channels, bias=bias)
+        self.lin_r = nn.Linear(in_channels, heads * out_channels, bias=bias)
+        self.att = nn.Parameter(torch.empty(1, heads, out_channels))
+        self.lin_edge = nn.Linear(edge_dim, heads * out_channels, bias=False) if edge_dim is not None else None
+        if bias and concat:
+            self.bias = nn.Parameter(torch.empty(heads * out_channels))
+        elif bias:
+            self.bias = nn.Parameter(torch.empty(out_channels))
+        else:
+            self.register_parameter("bias", None)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        for lin in (self.lin_l, self.lin_r, self.lin_edge):
+            if lin is not None:
+                nn.init.xavier_uniform_(lin.weight)
+                if lin.bias is not None:
+                    nn.init.zeros_(lin.bias)
+        nn.init.xavier_uniform_(self.att)
+        if self.bias is not None:
+            nn.init.zeros_(self.bias)
+
+    def forward(self, x, edge_index, edge_attr=None):
+        H, C = self.heads, self.out_channels
+        x_l = self.lin_l(x).view(-1, H, C)
+        x_r = self.lin_r(x).view(-1, H, C)
+        if self.add_self_loops_:
+            n = x_l.size(0)
+            edge_index, edge_attr = remove_self_loops(edge_index, edge_attr)
+            edge_index, edge_attr = add_self_loops(edge_index, edge_attr, fill_value=self.fill_value, num_nodes=n)
+        src, dst = edge_index[0], edge_index[1]
+        s = x_r.index_select(0, dst) + x_l.index_select(0, src)
+        if edge_attr is not None:
+            if edge_attr.dim() == 1:
+                edge_attr = edge_attr.view(-1, 1)
+            s = s + self.lin_edge(edge_attr).view(-1, H, C)
+        s = torch.nn.functional.leaky_relu(s, self.negative_slope)
+        alpha = (s * self.att).sum(dim=-1)
+        alpha = softmax(alpha, dst, None, x_l.size(0))
+        alpha = torch.nn.functional.dropout(alpha, p=self.dropout, training=self.training)
+        out = scatter(x_l.index_select(0, src) * alpha.unsqueeze(-1), dst, dim=0, dim_size=x_l.size(0), reduce="sum")
+        out = out.view(-1, H * C) if self.concat else out.mean(dim=1)
+        if self.bias is not None:
+            out = out + self.bias
+        return out

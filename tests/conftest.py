@@ -77,3 +77,22 @@ def assert_fp32_parity(ours, ref32, ref64, what="", rtol=1e-5, noise_mult=4.0):
     tol = max(rtol * scale, noise_mult * noise)
     assert err <= tol + 1e-300, f"{what}: err {err:.3e} > tol {tol:.3e} (scale {scale:.3e}, ref32 noise {noise:.3e})"
     return err, tol
+
+
+def golden_gat(tag):
+    """GAT_DSSE golden file as (num_layers, state_dict, grads dict, raw npz)."""
+    z = load_golden(f"golden_model_{tag}.npz")
+    sd = {k[len("param."):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("param.")}
+    grads = {k[len("grad."):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("grad.")}
+    return int(z["num_layers"]), sd, grads, z
+
+
+def oracle_gat_run(orc, num_layers, sd, z, dtype):
+    """Oracle GAT_DSSE forward + WLS loss + autograd on the inputs of a golden file."""
+    x, ea, ei = torch.from_numpy(z["x"]).to(dtype), torch.from_numpy(z["edge_attr"]).to(dtype), torch.from_numpy(z["edge_index"])
+    st = [torch.from_numpy(z[k]).to(dtype) for k in ("x_mean", "x_std", "edge_mean", "edge_std")]
+    p = {k: v.to(dtype).clone().requires_grad_(True) for k, v in sd.items()}
+    out = orc.gat_dsse_forward(p, x[:, :8], ei, ea[:, :6], num_layers)
+    loss = orc.wls_loss(x, ea, out, *st, ei, REG_COEFS)
+    loss.backward()
+    return out.detach(), loss.detach(), {k: v.grad for k, v in p.items()}

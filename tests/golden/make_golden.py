@@ -119,6 +119,31 @@ def run_model(tag, kind, ctor, batch, stats, sd_seed, torch_seed, dtype=torch.fl
     print(tag, "out", tuple(out.shape), "loss", res.get("loss"), "masks", res["num_masks"])
 
 
+def run_gat(tag, batch, stats, sd_seed, num_layers=8):
+    """Reference GAT_DSSE (dss2_run.py:86 hyper-parameters) forward + gsp_wls_edge + backward on `batch`."""
+    sd = orc.init_gat_state_dict(num_layers=num_layers, seed=sd_seed)
+    model = ref_net.GAT_DSSE(dim_feat=8, dim_dense=32, dim_out=2, heads=1, num_layers=num_layers, edge_dim=6)
+    missing = model.load_state_dict(sd, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    model.train()
+    out = model(batch.x[:, :8], batch.edge_index, batch.edge_attr[:, :6])
+    res = {"x": batch.x.numpy(), "edge_index": batch.edge_index.numpy(), "edge_attr": batch.edge_attr.numpy(), "ptr": batch.ptr.numpy(),
+           "out": out.detach().numpy().copy(), "num_layers": num_layers, "sd_seed": sd_seed,
+           "x_mean": stats[0].numpy(), "x_std": stats[1].numpy(), "edge_mean": stats[2].numpy(), "edge_std": stats[3].numpy()}
+    got = {}
+    out.register_hook(lambda g_: got.__setitem__("g", g_.clone()))
+    loss = ref_loss(batch, out, stats)
+    loss.backward()
+    res["loss"] = np.array(loss.item())
+    res["out_after_loss"] = out.detach().numpy().copy()
+    res["grad_out"] = got["g"].numpy().copy()
+    for name, p in model.named_parameters():
+        res["grad." + name] = p.grad.detach().numpy().copy()
+        res["param." + name] = p.detach().numpy().copy()
+    np.savez_compressed(os.path.join(HERE, f"golden_model_{tag}.npz"), **res)
+    print(tag, "out", tuple(out.shape), "loss", res["loss"])
+
+
 def main():
     torch.set_num_threads(1)
     fix = np.load(os.path.join(HERE, "cigre14_scenarios.npz"), allow_pickle=False)
@@ -165,6 +190,8 @@ def main():
     run_model("mpn_cigre", "MPN", mpn, Batch.from_data_list(ds[30:35]), stats, sd_seed=3, torch_seed=13)
     run_model("skipmpn_cigre", "SkipMPN", skipmpn, Batch.from_data_list(ds[40:42]), stats, sd_seed=4, torch_seed=14)
 
+    run_gat("gat_cigre", Batch.from_data_list(ds[50:56]), stats, sd_seed=6)
+
     # ---- Oberrhein: synthetic scenarios from the product generator, reference model + loss on top ----
     grid = synth.load_grid("ober_sub")
     store = synth.synthetic_store(grid, 16, seed=1234)
@@ -172,6 +199,7 @@ def main():
     ob = Batch.from_data_list(graphs)
     ostats = (store.x_mean, store.x_std, store.edge_mean, store.edge_std)
     run_model("skippfn_ober", "SkipPFN", dict(default, n_gnn_layers=4, L=2), ob, ostats, sd_seed=5, torch_seed=15)
+    run_gat("gat_ober", ob, ostats, sd_seed=7)
     # a far-from-solution output so that all three soft-constraint penalties are active
     torch.manual_seed(99)
     wild = torch.stack([torch.randn(ob.x.shape[0]) * 3.0, torch.randn(ob.x.shape[0]) * 0.8], 1).requires_grad_(True)

@@ -131,3 +131,16 @@ def test_model_forward_backward_vs_reference(tag):
         assert_fp32_parity(loss32, z["loss"], loss64, "loss")
     for name, g in grads.items():
         assert_fp32_parity(g32[name], g, g64[name], name)
+
+
+@pytest.mark.parametrize("tag", ["gat_cigre", "gat_ober"])
+def test_gat_dsse_forward_backward_vs_reference(tag):
+    """Oracle GAT_DSSE (7 GATv2 layers + 2 Linear) + loss + autograd == the reference's GAT_DSSE run over the shim (same weights)."""
+    from conftest import golden_gat, oracle_gat_run
+    nl, sd, grads, z = golden_gat(tag)
+    out32, loss32, g32 = oracle_gat_run(orc, nl, sd, z, torch.float32)
+    out64, loss64, g64 = oracle_gat_run(orc, nl, sd, z, torch.float64)
+    assert_fp32_parity(out32, z["out"], out64, "out")
+    assert_fp32_parity(loss32, z["loss"], loss64, "loss")
+    for name, g in grads.items():
+        assert_fp32_parity(g32[name], g, g64[name], name)
