@@ -1,0 +1,621 @@
+// (f-1) GAT_DSSE: fused GATv2 layer (+ LeakyReLU) forward / backward and the two-Linear head.
+// Replaces networks.py:113-156 (PyG GATv2Conv(8, 8, heads=1, edge_dim=6, add_self_loops=True, fill_value='mean') x 7, each followed by
+// LeakyReLU(0.01), then Linear(8,32), Linear(32,2)) and its autograd.
+//
+// The script hands the ONE-WAY edge list to the model (networks.py:155-156 does not undirect).  The kernels walk the doubled-graph CSR
+// the other layers use: in row i the entries WITHOUT the reversed bit are the edges pointing at i (in edge order = PyG's scatter
+// order), the entries WITH it are the edges leaving i.  One thread owns one bus: channels are 8 wide, everything lives in registers,
+// the 208 layer parameters sit in shared memory.  PyG's attention per edge (j -> i), restated:
+//     x_l = W_l x + b_l, x_r = W_r x + b_r;  s = x_r[i] + x_l[j] + W_e a_e;  score = att . leaky_relu(s, 0.2)
+//     alpha = exp(score - max_i) / (sum_i exp(.) + 1e-16);  out[i] = sum_j alpha_ij x_l[j] + bias
+// with input self loops dropped and one loop per bus appended LAST whose attribute is the mean of the attributes of the edges pointing
+// at the bus (0 without any).  No per-edge tensor reaches HBM; the backward recomputes the edge terms (pass A: per-destination softmax
+// statistics, pass B: adjoints gathered per bus from its in- and out-edges: no atomics), weight gradients of the two node-level
+// Linears come from one outer-product reduction over the stored node adjoints.
+#include "common.cuh"
+
+namespace {
+
+constexpr int GC = 8;       // channels = dim_feat (heads = 1)
+constexpr int GFE = 8;      // edge_dim <= 8
+constexpr int GAT_THREADS = 128;
+constexpr int GAT_NODE_WS = 36;   // floats per bus of backward scratch: m, den, t, pad, g[8], x_r[8], d x_l[8], d x_r[8]
+
+struct GatW {
+  float wl[GC * GC], bl[GC], wr[GC * GC], br[GC], we[GC * GFE], att[GC], bias[GC];
+};
+
+struct GatArgs {
+  dss2_graph_t g;
+  const float* x;
+  int64_t xs;
+  const float* ea;
+  int64_t eas;
+  int fe;
+  const float *wl, *bl, *wr, *br, *we, *att, *bias;
+  float slope_att, slope_act;
+  int act;
+  float* y;           // fwd
+  const float* yout;  // bwd: the layer's output (activation gate)
+  const float* gy;
+  float* ws;          // [Nt][GAT_NODE_WS]
+  float* gx;
+  float* partials;
+  int64_t partial_stride;
+};
+
+__device__ __forceinline__ void load_weights(GatW& w, const GatArgs& a) {
+  for (int i = threadIdx.x; i < GC * GC; i += blockDim.x) {
+    w.wl[i] = a.wl[i];
+    w.wr[i] = a.wr[i];
+  }
+  for (int i = threadIdx.x; i < GC * GFE; i += blockDim.x) {
+    const int c = i / GFE, f = i % GFE;
+    w.we[i] = f < a.fe ? a.we[c * a.fe + f] : 0.0f;
+  }
+  if (threadIdx.x < GC) {
+    w.bl[threadIdx.x] = a.bl[threadIdx.x];
+    w.br[threadIdx.x] = a.br[threadIdx.x];
+    w.att[threadIdx.x] = a.att[threadIdx.x];
+    w.bias[threadIdx.x] = a.bias[threadIdx.x];
+  }
+}
+
+__device__ __forceinline__ void load_x(const GatArgs& a, int64_t n, float (&v)[GC]) {
+  const float* p = a.x + n * a.xs;
+#pragma unroll
+  for (int i = 0; i < GC; ++i) v[i] = p[i];
+}
+__device__ __forceinline__ void load_attr(const GatArgs& a, int64_t e, float (&v)[GFE]) {
+  const float* p = a.ea + e * a.eas;
+#pragma unroll
+  for (int i = 0; i < GFE; ++i) v[i] = i < a.fe ? p[i] : 0.0f;
+}
+// out = W v + b, W row-major [8][8] in shared memory
+__device__ __forceinline__ void lin8(const float* W, const float* b, const float (&v)[GC], float (&out)[GC]) {
+#pragma unroll
+  for (int c = 0; c < GC; ++c) {
+    float s = b[c];
+#pragma unroll
+    for (int i = 0; i < GC; ++i) s = fmaf(W[c * GC + i], v[i], s);
+    out[c] = s;
+  }
+}
+// s = x_r + x_l + W_e a
+__device__ __forceinline__ void edge_pre(const GatW& w, const float (&xr)[GC], const float (&xl)[GC], const float (&at)[GFE], float (&s)[GC]) {
+#pragma unroll
+  for (int c = 0; c < GC; ++c) {
+    float e = 0.0f;
+#pragma unroll
+    for (int f = 0; f < GFE; ++f) e = fmaf(w.we[c * GFE + f], at[f], e);
+    s[c] = (xr[c] + xl[c]) + e;
+  }
+}
+__device__ __forceinline__ float edge_score(const GatW& w, const float (&s)[GC], float slope) {
+  float sc = 0.0f;
+#pragma unroll
+  for (int c = 0; c < GC; ++c) sc = fmaf(s[c] > 0.0f ? s[c] : s[c] * slope, w.att[c], sc);
+  return sc;
+}
+
+// Per-destination softmax statistics of bus i: max score m, denominator den (incl. PyG's 1e-16), un-normalised weighted sum acc of
+// x_l over the in-edges and the loop, mean in-attribute abar.  `G` (optional) additionally gives t = sum_k alpha_k (G . x_l[k]).
+struct DstStats {
+  float m, den, t;
+};
+template <bool WITH_T>
+__device__ __forceinline__ DstStats dst_pass(const GatArgs& a, const GatW& w, int64_t i, const float (&xr)[GC], const float (&xl_i)[GC],
+                                             float (&abar)[GFE], float (&acc)[GC], const float (&G)[GC]) {
+  const dss2_graph_t& g = a.g;
+  const int beg = g.rowptr[i], end = g.rowptr[i + 1];
+  float m = -INFINITY;
+  int cnt = 0;
+#pragma unroll
+  for (int f = 0; f < GFE; ++f) abar[f] = 0.0f;
+  for (int z = beg; z < end; ++z) {
+    const uint32_t id = g.eid[z];
+    const int j = g.col[z];
+    if ((id >> 31) || j == i) continue;
+    float xj[GC], xl[GC], at[GFE], s[GC];
+    load_x(a, j, xj);
+    lin8(w.wl, w.bl, xj, xl);
+    load_attr(a, id, at);
+#pragma unroll
+    for (int f = 0; f < GFE; ++f) abar[f] += at[f];
+    ++cnt;
+    edge_pre(w, xr, xl, at, s);
+    m = fmaxf(m, edge_score(w, s, a.slope_att));
+  }
+  if (cnt > 0) {
+    const float c = (float)cnt;
+#pragma unroll
+    for (int f = 0; f < GFE; ++f) abar[f] = abar[f] / c;
+  }
+  float s_loop[GC];
+  edge_pre(w, xr, xl_i, abar, s_loop);
+  const float sc_loop = edge_score(w, s_loop, a.slope_att);
+  m = fmaxf(m, sc_loop);
+  float den = 0.0f, t = 0.0f;
+#pragma unroll
+  for (int c = 0; c < GC; ++c) acc[c] = 0.0f;
+  for (int z = beg; z < end; ++z) {
+    const uint32_t id = g.eid[z];
+    const int j = g.col[z];
+    if ((id >> 31) || j == i) continue;
+    float xj[GC], xl[GC], at[GFE], s[GC];
+    load_x(a, j, xj);
+    lin8(w.wl, w.bl, xj, xl);
+    load_attr(a, id, at);
+    edge_pre(w, xr, xl, at, s);
+    const float ex = expf(edge_score(w, s, a.slope_att) - m);
+    den += ex;
+    float dot = 0.0f;
+#pragma unroll
+    for (int c = 0; c < GC; ++c) {
+      acc[c] = fmaf(ex, xl[c], acc[c]);
+      if (WITH_T) dot = fmaf(G[c], xl[c], dot);
+    }
+    if (WITH_T) t = fmaf(ex, dot, t);
+  }
+  {
+    const float ex = expf(sc_loop - m);
+    den += ex;
+    float dot = 0.0f;
+#pragma unroll
+    for (int c = 0; c < GC; ++c) {
+      acc[c] = fmaf(ex, xl_i[c], acc[c]);
+      if (WITH_T) dot = fmaf(G[c], xl_i[c], dot);
+    }
+    if (WITH_T) t = fmaf(ex, dot, t);
+  }
+  den += 1e-16f;
+  DstStats r;
+  r.m = m;
+  r.den = den;
+  r.t = t / den;
+  return r;
+}
+
+__global__ void __launch_bounds__(GAT_THREADS) k_gat_fwd(GatArgs a) {
+  __shared__ GatW w;
+  load_weights(w, a);
+  __syncthreads();
+  const float zero[GC] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.g.num_nodes; i += (int64_t)gridDim.x * blockDim.x) {
+    float xi[GC], xr[GC], xl[GC], abar[GFE], acc[GC];
+    load_x(a, i, xi);
+    lin8(w.wr, w.br, xi, xr);
+    lin8(w.wl, w.bl, xi, xl);
+    const DstStats st = dst_pass<false>(a, w, i, xr, xl, abar, acc, zero);
+    float out[GC];
+#pragma unroll
+    for (int c = 0; c < GC; ++c) {
+      const float v = acc[c] / st.den + w.bias[c];
+      out[c] = (a.act && !(v > 0.0f)) ? v * a.slope_act : v;
+    }
+    float4* dst = reinterpret_cast<float4*>(a.y + i * GC);
+    dst[0] = make_float4(out[0], out[1], out[2], out[3]);
+    dst[1] = make_float4(out[4], out[5], out[6], out[7]);
+  }
+}
+
+// backward pass A: per bus g = grad_y * gate, x_r, softmax statistics (m, den, t)
+__global__ void __launch_bounds__(GAT_THREADS) k_gat_bwd_stats(GatArgs a) {
+  __shared__ GatW w;
+  load_weights(w, a);
+  __syncthreads();
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.g.num_nodes; i += (int64_t)gridDim.x * blockDim.x) {
+    float xi[GC], xr[GC], xl[GC], abar[GFE], acc[GC], G[GC];
+    load_x(a, i, xi);
+    lin8(w.wr, w.br, xi, xr);
+    lin8(w.wl, w.bl, xi, xl);
+#pragma unroll
+    for (int c = 0; c < GC; ++c) {
+      const float gate = (a.act && !(a.yout[i * GC + c] > 0.0f)) ? a.slope_act : 1.0f;
+      G[c] = a.gy[i * GC + c] * gate;
+    }
+    const DstStats st = dst_pass<true>(a, w, i, xr, xl, abar, acc, G);
+    float* o = a.ws + i * GAT_NODE_WS;
+    o[0] = st.m;
+    o[1] = st.den;
+    o[2] = st.t;
+#pragma unroll
+    for (int c = 0; c < GC; ++c) {
+      o[4 + c] = G[c];
+      o[12 + c] = xr[c];
+    }
+  }
+}
+
+// adjoint of one edge (j -> i) given the destination's statistics: returns alpha, fills ds = d loss / d s, adds to d att
+__device__ __forceinline__ float edge_adjoint(const GatArgs& a, const GatW& w, const float (&s)[GC], float m, float den, float t,
+                                              const float (&Gi)[GC], const float (&xl_j)[GC], float (&ds)[GC], float* datt) {
+  const float alpha = expf(edge_score(w, s, a.slope_att) - m) / den;
+  float dal = 0.0f;
+#pragma unroll
+  for (int c = 0; c < GC; ++c) dal = fmaf(Gi[c], xl_j[c], dal);
+  const float dsc = alpha * (dal - t);
+#pragma unroll
+  for (int c = 0; c < GC; ++c) {
+    const bool pos = s[c] > 0.0f;
+    ds[c] = dsc * w.att[c] * (pos ? 1.0f : a.slope_att);
+    if (datt) datt[c] = fmaf(dsc, pos ? s[c] : s[c] * a.slope_att, datt[c]);
+  }
+  return alpha;
+}
+
+// backward pass B: thread = bus n.  As destination it owns d x_r[n], d W_e, d att of its in-edges and loop; as source it gathers d x_l[n]
+// from its out-edges.  partial layout per CTA: [W_e 8 x fe | att 8 | bias 8] at the offsets the host passes via partials pointer.
+__global__ void __launch_bounds__(GAT_THREADS) k_gat_bwd(GatArgs a) {
+  __shared__ GatW w;
+  __shared__ float red[GAT_THREADS / 32][GC * GFE + 2 * GC];
+  load_weights(w, a);
+  __syncthreads();
+  const dss2_graph_t& g = a.g;
+  float dWe[GC * GFE], datt[GC], dbias[GC];
+#pragma unroll
+  for (int i = 0; i < GC * GFE; ++i) dWe[i] = 0.0f;
+#pragma unroll
+  for (int c = 0; c < GC; ++c) datt[c] = dbias[c] = 0.0f;
+  for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < g.num_nodes; n += (int64_t)gridDim.x * blockDim.x) {
+    float xn[GC], xl_n[GC], dxl[GC], dxr[GC];
+    load_x(a, n, xn);
+    lin8(w.wl, w.bl, xn, xl_n);
+#pragma unroll
+    for (int c = 0; c < GC; ++c) dxl[c] = dxr[c] = 0.0f;
+    const float* sn = a.ws + n * GAT_NODE_WS;
+    const float m_n = sn[0], den_n = sn[1], t_n = sn[2];
+    float Gn[GC], xr_n[GC];
+#pragma unroll
+    for (int c = 0; c < GC; ++c) {
+      Gn[c] = sn[4 + c];
+      xr_n[c] = sn[12 + c];
+      dbias[c] += Gn[c];
+    }
+    const int beg = g.rowptr[n], end = g.rowptr[n + 1];
+    float abar[GFE];
+    int cnt = 0;
+#pragma unroll
+    for (int f = 0; f < GFE; ++f) abar[f] = 0.0f;
+    for (int z = beg; z < end; ++z) {
+      const uint32_t id = g.eid[z];
+      const int o = g.col[z];
+      if (o == n) continue;   // self loops of the input are dropped (remove_self_loops)
+      float at[GFE], s[GC], ds[GC];
+      load_attr(a, id & 0x7fffffffu, at);
+      if (!(id >> 31)) {      // in-edge (o -> n): this bus is the destination
+        float xo[GC], xl_o[GC];
+        load_x(a, o, xo);
+        lin8(w.wl, w.bl, xo, xl_o);
+#pragma unroll
+        for (int f = 0; f < GFE; ++f) abar[f] += at[f];
+        ++cnt;
+        edge_pre(w, xr_n, xl_o, at, s);
+        edge_adjoint(a, w, s, m_n, den_n, t_n, Gn, xl_o, ds, datt);
+#pragma unroll
+        for (int c = 0; c < GC; ++c) {
+          dxr[c] += ds[c];
+#pragma unroll
+          for (int f = 0; f < GFE; ++f) dWe[c * GFE + f] = fmaf(ds[c], at[f], dWe[c * GFE + f]);
+        }
+      } else {                // out-edge (n -> o): this bus is the source
+        const float* so = a.ws + (int64_t)o * GAT_NODE_WS;
+        float Go[GC], xr_o[GC];
+#pragma unroll
+        for (int c = 0; c < GC; ++c) {
+          Go[c] = so[4 + c];
+          xr_o[c] = so[12 + c];
+        }
+        edge_pre(w, xr_o, xl_n, at, s);
+        const float alpha = edge_adjoint(a, w, s, so[0], so[1], so[2], Go, xl_n, ds, nullptr);
+#pragma unroll
+        for (int c = 0; c < GC; ++c) dxl[c] += fmaf(alpha, Go[c], ds[c]);
+      }
+    }
+    {   // the appended self loop (n -> n) with the mean in-attribute
+      if (cnt > 0) {
+        const float c = (float)cnt;
+#pragma unroll
+        for (int f = 0; f < GFE; ++f) abar[f] = abar[f] / c;
+      }
+      float s[GC], ds[GC];
+      edge_pre(w, xr_n, xl_n, abar, s);
+      const float alpha = edge_adjoint(a, w, s, m_n, den_n, t_n, Gn, xl_n, ds, datt);
+#pragma unroll
+      for (int c = 0; c < GC; ++c) {
+        dxr[c] += ds[c];
+        dxl[c] += fmaf(alpha, Gn[c], ds[c]);
+#pragma unroll
+        for (int f = 0; f < GFE; ++f) dWe[c * GFE + f] = fmaf(ds[c], abar[f], dWe[c * GFE + f]);
+      }
+    }
+    float* o = a.ws + n * GAT_NODE_WS;
+#pragma unroll
+    for (int c = 0; c < GC; ++c) {
+      o[20 + c] = dxl[c];
+      o[28 + c] = dxr[c];
+    }
+    if (a.gx) {   // grad_x = W_l^T d x_l + W_r^T d x_r
+      float gx[GC];
+#pragma unroll
+      for (int i = 0; i < GC; ++i) {
+        float s = 0.0f;
+#pragma unroll
+        for (int c = 0; c < GC; ++c) s = fmaf(w.wl[c * GC + i], dxl[c], fmaf(w.wr[c * GC + i], dxr[c], s));
+        gx[i] = s;
+      }
+      float4* dst = reinterpret_cast<float4*>(a.gx + n * GC);
+      dst[0] = make_float4(gx[0], gx[1], gx[2], gx[3]);
+      dst[1] = make_float4(gx[4], gx[5], gx[6], gx[7]);
+    }
+  }
+  // per-CTA partial: warp sums -> shared memory -> fixed-order sum over the warps
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < GC * GFE; ++i) {
+    const float v = warp_sum(dWe[i]);
+    if (lane == 0) red[warp][i] = v;
+  }
+#pragma unroll
+  for (int c = 0; c < GC; ++c) {
+    const float v1 = warp_sum(datt[c]), v2 = warp_sum(dbias[c]);
+    if (lane == 0) {
+      red[warp][GC * GFE + c] = v1;
+      red[warp][GC * GFE + GC + c] = v2;
+    }
+  }
+  __syncthreads();
+  float* part = a.partials + (size_t)blockIdx.x * a.partial_stride;
+  for (int i = threadIdx.x; i < GC * a.fe + 2 * GC; i += blockDim.x) {
+    int src;
+    if (i < GC * a.fe) src = (i / a.fe) * GFE + (i % a.fe);
+    else src = GC * GFE + (i - GC * a.fe);
+    float s = 0.0f;
+#pragma unroll
+    for (int wv = 0; wv < GAT_THREADS / 32; ++wv) s += red[wv][src];
+    part[i] = s;
+  }
+}
+
+// out_w[c][i] = sum_n A[n][c] * B[n][i], out_b[c] = sum_n A[n][c]: per-CTA partial sums of the weight / bias gradient of a node-level
+// Linear (A = adjoint of its output, B = its input), rows split contiguously over the CTAs, 64-row chunks staged in shared memory.
+constexpr int OR_THREADS = 256, OR_ROWS = 64;
+__global__ void __launch_bounds__(OR_THREADS) k_outer_reduce(int64_t num_rows, const float* __restrict__ A, int64_t as, int ca,
+                                                             const float* __restrict__ B, int64_t bs, int cb, float* partials,
+                                                             int64_t partial_stride, int64_t w_off, int64_t b_off) {
+  __shared__ float sA[OR_ROWS][33], sB[OR_ROWS][33];
+  const int tid = threadIdx.x;
+  const int nout = ca * (cb + 1);
+  float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};   // ca, cb <= 32 -> at most 1056 outputs over 256 threads
+  const int64_t per = (num_rows + gridDim.x - 1) / gridDim.x;
+  const int64_t r0 = blockIdx.x * per, r1 = min(num_rows, r0 + per);
+  for (int64_t base = r0; base < r1; base += OR_ROWS) {
+    const int rows = (int)min((int64_t)OR_ROWS, r1 - base);
+    for (int idx = tid; idx < rows * ca; idx += OR_THREADS) sA[idx / ca][idx % ca] = A[(base + idx / ca) * as + idx % ca];
+    for (int idx = tid; idx < rows * cb; idx += OR_THREADS) sB[idx / cb][idx % cb] = B[(base + idx / cb) * bs + idx % cb];
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+      const int o = tid + q * OR_THREADS;
+      if (o < nout) {
+        const int c = o / (cb + 1), i = o % (cb + 1);
+        float s = acc[q];
+        if (i < cb) {
+          for (int r = 0; r < rows; ++r) s = fmaf(sA[r][c], sB[r][i], s);
+        } else {
+          for (int r = 0; r < rows; ++r) s += sA[r][c];
+        }
+        acc[q] = s;
+      }
+    }
+    __syncthreads();
+  }
+  float* part = partials + (size_t)blockIdx.x * partial_stride;
+#pragma unroll
+  for (int q = 0; q < 5; ++q) {
+    const int o = tid + q * OR_THREADS;
+    if (o < nout) {
+      const int c = o / (cb + 1), i = o % (cb + 1);
+      if (i < cb) part[w_off + (int64_t)c * cb + i] = acc[q];
+      else part[b_off + c] = acc[q];
+    }
+  }
+}
+
+// ---- head: z = W2 (W1 x + b1) + b2 (no non-linearity in between, networks.py:150-151) ----
+constexpr int MLP_MAX = 32;
+struct MlpArgs {
+  int64_t n;
+  const float* x;
+  int din;
+  const float *w1, *b1;
+  int dmid;
+  const float *w2, *b2;
+  int dout;
+  float* h;          // [n, dmid]
+  float* z;          // [n, dout]
+  const float* gz;   // bwd
+  float* gh;         // [n, dmid]
+  float* gx;         // [n, din]
+};
+__global__ void __launch_bounds__(128) k_mlp2_fwd(MlpArgs a) {
+  __shared__ float w1[MLP_MAX * MLP_MAX], w2[MLP_MAX * MLP_MAX], b1[MLP_MAX], b2[MLP_MAX];
+  for (int i = threadIdx.x; i < a.dmid * a.din; i += blockDim.x) w1[i] = a.w1[i];
+  for (int i = threadIdx.x; i < a.dout * a.dmid; i += blockDim.x) w2[i] = a.w2[i];
+  if (threadIdx.x < a.dmid) b1[threadIdx.x] = a.b1[threadIdx.x];
+  if (threadIdx.x < a.dout) b2[threadIdx.x] = a.b2[threadIdx.x];
+  __syncthreads();
+  for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < a.n; n += (int64_t)gridDim.x * blockDim.x) {
+    float x[MLP_MAX], z[8];
+    for (int i = 0; i < a.din; ++i) x[i] = a.x[n * a.din + i];
+    for (int o = 0; o < a.dout; ++o) z[o] = b2[o];
+    for (int c = 0; c < a.dmid; ++c) {
+      float h = b1[c];
+      for (int i = 0; i < a.din; ++i) h = fmaf(w1[c * a.din + i], x[i], h);
+      a.h[n * a.dmid + c] = h;
+      for (int o = 0; o < a.dout; ++o) z[o] = fmaf(w2[o * a.dmid + c], h, z[o]);
+    }
+    for (int o = 0; o < a.dout; ++o) a.z[n * a.dout + o] = z[o];
+  }
+}
+__global__ void __launch_bounds__(128) k_mlp2_bwd(MlpArgs a) {
+  __shared__ float w1[MLP_MAX * MLP_MAX], w2[MLP_MAX * MLP_MAX];
+  for (int i = threadIdx.x; i < a.dmid * a.din; i += blockDim.x) w1[i] = a.w1[i];
+  for (int i = threadIdx.x; i < a.dout * a.dmid; i += blockDim.x) w2[i] = a.w2[i];
+  __syncthreads();
+  for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < a.n; n += (int64_t)gridDim.x * blockDim.x) {
+    float gz[8], gx[MLP_MAX];
+    for (int o = 0; o < a.dout; ++o) gz[o] = a.gz[n * a.dout + o];
+    for (int i = 0; i < a.din; ++i) gx[i] = 0.0f;
+    for (int c = 0; c < a.dmid; ++c) {
+      float gh = 0.0f;
+      for (int o = 0; o < a.dout; ++o) gh = fmaf(w2[o * a.dmid + c], gz[o], gh);
+      a.gh[n * a.dmid + c] = gh;
+      for (int i = 0; i < a.din; ++i) gx[i] = fmaf(w1[c * a.din + i], gh, gx[i]);
+    }
+    for (int i = 0; i < a.din; ++i) a.gx[n * a.din + i] = gx[i];
+  }
+}
+
+int grid_for(int64_t n, int threads) { return (int)max((int64_t)1, min((int64_t)dss2_sm_count() * 8, (n + threads - 1) / threads)); }
+
+int fill_args(const char* who, GatArgs& a, const dss2_graph_t* g, const float* x, int64_t xs, const float* ea, int64_t eas, int fe,
+              const float* wl, const float* bl, const float* wr, const float* br, const float* we, const float* att, const float* bias,
+              float slope_att, int act, float slope_act) {
+  DSS2_CHECK_ARG(g && x && ea && wl && bl && wr && br && we && att && bias, "%s: null argument", who);
+  DSS2_CHECK_ARG(fe >= 1 && fe <= GFE, "%s: edge_dim %d outside 1..%d", who, fe, GFE);
+  DSS2_CHECK_ARG(xs >= GC && eas >= fe, "%s: row strides too small", who);
+  a.g = *g;
+  a.x = x;
+  a.xs = xs;
+  a.ea = ea;
+  a.eas = eas;
+  a.fe = fe;
+  a.wl = wl;
+  a.bl = bl;
+  a.wr = wr;
+  a.br = br;
+  a.we = we;
+  a.att = att;
+  a.bias = bias;
+  a.slope_att = slope_att;
+  a.act = act;
+  a.slope_act = slope_act;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" size_t dss2_gat_ws_bytes(int64_t num_nodes) { return (size_t)num_nodes * GAT_NODE_WS * sizeof(float); }
+
+extern "C" int dss2_gat_fwd(const dss2_graph_t* g, const float* x, int64_t x_stride, const float* edge_attr, int64_t ea_stride, int fe,
+                            const float* lin_l_w, const float* lin_l_b, const float* lin_r_w, const float* lin_r_b,
+                            const float* lin_edge_w, const float* att, const float* bias, float att_slope, int act, float act_slope,
+                            float* y, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GatArgs a = {};
+  if (fill_args("dss2_gat_fwd", a, g, x, x_stride, edge_attr, ea_stride, fe, lin_l_w, lin_l_b, lin_r_w, lin_r_b, lin_edge_w, att, bias,
+                att_slope, act, act_slope))
+    return -1;
+  DSS2_CHECK_ARG(y && ((uintptr_t)y & 15) == 0, "dss2_gat_fwd: y must be a 16-byte aligned [Nt, 8] buffer");
+  if (g->num_nodes == 0) return 0;
+  a.y = y;
+  k_gat_fwd<<<grid_for(g->num_nodes, GAT_THREADS), GAT_THREADS, 0, stream>>>(a);
+  DSS2_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int dss2_gat_bwd(const dss2_graph_t* g, const float* x, int64_t x_stride, const float* edge_attr, int64_t ea_stride, int fe,
+                            const float* lin_l_w, const float* lin_l_b, const float* lin_r_w, const float* lin_r_b,
+                            const float* lin_edge_w, const float* att, const float* bias, float att_slope, int act, float act_slope,
+                            const float* y, const float* grad_y, float* grad_x, float* node_ws, size_t node_ws_bytes, float* partials,
+                            int64_t partial_stride, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GatArgs a = {};
+  if (fill_args("dss2_gat_bwd", a, g, x, x_stride, edge_attr, ea_stride, fe, lin_l_w, lin_l_b, lin_r_w, lin_r_b, lin_edge_w, att, bias,
+                att_slope, act, act_slope))
+    return -1;
+  DSS2_CHECK_ARG(grad_y && node_ws && partials && (!act || y), "dss2_gat_bwd: null argument");
+  DSS2_CHECK_ARG(g->undirected == 1, "dss2_gat_bwd: needs a graph built from the one-way edge list with undirect=1 (out-edges of a bus are "
+                 "found through the reversed entries)");
+  DSS2_CHECK_ARG(node_ws_bytes >= dss2_gat_ws_bytes(g->num_nodes), "dss2_gat_bwd: node workspace too small");
+  DSS2_CHECK_ARG(partial_stride >= 2 * (GC * GC + GC) + GC * fe + 2 * GC, "dss2_gat_bwd: partial_stride too small");
+  DSS2_CHECK_ARG(!grad_x || ((uintptr_t)grad_x & 15) == 0, "dss2_gat_bwd: grad_x must be 16-byte aligned");
+  if (g->num_nodes == 0) return 0;
+  a.yout = y;
+  a.gy = grad_y;
+  a.ws = node_ws;
+  a.gx = grad_x;
+  k_gat_bwd_stats<<<grid_for(g->num_nodes, GAT_THREADS), GAT_THREADS, 0, stream>>>(a);
+  DSS2_LAUNCH_CHECK();
+  // partial row: [lin_l.w 64 | lin_l.b 8 | lin_r.w 64 | lin_r.b 8 | lin_edge.w 8 fe | att 8 | bias 8]
+  const int np = dss2_num_partials();
+  a.partials = partials + 2 * (GC * GC + GC);
+  a.partial_stride = partial_stride;
+  k_gat_bwd<<<np, GAT_THREADS, 0, stream>>>(a);
+  DSS2_LAUNCH_CHECK();
+  // d W_l | d b_l and d W_r | d b_r from the stored node adjoints (columns 20..27 and 28..35 of the workspace)
+  k_outer_reduce<<<np, OR_THREADS, 0, stream>>>(g->num_nodes, node_ws + 20, GAT_NODE_WS, GC, x, x_stride, GC, partials, partial_stride, 0,
+                                                GC * GC);
+  DSS2_LAUNCH_CHECK();
+  k_outer_reduce<<<np, OR_THREADS, 0, stream>>>(g->num_nodes, node_ws + 28, GAT_NODE_WS, GC, x, x_stride, GC, partials, partial_stride,
+                                                GC * GC + GC, 2 * GC * GC + GC);
+  DSS2_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int dss2_mlp2_fwd(int64_t num_nodes, const float* x, int din, const float* w1, const float* b1, int dmid, const float* w2,
+                             const float* b2, int dout, float* h, float* z, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DSS2_CHECK_ARG(x && w1 && b1 && w2 && b2 && h && z, "dss2_mlp2_fwd: null argument");
+  DSS2_CHECK_ARG(din >= 1 && din <= MLP_MAX && dmid >= 1 && dmid <= MLP_MAX && dout >= 1 && dout <= 8, "dss2_mlp2_fwd: sizes %d -> %d -> %d unsupported",
+                 din, dmid, dout);
+  if (num_nodes == 0) return 0;
+  MlpArgs a = {};
+  a.n = num_nodes;
+  a.x = x;
+  a.din = din;
+  a.w1 = w1;
+  a.b1 = b1;
+  a.dmid = dmid;
+  a.w2 = w2;
+  a.b2 = b2;
+  a.dout = dout;
+  a.h = h;
+  a.z = z;
+  k_mlp2_fwd<<<grid_for(num_nodes, 128), 128, 0, stream>>>(a);
+  DSS2_LAUNCH_CHECK();
+  return 0;
+}
+
+// partial row layout: [w1 dmid x din | b1 dmid | w2 dout x dmid | b2 dout]
+extern "C" int dss2_mlp2_bwd(int64_t num_nodes, const float* x, int din, const float* w1, int dmid, const float* w2, int dout,
+                             const float* h, const float* grad_z, float* grad_h_ws, float* grad_x, float* partials, int64_t partial_stride,
+                             void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DSS2_CHECK_ARG(x && w1 && w2 && h && grad_z && grad_h_ws && grad_x && partials, "dss2_mlp2_bwd: null argument");
+  DSS2_CHECK_ARG(din >= 1 && din <= MLP_MAX && dmid >= 1 && dmid <= MLP_MAX && dout >= 1 && dout <= 8, "dss2_mlp2_bwd: sizes %d -> %d -> %d unsupported",
+                 din, dmid, dout);
+  DSS2_CHECK_ARG(partial_stride >= (int64_t)dmid * din + dmid + dout * dmid + dout, "dss2_mlp2_bwd: partial_stride too small");
+  if (num_nodes == 0) return 0;
+  MlpArgs a = {};
+  a.n = num_nodes;
+  a.x = x;
+  a.din = din;
+  a.w1 = w1;
+  a.dmid = dmid;
+  a.w2 = w2;
+  a.dout = dout;
+  a.gz = grad_z;
+  a.gh = grad_h_ws;
+  a.gx = grad_x;
+  k_mlp2_bwd<<<grid_for(num_nodes, 128), 128, 0, stream>>>(a);
+  DSS2_LAUNCH_CHECK();
+  const int np = dss2_num_partials();
+  const int64_t o_w1 = 0, o_b1 = (int64_t)dmid * din, o_w2 = o_b1 + dmid, o_b2 = o_w2 + (int64_t)dout * dmid;
+  k_outer_reduce<<<np, OR_THREADS, 0, stream>>>(num_nodes, grad_h_ws, dmid, dmid, x, din, din, partials, partial_stride, o_w1, o_b1);
+  DSS2_LAUNCH_CHECK();
+  k_outer_reduce<<<np, OR_THREADS, 0, stream>>>(num_nodes, grad_z, dout, dout, h, dmid, dmid, partials, partial_stride, o_w2, o_b2);
+  DSS2_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,191 @@
+"""Host side of GAT_DSSE (reference networks.py:113-156): architecture spec, flat parameter layout in the
+reference's state_dict names (`model.module_{i}.*`, PyG `nn.Sequential` naming), kernel launch sequence, autograd bridge.
+
+7 x [GATv2Conv(8, 8, heads=1, edge_dim) + LeakyReLU(0.01)] -> Linear(8, dim_dense) -> Linear(dim_dense, dim_out).
+All arithmetic is in csrc/gat.cu; there is no CPU fallback."""
+import ctypes
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+from .ops import ParamPack, _align4, require_cuda, resolve_graph, stage_rows
+
+GAT_C = 8   # channels the kernels are built for (dim_feat of dss2_run.py:73)
+
+
+@dataclass(frozen=True)
+class GATSpec:
+    dim_feat: int
+    dim_dense: int
+    dim_out: int
+    num_layers: int       # the reference builds num_layers - 1 GATv2 layers (networks.py:144)
+    edge_dim: int
+    att_slope: float = 0.2
+    act_slope: float = 0.01   # torch.nn.LeakyReLU() default (networks.py:137)
+
+    @property
+    def n_conv(self):
+        return self.num_layers - 1
+
+    def param_names(self):
+        """Reference parameter names (named_parameters() order of PyG's modules) with their shapes."""
+        out = []
+        for l in range(self.n_conv):
+            p = f"model.module_{2 * l}."
+            out += [(p + "att", (1, 1, self.dim_feat)), (p + "bias", (self.dim_feat,)),
+                    (p + "lin_l.weight", (self.dim_feat, self.dim_feat)), (p + "lin_l.bias", (self.dim_feat,)),
+                    (p + "lin_r.weight", (self.dim_feat, self.dim_feat)), (p + "lin_r.bias", (self.dim_feat,)),
+                    (p + "lin_edge.weight", (self.dim_feat, self.edge_dim))]
+        i = 2 * self.n_conv
+        out += [(f"model.module_{i}.weight", (self.dim_dense, self.dim_feat)), (f"model.module_{i}.bias", (self.dim_dense,)),
+                (f"model.module_{i + 1}.weight", (self.dim_out, self.dim_dense)), (f"model.module_{i + 1}.bias", (self.dim_out,))]
+        return out
+
+    def layout(self):
+        """name -> (offset, numel) in the flat fp32 buffer.  Per GATv2 layer the tensors sit in the order of the kernel's partial
+        gradient row [lin_l.w | lin_l.b | lin_r.w | lin_r.b | lin_edge.w | att | bias] (all sizes are multiples of 4 floats for
+        dim_feat = 8 and even edge_dim), the head as [w1 | b1 | w2 | b2]."""
+        off, table = 0, {}
+
+        def put(name, n):
+            nonlocal off
+            table[name] = (off, n)
+            off += n
+
+        c, fe = self.dim_feat, self.edge_dim
+        for l in range(self.n_conv):
+            p = f"model.module_{2 * l}."
+            put(p + "lin_l.weight", c * c)
+            put(p + "lin_l.bias", c)
+            put(p + "lin_r.weight", c * c)
+            put(p + "lin_r.bias", c)
+            put(p + "lin_edge.weight", c * fe)
+            put(p + "att", c)
+            put(p + "bias", c)
+            off = _align4(off)
+        i = 2 * self.n_conv
+        put(f"model.module_{i}.weight", self.dim_dense * c)
+        put(f"model.module_{i}.bias", self.dim_dense)
+        put(f"model.module_{i + 1}.weight", self.dim_out * self.dim_dense)
+        put(f"model.module_{i + 1}.bias", self.dim_out)
+        return table, _align4(off)
+
+
+def validate_gat_spec(sp):
+    if sp.dim_feat != GAT_C:
+        raise NotImplementedError(f"GAT_DSSE kernels are built for dim_feat == {GAT_C} (dss2_run.py:73), got {sp.dim_feat}")
+    if not (1 <= sp.edge_dim <= 8 and 1 <= sp.dim_dense <= 32 and 1 <= sp.dim_out <= 8 and sp.num_layers >= 2):
+        raise NotImplementedError(f"GAT_DSSE kernels support edge_dim <= 8, dim_dense <= 32, dim_out <= 8, num_layers >= 2; got {sp}")
+
+
+class GATRunner:
+    def __init__(self, spec):
+        validate_gat_spec(spec)
+        self.spec = spec
+        self.table, self.flat_size = spec.layout()
+        self.lib = _lib.load()
+        self.num_partials = self.lib.dss2_num_partials()
+
+    def _p(self, flat, name):
+        return ctypes.c_void_p(flat.data_ptr() + 4 * self.table[name][0])
+
+    def _layer(self, flat, l):
+        p = f"model.module_{2 * l}."
+        return [self._p(flat, p + k) for k in ("lin_l.weight", "lin_l.bias", "lin_r.weight", "lin_r.bias", "lin_edge.weight", "att", "bias")]
+
+    def alloc(self, num_nodes, device, need_grad=True):
+        sp = self.spec
+        f32 = dict(dtype=torch.float32, device=device)
+        b = {"acts": torch.empty(sp.n_conv, num_nodes, GAT_C, **f32),      # outputs of the GATv2 layers
+             "h": torch.empty(num_nodes, sp.dim_dense, **f32), "out": torch.empty(num_nodes, sp.dim_out, **f32)}
+        if need_grad:
+            b["g8"] = [torch.empty(num_nodes, GAT_C, **f32) for _ in range(2)]
+            b["gh"] = torch.empty(num_nodes, sp.dim_dense, **f32)
+            b["ws"] = torch.empty(self.lib.dss2_gat_ws_bytes(num_nodes) // 4, **f32)
+            b["partials"] = torch.zeros(self.num_partials, self.flat_size, **f32)
+        return b
+
+    def forward(self, graph, x, xs, ea, eas, flat, bufs):
+        sp, lib, st = self.spec, self.lib, _lib.stream()
+        g = graph.ref
+        for l in range(sp.n_conv):
+            xin, stride = (x, xs) if l == 0 else (bufs["acts"][l - 1], GAT_C)
+            _lib.check(lib.dss2_gat_fwd(g, _lib.ptr(xin), stride, _lib.ptr(ea), eas, sp.edge_dim, *self._layer(flat, l), sp.att_slope, 1,
+                                        sp.act_slope, _lib.ptr(bufs["acts"][l]), st), "dss2_gat_fwd")
+        i = 2 * sp.n_conv
+        _lib.check(lib.dss2_mlp2_fwd(graph.num_nodes, _lib.ptr(bufs["acts"][sp.n_conv - 1]), GAT_C, self._p(flat, f"model.module_{i}.weight"),
+                                     self._p(flat, f"model.module_{i}.bias"), sp.dim_dense, self._p(flat, f"model.module_{i + 1}.weight"),
+                                     self._p(flat, f"model.module_{i + 1}.bias"), sp.dim_out, _lib.ptr(bufs["h"]), _lib.ptr(bufs["out"]), st),
+                   "dss2_mlp2_fwd")
+        return bufs["out"]
+
+    def backward(self, graph, x, xs, ea, eas, flat, bufs, grad_out, flat_grad, need_gx=False):
+        """grad_out [Nt, dim_out] dense -> flat parameter gradient (and grad wrt x when need_gx)."""
+        sp, lib, st = self.spec, self.lib, _lib.stream()
+        g = graph.ref
+        part, pstride = bufs["partials"], self.flat_size
+
+        def pp(name):
+            return ctypes.c_void_p(part.data_ptr() + 4 * self.table[name][0])
+
+        i = 2 * sp.n_conv
+        gy = bufs["g8"][0]
+        _lib.check(lib.dss2_mlp2_bwd(graph.num_nodes, _lib.ptr(bufs["acts"][sp.n_conv - 1]), GAT_C, self._p(flat, f"model.module_{i}.weight"),
+                                     sp.dim_dense, self._p(flat, f"model.module_{i + 1}.weight"), sp.dim_out, _lib.ptr(bufs["h"]),
+                                     _lib.ptr(grad_out), _lib.ptr(bufs["gh"]), _lib.ptr(gy), pp(f"model.module_{i}.weight"), pstride, st),
+                   "dss2_mlp2_bwd")
+        gx_out = None
+        for l in reversed(range(sp.n_conv)):
+            xin, stride = (x, xs) if l == 0 else (bufs["acts"][l - 1], GAT_C)
+            want_gx = l > 0 or need_gx
+            gx = bufs["g8"][(sp.n_conv - l) & 1] if want_gx else None
+            _lib.check(lib.dss2_gat_bwd(g, _lib.ptr(xin), stride, _lib.ptr(ea), eas, sp.edge_dim, *self._layer(flat, l), sp.att_slope, 1,
+                                        sp.act_slope, _lib.ptr(bufs["acts"][l]), _lib.ptr(gy), _lib.ptr(gx), _lib.ptr(bufs["ws"]),
+                                        bufs["ws"].numel() * 4, pp(f"model.module_{2 * l}.lin_l.weight"), pstride, st), "dss2_gat_bwd")
+            gy = gx
+            gx_out = gx
+        _lib.check(lib.dss2_reduce_partials(_lib.ptr(part), pstride, self.num_partials, self.flat_size, _lib.ptr(flat_grad), 0, st),
+                   "dss2_reduce_partials")
+        return gx_out
+
+
+class _GATFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, edge_attr, edge_index, runner, pack, names, *params):
+        require_cuda()
+        out_device = x.device
+        named = dict(zip(names, params))
+        xg, xs = stage_rows(x)
+        eag, eas = stage_rows(edge_attr)
+        graph = resolve_graph(edge_index, xg.size(0))
+        with torch.cuda.device(xg.device):
+            flat = pack.gather(named)
+            bufs = runner.alloc(xg.size(0), xg.device, need_grad=any(p.requires_grad for p in params) or x.requires_grad)
+            out = runner.forward(graph, xg, xs, eag, eas, flat, bufs)
+        ctx.runner, ctx.pack, ctx.names, ctx.graph, ctx.params = runner, pack, names, graph, params
+        ctx.saved = (xg, xs, eag, eas, flat, bufs)
+        ctx.x_needs_grad, ctx.x_shape, ctx.x_device = x.requires_grad, x.shape, x.device
+        result = out.clone()
+        return result if out_device.type == "cuda" else result.to(out_device)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        xg, xs, eag, eas, flat, bufs = ctx.saved
+        runner = ctx.runner
+        go = grad_out.to(device=xg.device, dtype=torch.float32).contiguous()
+        with torch.cuda.device(xg.device):
+            flat_grad = torch.empty(runner.flat_size, dtype=torch.float32, device=xg.device)
+            gx = runner.backward(ctx.graph, xg, xs, eag, eas, flat, bufs, go, flat_grad, need_gx=ctx.x_needs_grad)
+        grads = ctx.pack.scatter_grads(flat_grad, dict(zip(ctx.names, ctx.params)))
+        gx_ret = gx.clone().to(ctx.x_device) if ctx.x_needs_grad else None
+        return (gx_ret, None, None, None, None, None, *grads)
+
+
+def gat_apply(runner, pack, named_params, x, edge_index, edge_attr):
+    names = tuple(named_params.keys())
+    return _GATFunction.apply(x, edge_attr, edge_index, runner, pack, names, *named_params.values())
+
+
+def make_machinery(spec):
+    return GATRunner(spec), ParamPack(spec)

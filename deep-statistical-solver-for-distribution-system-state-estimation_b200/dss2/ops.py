@@ -232,15 +232,12 @@ class ParamPack:
                         p.data = view
                 self.flat = flat
             return self.flat
-        # CPU parameters: one concatenation + one H2D copy
-        chunks = []
+        # CPU parameters: one host staging buffer in the layout's order + one H2D copy
+        host = torch.zeros(self.flat_size, dtype=torch.float32)
         for name, p in named_params.items():
             off, n = self.table[name]
-            chunks.append(p.data.reshape(-1).float())
-            pad = _align4(n) - n
-            if pad:
-                chunks.append(torch.zeros(pad))
-        return torch.cat(chunks).cuda(non_blocking=True)
+            host[off:off + n] = p.data.reshape(-1).float()
+        return host.cuda(non_blocking=True)
 
     def _is_packed(self, named_params):
         base = self.flat.data_ptr()

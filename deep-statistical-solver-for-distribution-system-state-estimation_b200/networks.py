@@ -11,8 +11,8 @@ Reference behaviours kept on purpose: dropout is active i
 EdgeAggregation.forward (networks.py:196-200) never reaches `message` and is not applied; all sub-nets of a
 PFN receive the same raw edge attributes; reversed edges negate attribute columns 0 and 2 (networks.py:252).
 There is no CPU fallback: without a CUDA device or the built library, forward raises.
-The other models of the reference module (gnn_dsse, GINE_DSSE, GAT_DSSE: GCN2/FA/GINE/GATv2 stacks) are the
-next row of the scope table; their names exist so that `from networks import ...` works.
+GAT_DSSE (networks.py:113-156, the as-shipped default of dss2_run.py:86) runs on its own fused GATv2 kernels
+(csrc/gat.cu).  gnn_dsse and GINE_DSSE (GCN2/FA/GINE stacks) remain names only so that `from networks import ...` works.
 """
 import math
 
@@ -144,4 +144,66 @@ def _next_row(name, where):
 
 gnn_dsse = _next_row("gnn_dsse", "networks.py:11-69")
 GINE_DSSE = _next_row("GINE_DSSE", "networks.py:71-111")
-GAT_DSSE = _next_row("GAT_DSSE", "networks.py:113-156")
+
+
+class _GATv2Params(nn.Module):
+    """Parameter holder with PyG GATv2Conv's names / shapes / initialisation (glorot weights, zero biases); the arithmetic is in the
+    fused kernel (csrc/gat.cu), so this module has no forward of its own."""
+
+    def __init__(self, channels, edge_dim):
+        super().__init__()
+        self.att = nn.Parameter(torch.empty(1, 1, channels))
+        self.bias = nn.Parameter(torch.zeros(channels))
+        self.lin_l = nn.Linear(channels, channels, bias=True)
+        self.lin_r = nn.Linear(channels, channels, bias=True)
+        self.lin_edge = nn.Linear(edge_dim, channels, bias=False)
+        for lin in (self.lin_l, self.lin_r, self.lin_edge):
+            nn.init.xavier_uniform_(lin.weight)
+            if lin.bias is not None:
+                nn.init.zeros_(lin.bias)
+        nn.init.xavier_uniform_(self.att)
+
+
+class GAT_DSSE(nn.Module):
+    """networks.py:113-156, the as-shipped default model of dss2_run.py:86: (num_layers - 1) x [GATv2Conv(dim_feat, dim_feat, heads,
+    edge_dim, add_self_loops, fill 'mean') + LeakyReLU()], Linear(dim_feat, dim_dense), Linear(dim_dense, dim_out), wrapped in a PyG
+    `Sequential` whose children are called `module_{i}` - kept, so that reference checkpoints (`model.module_0.att`, ...) load.
+    Built for the configuration the script uses (heads=1, concat, dropout 0, self loops, leaky_relu); anything else raises."""
+
+    def __init__(self, dim_feat, dim_dense, dim_out, num_layers, edge_dim, heads=1, concat=True, slope=0.2, self_loops=True, dropout=0.,
+                 nonlin='leaky_relu', model='gat'):
+        super().__init__()
+        if model != 'gat':
+            raise Exception('invalid model type')
+        if nonlin not in ('relu', 'tanh', 'leaky_relu'):
+            raise Exception('invalid activation type')
+        if heads != 1 or not concat or dropout != 0. or not self_loops or nonlin != 'leaky_relu':
+            raise NotImplementedError("GAT_DSSE kernels cover the configuration of dss2_run.py:86 (heads=1, concat=True, dropout=0, "
+                                      "self_loops=True, nonlin='leaky_relu')")
+        self.dim_out, self.num_layers, self.dim_feat, self.dim_dense, self.edge_dim = dim_out, num_layers, dim_feat, dim_dense, edge_dim
+        self.dim_hidden = self.channels = dim_feat
+        self.heads, self.concat, self.slope, self.dropout, self.loop = heads, concat, slope, dropout, self_loops
+        self.nonlin = nn.LeakyReLU()
+        self.model = nn.Module()
+        i = 0
+        for _ in range(num_layers - 1):
+            self.model.add_module(f"module_{i}", _GATv2Params(dim_feat, edge_dim))
+            self.model.add_module(f"module_{i + 1}", self.nonlin)
+            i += 2
+        self.model.add_module(f"module_{i}", nn.Linear(dim_feat, dim_dense))
+        self.model.add_module(f"module_{i + 1}", nn.Linear(dim_dense, dim_out))
+
+    def _machinery(self):
+        m = self.__dict__.get("_dss2_machinery")
+        if m is None:
+            from dss2 import gat
+            spec = gat.GATSpec(dim_feat=self.dim_feat, dim_dense=self.dim_dense, dim_out=self.dim_out, num_layers=self.num_layers,
+                               edge_dim=self.edge_dim, att_slope=float(self.slope), act_slope=float(self.nonlin.negative_slope))
+            m = gat.make_machinery(spec)
+            self.__dict__["_dss2_machinery"] = m
+        return m
+
+    def forward(self, x, edge_index, edge_attr):
+        from dss2 import gat
+        runner, pack = self._machinery()
+        return gat.gat_apply(runner, pack, dict(self.named_parameters()), x, edge_index, edge_attr)

@@ -232,6 +232,37 @@ int dss2_adamax_step(float* param, const float* grad, float* exp_avg, float* exp
                      float lr, float beta1, float beta2, float eps, float grad_scale,
                      uint64_t* step_state, int bump, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Next row: GAT_DSSE, the as-shipped default model of dss2_run.py:86 (networks.py:113-156):
+ * 7 x [PyG GATv2Conv(8, 8, heads=1, negative_slope=0.2, add_self_loops=True, edge_dim=6, fill_value='mean') + LeakyReLU(0.01)],
+ * Linear(8, dim_dense), Linear(dim_dense, 2).
+ *
+ * dss2_gat_fwd: one GATv2 layer (+ optional LeakyReLU, act != 0) on the ONE-WAY edge list the script passes: x [Nt,8] (row stride
+ * x_stride), edge_attr [Et,fe] (row stride ea_stride) -> y [Nt,8] dense.  Input self loops are dropped and one loop per bus is appended
+ * last with the mean attribute of the edges pointing at the bus; segment softmax as PyG (max-shifted, + 1e-16).
+ * Parameters with PyG's names and shapes: lin_l.weight/bias [8,8]/[8], lin_r.weight/bias, lin_edge.weight [8,fe], att [8], bias [8].
+ * dss2_gat_bwd: recompute-based backward.  y = the forward output (activation gate), grad_y its gradient, grad_x [Nt,8] or NULL,
+ * node_ws: dss2_gat_ws_bytes(Nt) of scratch; per-CTA partial gradients (dss2_num_partials() rows) in the order
+ * [lin_l.w 64 | lin_l.b 8 | lin_r.w 64 | lin_r.b 8 | lin_edge.w 8 fe | att 8 | bias 8].  Needs a graph built with undirect=1.
+ * dss2_mlp2_fwd/bwd: z = W2 (W1 x + b1) + b2 per bus (no non-linearity in between, networks.py:150-151); h [Nt,dmid] is kept for the
+ * backward; partial layout [w1 dmid x din | b1 dmid | w2 dout x dmid | b2 dout].
+ * ---------------------------------------------------------------------------------------------- */
+size_t dss2_gat_ws_bytes(int64_t num_nodes);
+int dss2_gat_fwd(const dss2_graph_t* g, const float* x, int64_t x_stride, const float* edge_attr, int64_t ea_stride, int fe,
+                 const float* lin_l_w, const float* lin_l_b, const float* lin_r_w, const float* lin_r_b,
+                 const float* lin_edge_w, const float* att, const float* bias, float att_slope, int act, float act_slope,
+                 float* y, void* stream);
+int dss2_gat_bwd(const dss2_graph_t* g, const float* x, int64_t x_stride, const float* edge_attr, int64_t ea_stride, int fe,
+                 const float* lin_l_w, const float* lin_l_b, const float* lin_r_w, const float* lin_r_b,
+                 const float* lin_edge_w, const float* att, const float* bias, float att_slope, int act, float act_slope,
+                 const float* y, const float* grad_y, float* grad_x, float* node_ws, size_t node_ws_bytes, float* partials,
+                 int64_t partial_stride, void* stream);
+int dss2_mlp2_fwd(int64_t num_nodes, const float* x, int din, const float* w1, const float* b1, int dmid, const float* w2,
+                  const float* b2, int dout, float* h, float* z, void* stream);
+int dss2_mlp2_bwd(int64_t num_nodes, const float* x, int din, const float* w1, int dmid, const float* w2, int dout,
+                  const float* h, const float* grad_z, float* grad_h_ws, float* grad_x, float* partials, int64_t partial_stride,
+                  void* stream);
+
 #ifdef __cplusplus
 }
 #endif

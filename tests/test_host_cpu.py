@@ -54,9 +54,27 @@ def test_no_cpu_fallback():
     import data
     with pytest.raises(_lib.Dss2Error):
         data.get_pflow(torch.zeros(3, 2), torch.tensor([[0], [1]]), torch.zeros(3, 3), torch.zeros(1, 7))
-    for name in ("GAT_DSSE", "GINE_DSSE", "gnn_dsse"):
+    for name in ("GINE_DSSE", "gnn_dsse"):
         with pytest.raises(NotImplementedError):
             getattr(networks, name)()
+    gat = networks.GAT_DSSE(dim_feat=8, dim_dense=32, dim_out=2, heads=1, num_layers=3, edge_dim=6)
+    with pytest.raises(_lib.Dss2Error):
+        gat(torch.zeros(4, 8), torch.tensor([[0, 1], [1, 2]]), torch.zeros(2, 6))
+    with pytest.raises(NotImplementedError):
+        networks.GAT_DSSE(dim_feat=8, dim_dense=32, dim_out=2, heads=2, num_layers=3, edge_dim=6)
+
+
+def test_gat_dsse_state_dict_names_match_reference_layout():
+    """Parameter names / shapes of GAT_DSSE equal the reference's (PyG Sequential naming), and the flat layout covers all of them."""
+    from dss2 import gat
+    import dss2_oracle as orc
+    m = networks.GAT_DSSE(dim_feat=8, dim_dense=32, dim_out=2, heads=1, num_layers=8, edge_dim=6)
+    sd = orc.init_gat_state_dict(seed=1)
+    assert set(sd) == set(m.state_dict()) and all(tuple(sd[k].shape) == tuple(v.shape) for k, v in m.state_dict().items())
+    table, size = gat.GATSpec(8, 32, 2, 8, 6).layout()
+    assert set(table) == set(dict(m.named_parameters()))
+    spans = sorted(table.values())
+    assert all(a[0] + a[1] <= b[0] for a, b in zip(spans, spans[1:])) and spans[-1][0] + spans[-1][1] <= size
 
 
 def test_unsupported_shapes_fail_loudly():
