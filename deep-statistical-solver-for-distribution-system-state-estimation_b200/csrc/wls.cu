@@ -502,6 +502,117 @@ __global__ void k_pflow(const int64_t* __restrict__ ei, int64_t Et, const float*
   }
 }
 
+// -------------------------------------------------------------------------------------------------
+// (f-4) Validation metrics of one batch, dss2_run.py:183-209: de-normalise V, mask the slack angle, squared / absolute errors of V and
+// theta, column sums for the std ratio, and line / transformer loading errors over the branches whose TRUE loading is non-zero -
+// both branch-flow evaluations (truth and estimate) in registers, 19 fp64 sums out, fixed-order last-CTA reduction.
+// -------------------------------------------------------------------------------------------------
+enum { M_SE_V = 0, M_AE_V, M_SE_TH, M_AE_TH, M_SV, M_SVV, M_STH, M_STHTH, M_YV, M_YVV, M_YTH, M_YTHTH,
+       M_CNT_L, M_SE_L, M_AE_L, M_CNT_T, M_SE_T, M_AE_T, M_PAD, M_N = 19 };
+struct EvalArgs {
+  int64_t Nt, Et;
+  const int64_t* ei;
+  const float* x;      // [Nt, >= 11]: column 9 = slack flag
+  int64_t xs;
+  const float* ea;     // [Et, >= 13]: columns 6.. = edge_param
+  int64_t eas;
+  const float* out;    // [Nt, 2] model output (normalised V, raw theta)
+  int64_t os;
+  const float* y;      // [Nt, 2] labels (V pu, theta rad)
+  int64_t ys;
+  float xm0, xs0;
+  const float* vminmax;
+  double* partial;     // [grid][M_N]
+  unsigned* counter;
+  double* sums;        // [M_N]
+};
+__global__ void __launch_bounds__(WLS_THREADS) k_eval_metrics(EvalArgs a) {
+  __shared__ double s_red[M_N][WLS_THREADS / 32];
+  __shared__ bool s_last;
+  const WlsGrid grid = wls_grid(a.vminmax[0], a.vminmax[1]);
+  double acc[M_N];
+#pragma unroll
+  for (int q = 0; q < M_N; ++q) acc[q] = 0.0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  for (int64_t n = t0; n < a.Nt; n += stride) {
+    const float v = a.out[n * a.os] * a.xs0 + a.xm0;                               // dss2_run.py:183
+    const float th = a.out[n * a.os + 1] * (1.0f - a.x[n * a.xs + 9]);             // :184
+    const float yv = a.y[n * a.ys], yth = a.y[n * a.ys + 1];
+    const float dv = v - yv, dth = th - yth;
+    acc[M_SE_V] += (double)(dv * dv);
+    acc[M_AE_V] += (double)fabsf(dv);
+    acc[M_SE_TH] += (double)(dth * dth);
+    acc[M_AE_TH] += (double)fabsf(dth);
+    acc[M_SV] += v;
+    acc[M_SVV] += (double)v * v;
+    acc[M_STH] += th;
+    acc[M_STHTH] += (double)th * th;
+    acc[M_YV] += yv;
+    acc[M_YVV] += (double)yv * yv;
+    acc[M_YTH] += yth;
+    acc[M_YTHTH] += (double)yth * yth;
+  }
+  for (int64_t e = t0; e < a.Et; e += stride) {
+    const int64_t i = a.ei[e], j = a.ei[a.Et + e];
+    const float* row = a.ea + e * a.eas;
+    WlsBranchIn in;
+    in.G = row[6];
+    in.B = row[7];
+    in.Gs = row[8];
+    in.Bs = row[9];
+    in.shift = row[11];
+    in.rating = row[12];
+    WlsBranch bt, bo;
+    in.vi = a.y[i * a.ys];
+    in.thi = a.y[i * a.ys + 1];
+    in.vj = a.y[j * a.ys];
+    in.thj = a.y[j * a.ys + 1];
+    wls_branch_forward(in, grid, bt);                                               // truth, :193
+    in.vi = a.out[i * a.os] * a.xs0 + a.xm0;
+    in.thi = a.out[i * a.os + 1] * (1.0f - a.x[i * a.xs + 9]);
+    in.vj = a.out[j * a.os] * a.xs0 + a.xm0;
+    in.thj = a.out[j * a.os + 1] * (1.0f - a.x[j * a.xs + 9]);
+    wls_branch_forward(in, grid, bo);                                               // estimate, :194
+    if (bt.ll != 0.0f) {                                                            // :196-197
+      const float d = bo.ll - bt.ll;
+      acc[M_CNT_L] += 1.0;
+      acc[M_SE_L] += (double)(d * d);
+      acc[M_AE_L] += (double)fabsf(d);
+    }
+    if (bt.lt != 0.0f) {                                                            // :199-200
+      const float d = bo.lt - bt.lt;
+      acc[M_CNT_T] += 1.0;
+      acc[M_SE_T] += (double)(d * d);
+      acc[M_AE_T] += (double)fabsf(d);
+    }
+  }
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int q = 0; q < M_N; ++q) {
+    const double v = warp_sum(acc[q]);
+    if (lane == 0) s_red[q][warp] = v;
+  }
+  __syncthreads();
+  if (tid < M_N) {
+    double v = 0;
+    for (int w = 0; w < WLS_THREADS / 32; ++w) v += s_red[tid][w];
+    a.partial[(size_t)blockIdx.x * M_N + tid] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(a.counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    if (tid < M_N) {
+      double v = 0;
+      for (unsigned c = 0; c < gridDim.x; ++c) v += ((volatile double*)a.partial)[(size_t)c * M_N + tid];
+      a.sums[tid] = v;
+    }
+    if (tid == 0) *a.counter = 0;
+  }
+}
+
 int wls_grid_size(const dss2_graph_t* g) { return max(1, min(g->num_tiles, dss2_sm_count() * 8)); }
 size_t wls_smem(const dss2_graph_t* g) { return (size_t)(6 * g->max_tile_nodes + 4 * g->max_tile_edges) * sizeof(float); }
 
@@ -556,6 +667,40 @@ extern "C" int dss2_wls_fwd_bwd(const dss2_graph_t* g, const float* x, int64_t x
     k_wls<true><<<grid, WLS_THREADS, smem, stream>>>(a);
     DSS2_LAUNCH_CHECK();
   }
+  return 0;
+}
+
+extern "C" size_t dss2_eval_workspace_bytes(void) { return 256 + (size_t)(dss2_sm_count() * 4 + 1) * M_N * sizeof(double); }
+
+extern "C" int dss2_eval_metrics(const int64_t* edge_index, int64_t num_nodes, int64_t num_edges, const float* x, int64_t x_stride,
+                                 const float* edge_attr, int64_t ea_stride, const float* output, int64_t out_stride, const float* y,
+                                 int64_t y_stride, float x_mean0, float x_std0, const float* vminmax, double* sums19, void* ws,
+                                 size_t ws_bytes, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DSS2_CHECK_ARG(edge_index && x && edge_attr && output && y && vminmax && sums19 && ws, "dss2_eval_metrics: null argument");
+  DSS2_CHECK_ARG(x_stride >= 11 && ea_stride >= 13 && out_stride >= 2 && y_stride >= 2, "dss2_eval_metrics: x needs 11 columns, edge_attr 13");
+  DSS2_CHECK_ARG(ws_bytes >= dss2_eval_workspace_bytes(), "dss2_eval_metrics: workspace too small");
+  EvalArgs a;
+  a.Nt = num_nodes;
+  a.Et = num_edges;
+  a.ei = edge_index;
+  a.x = x;
+  a.xs = x_stride;
+  a.ea = edge_attr;
+  a.eas = ea_stride;
+  a.out = output;
+  a.os = out_stride;
+  a.y = y;
+  a.ys = y_stride;
+  a.xm0 = x_mean0;
+  a.xs0 = x_std0;
+  a.vminmax = vminmax;
+  a.counter = (unsigned*)ws;                      // zero-initialised by the caller once; self-resetting
+  a.partial = (double*)((char*)ws + 256);
+  a.sums = sums19;
+  const int grid = (int)max((int64_t)1, min((int64_t)dss2_sm_count() * 4, (max(num_nodes, num_edges) + WLS_THREADS - 1) / WLS_THREADS));
+  k_eval_metrics<<<grid, WLS_THREADS, 0, stream>>>(a);
+  DSS2_LAUNCH_CHECK();
   return 0;
 }
 

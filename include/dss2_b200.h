@@ -222,6 +222,18 @@ int dss2_wls_fwd_bwd(const dss2_graph_t* g, const float* x, int64_t x_stride, co
 int dss2_pflow(const int64_t* edge_index, int64_t num_edges, const float* y, int64_t y_stride,
                const float* edge_param, int64_t ep_stride, const float* vminmax, float* out8, void* stream);
 
+/* Validation metrics of one batch (SURVEY.md 8f-4, dss2_run.py:183-209) in one kernel: x [Nt,>=11] (column 9 = slack flag),
+ * edge_attr [Et,>=13] (columns 6.. = branch parameters), output [Nt,2] = model output (normalised V, raw theta), y [Nt,2] = labels.
+ * sums19 (device, fp64): [0..3] sum (dV)^2, |dV|, (dth)^2, |dth| with V = out0*x_std0 + x_mean0 and th = out1*(1-slack);
+ * [4..7] sum V, V^2, th, th^2; [8..11] the same of the labels; [12..14] count, sum d^2, sum |d| of the line loading over branches whose
+ * TRUE line loading is non-zero; [15..17] the same for the transformer loading; [18] unused.  ws: dss2_eval_workspace_bytes(),
+ * zero-initialised once. */
+size_t dss2_eval_workspace_bytes(void);
+int dss2_eval_metrics(const int64_t* edge_index, int64_t num_nodes, int64_t num_edges, const float* x, int64_t x_stride,
+                      const float* edge_attr, int64_t ea_stride, const float* output, int64_t out_stride, const float* y,
+                      int64_t y_stride, float x_mean0, float x_std0, const float* vminmax, double* sums19, void* ws, size_t ws_bytes,
+                      void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Adjacent: flat-buffer Adamax (torch.optim.Adamax defaults, dss2_run.py:91-92,143).
  * step_state: device {uint64 seed, uint64 step}; the kernel uses step+1 for bias correction and, when

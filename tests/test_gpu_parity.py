@@ -1027,3 +1027,33 @@ def test_dss2_run_flow_with_default_gat_model(env):
         assert abs(m1[k] - m2[k]) <= 2e-2 * max(abs(m2[k]), 1e-6), (k, m1[k], m2[k])
     # checkpoints interchange (dss2_run.py:240-247): the trained state_dict carries the reference's names
     assert set(model.state_dict()) == set(sd0)
+
+
+# ------------------------------------------------------------------------------------------------ validation metrics (scope row 8f-4)
+@pytest.mark.parametrize("case", ["cigre14", "ober_sub"])
+def test_eval_metrics_kernel_matches_script_formulas(env, case):
+    """dss2.metrics.evaluate_batch (one kernel) against the metric block of the script (dss2_run.py:183-205) evaluated with torch ops
+    and the oracle's get_pflow in fp64."""
+    from dss2 import metrics
+    import torch.nn.functional as F
+    b = _small_batch(env, case, 6, seed=21)
+    st = env["synth"].synthetic_store(env["synth"].load_grid(case), 6, seed=21)
+    torch.manual_seed(3)
+    truth = torch.stack([(b.y[:, 0].cpu() - st.x_mean[0]) / st.x_std[0], b.y[:, 1].cpu()], 1)
+    out = truth + torch.randn_like(truth) * torch.tensor([0.05, 0.002])
+    got = metrics.evaluate_batch(out.cuda(), b.y, b.x, b.edge_index, b.edge_attr, st.x_mean, st.x_std)
+    x, ea, y, ei = b.x.cpu().double(), b.edge_attr.cpu().double(), b.y.cpu().double(), b.edge_index.cpu()
+    o = torch.cat([out[:, 0:1].double() * st.x_std[:1].double() + st.x_mean[:1].double(), out[:, 1:].double()], 1)
+    o[:, 1:] *= (1. - x[:, 9:10])
+    mae = lambda a_, b_: float((a_ - b_).abs().mean())
+    want = {"rmse_v": float(torch.sqrt(F.mse_loss(o[:, :1], y[:, :1]))), "rmse_th": float(torch.sqrt(F.mse_loss(o[:, 1:], y[:, 1:]))),
+            "mae_v": mae(o[:, :1], y[:, :1]), "mae_th": mae(o[:, 1:], y[:, 1:])}
+    tl, tt = orc.get_pflow(y, ei, x[:, 8:], ea[:, 6:])[0:2]
+    ol, ot = orc.get_pflow(o, ei, x[:, 8:], ea[:, 6:])[0:2]
+    tl2, ol2, tt2, ot2 = tl[tl.nonzero()], ol[tl.nonzero()], tt[tt.nonzero()], ot[tt.nonzero()]
+    want.update(rmse_loading=float(torch.sqrt(F.mse_loss(ol2, tl2))), mae_loading=mae(ol2, tl2),
+                rmse_loading_trafos=float(torch.sqrt(F.mse_loss(ot2, tt2))), mae_loading_trafos=mae(ot2, tt2),
+                prop_std_v=float((o.std(axis=0) / y.std(axis=0) * 100)[0]), prop_std_th=float((o.std(axis=0) / y.std(axis=0) * 100)[1]))
+    assert set(got) == set(want)
+    for k in want:
+        assert abs(got[k] - want[k]) <= 2e-4 * abs(want[k]) + 1e-9, (k, got[k], want[k])
