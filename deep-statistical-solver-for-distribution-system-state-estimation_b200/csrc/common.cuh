@@ -43,6 +43,13 @@ int dss2_sm_count();
     dss2_count_launch(1);                                                                        \
   } while (0)
 
+// tcgen05 transform of a layer on precomputed hop levels (tag_tc2.cu), used by the large-graph path in tag.cu
+int dss2_tc2_dense_fwd(const dss2_graph_t* g, const float* x, const float* lvl, const float* w, const float* bias, int cout, int K, int act,
+                       float p_drop, int drop_mode, const uint64_t* rng_state, uint32_t layer_uid, const uint8_t* mask, const float* res,
+                       int64_t res_stride, float* y, uint32_t* act_bits, cudaStream_t stream);
+int dss2_tc2_dense_bgx(const dss2_graph_t* g, const float* grad_y, const uint32_t* act_bits, float p_drop, const float* lvl, const float* w,
+                       int cout, int K, float* grad_x, cudaStream_t stream);
+
 // large-graph (num_tiles == 0) variants, implemented next to their tiled counterparts
 #define DSS2_NEED_SCRATCH(g, who)                                                                                        \
   DSS2_CHECK_ARG((g)->scratch && (g)->scratch_bytes >= dss2_generic_scratch_bytes((g)->num_nodes),                        \

@@ -614,6 +614,12 @@ inline int pad_cout(int cout) { return cout <= 2 ? 2 : (cout <= 8 ? 8 : 32); }
 
 extern "C" int dss2_num_partials(void) { return dss2_sm_count(); }
 
+// DSS2_DENSE_TC=0 keeps the large-graph transform on the CUDA cores (k_dense_tag): measurement / bisecting aid
+static bool dense_tc_enabled() {
+  const char* e = getenv("DSS2_DENSE_TC");
+  return !(e && e[0] == '0');
+}
+
 extern "C" int dss2_tag_fwd(const dss2_graph_t* g, const float* x, const float* w, const float* bias, int cout, int K, int act,
                             float p_drop, int drop_mode, const uint64_t* rng_state, uint32_t layer_uid, const uint8_t* mask,
                             const float* res, int64_t res_stride, float* y, uint32_t* act_bits, void* stream_) {
@@ -635,6 +641,9 @@ extern "C" int dss2_tag_fwd(const dss2_graph_t* g, const float* x, const float* 
       if (launch_hop(g, d.L[k - 1], lv + (size_t)(k - 1) * Nt * HID, stream)) return -3;
       d.L[k] = lv + (size_t)(k - 1) * Nt * HID;
     }
+    if (dense_tc_enabled() && K <= 2 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0)   // transform on the tensor cores (same kernel as the tiled path, hop-free)
+      return dss2_tc2_dense_fwd(g, x, lv, w, bias, cout, K, act, p_drop, drop_mode, rng_state, layer_uid, mask, res, res_stride, y, act_bits,
+                                stream);
     d.w = w;
     d.bias = bias;
     d.cout = cout;
@@ -710,15 +719,24 @@ extern "C" int dss2_tag_bwd(const dss2_graph_t* g, const float* x, const float* 
       if (launch_hop(g, d.L[k - 1], lvl + (size_t)(k - 1) * Nt * HID, stream)) return -3;
       d.L[k] = lvl + (size_t)(k - 1) * Nt * HID;
     }
-    k_transpose_w<<<12, 256, 0, stream>>>(w, cout, K, WT);
-    DSS2_LAUNCH_CHECK();
-    d.w = WT;
-    d.cout = HID;
-    d.y = grad_x;
-    d.Nt = Nt;
-    if (launch_dense_k(d, K, stream)) return -3;
+    if (dense_tc_enabled() && ((uintptr_t)grad_x & 15) == 0 && (cout != HID || ((uintptr_t)grad_y & 15) == 0)) {   // tensor cores, hop-free (see dss2_tag_fwd)
+      if (dss2_tc2_dense_bgx(g, grad_y, act ? act_bits : nullptr, p_drop, lvl, w, cout, K, grad_x, stream)) return -3;
+    } else {
+      k_transpose_w<<<12, 256, 0, stream>>>(w, cout, K, WT);
+      DSS2_LAUNCH_CHECK();
+      d.w = WT;
+      d.cout = HID;
+      d.y = grad_x;
+      d.Nt = Nt;
+      if (launch_dense_k(d, K, stream)) return -3;
+    }
+    // weight gradients: the tcgen05 streaming GEMM when its alignment contract holds (it measures 2x faster), else the exact FMA pass
+    const bool aligned = (((uintptr_t)x | (uintptr_t)grad_y | (uintptr_t)act_bits | (uintptr_t)partials) & 15) == 0;
+    if (dense_tc_enabled() && aligned)
+      return dss2_tag_bwd_tc2_gw(Nt, x, cout, K, act, p_drop, act_bits, grad_y, partials, partial_stride, bias_offset, lvl,
+                                 dss2_tag_bwd_tc2_workspace_bytes(Nt, K), stream_);
     return dss2_tag_gw_ffma(Nt, x, cout, K, act, p_drop, act_bits, grad_y, partials, partial_stride, bias_offset, lvl,
-                               dss2_tag_bwd_tc2_workspace_bytes(Nt, K), stream_);
+                            dss2_tag_bwd_tc2_workspace_bytes(Nt, K), stream_);
   }
   TagBwdArgs a;
   a.g = *g;

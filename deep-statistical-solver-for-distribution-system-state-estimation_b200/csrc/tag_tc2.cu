@@ -44,6 +44,7 @@ struct Tc2Args {
   float* out;               // FWD: y [Nt,cout].  BGX: grad_x [Nt,32]
   uint32_t* out_bits;       // FWD
   float* lvl_out;           // BGX: [K][Nt,32] hop levels 1..K of g (for k_tag_gw)
+  const float* dense_lvl;   // large-graph path: hop levels 1..K precomputed in global memory ([K][Nt,32]); tiles are plain row chunks
 };
 
 __device__ __forceinline__ char* align1024(char* p) {
@@ -142,9 +143,17 @@ __device__ __forceinline__ uint32_t keep_half(uint2 key, uint32_t tile, uint32_t
 struct TileNodes {
   int n0, n1;
 };
-__device__ __forceinline__ TileNodes tile_nodes(const dss2_graph_t& g, int t) {
+__device__ __forceinline__ TileNodes tile_nodes(const dss2_graph_t& g, int t, int dense_rows = 0) {
   TileNodes r;
   r.n0 = r.n1 = 0;
+  if (dense_rows) {   // hop-free mode: tile t = rows [t * dense_rows, (t + 1) * dense_rows)
+    const int64_t n0 = (int64_t)t * dense_rows;
+    if (n0 < g.num_nodes) {
+      r.n0 = (int)n0;
+      r.n1 = (int)min(g.num_nodes, n0 + dense_rows);
+    }
+    return r;
+  }
   if (t < g.num_tiles) {
     const int g0 = t * g.graphs_per_tile, g1 = min(g0 + g.graphs_per_tile, g.num_graphs);
     r.n0 = (int)g.ptr[g0];
@@ -209,13 +218,15 @@ __global__ void __launch_bounds__(256 * NB + 32, 3 - NB) k_tag_tc2(Tc2Args a) {
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = *tslot;
+  const int dense_rows = a.dense_lvl ? ROWS : 0;
+  const int ntiles = a.dense_lvl ? (int)((g.num_nodes + ROWS - 1) / ROWS) : g.num_tiles;
 
   if (issuer) {
     // ===== MMA issuer warp: D[:, 0:32] += A W_plain^T, D[:, 32:64] += A W_resid^T for A in {plain, residual} of every level =====
     const uint32_t idesc = tc::idesc_tf32(128, 64);
     uint32_t fpar[2] = {0u, 0u};
-    for (int t = blockIdx.x; t < g.num_tiles; t += gridDim.x) {
-      const TileNodes tn = tile_nodes(g, t);
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      const TileNodes tn = tile_nodes(g, t, dense_rows);
       const int nmb = (NB == 2 && tn.n1 - tn.n0 > 128) ? 2 : 1;
 #pragma unroll
       for (int k = 0; k <= K; ++k) {
@@ -254,7 +265,7 @@ __global__ void __launch_bounds__(256 * NB + 32, 3 - NB) k_tag_tc2(Tc2Args a) {
       for (int i = 0; i < HF; ++i) xr[i] = 0.0f;
       if ((int)row >= tn.n1 - tn.n0) return;
       const size_t n = (size_t)tn.n0 + row;
-      tp_next = load_row_topo(g, n);
+      if (!dense_rows) tp_next = load_row_topo(g, n);
       if (MODE == MODE_FWD || cout == 32) {
         const float4* src = reinterpret_cast<const float4*>(a.in + n * 32 + half * HF);
 #pragma unroll
@@ -282,10 +293,10 @@ __global__ void __launch_bounds__(256 * NB + 32, 3 - NB) k_tag_tc2(Tc2Args a) {
       named_bar_sync(1, TC2_WORKERS);
     };
 
-    TileNodes cur = tile_nodes(g, blockIdx.x);
-    TileNodes nxt = tile_nodes(g, blockIdx.x + gridDim.x);
+    TileNodes cur = tile_nodes(g, blockIdx.x, dense_rows);
+    TileNodes nxt = tile_nodes(g, blockIdx.x + gridDim.x, dense_rows);
     load_row(cur);
-    for (int t = blockIdx.x; t < g.num_tiles; t += gridDim.x) {
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
       const int nT = cur.n1 - cur.n0, n0 = cur.n0;
       const bool live = (int)row < nT;
       const size_t n = (size_t)n0 + row;
@@ -296,14 +307,24 @@ __global__ void __launch_bounds__(256 * NB + 32, 3 - NB) k_tag_tc2(Tc2Args a) {
       if (MODE == MODE_BGX) {   // see the note on the prefetch below: with the spill stores in flight the backward measures best here
         cur = nxt;
         load_row(cur);
-        nxt = tile_nodes(g, t + 2 * gridDim.x);
+        nxt = tile_nodes(g, t + 2 * gridDim.x, dense_rows);
       }
       // ---- levels 1..K ----
 #pragma unroll
       for (int k = 1; k <= K; ++k) {
         const int b = k & 1, pb = (k - 1) & 1;
         float h[HF];
-        if (live) hop_thread(h, g, tp, lv_p(pb), n, n0, half);
+        if (live && dense_rows) {   // large-graph path: the level was computed by a hop kernel over the whole graph
+          const float4* src = reinterpret_cast<const float4*>(a.dense_lvl + ((size_t)(k - 1) * g.num_nodes + n) * 32 + half * HF);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 v = ldg_stream4(src + q);
+            h[4 * q] = v.x;
+            h[4 * q + 1] = v.y;
+            h[4 * q + 2] = v.z;
+            h[4 * q + 3] = v.w;
+          }
+        } else if (live) hop_thread(h, g, tp, lv_p(pb), n, n0, half);
         else {
 #pragma unroll
           for (int i = 0; i < HF; ++i) h[i] = 0.0f;
@@ -329,7 +350,7 @@ __global__ void __launch_bounds__(256 * NB + 32, 3 - NB) k_tag_tc2(Tc2Args a) {
       if (MODE == MODE_FWD) {
         cur = nxt;
         load_row(cur);                                             // next tile: rows (same registers) + topology
-        nxt = tile_nodes(g, t + 2 * gridDim.x);                    // and the node range of the tile after it
+        nxt = tile_nodes(g, t + 2 * gridDim.x, dense_rows);                    // and the node range of the tile after it
       }
       // dropout keep bits do not depend on the MMAs: generate them while the tensor core finishes
       uint32_t keep_rng = 0xffffu;
@@ -800,7 +821,8 @@ int tc2_supported(const dss2_graph_t* g, int K) {
 template <int MODE, int K, int NB>
 int launch_tc2_inst(const Tc2Args& a, cudaStream_t stream) {
   const size_t smem = tc2_smem(K, NB);
-  const int grid = max(1, min(a.g.num_tiles, (3 - NB) * dss2_sm_count()));
+  const int tiles = a.dense_lvl ? (int)((a.g.num_nodes + 128 * NB - 1) / (128 * NB)) : a.g.num_tiles;
+  const int grid = max(1, min(tiles, (3 - NB) * dss2_sm_count()));
   DSS2_CUDA(cudaFuncSetAttribute(k_tag_tc2<MODE, K, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_tag_tc2<MODE, K, NB><<<grid, 256 * NB + 32, smem, stream>>>(a);
   DSS2_LAUNCH_CHECK();
@@ -816,6 +838,47 @@ int launch_tc2(const Tc2Args& a, int K, cudaStream_t stream) {
 }  // namespace
 
 extern "C" int dss2_tag_tc2_supported(const dss2_graph_t* g, int K) { return tc2_supported(g, K); }
+
+// Large-graph path (tag.cu): the transform of a layer on hop levels that already sit in global memory (lvl = [K][Nt,32], levels 1..K),
+// through the same tcgen05 kernel with plain 256-row tiles and the hop stage replaced by loads.  K in 1..2.
+int dss2_tc2_dense_fwd(const dss2_graph_t* g, const float* x, const float* lvl, const float* w, const float* bias, int cout, int K, int act,
+                       float p_drop, int drop_mode, const uint64_t* rng_state, uint32_t layer_uid, const uint8_t* mask, const float* res,
+                       int64_t res_stride, float* y, uint32_t* act_bits, cudaStream_t stream) {
+  Tc2Args a = {};
+  a.g = *g;
+  a.in = x;
+  a.dense_lvl = lvl;
+  a.w = w;
+  a.bias = bias;
+  a.cout = cout;
+  a.act = act;
+  if (p_drop == 0.0f) drop_mode = 0;
+  a.drop_mode = act ? drop_mode : 0;
+  a.scale = 1.0f / (float)(1.0 - (double)p_drop);
+  double thr = (1.0 - (double)p_drop) * 65536.0 + 0.5;
+  a.keep_thr16 = thr >= 65536.0 ? 65536u : (uint32_t)thr;
+  a.rng = rng_state;
+  a.layer_uid = layer_uid;
+  a.mask = mask;
+  a.res = res;
+  a.res_stride = res_stride;
+  a.out = y;
+  a.out_bits = act_bits;
+  return K == 1 ? launch_tc2_inst<MODE_FWD, 1, 2>(a, stream) : launch_tc2_inst<MODE_FWD, 2, 2>(a, stream);
+}
+int dss2_tc2_dense_bgx(const dss2_graph_t* g, const float* grad_y, const uint32_t* act_bits, float p_drop, const float* lvl, const float* w,
+                       int cout, int K, float* grad_x, cudaStream_t stream) {
+  Tc2Args a = {};
+  a.g = *g;
+  a.in = grad_y;        // [Nt,cout]; level 0 = grad_y * [y>0]/(1-p) is formed while loading, exactly as in the tiled backward
+  a.in_bits = act_bits;
+  a.dense_lvl = lvl;    // levels 1..K of that masked gradient (hop kernels)
+  a.w = w;
+  a.cout = cout;
+  a.scale = 1.0f / (float)(1.0 - (double)p_drop);
+  a.out = grad_x;
+  return K == 1 ? launch_tc2_inst<MODE_BGX, 1, 2>(a, stream) : launch_tc2_inst<MODE_BGX, 2, 2>(a, stream);
+}
 
 extern "C" int dss2_tag_fwd_tc2(const dss2_graph_t* g, const float* x, const float* w, const float* bias, int cout, int K, int act,
                                 float p_drop, int drop_mode, const uint64_t* rng_state, uint32_t layer_uid, const uint8_t* mask,
