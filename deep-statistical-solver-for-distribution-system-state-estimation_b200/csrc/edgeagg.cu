@@ -434,7 +434,8 @@ __global__ void __launch_bounds__(EA_THREADS) k_ea_fwd_g(EaArgs a, const float* 
 }
 
 // phase 2 backward: identical to the tile kernel's edge loop, with global gathers
-__global__ void __launch_bounds__(EA_THREADS, 1) k_ea_bwd_g(EaArgs a, const float* __restrict__ P, const float* __restrict__ Q,
+template <int NT>
+__global__ void __launch_bounds__(NT, 1) k_ea_bwd_g(EaArgs a, const float* __restrict__ P, const float* __restrict__ Q,
                                                             const float* __restrict__ GS) {
   extern __shared__ __align__(16) float smem[];
   const dss2_graph_t& g = a.g;
@@ -508,7 +509,7 @@ __global__ void __launch_bounds__(EA_THREADS, 1) k_ea_bwd_g(EaArgs a, const floa
   __syncthreads();
   float* part = a.partials + (size_t)blockIdx.x * a.partial_stride;
   const int n_w1 = HID * ld, off_b1 = n_w1, off_w2 = n_w1 + HID, off_b2 = off_w2 + HID * HID, total = off_b2 + HID;
-  for (int i = tid; i < total; i += EA_THREADS) {
+  for (int i = tid; i < total; i += NT) {
     int slot, ln;
     if (i < n_w1) {
       const int h = i / ld, c = i - h * ld;
@@ -527,7 +528,7 @@ __global__ void __launch_bounds__(EA_THREADS, 1) k_ea_bwd_g(EaArgs a, const floa
     }
     float sum = 0.0f;
 #pragma unroll
-    for (int w8 = 0; w8 < EA_WARPS; ++w8) sum += red[((size_t)w8 * PER + slot) * HID + ln];
+    for (int w8 = 0; w8 < NT / 32; ++w8) sum += red[((size_t)w8 * PER + slot) * HID + ln];
     part[i] = sum;
   }
 }
@@ -639,9 +640,10 @@ extern "C" int dss2_edgeagg_bwd(const dss2_graph_t* g, const float* x, int64_t x
     float* GS = Q + (size_t)Nt * HID;
     k_ea_nodes_g<<<ea_gen_grid(Nt), EA_THREADS, 0, stream>>>(a, P, Q, GS);
     DSS2_LAUNCH_CHECK();
-    const size_t red_bytes = (size_t)EA_WARPS * (3 * FP + 2 + HID) * HID * 4;
-    DSS2_CUDA(cudaFuncSetAttribute(k_ea_bwd_g, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)red_bytes));
-    k_ea_bwd_g<<<dss2_sm_count(), EA_THREADS, red_bytes, stream>>>(a, P, Q, GS);
+    constexpr int NTG = 512;   // 16 warps per SM: the row loop is latency bound (global gathers), one CTA per SM because of the per-CTA partial
+    const size_t red_bytes = (size_t)(NTG / 32) * (3 * FP + 2 + HID) * HID * 4;
+    DSS2_CUDA(cudaFuncSetAttribute(k_ea_bwd_g<NTG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)red_bytes));
+    k_ea_bwd_g<NTG><<<dss2_sm_count(), NTG, red_bytes, stream>>>(a, P, Q, GS);
     DSS2_LAUNCH_CHECK();
     return 0;
   }
