@@ -162,7 +162,7 @@ __device__ __forceinline__ TileNodes tile_nodes(const dss2_graph_t& g, int t, in
   return r;
 }
 
-template <int MODE, int K, int NB>
+template <int MODE, int K, int NB, bool DENSE>
 __global__ void __launch_bounds__(256 * NB + 32, 3 - NB) k_tag_tc2(Tc2Args a) {
   constexpr int TC2_WORKERS = 256 * NB;
   constexpr int TC2_THREADS = TC2_WORKERS + 32;
@@ -218,8 +218,8 @@ __global__ void __launch_bounds__(256 * NB + 32, 3 - NB) k_tag_tc2(Tc2Args a) {
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = *tslot;
-  const int dense_rows = a.dense_lvl ? ROWS : 0;
-  const int ntiles = a.dense_lvl ? (int)((g.num_nodes + ROWS - 1) / ROWS) : g.num_tiles;
+  constexpr int dense_rows = DENSE ? ROWS : 0;   // compile-time: the tiled instantiations carry none of the hop-free code
+  const int ntiles = DENSE ? (int)((g.num_nodes + ROWS - 1) / ROWS) : g.num_tiles;
 
   if (issuer) {
     // ===== MMA issuer warp: D[:, 0:32] += A W_plain^T, D[:, 32:64] += A W_resid^T for A in {plain, residual} of every level =====
@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(256 * NB + 32, 3 - NB) k_tag_tc2(Tc2Args a) {
       for (int k = 1; k <= K; ++k) {
         const int b = k & 1, pb = (k - 1) & 1;
         float h[HF];
-        if (live && dense_rows) {   // large-graph path: the level was computed by a hop kernel over the whole graph
+        if (DENSE && live) {   // large-graph path: the level was computed by a hop kernel over the whole graph
           const float4* src = reinterpret_cast<const float4*>(a.dense_lvl + ((size_t)(k - 1) * g.num_nodes + n) * 32 + half * HF);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(256 * NB + 32, 3 - NB) k_tag_tc2(Tc2Args a) {
             h[4 * q + 2] = v.z;
             h[4 * q + 3] = v.w;
           }
-        } else if (live) hop_thread(h, g, tp, lv_p(pb), n, n0, half);
+        } else if (!DENSE && live) hop_thread(h, g, tp, lv_p(pb), n, n0, half);
         else {
 #pragma unroll
           for (int i = 0; i < HF; ++i) h[i] = 0.0f;
@@ -818,13 +818,13 @@ int tc2_supported(const dss2_graph_t* g, int K) {
   return g && g->num_tiles > 0 && g->max_tile_nodes <= T2_MAX && K >= 1 && K <= 2 && g->ell_w && g->ell_ci;
 }
 
-template <int MODE, int K, int NB>
+template <int MODE, int K, int NB, bool DENSE = false>
 int launch_tc2_inst(const Tc2Args& a, cudaStream_t stream) {
   const size_t smem = tc2_smem(K, NB);
-  const int tiles = a.dense_lvl ? (int)((a.g.num_nodes + 128 * NB - 1) / (128 * NB)) : a.g.num_tiles;
+  const int tiles = DENSE ? (int)((a.g.num_nodes + 128 * NB - 1) / (128 * NB)) : a.g.num_tiles;
   const int grid = max(1, min(tiles, (3 - NB) * dss2_sm_count()));
-  DSS2_CUDA(cudaFuncSetAttribute(k_tag_tc2<MODE, K, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_tag_tc2<MODE, K, NB><<<grid, 256 * NB + 32, smem, stream>>>(a);
+  DSS2_CUDA(cudaFuncSetAttribute(k_tag_tc2<MODE, K, NB, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_tag_tc2<MODE, K, NB, DENSE><<<grid, 256 * NB + 32, smem, stream>>>(a);
   DSS2_LAUNCH_CHECK();
   return 0;
 }
@@ -864,7 +864,7 @@ int dss2_tc2_dense_fwd(const dss2_graph_t* g, const float* x, const float* lvl, 
   a.res_stride = res_stride;
   a.out = y;
   a.out_bits = act_bits;
-  return K == 1 ? launch_tc2_inst<MODE_FWD, 1, 2>(a, stream) : launch_tc2_inst<MODE_FWD, 2, 2>(a, stream);
+  return K == 1 ? launch_tc2_inst<MODE_FWD, 1, 2, true>(a, stream) : launch_tc2_inst<MODE_FWD, 2, 2, true>(a, stream);
 }
 int dss2_tc2_dense_bgx(const dss2_graph_t* g, const float* grad_y, const uint32_t* act_bits, float p_drop, const float* lvl, const float* w,
                        int cout, int K, float* grad_x, cudaStream_t stream) {
@@ -877,7 +877,7 @@ int dss2_tc2_dense_bgx(const dss2_graph_t* g, const float* grad_y, const uint32_
   a.cout = cout;
   a.scale = 1.0f / (float)(1.0 - (double)p_drop);
   a.out = grad_x;
-  return K == 1 ? launch_tc2_inst<MODE_BGX, 1, 2>(a, stream) : launch_tc2_inst<MODE_BGX, 2, 2>(a, stream);
+  return K == 1 ? launch_tc2_inst<MODE_BGX, 1, 2, true>(a, stream) : launch_tc2_inst<MODE_BGX, 2, 2, true>(a, stream);
 }
 
 extern "C" int dss2_tag_fwd_tc2(const dss2_graph_t* g, const float* x, const float* w, const float* bias, int cout, int K, int act,
