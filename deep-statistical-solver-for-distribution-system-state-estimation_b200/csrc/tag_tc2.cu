@@ -52,22 +52,6 @@ __device__ __forceinline__ char* align1024(char* p) {
   return p + (((a + 1023u) & ~1023u) - a);
 }
 
-// 32 Bernoulli(keep) decisions for one node row (same generator as tag_tc.cu)
-__device__ __forceinline__ uint32_t keep_word(uint2 key, uint32_t tile, uint32_t row, uint32_t step_lo, uint32_t thr16) {
-  uint32_t word = 0;
-#pragma unroll
-  for (uint32_t q = 0; q < 4; ++q) {
-    const uint4 r = philox4x32_10(make_uint4(tile, row, q, step_lo), key);
-    const uint32_t u[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-    for (uint32_t i = 0; i < 4; ++i) {
-      word |= ((u[i] & 0xffffu) < thr16 ? 1u : 0u) << (q * 8 + 2 * i);
-      word |= ((u[i] >> 16) < thr16 ? 1u : 0u) << (q * 8 + 2 * i + 1);
-    }
-  }
-  return word;
-}
-
 // Thread mapping of the layer kernel: 256 threads per tile, thread = (row, half): row = tid & 127 (= its TMEM lane), half = tid >> 7
 // owns features [16*half, 16*half + 16).  Two threads per row double the number of busy warps on grids whose tile holds a single
 // graph (Oberrhein: 70 of 128 rows) and halve every per-thread dependency chain.
