@@ -231,6 +231,12 @@ def main():
             gref, P(x_l), wp, bp, 32, sp.K, 1, sp.p_drop, 1, P(trainer.step_state), 3, None, None, 0, P(y_l), P(bits_l), st_()), "fwd"),
             nt * (2 * 128 + 4) + 4 * (nt + 1) + 16 * et, "x in, y out, sign word, CSR")
 
+    # the fused loss (2 kernels: reduction pass + gradient pass), on the trainer's own buffers
+    kernels["k_wls<false>+k_wls<true> (branch flows + WLS loss, forward and backward)"] = (lambda: _lib.check(lib.dss2_wls_fwd_bwd(
+        gref, P(trainer.batch["x"]), 11, P(trainer.batch["edge_attr"]), 13, P(bufs["outs"][-1]), P(trainer.stats), REG["lam_v"], REG["lam_p"],
+        REG["lam_pf"], REG["lam_reg"], P(trainer.batch["vminmax"]), 1, P(trainer.loss), None, P(trainer.grad_out), P(trainer.wls_ws),
+        trainer.wls_ws.numel(), st_()), "wls"), 2 * (60 * nt + 68 * et), "x row 44 + out 8 + grad_out 8 per bus, edge_attr row 52 + edge_index 16 per branch, two passes")
+
     def time_kernel(fn, reps=30):
         flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # 256 MB > 126 MB L2
         durs = []
