@@ -273,6 +273,18 @@ def main():
                 "note": "layer kernels are bound by the per-tile dependency chain (shared-memory gathers, barriers, tcgen05 issue), not by HBM: "
                         "see DESIGN.md section 4 and profiles/",
                 "all_layer_kernels": timed}
+    # whole-step view with SURVEY.md 8(d)'s per-layer algorithmic bytes (topology counted as 0: per-topology template)
+    hid, fn = 32, sp.fn
+    step_bytes = 2 * (60 * nt + 68 * et)                                     # loss, two passes
+    for s_ in range(sp.L):
+        cin0 = 44 if s_ == 0 else 4 * fn                                     # EdgeAggregation reads the 11-wide x rows in sub-net 0
+        step_bytes += (cin0 * nt + 52 * et + 16 * et + 4 * hid * nt) + (cin0 * nt + 52 * et + 16 * et + 4 * hid * nt + (4 * fn * nt if s_ else 0))
+        for l_ in range(sp.n_layers):
+            cout_ = (sp.dim_out if s_ == sp.L - 1 else fn) if l_ == sp.n_layers - 1 else hid
+            step_bytes += 4 * nt * (hid + cout_) + 4 * nt * (2 * hid + cout_)  # TAG forward + recompute-style backward
+    roofline["step"] = {"algorithmic_bytes_per_step": step_bytes, "achieved": step_bytes / (ms_total / K / 1e3) / 1e9, "unit": "GB/s",
+                        "frac": step_bytes / (ms_total / K / 1e3) / 1e9 / peak,
+                        "definition": "SURVEY.md 8(d): loss 2x(60 Nt + 68 Et); EdgeAggregation fwd+bwd; TAG 4 Nt (Cin+Cout) fwd + 4 Nt (2 Cin+Cout) bwd per layer"}
 
     # ---- end to end through the host-buffer API: pinned host scenarios -> H2D -> step -> D2H loss, all inside the timed region ----
     e2e = None
