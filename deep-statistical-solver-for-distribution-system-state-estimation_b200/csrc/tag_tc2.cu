@@ -271,10 +271,12 @@ __global__ void __launch_bounds__(256 * NB + 32, 3 - NB) k_tag_tc2(Tc2Args a) {
         for (int c = 0; c < HF; ++c) xr[c] = ((word >> c) & 1u) ? xr[c] * a.scale : 0.0f;
       }
     };
-    auto publish = [&](int b) {   // my part of buffer b is written: make it visible to the tensor core, tell the issuer, meet the workers
+    // my part of buffer b is written: make it visible to the tensor core, tell the issuer and - when the next stage gathers other
+    // threads' rows - meet the workers (after the last level nobody gathers: the MMAs are the only readers, no barrier needed)
+    auto publish = [&](int b, bool meet = true) {
       fence_proxy_async();
       tc::mbar_arrive(&full[b]);
-      named_bar_sync(1, TC2_WORKERS);
+      if (meet) named_bar_sync(1, TC2_WORKERS);
     };
 
     TileNodes cur = tile_nodes(g, blockIdx.x, dense_rows);
@@ -318,7 +320,7 @@ __global__ void __launch_bounds__(256 * NB + 32, 3 - NB) k_tag_tc2(Tc2Args a) {
           par[b] ^= 1u;
         }
         store_half_sw128(h, lv_p(b), lv_l(b), row, half);
-        publish(b);
+        publish(b, k < K);
         // hop-level spill for the weight-gradient pass.  Its stores drain during the next hop; the fence of the next publish still
         // waits for their tail (measured: cheaper than deferring all spills to the tile end, where they pile up with the output
         // stores in front of the next tile's first fence: 88 vs 103 us)
