@@ -384,8 +384,14 @@ __global__ void __launch_bounds__(OR_THREADS) k_outer_reduce(int64_t num_rows, c
                                                              const float* __restrict__ B, int64_t bs, int cb, float* partials,
                                                              int64_t partial_stride, int64_t w_off, int64_t b_off) {
   __shared__ float sA[OR_ROWS][33], sB[OR_ROWS][33];
+  __shared__ float s_part[OR_THREADS];
   const int tid = threadIdx.x;
   const int nout = ca * (cb + 1);
+  // few outputs (a GATv2 layer has 72): several threads share one output and take the rows of a chunk round robin (`slices`), combined
+  // in a fixed order at the end; many outputs (the head: up to 1056): every thread owns up to 5 outputs and walks all rows
+  const int slices = nout <= OR_THREADS ? OR_THREADS / nout : 1;
+  const bool sliced = nout <= OR_THREADS;
+  const int my_o = tid % nout, my_sl = tid / nout;
   float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};   // ca, cb <= 32 -> at most 1056 outputs over 256 threads
   const int64_t per = (num_rows + gridDim.x - 1) / gridDim.x;
   const int64_t r0 = blockIdx.x * per, r1 = min(num_rows, r0 + per);
@@ -394,23 +400,48 @@ __global__ void __launch_bounds__(OR_THREADS) k_outer_reduce(int64_t num_rows, c
     for (int idx = tid; idx < rows * ca; idx += OR_THREADS) sA[idx / ca][idx % ca] = A[(base + idx / ca) * as + idx % ca];
     for (int idx = tid; idx < rows * cb; idx += OR_THREADS) sB[idx / cb][idx % cb] = B[(base + idx / cb) * bs + idx % cb];
     __syncthreads();
-#pragma unroll
-    for (int q = 0; q < 5; ++q) {
-      const int o = tid + q * OR_THREADS;
-      if (o < nout) {
-        const int c = o / (cb + 1), i = o % (cb + 1);
-        float s = acc[q];
+    if (sliced) {
+      if (my_sl < slices) {
+        const int c = my_o / (cb + 1), i = my_o % (cb + 1);
+        float s = acc[0];
         if (i < cb) {
-          for (int r = 0; r < rows; ++r) s = fmaf(sA[r][c], sB[r][i], s);
+          for (int r = my_sl; r < rows; r += slices) s = fmaf(sA[r][c], sB[r][i], s);
         } else {
-          for (int r = 0; r < rows; ++r) s += sA[r][c];
+          for (int r = my_sl; r < rows; r += slices) s += sA[r][c];
         }
-        acc[q] = s;
+        acc[0] = s;
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 5; ++q) {
+        const int o = tid + q * OR_THREADS;
+        if (o < nout) {
+          const int c = o / (cb + 1), i = o % (cb + 1);
+          float s = acc[q];
+          if (i < cb) {
+            for (int r = 0; r < rows; ++r) s = fmaf(sA[r][c], sB[r][i], s);
+          } else {
+            for (int r = 0; r < rows; ++r) s += sA[r][c];
+          }
+          acc[q] = s;
+        }
       }
     }
     __syncthreads();
   }
   float* part = partials + (size_t)blockIdx.x * partial_stride;
+  if (sliced) {
+    s_part[tid] = acc[0];
+    __syncthreads();
+    if (tid < nout) {
+      float s = 0.0f;
+      for (int sl = 0; sl < slices; ++sl) s += s_part[sl * nout + tid];
+      const int c = tid / (cb + 1), i = tid % (cb + 1);
+      if (i < cb) part[w_off + (int64_t)c * cb + i] = s;
+      else part[b_off + c] = s;
+    }
+    return;
+  }
 #pragma unroll
   for (int q = 0; q < 5; ++q) {
     const int o = tid + q * OR_THREADS;
