@@ -508,6 +508,60 @@ __global__ void __launch_bounds__(128) k_mlp2_bwd(MlpArgs a) {
   }
 }
 
+// the sizes of the script (dss2_run.py:73-76: 8 -> 32 -> 2) fully unrolled: rows in registers instead of runtime-indexed local arrays
+template <int DIN, int DMID, int DOUT>
+__global__ void __launch_bounds__(128) k_mlp2_fwd_fixed(MlpArgs a) {
+  __shared__ float w1[DMID * DIN], w2[DOUT * DMID], b1[DMID], b2[DOUT];
+  for (int i = threadIdx.x; i < DMID * DIN; i += blockDim.x) w1[i] = a.w1[i];
+  for (int i = threadIdx.x; i < DOUT * DMID; i += blockDim.x) w2[i] = a.w2[i];
+  if (threadIdx.x < DMID) b1[threadIdx.x] = a.b1[threadIdx.x];
+  if (threadIdx.x < DOUT) b2[threadIdx.x] = a.b2[threadIdx.x];
+  __syncthreads();
+  for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < a.n; n += (int64_t)gridDim.x * blockDim.x) {
+    float x[DIN], z[DOUT];
+#pragma unroll
+    for (int i = 0; i < DIN; ++i) x[i] = a.x[n * DIN + i];
+#pragma unroll
+    for (int o = 0; o < DOUT; ++o) z[o] = b2[o];
+#pragma unroll
+    for (int c = 0; c < DMID; ++c) {
+      float h = b1[c];
+#pragma unroll
+      for (int i = 0; i < DIN; ++i) h = fmaf(w1[c * DIN + i], x[i], h);
+      a.h[n * DMID + c] = h;
+#pragma unroll
+      for (int o = 0; o < DOUT; ++o) z[o] = fmaf(w2[o * DMID + c], h, z[o]);
+    }
+#pragma unroll
+    for (int o = 0; o < DOUT; ++o) a.z[n * DOUT + o] = z[o];
+  }
+}
+template <int DIN, int DMID, int DOUT>
+__global__ void __launch_bounds__(128) k_mlp2_bwd_fixed(MlpArgs a) {
+  __shared__ float w1[DMID * DIN], w2[DOUT * DMID];
+  for (int i = threadIdx.x; i < DMID * DIN; i += blockDim.x) w1[i] = a.w1[i];
+  for (int i = threadIdx.x; i < DOUT * DMID; i += blockDim.x) w2[i] = a.w2[i];
+  __syncthreads();
+  for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < a.n; n += (int64_t)gridDim.x * blockDim.x) {
+    float gz[DOUT], gx[DIN];
+#pragma unroll
+    for (int o = 0; o < DOUT; ++o) gz[o] = a.gz[n * DOUT + o];
+#pragma unroll
+    for (int i = 0; i < DIN; ++i) gx[i] = 0.0f;
+#pragma unroll
+    for (int c = 0; c < DMID; ++c) {
+      float gh = 0.0f;
+#pragma unroll
+      for (int o = 0; o < DOUT; ++o) gh = fmaf(w2[o * DMID + c], gz[o], gh);
+      a.gh[n * DMID + c] = gh;
+#pragma unroll
+      for (int i = 0; i < DIN; ++i) gx[i] = fmaf(w1[c * DIN + i], gh, gx[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < DIN; ++i) a.gx[n * DIN + i] = gx[i];
+  }
+}
+
 int grid_for(int64_t n, int threads) { return (int)max((int64_t)1, min((int64_t)dss2_sm_count() * 8, (n + threads - 1) / threads)); }
 
 int fill_args(const char* who, GatArgs& a, const dss2_graph_t* g, const float* x, int64_t xs, const float* ea, int64_t eas, int fe,
@@ -614,7 +668,8 @@ extern "C" int dss2_mlp2_fwd(int64_t num_nodes, const float* x, int din, const f
   a.dout = dout;
   a.h = h;
   a.z = z;
-  k_mlp2_fwd<<<grid_for(num_nodes, 128), 128, 0, stream>>>(a);
+  if (din == 8 && dmid == 32 && dout == 2) k_mlp2_fwd_fixed<8, 32, 2><<<grid_for(num_nodes, 128), 128, 0, stream>>>(a);
+  else k_mlp2_fwd<<<grid_for(num_nodes, 128), 128, 0, stream>>>(a);
   DSS2_LAUNCH_CHECK();
   return 0;
 }
@@ -640,7 +695,8 @@ extern "C" int dss2_mlp2_bwd(int64_t num_nodes, const float* x, int din, const f
   a.gz = grad_z;
   a.gh = grad_h_ws;
   a.gx = grad_x;
-  k_mlp2_bwd<<<grid_for(num_nodes, 128), 128, 0, stream>>>(a);
+  if (din == 8 && dmid == 32 && dout == 2) k_mlp2_bwd_fixed<8, 32, 2><<<grid_for(num_nodes, 128), 128, 0, stream>>>(a);
+  else k_mlp2_bwd<<<grid_for(num_nodes, 128), 128, 0, stream>>>(a);
   DSS2_LAUNCH_CHECK();
   const int np = dss2_num_partials();
   const int64_t o_w1 = 0, o_b1 = (int64_t)dmid * din, o_w2 = o_b1 + dmid, o_b2 = o_w2 + (int64_t)dout * dmid;
