@@ -277,6 +277,50 @@ def init_gat_state_dict(dim_feat=8, dim_dense=32, dim_out=2, num_layers=8, edge_
 
 
 # --------------------------------------------------------------------------------------------
+# GINE_DSSE (networks.py:71-111): 7 x (GINEConv(nn = ONE Linear(8, 8) shared by all layers, eps, edge_dim=6) + LeakyReLU(0.01)),
+# Linear(8, 32), Linear(32, 2).  SURVEY.md 8f-1.
+# --------------------------------------------------------------------------------------------
+
+
+def gine_dsse_forward(sd, x, edge_index, edge_attr, num_layers=8):
+    """GINE_DSSE.forward (networks.py:110-111) from a reference-named state_dict: `nn.*` (the shared Linear), per layer
+    `model.module_{2l}.lin.*` (edge Linear, with bias) and the buffer `model.module_{2l}.eps`; one-way edge list, no self-loop handling."""
+    n = x.size(0)
+    src, dst = edge_index[0], edge_index[1]
+    h = x
+    for l in range(num_layers - 1):
+        p = f"model.module_{2 * l}."
+        eps = sd[p + "eps"].to(x.dtype) if (p + "eps") in sd else torch.zeros(1, dtype=x.dtype)
+        msg = torch.relu(h[src] + edge_attr @ sd[p + "lin.weight"].t() + sd[p + "lin.bias"])
+        agg = segment_sum(msg, dst, n)
+        h = (agg + (1 + eps) * h) @ sd["nn.weight"].t() + sd["nn.bias"]
+        h = torch.nn.functional.leaky_relu(h, 0.01)
+    i = 2 * (num_layers - 1)
+    h = h @ sd[f"model.module_{i}.weight"].t() + sd[f"model.module_{i}.bias"]
+    return h @ sd[f"model.module_{i + 1}.weight"].t() + sd[f"model.module_{i + 1}.bias"]
+
+
+def init_gine_state_dict(dim_feat=8, dim_dense=32, dim_out=2, num_layers=8, edge_dim=6, seed=0, dtype=torch.float32):
+    """Random GINE_DSSE parameters under the names named_parameters() reports (shared `nn.*` once)."""
+    g = torch.Generator().manual_seed(seed)
+
+    def u(*shape, bound):
+        return ((torch.rand(*shape, generator=g, dtype=torch.float64) * 2 - 1) * bound).to(dtype)
+
+    sd = {"nn.weight": u(dim_feat, dim_feat, bound=0.45), "nn.bias": u(dim_feat, bound=0.1)}
+    for l in range(num_layers - 1):
+        p = f"model.module_{2 * l}."
+        sd[p + "lin.weight"] = u(dim_feat, edge_dim, bound=0.4)
+        sd[p + "lin.bias"] = u(dim_feat, bound=0.1)
+    i = 2 * (num_layers - 1)
+    sd[f"model.module_{i}.weight"] = u(dim_dense, dim_feat, bound=1.0 / math.sqrt(dim_feat))
+    sd[f"model.module_{i}.bias"] = u(dim_dense, bound=1.0 / math.sqrt(dim_feat))
+    sd[f"model.module_{i + 1}.weight"] = u(dim_out, dim_dense, bound=1.0 / math.sqrt(dim_dense))
+    sd[f"model.module_{i + 1}.bias"] = u(dim_out, bound=1.0 / math.sqrt(dim_dense))
+    return sd
+
+
+# --------------------------------------------------------------------------------------------
 # physics: branch flows (data.py:328-390) and the WLS loss (data.py:393-459)
 # --------------------------------------------------------------------------------------------
 

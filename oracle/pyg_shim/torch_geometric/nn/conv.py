@@ -2,8 +2,8 @@
 
 Implemented from PyG's published semantics: MessagePassing(aggr='add', flow='source_to_target'),
 gcn_norm(add_self_loops=False), TAGConv, and GATv2Conv (the as-shipped default model of
-dss2_run.py:86).  The other conv classes named by reference networks.py:7 (GCN2Conv, FAConv, GINEConv,
-GCNConv, ChebConv) exist only as names so that the reference module imports.
+dss2_run.py:86).  The other conv classes named by reference networks.py:7 (GCN2Conv, FAConv,
+GCNConv, ChebConv) exist only as names so that the reference module imports; GINEConv (networks.py:100) is restated too.
 """
 import inspect
 
@@ -118,7 +118,39 @@ def _outside_hot_path(name):
 
 GCN2Conv = _outside_hot_path("GCN2Conv")
 FAConv = _outside_hot_path("FAConv")
-GINEConv = _outside_hot_path("GINEConv")
+
+class GINEConv(MessagePassing):
+    """PyG GINEConv(nn, eps=0., train_eps=False, edge_dim=None), as used at reference networks.py:100:
+      out_i = nn( (1 + eps) * x_i + sum_{j -> i} relu(x_j + lin(a_ji)) ), lin = Linear(edge_dim, in_channels of nn) (with bias),
+      eps a buffer (train_eps=False) or a parameter, initialised to `eps`."""
+
+    def __init__(self, nn, eps=0.0, train_eps=False, edge_dim=None, **kwargs):
+        kwargs.setdefault("aggr", "add")
+        super().__init__(**kwargs)
+        self.nn = nn
+        self.initial_eps = eps
+        if train_eps:
+            self.eps = torch.nn.Parameter(torch.empty(1))
+        else:
+            self.register_buffer("eps", torch.empty(1))
+        if edge_dim is not None:
+            first = nn[0] if isinstance(nn, torch.nn.Sequential) else nn
+            in_channels = first.in_features if hasattr(first, "in_features") else first.in_channels
+            self.lin = torch.nn.Linear(edge_dim, in_channels)
+        else:
+            self.lin = None
+        self.eps.data.fill_(self.initial_eps)
+
+    def forward(self, x, edge_index, edge_attr=None):
+        out = self.propagate(edge_index, x=x, edge_attr=edge_attr)
+        out = out + (1 + self.eps) * x
+        return self.nn(out)
+
+    def message(self, x_j, edge_attr):
+        if self.lin is not None:
+            edge_attr = self.lin(edge_attr)
+        return (x_j + edge_attr).relu()
+
 GCNConv = _outside_hot_path("GCNConv")
 ChebConv = _outside_hot_path("ChebConv")
 

@@ -96,3 +96,14 @@ def oracle_gat_run(orc, num_layers, sd, z, dtype):
     loss = orc.wls_loss(x, ea, out, *st, ei, REG_COEFS)
     loss.backward()
     return out.detach(), loss.detach(), {k: v.grad for k, v in p.items()}
+
+
+def oracle_gine_run(orc, num_layers, sd, z, dtype):
+    """Oracle GINE_DSSE forward + WLS loss + autograd on the inputs of a golden file."""
+    x, ea, ei = torch.from_numpy(z["x"]).to(dtype), torch.from_numpy(z["edge_attr"]).to(dtype), torch.from_numpy(z["edge_index"])
+    st = [torch.from_numpy(z[k]).to(dtype) for k in ("x_mean", "x_std", "edge_mean", "edge_std")]
+    p = {k: v.to(dtype).clone().requires_grad_(True) for k, v in sd.items()}
+    out = orc.gine_dsse_forward(p, x[:, :8], ei, ea[:, :6], num_layers)
+    loss = orc.wls_loss(x, ea, out, *st, ei, REG_COEFS)
+    loss.backward()
+    return out.detach(), loss.detach(), {k: v.grad for k, v in p.items()}

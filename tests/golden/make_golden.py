@@ -144,6 +144,32 @@ def run_gat(tag, batch, stats, sd_seed, num_layers=8):
     print(tag, "out", tuple(out.shape), "loss", res["loss"])
 
 
+def run_gine(tag, batch, stats, sd_seed, num_layers=8):
+    """Reference GINE_DSSE forward + gsp_wls_edge + backward on `batch` (parameters stored under their named_parameters() names)."""
+    sd = orc.init_gine_state_dict(num_layers=num_layers, seed=sd_seed)
+    model = ref_net.GINE_DSSE(dim_feat=8, dim_dense=32, dim_out=2, num_layers=num_layers, edge_dim=6)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            p.copy_(sd[name])
+    model.train()
+    out = model(batch.x[:, :8], batch.edge_index, batch.edge_attr[:, :6])
+    res = {"x": batch.x.numpy(), "edge_index": batch.edge_index.numpy(), "edge_attr": batch.edge_attr.numpy(), "ptr": batch.ptr.numpy(),
+           "out": out.detach().numpy().copy(), "num_layers": num_layers, "sd_seed": sd_seed,
+           "x_mean": stats[0].numpy(), "x_std": stats[1].numpy(), "edge_mean": stats[2].numpy(), "edge_std": stats[3].numpy(),
+           "state_dict_keys": np.array(list(model.state_dict().keys()))}
+    got = {}
+    out.register_hook(lambda g_: got.__setitem__("g", g_.clone()))
+    loss = ref_loss(batch, out, stats)
+    loss.backward()
+    res["loss"] = np.array(loss.item())
+    res["grad_out"] = got["g"].numpy().copy()
+    for name, p in model.named_parameters():
+        res["grad." + name] = p.grad.detach().numpy().copy()
+        res["param." + name] = p.detach().numpy().copy()
+    np.savez_compressed(os.path.join(HERE, f"golden_model_{tag}.npz"), **res)
+    print(tag, "out", tuple(out.shape), "loss", res["loss"])
+
+
 def main():
     torch.set_num_threads(1)
     fix = np.load(os.path.join(HERE, "cigre14_scenarios.npz"), allow_pickle=False)
@@ -191,6 +217,7 @@ def main():
     run_model("skipmpn_cigre", "SkipMPN", skipmpn, Batch.from_data_list(ds[40:42]), stats, sd_seed=4, torch_seed=14)
 
     run_gat("gat_cigre", Batch.from_data_list(ds[50:56]), stats, sd_seed=6)
+    run_gine("gine_cigre", Batch.from_data_list(ds[60:65]), stats, sd_seed=8)
 
     # ---- Oberrhein: synthetic scenarios from the product generator, reference model + loss on top ----
     grid = synth.load_grid("ober_sub")
@@ -200,6 +227,7 @@ def main():
     ostats = (store.x_mean, store.x_std, store.edge_mean, store.edge_std)
     run_model("skippfn_ober", "SkipPFN", dict(default, n_gnn_layers=4, L=2), ob, ostats, sd_seed=5, torch_seed=15)
     run_gat("gat_ober", ob, ostats, sd_seed=7)
+    run_gine("gine_ober", ob, ostats, sd_seed=9)
     # a far-from-solution output so that all three soft-constraint penalties are active
     torch.manual_seed(99)
     wild = torch.stack([torch.randn(ob.x.shape[0]) * 3.0, torch.randn(ob.x.shape[0]) * 0.8], 1).requires_grad_(True)

@@ -144,3 +144,16 @@ def test_gat_dsse_forward_backward_vs_reference(tag):
     assert_fp32_parity(loss32, z["loss"], loss64, "loss")
     for name, g in grads.items():
         assert_fp32_parity(g32[name], g, g64[name], name)
+
+
+@pytest.mark.parametrize("tag", ["gine_cigre", "gine_ober"])
+def test_gine_dsse_forward_backward_vs_reference(tag):
+    """Oracle GINE_DSSE (7 GINEConv layers sharing one Linear + 2 Linear) + loss + autograd == the reference's GINE_DSSE run over the shim."""
+    from conftest import golden_gat, oracle_gine_run
+    nl, sd, grads, z = golden_gat(tag)
+    out32, loss32, g32 = oracle_gine_run(orc, nl, sd, z, torch.float32)
+    out64, loss64, g64 = oracle_gine_run(orc, nl, sd, z, torch.float64)
+    assert_fp32_parity(out32, z["out"], out64, "out")
+    assert_fp32_parity(loss32, z["loss"], loss64, "loss")
+    for name, g in grads.items():
+        assert_fp32_parity(g32[name], g, g64[name], name)
