@@ -562,6 +562,194 @@ __global__ void __launch_bounds__(128) k_mlp2_bwd_fixed(MlpArgs a) {
   }
 }
 
+// -------------------------------------------------------------------------------------------------
+// GINE_DSSE layer (networks.py:71-111, PyG GINEConv): out_i = nn((1 + eps) x_i + sum_{j -> i} relu(x_j + lin(a_ji))), LeakyReLU.
+// `nn` is ONE Linear(8, 8) shared by all layers of the model, `lin` = Linear(edge_dim, 8) per layer.  Same thread-per-bus structure
+// as the GATv2 kernels: one-way edge list, in-edges = CSR entries without the reversed bit, out-edges = entries with it.
+// -------------------------------------------------------------------------------------------------
+constexpr int GINE_NODE_WS = 24;   // per bus: g[8] (gated output gradient), gh[8] (= W_nn^T g), h[8] (input of nn)
+struct GineW {
+  float wn[GC * GC], bn[GC], we[GC * GFE], be[GC];
+};
+struct GineArgs {
+  dss2_graph_t g;
+  const float* x;
+  int64_t xs;
+  const float* ea;
+  int64_t eas;
+  int fe;
+  const float *wn, *bn, *we, *be;
+  float eps, slope_act;
+  int act;
+  float* y;
+  const float* yout;
+  const float* gy;
+  float* ws;
+  float* gx;
+  float* partials;
+  int64_t partial_stride;
+};
+__device__ __forceinline__ void gine_load_weights(GineW& w, const GineArgs& a) {
+  for (int i = threadIdx.x; i < GC * GC; i += blockDim.x) w.wn[i] = a.wn[i];
+  for (int i = threadIdx.x; i < GC * GFE; i += blockDim.x) {
+    const int c = i / GFE, f = i % GFE;
+    w.we[i] = f < a.fe ? a.we[c * a.fe + f] : 0.0f;
+  }
+  if (threadIdx.x < GC) {
+    w.bn[threadIdx.x] = a.bn[threadIdx.x];
+    w.be[threadIdx.x] = a.be[threadIdx.x];
+  }
+}
+__device__ __forceinline__ void gine_load_x(const GineArgs& a, int64_t n, float (&v)[GC]) {
+  const float* p = a.x + n * a.xs;
+#pragma unroll
+  for (int i = 0; i < GC; ++i) v[i] = p[i];
+}
+// pre = x_src + (W_e a + b_e)
+__device__ __forceinline__ void gine_pre(const GineArgs& a, const GineW& w, const float (&xs_)[GC], uint32_t id, float (&at)[GFE], float (&pre)[GC]) {
+  const float* p = a.ea + (int64_t)(id & 0x7fffffffu) * a.eas;
+#pragma unroll
+  for (int f = 0; f < GFE; ++f) at[f] = f < a.fe ? p[f] : 0.0f;
+#pragma unroll
+  for (int c = 0; c < GC; ++c) {
+    float e = 0.0f;
+#pragma unroll
+    for (int f = 0; f < GFE; ++f) e = fmaf(w.we[c * GFE + f], at[f], e);
+    pre[c] = xs_[c] + (e + w.be[c]);
+  }
+}
+// h = (1 + eps) x_i + sum over the in-edges of relu(pre)
+__device__ __forceinline__ void gine_h(const GineArgs& a, const GineW& w, int64_t i, const float (&xi)[GC], float (&h)[GC]) {
+  const dss2_graph_t& g = a.g;
+  float agg[GC];
+#pragma unroll
+  for (int c = 0; c < GC; ++c) agg[c] = 0.0f;
+  for (int z = g.rowptr[i]; z < g.rowptr[i + 1]; ++z) {
+    const uint32_t id = g.eid[z];
+    if (id >> 31) continue;
+    float xj[GC], at[GFE], pre[GC];
+    gine_load_x(a, g.col[z], xj);
+    gine_pre(a, w, xj, id, at, pre);
+#pragma unroll
+    for (int c = 0; c < GC; ++c) agg[c] += fmaxf(pre[c], 0.0f);
+  }
+#pragma unroll
+  for (int c = 0; c < GC; ++c) h[c] = agg[c] + (1.0f + a.eps) * xi[c];
+}
+__global__ void __launch_bounds__(GAT_THREADS) k_gine_fwd(GineArgs a) {
+  __shared__ GineW w;
+  gine_load_weights(w, a);
+  __syncthreads();
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.g.num_nodes; i += (int64_t)gridDim.x * blockDim.x) {
+    float xi[GC], h[GC], out[GC];
+    gine_load_x(a, i, xi);
+    gine_h(a, w, i, xi, h);
+    lin8(w.wn, w.bn, h, out);
+#pragma unroll
+    for (int c = 0; c < GC; ++c) out[c] = (a.act && !(out[c] > 0.0f)) ? out[c] * a.slope_act : out[c];
+    float4* dst = reinterpret_cast<float4*>(a.y + i * GC);
+    dst[0] = make_float4(out[0], out[1], out[2], out[3]);
+    dst[1] = make_float4(out[4], out[5], out[6], out[7]);
+  }
+}
+// backward pass A: per bus g = grad_y * gate, gh = W_nn^T g, h (recomputed)
+__global__ void __launch_bounds__(GAT_THREADS) k_gine_bwd_a(GineArgs a) {
+  __shared__ GineW w;
+  gine_load_weights(w, a);
+  __syncthreads();
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.g.num_nodes; i += (int64_t)gridDim.x * blockDim.x) {
+    float xi[GC], h[GC], G[GC];
+    gine_load_x(a, i, xi);
+    gine_h(a, w, i, xi, h);
+    float* o = a.ws + i * GINE_NODE_WS;
+#pragma unroll
+    for (int c = 0; c < GC; ++c) {
+      const float gate = (a.act && !(a.yout[i * GC + c] > 0.0f)) ? a.slope_act : 1.0f;
+      G[c] = a.gy[i * GC + c] * gate;
+      o[c] = G[c];
+      o[16 + c] = h[c];
+    }
+#pragma unroll
+    for (int k = 0; k < GC; ++k) {
+      float s = 0.0f;
+#pragma unroll
+      for (int c = 0; c < GC; ++c) s = fmaf(w.wn[c * GC + k], G[c], s);
+      o[8 + k] = s;
+    }
+  }
+}
+// backward pass B: thread = bus n: d W_e / d b_e of its in-edges, d x[n] from its own term and its out-edges.
+// partial layout per CTA at a.partials: [lin.weight 8 x fe | lin.bias 8]
+__global__ void __launch_bounds__(GAT_THREADS) k_gine_bwd_b(GineArgs a) {
+  __shared__ GineW w;
+  __shared__ float red[GAT_THREADS / 32][GC * GFE + GC];
+  gine_load_weights(w, a);
+  __syncthreads();
+  const dss2_graph_t& g = a.g;
+  float dWe[GC * GFE], dbe[GC];
+#pragma unroll
+  for (int i = 0; i < GC * GFE; ++i) dWe[i] = 0.0f;
+#pragma unroll
+  for (int c = 0; c < GC; ++c) dbe[c] = 0.0f;
+  for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < g.num_nodes; n += (int64_t)gridDim.x * blockDim.x) {
+    float xn[GC], ghn[GC], dx[GC];
+    gine_load_x(a, n, xn);
+    const float* sn = a.ws + n * GINE_NODE_WS;
+#pragma unroll
+    for (int c = 0; c < GC; ++c) {
+      ghn[c] = sn[8 + c];
+      dx[c] = (1.0f + a.eps) * ghn[c];
+    }
+    for (int z = g.rowptr[n]; z < g.rowptr[n + 1]; ++z) {
+      const uint32_t id = g.eid[z];
+      const int o = g.col[z];
+      float at[GFE], pre[GC];
+      if (!(id >> 31)) {   // in-edge (o -> n)
+        float xo[GC];
+        gine_load_x(a, o, xo);
+        gine_pre(a, w, xo, id, at, pre);
+#pragma unroll
+        for (int c = 0; c < GC; ++c) {
+          const float t = pre[c] > 0.0f ? ghn[c] : 0.0f;
+          dbe[c] += t;
+#pragma unroll
+          for (int f = 0; f < GFE; ++f) dWe[c * GFE + f] = fmaf(t, at[f], dWe[c * GFE + f]);
+        }
+      } else {             // out-edge (n -> o)
+        gine_pre(a, w, xn, id, at, pre);
+        const float* so = a.ws + (int64_t)o * GINE_NODE_WS;
+#pragma unroll
+        for (int c = 0; c < GC; ++c) dx[c] += pre[c] > 0.0f ? so[8 + c] : 0.0f;
+      }
+    }
+    if (a.gx) {
+      float4* dst = reinterpret_cast<float4*>(a.gx + n * GC);
+      dst[0] = make_float4(dx[0], dx[1], dx[2], dx[3]);
+      dst[1] = make_float4(dx[4], dx[5], dx[6], dx[7]);
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < GC * GFE; ++i) {
+    const float v = warp_sum(dWe[i]);
+    if (lane == 0) red[warp][i] = v;
+  }
+#pragma unroll
+  for (int c = 0; c < GC; ++c) {
+    const float v = warp_sum(dbe[c]);
+    if (lane == 0) red[warp][GC * GFE + c] = v;
+  }
+  __syncthreads();
+  float* part = a.partials + (size_t)blockIdx.x * a.partial_stride;
+  for (int i = threadIdx.x; i < GC * a.fe + GC; i += blockDim.x) {
+    const int src = i < GC * a.fe ? (i / a.fe) * GFE + (i % a.fe) : GC * GFE + (i - GC * a.fe);
+    float s = 0.0f;
+#pragma unroll
+    for (int wv = 0; wv < GAT_THREADS / 32; ++wv) s += red[wv][src];
+    part[i] = s;
+  }
+}
+
 int grid_for(int64_t n, int threads) { return (int)max((int64_t)1, min((int64_t)dss2_sm_count() * 8, (n + threads - 1) / threads)); }
 
 int fill_args(const char* who, GatArgs& a, const dss2_graph_t* g, const float* x, int64_t xs, const float* ea, int64_t eas, int fe,
@@ -645,6 +833,74 @@ extern "C" int dss2_gat_bwd(const dss2_graph_t* g, const float* x, int64_t x_str
   DSS2_LAUNCH_CHECK();
   k_outer_reduce<<<np, OR_THREADS, 0, stream>>>(g->num_nodes, node_ws + 28, GAT_NODE_WS, GC, x, x_stride, GC, partials, partial_stride,
                                                 GC * GC + GC, 2 * GC * GC + GC);
+  DSS2_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" size_t dss2_gine_ws_bytes(int64_t num_nodes) { return (size_t)num_nodes * GINE_NODE_WS * sizeof(float); }
+
+static int gine_fill(const char* who, GineArgs& a, const dss2_graph_t* g, const float* x, int64_t xs, const float* ea, int64_t eas, int fe,
+                     const float* nn_w, const float* nn_b, const float* lin_w, const float* lin_b, float eps, int act, float act_slope) {
+  DSS2_CHECK_ARG(g && x && ea && nn_w && nn_b && lin_w && lin_b, "%s: null argument", who);
+  DSS2_CHECK_ARG(fe >= 1 && fe <= GFE && xs >= GC && eas >= fe, "%s: edge_dim %d outside 1..%d or row strides too small", who, fe, GFE);
+  a.g = *g;
+  a.x = x;
+  a.xs = xs;
+  a.ea = ea;
+  a.eas = eas;
+  a.fe = fe;
+  a.wn = nn_w;
+  a.bn = nn_b;
+  a.we = lin_w;
+  a.be = lin_b;
+  a.eps = eps;
+  a.act = act;
+  a.slope_act = act_slope;
+  return 0;
+}
+
+extern "C" int dss2_gine_fwd(const dss2_graph_t* g, const float* x, int64_t x_stride, const float* edge_attr, int64_t ea_stride, int fe,
+                             const float* nn_w, const float* nn_b, const float* lin_w, const float* lin_b, float eps, int act,
+                             float act_slope, float* y, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GineArgs a = {};
+  if (gine_fill("dss2_gine_fwd", a, g, x, x_stride, edge_attr, ea_stride, fe, nn_w, nn_b, lin_w, lin_b, eps, act, act_slope)) return -1;
+  DSS2_CHECK_ARG(y && ((uintptr_t)y & 15) == 0, "dss2_gine_fwd: y must be a 16-byte aligned [Nt, 8] buffer");
+  if (g->num_nodes == 0) return 0;
+  a.y = y;
+  k_gine_fwd<<<grid_for(g->num_nodes, GAT_THREADS), GAT_THREADS, 0, stream>>>(a);
+  DSS2_LAUNCH_CHECK();
+  return 0;
+}
+
+// partials_lin: per-CTA rows [lin.weight 8 fe | lin.bias 8]; partials_nn: per-CTA rows [nn.weight 64 | nn.bias 8] of THIS layer's share of
+// the shared Linear's gradient (the host adds the layers' shares); both with row stride partial_stride, dss2_num_partials() rows.
+extern "C" int dss2_gine_bwd(const dss2_graph_t* g, const float* x, int64_t x_stride, const float* edge_attr, int64_t ea_stride, int fe,
+                             const float* nn_w, const float* nn_b, const float* lin_w, const float* lin_b, float eps, int act,
+                             float act_slope, const float* y, const float* grad_y, float* grad_x, float* node_ws, size_t node_ws_bytes,
+                             float* partials_lin, float* partials_nn, int64_t partial_stride, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GineArgs a = {};
+  if (gine_fill("dss2_gine_bwd", a, g, x, x_stride, edge_attr, ea_stride, fe, nn_w, nn_b, lin_w, lin_b, eps, act, act_slope)) return -1;
+  DSS2_CHECK_ARG(grad_y && node_ws && partials_lin && partials_nn && (!act || y), "dss2_gine_bwd: null argument");
+  DSS2_CHECK_ARG(g->undirected == 1, "dss2_gine_bwd: needs a graph built from the one-way edge list with undirect=1");
+  DSS2_CHECK_ARG(node_ws_bytes >= dss2_gine_ws_bytes(g->num_nodes), "dss2_gine_bwd: node workspace too small");
+  DSS2_CHECK_ARG(!grad_x || ((uintptr_t)grad_x & 15) == 0, "dss2_gine_bwd: grad_x must be 16-byte aligned");
+  if (g->num_nodes == 0) return 0;
+  a.yout = y;
+  a.gy = grad_y;
+  a.ws = node_ws;
+  a.gx = grad_x;
+  k_gine_bwd_a<<<grid_for(g->num_nodes, GAT_THREADS), GAT_THREADS, 0, stream>>>(a);
+  DSS2_LAUNCH_CHECK();
+  const int np = dss2_num_partials();
+  a.partials = partials_lin;
+  a.partial_stride = partial_stride;
+  k_gine_bwd_b<<<np, GAT_THREADS, 0, stream>>>(a);
+  DSS2_LAUNCH_CHECK();
+  // d W_nn | d b_nn = sum_n g[n] (x) [h[n], 1]
+  k_outer_reduce<<<np, OR_THREADS, 0, stream>>>(g->num_nodes, node_ws, GINE_NODE_WS, GC, node_ws + 16, GINE_NODE_WS, GC, partials_nn,
+                                                partial_stride, 0, GC * GC);
   DSS2_LAUNCH_CHECK();
   return 0;
 }

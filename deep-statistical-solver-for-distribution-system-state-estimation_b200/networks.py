@@ -12,7 +12,8 @@ EdgeAggregation.forward (networks.py:196-200) never reaches `message` and is not
 PFN receive the same raw edge attributes; reversed edges negate attribute columns 0 and 2 (networks.py:252).
 There is no CPU fallback: without a CUDA device or the built library, forward raises.
 GAT_DSSE (networks.py:113-156, the as-shipped default of dss2_run.py:86) runs on its own fused GATv2 kernels
-(csrc/gat.cu).  gnn_dsse and GINE_DSSE (GCN2/FA/GINE stacks) remain names only so that `from networks import ...` works.
+(csrc/gat.cu), and so does GINE_DSSE (networks.py:71-111).  gnn_dsse (GCN2/FA/Cheb/GCN stacks) remains a name only so that
+`from networks import ...` works.
 """
 import math
 
@@ -143,7 +144,64 @@ def _next_row(name, where):
 
 
 gnn_dsse = _next_row("gnn_dsse", "networks.py:11-69")
-GINE_DSSE = _next_row("GINE_DSSE", "networks.py:71-111")
+
+
+class _GINEParams(nn.Module):
+    """Parameter holder with PyG GINEConv's names: `nn` (the Linear handed in, shared by every layer of the model), `lin`
+    (Linear(edge_dim, in_channels)), buffer `eps`.  The arithmetic is in the fused kernel (csrc/gat.cu)."""
+
+    def __init__(self, shared_nn, eps, edge_dim):
+        super().__init__()
+        self.nn = shared_nn
+        self.register_buffer("eps", torch.full((1,), float(eps)))
+        self.lin = nn.Linear(edge_dim, shared_nn.in_features)
+
+
+class GINE_DSSE(nn.Module):
+    """networks.py:71-111: (num_layers - 1) x [GINEConv(nn, eps, train_eps, edge_dim) + LeakyReLU()], Linear(dim_feat, dim_dense),
+    Linear(dim_dense, dim_out) inside a PyG `Sequential` (children `module_{i}`).  As in the reference, `nn` is ONE
+    Linear(dim_feat, dim_feat) shared by all layers (it also appears as `model.module_{2l}.nn.*` in the state_dict)."""
+
+    def __init__(self, dim_feat, dim_dense, dim_out, num_layers, edge_dim, nn='mlp', nonlin='leaky_relu', eps=0., train_eps=False,
+                 model='gine'):
+        super().__init__()
+        import torch.nn as tnn        # the reference's `nn` argument shadows torch.nn (networks.py:72): only leaky_relu can work there
+        if nn != 'mlp':
+            raise Exception('invalid nn type')
+        if nonlin != 'leaky_relu':
+            raise NotImplementedError("GINE_DSSE: the reference itself only works with nonlin='leaky_relu' (its `nn` argument shadows "
+                                      "torch.nn, networks.py:72,88-91)")
+        if model != 'gine':
+            raise Exception('invalid model type')
+        if train_eps:
+            raise NotImplementedError("GINE_DSSE kernels cover train_eps=False (the default)")
+        self.dim_out, self.num_layers, self.dim_feat, self.dim_dense = dim_out, num_layers, dim_feat, dim_dense
+        self.eps, self.train_eps, self.edge_dim, self.dim_hidden = eps, train_eps, edge_dim, dim_feat
+        self.nn = tnn.Linear(dim_feat, dim_feat)
+        self.nonlin = tnn.LeakyReLU()
+        self.model = tnn.Module()
+        i = 0
+        for _ in range(num_layers - 1):
+            self.model.add_module(f"module_{i}", _GINEParams(self.nn, eps, edge_dim))
+            self.model.add_module(f"module_{i + 1}", self.nonlin)
+            i += 2
+        self.model.add_module(f"module_{i}", tnn.Linear(dim_feat, dim_dense))
+        self.model.add_module(f"module_{i + 1}", tnn.Linear(dim_dense, dim_out))
+
+    def _machinery(self):
+        m = self.__dict__.get("_dss2_machinery")
+        if m is None:
+            from dss2 import gine
+            spec = gine.GINESpec(dim_feat=self.dim_feat, dim_dense=self.dim_dense, dim_out=self.dim_out, num_layers=self.num_layers,
+                                 edge_dim=self.edge_dim, eps=float(self.eps), act_slope=float(self.nonlin.negative_slope))
+            m = gine.make_machinery(spec)
+            self.__dict__["_dss2_machinery"] = m
+        return m
+
+    def forward(self, x, edge_index, edge_attr):
+        from dss2 import gine
+        runner, pack = self._machinery()
+        return gine.gine_apply(runner, pack, dict(self.named_parameters()), x, edge_index, edge_attr)
 
 
 class _GATv2Params(nn.Module):

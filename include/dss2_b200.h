@@ -269,6 +269,18 @@ int dss2_gat_bwd(const dss2_graph_t* g, const float* x, int64_t x_stride, const 
                  const float* lin_edge_w, const float* att, const float* bias, float att_slope, int act, float act_slope,
                  const float* y, const float* grad_y, float* grad_x, float* node_ws, size_t node_ws_bytes, float* partials,
                  int64_t partial_stride, void* stream);
+/* GINE_DSSE layer (networks.py:71-111, PyG GINEConv + LeakyReLU): y_i = leaky(nn((1 + eps) x_i + sum_{j->i} relu(x_j + lin(a_ji)))) with
+ * nn = the model's ONE shared Linear(8,8) and lin = this layer's Linear(edge_dim, 8); one-way edge list.  Backward: node_ws of
+ * dss2_gine_ws_bytes(Nt); per-CTA partial rows [lin.weight 8 fe | lin.bias 8] at partials_lin and [nn.weight 64 | nn.bias 8] (this
+ * layer's share of the shared Linear's gradient) at partials_nn, both with row stride partial_stride. */
+size_t dss2_gine_ws_bytes(int64_t num_nodes);
+int dss2_gine_fwd(const dss2_graph_t* g, const float* x, int64_t x_stride, const float* edge_attr, int64_t ea_stride, int fe,
+                  const float* nn_w, const float* nn_b, const float* lin_w, const float* lin_b, float eps, int act, float act_slope,
+                  float* y, void* stream);
+int dss2_gine_bwd(const dss2_graph_t* g, const float* x, int64_t x_stride, const float* edge_attr, int64_t ea_stride, int fe,
+                  const float* nn_w, const float* nn_b, const float* lin_w, const float* lin_b, float eps, int act, float act_slope,
+                  const float* y, const float* grad_y, float* grad_x, float* node_ws, size_t node_ws_bytes, float* partials_lin,
+                  float* partials_nn, int64_t partial_stride, void* stream);
 int dss2_mlp2_fwd(int64_t num_nodes, const float* x, int din, const float* w1, const float* b1, int dmid, const float* w2,
                   const float* b2, int dout, float* h, float* z, void* stream);
 int dss2_mlp2_bwd(int64_t num_nodes, const float* x, int din, const float* w1, int dmid, const float* w2, int dout,

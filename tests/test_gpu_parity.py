@@ -1067,3 +1067,64 @@ def test_eval_metrics_kernel_matches_script_formulas(env, case):
     assert set(got) == set(want)
     for k in want:
         assert abs(got[k] - want[k]) <= 2e-4 * abs(want[k]) + 1e-9, (k, got[k], want[k])
+
+
+# ------------------------------------------------------------------------------------------------ GINE_DSSE (scope row 8f-1)
+@pytest.mark.parametrize("tag", ["gine_cigre", "gine_ober"])
+@pytest.mark.parametrize("where", ["cuda", "cpu"])
+def test_gine_dsse_matches_reference_run(env, tag, where):
+    """networks.GINE_DSSE (fused GINEConv kernels, one Linear shared by all layers) with the weights of the reference run: output, loss
+    and every parameter gradient against the reference's own GINE_DSSE executed over the shim, fp64 oracle as arbiter."""
+    from conftest import golden_gat, oracle_gine_run
+    nl, sd, grads, z = golden_gat(tag)
+    model = env["networks"].GINE_DSSE(dim_feat=8, dim_dense=32, dim_out=2, num_layers=nl, edge_dim=6)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            p.copy_(sd[name])
+    model = model.to(where).train()
+    x, ea, ei = torch.from_numpy(z["x"]).to(where), torch.from_numpy(z["edge_attr"]).to(where), torch.from_numpy(z["edge_index"]).to(where)
+    st = [torch.from_numpy(z[k]) for k in ("x_mean", "x_std", "edge_mean", "edge_std")]
+    out = model(x[:, :8], ei, ea[:, :6])
+    assert out.device.type == where and out.shape == (x.size(0), 2)
+    out_before = out.detach().clone()
+    loss = env["data"].gsp_wls_edge(input=x[:, :8], edge_input=ea[:, :6], output=out, x_mean=st[0], x_std=st[1], edge_mean=st[2],
+                                    edge_std=st[3], edge_index=ei, reg_coefs=REG_COEFS, num_samples=None, node_param=x[:, 8:],
+                                    edge_param=ea[:, 6:])
+    loss.backward()
+    o64, l64, g64 = oracle_gine_run(orc, nl, sd, z, torch.float64)
+    assert_fp32_parity(out_before, z["out"], o64, "out")
+    assert_fp32_parity(loss.detach(), z["loss"], l64, "loss")
+    for name, p in model.named_parameters():
+        assert p.grad is not None and p.grad.device.type == where, name
+        assert_fp32_parity(p.grad, grads[name], g64[name], name)
+
+
+def test_gine_layer_input_gradient_and_self_loops(env):
+    """GINE layers on a graph with input self loops (kept by GINEConv), a bus without in-edges and a hub: output, gradient w.r.t. the
+    input and all parameter gradients against the oracle's autograd."""
+    torch.manual_seed(6)
+    n = 9
+    ei = torch.tensor([[0, 1, 2, 2, 3, 5, 6, 6, 4], [1, 2, 3, 2, 1, 1, 7, 8, 4]])
+    x = torch.randn(n, 8)
+    ea = torch.randn(ei.size(1), 6)
+    sd = orc.init_gine_state_dict(num_layers=3, seed=10)
+    model = env["networks"].GINE_DSSE(dim_feat=8, dim_dense=32, dim_out=2, num_layers=3, edge_dim=6)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            p.copy_(sd[name])
+    model = model.cuda()
+    xg = x.cuda().requires_grad_(True)
+    out = model(xg, ei.cuda(), ea.cuda())
+    gw = torch.linspace(-1, 1, out.numel()).view_as(out)
+    (out * gw.cuda()).sum().backward()
+    res = {}
+    for dtype in (torch.float32, torch.float64):
+        xc = x.detach().clone().to(dtype).requires_grad_(True)
+        p = {k: v.to(dtype).clone().requires_grad_(True) for k, v in sd.items()}
+        o = orc.gine_dsse_forward(p, xc, ei, ea.to(dtype), 3)
+        (o * gw.to(dtype)).sum().backward()
+        res[dtype] = (o.detach(), xc.grad, {k: v.grad for k, v in p.items()})
+    assert_fp32_parity(out.detach(), res[torch.float32][0], res[torch.float64][0], "out")
+    assert_fp32_parity(xg.grad, res[torch.float32][1], res[torch.float64][1], "grad_x")
+    for name, p in model.named_parameters():
+        assert_fp32_parity(p.grad, res[torch.float32][2][name], res[torch.float64][2][name], name)

@@ -54,9 +54,13 @@ def test_no_cpu_fallback():
     import data
     with pytest.raises(_lib.Dss2Error):
         data.get_pflow(torch.zeros(3, 2), torch.tensor([[0], [1]]), torch.zeros(3, 3), torch.zeros(1, 7))
-    for name in ("GINE_DSSE", "gnn_dsse"):
-        with pytest.raises(NotImplementedError):
-            getattr(networks, name)()
+    with pytest.raises(NotImplementedError):
+        networks.gnn_dsse()
+    gine = networks.GINE_DSSE(dim_feat=8, dim_dense=32, dim_out=2, num_layers=3, edge_dim=6)
+    with pytest.raises(_lib.Dss2Error):
+        gine(torch.zeros(4, 8), torch.tensor([[0, 1], [1, 2]]), torch.zeros(2, 6))
+    with pytest.raises(NotImplementedError):
+        networks.GINE_DSSE(dim_feat=8, dim_dense=32, dim_out=2, num_layers=3, edge_dim=6, train_eps=True)
     gat = networks.GAT_DSSE(dim_feat=8, dim_dense=32, dim_out=2, heads=1, num_layers=3, edge_dim=6)
     with pytest.raises(_lib.Dss2Error):
         gat(torch.zeros(4, 8), torch.tensor([[0, 1], [1, 2]]), torch.zeros(2, 6))
@@ -75,6 +79,20 @@ def test_gat_dsse_state_dict_names_match_reference_layout():
     assert set(table) == set(dict(m.named_parameters()))
     spans = sorted(table.values())
     assert all(a[0] + a[1] <= b[0] for a, b in zip(spans, spans[1:])) and spans[-1][0] + spans[-1][1] <= size
+
+
+def test_gine_dsse_state_dict_names_match_reference():
+    """GINE_DSSE exposes the reference's state_dict keys, including the shared Linear's aliases `model.module_{2l}.nn.*` and the
+    `eps` buffers, and reports the shared parameters once."""
+    from conftest import load_golden
+    from dss2 import gine
+    z = load_golden("golden_model_gine_cigre.npz")
+    m = networks.GINE_DSSE(dim_feat=8, dim_dense=32, dim_out=2, num_layers=int(z["num_layers"]), edge_dim=6)
+    assert sorted(m.state_dict().keys()) == sorted(z["state_dict_keys"].tolist())
+    names = [n for n, _ in m.named_parameters()]
+    assert names.count("nn.weight") == 1 and not any(".nn." in n for n in names)
+    table, _ = gine.GINESpec(8, 32, 2, int(z["num_layers"]), 6).layout()
+    assert set(table) == set(names)
 
 
 def test_unsupported_shapes_fail_loudly():
