@@ -231,6 +231,20 @@ def main():
             gref, P(x_l), wp, bp, 32, sp.K, 1, sp.p_drop, 1, P(trainer.step_state), 3, None, None, 0, P(y_l), P(bits_l), st_()), "fwd"),
             nt * (2 * 128 + 4) + 4 * (nt + 1) + 16 * et, "x in, y out, sign word, CSR")
 
+    # EdgeAggregation of sub-net 1 (input = the previous sub-net's 8-wide output, gradient to the input and skip path needed)
+    pre1 = "mpns.1.edge_aggr.edge_aggr."
+    ea_w = [run._p(trainer.flat, pre1 + n_) for n_ in ("0.weight", "0.bias", "2.weight", "2.bias")]
+    ea_part = ctypes.c_void_p(bufs["partials"].data_ptr() + 4 * run.table[pre1 + "0.weight"][0])
+    x_in, eattr = bufs["outs"][0], trainer.batch["edge_attr"]
+    ea_fwd_bytes = 32 * nt + 52 * et + 16 * et + 128 * nt
+    kernels["k_edgeagg_fwd (EdgeAggregation forward)"] = (lambda: _lib.check(lib.dss2_edgeagg_fwd(
+        gref, P(x_in), sp.fn, sp.fn, P(eattr), 13, sp.fe, *ea_w, P(bufs["acts"][1, 0]), st_()), "ea_fwd"),
+        ea_fwd_bytes, "SURVEY 8(d): x row 32 + out row 128 per bus, edge_attr row 52 + edge_index 16 per branch")
+    kernels["k_edgeagg_bwd (EdgeAggregation backward: grad_x + parameter gradients)"] = (lambda: _lib.check(lib.dss2_edgeagg_bwd(
+        gref, P(x_in), sp.fn, sp.fn, P(eattr), 13, sp.fe, *ea_w, P(gy_l), P(bufs["gsub"][0]), sp.fn, P(bufs["gsub"][1]), ea_part,
+        run.flat_size, st_()), "ea_bwd"),
+        ea_fwd_bytes + 32 * nt, "SURVEY 8(d): forward bytes with grad_out in place of out, + grad_x row 32 per bus")
+
     # the fused loss (2 kernels: reduction pass + gradient pass), on the trainer's own buffers
     kernels["k_wls<false>+k_wls<true> (branch flows + WLS loss, forward and backward)"] = (lambda: _lib.check(lib.dss2_wls_fwd_bwd(
         gref, P(trainer.batch["x"]), 11, P(trainer.batch["edge_attr"]), 13, P(bufs["outs"][-1]), P(trainer.stats), REG["lam_v"], REG["lam_p"],

@@ -742,6 +742,8 @@ extern "C" int dss2_tag_bwd(const dss2_graph_t* g, const float* x, const float* 
       d.Nt = Nt;
       if (launch_dense_k(d, K, stream)) return -3;
     }
+    // the hop levels above are plain rows: say so in the format word the weight-gradient kernels read behind them
+    DSS2_CUDA(cudaMemsetAsync(lvl + (size_t)K * Nt * HID, 0, sizeof(uint32_t), stream));
     // weight gradients: the tcgen05 streaming GEMM when its alignment contract holds (it measures 2x faster), else the exact FMA pass
     const bool aligned = (((uintptr_t)x | (uintptr_t)grad_y | (uintptr_t)act_bits | (uintptr_t)partials) & 15) == 0;
     if (dense_tc_enabled() && aligned)

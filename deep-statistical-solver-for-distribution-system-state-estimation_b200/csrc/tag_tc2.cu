@@ -19,159 +19,72 @@
 #include "common.cuh"
 #include "tc.cuh"
 
+#ifdef DSS2_STAMPS
+// diagnostic build only (tools/stamps.sh): per-phase clock64 totals of worker thread 0 and of the issuer of CTA 0
+__device__ unsigned long long g_tc2_stamps[32];
+#define STAMP(i)                                                    \
+  do {                                                              \
+    if (blockIdx.x == 0 && (tid == 0)) {                            \
+      const long long now_ = clock64();                             \
+      g_tc2_stamps[i] += (unsigned long long)(now_ - stamp_prev_);  \
+      stamp_prev_ = now_;                                           \
+    }                                                               \
+  } while (0)
+#define STAMP_I(i)                                                  \
+  do {                                                              \
+    if (blockIdx.x == 0 && (tid & 31) == 0) {                       \
+      const long long now_ = clock64();                             \
+      g_tc2_stamps[i] += (unsigned long long)(now_ - stamp_prev_);  \
+      stamp_prev_ = now_;                                           \
+    }                                                               \
+  } while (0)
+#else
+#define STAMP(i)
+#define STAMP_I(i)
+#endif
+
+#include "tc2_shared.cuh"
+
 namespace {
 
-constexpr int T2_MAX = 256;                      // rows per tile (2 MMA blocks of 128)
-constexpr uint32_t W_TILE = 32 * tc::ROW_BYTES;  // 4 KB
-enum { MODE_FWD = 0, MODE_BGX = 1 };
-
-struct Tc2Args {
-  dss2_graph_t g;
-  const float* in;          // FWD: x [Nt,32].  BGX: grad_y [Nt,cout]
-  const uint32_t* in_bits;  // BGX: sign words of the forward output (NULL when the layer had no activation)
-  const float* w;           // [K+1][cout][32]
-  const float* bias;        // FWD
-  int cout;
-  int act;                  // FWD: apply dropout + ReLU
-  float scale;              // 1/(1-p)
-  uint32_t keep_thr16;
-  int drop_mode;
-  const uint64_t* rng;
-  uint32_t layer_uid;
-  const uint8_t* mask;
-  const float* res;
-  int64_t res_stride;
-  float* out;               // FWD: y [Nt,cout].  BGX: grad_x [Nt,32]
-  uint32_t* out_bits;       // FWD
-  float* lvl_out;           // BGX: [K][Nt,32] hop levels 1..K of g (for k_tag_gw)
-  const float* dense_lvl;   // large-graph path: hop levels 1..K precomputed in global memory ([K][Nt,32]); tiles are plain row chunks
-};
-
-__device__ __forceinline__ char* align1024(char* p) {
-  const uint32_t a = smem_u32(p);
-  return p + (((a + 1023u) & ~1023u) - a);
-}
-
-// Thread mapping of the layer kernel: 256 threads per tile, thread = (row, half): row = tid & 127 (= its TMEM lane), half = tid >> 7
-// owns features [16*half, 16*half + 16).  Two threads per row double the number of busy warps on grids whose tile holds a single
-// graph (Oberrhein: 70 of 128 rows) and halve every per-thread dependency chain.
-// NB = MMA blocks (128 rows each) per tile: NB = 2 packs e.g. 3 Oberrhein graphs (210 rows) or 17 CIGRE graphs (255 rows) into one
-// tile, so that more live rows share one pass through the per-tile dependency chain; workers = 256 per block + 1 issuer warp.
-constexpr int HF = 16;
-
-__device__ __forceinline__ void store_half_sw128(const float (&v)[HF], char* pt, char* lt, uint32_t row, uint32_t half) {
-  const uint32_t code = tc::row_code(row);
-#pragma unroll
-  for (uint32_t q = 0; q < 4; ++q)
-    tc::plain_store4(make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]), pt, lt, code ^ ((half * 4 + q) << 4));
-}
-
-// h += w * plain[src row][16*half ...]: one neighbour, exact fp32 values from the plain tile
-__device__ __forceinline__ void gather_half(float (&h)[HF], const char* pt, uint32_t src, float w, uint32_t half) {
-  const uint32_t code = tc::row_code(src);
-#pragma unroll
-  for (uint32_t q = 0; q < 4; ++q) {
-    const float4 a = *reinterpret_cast<const float4*>(pt + (code ^ ((half * 4 + q) << 4)));
-    h[4 * q + 0] = fmaf(w, a.x, h[4 * q + 0]);
-    h[4 * q + 1] = fmaf(w, a.y, h[4 * q + 1]);
-    h[4 * q + 2] = fmaf(w, a.z, h[4 * q + 2]);
-    h[4 * q + 3] = fmaf(w, a.w, h[4 * q + 3]);
-  }
-}
-
-struct RowTopo {
-  float4 w;        // weights of the first 4 entries
-  uint32_t cols;   // 4 x 8-bit tile-local sources
-  uint32_t deg;
-};
-__device__ __forceinline__ RowTopo load_row_topo(const dss2_graph_t& g, size_t n) {
-  RowTopo t;
-  t.w = reinterpret_cast<const float4*>(g.ell_w)[n];
-  const uint2 ci = reinterpret_cast<const uint2*>(g.ell_ci)[n];
-  t.cols = ci.x;
-  t.deg = ci.y;
-  return t;
-}
-
-// one hop for this thread's half row: entries in CSR order = PyG scatter order
-__device__ __forceinline__ void hop_thread(float (&h)[HF], const dss2_graph_t& g, const RowTopo& tp, const char* pt, size_t n, int n0,
-                                           uint32_t half) {
-#pragma unroll
-  for (int i = 0; i < HF; ++i) h[i] = 0.0f;
-  const float wv[4] = {tp.w.x, tp.w.y, tp.w.z, tp.w.w};
-#pragma unroll
-  for (uint32_t d = 0; d < 4; ++d)
-    if (d < tp.deg) gather_half(h, pt, (tp.cols >> (8 * d)) & 0xffu, wv[d], half);
-  if (tp.deg > 4) {   // rare: hub nodes
-    const int beg = g.rowptr[n];
-    for (int z = beg + 4; z < beg + (int)tp.deg; ++z) gather_half(h, pt, (uint32_t)(g.col[z] - n0), g.w[z], half);
-  }
-}
-
-// 16 Bernoulli(keep) decisions: features [16*half, 16*half+16) of one node row
-__device__ __forceinline__ uint32_t keep_half(uint2 key, uint32_t tile, uint32_t row, uint32_t half, uint32_t step_lo, uint32_t thr16) {
-  uint32_t word = 0;
-#pragma unroll
-  for (uint32_t q = 0; q < 2; ++q) {
-    const uint4 r = philox4x32_10(make_uint4(tile, row, half * 2 + q, step_lo), key);
-    const uint32_t u[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-    for (uint32_t i = 0; i < 4; ++i) {
-      word |= ((u[i] & 0xffffu) < thr16 ? 1u : 0u) << (q * 8 + 2 * i);
-      word |= ((u[i] >> 16) < thr16 ? 1u : 0u) << (q * 8 + 2 * i + 1);
-    }
-  }
-  return word;
-}
-
-struct TileNodes {
-  int n0, n1;
-};
-__device__ __forceinline__ TileNodes tile_nodes(const dss2_graph_t& g, int t, int dense_rows = 0) {
-  TileNodes r;
-  r.n0 = r.n1 = 0;
-  if (dense_rows) {   // hop-free mode: tile t = rows [t * dense_rows, (t + 1) * dense_rows)
-    const int64_t n0 = (int64_t)t * dense_rows;
-    if (n0 < g.num_nodes) {
-      r.n0 = (int)n0;
-      r.n1 = (int)min(g.num_nodes, n0 + dense_rows);
-    }
-    return r;
-  }
-  if (t < g.num_tiles) {
-    const int g0 = t * g.graphs_per_tile, g1 = min(g0 + g.graphs_per_tile, g.num_graphs);
-    r.n0 = (int)g.ptr[g0];
-    r.n1 = (int)g.ptr[g1];
-  }
-  return r;
-}
-
-template <int MODE, int K, int NB, bool DENSE>
-__global__ void __launch_bounds__(256 * NB + 32, 3 - NB) k_tag_tc2(Tc2Args a) {
-  constexpr int TC2_WORKERS = 256 * NB;
-  constexpr int TC2_THREADS = TC2_WORKERS + 32;
-  constexpr int ROWS = 128 * NB;
+// TA = "A operand in tensor memory": thread (row, half) IS TMEM lane `row`, so a hop level goes straight from the thread's registers
+// into the A operand with tcgen05.st (plain fp32 word + rounded residual, 64 columns per level and 128-row block); the MMAs read A
+// from TMEM and only the 8 KB weight operand from shared memory.  What that removes from the per-tile chain (clock64 stamps,
+// profiles/r2_stamps_*.txt): the residual tiles and their 12 STS.128 per thread, the shared-memory copy of the last level (nobody
+// gathers from it), the 4 KB A read of every MMA (the K-major 32-byte slices made an M128 N64 K8 MMA take 100-180 cycles against a
+// 32-cycle floor while the workers' gathers hammered the same banks) and all three fence.proxy.async per tile - shared memory is
+// only read by generic-proxy gathers now, so a plain bar.sync orders it, and the TMEM hand-over is tcgen05.wait::st + fence.
+template <int MODE, int K, int RW, bool DENSE, bool TA>
+__global__ void __launch_bounds__(Tc2Shape<RW>::THREADS, Tc2Shape<RW>::CTAS_PER_SM) k_tag_tc2(Tc2Args a) {
+  using Shape = Tc2Shape<RW>;
+  constexpr int NB = Shape::NB;
+  constexpr int TC2_WORKERS = Shape::WORKERS;
+  constexpr int TC2_THREADS = Shape::THREADS;
+  constexpr int ROWS = Shape::ROWS;
   constexpr uint32_t LV_TILE = ROWS * tc::ROW_BYTES;   // one operand tile (plain or residual) of one hop level
+  constexpr int NLV = TA ? 2 : 4;                      // TA: two rotating plain tiles (gather sources); else [2 buffers][plain, residual]
+  constexpr uint32_t TMEM_COLS = TA ? (NB == 1 ? 256u : 512u) : 64u * NB;   // D: 64 per block; TA: + [2 buffers][NB blocks][plain 32 | residual 32]
   extern __shared__ char raw[];
   const dss2_graph_t& g = a.g;
   char* base = align1024(raw);
-  char* Wt = base;                                  // [(K+1)] x 8 KB: rows 0-31 plain W_k, rows 32-63 residual -> one N = 64 operand
-  char* Lv = Wt + (K + 1) * 2 * W_TILE;             // [2 buffers][plain, residual] level tiles
-  char* tail = Lv + 4 * LV_TILE;
+  char* Lv = base;                                  // level tiles
+  char* Wt = Lv + NLV * LV_TILE;                    // [(K+1)] x 8 KB: rows 0-31 plain W_k, rows 32-63 residual -> one N = 64 operand
+  char* tail = Wt + (K + 1) * 2 * W_TILE;           // (behind the level tiles: a 96-row tile's M = 128 operand read runs 4 KB past its end)
   float* bias_s = reinterpret_cast<float*>(tail);
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 128);   // [2]: "MMAs reading buffer b have completed"   (tcgen05.commit)
   uint64_t* full = bars + 2;                                  // [2]: "all workers have written buffer b"       (256 arrivals)
   uint32_t* tslot = reinterpret_cast<uint32_t*>(full + 2);
   const int tid = threadIdx.x, warp = tid >> 5;
-  const bool issuer = warp == TC2_WORKERS / 32;
-  // worker tid = half * ROWS + row: warp % 4 == (row / 32) % 4 = the TMEM lane quarter this warp may read
-  const uint32_t row = (uint32_t)tid % ROWS, half = ((uint32_t)tid / ROWS) & 1u;
+  const bool issuer = warp == Shape::ISSUER_WARP;
+  // worker tid = half * ROWS + row (RW = 3: half * 128 + row): warp % 4 == (row / 32) % 4 = the TMEM lane quarter this warp may read
+  const uint32_t row = RW == 3 ? ((uint32_t)tid & 127u) : (uint32_t)tid % ROWS;
+  const uint32_t half = RW == 3 ? ((uint32_t)tid >> 7) : (((uint32_t)tid / ROWS) & 1u);
   const int cout = a.cout;
-  auto lv_p = [&](int b) { return Lv + (size_t)(2 * b) * LV_TILE; };
-  auto lv_l = [&](int b) { return Lv + (size_t)(2 * b + 1) * LV_TILE; };
+  auto lv_p = [&](int b) { return Lv + (size_t)(TA ? b : 2 * b) * LV_TILE; };
+  auto lv_l = [&](int b) { return Lv + (size_t)(2 * b + 1) * LV_TILE; };   // !TA only
 
   // ---- one-time setup ----
-  if (warp == 0) tc::tmem_alloc(tslot, 64 * NB);
+  if (warp == 0) tc::tmem_alloc(tslot, TMEM_COLS);
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
@@ -190,6 +103,8 @@ __global__ void __launch_bounds__(256 * NB + 32, 3 - NB) k_tag_tc2(Tc2Args a) {
     *reinterpret_cast<float*>(Wt + (size_t)(2 * k + 1) * W_TILE + off) = tc::tf32_residual(v);
   }
   if (tid < 32) bias_s[tid] = (MODE == MODE_FWD && tid < cout) ? a.bias[tid] : 0.0f;
+  if (MODE == MODE_BGX && a.lvl_out && blockIdx.x == 0 && tid == 0)   // format word of the hop-level spill: plain rows
+    *reinterpret_cast<uint32_t*>(a.lvl_out + (size_t)K * g.num_nodes * 32) = 0u;
   uint2 key = make_uint2(0u, 0u);
   uint32_t step_lo = 0;
   if (MODE == MODE_FWD && a.drop_mode == 1) {
@@ -201,7 +116,7 @@ __global__ void __launch_bounds__(256 * NB + 32, 3 - NB) k_tag_tc2(Tc2Args a) {
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
-  const uint32_t tmem = *tslot;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tslot, 0);   // warp-uniform for the compiler (MMA operands live in uniform registers)
   constexpr int dense_rows = DENSE ? ROWS : 0;   // compile-time: the tiled instantiations carry none of the hop-free code
   const int ntiles = DENSE ? (int)((g.num_nodes + ROWS - 1) / ROWS) : g.num_tiles;
 
@@ -209,6 +124,9 @@ __global__ void __launch_bounds__(256 * NB + 32, 3 - NB) k_tag_tc2(Tc2Args a) {
     // ===== MMA issuer warp: D[:, 0:32] += A W_plain^T, D[:, 32:64] += A W_resid^T for A in {plain, residual} of every level =====
     const uint32_t idesc = tc::idesc_tf32(128, 64);
     uint32_t fpar[2] = {0u, 0u};
+#ifdef DSS2_STAMPS
+    long long stamp_prev_ = clock64();
+#endif
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
       const TileNodes tn = tile_nodes(g, t, dense_rows);
       const int nmb = (NB == 2 && tn.n1 - tn.n0 > 128) ? 2 : 1;
@@ -217,22 +135,34 @@ __global__ void __launch_bounds__(256 * NB + 32, 3 - NB) k_tag_tc2(Tc2Args a) {
         const int b = k & 1;
         mbar_wait(&full[b], fpar[b]);
         fpar[b] ^= 1u;
+        STAMP_I(16 + 2 * k);
         tc::fence_after_sync();
-        if ((tid & 31) == 0) {
+        if (tc::elect_one()) {
           const uint64_t dW = tc::smem_desc_sw128(smem_u32(Wt + (size_t)(2 * k) * W_TILE));
           for (int mb = 0; mb < nmb; ++mb) {
-            const uint64_t dP = tc::smem_desc_sw128(smem_u32(lv_p(b)) + mb * 128 * tc::ROW_BYTES);
-            const uint64_t dL = tc::smem_desc_sw128(smem_u32(lv_l(b)) + mb * 128 * tc::ROW_BYTES);
+            if (TA) {
+              const uint32_t aT = tmem + 64 * NB + (uint32_t)(b * NB + mb) * 64;   // plain word columns [0, 32), residual [32, 64)
 #pragma unroll
-            for (uint32_t kk = 0; kk < 4; ++kk) {
-              const uint32_t o = kk * tc::KSTEP_BYTES;
-              tc::mma_tf32(tmem + mb * 64, tc::desc_advance(dL, o), tc::desc_advance(dW, o), idesc, (k == 0 && kk == 0) ? 0u : 1u);
-              tc::mma_tf32(tmem + mb * 64, tc::desc_advance(dP, o), tc::desc_advance(dW, o), idesc, 1u);
+              for (uint32_t kk = 0; kk < 4; ++kk) {
+                const uint32_t o = kk * tc::KSTEP_BYTES;
+                tc::mma_tf32_ts(tmem + mb * 64, aT + 32 + kk * 8, tc::desc_advance(dW, o), idesc, (k == 0 && kk == 0) ? 0u : 1u);
+                tc::mma_tf32_ts(tmem + mb * 64, aT + kk * 8, tc::desc_advance(dW, o), idesc, 1u);
+              }
+            } else {
+              const uint64_t dP = tc::smem_desc_sw128(smem_u32(lv_p(b)) + mb * 128 * tc::ROW_BYTES);
+              const uint64_t dL = tc::smem_desc_sw128(smem_u32(lv_l(b)) + mb * 128 * tc::ROW_BYTES);
+#pragma unroll
+              for (uint32_t kk = 0; kk < 4; ++kk) {
+                const uint32_t o = kk * tc::KSTEP_BYTES;
+                tc::mma_tf32(tmem + mb * 64, tc::desc_advance(dL, o), tc::desc_advance(dW, o), idesc, (k == 0 && kk == 0) ? 0u : 1u);
+                tc::mma_tf32(tmem + mb * 64, tc::desc_advance(dP, o), tc::desc_advance(dW, o), idesc, 1u);
+              }
             }
           }
           tc::mma_commit(&bars[b]);
         }
         __syncwarp();
+        STAMP_I(17 + 2 * k);
       }
     }
   } else {
@@ -240,6 +170,7 @@ __global__ void __launch_bounds__(256 * NB + 32, 3 - NB) k_tag_tc2(Tc2Args a) {
     uint32_t par[2] = {0u, 0u};
     // software pipeline over this CTA's tiles: node range two tiles ahead, rows + topology one tile ahead (all in registers)
     float xr[HF];
+    uint32_t xr_bits = 0;
     RowTopo tp_next;
     tp_next.deg = 0;
     tp_next.cols = 0;
@@ -265,32 +196,69 @@ __global__ void __launch_bounds__(256 * NB + 32, 3 - NB) k_tag_tc2(Tc2Args a) {
         for (int c = 0; c < HF; ++c)
           if ((int)(half * HF) + c < cout) xr[c] = a.in[n * cout + half * HF + c];
       }
+      // BGX: the sign word is only LOADED here; the mask is applied when the tile starts (apply_mask), so that this prefetch never
+      // waits for its own loads (clock64 stamps: masking in place exposed ~3000 cycles of DRAM latency per tile)
+      if (MODE == MODE_BGX && a.in_bits) xr_bits = a.in_bits[n] >> (half * HF);
+    };
+    auto apply_mask = [&]() {
       if (MODE == MODE_BGX && a.in_bits) {
-        const uint32_t word = a.in_bits[n] >> (half * HF);
 #pragma unroll
-        for (int c = 0; c < HF; ++c) xr[c] = ((word >> c) & 1u) ? xr[c] * a.scale : 0.0f;
+        for (int c = 0; c < HF; ++c) xr[c] = ((xr_bits >> c) & 1u) ? xr[c] * a.scale : 0.0f;
       }
     };
     // my part of buffer b is written: make it visible to the tensor core, tell the issuer and - when the next stage gathers other
     // threads' rows - meet the workers (after the last level nobody gathers: the MMAs are the only readers, no barrier needed)
     auto publish = [&](int b, bool meet = true) {
-      fence_proxy_async();
+      if (TA) {
+        tc::tmem_wait_st();
+        tc::fence_before_sync();
+      } else {
+        fence_proxy_async();
+      }
       tc::mbar_arrive(&full[b]);
       if (meet) named_bar_sync(1, TC2_WORKERS);
+    };
+    // this thread's half row of a hop level -> operand storage of buffer b (and, when a later hop gathers from it, the plain tile)
+    const uint32_t tlane = (uint32_t)((warp & 3) * 32) << 16;
+    auto store_level = [&](const float (&v)[HF], int b, bool gathered) {
+      if (!TA) {
+        store_half_sw128(v, lv_p(b), lv_l(b), row, half);
+        return;
+      }
+      if (gathered) {
+        const uint32_t code = tc::row_code(row);
+        char* pt = lv_p(b);
+#pragma unroll
+        for (uint32_t q = 0; q < 4; ++q)
+          *reinterpret_cast<float4*>(pt + (code ^ ((half * 4 + q) << 4))) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      }
+      const uint32_t ta = tmem + tlane + 64 * NB + (uint32_t)(b * NB + (row >> 7)) * 64 + half * HF;
+      tc::tmem_st16(ta, v);
+      float r[HF];
+#pragma unroll
+      for (int i = 0; i < HF; ++i) r[i] = tc::tf32_residual(v[i]);
+      tc::tmem_st16(ta + 32, r);
     };
 
     TileNodes cur = tile_nodes(g, blockIdx.x, dense_rows);
     TileNodes nxt = tile_nodes(g, blockIdx.x + gridDim.x, dense_rows);
     load_row(cur);
+#ifdef DSS2_STAMPS
+    long long stamp_prev_ = clock64();
+#endif
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      STAMP(0);
       const int nT = cur.n1 - cur.n0, n0 = cur.n0;
       const bool live = (int)row < nT;
       const size_t n = (size_t)n0 + row;
       const RowTopo tp = tp_next;
       // ---- level 0 (buffer 0 is free: the previous tile's epilogue waited for its last MMAs) ----
-      store_half_sw128(xr, lv_p(0), lv_l(0), row, half);          // dead rows store zeros: keeps the MMA input finite
+      apply_mask();
+      store_level(xr, 0, true);                                   // dead rows store zeros: keeps the MMA input finite
+      STAMP(1);
       publish(0);
-      if (MODE == MODE_BGX) {   // see the note on the prefetch below: with the spill stores in flight the backward measures best here
+      STAMP(2);
+      if (MODE == MODE_BGX && !(a.flags & 1)) {   // see the note on the prefetch below: with the spill stores in flight the backward measures best here
         cur = nxt;
         load_row(cur);
         nxt = tile_nodes(g, t + 2 * gridDim.x, dense_rows);
@@ -315,16 +283,20 @@ __global__ void __launch_bounds__(256 * NB + 32, 3 - NB) k_tag_tc2(Tc2Args a) {
 #pragma unroll
           for (int i = 0; i < HF; ++i) h[i] = 0.0f;
         }
+        STAMP(3 + 4 * (k - 1));   // hop
         if (k >= 2) {   // buffer b still feeds the MMAs of level k-2
           mbar_wait(&bars[b], par[b]);
           par[b] ^= 1u;
         }
-        store_half_sw128(h, lv_p(b), lv_l(b), row, half);
+        STAMP(4 + 4 * (k - 1));   // wait for the buffer
+        store_level(h, b, k < K);
+        STAMP(5 + 4 * (k - 1));   // store
         publish(b, k < K);
+        STAMP(6 + 4 * (k - 1));   // publish
         // hop-level spill for the weight-gradient pass.  Its stores drain during the next hop; the fence of the next publish still
         // waits for their tail (measured: cheaper than deferring all spills to the tile end, where they pile up with the output
         // stores in front of the next tile's first fence: 88 vs 103 us)
-        if (MODE == MODE_BGX && a.lvl_out && live) {
+        if (MODE == MODE_BGX && a.lvl_out && live && !(a.flags & 2)) {
           float4* dst = reinterpret_cast<float4*>(a.lvl_out + ((size_t)(k - 1) * g.num_nodes + n) * 32 + half * HF);
 #pragma unroll
           for (int q = 0; q < 4; ++q) dst[q] = make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
@@ -333,7 +305,7 @@ __global__ void __launch_bounds__(256 * NB + 32, 3 - NB) k_tag_tc2(Tc2Args a) {
       // The prefetch of the next tile sits here, behind the tile's LAST proxy fence: fence.proxy.async waits for every earlier memory
       // operation of the thread, global ones included (clock64 stamps: a prefetch issued before a publish costs ~2000 cycles of
       // exposed DRAM latency at that publish).  From here the loads have the whole epilogue to land.
-      if (MODE == MODE_FWD) {
+      if (MODE == MODE_FWD || (a.flags & 1)) {
         cur = nxt;
         load_row(cur);                                             // next tile: rows (same registers) + topology
         nxt = tile_nodes(g, t + 2 * gridDim.x, dense_rows);                    // and the node range of the tile after it
@@ -341,6 +313,7 @@ __global__ void __launch_bounds__(256 * NB + 32, 3 - NB) k_tag_tc2(Tc2Args a) {
       // dropout keep bits do not depend on the MMAs: generate them while the tensor core finishes
       uint32_t keep_rng = 0xffffu;
       if (MODE == MODE_FWD && a.act && a.drop_mode == 1 && live) keep_rng = keep_half(key, (uint32_t)t, row, half, step_lo, a.keep_thr16);
+      STAMP(11);   // spill / prefetch / rng
       // ---- all MMAs of the tile complete when the last two commits have arrived ----
       if (K >= 1) {
         const int b2 = (K - 1) & 1;
@@ -353,13 +326,19 @@ __global__ void __launch_bounds__(256 * NB + 32, 3 - NB) k_tag_tc2(Tc2Args a) {
         par[b1] ^= 1u;
       }
       tc::fence_after_sync();
-      float v[HF], v2[HF];
-      const uint32_t taddr = tmem + (row >> 7) * 64 + half * HF + ((uint32_t)((warp & 3) * 32) << 16);
-      tc::tmem_ld16(taddr, v);
-      tc::tmem_ld16(taddr + 32, v2);
-      tc::fence_before_sync();        // orders these TMEM reads before the next tile's "buffer written" arrival -> issuer -> overwrite of D
+      STAMP(12);   // wait for the MMAs
+      float v[HF];
+      {
+        uint32_t r1[HF], r2[HF];
+        const uint32_t taddr = tmem + (row >> 7) * 64 + half * HF + tlane;
+        tc::tmem_ld16_nowait(taddr, r1);
+        tc::tmem_ld16_nowait(taddr + 32, r2);
+        tc::tmem_wait_ld();
 #pragma unroll
-      for (int c = 0; c < HF; ++c) v[c] += v2[c];
+        for (int c = 0; c < HF; ++c) v[c] = __uint_as_float(r1[c]) + __uint_as_float(r2[c]);
+      }
+      tc::fence_before_sync();        // orders these TMEM reads before the next tile's "buffer written" arrival -> issuer -> overwrite of D
+      STAMP(13);   // TMEM loads
       if (live) {
         if (MODE == MODE_FWD) {
 #pragma unroll
@@ -417,11 +396,12 @@ __global__ void __launch_bounds__(256 * NB + 32, 3 - NB) k_tag_tc2(Tc2Args a) {
             if ((int)(half * HF) + c < ow) a.out[n * ow + half * HF + c] = v[c];
         }
       }
+      STAMP(14);   // epilogue
     }
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem, 64 * NB);
+  if (warp == 0) tc::tmem_dealloc(tmem, TMEM_COLS);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -435,7 +415,9 @@ struct GwArgs {
   const float* x;          // layer input [Nt,32]
   const float* gy;         // grad wrt layer output [Nt,cout]
   const uint32_t* bits;    // sign words or NULL
-  const float* lvl;        // [K][Nt,32] = A g, A^2 g from k_tag_tc2<BGX>
+  const float* lvl;        // [K][Nt,32] = A g, A^2 g from the backward-to-input kernel
+  const uint32_t* lvl_fmt; // device word behind the levels: 0 = plain rows, 1 = rows as k_tag_tc3 spills them (16-byte chunk c of row n
+                           // stored at chunk c ^ (n & 7): byte image of its shared-memory tiles); NULL = plain
   int cout;
   float scale;
   float* partials;         // row = blockIdx.x
@@ -497,15 +479,16 @@ __global__ void __launch_bounds__(GW_THREADS, 1) k_tag_gw(GwArgs a) {
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
-  const uint32_t tmem = *tslot;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tslot, 0);   // warp-uniform for the compiler
 
   const int64_t num_chunks = (a.num_nodes + GW_ROWS - 1) / GW_ROWS;
   const int64_t full_chunks = a.num_nodes / GW_ROWS;       // only whole chunks go through the bulk-copy engine
+  const bool lvl_swz = a.lvl_fmt && *a.lvl_fmt == 1u;      // chunk rows start at multiples of 64, so (global row & 7) == (chunk row & 7)
   float gb[4] = {0.f, 0.f, 0.f, 0.f};
   int it = 0;                                              // chunks this CTA has processed (same count in every role)
 
   if (producer) {
-    if ((tid & 31) == 0) {
+    if (tc::elect_one()) {
       const uint32_t gy_bytes = (uint32_t)(GW_ROWS * cout * 4);
       const uint32_t tx = GW_TILE * (K >= 2 ? 3 : 2) + gy_bytes + (a.bits ? 256u : 0u);
       auto issue = [&](int64_t ch, int s) {
@@ -528,7 +511,7 @@ __global__ void __launch_bounds__(GW_THREADS, 1) k_tag_gw(GwArgs a) {
     }
     __syncwarp();
   } else if (issuer) {
-    if ((tid & 31) == 0) {
+    if (tc::elect_one()) {
       const uint32_t idesc = tc::idesc_tf32(128, 64, 1, 1);
       for (int64_t ch = blockIdx.x; ch < num_chunks; ch += gridDim.x, ++it) {
         const int b = it & 1;
@@ -558,10 +541,11 @@ __global__ void __launch_bounds__(GW_THREADS, 1) k_tag_gw(GwArgs a) {
       float4 vx, vg, v1, v2;
       vx = vg = v1 = v2 = make_float4(0.f, 0.f, 0.f, 0.f);
       uint32_t word = 0xffffffffu;
+      const uint32_t cl = cq ^ (lvl_swz ? (r & 7u) : 0u);   // chunk position of columns [4 cq, 4 cq + 4) in a spilled level row
       if (staged) {
         vx = *reinterpret_cast<const float4*>(st + r * 128 + cq * 16);
-        v1 = *reinterpret_cast<const float4*>(st + 2 * GW_TILE + r * 128 + cq * 16);
-        if (K >= 2) v2 = *reinterpret_cast<const float4*>(st + 3 * GW_TILE + r * 128 + cq * 16);
+        v1 = *reinterpret_cast<const float4*>(st + 2 * GW_TILE + r * 128 + cl * 16);
+        if (K >= 2) v2 = *reinterpret_cast<const float4*>(st + 3 * GW_TILE + r * 128 + cl * 16);
         if (cout == 32) {
           vg = *reinterpret_cast<const float4*>(st + GW_TILE + r * 128 + cq * 16);
         } else {
@@ -575,8 +559,8 @@ __global__ void __launch_bounds__(GW_THREADS, 1) k_tag_gw(GwArgs a) {
         if (a.bits) word = reinterpret_cast<const uint32_t*>(st + 4 * GW_TILE)[r];
       } else if (n < a.num_nodes) {   // the one ragged chunk at the end of the batch: plain bounded loads
         vx = *reinterpret_cast<const float4*>(a.x + n * 32 + cq * 4);
-        v1 = *reinterpret_cast<const float4*>(a.lvl + n * 32 + cq * 4);
-        if (K >= 2) v2 = *reinterpret_cast<const float4*>(a.lvl + (a.num_nodes + n) * 32 + cq * 4);
+        v1 = *reinterpret_cast<const float4*>(a.lvl + n * 32 + cl * 4);
+        if (K >= 2) v2 = *reinterpret_cast<const float4*>(a.lvl + (a.num_nodes + n) * 32 + cl * 4);
         float t4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int e = 0; e < 4; ++e)
@@ -703,6 +687,7 @@ __global__ void __launch_bounds__(GWF_THREADS, 1) k_tag_gw_ffma(GwArgs a) {
 
   const uint32_t cq = tid & 7, rs = tid >> 3;          // pre-pass mapping: 16-byte column chunk, row (and row + 32)
   const int i_feat = tid & 31, c0 = (tid >> 5) * 4;    // main mapping
+  const bool lvl_swz = a.lvl_fmt && *a.lvl_fmt == 1u;
   float gb[4] = {0.f, 0.f, 0.f, 0.f};
   float acc[K + 1][4];
 #pragma unroll
@@ -725,7 +710,7 @@ __global__ void __launch_bounds__(GWF_THREADS, 1) k_tag_gw_ffma(GwArgs a) {
         reinterpret_cast<float*>(st)[idx] = inb ? a.x[(n0 + r) * 32 + j] : 0.0f;
 #pragma unroll
         for (int k = 0; k < K; ++k)
-          reinterpret_cast<float*>(st + (2 + k) * GW_TILE)[idx] = inb ? a.lvl[((int64_t)k * a.num_nodes + n0 + r) * 32 + j] : 0.0f;
+          reinterpret_cast<float*>(st + (2 + k) * GW_TILE)[idx] = inb ? a.lvl[((int64_t)k * a.num_nodes + n0 + r) * 32 + j] : 0.0f;   // byte image: keeps the level format
         if (j < cout) reinterpret_cast<float*>(st + GW_TILE)[r * cout + j] = inb ? a.gy[(n0 + r) * cout + j] : 0.0f;
         if (a.bits && j == 0) reinterpret_cast<uint32_t*>(st + (K + 2) * GW_TILE)[r] = inb ? a.bits[n0 + r] : 0u;
       }
@@ -772,7 +757,7 @@ __global__ void __launch_bounds__(GWF_THREADS, 1) k_tag_gw_ffma(GwArgs a) {
       acc[0][3] = fmaf(l0.w, xv, acc[0][3]);
 #pragma unroll
       for (int k = 1; k <= K; ++k) {
-        const float4 lk = *reinterpret_cast<const float4*>(st + (1 + k) * GW_TILE + r * 128 + c0 * 4);
+        const float4 lk = *reinterpret_cast<const float4*>(st + (1 + k) * GW_TILE + r * 128 + (((uint32_t)(c0 >> 2) ^ (lvl_swz ? (uint32_t)(r & 7) : 0u)) << 4));
         acc[k][0] = fmaf(lk.x, xv, acc[k][0]);
         acc[k][1] = fmaf(lk.y, xv, acc[k][1]);
         acc[k][2] = fmaf(lk.z, xv, acc[k][2]);
@@ -797,33 +782,66 @@ __global__ void __launch_bounds__(GWF_THREADS, 1) k_tag_gw_ffma(GwArgs a) {
   }
 }
 
-size_t tc2_smem(int K, int nb) { return 1024 + (size_t)(K + 1) * 2 * W_TILE + 4 * (size_t)nb * 128 * tc::ROW_BYTES + 256; }   // 89 KB (2 CTAs/SM) or 153 KB
+size_t tc2_smem(int K, int rw, bool ta) { return 1024 + (size_t)(K + 1) * 2 * W_TILE + (ta ? 2 : 4) * (size_t)rw * 32 * tc::ROW_BYTES + 256; }   // K = 2: 73 KB (3 CTAs/SM), 89 KB (2) or 153 KB
 size_t gw_smem(int K) { return 1024 + 2 * gw_ops_bytes(K) + GW_STAGES * GW_STAGE_BYTES + 128; }   // 128: 10 mbarriers + TMEM slot
 
 int tc2_supported(const dss2_graph_t* g, int K) {
   return g && g->num_tiles > 0 && g->max_tile_nodes <= T2_MAX && K >= 1 && K <= 2 && g->ell_w && g->ell_ci;
 }
 
-template <int MODE, int K, int NB, bool DENSE = false>
-int launch_tc2_inst(const Tc2Args& a, cudaStream_t stream) {
-  const size_t smem = tc2_smem(K, NB);
-  const int tiles = DENSE ? (int)((a.g.num_nodes + 128 * NB - 1) / (128 * NB)) : a.g.num_tiles;
-  const int grid = max(1, min(tiles, (3 - NB) * dss2_sm_count()));
-  DSS2_CUDA(cudaFuncSetAttribute(k_tag_tc2<MODE, K, NB, DENSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_tag_tc2<MODE, K, NB, DENSE><<<grid, 256 * NB + 32, smem, stream>>>(a);
+// DSS2_TC2_TA=0 selects the shared-memory A operand (the round-1 kernels) for A/B measurements
+bool tc2_use_ta() {
+  static const bool v = [] {
+    const char* e = getenv("DSS2_TC2_TA");
+    return !(e && e[0] == '0');
+  }();
+  return v;
+}
+
+template <int MODE, int K, int RW, bool DENSE, bool TA>
+int launch_tc2_inst2(const Tc2Args& a, cudaStream_t stream) {
+  using Shape = Tc2Shape<RW>;
+  const size_t smem = tc2_smem(K, RW, TA);
+  const int tiles = DENSE ? (int)((a.g.num_nodes + Shape::ROWS - 1) / Shape::ROWS) : a.g.num_tiles;
+  const int per_sm = TA ? (Shape::NB == 1 ? 2 : 1) : Shape::CTAS_PER_SM;   // TA: 256 / 512 of the SM's 512 TMEM columns per CTA
+  const int grid = max(1, min(tiles, per_sm * dss2_sm_count()));
+  DSS2_CUDA(cudaFuncSetAttribute(k_tag_tc2<MODE, K, RW, DENSE, TA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_tag_tc2<MODE, K, RW, DENSE, TA><<<grid, Shape::THREADS, smem, stream>>>(a);
   DSS2_LAUNCH_CHECK();
   return 0;
 }
+template <int MODE, int K, int RW, bool DENSE = false>
+int launch_tc2_inst(const Tc2Args& a, cudaStream_t stream) {
+  return tc2_use_ta() ? launch_tc2_inst2<MODE, K, RW, DENSE, true>(a, stream) : launch_tc2_inst2<MODE, K, RW, DENSE, false>(a, stream);
+}
+template <int MODE, int K>
+int launch_tc2_k(const Tc2Args& a, cudaStream_t stream) {
+  const int rows = a.g.max_tile_nodes;
+  if (rows <= 96 && getenv("DSS2_TC2_RW3")) return launch_tc2_inst<MODE, K, 3>(a, stream);
+  if (rows <= 128) return launch_tc2_inst<MODE, K, 4>(a, stream);
+  return launch_tc2_inst<MODE, K, 8>(a, stream);
+}
 template <int MODE>
-int launch_tc2(const Tc2Args& a, int K, cudaStream_t stream) {
-  const bool two = a.g.max_tile_nodes > 128;
-  if (K == 1) return two ? launch_tc2_inst<MODE, 1, 2>(a, stream) : launch_tc2_inst<MODE, 1, 1>(a, stream);
-  return two ? launch_tc2_inst<MODE, 2, 2>(a, stream) : launch_tc2_inst<MODE, 2, 1>(a, stream);
+int launch_tc2(const Tc2Args& a_in, int K, cudaStream_t stream) {
+  Tc2Args a = a_in;
+  static const int flags = [] { const char* e = getenv("DSS2_TC2_FLAGS"); return e ? atoi(e) : 0; }();
+  a.flags = flags;
+  return K == 1 ? launch_tc2_k<MODE, 1>(a, stream) : launch_tc2_k<MODE, 2>(a, stream);
 }
 
 }  // namespace
 
 extern "C" int dss2_tag_tc2_supported(const dss2_graph_t* g, int K) { return tc2_supported(g, K); }
+
+#ifdef DSS2_STAMPS
+// diagnostic build: read (and clear) the phase counters
+extern "C" int dss2_tc2_stamps(unsigned long long* host_out) {
+  unsigned long long zero[32] = {};
+  if (cudaMemcpyFromSymbol(host_out, g_tc2_stamps, sizeof(zero)) != cudaSuccess) return -1;
+  if (cudaMemcpyToSymbol(g_tc2_stamps, zero, sizeof(zero)) != cudaSuccess) return -1;
+  return 0;
+}
+#endif
 
 // Large-graph path (tag.cu): the transform of a layer on hop levels that already sit in global memory (lvl = [K][Nt,32], levels 1..K),
 // through the same tcgen05 kernel with plain 256-row tiles and the hop stage replaced by loads.  K in 1..2.
@@ -850,7 +868,7 @@ int dss2_tc2_dense_fwd(const dss2_graph_t* g, const float* x, const float* lvl, 
   a.res_stride = res_stride;
   a.out = y;
   a.out_bits = act_bits;
-  return K == 1 ? launch_tc2_inst<MODE_FWD, 1, 2, true>(a, stream) : launch_tc2_inst<MODE_FWD, 2, 2, true>(a, stream);
+  return K == 1 ? launch_tc2_inst<MODE_FWD, 1, 8, true>(a, stream) : launch_tc2_inst<MODE_FWD, 2, 8, true>(a, stream);
 }
 int dss2_tc2_dense_bgx(const dss2_graph_t* g, const float* grad_y, const uint32_t* act_bits, float p_drop, const float* lvl, const float* w,
                        int cout, int K, float* grad_x, cudaStream_t stream) {
@@ -863,7 +881,7 @@ int dss2_tc2_dense_bgx(const dss2_graph_t* g, const float* grad_y, const uint32_
   a.cout = cout;
   a.scale = 1.0f / (float)(1.0 - (double)p_drop);
   a.out = grad_x;
-  return K == 1 ? launch_tc2_inst<MODE_BGX, 1, 2, true>(a, stream) : launch_tc2_inst<MODE_BGX, 2, 2, true>(a, stream);
+  return K == 1 ? launch_tc2_inst<MODE_BGX, 1, 8, true>(a, stream) : launch_tc2_inst<MODE_BGX, 2, 8, true>(a, stream);
 }
 
 extern "C" int dss2_tag_fwd_tc2(const dss2_graph_t* g, const float* x, const float* w, const float* bias, int cout, int K, int act,
@@ -896,6 +914,8 @@ extern "C" int dss2_tag_fwd_tc2(const dss2_graph_t* g, const float* x, const flo
   a.res_stride = res_stride;
   a.out = y;
   a.out_bits = act_bits;
+  const int rc3 = dss2_tc3_launch(MODE_FWD, a, K, stream);   // the TMA-fed kernel when it serves the shape
+  if (rc3 <= 0) return rc3;
   return launch_tc2<MODE_FWD>(a, K, stream);
 }
 
@@ -921,6 +941,8 @@ extern "C" int dss2_tag_bwd_tc2_gx(const dss2_graph_t* g, const float* w, int co
   a.scale = 1.0f / (float)(1.0 - (double)p_drop);
   a.out = grad_x;
   a.lvl_out = (float*)ws;
+  const int rc3 = dss2_tc3_launch(MODE_BGX, a, K, stream);
+  if (rc3 <= 0) return rc3;
   return launch_tc2<MODE_BGX>(a, K, stream);
 }
 
@@ -942,6 +964,7 @@ extern "C" int dss2_tag_bwd_tc2_gw(int64_t num_nodes, const float* x, int cout, 
   b.gy = grad_y;
   b.bits = act ? act_bits : nullptr;
   b.lvl = (const float*)ws;
+  b.lvl_fmt = reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(ws) + (size_t)K * num_nodes * HID * sizeof(float));
   b.cout = cout;
   b.scale = 1.0f / (float)(1.0 - (double)p_drop);
   b.partials = partials;
@@ -968,7 +991,7 @@ extern "C" int dss2_tag_gw_ffma(int64_t num_nodes, const float* x, int cout, int
   DSS2_CHECK_ARG(x && grad_y && partials && ws, "dss2_tag_gw_ffma: null argument");
   DSS2_CHECK_ARG(cout >= 1 && cout <= HID && K >= 1 && K <= 3, "dss2_tag_gw_ffma: cout %d / K %d unsupported", cout, K);
   DSS2_CHECK_ARG(!act || act_bits, "dss2_tag_gw_ffma: activation layers need act_bits from the forward");
-  DSS2_CHECK_ARG(ws_bytes >= (size_t)K * num_nodes * HID * sizeof(float), "dss2_tag_gw_ffma: workspace too small");
+  DSS2_CHECK_ARG(ws_bytes >= dss2_tag_bwd_tc2_workspace_bytes(num_nodes, K), "dss2_tag_gw_ffma: workspace too small");
   DSS2_CHECK_ARG(partial_stride >= (int64_t)(K + 1) * cout * HID + cout, "dss2_tag_gw_ffma: partial_stride too small");
   DSS2_CHECK_ARG((((uintptr_t)x | (uintptr_t)grad_y | (uintptr_t)ws | (uintptr_t)act_bits) & 15) == 0 && (num_nodes * HID * 4) % 16 == 0,
                  "dss2_tag_gw_ffma: x, grad_y, act_bits and ws must be 16-byte aligned (bulk-copy sources)");
@@ -979,6 +1002,7 @@ extern "C" int dss2_tag_gw_ffma(int64_t num_nodes, const float* x, int cout, int
   b.gy = grad_y;
   b.bits = act ? act_bits : nullptr;
   b.lvl = (const float*)ws;
+  b.lvl_fmt = reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(ws) + (size_t)K * num_nodes * HID * sizeof(float));
   b.cout = cout;
   b.scale = 1.0f / (float)(1.0 - (double)p_drop);
   b.partials = partials;

@@ -1,0 +1,406 @@
+// (b2) TAG layer on tcgen05, third generation: k_tag_tc3 = k_tag_tc2's arithmetic with every global-memory access of the worker
+// threads moved onto the TMA engine.
+//
+// Why (clock64 stamps of one worker thread, Oberrhein B=4096, profiles/r2_stamps_tc2.txt): of the 12.3 k (forward) / 14.8 k
+// (backward-to-input) cycles a 210-row tile spent in k_tag_tc2, ~2.2 k were the next tile's row prefetch (16 warps x 7 LDG: the
+// LSU moves 64 B per cycle and the gathers of the hops queue behind it) and, in the backward, ~2.8 k the hop-level spill (8
+// STG.128 per thread).  Here
+//   * the MMA-issuer warp's elected lane lands the NEXT-BUT-ONE tile in a two-stage shared-memory ring: the 32-wide rows with one
+//     cp.async.bulk.tensor (SWIZZLE_128B tensor map: a thread then reads its own row without bank conflicts), the ELL topology and
+//     the sign words with 1-D bulk copies; the tile's node range travels through shared memory with them, so a worker issues no
+//     global load at all;
+//   * the backward's hop levels leave as ONE cp.async.bulk store per level straight from the plain level tile the next hop
+//     gathers from.  That tile is software-swizzled by the GLOBAL row (16-byte chunk c of row n sits at chunk c ^ (n & 7)), so its
+//     byte image in global memory can be un-swizzled by the weight-gradient kernel without knowing the tiling (format word 1
+//     behind the levels, see GwArgs::lvl_fmt);
+//   * the A operand lives in tensor memory as in k_tag_tc2<TA> (tcgen05.st by the thread that owns the row), so shared memory is
+//     read by generic-proxy gathers only and the sole proxy fence left is the one in front of the spill (cheap now: a worker has
+//     no global access in flight when it executes it).
+// Everything else (thread = (row, half), hop order = PyG scatter order, 3xTF32 with all four terms, epilogue) is k_tag_tc2's.
+// Served: tiled graphs, K in 1..2, forward with any cout, backward-to-input with cout == 32 (the 35 hidden layers); the caller
+// falls back to k_tag_tc2 otherwise.
+#include <cuda.h>
+
+#include "tc2_shared.cuh"
+
+namespace {
+
+// ---- tensor map (driver entry point fetched at run time: the library must load on machines without libcuda) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+// [rows, 32] fp32 row-major, box = [box_rows, 32], 128-byte swizzle, out-of-range rows read as zeros
+int make_row_map(CUtensorMap* m, const float* base, int64_t rows, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return -1;
+  const cuuint64_t dims[2] = {32, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {128};
+  const cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS
+             ? 0
+             : -1;
+}
+
+__device__ __forceinline__ void tma_load_rows(void* smem_dst, const CUtensorMap* map, int row0, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(map), "r"(0), "r"(row0), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <int RW>
+struct Tc3Smem {
+  static constexpr int ROWS = 32 * RW;
+  static constexpr uint32_t LV_TILE = ROWS * tc::ROW_BYTES;
+  // one input stage: rows (hardware swizzle, 1024-byte aligned) | ELL weights (16 B / row) | ELL columns + degree (8 B / row, the
+  // copy starts at an even row) | sign words (4 B / row, the copy starts at a multiple of 4 rows)
+  static constexpr uint32_t ST_W = LV_TILE, ST_CI = ST_W + ROWS * 16, ST_BITS = ST_CI + ROWS * 8 + 16, ST_END = ST_BITS + ROWS * 4 + 16;
+  static constexpr uint32_t STAGE = (ST_END + 1023u) & ~1023u;
+  static size_t bytes(int K) { return 1024 + 2 * (size_t)LV_TILE + 2 * (size_t)STAGE + (size_t)(K + 1) * 2 * W_TILE + 512; }
+};
+
+template <int MODE, int K, int RW>
+__global__ void __launch_bounds__(Tc2Shape<RW>::THREADS, RW == 8 ? 1 : 2) k_tag_tc3(Tc2Args a, const __grid_constant__ CUtensorMap in_map) {
+  using Shape = Tc2Shape<RW>;
+  using Sm = Tc3Smem<RW>;
+  constexpr int NB = Shape::NB;
+  constexpr int WORKERS = Shape::WORKERS;
+  constexpr int THREADS = Shape::THREADS;
+  constexpr int ROWS = Shape::ROWS;
+  constexpr uint32_t LV_TILE = Sm::LV_TILE;
+  constexpr uint32_t TMEM_COLS = NB == 1 ? 256u : 512u;   // D: 64 per block; A: [2 buffers][NB blocks][plain 32 | residual 32]
+  extern __shared__ char raw[];
+  const dss2_graph_t& g = a.g;
+  char* base = align1024(raw);
+  char* Lv = base;                                  // [2] plain level tiles (gather sources, spill sources)
+  char* St = Lv + 2 * LV_TILE;                      // [2] input stages
+  char* Wt = St + 2 * Sm::STAGE;                    // [(K+1)] x 8 KB: rows 0-31 plain W_k, rows 32-63 residual -> one N = 64 operand
+  char* tail = Wt + (K + 1) * 2 * W_TILE;
+  float* bias_s = reinterpret_cast<float*>(tail);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 128);   // [2] "MMAs (and the spill) reading buffer b have completed"
+  uint64_t* full = bars + 2;                                  // [2] "all workers have written buffer b"
+  uint64_t* in_full = full + 2;                               // [2] "input stage s has landed"
+  int* tinfo = reinterpret_cast<int*>(in_full + 2);           // [2][2] node range of the tile in stage s
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(tinfo + 4);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const bool issuer = warp == Shape::ISSUER_WARP;
+  const uint32_t row = (uint32_t)tid % ROWS, half = ((uint32_t)tid / ROWS) & 1u;
+  const int cout = a.cout;
+  const bool spill = MODE == MODE_BGX && a.lvl_out != nullptr;
+  const bool has_bits = MODE == MODE_BGX && a.in_bits != nullptr;
+
+  // ---- one-time setup ----
+  if (warp == 0) tc::tmem_alloc(tslot, TMEM_COLS);
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars[i], 1);
+      mbar_init(&full[i], WORKERS);
+      mbar_init(&in_full[i], 1);
+    }
+    fence_mbar_init();
+    if (spill && blockIdx.x == 0) *reinterpret_cast<uint32_t*>(a.lvl_out + (size_t)K * g.num_nodes * 32) = 1u;   // spill format: swizzled rows
+  }
+  for (int idx = tid; idx < (K + 1) * 32 * 32; idx += THREADS) {   // weight operand, as in k_tag_tc2
+    const int k = idx >> 10, nrow = (idx >> 5) & 31, kk = idx & 31;
+    const int c = MODE == MODE_FWD ? nrow : kk, j = MODE == MODE_FWD ? kk : nrow;
+    const float v = c < cout ? a.w[((size_t)k * cout + c) * HID + j] : 0.0f;
+    const uint32_t off = tc::swz_off((uint32_t)nrow, (uint32_t)kk);
+    *reinterpret_cast<float*>(Wt + (size_t)(2 * k) * W_TILE + off) = v;
+    *reinterpret_cast<float*>(Wt + (size_t)(2 * k + 1) * W_TILE + off) = tc::tf32_residual(v);
+  }
+  if (tid < 32) bias_s[tid] = (MODE == MODE_FWD && tid < cout) ? a.bias[tid] : 0.0f;
+  uint2 key = make_uint2(0u, 0u);
+  uint32_t step_lo = 0;
+  if (MODE == MODE_FWD && a.drop_mode == 1) {
+    const uint64_t seed = a.rng[0], step = a.rng[1];
+    key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32) ^ (a.layer_uid * 0x9E3779B9u) ^ (uint32_t)(step >> 32));
+    step_lo = (uint32_t)step;
+  }
+  fence_proxy_async();
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tslot, 0);
+  const int ntiles = g.num_tiles;
+
+  if (issuer) {
+    // ===== issuer warp: input ring, MMAs, hop-level spill (all by the elected lane) =====
+    const uint32_t idesc = tc::idesc_tf32(128, 64);
+    uint32_t fpar[2] = {0u, 0u};
+    // land tile `tn` in stage s; the node range goes with it (written before the arrive.expect_tx, which releases it)
+    auto issue_in = [&](const TileNodes& tn, int s) {
+      const int nT = tn.n1 - tn.n0;
+      if (nT <= 0) return;
+      char* st = St + (size_t)s * Sm::STAGE;
+      const int r2 = tn.n0 & ~1, r4 = tn.n0 & ~3;
+      const uint32_t ci_bytes = (uint32_t)(((tn.n0 - r2 + nT) * 8 + 15) & ~15);
+      const uint32_t bit_bytes = has_bits ? (uint32_t)(((tn.n0 - r4 + nT) * 4 + 15) & ~15) : 0u;
+      tinfo[2 * s] = tn.n0;
+      tinfo[2 * s + 1] = tn.n1;
+      mbar_expect_tx(&in_full[s], LV_TILE + (uint32_t)nT * 16u + ci_bytes + bit_bytes);
+      tma_load_rows(st, &in_map, tn.n0, &in_full[s]);
+      bulk_g2s(st + Sm::ST_W, reinterpret_cast<const char*>(g.ell_w) + (size_t)tn.n0 * 16, (uint32_t)nT * 16u, &in_full[s]);
+      bulk_g2s(st + Sm::ST_CI, reinterpret_cast<const char*>(g.ell_ci) + (size_t)r2 * 8, ci_bytes, &in_full[s]);
+      if (has_bits) bulk_g2s(st + Sm::ST_BITS, reinterpret_cast<const char*>(a.in_bits) + (size_t)r4 * 4, bit_bytes, &in_full[s]);
+    };
+    TileNodes t0 = tile_nodes(g, blockIdx.x), t1 = tile_nodes(g, blockIdx.x + gridDim.x), t2 = tile_nodes(g, blockIdx.x + 2 * gridDim.x);
+    if (tc::elect_one()) {
+      issue_in(t0, 0);
+      issue_in(t1, 1);
+    }
+    __syncwarp();
+    int it = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      const int s = it & 1;
+      const int n0 = t0.n0, nT = t0.n1 - t0.n0;
+      const int nmb = (NB == 2 && nT > 128) ? 2 : 1;
+      const TileNodes t3 = tile_nodes(g, t + 3 * gridDim.x);   // node range three tiles ahead: its loads have a whole tile to land
+#pragma unroll
+      for (int k = 0; k <= K; ++k) {
+        const int b = k & 1;
+        mbar_wait(&full[b], fpar[b]);
+        fpar[b] ^= 1u;
+        tc::fence_after_sync();
+        if (tc::elect_one()) {
+          // every worker has read stage s (it arrives on full[0] after storing level 0): refill it with the tile after next
+          if (k == 0) issue_in(t2, s);
+          if (spill && k >= 1) {
+            bulk_s2g(a.lvl_out + ((size_t)(k - 1) * g.num_nodes + n0) * 32, Lv + (size_t)b * LV_TILE, (uint32_t)nT * 128u);
+            bulk_commit();
+          }
+          const uint64_t dW = tc::smem_desc_sw128(smem_u32(Wt + (size_t)(2 * k) * W_TILE));
+          for (int mb = 0; mb < nmb; ++mb) {
+            const uint32_t aT = tmem + 64 * NB + (uint32_t)(b * NB + mb) * 64;   // plain word columns [0, 32), residual [32, 64)
+#pragma unroll
+            for (uint32_t kk = 0; kk < 4; ++kk) {
+              const uint32_t o = kk * tc::KSTEP_BYTES;
+              tc::mma_tf32_ts(tmem + mb * 64, aT + 32 + kk * 8, tc::desc_advance(dW, o), idesc, (k == 0 && kk == 0) ? 0u : 1u);
+              tc::mma_tf32_ts(tmem + mb * 64, aT + kk * 8, tc::desc_advance(dW, o), idesc, 1u);
+            }
+          }
+          if (spill && k >= 1) bulk_wait_read0();   // the level tile may be overwritten once bars[b] fires
+          tc::mma_commit(&bars[b]);
+        }
+        __syncwarp();
+      }
+      t0 = t1;
+      t1 = t2;
+      t2 = t3;
+    }
+    if (spill && tc::elect_one()) bulk_wait0();   // the spilled levels are complete in global memory before the kernel ends
+    __syncwarp();
+  } else {
+    // ===== worker warps: thread = (row, half) =====
+    uint32_t par[2] = {0u, 0u}, ipar[2] = {0u, 0u};
+    const uint32_t tlane = (uint32_t)((warp & 3) * 32) << 16;
+    uint32_t phase = 0;   // n0 & 7 of the current tile: software swizzle key of the plain level tiles = global row & 7
+    auto publish = [&](int b, bool meet, bool spilled) {
+      if (spilled) fence_proxy_async();   // the bulk store reads this thread's STS through the async proxy
+      tc::tmem_wait_st();
+      tc::fence_before_sync();
+      tc::mbar_arrive(&full[b]);
+      if (meet) named_bar_sync(1, WORKERS);
+    };
+    auto store_level = [&](const float (&v)[HF], int b, bool to_smem) {
+      if (to_smem) {
+        const uint32_t code = row_code_ph(row, phase);
+        char* pt = Lv + (size_t)b * LV_TILE;
+#pragma unroll
+        for (uint32_t q = 0; q < 4; ++q)
+          *reinterpret_cast<float4*>(pt + (code ^ ((half * 4 + q) << 4))) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      }
+      const uint32_t ta = tmem + tlane + 64 * NB + (uint32_t)(b * NB + (row >> 7)) * 64 + half * HF;
+      tc::tmem_st16(ta, v);
+      float r[HF];
+#pragma unroll
+      for (int i = 0; i < HF; ++i) r[i] = tc::tf32_residual(v[i]);
+      tc::tmem_st16(ta + 32, r);
+    };
+
+    int it = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+      const int s = it & 1;
+      const char* st = St + (size_t)s * Sm::STAGE;
+      mbar_wait(&in_full[s], ipar[s]);
+      ipar[s] ^= 1u;
+      const int n0 = tinfo[2 * s], nT = tinfo[2 * s + 1] - n0;
+      const bool live = (int)row < nT;
+      const size_t n = (size_t)n0 + row;
+      phase = (uint32_t)n0 & 7u;
+      // ---- this thread's half row and topology out of the stage (the tensor map swizzles by the stage row) ----
+      float xr[HF];
+      RowTopo tp;
+      {
+        const uint32_t code = tc::row_code(row);
+#pragma unroll
+        for (uint32_t q = 0; q < 4; ++q) {
+          const float4 v = *reinterpret_cast<const float4*>(st + (code ^ ((half * 4 + q) << 4)));
+          xr[4 * q] = v.x;
+          xr[4 * q + 1] = v.y;
+          xr[4 * q + 2] = v.z;
+          xr[4 * q + 3] = v.w;
+        }
+        tp.w = *reinterpret_cast<const float4*>(st + Sm::ST_W + row * 16);
+        const uint2 ci = *reinterpret_cast<const uint2*>(st + Sm::ST_CI + ((uint32_t)(n0 & 1) + row) * 8);
+        tp.cols = ci.x;
+        tp.deg = ci.y;
+        uint32_t word = 0xffffu;
+        if (has_bits) word = *reinterpret_cast<const uint32_t*>(st + Sm::ST_BITS + ((uint32_t)(n0 & 3) + row) * 4) >> (half * HF);
+        if (!live) word = 0u;   // rows past the tile hold the next tile's data: the MMA input of dead rows is zero
+#pragma unroll
+        for (int c = 0; c < HF; ++c) {
+          const float sc = has_bits ? xr[c] * a.scale : xr[c];
+          xr[c] = ((word >> c) & 1u) ? sc : 0.0f;
+        }
+      }
+      // ---- level 0 (buffer 0 is free: the previous tile's epilogue waited for its last MMAs) ----
+      store_level(xr, 0, true);
+      publish(0, true, false);
+      // ---- levels 1..K ----
+#pragma unroll
+      for (int k = 1; k <= K; ++k) {
+        const int b = k & 1, pb = (k - 1) & 1;
+        float h[HF];
+        if (live) hop_thread(h, g, tp, Lv + (size_t)pb * LV_TILE, n, n0, half, phase);
+        else {
+#pragma unroll
+          for (int i = 0; i < HF; ++i) h[i] = 0.0f;
+        }
+        if (k >= 2) {   // buffer b still feeds the MMAs (and the spill) of level k-2
+          mbar_wait(&bars[b], par[b]);
+          par[b] ^= 1u;
+        }
+        store_level(h, b, k < K || spill);
+        publish(b, k < K, spill);
+      }
+      // dropout keep bits do not depend on the MMAs: generate them while the tensor core finishes
+      uint32_t keep_rng = 0xffffu;
+      if (MODE == MODE_FWD && a.act && a.drop_mode == 1 && live) keep_rng = keep_half(key, (uint32_t)t, row, half, step_lo, a.keep_thr16);
+      // ---- all MMAs of the tile complete when the last two commits have arrived ----
+      if (K >= 1) {
+        const int b2 = (K - 1) & 1;
+        mbar_wait(&bars[b2], par[b2]);
+        par[b2] ^= 1u;
+      }
+      {
+        const int b1 = K & 1;
+        mbar_wait(&bars[b1], par[b1]);
+        par[b1] ^= 1u;
+      }
+      tc::fence_after_sync();
+      float v[HF];
+      {
+        uint32_t r1[HF], r2[HF];
+        const uint32_t taddr = tmem + (row >> 7) * 64 + half * HF + tlane;
+        tc::tmem_ld16_nowait(taddr, r1);
+        tc::tmem_ld16_nowait(taddr + 32, r2);
+        tc::tmem_wait_ld();
+#pragma unroll
+        for (int c = 0; c < HF; ++c) v[c] = __uint_as_float(r1[c]) + __uint_as_float(r2[c]);
+      }
+      tc::fence_before_sync();        // orders these TMEM reads before the next tile's "buffer written" arrival -> issuer -> overwrite of D
+      if (live) {
+        if (MODE == MODE_FWD) {
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            const float4 bq = *reinterpret_cast<const float4*>(bias_s + half * HF + 4 * c4);
+            v[4 * c4 + 0] += bq.x;
+            v[4 * c4 + 1] += bq.y;
+            v[4 * c4 + 2] += bq.z;
+            v[4 * c4 + 3] += bq.w;
+          }
+          if (a.act) {
+            uint32_t keep = 0xffffu;
+            if (a.drop_mode == 1) {
+              keep = keep_rng;
+            } else if (a.drop_mode == 2) {
+              const uint4 m0 = *reinterpret_cast<const uint4*>(a.mask + n * HID + half * HF);
+              const uint32_t mw[4] = {m0.x, m0.y, m0.z, m0.w};
+              keep = 0u;
+#pragma unroll
+              for (int c = 0; c < HF; ++c) keep |= (((mw[c >> 2] >> ((c & 3) * 8)) & 0xffu) != 0u ? 1u : 0u) << c;
+            }
+            uint32_t word = 0u;
+#pragma unroll
+            for (int c = 0; c < HF; ++c) {
+              float xv = v[c];
+              if (a.drop_mode != 0) xv = ((keep >> c) & 1u) ? xv * a.scale : 0.0f;
+              xv = fmaxf(xv, 0.0f);
+              word |= (xv > 0.0f ? 1u : 0u) << c;
+              v[c] = xv;
+            }
+            if (a.out_bits) reinterpret_cast<uint16_t*>(a.out_bits)[2 * n + half] = (uint16_t)word;   // little endian halves
+          }
+          if (a.res) {
+#pragma unroll
+            for (int c = 0; c < HF; ++c)
+              if ((int)(half * HF) + c < cout) v[c] += a.res[n * a.res_stride + half * HF + c];
+          }
+        }
+        const int ow = MODE == MODE_FWD ? cout : 32;
+        if (ow == 32) {
+          float4* dst = reinterpret_cast<float4*>(a.out + n * 32 + half * HF);
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) dst[c4] = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+        } else if (ow == 8) {
+          if (half == 0) {
+            float4* dst = reinterpret_cast<float4*>(a.out + n * 8);
+            dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+            dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+          }
+        } else if (ow == 2) {
+          if (half == 0) *reinterpret_cast<float2*>(a.out + n * 2) = make_float2(v[0], v[1]);
+        } else {
+#pragma unroll
+          for (int c = 0; c < HF; ++c)
+            if ((int)(half * HF) + c < ow) a.out[n * ow + half * HF + c] = v[c];
+        }
+      }
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, TMEM_COLS);
+}
+
+template <int MODE, int K, int RW>
+int launch_tc3(const Tc2Args& a, cudaStream_t stream) {
+  using Shape = Tc2Shape<RW>;
+  CUtensorMap map;
+  if (make_row_map(&map, a.in, a.g.num_nodes, Shape::ROWS)) return 1;   // no driver entry point / rejected: the caller falls back
+  const size_t smem = Tc3Smem<RW>::bytes(K);
+  const int grid = max(1, min(a.g.num_tiles, (RW == 8 ? 1 : 2) * dss2_sm_count()));
+  DSS2_CUDA(cudaFuncSetAttribute(k_tag_tc3<MODE, K, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_tag_tc3<MODE, K, RW><<<grid, Shape::THREADS, smem, stream>>>(a, map);
+  DSS2_LAUNCH_CHECK();
+  return 0;
+}
+template <int MODE, int K>
+int launch_tc3_k(const Tc2Args& a, cudaStream_t stream) {
+  return a.g.max_tile_nodes <= 128 ? launch_tc3<MODE, K, 4>(a, stream) : launch_tc3<MODE, K, 8>(a, stream);
+}
+
+}  // namespace
+
+int dss2_tc3_launch(int mode, const Tc2Args& a, int K, cudaStream_t stream) {
+  static const bool enabled = [] {
+    const char* e = getenv("DSS2_TC3");
+    return !(e && e[0] == '0');
+  }();
+  const dss2_graph_t& g = a.g;
+  if (!enabled || g.num_tiles <= 0 || g.max_tile_nodes > T2_MAX || K < 1 || K > 2 || !g.ell_w || !g.ell_ci) return 1;
+  if (mode == MODE_BGX && a.cout != 32) return 1;                         // narrow grad_y rows: k_tag_tc2 loads them directly
+  if ((((uintptr_t)a.in | (uintptr_t)a.in_bits | (uintptr_t)a.lvl_out) & 15) != 0) return 1;   // TMA / bulk-copy alignment
+  if (mode == MODE_FWD) return K == 1 ? launch_tc3_k<MODE_FWD, 1>(a, stream) : launch_tc3_k<MODE_FWD, 2>(a, stream);
+  return K == 1 ? launch_tc3_k<MODE_BGX, 1>(a, stream) : launch_tc3_k<MODE_BGX, 2>(a, stream);
+}
