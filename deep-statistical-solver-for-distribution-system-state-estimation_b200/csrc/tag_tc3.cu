@@ -23,6 +23,36 @@
 
 #include "tc2_shared.cuh"
 
+#ifdef DSS2_STAMPS
+// diagnostic build only (tools/stamps.sh): per-phase clock64 totals of worker thread 0 and of the issuer of CTA 0
+__device__ unsigned long long g_tc3_stamps[32];
+#define STAMP(i)                                                    \
+  do {                                                              \
+    if (blockIdx.x == 0 && (tid == 0)) {                            \
+      const long long now_ = clock64();                             \
+      g_tc3_stamps[i] += (unsigned long long)(now_ - stamp_prev_);  \
+      stamp_prev_ = now_;                                           \
+    }                                                               \
+  } while (0)
+#define STAMP_I(i)                                                  \
+  do {                                                              \
+    if (blockIdx.x == 0 && (tid & 31) == 0) {                       \
+      const long long now_ = clock64();                             \
+      g_tc3_stamps[i] += (unsigned long long)(now_ - stamp_prev_);  \
+      stamp_prev_ = now_;                                           \
+    }                                                               \
+  } while (0)
+extern "C" int dss2_tc3_stamps(unsigned long long* host_out) {
+  unsigned long long zero[32] = {};
+  if (cudaMemcpyFromSymbol(host_out, g_tc3_stamps, sizeof(zero)) != cudaSuccess) return -1;
+  if (cudaMemcpyToSymbol(g_tc3_stamps, zero, sizeof(zero)) != cudaSuccess) return -1;
+  return 0;
+}
+#else
+#define STAMP(i)
+#define STAMP_I(i)
+#endif
+
 namespace {
 
 // ---- tensor map (driver entry point fetched at run time: the library must load on machines without libcuda) ----
@@ -87,10 +117,11 @@ __global__ void __launch_bounds__(Tc2Shape<RW>::THREADS, RW == 8 ? 1 : 2) k_tag_
   char* Wt = St + 2 * Sm::STAGE;                    // [(K+1)] x 8 KB: rows 0-31 plain W_k, rows 32-63 residual -> one N = 64 operand
   char* tail = Wt + (K + 1) * 2 * W_TILE;
   float* bias_s = reinterpret_cast<float*>(tail);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 128);   // [2] "MMAs (and the spill) reading buffer b have completed"
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail + 128);   // [2] "MMAs reading TMEM buffer b have completed"            (tcgen05.commit)
   uint64_t* full = bars + 2;                                  // [2] "all workers have written buffer b"
   uint64_t* in_full = full + 2;                               // [2] "input stage s has landed"
-  int* tinfo = reinterpret_cast<int*>(in_full + 2);           // [2][2] node range of the tile in stage s
+  uint64_t* sp_done = in_full + 2;                            // [2] "the spill has read plain tile b" (once per tile and buffer)
+  int* tinfo = reinterpret_cast<int*>(sp_done + 2);           // [2][2] node range of the tile in stage s
   uint32_t* tslot = reinterpret_cast<uint32_t*>(tinfo + 4);
   const int tid = threadIdx.x, warp = tid >> 5;
   const bool issuer = warp == Shape::ISSUER_WARP;
@@ -106,6 +137,7 @@ __global__ void __launch_bounds__(Tc2Shape<RW>::THREADS, RW == 8 ? 1 : 2) k_tag_
       mbar_init(&bars[i], 1);
       mbar_init(&full[i], WORKERS);
       mbar_init(&in_full[i], 1);
+      mbar_init(&sp_done[i], 1);
     }
     fence_mbar_init();
     if (spill && blockIdx.x == 0) *reinterpret_cast<uint32_t*>(a.lvl_out + (size_t)K * g.num_nodes * 32) = 1u;   // spill format: swizzled rows
@@ -160,6 +192,9 @@ __global__ void __launch_bounds__(Tc2Shape<RW>::THREADS, RW == 8 ? 1 : 2) k_tag_
     }
     __syncwarp();
     int it = 0;
+#ifdef DSS2_STAMPS
+    long long stamp_prev_ = clock64();
+#endif
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
       const int s = it & 1;
       const int n0 = t0.n0, nT = t0.n1 - t0.n0;
@@ -170,6 +205,7 @@ __global__ void __launch_bounds__(Tc2Shape<RW>::THREADS, RW == 8 ? 1 : 2) k_tag_
         const int b = k & 1;
         mbar_wait(&full[b], fpar[b]);
         fpar[b] ^= 1u;
+        STAMP_I(16 + 2 * k);
         tc::fence_after_sync();
         if (tc::elect_one()) {
           // every worker has read stage s (it arrives on full[0] after storing level 0): refill it with the tile after next
@@ -188,10 +224,14 @@ __global__ void __launch_bounds__(Tc2Shape<RW>::THREADS, RW == 8 ? 1 : 2) k_tag_
               tc::mma_tf32_ts(tmem + mb * 64, aT + kk * 8, tc::desc_advance(dW, o), idesc, 1u);
             }
           }
-          if (spill && k >= 1) bulk_wait_read0();   // the level tile may be overwritten once bars[b] fires
           tc::mma_commit(&bars[b]);
+          if (spill && k >= 1) {   // the plain tile may be overwritten once the bulk engine has read it (separate from the MMAs' commit:
+            bulk_wait_read0();     // the epilogue only waits for the accumulators)
+            tc::mbar_arrive(&sp_done[b]);
+          }
         }
         __syncwarp();
+        STAMP_I(17 + 2 * k);
       }
       t0 = t1;
       t1 = t2;
@@ -201,7 +241,7 @@ __global__ void __launch_bounds__(Tc2Shape<RW>::THREADS, RW == 8 ? 1 : 2) k_tag_
     __syncwarp();
   } else {
     // ===== worker warps: thread = (row, half) =====
-    uint32_t par[2] = {0u, 0u}, ipar[2] = {0u, 0u};
+    uint32_t par[2] = {0u, 0u}, ipar[2] = {0u, 0u}, spar[2] = {0u, 0u};
     const uint32_t tlane = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t phase = 0;   // n0 & 7 of the current tile: software swizzle key of the plain level tiles = global row & 7
     auto publish = [&](int b, bool meet, bool spilled) {
@@ -228,11 +268,15 @@ __global__ void __launch_bounds__(Tc2Shape<RW>::THREADS, RW == 8 ? 1 : 2) k_tag_
     };
 
     int it = 0;
+#ifdef DSS2_STAMPS
+    long long stamp_prev_ = clock64();
+#endif
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
       const int s = it & 1;
       const char* st = St + (size_t)s * Sm::STAGE;
       mbar_wait(&in_full[s], ipar[s]);
       ipar[s] ^= 1u;
+      STAMP(0);   // wait for the input stage
       const int n0 = tinfo[2 * s], nT = tinfo[2 * s + 1] - n0;
       const bool live = (int)row < nT;
       const size_t n = (size_t)n0 + row;
@@ -263,9 +307,16 @@ __global__ void __launch_bounds__(Tc2Shape<RW>::THREADS, RW == 8 ? 1 : 2) k_tag_
           xr[c] = ((word >> c) & 1u) ? sc : 0.0f;
         }
       }
-      // ---- level 0 (buffer 0 is free: the previous tile's epilogue waited for its last MMAs) ----
+      // ---- level 0 (TMEM buffer 0 is free: the previous tile's epilogue waited for its last MMAs; the plain tile once the
+      //      previous tile's spill of the level that shared it has been read) ----
+      if (spill && K >= 2 && it > 0) {
+        mbar_wait(&sp_done[0], spar[0]);
+        spar[0] ^= 1u;
+      }
       store_level(xr, 0, true);
+      STAMP(1);   // stage read + store L0
       publish(0, true, false);
+      STAMP(2);
       // ---- levels 1..K ----
 #pragma unroll
       for (int k = 1; k <= K; ++k) {
@@ -276,16 +327,25 @@ __global__ void __launch_bounds__(Tc2Shape<RW>::THREADS, RW == 8 ? 1 : 2) k_tag_
 #pragma unroll
           for (int i = 0; i < HF; ++i) h[i] = 0.0f;
         }
-        if (k >= 2) {   // buffer b still feeds the MMAs (and the spill) of level k-2
+        STAMP(3 + 4 * (k - 1));
+        if (k >= 2) {   // TMEM buffer b still feeds the MMAs of level k-2
           mbar_wait(&bars[b], par[b]);
           par[b] ^= 1u;
         }
+        if (spill && k == 1 && it > 0) {   // plain tile 1: the previous tile's level-1 spill (level 2 shares tile 0 with the unspilled level 0)
+          mbar_wait(&sp_done[1], spar[1]);
+          spar[1] ^= 1u;
+        }
+        STAMP(4 + 4 * (k - 1));
         store_level(h, b, k < K || spill);
+        STAMP(5 + 4 * (k - 1));
         publish(b, k < K, spill);
+        STAMP(6 + 4 * (k - 1));
       }
       // dropout keep bits do not depend on the MMAs: generate them while the tensor core finishes
       uint32_t keep_rng = 0xffffu;
       if (MODE == MODE_FWD && a.act && a.drop_mode == 1 && live) keep_rng = keep_half(key, (uint32_t)t, row, half, step_lo, a.keep_thr16);
+      STAMP(11);
       // ---- all MMAs of the tile complete when the last two commits have arrived ----
       if (K >= 1) {
         const int b2 = (K - 1) & 1;
@@ -298,6 +358,7 @@ __global__ void __launch_bounds__(Tc2Shape<RW>::THREADS, RW == 8 ? 1 : 2) k_tag_
         par[b1] ^= 1u;
       }
       tc::fence_after_sync();
+      STAMP(12);
       float v[HF];
       {
         uint32_t r1[HF], r2[HF];
@@ -309,6 +370,7 @@ __global__ void __launch_bounds__(Tc2Shape<RW>::THREADS, RW == 8 ? 1 : 2) k_tag_
         for (int c = 0; c < HF; ++c) v[c] = __uint_as_float(r1[c]) + __uint_as_float(r2[c]);
       }
       tc::fence_before_sync();        // orders these TMEM reads before the next tile's "buffer written" arrival -> issuer -> overwrite of D
+      STAMP(13);
       if (live) {
         if (MODE == MODE_FWD) {
 #pragma unroll
@@ -349,9 +411,7 @@ __global__ void __launch_bounds__(Tc2Shape<RW>::THREADS, RW == 8 ? 1 : 2) k_tag_
         }
         const int ow = MODE == MODE_FWD ? cout : 32;
         if (ow == 32) {
-          float4* dst = reinterpret_cast<float4*>(a.out + n * 32 + half * HF);
-#pragma unroll
-          for (int c4 = 0; c4 < 4; ++c4) dst[c4] = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+          // stored below, after a 4x4 lane transpose
         } else if (ow == 8) {
           if (half == 0) {
             float4* dst = reinterpret_cast<float4*>(a.out + n * 8);
@@ -366,6 +426,35 @@ __global__ void __launch_bounds__(Tc2Shape<RW>::THREADS, RW == 8 ? 1 : 2) k_tag_
             if ((int)(half * HF) + c < ow) a.out[n * ow + half * HF + c] = v[c];
         }
       }
+      if ((MODE == MODE_FWD ? cout : 32) == 32) {
+        // A thread holds 64 contiguous bytes of ITS row, so a plain STG.128 of the warp touches 32 different 128-byte lines (16 bytes
+        // each): ~2000 cycles per tile in the stamps.  Transpose 4x4 chunks inside each group of 4 lanes (rows 4g..4g+3): lane i ends
+        // up with chunk i of all four rows, and one warp store then writes 8 rows x 64 contiguous bytes.
+        const uint32_t li = (uint32_t)tid & 3u;
+        float4 c[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) c[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        auto sel = [](bool p, const float4& x, const float4& y) { return p ? x : y; };
+        auto xchg = [](const float4& x, int m) {
+          return make_float4(__shfl_xor_sync(0xffffffffu, x.x, m), __shfl_xor_sync(0xffffffffu, x.y, m), __shfl_xor_sync(0xffffffffu, x.z, m),
+                             __shfl_xor_sync(0xffffffffu, x.w, m));
+        };
+        const bool hi2 = li & 2u, hi1 = li & 1u;
+        // step A (lanes i, i^2): lane keeps the chunk pair {0,1} (i < 2) or {2,3} of its own row and of row i^2
+        const float4 ra0 = xchg(sel(hi2, c[0], c[2]), 2), ra1 = xchg(sel(hi2, c[1], c[3]), 2);
+        const float4 b0 = sel(hi2, ra0, c[0]), b1 = sel(hi2, ra1, c[1]), b2 = sel(hi2, c[2], ra0), b3 = sel(hi2, c[3], ra1);
+        // step B (lanes i, i^1): lane keeps chunk i of its two rows and receives chunk i of the partner's two rows
+        const float4 rb0 = xchg(sel(hi1, b0, b1), 1), rb1 = xchg(sel(hi1, b2, b3), 1);
+        const float4 k0 = sel(hi1, b1, b0), k1 = sel(hi1, b3, b2);
+        const float4 w0 = sel(hi1, rb0, k0), w1 = sel(hi1, k0, rb0), w2 = sel(hi1, rb1, k1), w3 = sel(hi1, k1, rb1);
+        const uint32_t rbase = row & ~3u;
+        float* dst = a.out + ((size_t)n0 + rbase) * 32 + (half * 4 + li) * 4;
+        if ((int)rbase + 0 < nT) *reinterpret_cast<float4*>(dst) = w0;
+        if ((int)rbase + 1 < nT) *reinterpret_cast<float4*>(dst + 32) = w1;
+        if ((int)rbase + 2 < nT) *reinterpret_cast<float4*>(dst + 64) = w2;
+        if ((int)rbase + 3 < nT) *reinterpret_cast<float4*>(dst + 96) = w3;
+      }
+      STAMP(14);
     }
   }
   tc::fence_before_sync();

@@ -10,7 +10,7 @@ import torch  # noqa: E402
 from dss2 import _lib, synth  # noqa: E402
 from dss2.trainer import GraphedTrainer, default_spec  # noqa: E402
 
-NAMES = ["tile top", "store L0", "publish L0", "hop 1", "wait buffer 1", "store L1", "publish L1", "hop 2", "wait buffer 2", "store L2",
+NAMES = ["tile top / wait input", "store L0", "publish L0", "hop 1", "wait buffer 1", "store L1", "publish L1", "hop 2", "wait buffer 2", "store L2",
          "publish L2", "prefetch/rng", "wait MMAs", "TMEM ld", "epilogue"]
 
 
@@ -20,13 +20,14 @@ def main():
     store = synth.synthetic_store(synth.load_grid("ober_sub"), B, seed=1, device=dev)
     tr = GraphedTrainer(store, B, spec=default_spec(), seed=0, use_cuda_graph=False)
     lib, P = _lib.load(), _lib.ptr
-    lib.dss2_tc2_stamps.restype = ctypes.c_int
-    lib.dss2_tc2_stamps.argtypes = [ctypes.c_void_p]
+    getter = lib.dss2_tc2_stamps if os.environ.get("DSS2_TC3") == "0" else lib.dss2_tc3_stamps
+    getter.restype = ctypes.c_int
+    getter.argtypes = [ctypes.c_void_p]
     run, bufs, sp = tr.runner, tr.bufs, tr.spec
     tr._enqueue(with_optimizer=False)
     torch.cuda.synchronize()
     buf = (ctypes.c_ulonglong * 32)()
-    lib.dss2_tc2_stamps(buf)
+    getter(buf)
     name_w, name_b = "mpns.0.convs.3.lins.0.weight", "mpns.0.convs.3.bias"
     wp, bp = run._p(tr.flat, name_w), run._p(tr.flat, name_b)
     g = tr.graph
@@ -37,7 +38,7 @@ def main():
 
     def show(title, tiles_cta0):
         torch.cuda.synchronize()
-        lib.dss2_tc2_stamps(buf)
+        getter(buf)
         v = [int(buf[i]) for i in range(32)]
         tot = sum(v[:15])
         n = reps * tiles_cta0
