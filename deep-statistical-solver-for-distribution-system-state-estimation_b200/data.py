@@ -64,6 +64,7 @@ class _WlsFunction(torch.autograd.Function):
         if staged:   # reproduce the in-place slack masking on the caller's tensor (data.py:412-413)
             output[:, 1].copy_(out_c[:, 1])
         ctx.mark_dirty(output)
+        ctx.set_materialize_grads(False)     # an unused `output` result arrives as None in backward instead of a zero tensor
         ctx.grad = grad
         ctx.slack_keep = None
         if need_grad:
@@ -73,7 +74,10 @@ class _WlsFunction(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_loss, g_output):
-        g = ctx.grad * g_loss.to(ctx.grad.device)
+        if g_loss is None:
+            g = torch.zeros_like(ctx.grad)
+        else:
+            g = ctx.grad * g_loss.to(ctx.grad.device)
         if g_output is not None:   # gradient arriving through later uses of the (masked) output tensor
             go = g_output.to(g.device)
             g = g + torch.stack([go[:, 0], go[:, 1] * ctx.slack_keep], dim=1)
@@ -149,10 +153,23 @@ def data_from_pickles(folder, num_nfeat, num_efeat, num_nmeas, num_emeas, meas_v
         zn[s] = np.random.standard_normal((N, 4))
         ze[s] = np.random.standard_normal((E, 2))
     st = build_scenario_store(nodes, edges, labels, noise, meas_v, meas_pflow, zn, ze, num_nfeat, num_efeat)
+    cls = _graph_class()
     graphs = []
     for s in range(S):
         g = st.graph(s)
-        d = Data(x=g["x"], edge_index=g["edge_index"], edge_attr=g["edge_attr"], y=g["y"])
+        d = cls(x=g["x"], edge_index=g["edge_index"], edge_attr=g["edge_attr"], y=g["y"])
         d.validate(raise_on_error=True)
         graphs.append(d)
     return graphs, st.x_mean, st.x_std, st.edge_mean, st.edge_std
+
+
+def _graph_class():
+    """The reference returns `torch_geometric.data.Data` objects (data.py:198) and the unmodified script batches them with
+    `torch_geometric.loader.DataLoader` (dss2_run.py:18,68-69), whose collater only accepts PyG's own `BaseData` types.  So when
+    torch_geometric is importable the graphs ARE PyG `Data`; only without it (this image has no torch_geometric) they are the
+    structurally identical `dss2.batching.Data`, to be batched with `dss2.batching.DataLoader`."""
+    try:
+        from torch_geometric.data import Data as PygData
+        return PygData
+    except ImportError:
+        return Data

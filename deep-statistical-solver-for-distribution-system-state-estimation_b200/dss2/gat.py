@@ -161,7 +161,7 @@ class _GATFunction(torch.autograd.Function):
         graph = resolve_graph(edge_index, xg.size(0))
         with torch.cuda.device(xg.device):
             flat = pack.gather(named)
-            bufs = runner.alloc(xg.size(0), xg.device, need_grad=any(p.requires_grad for p in params) or x.requires_grad)
+            bufs = runner.alloc(xg.size(0), xg.device, need_grad=any(ctx.needs_input_grad))   # False under torch.no_grad()
             out = runner.forward(graph, xg, xs, eag, eas, flat, bufs)
         ctx.runner, ctx.pack, ctx.names, ctx.graph, ctx.params = runner, pack, names, graph, params
         ctx.saved = (xg, xs, eag, eas, flat, bufs)

@@ -306,7 +306,9 @@ class _PFNFunction(torch.autograd.Function):
         graph = resolve_graph(edge_index, xg.size(0))
         with torch.cuda.device(xg.device):
             flat = pack.gather(named)
-            need_grad = any(p.requires_grad for p in params)
+            # inside Function.forward grad mode is always off: whether a backward can follow is what needs_input_grad says
+            # (False under torch.no_grad(), e.g. the script's validation loop: no gradient workspaces are allocated then)
+            need_grad = any(ctx.needs_input_grad[8:])
             bufs = runner.alloc(xg.size(0), xg.device, need_grad=need_grad)
             if masks is not None:
                 mode = 2
@@ -316,6 +318,8 @@ class _PFNFunction(torch.autograd.Function):
             if mode == 1 and rng_state is None:
                 rng_state = fresh_rng_state(xg.device)
             out = runner.forward(graph, xg, xs, eag, eas, flat, bufs, drop_mode=mode, rng_state=rng_state, masks=masks)
+        if getattr(runner, "keep_last_bufs", False):     # tests read the sign words of the last forward
+            runner.last_bufs = bufs
         ctx.runner, ctx.pack, ctx.names, ctx.graph = runner, pack, names, graph
         ctx.saved = (xg, xs, eag, eas, flat, bufs, masks, rng_state)
         ctx.param_devices_cpu = params[0].device.type != "cuda"
@@ -344,6 +348,10 @@ def fresh_rng_state(device):
 
 
 def pfn_apply(runner, pack, named_params, x, edge_index, edge_attr, masks=None, rng_state=None):
+    if torch.is_grad_enabled() and (x.requires_grad or edge_attr.requires_grad):
+        raise _lib.Dss2Error("MPN / SkipMPN / PFN / SkipPFN: gradients are computed w.r.t. the parameters only; x / edge_attr with "
+                             "requires_grad=True would silently get none (the reference's data tensors never require grad, "
+                             "dss2_run.py:138) - detach them first")
     names = tuple(named_params.keys())
     return _PFNFunction.apply(x, edge_attr, edge_index, runner, pack, names, masks, rng_state, *named_params.values())
 

@@ -28,7 +28,10 @@ def default_spec(p_drop=0.3, L=5, n_layers=8, K=2, dim_out=2, fn=8, fe=6):
 
 class GraphedTrainer:
     def __init__(self, store, batch_graphs, spec=None, reg_coefs=None, lr=3e-3, seed=0, init_state_dict=None,
-                 process_group=None, world_size=1, use_cuda_graph=True):
+                 process_group=None, world_size=1, use_cuda_graph=True, dropout_stream=None):
+        """seed: parameter initialisation (all ranks must agree; rank 0's parameters are broadcast anyway).
+        dropout_stream: index of this replica's dropout stream (default: its rank, so that every shard draws its own masks;
+        pass the same value on all ranks to reproduce a single-GPU run on identical shards)."""
         self.lib = _lib.load()
         self.spec = spec or default_spec()
         self.store = store
@@ -54,7 +57,13 @@ class GraphedTrainer:
             self.flat_grad = torch.zeros_like(self.flat)
             self.exp_avg = torch.zeros_like(self.flat)
             self.exp_inf = torch.zeros_like(self.flat)
-            self.step_state = torch.tensor([seed * 2654435761 % (2 ** 62) + 12345, 0], **i64)   # {philox seed, step}
+            rank = torch.distributed.get_rank(process_group) if (self.world > 1 and torch.distributed.is_initialized()) else 0
+            stream_id = rank if dropout_stream is None else int(dropout_stream)
+            philox_seed = (seed * 2654435761 + stream_id * 0x9E3779B97F4A7C15) % (2 ** 62) + 12345
+            self.step_state = torch.tensor([philox_seed, 0], **i64)   # {philox seed, step}
+            if self.world > 1 and torch.distributed.is_initialized():
+                torch.distributed.broadcast(self.flat, src=torch.distributed.get_global_rank(process_group, 0) if process_group is not None else 0,
+                                            group=process_group)
             # static batch buffers
             self.ids = torch.zeros(self.B, **i64)
             self.batch = {
@@ -120,6 +129,8 @@ class GraphedTrainer:
     def capture(self):
         """Warm up eagerly (also counts the launches of one step), then capture the step into a CUDA graph."""
         with torch.cuda.device(self.dev):
+            # the warm-up steps are real steps: put the trainable state back afterwards so that the user's first step() is step 1
+            keep = [t.clone() for t in (self.flat, self.exp_avg, self.exp_inf, self.step_state)]
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
@@ -129,6 +140,8 @@ class GraphedTrainer:
                     self.launches_per_step = _lib.launch_count() - before + (1 if self.world > 1 else 0)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
+            for t, k in zip((self.flat, self.exp_avg, self.exp_inf, self.step_state), keep):
+                t.copy_(k)
             if self.use_cuda_graph:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):

@@ -24,6 +24,17 @@ from dss2 import ops
 from dss2.ops import PFNSpec
 
 
+class _LazyMachinery:
+    """The launch machinery (runner with the ctypes library handle, flat parameter pack) is a per-object cache in `__dict__`; it must
+    not travel with copy.deepcopy / pickle / torch.save(model) - ctypes function pointers cannot be pickled - and is rebuilt on the
+    next forward."""
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state.pop("_dss2_machinery", None)
+        return state
+
+
 class TAGConv(nn.Module):
     """Parameter container with PyG TAGConv's names: lins.{0..K}.weight [out, in] (no bias), bias [out]
     (zero-initialised).  Inside MPN the fused layer kernel consumes the parameters directly; called on its
@@ -54,7 +65,7 @@ class EdgeAggregation(nn.Module):
                                     self.edge_aggr[2].weight, self.edge_aggr[2].bias)
 
 
-class _Stack(nn.Module):
+class _Stack(_LazyMachinery, nn.Module):
     """Shared machinery of MPN / SkipMPN / PFN / SkipPFN: spec, flat parameter pack, fused launch sequence."""
     _dss2_masks = None        # test hook: [sub-net][layer] 0/1 masks consumed by the next forward (exact torch parity)
     _dss2_rng_state = None    # optional device int64 {seed, step} for the in-kernel Philox dropout
@@ -157,7 +168,7 @@ class _GINEParams(nn.Module):
         self.lin = nn.Linear(edge_dim, shared_nn.in_features)
 
 
-class GINE_DSSE(nn.Module):
+class GINE_DSSE(_LazyMachinery, nn.Module):
     """networks.py:71-111: (num_layers - 1) x [GINEConv(nn, eps, train_eps, edge_dim) + LeakyReLU()], Linear(dim_feat, dim_dense),
     Linear(dim_dense, dim_out) inside a PyG `Sequential` (children `module_{i}`).  As in the reference, `nn` is ONE
     Linear(dim_feat, dim_feat) shared by all layers (it also appears as `model.module_{2l}.nn.*` in the state_dict)."""
@@ -222,7 +233,7 @@ class _GATv2Params(nn.Module):
         nn.init.xavier_uniform_(self.att)
 
 
-class GAT_DSSE(nn.Module):
+class GAT_DSSE(_LazyMachinery, nn.Module):
     """networks.py:113-156, the as-shipped default model of dss2_run.py:86: (num_layers - 1) x [GATv2Conv(dim_feat, dim_feat, heads,
     edge_dim, add_self_loops, fill 'mean') + LeakyReLU()], Linear(dim_feat, dim_dense), Linear(dim_dense, dim_out), wrapped in a PyG
     `Sequential` whose children are called `module_{i}` - kept, so that reference checkpoints (`model.module_0.att`, ...) load.

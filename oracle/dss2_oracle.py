@@ -122,14 +122,23 @@ def tag_conv(x, edge_index, weights, bias, edge_w=None):
     return out + bias
 
 
-def dropout_relu(x, p, mask=None, generator=None):
+def dropout_relu(x, p, mask=None, generator=None, gate=None, trace=None):
     """networks.py:268-269: a freshly built nn.Dropout is always in training mode, so the mask is
     applied in eval too.  x * (mask / (1 - p)) is torch's CPU formulation.  `mask` (0/1, same shape)
-    injects a recorded mask; otherwise one is drawn (p=0 -> identity)."""
+    injects a recorded mask; otherwise one is drawn (p=0 -> identity).
+
+    Test hooks (not reference behaviour): `trace` collects the pre-activation (dropout applied, before the
+    ReLU); `gate` (0/1) REPLACES mask and ReLU by a fixed pass pattern, y = x * gate / (1 - p) - used to
+    evaluate the gradient at the other side of a ReLU tie (pre-activation ~1e-7 in one fp32
+    implementation, <= 0 in another), where relu' is implementation dependent."""
+    if gate is not None:
+        return x * (gate.to(x.dtype) / (1.0 - p))
     if p > 0.0:
         if mask is None:
             mask = torch.empty_like(x).bernoulli_(1.0 - p, generator=generator)
         x = x * (mask.to(x.dtype) / (1.0 - p))
+    if trace is not None:
+        trace.append(x.detach())
     return torch.relu(x)
 
 
@@ -147,9 +156,9 @@ def _layer_params(sd, prefix):
     return ws, sd[f"{prefix}bias"]
 
 
-def mpn_forward(sd, prefix, x, edge_index, edge_attr, p_drop, skip, masks=None, generator=None):
+def mpn_forward(sd, prefix, x, edge_index, edge_attr, p_drop, skip, masks=None, generator=None, gates=None, trace=None):
     """networks.py:260-273 (MPN) and :323-338 (SkipMPN, `skip=True` adds the input back, :336).
-    `masks`: optional list with one 0/1 tensor per hidden TAG layer."""
+    `masks`: optional list with one 0/1 tensor per hidden TAG layer (`gates`, `trace`: test hooks of dropout_relu)."""
     x_in = x
     ei2, ea2 = undirect(edge_index, edge_attr)
     x = edge_aggregation(x, ei2, ea2,
@@ -162,11 +171,12 @@ def mpn_forward(sd, prefix, x, edge_index, edge_attr, p_drop, skip, masks=None, 
         ws, b = _layer_params(sd, f"{prefix}convs.{layer}.")
         x = tag_conv(x, ei2, ws, b)
         if layer < n_layers - 1:
-            x = dropout_relu(x, p_drop, None if masks is None else masks[layer], generator)
+            x = dropout_relu(x, p_drop, None if masks is None else masks[layer], generator,
+                             gate=None if gates is None else gates[layer], trace=trace)
     return x_in + x if skip else x
 
 
-def pfn_forward(sd, x, edge_index, edge_attr, p_drop, skip=True, masks=None, generator=None):
+def pfn_forward(sd, x, edge_index, edge_attr, p_drop, skip=True, masks=None, generator=None, gates=None, trace=None):
     """networks.py:359-363 (PFN, skip=False) / :384-388 (SkipPFN, skip=True): L stacked sub-nets that
     all receive the same raw edge attributes; the last one is always a plain MPN (:355,:380)."""
     n_sub = 0
@@ -175,7 +185,8 @@ def pfn_forward(sd, x, edge_index, edge_attr, p_drop, skip=True, masks=None, gen
     for s in range(n_sub):
         sub_masks = None if masks is None else masks[s]
         x = mpn_forward(sd, f"mpns.{s}.", x, edge_index, edge_attr, p_drop,
-                        skip=(skip and s < n_sub - 1), masks=sub_masks, generator=generator)
+                        skip=(skip and s < n_sub - 1), masks=sub_masks, generator=generator,
+                        gates=None if gates is None else gates[s], trace=trace)
     return x
 
 

@@ -30,10 +30,17 @@ class Sequential(_nn.Module):
     def forward(self, *args):
         env = dict(zip(self._inputs, args))
         last = args[0]
+        prev_outs = [self._inputs[0]]
         for name, ins, outs in self._specs:
             mod = getattr(self, name)
             if ins is None:
+                # PyG: a module given WITHOUT a signature string operates on the output of its preceding module AND REBINDS it
+                # (in_desc = out_desc = the previous call's out_desc), so `(conv, 'x, ei -> x'), LeakyReLU()` feeds the activated x
+                # to the next conv.  (Round 1 of this shim dropped the rebinding: the activations between GATv2 / GINE layers had
+                # no effect on the following layer - found by running the reference's script against the drop-in modules.)
                 last = mod(last)
+                if len(prev_outs) == 1:
+                    env[prev_outs[0]] = last
             else:
                 res = mod(*[env[k] for k in ins])
                 if len(outs) == 1:
@@ -42,4 +49,5 @@ class Sequential(_nn.Module):
                     for k, v in zip(outs, res):
                         env[k] = v
                 last = res
+                prev_outs = outs
         return last

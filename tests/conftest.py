@@ -29,6 +29,39 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(skip)
 
 
+# every assert_fp32_parity call of a GPU run is recorded and written to gpurun_out/PARITY.json (copied to profiles/PARITY_rNN.json)
+_PARITY_LOG = []
+_CURRENT_TEST = {"id": ""}
+
+
+@pytest.fixture(autouse=True)
+def _remember_test_id(request):
+    _CURRENT_TEST["id"] = request.node.nodeid
+    yield
+
+
+def note_parity(what, **fields):
+    """Extra record in the parity log (e.g. a ReLU-tie case that switched the gradient reference)."""
+    _PARITY_LOG.append(dict(test=_CURRENT_TEST["id"], what=what, **fields))
+
+
+def pytest_sessionfinish(session, exitstatus):
+    if not _PARITY_LOG or not torch.cuda.is_available():
+        return
+    import json
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out_dir, exist_ok=True)
+    rows = [r for r in _PARITY_LOG if "err_over_tol" in r]
+    worst = sorted(rows, key=lambda r: -r["err_over_tol"])[:25]
+    summary = {"criterion": "err = max|ours - fp64 oracle| <= tol = max(rtol * max|fp64|, noise_mult * max|reference fp32 - fp64|), rtol = 1e-5",
+               "device": torch.cuda.get_device_name(0), "calls": len(rows), "max_err_over_tol": max((r["err_over_tol"] for r in rows), default=0.0),
+               "max_err_over_scale": max((r["err_over_scale"] for r in rows), default=0.0),
+               "calls_decided_by_rtol_alone": sum(1 for r in rows if r["err_over_scale"] <= r["rtol"]),
+               "notes": [r for r in _PARITY_LOG if "err_over_tol" not in r], "worst_25": worst, "all": rows}
+    with open(os.path.join(out_dir, "PARITY.json"), "w") as f:
+        json.dump(summary, f, indent=1)
+
+
 def load_golden(name):
     return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
 
@@ -69,14 +102,45 @@ def assert_fp32_parity(ours, ref32, ref64, what="", rtol=1e-5, noise_mult=4.0):
     last-layer theta-bias gradient are sums of +-1e3-sized terms that cancel to ~0; ours and the reference's result are two
     draws of the same rounding noise, and a ratio of 2-3 between two draws is ordinary.)"""
     ours = torch.as_tensor(ours).double().cpu()
-    ref32 = torch.as_tensor(ref32).double().cpu()
     ref64 = torch.as_tensor(ref64).double().cpu()
+    # `ref32` may be a list of fp32 evaluations of the reference that are equally valid (e.g. the same batch with its edge list in
+    # another order: PyG's scatter order follows the edge order, its CUDA scatter is unordered): the noise is the worst of them
+    refs = ref32 if isinstance(ref32, (list, tuple)) else [ref32]
+    refs = [torch.as_tensor(r).double().cpu() for r in refs]
     scale = float(ref64.abs().max()) if ref64.numel() else 0.0
-    noise = float((ref32 - ref64).abs().max()) if ref64.numel() else 0.0
+    noise = max(float((r - ref64).abs().max()) for r in refs) if ref64.numel() else 0.0
     err = float((ours - ref64).abs().max()) if ref64.numel() else 0.0
+    # the noise term is only meaningful when the reference's fp32 result and the fp64 oracle describe the SAME computation: if they
+    # are far apart (round 1: GAT / GINE goldens recorded over a shim whose Sequential dropped the activations, 100 % apart from the
+    # oracle) the criterion would accept anything - fail loudly instead
+    # (50 %: the deliberately cancelling cases - residuals and gradients AT the solution - legitimately show fp32-vs-fp64
+    # differences of 20 % of a near-zero scale; a wrong reference is off by 100 % and more)
+    assert noise <= 0.5 * scale + 1e-300, (f"{what}: the reference's fp32 result and the fp64 oracle disagree by {noise:.3e} "
+                                            f"(scale {scale:.3e}): not rounding noise, one of them is wrong")
     tol = max(rtol * scale, noise_mult * noise)
+    _PARITY_LOG.append({"test": _CURRENT_TEST["id"], "what": what, "err": err, "tol": tol, "scale": scale, "ref32_noise": noise, "rtol": rtol,
+                        "noise_mult": noise_mult, "err_over_tol": err / (tol + 1e-300), "err_over_scale": err / (scale + 1e-300)})
     assert err <= tol + 1e-300, f"{what}: err {err:.3e} > tol {tol:.3e} (scale {scale:.3e}, ref32 noise {noise:.3e})"
     return err, tol
+
+
+def permute_edges(batch, seed):
+    """The same collated batch (dict of the oracle's `collate`) with its edge list in another order: mathematically the same graph,
+    another fp32 summation order in every scatter of the reference."""
+    g = torch.Generator().manual_seed(seed)
+    perm = torch.randperm(batch["edge_index"].shape[1], generator=g)
+    out = dict(batch)
+    out["edge_index"] = batch["edge_index"][:, perm].contiguous()
+    out["edge_attr"] = batch["edge_attr"][perm].contiguous()
+    return out
+
+
+def permuted_golden(z, seed):
+    """dict view of a golden npz with the edge list in another order (for the oracle_*_run helpers)."""
+    d = {k: z[k] for k in ("x", "edge_attr", "edge_index", "x_mean", "x_std", "edge_mean", "edge_std")}
+    pb = permute_edges({"edge_index": torch.from_numpy(z["edge_index"]), "edge_attr": torch.from_numpy(z["edge_attr"])}, seed)
+    d["edge_index"], d["edge_attr"] = pb["edge_index"].numpy(), pb["edge_attr"].numpy()
+    return d
 
 
 def golden_gat(tag):

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import REG_COEFS, assert_fp32_parity, golden_model, load_golden, split_masks
+from conftest import REG_COEFS, assert_fp32_parity, golden_model, load_golden, note_parity, permute_edges, split_masks
 import dss2_oracle as orc
 
 pytestmark = pytest.mark.gpu
@@ -304,20 +304,68 @@ def test_tag_conv_forward_backward(env, cout, K):
 
 
 # ------------------------------------------------------------------------------------------------ whole models vs the reference run
-def _oracle_model(kind, ctor, sd, x, ea, ei, masks, stats, grad_out, dtype):
+def _oracle_model(kind, ctor, sd, x, ea, ei, masks, stats, grad_out, dtype, gates=None, trace=None):
+    """Oracle forward + loss + autograd.  `gates` ([sub-net][hidden layer] 0/1 tensors) fixes the dropout/ReLU pass pattern,
+    `trace` collects the hidden layers' pre-activations (see oracle dropout_relu)."""
     sd = {k: v.to(dtype).clone().requires_grad_(True) for k, v in sd.items()}
     x, ea = x.to(dtype), ea.to(dtype)
     p = ctor["dropout_rate"]
     if kind in ("MPN", "SkipMPN"):
-        out = orc.mpn_forward(sd, "", x[:, :8], ei, ea[:, :6], p, skip=(kind == "SkipMPN"), masks=masks)
+        out = orc.mpn_forward(sd, "", x[:, :8], ei, ea[:, :6], p, skip=(kind == "SkipMPN"), masks=masks,
+                              gates=None if gates is None else gates[0], trace=trace)
     else:
-        out = orc.pfn_forward(sd, x[:, :8], ei, ea[:, :6], p, skip=(kind == "SkipPFN"), masks=split_masks(masks, ctor))
+        out = orc.pfn_forward(sd, x[:, :8], ei, ea[:, :6], p, skip=(kind == "SkipPFN"), masks=split_masks(masks, ctor), gates=gates, trace=trace)
     if ctor["dim_out"] == 2:
         loss = orc.wls_loss(x, ea, out, *[s.to(dtype) for s in stats], ei, REG_COEFS)
     else:
         loss = (out * grad_out.to(dtype)).sum()
     loss.backward()
     return out.detach(), loss.detach(), {k: v.grad for k, v in sd.items()}
+
+
+def _kernel_gates(bufs, n_sub, n_hidden, nt):
+    """[sub-net][hidden layer] -> [nt, 32] 0/1 tensor: the pass pattern (dropout kept AND pre-activation > 0) our forward recorded."""
+    bits = bufs["bits"][:, :, :nt].cpu().to(torch.int64) & 0xFFFFFFFF
+    shifts = torch.arange(32, dtype=torch.int64)
+    return [[((bits[s_, l_].unsqueeze(1) >> shifts) & 1).to(torch.float32) for l_ in range(n_hidden)] for s_ in range(n_sub)]
+
+
+def assert_gradients_vs_oracle(what, ours, golden_grads, kind, ctor, sd, xc, eac, eic, masks, st, go, bufs, noise_mult=4.0, edge_orders=0):
+    """Parameter gradients against the ORACLE (never against another kernel of this repo).
+
+    relu' is discontinuous: a pre-activation that is +-1e-7 in one fp32 implementation and on the other side of 0 in another changes
+    the gradient legitimately.  So the pass pattern our kernels recorded (sign words) is compared with the fp64 oracle's first.  No
+    difference: the gradients must match the reference run's (golden file) under the usual criterion.  A difference: every differing
+    entry must be a genuine tie (|fp64 pre-activation| <= 1e-6 of that layer's largest), and the gradients must match the oracle
+    evaluated WITH OUR pass pattern (fp32 run = reference value, fp64 run = arbiter).  The tie case is written to the parity log."""
+    n_sub = ctor.get("L", 1) if kind in ("PFN", "SkipPFN") else 1
+    n_hidden = ctor["n_gnn_layers"] - 1
+    nt = xc.size(0)
+    trace = []
+    _, _, g64 = _oracle_model(kind, ctor, sd, xc, eac, eic, masks, st, go, torch.float64, trace=trace)
+    ref32, ref64 = golden_grads, g64
+    ties, gates = 0, None
+    if n_hidden > 0:
+        gates = _kernel_gates(bufs, n_sub, n_hidden, nt)
+        for s_ in range(n_sub):
+            for l_ in range(n_hidden):
+                pre = trace[s_ * n_hidden + l_]
+                differ = (gates[s_][l_] > 0) != (pre > 0)
+                if bool(differ.any()):
+                    ties += int(differ.sum())
+                    worst = float(pre[differ].abs().max()) / (float(pre.abs().max()) + 1e-300)
+                    assert worst <= 1e-6, f"{what}: sign word differs from the fp64 oracle at a pre-activation of relative size {worst:.2e} (not a tie)"
+        if ties:
+            note_parity(f"{what}: {ties} ReLU tie(s); gradients compared with the oracle under the kernel's pass pattern", ties=ties)
+            _, _, ref64 = _oracle_model(kind, ctor, sd, xc, eac, eic, masks, st, go, torch.float64, gates=gates)
+            _, _, ref32 = _oracle_model(kind, ctor, sd, xc, eac, eic, masks, st, go, torch.float32, gates=gates)
+    refs = [ref32]
+    for o_ in range(edge_orders):   # further fp32 evaluations of the reference, edge list in another order (see conftest.permute_edges)
+        pb = permute_edges({"edge_index": eic, "edge_attr": eac}, 100 + o_)
+        refs.append(_oracle_model(kind, ctor, sd, xc, pb["edge_attr"], pb["edge_index"], masks, st, go, torch.float32,
+                                  gates=gates if ties else None)[2])
+    for name, g in ours.items():
+        assert_fp32_parity(g, [r[name] for r in refs], ref64[name], f"{name} ({what})", noise_mult=noise_mult)
 
 
 @pytest.mark.parametrize("tag", ["skippfn_cigre", "pfn_small_cigre", "mpn_cigre", "skipmpn_cigre", "skippfn_ober"])
@@ -337,6 +385,8 @@ def test_model_matches_reference_run(env, tag, where):
     per_sub = split_masks(masks, ctor) if kind in ("PFN", "SkipPFN") else ([masks] if masks is not None else None)
     model._dss2_masks = per_sub
     model.train()
+    runner = model._machinery()[0]
+    runner.keep_last_bufs = True          # the sign words of the forward, for the tie check of the gradients
     out = model(x[:, :8], ei, ea[:, :6])
     assert out.device.type == where and out.shape == (x.size(0), ctor["dim_out"])
     out_before = out.detach().clone()
@@ -352,13 +402,32 @@ def test_model_matches_reference_run(env, tag, where):
     assert_fp32_parity(out_before, o32, o64, "out")
     if "loss" in z.files:
         assert_fp32_parity(loss.detach(), z["loss"], l64, "loss")
-    try:
-        for name, p in model.named_parameters():
-            assert p.grad is not None and p.grad.device.type == where, name
-            assert_fp32_parity(p.grad, g32[name], g64[name], name)
-    except AssertionError:
-        # a ReLU tie (|pre-activation| ~ 1e-7) makes the gradient implementation dependent: verify that this is the cause
-        _tie_aware_model_check(env, tag, env["ops"].TAG_IMPL)
+    ours = {}
+    for name, p in model.named_parameters():
+        assert p.grad is not None and p.grad.device.type == where, name
+        ours[name] = p.grad
+    assert_gradients_vs_oracle(f"{tag}/{where}", ours, g32, kind, ctor, sd, x.cpu(), ea.cpu(), ei.cpu(), masks, st, go, runner.last_bufs)
+
+
+def test_models_survive_deepcopy_and_pickle_after_a_forward(env, tmp_path):
+    """copy.deepcopy(model) / torch.save(model) after the first forward (best-model snapshots, EMA copies): the cached launch machinery
+    holds ctypes handles and must stay behind; the copy rebuilds its own and computes the same thing."""
+    import copy
+    b = _small_batch(env, "cigre14", 4, seed=2)
+    for model in (env["networks"].SkipPFN(8, 6, 2, 32, 2, 2, 0.0, 2).cuda(),
+                  env["networks"].GAT_DSSE(dim_feat=8, dim_dense=32, dim_out=2, heads=1, num_layers=3, edge_dim=6).cuda(),
+                  env["networks"].GINE_DSSE(dim_feat=8, dim_dense=32, dim_out=2, num_layers=3, edge_dim=6).cuda()):
+        out = model(b.x[:, :8], b.edge_index, b.edge_attr[:, :6]).detach().clone()
+        twin = copy.deepcopy(model)
+        assert torch.equal(twin(b.x[:, :8], b.edge_index, b.edge_attr[:, :6]).detach(), out)
+        path = os.path.join(str(tmp_path), type(model).__name__ + ".pt")
+        torch.save(model, path)
+        again = torch.load(path, weights_only=False)
+        assert torch.equal(again(b.x[:, :8], b.edge_index, b.edge_attr[:, :6]).detach(), out)
+        with torch.no_grad():           # the copy owns its parameters
+            for p_ in twin.parameters():
+                p_.add_(1.0)
+        assert torch.equal(model(b.x[:, :8], b.edge_index, b.edge_attr[:, :6]).detach(), out)
 
 
 def test_state_dict_round_trip_and_repack(env):
@@ -417,6 +486,44 @@ def test_philox_dropout_statistics_and_replay(env):
 
 
 # ------------------------------------------------------------------------------------------------ full-size properties (BASELINE config 3)
+def test_oberrhein_batch_4096_full_parity_vs_fp64_oracle(env):
+    """The bench configuration itself (BASELINE config 3: ober_sub, B = 4096, SkipPFN(8,6,2,32,8,2,.,5), Nt = 286 720) through the
+    throughput tier (GraphedTrainer: packer -> forward -> fused loss fwd+bwd -> backward -> partial reduction), dropout off, against the
+    oracle on the host in fp64 (arbiter) and fp32: model output, loss and every parameter gradient under the standard criterion.
+    Slow (about a minute of CPU for the oracle runs)."""
+    from dss2.trainer import GraphedTrainer, default_spec
+    B = 4096
+    store = env["synth"].synthetic_store(env["synth"].load_grid("ober_sub"), B, seed=1234)
+    spec = default_spec(p_drop=0.0)
+    sd0 = orc.init_state_dict("SkipPFN", seed=0)
+    g = torch.Generator().manual_seed(3)
+    for k in sd0:
+        if "convs." in k and k.endswith(".bias"):
+            sd0[k] = (torch.rand(sd0[k].shape, generator=g) - 0.5) * 0.2
+    tr = GraphedTrainer(store.to("cuda"), B, spec=spec, reg_coefs=REG_COEFS, seed=0, init_state_dict=sd0, use_cuda_graph=False)
+    assert tr.nt == 286720 and tr.graph.c.num_tiles > 0
+    tr.ids.copy_(torch.arange(B, device="cuda"))
+    tr._enqueue(with_optimizer=False)
+    torch.cuda.synchronize()
+    out_gpu, loss_gpu, flat_grad = tr.bufs["outs"][-1].clone(), tr.loss.clone(), tr.flat_grad.clone()
+    batch = orc.collate([store.graph(i) for i in range(B)])
+    st = [store.x_mean, store.x_std, store.edge_mean, store.edge_std]
+    ctor = dict(dim_featn=8, dim_feate=6, dim_out=2, dim_hid=32, n_gnn_layers=8, K=2, dropout_rate=0.0, L=5)
+    torch.set_num_threads(os.cpu_count() or 1)
+    o64, l64, _ = _oracle_model("SkipPFN", ctor, sd0, batch["x"], batch["edge_attr"], batch["edge_index"], None, st, None, torch.float64)
+    o32, l32, g32 = _oracle_model("SkipPFN", ctor, sd0, batch["x"], batch["edge_attr"], batch["edge_index"], None, st, None, torch.float32)
+    # the loss call zeroes theta at the slack buses of `output` in place (data.py:412-413): compare the V column and the masked theta
+    slack = batch["x"][:, 9] == 1.0
+    o64m, o32m = o64.clone(), o32.clone()
+    o64m[slack, 1] = 0.0
+    o32m[slack, 1] = 0.0
+    assert_fp32_parity(out_gpu, o32m, o64m, "out (B=4096)")
+    assert_fp32_parity(loss_gpu, l32, l64, "loss (B=4096)")
+    ours = {name: flat_grad[off:off + n].reshape(sd0[name].shape) for name, (off, n) in tr.runner.table.items()}
+    assert_gradients_vs_oracle("ober B=4096", ours, g32, "SkipPFN", ctor, sd0, batch["x"], batch["edge_attr"], batch["edge_index"], None, st,
+                               None, tr.bufs)
+
+
 def test_oberrhein_batch_4096_properties(env):
     """ober_sub, B = 4096 (Nt = 286 720): the oracle is too slow here, so size-independent properties instead:
     (i) determinism (bit-identical repeats), (ii) a batch is a disjoint union: each graph's output / loss gradient equals what
@@ -582,12 +689,10 @@ def test_tag_fwd_tensor_core_matches_cuda_core_kernel(env, case, nb, cout, act, 
             assert float(y_ref[rows].abs().min(dim=1).values.max()) < 1e-4
 
 
-def _tie_aware_model_check(env, tag, impl, noise_mult=4.0, large_graph=False):
-    """Whole model with TAG kernels `impl` against the reference run (same weights, same dropout masks).
-    Output and loss: fp64-arbiter parity.  Gradients: ReLU' is discontinuous, so a pre-activation that is ~1e-7 in one fp32
-    implementation and exactly 0 in another legitimately changes the gradient; the check therefore (i) demands identical sign words
-    except at such ties (|y| < 1e-6 in both kernels), (ii) if there is no tie, demands gradient parity with the reference run,
-    (iii) if there is one, demands that the gradients equal those of the CUDA-core kernels given the same sign words."""
+def _tie_aware_model_check(env, tag, impl, noise_mult=4.0, large_graph=False, edge_orders=0):
+    """Whole model through the runner with TAG kernels `impl` against the reference run (same weights, same dropout masks): output
+    and loss by the fp64-arbiter criterion, parameter gradients by `assert_gradients_vs_oracle` (reference run, or - at a ReLU tie -
+    the oracle under the kernel's own pass pattern; never another kernel of this repo)."""
     ops = env["ops"]
     saved_impl = ops.TAG_IMPL
     ctor, kind, sd, grads, masks, z = golden_model(tag)
@@ -598,66 +703,35 @@ def _tie_aware_model_check(env, tag, impl, noise_mult=4.0, large_graph=False):
     model = model.cuda()
     runner, pack = model._machinery()
     flat = pack.gather(dict(model.named_parameters()))
-    ops.TAG_IMPL = "tc2"                      # tile_cap 128 structure serves every implementation
+    ops.TAG_IMPL = "tc2"                      # one batch structure serves every implementation
     graph = ops.resolve_graph(ei, x.size(0))
     per_sub = split_masks(masks, ctor) if kind in ("PFN", "SkipPFN") else ([masks] if masks is not None else None)
     m = None if per_sub is None else [[t.cuda().to(torch.uint8).contiguous() for t in sub] for sub in per_sub]
     mode = 2 if m is not None else 0
     go = torch.from_numpy(z["grad_out"]).cuda().contiguous()
-
-    def select(which):
-        # large-graph path: the CUDA-core reference run is the same entry point with the tensor-core transform switched off
-        ops.TAG_IMPL = which if not large_graph else "ffma"
+    try:
+        ops.TAG_IMPL = impl if not large_graph else "ffma"
         if large_graph:
-            os.environ["DSS2_DENSE_TC"] = "1" if which == impl else "0"
-
-    def forward(which):
-        select(which)
+            os.environ["DSS2_DENSE_TC"] = "1"
         bufs = runner.alloc(x.size(0), x.device, need_grad=True)
         out = runner.forward(graph, x, 11, ea, 13, flat, bufs, drop_mode=mode, masks=m).clone()
-        return bufs, out
-
-    def backward(which, bufs, out):
-        select(which)
+        o64, l64, _ = _oracle_model(kind, ctor, sd, x.cpu(), ea.cpu(), ei.cpu(), masks, st, torch.from_numpy(z["grad_out"]), torch.float64)
+        assert_fp32_parity(out, z["out"], o64, f"out ({impl})")
         if ctor["dim_out"] == 2:
             leaf = out.clone().requires_grad_(True)
             loss = env["data"].gsp_wls_edge(input=x[:, :8], edge_input=ea[:, :6], output=leaf * 1.0, x_mean=st[0], x_std=st[1],
                                             edge_mean=st[2], edge_std=st[3], edge_index=ei, reg_coefs=REG_COEFS, num_samples=None,
                                             node_param=x[:, 8:], edge_param=ea[:, 6:])
             loss.backward()
-            g_out, loss = leaf.grad.contiguous(), loss.detach()
+            g_out = leaf.grad.contiguous()
+            assert_fp32_parity(loss.detach(), z["loss"], l64, f"loss ({impl})")
         else:
-            g_out, loss = go, None
+            g_out = go
         fg = torch.zeros(runner.flat_size, device="cuda")
         runner.backward(graph, x, 11, ea, 13, flat, bufs, g_out, fg)
-        return loss, fg
-
-    try:
-        b_cc, out_cc = forward("ffma")
-        b_i, out_i = forward(impl)
-        o64, l64, g64 = _oracle_model(kind, ctor, sd, x.cpu(), ea.cpu(), ei.cpu(), masks, st, torch.from_numpy(z["grad_out"]), torch.float64)
-        assert_fp32_parity(out_i, z["out"], o64, f"out ({impl})")
-        loss_i, fg_i = backward(impl, b_i, out_i)
-        if loss_i is not None:
-            assert_fp32_parity(loss_i, z["loss"], l64, f"loss ({impl})")
-        nl = ctor["n_gnn_layers"] - 1
-        nn_ = x.size(0)
-        differ = (b_cc["bits"][:, :nl, :nn_] != b_i["bits"][:, :nl, :nn_]).nonzero().tolist() if nl > 0 else []
-        for s_, l_, n_ in differ:
-            wa, wb = int(b_cc["bits"][s_, l_, n_]) & 0xFFFFFFFF, int(b_i["bits"][s_, l_, n_]) & 0xFFFFFFFF
-            for c in range(32):
-                if ((wa ^ wb) >> c) & 1:
-                    assert abs(float(b_cc["acts"][s_, l_ + 1, n_, c])) < 1e-6 and abs(float(b_i["acts"][s_, l_ + 1, n_, c])) < 1e-6
-        table = runner.table
-        if not differ:
-            for name, (off, n) in table.items():
-                assert_fp32_parity(fg_i[off:off + n], grads[name].reshape(-1), g64[name].reshape(-1), f"{name} ({impl})", noise_mult=noise_mult)
-        else:
-            b_cc["bits"].copy_(b_i["bits"])
-            _, fg_h = backward("ffma", b_cc, out_cc)
-            for name, (off, n) in table.items():
-                scale = float(fg_h[off:off + n].abs().max()) + 1e-30
-                assert float((fg_i[off:off + n] - fg_h[off:off + n]).abs().max()) <= 2e-4 * scale, f"{name} ({impl}, tie case)"
+        ours = {name: fg[off:off + n].reshape(sd[name].shape) for name, (off, n) in runner.table.items()}
+        assert_gradients_vs_oracle(f"{tag}/{impl}", ours, grads, kind, ctor, sd, x.cpu(), ea.cpu(), ei.cpu(), masks, st,
+                                   torch.from_numpy(z["grad_out"]), bufs, noise_mult=noise_mult, edge_orders=edge_orders)
     finally:
         ops.TAG_IMPL = saved_impl
         os.environ.pop("DSS2_DENSE_TC", None)
@@ -765,21 +839,21 @@ def test_graphed_trainer_step_matches_oracle(env, case, nb):
     # oracle: same batch, fp32 and fp64
     batch = orc.collate([store.graph(int(i)) for i in ids])
     res = {}
-    for dtype in (torch.float32, torch.float64):
+    # the reference in fp64 (arbiter), in fp32, and in fp32 with the batch's edge list in two other orders: the chained step at a
+    # random-init operating point (huge soft-constraint penalties) is ill conditioned, and the fp32 result of the reference itself
+    # moves with the summation order of its scatters.  The tolerance is the standard 4x - of the worst of these equally valid runs.
+    for tag_, dtype, bt in (("f64", torch.float64, batch), ("f32", torch.float32, batch), ("f32_p1", torch.float32, permute_edges(batch, 1)),
+                            ("f32_p2", torch.float32, permute_edges(batch, 2))):
         sd = {k: v.to(dtype).clone().requires_grad_(True) for k, v in sd0.items()}
-        out = orc.pfn_forward(sd, batch["x"].to(dtype)[:, :8], batch["edge_index"], batch["edge_attr"].to(dtype)[:, :6], 0.0, skip=True)
-        loss = orc.wls_loss(batch["x"].to(dtype), batch["edge_attr"].to(dtype), out, store.x_mean.to(dtype), store.x_std.to(dtype),
-                            store.edge_mean.to(dtype), store.edge_std.to(dtype), batch["edge_index"], REG_COEFS)
+        out = orc.pfn_forward(sd, bt["x"].to(dtype)[:, :8], bt["edge_index"], bt["edge_attr"].to(dtype)[:, :6], 0.0, skip=True)
+        loss = orc.wls_loss(bt["x"].to(dtype), bt["edge_attr"].to(dtype), out, store.x_mean.to(dtype), store.x_std.to(dtype),
+                            store.edge_mean.to(dtype), store.edge_std.to(dtype), bt["edge_index"], REG_COEFS)
         loss.backward()
-        res[dtype] = (loss.detach(), {k: v.grad for k, v in sd.items()})
-    assert_fp32_parity(loss_gpu, res[torch.float32][0], res[torch.float64][0], "loss")
-    # Gradients after a chain of 12 layer kernels + loss at a random-init operating point (huge soft-constraint penalties): measured on
-    # B200, BOTH the CUDA-core fp32 kernels (1.03e-5) and the tcgen05 kernels (1.6e-5) land at the 1e-5 line on the Oberrhein case while
-    # the oracle's fp32-vs-fp64 self-noise (same op order) is 1e-6 - i.e. the case is conditioning-limited, not implementation-limited.
-    # Every kernel individually meets the strict criterion (layer-level and golden-model tests above); here the noise allowance is 8x.
+        res[tag_] = (loss.detach(), {k: v.grad for k, v in sd.items()})
+    assert_fp32_parity(loss_gpu, [res[t_][0] for t_ in ("f32", "f32_p1", "f32_p2")], res["f64"][0], "loss")
     for name, (off, n) in tr.runner.table.items():
-        assert_fp32_parity(flat_grad[off:off + n], res[torch.float32][1][name].reshape(-1), res[torch.float64][1][name].reshape(-1), name,
-                           noise_mult=8.0)
+        assert_fp32_parity(flat_grad[off:off + n], [res[t_][1][name].reshape(-1) for t_ in ("f32", "f32_p1", "f32_p2")],
+                           res["f64"][1][name].reshape(-1), name)
     # optimizer: our flat Adamax == torch.optim.Adamax on the same gradient, two steps
     ref_p = tr.flat.clone().requires_grad_(True)
     opt = torch.optim.Adamax([ref_p], lr=3e-3)
@@ -822,7 +896,7 @@ def test_large_graph_path_models_match_reference_run(env, tiny_tiles, tag):
     # large-graph kernels' summation order lands one weight gradient at 4.02x that noise (1.1e-5 of the scale), measured identically
     # with the exact fp32 weight-gradient pass and the tcgen05 one, i.e. inherited rounding of the inputs, not a kernel defect.
     # "cuda-core" = the large-graph path with DSS2_DENSE_TC=0 (k_dense_tag), "tc-dense" = its default (tcgen05 transform on the hop levels)
-    _tie_aware_model_check(env, tag, "tc-dense", noise_mult=6.0 if tag == "pfn_small_cigre" else 4.0, large_graph=True)
+    _tie_aware_model_check(env, tag, "tc-dense", large_graph=True, edge_orders=2 if tag == "pfn_small_cigre" else 0)
 
 
 @pytest.mark.parametrize("tag", ["skippfn_cigre", "skippfn_ober"])
@@ -883,16 +957,19 @@ def _mixed_grid_model_check(env):
                                     node_param=b.x[:, 8:], edge_param=b.edge_attr[:, 6:])
     loss.backward()
     res = {}
-    for dtype in (torch.float32, torch.float64):
+    # fp64 arbiter + the reference in fp32 under three equally valid edge orders (see test_graphed_trainer_step_matches_oracle)
+    for tag_, dtype, bt in (("f64", torch.float64, ref), ("f32", torch.float32, ref), ("f32_p1", torch.float32, permute_edges(ref, 1)),
+                            ("f32_p2", torch.float32, permute_edges(ref, 2))):
         p = {k: v.to(dtype).clone().requires_grad_(True) for k, v in sd.items()}
-        o = orc.pfn_forward(p, ref["x"].to(dtype)[:, :8], ref["edge_index"], ref["edge_attr"].to(dtype)[:, :6], 0.0, skip=True)
-        l = orc.wls_loss(ref["x"].to(dtype), ref["edge_attr"].to(dtype), o, *[s.to(dtype) for s in stats], ref["edge_index"], REG_COEFS)
+        o = orc.pfn_forward(p, bt["x"].to(dtype)[:, :8], bt["edge_index"], bt["edge_attr"].to(dtype)[:, :6], 0.0, skip=True)
+        l = orc.wls_loss(bt["x"].to(dtype), bt["edge_attr"].to(dtype), o, *[s.to(dtype) for s in stats], bt["edge_index"], REG_COEFS)
         l.backward()
-        res[dtype] = (o.detach(), l.detach(), {k: v.grad for k, v in p.items()})
-    assert_fp32_parity(out_before, res[torch.float32][0], res[torch.float64][0], "out")
-    assert_fp32_parity(loss.detach(), res[torch.float32][1], res[torch.float64][1], "loss")
+        res[tag_] = (o.detach(), l.detach(), {k: v.grad for k, v in p.items()})
+    f32s = ("f32", "f32_p1", "f32_p2")
+    assert_fp32_parity(out_before, [res[t_][0] for t_ in f32s], res["f64"][0], "out")
+    assert_fp32_parity(loss.detach(), [res[t_][1] for t_ in f32s], res["f64"][1], "loss")
     for name, prm in model.named_parameters():
-        assert_fp32_parity(prm.grad, res[torch.float32][2][name], res[torch.float64][2][name], name, noise_mult=8.0)
+        assert_fp32_parity(prm.grad, [res[t_][2][name] for t_ in f32s], res["f64"][2][name], name)
 
 
 def test_ragged_mixed_grid_batch_tiled(env):
@@ -926,11 +1003,36 @@ def test_gat_dsse_matches_reference_run(env, tag, where):
                                     edge_param=ea[:, 6:])
     loss.backward()
     o64, l64, g64 = oracle_gat_run(orc, nl, sd, z, torch.float64)
-    assert_fp32_parity(out_before, z["out"], o64, "out")
-    assert_fp32_parity(loss.detach(), z["loss"], l64, "loss")
+    # equally valid fp32 evaluations of the reference define the noise: its recorded run (golden), the oracle's fp32 run and that run
+    # with the edge list in two other orders (the loss of these cases is a sum of terms that cancel to ~1e-3 of their size, so its last
+    # bits depend on the summation order of the bus injections)
+    from conftest import permuted_golden
+    runs = [oracle_gat_run(orc, nl, sd, z, torch.float32)] + [oracle_gat_run(orc, nl, sd, permuted_golden(z, s_), torch.float32) for s_ in (1, 2)]
+    assert_fp32_parity(out_before, [z["out"]] + [r[0] for r in runs], o64, "out")
+    # the loss value is ill conditioned w.r.t. the model output here (large weights on nearly cancelling residuals: a 1e-7 change of
+    # `out` moves it by 1e-5): so the LOSS KERNEL is checked on the output it actually received - fp64 / fp32 oracle loss of OUR output -
+    # and the model output itself against the reference just above
+    xo, eo, oo = x.cpu(), ea.cpu(), out_before.cpu()
+    l_ref = {dt: orc.wls_loss(xo.to(dt), eo.to(dt), oo.to(dt), *[t_.to(dt) for t_ in st], ei.cpu(), REG_COEFS) for dt in (torch.float32, torch.float64)}
+    assert_fp32_parity(loss.detach(), l_ref[torch.float32], l_ref[torch.float64], "loss (of our output)")
+    assert abs(float(loss) - float(l64)) <= 1e-4 * abs(float(l64)), "loss vs the reference run"
+    # gradients, end to end through our loss: the upstream gradient d loss / d out carries the conditioning described above, so this
+    # comparison with the reference run is held to max(1e-4 of each tensor's scale, 16x the reference's own fp32 noise) ...
     for name, p in model.named_parameters():
         assert p.grad is not None and p.grad.device.type == where, name
-        assert_fp32_parity(p.grad, grads[name], g64[name], name)
+        assert_fp32_parity(p.grad, [grads[name]] + [r[2][name] for r in runs], g64[name], name + " (end to end)", rtol=1e-4, noise_mult=16.0)
+    # ... and the model's BACKWARD KERNELS to the strict criterion on the upstream gradient the reference run recorded: both sides
+    # differentiate sum(out * grad_out)
+    go = torch.from_numpy(z["grad_out"])
+    model.zero_grad()
+    model(x[:, :8], ei, ea[:, :6]).backward(go.to(where))
+    lin = {}
+    for dt in (torch.float32, torch.float64):
+        pp = {k: v.to(dt).clone().requires_grad_(True) for k, v in sd.items()}
+        (orc.gat_dsse_forward(pp, x.cpu().to(dt)[:, :8], ei.cpu(), ea.cpu().to(dt)[:, :6], nl) * go.to(dt)).sum().backward()
+        lin[dt] = {k: v.grad for k, v in pp.items()}
+    for name, p in model.named_parameters():
+        assert_fp32_parity(p.grad, lin[torch.float32][name], lin[torch.float64][name], name + " (recorded grad_out)")
 
 
 def test_gat_layer_input_gradient_and_self_loops(env):
@@ -1092,11 +1194,36 @@ def test_gine_dsse_matches_reference_run(env, tag, where):
                                     edge_param=ea[:, 6:])
     loss.backward()
     o64, l64, g64 = oracle_gine_run(orc, nl, sd, z, torch.float64)
-    assert_fp32_parity(out_before, z["out"], o64, "out")
-    assert_fp32_parity(loss.detach(), z["loss"], l64, "loss")
+    # equally valid fp32 evaluations of the reference define the noise: its recorded run (golden), the oracle's fp32 run and that run
+    # with the edge list in two other orders (the loss of these cases is a sum of terms that cancel to ~1e-3 of their size, so its last
+    # bits depend on the summation order of the bus injections)
+    from conftest import permuted_golden
+    runs = [oracle_gine_run(orc, nl, sd, z, torch.float32)] + [oracle_gine_run(orc, nl, sd, permuted_golden(z, s_), torch.float32) for s_ in (1, 2)]
+    assert_fp32_parity(out_before, [z["out"]] + [r[0] for r in runs], o64, "out")
+    # the loss value is ill conditioned w.r.t. the model output here (large weights on nearly cancelling residuals: a 1e-7 change of
+    # `out` moves it by 1e-5): so the LOSS KERNEL is checked on the output it actually received - fp64 / fp32 oracle loss of OUR output -
+    # and the model output itself against the reference just above
+    xo, eo, oo = x.cpu(), ea.cpu(), out_before.cpu()
+    l_ref = {dt: orc.wls_loss(xo.to(dt), eo.to(dt), oo.to(dt), *[t_.to(dt) for t_ in st], ei.cpu(), REG_COEFS) for dt in (torch.float32, torch.float64)}
+    assert_fp32_parity(loss.detach(), l_ref[torch.float32], l_ref[torch.float64], "loss (of our output)")
+    assert abs(float(loss) - float(l64)) <= 1e-4 * abs(float(l64)), "loss vs the reference run"
+    # gradients, end to end through our loss: the upstream gradient d loss / d out carries the conditioning described above, so this
+    # comparison with the reference run is held to max(1e-4 of each tensor's scale, 16x the reference's own fp32 noise) ...
     for name, p in model.named_parameters():
         assert p.grad is not None and p.grad.device.type == where, name
-        assert_fp32_parity(p.grad, grads[name], g64[name], name)
+        assert_fp32_parity(p.grad, [grads[name]] + [r[2][name] for r in runs], g64[name], name + " (end to end)", rtol=1e-4, noise_mult=16.0)
+    # ... and the model's BACKWARD KERNELS to the strict criterion on the upstream gradient the reference run recorded: both sides
+    # differentiate sum(out * grad_out)
+    go = torch.from_numpy(z["grad_out"])
+    model.zero_grad()
+    model(x[:, :8], ei, ea[:, :6]).backward(go.to(where))
+    lin = {}
+    for dt in (torch.float32, torch.float64):
+        pp = {k: v.to(dt).clone().requires_grad_(True) for k, v in sd.items()}
+        (orc.gine_dsse_forward(pp, x.cpu().to(dt)[:, :8], ei.cpu(), ea.cpu().to(dt)[:, :6], nl) * go.to(dt)).sum().backward()
+        lin[dt] = {k: v.grad for k, v in pp.items()}
+    for name, p in model.named_parameters():
+        assert_fp32_parity(p.grad, lin[torch.float32][name], lin[torch.float64][name], name + " (recorded grad_out)")
 
 
 def test_gine_layer_input_gradient_and_self_loops(env):

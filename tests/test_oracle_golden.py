@@ -140,10 +140,11 @@ def test_gat_dsse_forward_backward_vs_reference(tag):
     nl, sd, grads, z = golden_gat(tag)
     out32, loss32, g32 = oracle_gat_run(orc, nl, sd, z, torch.float32)
     out64, loss64, g64 = oracle_gat_run(orc, nl, sd, z, torch.float64)
-    assert_fp32_parity(out32, z["out"], out64, "out")
-    assert_fp32_parity(loss32, z["loss"], loss64, "loss")
+    # pinning direction: the REFERENCE's recorded run must sit within fp32 noise of the fp64 oracle (noise = the oracle's own fp32 run)
+    assert_fp32_parity(z["out"], out32, out64, "out")
+    assert_fp32_parity(z["loss"], loss32, loss64, "loss")
     for name, g in grads.items():
-        assert_fp32_parity(g32[name], g, g64[name], name)
+        assert_fp32_parity(g, g32[name], g64[name], name)
 
 
 @pytest.mark.parametrize("tag", ["gine_cigre", "gine_ober"])
@@ -153,7 +154,8 @@ def test_gine_dsse_forward_backward_vs_reference(tag):
     nl, sd, grads, z = golden_gat(tag)
     out32, loss32, g32 = oracle_gine_run(orc, nl, sd, z, torch.float32)
     out64, loss64, g64 = oracle_gine_run(orc, nl, sd, z, torch.float64)
-    assert_fp32_parity(out32, z["out"], out64, "out")
-    assert_fp32_parity(loss32, z["loss"], loss64, "loss")
+    # pinning direction (see the GAT test above)
+    assert_fp32_parity(z["out"], out32, out64, "out")
+    assert_fp32_parity(z["loss"], loss32, loss64, "loss")
     for name, g in grads.items():
-        assert_fp32_parity(g32[name], g, g64[name], name)
+        assert_fp32_parity(g, g32[name], g64[name], name)
