@@ -1141,6 +1141,32 @@ def test_dss2_run_flow_with_default_gat_model(env):
     assert set(model.state_dict()) == set(sd0)
 
 
+# ------------------------------------------------------------------------------------------------ dataset builder on the device (scope row 8f-3)
+def test_dataset_builder_on_the_device_vs_reference_golden(env):
+    """build_scenario_store(device='cuda') on the reference's own CIGRE-14 scenarios and its np.random noise stream against the golden
+    the reference's data_from_pickles produced (golden_dataset_cigre14.npz; the CPU build is bit-exact with it, test_host_cpu).  On the
+    device the element-wise pipeline (noise injection in fp64, weights 1/max(|sigma|,eps)^2 with the >= 1e12 cut, interleaving, raw
+    parameter columns, edge list, labels) is bit-exact too; the masked z-score statistics are fp32 sums over 1920 rows whose
+    summation order differs between torch's CPU and CUDA reductions, so statistics and normalised columns agree to fp32 rounding
+    (a few ulp), with identical zero patterns."""
+    gd = load_golden("golden_dataset_cigre14.npz")
+    fx = load_golden("cigre14_scenarios.npz")
+    grid = env["synth"].load_grid("cigre14")
+    S = fx["nodes"].shape[0]
+    zn, ze = env["dataset"].reference_noise_stream(0, S, 15, 14)
+    st = env["dataset"].build_scenario_store(fx["nodes"], fx["edges"], fx["labels"], grid["noise_param"], grid["meas_v"], grid["meas_pflow"],
+                                             zn, ze, device="cuda")
+    x, ea = st.x.cpu().numpy(), st.edge_attr.cpu().numpy()
+    n, e = gd["x"].shape[0], gd["edge_attr"].shape[0]
+    assert np.array_equal(st.edge_index.cpu().numpy()[:, :14], gd["edge_index"])
+    assert np.array_equal(st.y.cpu().numpy()[:n], gd["y"])
+    assert np.array_equal(x[:n, 8:], gd["x"][:, 8:]) and np.array_equal(ea[:e, 6:], gd["edge_attr"][:, 6:])       # raw parameter columns
+    assert np.array_equal(x[:n, :8] == 0, gd["x"][:, :8] == 0) and np.array_equal(ea[:e, :6] == 0, gd["edge_attr"][:, :6] == 0)
+    for ours, ref in ((st.x_mean, gd["x_mean"]), (st.x_std, gd["x_std"]), (st.edge_mean, gd["edge_mean"]), (st.edge_std, gd["edge_std"])):
+        assert np.allclose(ours.cpu().numpy(), ref, rtol=2e-6, atol=0), (ours, ref)
+    assert np.allclose(x[:n, :8], gd["x"][:, :8], rtol=2e-5, atol=2e-6) and np.allclose(ea[:e, :6], gd["edge_attr"][:, :6], rtol=2e-5, atol=2e-6)
+
+
 # ------------------------------------------------------------------------------------------------ validation metrics (scope row 8f-4)
 @pytest.mark.parametrize("case", ["cigre14", "ober_sub"])
 def test_eval_metrics_kernel_matches_script_formulas(env, case):
