@@ -148,11 +148,16 @@ int dss2_tag_fwd_tc(const dss2_graph_t* g, const float* x, const float* w, const
                     int act, float p_drop, int drop_mode, const uint64_t* rng_state, uint32_t layer_uid,
                     const uint8_t* mask, const float* res, int64_t res_stride,
                     float* y, uint32_t* act_bits, void* stream);
-/* Second-generation tensor-core layer kernels (thread-per-row CUDA-core stages, rotating level buffers, 2 CTAs/SM); need a graph
- * built with tile_cap <= 128 and K <= 2.  Forward: same contract as dss2_tag_fwd.  Backward: same contract as dss2_tag_bwd plus a
- * workspace of dss2_tag_bwd_tc2_workspace_bytes() for the hop levels of the masked output gradient; it runs the backward-to-input as
- * the forward kernel with transposed weights (grad_x = sum_k (A^k g) W_k) and the weight gradients as one streaming MN-major GEMM
- * (grad_W_k = (A^k g)^T x), with no hop recomputation on x.  Pointers must be 16-byte aligned (TMA bulk copies, 128-bit accesses). */
+/* Second/third-generation tensor-core layer kernels (thread = (row, half row); A operand in tensor memory; tiled graphs with
+ * tile_cap <= 256 and K <= 2).  Forward: same contract as dss2_tag_fwd.  Backward: same contract as dss2_tag_bwd plus a workspace of
+ * dss2_tag_bwd_tc2_workspace_bytes() for the hop levels of the masked output gradient; it runs the backward-to-input as the forward
+ * kernel with transposed weights (grad_x = sum_k (A^k g) W_k) and the weight gradients as one streaming MN-major GEMM
+ * (grad_W_k = (A^k g)^T x), with no hop recomputation on x.  When every pointer is 16-byte aligned the entry points launch the
+ * TMA-fed kernel k_tag_tc3 (inputs by cp.async.bulk[.tensor], hop levels spilled by bulk store; the forward for any cout, the
+ * backward-to-input for cout == 32), else k_tag_tc2 with direct loads (DSS2_TC3=0 forces that).  Contract details of the TMA path:
+ * act_bits buffers hold (num_nodes + 3) & ~3 words (the sign words of a tile are copied from a 16-byte aligned start);
+ * the last 256 bytes of the backward workspace carry a format word written by _gx and read by _gw / dss2_tag_gw_ffma (0 = plain
+ * level rows, 1 = rows whose 16-byte chunk c is stored at chunk c ^ (row & 7)): pass the SAME workspace to both. */
 int dss2_tag_tc2_supported(const dss2_graph_t* g, int K);
 int dss2_tag_fwd_tc2(const dss2_graph_t* g, const float* x, const float* w, const float* bias, int cout, int K,
                      int act, float p_drop, int drop_mode, const uint64_t* rng_state, uint32_t layer_uid,
