@@ -527,7 +527,7 @@ def main():
         stage.edge_attr.copy_(store.edge_attr[:SB * e])
         t2 = GraphedTrainer(stage, B, spec=default_spec(), reg_coefs=REG, seed=0, process_group=pg, world_size=world,
                             use_cuda_graph=not args.no_graph).capture()
-        nbuf = 4
+        nbuf = max(1, min(4, args.scenarios // B))
         host_x = [store.x[i * B * n:(i + 1) * B * n].cpu().pin_memory() for i in range(nbuf)]
         host_ea = [store.edge_attr[i * B * e:(i + 1) * B * e].cpu().pin_memory() for i in range(nbuf)]
         host_loss = torch.zeros(K + W, dtype=torch.float32).pin_memory()

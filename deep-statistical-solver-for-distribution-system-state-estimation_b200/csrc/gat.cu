@@ -750,6 +750,170 @@ __global__ void __launch_bounds__(GAT_THREADS) k_gine_bwd_b(GineArgs a) {
   }
 }
 
+// -------------------------------------------------------------------------------------------------
+// gnn_dsse (networks.py:11-69): GCN2Conv / TAGConv stacks at width dim_feat <= 8 on the ONE-WAY edge list as given (the model does not
+// un-direct it), built from four small thread-per-bus kernels.  The CSR rows of dss2_graph_t hold the in-edges of a bus (entries
+// without the reversed flag, in edge order = PyG's scatter order) and, flagged, its out-edges: the transposed propagation of the
+// backward walks the same row.
+// -------------------------------------------------------------------------------------------------
+struct GnnArgs {
+  dss2_graph_t g;
+  const float* dinv;     // [Nt] deg^-1/2 of gcn_norm (in-degree, + 1 with self loops), inf -> 0
+  int self_loops;
+  int transposed;
+  const float* x;        // [Nt, >= 8], row stride xs
+  int64_t xs;
+  float scale;           // out = scale * (A x) + add_scale * add
+  const float* add;
+  int64_t adds;
+  float add_scale;
+  float* out;            // [Nt, 8]
+};
+
+__global__ void __launch_bounds__(GAT_THREADS) k_gcn_dinv(dss2_graph_t g, int self_loops, float* dinv) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < g.num_nodes; i += (int64_t)gridDim.x * blockDim.x) {
+    int deg = self_loops ? 1 : 0;
+    for (int z = g.rowptr[i]; z < g.rowptr[i + 1]; ++z) deg += (g.eid[z] >> 31) ? 0 : 1;
+    dinv[i] = deg > 0 ? 1.0f / sqrtf((float)deg) : 0.0f;   // deg.pow(-0.5), inf -> 0 (gcn_norm)
+  }
+}
+
+// out[i] = scale * sum_{j -> i} dinv[j] dinv[i] x[j] (+ self loop last, as add_remaining_self_loops appends it) + add_scale * add[i];
+// transposed: the sum runs over the out-edges i -> j instead (adjoint of the propagation).  Every product / sum is rounded on its own
+// like the eager ops of the reference (no fused multiply-add).
+__global__ void __launch_bounds__(GAT_THREADS) k_prop8(GnnArgs a) {
+  const dss2_graph_t& g = a.g;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < g.num_nodes; i += (int64_t)gridDim.x * blockDim.x) {
+    const float di = a.dinv[i];
+    float acc[GC];
+#pragma unroll
+    for (int c = 0; c < GC; ++c) acc[c] = 0.0f;
+    for (int z = g.rowptr[i]; z < g.rowptr[i + 1]; ++z) {
+      const bool rev = g.eid[z] >> 31;
+      if (rev != (a.transposed != 0)) continue;
+      const int64_t j = g.col[z];
+      const float w = __fmul_rn(a.dinv[j], di);
+      const float* xj = a.x + j * a.xs;
+#pragma unroll
+      for (int c = 0; c < GC; ++c) acc[c] = __fadd_rn(acc[c], __fmul_rn(w, xj[c]));
+    }
+    if (a.self_loops) {
+      const float w = __fmul_rn(di, di);
+      const float* xi = a.x + i * a.xs;
+#pragma unroll
+      for (int c = 0; c < GC; ++c) acc[c] = __fadd_rn(acc[c], __fmul_rn(w, xi[c]));
+    }
+    float o[GC];
+#pragma unroll
+    for (int c = 0; c < GC; ++c) {
+      o[c] = __fmul_rn(acc[c], a.scale);
+      if (a.add) o[c] = __fadd_rn(o[c], __fmul_rn(a.add_scale, a.add[i * a.adds + c]));
+    }
+    float4* dst = reinterpret_cast<float4*>(a.out + i * GC);
+    dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+    dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+  }
+}
+
+struct Lin8Args {
+  int64_t num_nodes;
+  int M;                  // matrices (1 for GCN2Conv, K + 1 for TAGConv)
+  int wt;                 // 0: z = in W (GCN2Conv weight1 [in, out]); 1: z = in W^T (Linear weight [out, in])
+  const float* in[4];     // [Nt, >= 8] each
+  int64_t ins[4];
+  const float* w;         // [M][8][8]
+  const float* bias;      // [8] or NULL
+  int act;                // 0 none, 1 leaky_relu(slope), 2 relu, 3 tanh
+  float slope;
+  float* y;               // fwd: [Nt, 8]
+  const float* yout;      // bwd: the forward's y
+  const float* gy;        // bwd: [Nt, 8]
+  float* gz;              // bwd: [Nt, 8] adjoint of the pre-activation (input of the weight-gradient reduction)
+  float* gin[4];          // bwd: [Nt, 8] adjoint of in[m]
+  float* acc;             // bwd, optional: acc[n] += acc_scale * gin[0][n]   (GCN2Conv: the x_0 path)
+  float acc_scale;
+};
+struct Lin8W {
+  float w[4][GC * GC], b[GC];
+};
+__device__ __forceinline__ void lin8_load(Lin8W& s, const Lin8Args& a) {
+  for (int i = threadIdx.x; i < a.M * GC * GC; i += blockDim.x) s.w[i / (GC * GC)][i % (GC * GC)] = a.w[i];
+  if (threadIdx.x < GC) s.b[threadIdx.x] = a.bias ? a.bias[threadIdx.x] : 0.0f;
+}
+__global__ void __launch_bounds__(GAT_THREADS) k_lin8_fwd(Lin8Args a) {
+  __shared__ Lin8W s;
+  lin8_load(s, a);
+  __syncthreads();
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.num_nodes; i += (int64_t)gridDim.x * blockDim.x) {
+    float z[GC];
+#pragma unroll
+    for (int c = 0; c < GC; ++c) z[c] = 0.0f;
+    for (int m = 0; m < a.M; ++m) {
+      float v[GC], t[GC];
+      const float* p = a.in[m] + i * a.ins[m];
+#pragma unroll
+      for (int j = 0; j < GC; ++j) v[j] = p[j];
+#pragma unroll
+      for (int c = 0; c < GC; ++c) {
+        float d = 0.0f;
+#pragma unroll
+        for (int j = 0; j < GC; ++j) d = fmaf(v[j], a.wt ? s.w[m][c * GC + j] : s.w[m][j * GC + c], d);
+        t[c] = d;
+      }
+#pragma unroll
+      for (int c = 0; c < GC; ++c) z[c] = m == 0 ? t[c] : z[c] + t[c];   // out = lins[0](x); out = out + lins[k](x_k)
+    }
+#pragma unroll
+    for (int c = 0; c < GC; ++c) {
+      float v = a.bias ? z[c] + s.b[c] : z[c];
+      if (a.act == 1) v = v > 0.0f ? v : v * a.slope;
+      else if (a.act == 2) v = fmaxf(v, 0.0f);
+      else if (a.act == 3) v = tanhf(v);
+      z[c] = v;
+    }
+    float4* dst = reinterpret_cast<float4*>(a.y + i * GC);
+    dst[0] = make_float4(z[0], z[1], z[2], z[3]);
+    dst[1] = make_float4(z[4], z[5], z[6], z[7]);
+  }
+}
+__global__ void __launch_bounds__(GAT_THREADS) k_lin8_bwd(Lin8Args a) {
+  __shared__ Lin8W s;
+  lin8_load(s, a);
+  __syncthreads();
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.num_nodes; i += (int64_t)gridDim.x * blockDim.x) {
+    float g[GC];
+#pragma unroll
+    for (int c = 0; c < GC; ++c) {
+      const float y = a.yout ? a.yout[i * GC + c] : 0.0f;
+      float d = 1.0f;
+      if (a.act == 1) d = y > 0.0f ? 1.0f : a.slope;
+      else if (a.act == 2) d = y > 0.0f ? 1.0f : 0.0f;
+      else if (a.act == 3) d = 1.0f - y * y;
+      g[c] = a.gy[i * GC + c] * d;
+    }
+    float4* gz = reinterpret_cast<float4*>(a.gz + i * GC);
+    gz[0] = make_float4(g[0], g[1], g[2], g[3]);
+    gz[1] = make_float4(g[4], g[5], g[6], g[7]);
+    for (int m = 0; m < a.M; ++m) {
+      float o[GC];
+#pragma unroll
+      for (int j = 0; j < GC; ++j) {
+        float d = 0.0f;
+#pragma unroll
+        for (int c = 0; c < GC; ++c) d = fmaf(g[c], a.wt ? s.w[m][c * GC + j] : s.w[m][j * GC + c], d);
+        o[j] = d;
+      }
+      float4* dst = reinterpret_cast<float4*>(a.gin[m] + i * GC);
+      dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+      dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+      if (m == 0 && a.acc) {
+#pragma unroll
+        for (int j = 0; j < GC; ++j) a.acc[i * GC + j] += a.acc_scale * o[j];
+      }
+    }
+  }
+}
+
 int grid_for(int64_t n, int threads) { return (int)max((int64_t)1, min((int64_t)dss2_sm_count() * 8, (n + threads - 1) / threads)); }
 
 int fill_args(const char* who, GatArgs& a, const dss2_graph_t* g, const float* x, int64_t xs, const float* ea, int64_t eas, int fe,
@@ -960,5 +1124,110 @@ extern "C" int dss2_mlp2_bwd(int64_t num_nodes, const float* x, int din, const f
   DSS2_LAUNCH_CHECK();
   k_outer_reduce<<<np, OR_THREADS, 0, stream>>>(num_nodes, grad_z, dout, dout, h, dmid, dmid, partials, partial_stride, o_w2, o_b2);
   DSS2_LAUNCH_CHECK();
+  return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// gnn_dsse building blocks (networks.py:11-69), see the kernels above
+// -------------------------------------------------------------------------------------------------
+extern "C" int dss2_gcn_dinv(const dss2_graph_t* g, int self_loops, float* dinv, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DSS2_CHECK_ARG(g && dinv, "dss2_gcn_dinv: null argument");
+  DSS2_CHECK_ARG(g->undirected == 1, "dss2_gcn_dinv: needs a graph built from the one-way edge list with undirect=1");
+  if (g->num_nodes == 0) return 0;
+  k_gcn_dinv<<<grid_for(g->num_nodes, GAT_THREADS), GAT_THREADS, 0, stream>>>(*g, self_loops, dinv);
+  DSS2_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int dss2_gcn_prop8(const dss2_graph_t* g, const float* dinv, int self_loops, int transposed, const float* x, int64_t x_stride,
+                              float scale, const float* add, int64_t add_stride, float add_scale, float* out, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DSS2_CHECK_ARG(g && dinv && x && out, "dss2_gcn_prop8: null argument");
+  DSS2_CHECK_ARG(x_stride >= GC && (!add || add_stride >= GC) && ((uintptr_t)out & 15) == 0, "dss2_gcn_prop8: rows must hold 8 floats, out 16-byte aligned");
+  DSS2_CHECK_ARG(x != out, "dss2_gcn_prop8: in-place propagation is not possible");
+  if (g->num_nodes == 0) return 0;
+  GnnArgs a = {};
+  a.g = *g;
+  a.dinv = dinv;
+  a.self_loops = self_loops;
+  a.transposed = transposed;
+  a.x = x;
+  a.xs = x_stride;
+  a.scale = scale;
+  a.add = add;
+  a.adds = add_stride;
+  a.add_scale = add_scale;
+  a.out = out;
+  k_prop8<<<grid_for(g->num_nodes, GAT_THREADS), GAT_THREADS, 0, stream>>>(a);
+  DSS2_LAUNCH_CHECK();
+  return 0;
+}
+
+static int lin8_fill(const char* who, Lin8Args& a, int64_t num_nodes, int M, int wt, const float* const* in, const int64_t* in_strides, const float* w,
+                     const float* bias, int act, float slope) {
+  DSS2_CHECK_ARG(M >= 1 && M <= 4 && in && in_strides && w, "%s: 1..4 input matrices", who);
+  DSS2_CHECK_ARG(act >= 0 && act <= 3, "%s: act %d outside 0..3", who, act);
+  a.num_nodes = num_nodes;
+  a.M = M;
+  a.wt = wt;
+  for (int m = 0; m < M; ++m) {
+    DSS2_CHECK_ARG(in[m] && in_strides[m] >= GC, "%s: input %d missing or narrower than 8", who, m);
+    a.in[m] = in[m];
+    a.ins[m] = in_strides[m];
+  }
+  a.w = w;
+  a.bias = bias;
+  a.act = act;
+  a.slope = slope;
+  return 0;
+}
+
+extern "C" int dss2_lin8_fwd(int64_t num_nodes, int M, int weight_is_out_by_in, const float* const* in, const int64_t* in_strides, const float* w,
+                             const float* bias, int act, float slope, float* y, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  Lin8Args a = {};
+  if (lin8_fill("dss2_lin8_fwd", a, num_nodes, M, weight_is_out_by_in, in, in_strides, w, bias, act, slope)) return -1;
+  DSS2_CHECK_ARG(y && ((uintptr_t)y & 15) == 0, "dss2_lin8_fwd: y must be a 16-byte aligned [Nt, 8] buffer");
+  if (num_nodes == 0) return 0;
+  a.y = y;
+  k_lin8_fwd<<<grid_for(num_nodes, GAT_THREADS), GAT_THREADS, 0, stream>>>(a);
+  DSS2_LAUNCH_CHECK();
+  return 0;
+}
+
+// grad_in[m] [Nt, 8] for every input, grad_z [Nt, 8]; weight gradients: per-CTA partial sums at partials + m * 64 (layout of `w`),
+// bias gradient (sum of grad_z) at partials + bias_offset (pass scratch space when the layer has no bias).  acc (optional):
+// acc += acc_scale * grad_in[0] (GCN2Conv's x_0 path).
+extern "C" int dss2_lin8_bwd(int64_t num_nodes, int M, int weight_is_out_by_in, const float* const* in, const int64_t* in_strides, const float* w,
+                             int act, float slope, const float* y, const float* grad_y, float* grad_z, float* const* grad_in, float* acc,
+                             float acc_scale, float* partials, int64_t partial_stride, int64_t bias_offset, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  Lin8Args a = {};
+  if (lin8_fill("dss2_lin8_bwd", a, num_nodes, M, weight_is_out_by_in, in, in_strides, w, nullptr, act, slope)) return -1;
+  DSS2_CHECK_ARG(grad_y && grad_z && grad_in && partials && (!act || y), "dss2_lin8_bwd: null argument");
+  if (num_nodes == 0) return 0;
+  a.yout = y;
+  a.gy = grad_y;
+  a.gz = grad_z;
+  for (int m = 0; m < M; ++m) {
+    DSS2_CHECK_ARG(grad_in[m] && ((uintptr_t)grad_in[m] & 15) == 0, "dss2_lin8_bwd: grad_in[%d] missing or unaligned", m);
+    a.gin[m] = grad_in[m];
+  }
+  a.acc = acc;
+  a.acc_scale = acc_scale;
+  k_lin8_bwd<<<grid_for(num_nodes, GAT_THREADS), GAT_THREADS, 0, stream>>>(a);
+  DSS2_LAUNCH_CHECK();
+  const int np = dss2_num_partials();
+  for (int m = 0; m < M; ++m) {
+    // Linear weight [out c][in j]: sum_n gz[n][c] in[n][j];  GCN2Conv weight1 [in j][out c]: sum_n in[n][j] gz[n][c]
+    if (weight_is_out_by_in)
+      k_outer_reduce<<<np, OR_THREADS, 0, stream>>>(num_nodes, grad_z, GC, GC, in[m], in_strides[m], GC, partials, partial_stride, (int64_t)m * GC * GC,
+                                                    bias_offset);
+    else
+      k_outer_reduce<<<np, OR_THREADS, 0, stream>>>(num_nodes, in[m], in_strides[m], GC, grad_z, GC, GC, partials, partial_stride, (int64_t)m * GC * GC,
+                                                    bias_offset);
+    DSS2_LAUNCH_CHECK();
+  }
   return 0;
 }

@@ -12,8 +12,7 @@ EdgeAggregation.forward (networks.py:196-200) never reaches `message` and is not
 PFN receive the same raw edge attributes; reversed edges negate attribute columns 0 and 2 (networks.py:252).
 There is no CPU fallback: without a CUDA device or the built library, forward raises.
 GAT_DSSE (networks.py:113-156, the as-shipped default of dss2_run.py:86) runs on its own fused GATv2 kernels
-(csrc/gat.cu), and so does GINE_DSSE (networks.py:71-111).  gnn_dsse (GCN2/FA/Cheb/GCN stacks) remains a name only so that
-`from networks import ...` works.
+(csrc/gat.cu), and so do GINE_DSSE (networks.py:71-111) and gnn_dsse (networks.py:11-69; model='gcn2' and 'tagcn').
 """
 import math
 
@@ -145,16 +144,63 @@ class SkipPFN(PFN):
     _sub = SkipMPN
 
 
-def _next_row(name, where):
-    class _Pending(nn.Module):
-        def __init__(self, *args, **kwargs):
-            raise NotImplementedError(f"{name} ({where}) is outside the B200 hot path built so far (SURVEY.md 8f-1: "
-                                      "GATv2 / GINE / GCN2 / FA layers are the next row); use MPN / SkipMPN / PFN / SkipPFN")
-    _Pending.__name__ = name
-    return _Pending
+class _GCN2Params(nn.Module):
+    """Parameter holder with PyG GCN2Conv's name / shape / initialisation: `weight1` [channels, channels], glorot (shared_weights=True:
+    no `weight2`).  The arithmetic is in the fused kernels (csrc/gat.cu)."""
+
+    def __init__(self, channels):
+        super().__init__()
+        self.weight1 = nn.Parameter(torch.empty(channels, channels))
+        nn.init.xavier_uniform_(self.weight1)
 
 
-gnn_dsse = _next_row("gnn_dsse", "networks.py:11-69")
+class gnn_dsse(_LazyMachinery, nn.Module):
+    """networks.py:11-69: (num_layers - 1) x [conv + nonlin], Linear(dim_feat, dim_dense), Linear(dim_dense, dim_out) in a PyG `Sequential`
+    (children `module_{i}`), `forward(x, edge_index)` with x_0 = x.  conv = GCN2Conv(channels, alpha=main_param, theta, shared_weights,
+    cached, normalize, add_self_loops) for model='gcn2' (the default) or TAGConv(channels, channels, K, bias, normalize) for
+    model='tagcn'.  Built for what the reference's defaults select (theta=None, shared_weights=True, normalize=True, dropout 0);
+    model='fagcn' and the other settings raise.  `cached=True` is accepted and ignored: the normalisation is recomputed per batch."""
+
+    def __init__(self, dim_feat, dim_dense, dim_out, num_layers, nonlin='leaky_relu', main_param=0.1, K=3, bias=True, dropout=0., theta=None,
+                 shared_weights=True, cached=True, add_self_loops=True, normalize=True, model='gcn2'):
+        super().__init__()
+        if nonlin not in ('relu', 'tanh', 'leaky_relu'):
+            raise Exception('invalid activation type')
+        if model not in ('gcn2', 'fagcn', 'tagcn'):
+            raise Exception('invalid model type')
+        if model == 'fagcn':
+            raise NotImplementedError("gnn_dsse(model='fagcn') (FAConv, networks.py:44-50) is not built; 'gcn2' and 'tagcn' are")
+        if theta is not None or not shared_weights or not normalize:
+            raise NotImplementedError("gnn_dsse kernels cover theta=None, shared_weights=True, normalize=True (the reference's defaults)")
+        self.channels, self.main_param, self.dim_out, self.K, self.dropout, self.bias = dim_feat, main_param, dim_out, K, dropout, bias
+        self.theta, self.num_layers, self.shared_weights, self.cached = theta, num_layers, shared_weights, cached
+        self.normalize, self.add_self_loops, self.dim_dense, self.kind, self.nonlin_name = normalize, add_self_loops, dim_dense, model, nonlin
+        self.nonlin = {'relu': nn.ReLU, 'tanh': nn.Tanh, 'leaky_relu': nn.LeakyReLU}[nonlin]()
+        self.model = nn.Module()
+        i = 0
+        for _ in range(num_layers - 1):
+            self.model.add_module(f"module_{i}", _GCN2Params(dim_feat) if model == 'gcn2' else TAGConv(dim_feat, dim_feat, K=K, bias=bias))
+            self.model.add_module(f"module_{i + 1}", self.nonlin)
+            i += 2
+        self.model.add_module(f"module_{i}", nn.Linear(dim_feat, dim_dense))
+        self.model.add_module(f"module_{i + 1}", nn.Linear(dim_dense, dim_out))
+
+    def _machinery(self):
+        m = self.__dict__.get("_dss2_machinery")
+        if m is None:
+            from dss2 import gnn
+            spec = gnn.GNNSpec(model=self.kind, dim_feat=self.channels, dim_dense=self.dim_dense, dim_out=self.dim_out,
+                               num_layers=self.num_layers, alpha=float(self.main_param), K=self.K, bias=bool(self.bias),
+                               self_loops=bool(self.add_self_loops), normalize=bool(self.normalize), act=self.nonlin_name,
+                               act_slope=float(getattr(self.nonlin, "negative_slope", 0.0)))
+            m = gnn.make_machinery(spec)
+            self.__dict__["_dss2_machinery"] = m
+        return m
+
+    def forward(self, x, edge_index):
+        from dss2 import gnn
+        runner, pack = self._machinery()
+        return gnn.gnn_apply(runner, pack, dict(self.named_parameters()), x, edge_index)
 
 
 class _GINEParams(nn.Module):

@@ -292,6 +292,25 @@ int dss2_mlp2_bwd(int64_t num_nodes, const float* x, int din, const float* w1, i
                   const float* h, const float* grad_z, float* grad_h_ws, float* grad_x, float* partials, int64_t partial_stride,
                   void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * gnn_dsse building blocks (networks.py:11-69: GCN2Conv / TAGConv stacks at width dim_feat <= 8 on the one-way edge list as given).
+ * dss2_gcn_dinv: gcn_norm's deg^-1/2 per bus (in-degree, + 1 with add_self_loops; inf -> 0).
+ * dss2_gcn_prop8: out = scale * (A_hat x) + add_scale * add with A_hat = D^-1/2 (A [+ I]) D^-1/2 over the in-edges in PyG's scatter
+ *   order (self loop last), or - transposed != 0 - over the out-edges (adjoint).  Rows are 8 floats (zero padded), x with row stride.
+ * dss2_lin8_fwd/bwd: y = act(sum_m in_m W_m [+ b]) per bus for M <= 4 inputs of width 8; weight_is_out_by_in = 1 for torch Linear
+ *   weights [out, in] (TAGConv.lins), 0 for GCN2Conv.weight1 [in, out]; act: 0 none, 1 leaky_relu(slope), 2 relu, 3 tanh.  The backward
+ *   writes grad_z, grad_in[m], optionally acc += acc_scale * grad_in[0], and per-CTA partial sums of the weight gradients (layout of w)
+ *   at partials, of the bias gradient at partials + bias_offset.
+ * ---------------------------------------------------------------------------------------------- */
+int dss2_gcn_dinv(const dss2_graph_t* g, int self_loops, float* dinv, void* stream);
+int dss2_gcn_prop8(const dss2_graph_t* g, const float* dinv, int self_loops, int transposed, const float* x, int64_t x_stride,
+                   float scale, const float* add, int64_t add_stride, float add_scale, float* out, void* stream);
+int dss2_lin8_fwd(int64_t num_nodes, int M, int weight_is_out_by_in, const float* const* in, const int64_t* in_strides, const float* w,
+                  const float* bias, int act, float slope, float* y, void* stream);
+int dss2_lin8_bwd(int64_t num_nodes, int M, int weight_is_out_by_in, const float* const* in, const int64_t* in_strides, const float* w,
+                  int act, float slope, const float* y, const float* grad_y, float* grad_z, float* const* grad_in, float* acc,
+                  float acc_scale, float* partials, int64_t partial_stride, int64_t bias_offset, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

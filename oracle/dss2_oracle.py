@@ -332,6 +332,75 @@ def init_gine_state_dict(dim_feat=8, dim_dense=32, dim_out=2, num_layers=8, edge
 
 
 # --------------------------------------------------------------------------------------------
+# gnn_dsse (networks.py:11-69): (num_layers - 1) x [conv + nonlin], Linear(dim_feat, dim_dense), Linear(dim_dense, dim_out);
+# forward(x, edge_index) with x_0 = x, on the edge list AS GIVEN (no un-directing).  model='gcn2': GCN2Conv(channels, alpha,
+# shared_weights=True, add_self_loops, normalize); model='tagcn': TAGConv(channels, channels, K, bias, normalize).
+# --------------------------------------------------------------------------------------------
+
+
+def gcn_norm_self_loops(edge_index, num_nodes, dtype):
+    """PyG gcn_norm(add_self_loops=True) for an edge list without self loops: the edges keep their order, one loop per node is
+    appended; deg = in-degree + 1 by target; w = deg[src]^-1/2 * deg[dst]^-1/2."""
+    loop = torch.arange(num_nodes)
+    ei = torch.cat([edge_index, torch.stack([loop, loop])], dim=1)
+    return ei, gcn_weights(ei, num_nodes, dtype)
+
+
+def gnn_dsse_forward(sd, x, edge_index, num_layers, model="gcn2", alpha=0.1, K=3, add_self_loops=True, slope=0.01):
+    """gnn_dsse.forward (networks.py:67-69) from a reference-named state_dict (`model.module_{2l}.weight1` / `.lins.{k}.weight`, `.bias`)."""
+    n = x.size(0)
+    x0, h = x, x
+    for l in range(num_layers - 1):
+        p = f"model.module_{2 * l}."
+        if model == "gcn2":
+            if add_self_loops:
+                ei, w = gcn_norm_self_loops(edge_index, n, x.dtype)
+            else:
+                ei, w = edge_index, gcn_weights(edge_index, n, x.dtype)
+            prop = segment_sum(w.view(-1, 1) * h[ei[0]], ei[1], n)          # GCN2Conv.message / aggr='add'
+            out = prop * (1 - alpha) + alpha * x0                           # x.mul_(1 - alpha); x_0 = alpha * x_0; x.add_(x_0)
+            h = out @ sd[p + "weight1"]                                     # addmm(out, out, weight1, beta=0, alpha=1)
+        elif model == "tagcn":
+            ws = []
+            k = 0
+            while f"{p}lins.{k}.weight" in sd:
+                ws.append(sd[f"{p}lins.{k}.weight"])
+                k += 1
+            h = tag_conv(h, edge_index, ws, sd.get(p + "bias"))
+        else:
+            raise NotImplementedError(model)
+        h = torch.nn.functional.leaky_relu(h, slope)
+    i = 2 * (num_layers - 1)
+    h = h @ sd[f"model.module_{i}.weight"].t() + sd[f"model.module_{i}.bias"]
+    return h @ sd[f"model.module_{i + 1}.weight"].t() + sd[f"model.module_{i + 1}.bias"]
+
+
+def init_gnn_state_dict(model="gcn2", dim_feat=8, dim_dense=32, dim_out=2, num_layers=4, K=3, seed=0, dtype=torch.float32):
+    """Random parameters under the reference's names (PyG Sequential children `module_{i}`); biases non-zero so that they matter."""
+    g = torch.Generator().manual_seed(seed)
+
+    def u(*shape, bound):
+        return ((torch.rand(*shape, generator=g) * 2 - 1) * bound).to(dtype)
+
+    sd = {}
+    c = dim_feat
+    for l in range(num_layers - 1):
+        p = f"model.module_{2 * l}."
+        if model == "gcn2":
+            sd[p + "weight1"] = u(c, c, bound=math.sqrt(6.0 / (2 * c)))
+        else:
+            sd[p + "bias"] = u(c, bound=0.1)
+            for k in range(K + 1):
+                sd[p + f"lins.{k}.weight"] = u(c, c, bound=1.0 / math.sqrt(c))
+    i = 2 * (num_layers - 1)
+    sd[f"model.module_{i}.weight"] = u(dim_dense, c, bound=1.0 / math.sqrt(c))
+    sd[f"model.module_{i}.bias"] = u(dim_dense, bound=1.0 / math.sqrt(c))
+    sd[f"model.module_{i + 1}.weight"] = u(dim_out, dim_dense, bound=1.0 / math.sqrt(dim_dense))
+    sd[f"model.module_{i + 1}.bias"] = u(dim_out, bound=1.0 / math.sqrt(dim_dense))
+    return sd
+
+
+# --------------------------------------------------------------------------------------------
 # physics: branch flows (data.py:328-390) and the WLS loss (data.py:393-459)
 # --------------------------------------------------------------------------------------------
 

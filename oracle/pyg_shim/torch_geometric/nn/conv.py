@@ -1,8 +1,8 @@
 """`torch_geometric.nn.conv` subset (oracle shim, test infrastructure).
 
 Implemented from PyG's published semantics: MessagePassing(aggr='add', flow='source_to_target'),
-gcn_norm(add_self_loops=False), TAGConv, and GATv2Conv (the as-shipped default model of
-dss2_run.py:86).  The other conv classes named by reference networks.py:7 (GCN2Conv, FAConv,
+gcn_norm, TAGConv, GCN2Conv, and GATv2Conv (the as-shipped default model of
+dss2_run.py:86).  The other conv classes named by reference networks.py:7 (FAConv,
 GCNConv, ChebConv) exist only as names so that the reference module imports; GINEConv (networks.py:100) is restated too.
 """
 import inspect
@@ -61,10 +61,18 @@ def gcn_norm(edge_index, edge_weight=None, num_nodes=None, improved=False, add_s
              flow="source_to_target", dtype=None):
     """PyG `gcn_norm` for dense-index input.  TAGConv calls it with add_self_loops=False:
     w = 1; deg = scatter(w, col, N); dis = deg^-1/2 with inf -> 0; w = dis[row] * w * dis[col]."""
-    if add_self_loops:
-        raise NotImplementedError("shim: only the add_self_loops=False path (TAGConv) is restated")
     if edge_weight is None:
         edge_weight = torch.ones((edge_index.size(1),), dtype=dtype, device=edge_index.device)
+    if add_self_loops:
+        # PyG `add_remaining_self_loops(edge_index, edge_weight, fill_value = 2 if improved else 1, num_nodes)`: the non-loop edges keep
+        # their order, then ONE loop per node is appended (an existing loop keeps its weight; the reference's data has none)
+        keep = edge_index[0] != edge_index[1]
+        loop_w = torch.full((num_nodes,), 2.0 if improved else 1.0, dtype=edge_weight.dtype, device=edge_index.device)
+        if bool((~keep).any()):
+            loop_w[edge_index[0][~keep]] = edge_weight[~keep]
+        loop = torch.arange(num_nodes, device=edge_index.device)
+        edge_index = torch.cat([edge_index[:, keep], torch.stack([loop, loop])], dim=1)
+        edge_weight = torch.cat([edge_weight[keep], loop_w])
     row, col = edge_index[0], edge_index[1]
     idx = col if flow == "source_to_target" else row
     deg = scatter(edge_weight, idx, dim=0, dim_size=num_nodes, reduce="sum")
@@ -116,7 +124,59 @@ def _outside_hot_path(name):
     return _Stub
 
 
-GCN2Conv = _outside_hot_path("GCN2Conv")
+class GCN2Conv(MessagePassing):
+    """PyG GCN2Conv(channels, alpha, theta=None, layer=None, shared_weights=True, cached=False, add_self_loops=True, normalize=True), as
+    used at reference networks.py:44: weight1 [channels, channels] glorot (weight2 only when shared_weights=False);
+    beta = log(theta / layer + 1) when both are given, else 1.
+      forward(x, x_0, edge_index): gcn_norm(add_self_loops) (cached after the first call when cached=True);
+      x = propagate(A_hat x); x.mul_(1 - alpha); x_0 = alpha * x_0[:N]; out = x.add_(x_0);
+      out = addmm(out, out, weight1, beta = 1 - beta, alpha = beta)   (beta = 1: out @ weight1)."""
+
+    def __init__(self, channels, alpha, theta=None, layer=None, shared_weights=True, cached=False, add_self_loops=True, normalize=True,
+                 **kwargs):
+        kwargs.setdefault("aggr", "add")
+        super().__init__(**kwargs)
+        import math
+        self.channels, self.alpha, self.beta = channels, alpha, 1.0
+        if theta is not None or layer is not None:
+            assert theta is not None and layer is not None
+            self.beta = math.log(theta / layer + 1)
+        self.cached, self.normalize, self.add_self_loops_ = cached, normalize, add_self_loops
+        self._cached_edge_index = None
+        self.weight1 = nn.Parameter(torch.empty(channels, channels))
+        if shared_weights:
+            self.register_parameter("weight2", None)
+        else:
+            self.weight2 = nn.Parameter(torch.empty(channels, channels))
+        nn.init.xavier_uniform_(self.weight1)
+        if self.weight2 is not None:
+            nn.init.xavier_uniform_(self.weight2)
+
+    def forward(self, x, x_0, edge_index, edge_weight=None):
+        if self.normalize:
+            cache = self._cached_edge_index
+            if cache is None:
+                edge_index, edge_weight = gcn_norm(edge_index, edge_weight, x.size(self.node_dim), False, self.add_self_loops_, self.flow,
+                                                   dtype=x.dtype)
+                if self.cached:
+                    self._cached_edge_index = (edge_index, edge_weight)
+            else:
+                edge_index, edge_weight = cache
+        x = self.propagate(edge_index, x=x, edge_weight=edge_weight)
+        x.mul_(1 - self.alpha)
+        x_0 = self.alpha * x_0[:x.size(0)]
+        if self.weight2 is None:
+            out = x.add_(x_0)
+            out = torch.addmm(out, out, self.weight1, beta=1. - self.beta, alpha=self.beta)
+        else:
+            out = torch.addmm(x, x, self.weight1, beta=1. - self.beta, alpha=self.beta)
+            out = out + torch.addmm(x_0, x_0, self.weight2, beta=1. - self.beta, alpha=self.beta)
+        return out
+
+    def message(self, x_j, edge_weight):
+        return x_j if edge_weight is None else edge_weight.view(-1, 1) * x_j
+
+
 FAConv = _outside_hot_path("FAConv")
 
 class GINEConv(MessagePassing):

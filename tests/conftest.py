@@ -171,3 +171,14 @@ def oracle_gine_run(orc, num_layers, sd, z, dtype):
     loss = orc.wls_loss(x, ea, out, *st, ei, REG_COEFS)
     loss.backward()
     return out.detach(), loss.detach(), {k: v.grad for k, v in p.items()}
+
+
+def oracle_gnn_run(orc, z, sd, dtype, grad_out=None):
+    """Oracle gnn_dsse forward + (WLS loss | sum(out * grad_out)) + autograd on the inputs of a golden file."""
+    x, ea, ei = torch.from_numpy(z["x"]).to(dtype), torch.from_numpy(z["edge_attr"]).to(dtype), torch.from_numpy(z["edge_index"])
+    st = [torch.from_numpy(z[k]).to(dtype) for k in ("x_mean", "x_std", "edge_mean", "edge_std")]
+    p = {k: v.to(dtype).clone().requires_grad_(True) for k, v in sd.items()}
+    out = orc.gnn_dsse_forward(p, x[:, :8], ei, int(z["num_layers"]), model=str(z["model"]), K=int(z["K"]))
+    loss = orc.wls_loss(x, ea, out, *st, ei, REG_COEFS) if grad_out is None else (out * grad_out.to(dtype)).sum()
+    loss.backward()
+    return out.detach(), loss.detach(), {k: v.grad for k, v in p.items()}

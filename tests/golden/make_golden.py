@@ -144,6 +144,31 @@ def run_gat(tag, batch, stats, sd_seed, num_layers=8):
     print(tag, "out", tuple(out.shape), "loss", res["loss"])
 
 
+def run_gnn(tag, model, batch, stats, sd_seed, num_layers=4, K=3):
+    """Reference gnn_dsse (networks.py:11-69; model='gcn2' or 'tagcn', defaults otherwise; cached=False so that the run does not depend
+    on call history) forward + gsp_wls_edge + backward on `batch`.  forward(x, edge_index): the one-way edge list as the script has it."""
+    sd = orc.init_gnn_state_dict(model=model, num_layers=num_layers, K=K, seed=sd_seed)
+    net = ref_net.gnn_dsse(dim_feat=8, dim_dense=32, dim_out=2, num_layers=num_layers, K=K, cached=False, model=model)
+    missing = net.load_state_dict(sd, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    net.train()
+    out = net(batch.x[:, :8], batch.edge_index)
+    res = {"x": batch.x.numpy(), "edge_index": batch.edge_index.numpy(), "edge_attr": batch.edge_attr.numpy(), "ptr": batch.ptr.numpy(),
+           "out": out.detach().numpy().copy(), "num_layers": num_layers, "K": K, "model": model, "sd_seed": sd_seed,
+           "x_mean": stats[0].numpy(), "x_std": stats[1].numpy(), "edge_mean": stats[2].numpy(), "edge_std": stats[3].numpy()}
+    got = {}
+    out.register_hook(lambda g_: got.__setitem__("g", g_.clone()))
+    loss = ref_loss(batch, out, stats)
+    loss.backward()
+    res["loss"] = np.array(loss.item())
+    res["grad_out"] = got["g"].numpy().copy()
+    for name, p in net.named_parameters():
+        res["grad." + name] = p.grad.detach().numpy().copy()
+        res["param." + name] = p.detach().numpy().copy()
+    np.savez_compressed(os.path.join(HERE, f"golden_model_{tag}.npz"), **res)
+    print(tag, "out", tuple(out.shape), "loss", res["loss"])
+
+
 def run_gine(tag, batch, stats, sd_seed, num_layers=8):
     """Reference GINE_DSSE forward + gsp_wls_edge + backward on `batch` (parameters stored under their named_parameters() names)."""
     sd = orc.init_gine_state_dict(num_layers=num_layers, seed=sd_seed)
@@ -218,6 +243,8 @@ def main():
 
     run_gat("gat_cigre", Batch.from_data_list(ds[50:56]), stats, sd_seed=6)
     run_gine("gine_cigre", Batch.from_data_list(ds[60:65]), stats, sd_seed=8)
+    run_gnn("gnn_gcn2_cigre", "gcn2", Batch.from_data_list(ds[70:76]), stats, sd_seed=21)
+    run_gnn("gnn_tagcn_cigre", "tagcn", Batch.from_data_list(ds[80:85]), stats, sd_seed=22)
 
     # ---- Oberrhein: synthetic scenarios from the product generator, reference model + loss on top ----
     grid = synth.load_grid("ober_sub")
@@ -228,6 +255,7 @@ def main():
     run_model("skippfn_ober", "SkipPFN", dict(default, n_gnn_layers=4, L=2), ob, ostats, sd_seed=5, torch_seed=15)
     run_gat("gat_ober", ob, ostats, sd_seed=7)
     run_gine("gine_ober", ob, ostats, sd_seed=9)
+    run_gnn("gnn_gcn2_ober", "gcn2", ob, ostats, sd_seed=23, num_layers=8)
     # a far-from-solution output so that all three soft-constraint penalties are active
     torch.manual_seed(99)
     wild = torch.stack([torch.randn(ob.x.shape[0]) * 3.0, torch.randn(ob.x.shape[0]) * 0.8], 1).requires_grad_(True)

@@ -1141,6 +1141,55 @@ def test_dss2_run_flow_with_default_gat_model(env):
     assert set(model.state_dict()) == set(sd0)
 
 
+# ------------------------------------------------------------------------------------------------ gnn_dsse (rest of scope row 8f-1)
+@pytest.mark.parametrize("tag", ["gnn_gcn2_cigre", "gnn_tagcn_cigre", "gnn_gcn2_ober"])
+@pytest.mark.parametrize("where", ["cuda", "cpu"])
+def test_gnn_dsse_matches_reference_run(env, tag, where):
+    """networks.gnn_dsse (model='gcn2' / 'tagcn'; thread-per-bus propagation and 8x8 transform kernels) with the weights of the reference
+    run: model output against the reference's own gnn_dsse executed over the shim (golden), the loss kernel on the output it received,
+    every parameter gradient on the upstream gradient the reference run recorded (strict) and end to end through the loss, and the
+    gradient w.r.t. x (x feeds both the first layer and, as x_0, every GCN2Conv).  fp64 oracle as arbiter."""
+    from conftest import golden_gat, oracle_gnn_run
+    nl, sd, grads, z = golden_gat(tag)
+    kind, K = str(z["model"]), int(z["K"])
+    model = env["networks"].gnn_dsse(dim_feat=8, dim_dense=32, dim_out=2, num_layers=nl, K=K, model=kind)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(where).train()
+    x, ea, ei = torch.from_numpy(z["x"]).to(where), torch.from_numpy(z["edge_attr"]).to(where), torch.from_numpy(z["edge_index"]).to(where)
+    st = [torch.from_numpy(z[k]) for k in ("x_mean", "x_std", "edge_mean", "edge_std")]
+    out = model(x[:, :8], ei)
+    assert out.device.type == where and out.shape == (x.size(0), 2)
+    out_before = out.detach().clone()
+    loss = env["data"].gsp_wls_edge(input=x[:, :8], edge_input=ea[:, :6], output=out, x_mean=st[0], x_std=st[1], edge_mean=st[2],
+                                    edge_std=st[3], edge_index=ei, reg_coefs=REG_COEFS, num_samples=None, node_param=x[:, 8:],
+                                    edge_param=ea[:, 6:])
+    loss.backward()
+    o32, l32, g32 = oracle_gnn_run(orc, z, sd, torch.float32)
+    o64, l64, g64 = oracle_gnn_run(orc, z, sd, torch.float64)
+    assert_fp32_parity(out_before, [z["out"], o32], o64, "out")
+    xo, eo, oo = x.cpu(), ea.cpu(), out_before.cpu()
+    l_ref = {dt: orc.wls_loss(xo.to(dt), eo.to(dt), oo.to(dt), *[t_.to(dt) for t_ in st], ei.cpu(), REG_COEFS) for dt in (torch.float32, torch.float64)}
+    assert_fp32_parity(loss.detach(), l_ref[torch.float32], l_ref[torch.float64], "loss (of our output)")
+    assert abs(float(loss) - float(l64)) <= 1e-4 * abs(float(l64)), "loss vs the reference run"
+    for name, p in model.named_parameters():
+        assert p.grad is not None and p.grad.device.type == where, name
+        assert_fp32_parity(p.grad, [grads[name], g32[name]], g64[name], name + " (end to end)", rtol=1e-4, noise_mult=16.0)
+    # backward kernels on the recorded upstream gradient, including the gradient w.r.t. the input
+    go = torch.from_numpy(z["grad_out"])
+    model.zero_grad()
+    xin = x[:, :8].clone().requires_grad_(True)
+    model(xin, ei).backward(go.to(where))
+    lin = {}
+    for dt in (torch.float32, torch.float64):
+        pp = {k: v.to(dt).clone().requires_grad_(True) for k, v in sd.items()}
+        xr = x.cpu().to(dt)[:, :8].clone().requires_grad_(True)
+        (orc.gnn_dsse_forward(pp, xr, ei.cpu(), nl, model=kind, K=K) * go.to(dt)).sum().backward()
+        lin[dt] = ({k: v.grad for k, v in pp.items()}, xr.grad)
+    for name, p in model.named_parameters():
+        assert_fp32_parity(p.grad, lin[torch.float32][0][name], lin[torch.float64][0][name], name + " (recorded grad_out)")
+    assert_fp32_parity(xin.grad, lin[torch.float32][1], lin[torch.float64][1], "grad_x (recorded grad_out)")
+
+
 # ------------------------------------------------------------------------------------------------ dataset builder on the device (scope row 8f-3)
 def test_dataset_builder_on_the_device_vs_reference_golden(env):
     """build_scenario_store(device='cuda') on the reference's own CIGRE-14 scenarios and its np.random noise stream against the golden

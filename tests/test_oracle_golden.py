@@ -159,3 +159,17 @@ def test_gine_dsse_forward_backward_vs_reference(tag):
     assert_fp32_parity(z["loss"], loss32, loss64, "loss")
     for name, g in grads.items():
         assert_fp32_parity(g, g32[name], g64[name], name)
+
+
+@pytest.mark.parametrize("tag", ["gnn_gcn2_cigre", "gnn_tagcn_cigre", "gnn_gcn2_ober"])
+def test_gnn_dsse_forward_backward_vs_reference(tag):
+    """Oracle gnn_dsse (GCN2Conv / TAGConv stacks on the one-way edge list + 2 Linear) + loss + autograd == the reference's gnn_dsse run
+    over the shim (same weights): the reference's recorded run must sit within fp32 noise of the fp64 oracle."""
+    from conftest import golden_gat, oracle_gnn_run
+    _, sd, grads, z = golden_gat(tag)
+    out32, loss32, g32 = oracle_gnn_run(orc, z, sd, torch.float32)
+    out64, loss64, g64 = oracle_gnn_run(orc, z, sd, torch.float64)
+    assert_fp32_parity(z["out"], out32, out64, "out")
+    assert_fp32_parity(z["loss"], loss32, loss64, "loss")
+    for name, g in grads.items():
+        assert_fp32_parity(g, g32[name], g64[name], name)
