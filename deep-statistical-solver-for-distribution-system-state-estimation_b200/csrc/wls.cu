@@ -502,7 +502,7 @@ int wls_generic(const WlsArgs& a, bool want_grad, cudaStream_t stream) {
 
 // get_pflow as a plain per-branch kernel (evaluation path, dss2_run.py:193-194): outputs are API tensors.
 __global__ void k_pflow(const int64_t* __restrict__ ei, int64_t Et, const float* __restrict__ y, int64_t ys,
-                        const float* __restrict__ ep, int64_t eps_, const float* __restrict__ vminmax, float* out8) {
+                        const float* __restrict__ ep, int64_t eps_, const float* __restrict__ vminmax, float* out8, int use_shift) {
   const WlsGrid grid = wls_grid(vminmax[0], vminmax[1]);
   for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < Et; e += (int64_t)gridDim.x * blockDim.x) {
     int64_t i = ei[e], j = ei[Et + e];
@@ -519,7 +519,7 @@ __global__ void k_pflow(const int64_t* __restrict__ ei, int64_t Et, const float*
     in.shift = row[5];
     in.rating = row[6];
     WlsBranch b;
-    wls_branch_forward(in, grid, b);
+    wls_branch_forward_delta(in, grid, b, use_shift ? (in.thi - in.thj) - in.shift : in.thi - in.thj);   // data.py:362-365
     out8[e] = b.ll;
     out8[Et + e] = b.lt;
     out8[2 * Et + e] = b.pf;
@@ -528,6 +528,47 @@ __global__ void k_pflow(const int64_t* __restrict__ ei, int64_t Et, const float*
     out8[5 * Et + e] = b.qt;
     out8[6 * Et + e] = b.i_f;
     out8[7 * Et + e] = b.i_t;
+  }
+}
+
+// Adjoint of get_pflow w.r.t. y = (V, theta): thread = bus n, which walks its incident branches through the CSR row of the doubled
+// graph (a non-reversed entry: n is the `to` end; a reversed one: n is the `from` end), re-evaluates the branch and keeps its own
+// end's share - every branch is evaluated once per end, no atomics, fixed order.
+__global__ void k_pflow_bwd(dss2_graph_t g, const float* __restrict__ y, int64_t ys, const float* __restrict__ ep, int64_t eps_,
+                            const float* __restrict__ vminmax, const float* __restrict__ gout8, int use_shift, float* __restrict__ gy) {
+  const WlsGrid grid = wls_grid(vminmax[0], vminmax[1]);
+  const int64_t Et = g.num_edges;
+  for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < g.num_nodes; n += (int64_t)gridDim.x * blockDim.x) {
+    float gv = 0.0f, gth = 0.0f;
+    for (int z = g.rowptr[n]; z < g.rowptr[n + 1]; ++z) {
+      const uint32_t id = g.eid[z];
+      const int64_t e = id & 0x7fffffffu;
+      const bool from_end = id >> 31;
+      const int64_t i = from_end ? n : g.col[z], j = from_end ? g.col[z] : n;
+      const float* row = ep + e * eps_;
+      WlsBranchIn in;
+      in.vi = y[i * ys];
+      in.thi = y[i * ys + 1];
+      in.vj = y[j * ys];
+      in.thj = y[j * ys + 1];
+      in.G = row[0];
+      in.B = row[1];
+      in.Gs = row[2];
+      in.Bs = row[3];
+      in.shift = row[5];
+      in.rating = row[6];
+      WlsBranch b;
+      wls_branch_forward_delta(in, grid, b, use_shift ? (in.thi - in.thj) - in.shift : in.thi - in.thj);
+      float go[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) go[q] = gout8[q * Et + e];
+      float dvi, dvj, ddel;
+      wls_pflow_backward(in, grid, b, go, dvi, dvj, ddel);
+      gv += from_end ? dvi : dvj;
+      gth += from_end ? ddel : -ddel;
+    }
+    gy[2 * n] = gv;
+    gy[2 * n + 1] = gth;
   }
 }
 
@@ -736,11 +777,28 @@ extern "C" int dss2_eval_metrics(const int64_t* edge_index, int64_t num_nodes, i
 
 extern "C" int dss2_pflow(const int64_t* edge_index, int64_t Et, const float* y, int64_t y_stride, const float* edge_param,
                           int64_t ep_stride, const float* vminmax, float* out8, void* stream_) {
+  return dss2_pflow_ex(edge_index, Et, y, y_stride, edge_param, ep_stride, vminmax, 0, out8, stream_);
+}
+
+extern "C" int dss2_pflow_ex(const int64_t* edge_index, int64_t Et, const float* y, int64_t y_stride, const float* edge_param,
+                             int64_t ep_stride, const float* vminmax, int use_shift, float* out8, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   DSS2_CHECK_ARG(edge_index && y && edge_param && vminmax && out8, "dss2_pflow: null argument");
   if (Et == 0) return 0;
   int grid = (int)max((int64_t)1, min((int64_t)148 * 8, (Et + 255) / 256));
-  k_pflow<<<grid, 256, 0, stream>>>(edge_index, Et, y, y_stride, edge_param, ep_stride, vminmax, out8);
+  k_pflow<<<grid, 256, 0, stream>>>(edge_index, Et, y, y_stride, edge_param, ep_stride, vminmax, out8, use_shift);
+  DSS2_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int dss2_pflow_bwd(const dss2_graph_t* g, const float* y, int64_t y_stride, const float* edge_param, int64_t ep_stride,
+                              const float* vminmax, int use_shift, const float* grad_out8, float* grad_y, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DSS2_CHECK_ARG(g && y && edge_param && vminmax && grad_out8 && grad_y, "dss2_pflow_bwd: null argument");
+  DSS2_CHECK_ARG(g->undirected == 1, "dss2_pflow_bwd: needs a graph built from the one-way edge list with undirect=1");
+  if (g->num_nodes == 0) return 0;
+  int grid = (int)max((int64_t)1, min((int64_t)148 * 8, (g->num_nodes + 255) / 256));
+  k_pflow_bwd<<<grid, 256, 0, stream>>>(*g, y, y_stride, edge_param, ep_stride, vminmax, grad_out8, use_shift, grad_y);
   DSS2_LAUNCH_CHECK();
   return 0;
 }

@@ -61,9 +61,10 @@ struct WlsBranch {
   float ll, lt;
 };
 
-WLS_HD void wls_branch_forward(const WlsBranchIn& in, const WlsGrid& g, WlsBranch& b) {
+// `delta` = Th_i - Th_j - shift as the caller formed it (shift = 0 for phase_shift=True, data.py:362-365)
+WLS_HD void wls_branch_forward_delta(const WlsBranchIn& in, const WlsGrid& g, WlsBranch& b, float delta) {
   float vi = in.vi, vj = in.vj;
-  b.delta = in.thi - in.thj;                       // shift ignored: phase_shift=True, data.py:362-363
+  b.delta = delta;
   b.cs = cosf(b.delta);
   b.sn = sinf(b.delta);
   float nvv = (-vi) * vj;                          // "- V_i * V_j" binds as (-V_i) * V_j
@@ -85,6 +86,10 @@ WLS_HD void wls_branch_forward(const WlsBranchIn& in, const WlsGrid& g, WlsBranc
   b.ll = ((1.0f - b.tpos) * fmaxf(b.i_f, b.i_t)) / in.rating;
   b.lt = (b.tpos * fmaxf(b.i_f * g.v_hv, b.i_t * g.v_lv)) / in.rating;
   b.loading = b.ll + b.lt;
+}
+
+WLS_HD void wls_branch_forward(const WlsBranchIn& in, const WlsGrid& g, WlsBranch& b) {
+  wls_branch_forward_delta(in, g, b, in.thi - in.thj);   // shift ignored: phase_shift=True, data.py:362-363
 }
 
 // Adjoint of wls_branch_forward.  Inputs: adjoints of the four flows as seen by the bus-injection and
@@ -141,6 +146,41 @@ WLS_HD void wls_branch_backward(const WlsBranchIn& in, const WlsGrid& g, const W
   dvi += dqt * (c * vj * B2);
   dvj += dqt * (c * (vi * B2 - 2.0f * bsh * vj));
   ddel += dqt * (c * vv * A2);
+}
+
+// Adjoint of get_pflow's eight outputs (data.py:390: loading_lines, loading_trafo, P_from, Q_from, P_to, Q_to, I_from, I_to) w.r.t.
+// V_i, V_j and delta: the same chain as wls_branch_backward with the two loading terms and the two currents fed separately.
+WLS_HD void wls_pflow_backward(const WlsBranchIn& in, const WlsGrid& g, const WlsBranch& b, const float (&go)[8], float& dvi, float& dvj,
+                               float& ddel) {
+  float vi = in.vi, vj = in.vj;
+  float dpf = go[2], dqf = go[3], dpt = go[4], dqt = go[5];
+  dvi = 0.0f;
+  dvj = 0.0f;
+  float dm1 = go[0] * (1.0f - b.tpos) / in.rating;
+  float dm2 = go[1] * b.tpos / in.rating;
+  float w1f = b.i_f > b.i_t ? 1.0f : (b.i_f < b.i_t ? 0.0f : 0.5f);
+  float a = b.i_f * g.v_hv, c2 = b.i_t * g.v_lv;
+  float w2f = a > c2 ? 1.0f : (a < c2 ? 0.0f : 0.5f);
+  float di_f = go[6] + dm1 * w1f + dm2 * w2f * g.v_hv;
+  float di_t = go[7] + dm1 * (1.0f - w1f) + dm2 * (1.0f - w2f) * g.v_lv;
+  if (di_f != 0.0f || di_t != 0.0f) {
+    float dhf = di_f / (((vi * g.v_lv) * g.sqrt3) * b.den);
+    float dht = di_t / ((vj * g.v_lv) * g.sqrt3);
+    if (b.hf != 0.0f) {
+      dpf += dhf * (b.pf / b.hf);
+      dqf += dhf * (b.qf / b.hf);
+    }
+    if (b.ht != 0.0f) {
+      dpt += dht * (b.pt / b.ht);
+      dqt += dht * (b.qt / b.ht);
+    }
+    dvi += -di_f * b.i_f / vi;
+    dvj += -di_t * b.i_t / vj;
+  }
+  float dv2i, dv2j;
+  wls_branch_backward(in, g, b, dpf, dqf, dpt, dqt, 0.0f, 0.0f, dv2i, dv2j, ddel);
+  dvi += dv2i;
+  dvj += dv2j;
 }
 
 // ---- per-bus terms ----

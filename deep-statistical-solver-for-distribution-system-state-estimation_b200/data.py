@@ -100,31 +100,57 @@ def gsp_wls_edge(input, edge_input, output, x_mean, x_std, edge_mean, edge_std, 
     return loss
 
 
+class _PflowFunction(torch.autograd.Function):
+    """get_pflow with its adjoint w.r.t. y (the reference's is plain autograd code, data.py:328-390)."""
+
+    @staticmethod
+    def forward(ctx, y, edge_index, node_param, edge_param, use_shift):
+        lib = _lib.load()
+        out_device = y.device
+        yg, ys = ops.stage_rows(y.detach())
+        npg, nps = ops.stage_rows(node_param)
+        epg, eps = ops.stage_rows(edge_param)
+        ei = edge_index if edge_index.device.type == "cuda" else edge_index.cuda(non_blocking=True)
+        ei = ei.long().contiguous()
+        et = ei.size(1)
+        out8 = torch.empty(8, et, dtype=torch.float32, device=yg.device)
+        with torch.cuda.device(yg.device):
+            vmm = _vminmax(npg, nps, 0, npg.size(0))
+            _lib.check(lib.dss2_pflow_ex(_lib.ptr(ei), et, _lib.ptr(yg), ys, _lib.ptr(epg), eps, _lib.ptr(vmm), int(use_shift), _lib.ptr(out8),
+                                         _lib.stream()), "dss2_pflow")
+        if ctx.needs_input_grad[0]:
+            ctx.saved = (yg, ys, epg, eps, vmm, edge_index, int(use_shift), out_device, et)
+        ctx.set_materialize_grads(False)
+        if out_device.type != "cuda":
+            out8 = out8.to(out_device)
+        return tuple(out8[i] for i in range(8))
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        lib = _lib.load()
+        yg, ys, epg, eps, vmm, edge_index, use_shift, out_device, et = ctx.saved
+        graph = ops.resolve_graph(edge_index, yg.size(0))
+        if graph.c.undirected != 1:
+            raise _lib.Dss2Error("get_pflow backward expects the one-way edge list of the reference's data (from_bus -> to_bus)")
+        g8 = torch.zeros(8, et, dtype=torch.float32, device=yg.device)
+        for i, go in enumerate(gouts):
+            if go is not None:
+                g8[i].copy_(go.to(device=yg.device, dtype=torch.float32))
+        gy = torch.empty(yg.size(0), 2, dtype=torch.float32, device=yg.device)
+        with torch.cuda.device(yg.device):
+            _lib.check(lib.dss2_pflow_bwd(graph.ref, _lib.ptr(yg), ys, _lib.ptr(epg), eps, _lib.ptr(vmm), use_shift, _lib.ptr(g8), _lib.ptr(gy),
+                                          _lib.stream()), "dss2_pflow_bwd")
+        return gy.to(out_device), None, None, None, None
+
+
 def get_pflow(y, edge_index, node_param, edge_param, phase_shift=True):
-    """data.py:328-390.  Returns (loading_lines, loading_trafo, P_from, Q_from, P_to, Q_to, I_from, I_to), each [Et],
-    on the device of `y`.  Forward only (the reference uses it under no_grad for the evaluation metrics,
-    dss2_run.py:193-194; inside the loss its gradient is part of the fused kernel)."""
+    """data.py:328-390.  Returns (loading_lines, loading_trafo, P_from, Q_from, P_to, Q_to, I_from, I_to), each [Et], on the device of
+    `y`, differentiable w.r.t. `y` like the reference's (one fused adjoint kernel; inside `gsp_wls_edge` the gradient is part of the
+    loss kernel instead).  phase_shift=False subtracts the branch's phase shift from the angle difference (data.py:364-365)."""
     ops.require_cuda()
-    if not phase_shift:
-        raise NotImplementedError("get_pflow(phase_shift=False): the reference never takes this branch (data.py:362-365)")
-    if torch.is_grad_enabled() and y.requires_grad:
-        raise _lib.Dss2Error("get_pflow is forward-only; use gsp_wls_edge for a differentiable loss, or call under torch.no_grad()")
-    lib = _lib.load()
-    out_device = y.device
-    yg, ys = ops.stage_rows(y)
-    npg, nps = ops.stage_rows(node_param)
-    epg, eps = ops.stage_rows(edge_param)
-    ei = edge_index if edge_index.device.type == "cuda" else edge_index.cuda(non_blocking=True)
-    ei = ei.long().contiguous()
-    et = ei.size(1)
-    out8 = torch.empty(8, et, dtype=torch.float32, device=yg.device)
-    with torch.cuda.device(yg.device):
-        vmm = _vminmax(npg, nps, 0, npg.size(0))
-        _lib.check(lib.dss2_pflow(_lib.ptr(ei), et, _lib.ptr(yg), ys, _lib.ptr(epg), eps, _lib.ptr(vmm), _lib.ptr(out8), _lib.stream()),
-                   "dss2_pflow")
-    if out_device.type != "cuda":
-        out8 = out8.to(out_device)
-    return tuple(out8[i] for i in range(8))
+    if y.size(1) != 2:
+        raise _lib.Dss2Error("get_pflow expects y = [V pu, theta rad] per bus")
+    return _PflowFunction.apply(y, edge_index, node_param, edge_param, not phase_shift)
 
 
 def gsp_wls(*args, **kwargs):

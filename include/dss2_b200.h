@@ -226,6 +226,13 @@ int dss2_wls_fwd_bwd(const dss2_graph_t* g, const float* x, int64_t x_stride, co
  * out8 [8,Et]: loading_lines, loading_trafo, P_from, Q_from, P_to, Q_to, I_from, I_to. */
 int dss2_pflow(const int64_t* edge_index, int64_t num_edges, const float* y, int64_t y_stride,
                const float* edge_param, int64_t ep_stride, const float* vminmax, float* out8, void* stream);
+/* dss2_pflow_ex: use_shift != 0 evaluates delta = (theta_i - theta_j) - phase_shift (get_pflow(..., phase_shift=False), data.py:364-365).
+ * dss2_pflow_bwd: adjoint of the eight outputs w.r.t. y (the reference's get_pflow is plain autograd code): grad_out8 [8, Et] dense
+ * (zeros for unused outputs), grad_y [Nt, 2] dense; g = the batch structure of the one-way edge list (undirect = 1). */
+int dss2_pflow_ex(const int64_t* edge_index, int64_t num_edges, const float* y, int64_t y_stride, const float* edge_param,
+                  int64_t ep_stride, const float* vminmax, int use_shift, float* out8, void* stream);
+int dss2_pflow_bwd(const dss2_graph_t* g, const float* y, int64_t y_stride, const float* edge_param, int64_t ep_stride,
+                   const float* vminmax, int use_shift, const float* grad_out8, float* grad_y, void* stream);
 
 /* Validation metrics of one batch (SURVEY.md 8f-4, dss2_run.py:183-209) in one kernel: x [Nt,>=11] (column 9 = slack flag),
  * edge_attr [Et,>=13] (columns 6.. = branch parameters), output [Nt,2] = model output (normalised V, raw theta), y [Nt,2] = labels.

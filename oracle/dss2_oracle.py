@@ -405,8 +405,9 @@ def init_gnn_state_dict(model="gcn2", dim_feat=8, dim_dense=32, dim_out=2, num_l
 # --------------------------------------------------------------------------------------------
 
 
-def get_pflow(y, edge_index, node_param, edge_param):
-    """data.py:328-390 with phase_shift=True (the only way it is called: angle shift ignored, :362-363).
+def get_pflow(y, edge_index, node_param, edge_param, phase_shift=True):
+    """data.py:328-390.  phase_shift=True is the only way the script calls it (angle shift ignored, :362-363);
+    phase_shift=False subtracts the branch's phase-shift column from the angle difference (:364-365).
 
     y[Nt,2] = (V pu, theta rad); edge_index one-way [2,Et]; node_param[:,0] = vn_kv;
     edge_param = (G, B, Gs, Bs, closed, phase_shift, imax_or_sn).
@@ -417,6 +418,8 @@ def get_pflow(y, edge_index, node_param, edge_param):
     frm, to = edge_index[0], edge_index[1]
     vi, vj = y[:, 0][frm], y[:, 0][to]                  # :355-358
     delta = y[:, 1][frm] - y[:, 1][to]                  # shift = 0
+    if not phase_shift:
+        delta = delta - edge_param[:, 5].detach()       # :365 torch.tensor(edge_param[:,5]) is a detached copy
     g, b, gs, bs = edge_param[:, 0], edge_param[:, 1], edge_param[:, 2], edge_param[:, 3]
     is_trafo = torch.ceil(edge_param[:, 5].detach())    # :367 (3 on Oberrhein: quirk kept)
     rating = edge_param[:, 6].detach()                  # :368

@@ -87,3 +87,32 @@ extern "C" int wls_host_loss(const float* x, const float* ea, const int64_t* ei,
   }
   return 0;
 }
+
+// get_pflow and its adjoint w.r.t. y through wls_branch_forward_delta / wls_pflow_backward (k_pflow, k_pflow_bwd in csrc/wls.cu).
+extern "C" int wls_host_pflow(const float* y, const float* node_param, int64_t np_stride, const float* edge_param, const int64_t* ei,
+                              int64_t Nt, int64_t Et, int use_shift, const float* gout8, float* out8, float* grad_y) {
+  float vmin = 1e30f, vmax = 0.f;
+  for (int64_t n = 0; n < Nt; ++n) {
+    vmin = fminf(vmin, node_param[n * np_stride]);
+    vmax = fmaxf(vmax, node_param[n * np_stride]);
+  }
+  WlsGrid grid = wls_grid(vmin, vmax);
+  for (int64_t n = 0; n < 2 * Nt; ++n) grad_y[n] = 0.f;
+  for (int64_t e = 0; e < Et; ++e) {
+    int64_t i = ei[e], j = ei[Et + e];
+    const float* row = edge_param + e * 7;
+    WlsBranchIn in{y[2 * i], y[2 * j], y[2 * i + 1], y[2 * j + 1], row[0], row[1], row[2], row[3], row[5], row[6]};
+    WlsBranch b;
+    wls_branch_forward_delta(in, grid, b, use_shift ? (in.thi - in.thj) - in.shift : in.thi - in.thj);
+    const float o[8] = {b.ll, b.lt, b.pf, b.qf, b.pt, b.qt, b.i_f, b.i_t};
+    float go[8];
+    for (int q = 0; q < 8; ++q) {
+      out8[q * Et + e] = o[q];
+      go[q] = gout8[q * Et + e];
+    }
+    float dvi, dvj, ddel;
+    wls_pflow_backward(in, grid, b, go, dvi, dvj, ddel);
+    grad_y[2 * i] += dvi; grad_y[2 * j] += dvj; grad_y[2 * i + 1] += ddel; grad_y[2 * j + 1] -= ddel;
+  }
+  return 0;
+}

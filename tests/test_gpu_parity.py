@@ -245,6 +245,48 @@ def test_get_pflow_vs_oracle_and_pandapower(env):
     assert cpu[0].device.type == "cpu" and torch.equal(cpu[3], got[3].cpu())
 
 
+@pytest.mark.parametrize("phase_shift", [True, False])
+@pytest.mark.parametrize("where", ["cuda", "cpu"])
+def test_get_pflow_is_differentiable_like_the_reference(env, phase_shift, where):
+    """data.py:328-390 is plain autograd code: gradients of any of the eight outputs w.r.t. y, with and without the phase-shift
+    column (data.py:362-365), for CUDA and CPU-tensor callers, against the oracle's autograd (fp64 arbiter)."""
+    z = load_golden("golden_loss_ober_wild.npz")
+    x, ea, ei = torch.from_numpy(z["x"]), torch.from_numpy(z["edge_attr"]), torch.from_numpy(z["edge_index"]).long()
+    nt, et = x.size(0), ea.size(0)
+    gen = torch.Generator().manual_seed(11)
+    y = torch.stack([1.0 + 0.05 * torch.randn(nt, generator=gen), 0.2 * torch.randn(nt, generator=gen)], 1)
+    gout = torch.randn(8, et, generator=gen)
+
+    def oracle(dtype):
+        yt = y.detach().clone().to(dtype).requires_grad_(True)
+        outs = orc.get_pflow(yt, ei, x[:, 8:].to(dtype), ea[:, 6:].to(dtype), phase_shift=phase_shift)
+        sum((o * gout[q].to(dtype)).sum() for q, o in enumerate(outs)).backward()
+        return [o.detach() for o in outs], yt.grad
+
+    o32, g32 = oracle(torch.float32)
+    o64, g64 = oracle(torch.float64)
+    dev = torch.device(where)
+    yt = y.detach().clone().to(dev).requires_grad_(True)
+    outs = env["data"].get_pflow(yt, ei.to(dev), node_param=x[:, 8:].to(dev), edge_param=ea[:, 6:].to(dev), phase_shift=phase_shift)
+    assert all(o.device.type == where for o in outs)
+    sum((o * gout[q].to(dev)).sum() for q, o in enumerate(outs)).backward()
+    for q in range(8):
+        assert_fp32_parity(outs[q].detach().cpu(), o32[q], o64[q], f"pflow[{q}]")
+    assert yt.grad.device.type == where
+    assert_fp32_parity(yt.grad.cpu(), g32, g64, "grad_y")
+    # only some outputs used (the others arrive as None: set_materialize_grads(False))
+    yt2 = y.detach().clone().to(dev).requires_grad_(True)
+    o2 = env["data"].get_pflow(yt2, ei.to(dev), node_param=x[:, 8:].to(dev), edge_param=ea[:, 6:].to(dev), phase_shift=phase_shift)
+    (o2[0] + o2[1]).sum().backward()
+    y64 = y.double().requires_grad_(True)
+    r2 = orc.get_pflow(y64, ei, x[:, 8:].double(), ea[:, 6:].double(), phase_shift=phase_shift)
+    (r2[0] + r2[1]).sum().backward()
+    y32 = y.clone().requires_grad_(True)
+    r3 = orc.get_pflow(y32, ei, x[:, 8:], ea[:, 6:], phase_shift=phase_shift)
+    (r3[0] + r3[1]).sum().backward()
+    assert_fp32_parity(yt2.grad.cpu(), y32.grad, y64.grad, "grad_y (loading only)")
+
+
 # ------------------------------------------------------------------------------------------------ (b) layers
 def _small_batch(env, case="ober_sub", nb=5, seed=7):
     grid = env["synth"].load_grid(case)

@@ -91,3 +91,40 @@ def test_near_solution_and_pflow(host_lib):
     ref64 = orc.get_pflow(state.double(), torch.from_numpy(ei), torch.from_numpy(x[:, 8:]).double(), torch.from_numpy(ea[:, 6:]).double())
     for q in range(8):
         assert_fp32_parity(pf[q], ref[q], ref64[q], f"pflow[{q}]")
+
+
+@pytest.mark.parametrize("phase_shift", [True, False])
+def test_pflow_adjoint_vs_oracle_autograd(host_lib, phase_shift):
+    """get_pflow is plain autograd code in the reference (data.py:328-390): the adjoint of all eight outputs w.r.t. y = (V, theta),
+    `wls_pflow_backward`, against the oracle's autograd; phase_shift=False takes the branch's shift column (data.py:364-365).  The
+    Oberrhein batch has a transformer (trafo_pos = 3 quirk) and both loading columns active."""
+    z = load_golden("golden_loss_ober_wild.npz")
+    x, ea, ei = z["x"], z["edge_attr"], z["edge_index"]
+    nt, et = x.shape[0], ea.shape[0]
+    rng = np.random.default_rng(5)
+    y = np.stack([1.0 + 0.05 * rng.standard_normal(nt), 0.2 * rng.standard_normal(nt)], 1).astype(np.float32)
+    gout = rng.standard_normal((8, et)).astype(np.float32)
+    node_param = np.ascontiguousarray(x[:, 8:], np.float32)
+    edge_param = np.ascontiguousarray(ea[:, 6:], np.float32)
+    if not phase_shift:
+        assert np.abs(edge_param[:, 5]).max() > 0
+    out8 = np.zeros((8, et), np.float32)
+    gy = np.zeros((nt, 2), np.float32)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    eic = np.ascontiguousarray(ei, np.int64)
+    rc = host_lib.wls_host_pflow(p(y), p(node_param), ctypes.c_int64(node_param.shape[1]), p(edge_param), p(eic), ctypes.c_int64(nt),
+                                 ctypes.c_int64(et), ctypes.c_int(0 if phase_shift else 1), p(gout), p(out8), p(gy))
+    assert rc == 0
+
+    def oracle(dtype):
+        yt = torch.from_numpy(y).to(dtype).requires_grad_(True)
+        outs = orc.get_pflow(yt, torch.from_numpy(eic), torch.from_numpy(node_param).to(dtype), torch.from_numpy(edge_param).to(dtype),
+                             phase_shift=phase_shift)
+        sum((o * torch.from_numpy(gout[q]).to(dtype)).sum() for q, o in enumerate(outs)).backward()
+        return [o.detach() for o in outs], yt.grad
+
+    o32, g32 = oracle(torch.float32)
+    o64, g64 = oracle(torch.float64)
+    for q in range(8):
+        assert_fp32_parity(out8[q], o32[q], o64[q], f"pflow[{q}]")
+    assert_fp32_parity(gy, g32, g64, "grad_y")
