@@ -50,6 +50,17 @@ int dss2_tc2_dense_fwd(const dss2_graph_t* g, const float* x, const float* lvl, 
 int dss2_tc2_dense_bgx(const dss2_graph_t* g, const float* grad_y, const uint32_t* act_bits, float p_drop, const float* lvl, const float* w,
                        int cout, int K, float* grad_x, cudaStream_t stream);
 
+// thread-per-row EdgeAggregation kernels (edgeagg_row.cu), selected by the dss2_edgeagg_* entry points in edgeagg.cu
+int dss2_ea_row_fits(const dss2_graph_t* g, int64_t x_stride, int64_t ea_stride, int fe, int bwd);
+int dss2_ea_row_scratch_slot();
+int dss2_ea_row_upload(int slot0, int n, const float* const* w1, const float* const* b1, const float* const* w2, const float* const* b2, int fn,
+                       int fe, cudaStream_t stream);
+int dss2_ea_row_fwd(const dss2_graph_t* g, const float* x, int64_t x_stride, int fn, const float* edge_attr, int64_t ea_stride, int fe, int slot,
+                    float* out, cudaStream_t stream);
+int dss2_ea_row_bwd(const dss2_graph_t* g, const float* x, int64_t x_stride, int fn, const float* edge_attr, int64_t ea_stride, int fe, int slot,
+                    const float* grad_out, const float* skip_grad, int64_t skip_stride, float* grad_x, float* partials, int64_t partial_stride,
+                    cudaStream_t stream);
+
 // large-graph (num_tiles == 0) variants, implemented next to their tiled counterparts
 #define DSS2_NEED_SCRATCH(g, who)                                                                                        \
   DSS2_CHECK_ARG((g)->scratch && (g)->scratch_bytes >= dss2_generic_scratch_bytes((g)->num_nodes),                        \

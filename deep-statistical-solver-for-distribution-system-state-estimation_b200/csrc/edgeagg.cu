@@ -550,6 +550,13 @@ int ea_threads(const char* env, int dflt) {
   return (n == 256 || n == 384 || n == 512) ? n : dflt;
 }
 
+// DSS2_EA_IMPL=warp keeps the round-1 warp-per-row kernels of this file (measured alternative); default = edgeagg_row.cu
+bool ea_use_row(const dss2_graph_t* g, int64_t x_stride, int64_t ea_stride, int fe, int bwd) {
+  const char* v = getenv("DSS2_EA_IMPL");
+  if (v && v[0] == 'w') return false;
+  return dss2_ea_row_fits(g, x_stride, ea_stride, fe, bwd) != 0;
+}
+
 int check_common(const char* who, const dss2_graph_t* g, const float* x, int fn, const float* ea, int fe, const float* w1,
                  const float* b1, const float* w2, const float* b2) {
   DSS2_CHECK_ARG(g && x && ea && w1 && b1 && w2 && b2, "%s: null argument", who);
@@ -588,6 +595,11 @@ extern "C" int dss2_edgeagg_fwd(const dss2_graph_t* g, const float* x, int64_t x
     k_ea_fwd_g<<<ea_gen_grid(g->num_nodes), EA_THREADS, 0, stream>>>(a, P, Q);
     DSS2_LAUNCH_CHECK();
     return 0;
+  }
+  if (ea_use_row(g, x_stride, ea_stride, fe, 0)) {   // weights through the scratch constant-memory slot, then the thread-per-row kernel
+    const int slot = dss2_ea_row_scratch_slot();
+    if (dss2_ea_row_upload(slot, 1, &w1, &b1, &w2, &b2, fn, fe, stream)) return -1;
+    return dss2_ea_row_fwd(g, x, x_stride, fn, edge_attr, ea_stride, fe, slot, out, stream);
   }
   size_t smem = ea_smem(g, 2);
   DSS2_CHECK_ARG(smem <= 113 * 1024, "dss2_edgeagg_fwd: tile needs %zu bytes of shared memory", smem);
@@ -647,6 +659,12 @@ extern "C" int dss2_edgeagg_bwd(const dss2_graph_t* g, const float* x, int64_t x
     DSS2_LAUNCH_CHECK();
     return 0;
   }
+  if (ea_use_row(g, x_stride, ea_stride, fe, 1)) {
+    const int slot = dss2_ea_row_scratch_slot();
+    if (dss2_ea_row_upload(slot, 1, &w1, &b1, &w2, &b2, fn, fe, stream)) return -1;
+    return dss2_ea_row_bwd(g, x, x_stride, fn, edge_attr, ea_stride, fe, slot, grad_out, skip_grad, skip_stride, grad_x, partials, partial_stride,
+                           stream);
+  }
   const int nt = ea_threads("DSS2_EA_BWD_THREADS", EA_BWD_THREADS);
   size_t smem = ea_smem(g, 4);
   size_t red = (size_t)(nt / 32) * (3 * FP + 2 + HID) * HID * 4;
@@ -661,4 +679,44 @@ extern "C" int dss2_edgeagg_bwd(const dss2_graph_t* g, const float* x, int64_t x
 #undef DSS2_EA_BWD
   DSS2_LAUNCH_CHECK();
   return 0;
+}
+
+// Prepared-weights variant (throughput tier): dss2_edgeagg_upload moves the weights of up to 7 EdgeAggregation modules into
+// constant-memory slots once per step; the _slot entry points then run the thread-per-row kernels without touching the weight tensors.
+extern "C" int dss2_edgeagg_slots_ok(const dss2_graph_t* g, int64_t x_stride, int64_t ea_stride, int fe) {
+  if (!g) return 0;
+  return ea_use_row(g, x_stride, ea_stride, fe, 0) && ea_use_row(g, x_stride, ea_stride, fe, 1) ? dss2_ea_row_scratch_slot() : 0;
+}
+
+extern "C" int dss2_edgeagg_upload(int slot0, int n, const float* const* w1, const float* const* b1, const float* const* w2,
+                                   const float* const* b2, int fn, int fe, void* stream_) {
+  DSS2_CHECK_ARG(w1 && b1 && w2 && b2, "dss2_edgeagg_upload: null argument");
+  DSS2_CHECK_ARG(slot0 >= 0 && n >= 1 && slot0 + n <= dss2_ea_row_scratch_slot(), "dss2_edgeagg_upload: slots %d..%d outside 0..%d", slot0,
+                 slot0 + n - 1, dss2_ea_row_scratch_slot() - 1);
+  return dss2_ea_row_upload(slot0, n, w1, b1, w2, b2, fn, fe, (cudaStream_t)stream_);
+}
+
+extern "C" int dss2_edgeagg_fwd_slot(const dss2_graph_t* g, const float* x, int64_t x_stride, int fn, const float* edge_attr, int64_t ea_stride,
+                                     int fe, int slot, float* out, void* stream_) {
+  DSS2_CHECK_ARG(g && x && edge_attr && out, "dss2_edgeagg_fwd_slot: null argument");
+  DSS2_CHECK_ARG(slot >= 0 && slot < dss2_ea_row_scratch_slot(), "dss2_edgeagg_fwd_slot: slot %d", slot);
+  DSS2_CHECK_ARG(fn >= 1 && fn <= FP && fe >= 1, "dss2_edgeagg_fwd_slot: feature counts");
+  if (g->num_nodes == 0) return 0;
+  DSS2_CHECK_ARG(dss2_ea_row_fits(g, x_stride, ea_stride, fe, 0), "dss2_edgeagg_fwd_slot: batch does not fit the thread-per-row kernels "
+                 "(check dss2_edgeagg_slots_ok and use dss2_edgeagg_fwd)");
+  return dss2_ea_row_fwd(g, x, x_stride, fn, edge_attr, ea_stride, fe, slot, out, (cudaStream_t)stream_);
+}
+
+extern "C" int dss2_edgeagg_bwd_slot(const dss2_graph_t* g, const float* x, int64_t x_stride, int fn, const float* edge_attr, int64_t ea_stride,
+                                     int fe, int slot, const float* grad_out, const float* skip_grad, int64_t skip_stride, float* grad_x,
+                                     float* partials, int64_t partial_stride, void* stream_) {
+  DSS2_CHECK_ARG(g && x && edge_attr && grad_out && partials, "dss2_edgeagg_bwd_slot: null argument");
+  DSS2_CHECK_ARG(slot >= 0 && slot < dss2_ea_row_scratch_slot(), "dss2_edgeagg_bwd_slot: slot %d", slot);
+  DSS2_CHECK_ARG(fn >= 1 && fn <= FP && fe >= 1, "dss2_edgeagg_bwd_slot: feature counts");
+  DSS2_CHECK_ARG(partial_stride >= (int64_t)HID * (2 * fn + fe) + HID + HID * HID + HID, "dss2_edgeagg_bwd_slot: partial_stride too small");
+  DSS2_CHECK_ARG(g->undirected == 1, "dss2_edgeagg_bwd_slot: needs the one-way edge list of the reference's data");
+  DSS2_CHECK_ARG(dss2_ea_row_fits(g, x_stride, ea_stride, fe, 1), "dss2_edgeagg_bwd_slot: batch does not fit the thread-per-row kernels "
+                 "(check dss2_edgeagg_slots_ok and use dss2_edgeagg_bwd)");
+  return dss2_ea_row_bwd(g, x, x_stride, fn, edge_attr, ea_stride, fe, slot, grad_out, skip_grad, skip_stride, grad_x, partials, partial_stride,
+                         (cudaStream_t)stream_);
 }

@@ -11,6 +11,7 @@ import torch
 from . import _lib
 from .graph import BatchGraph, graph_for
 
+MAX_EA_SLOTS = 7   # constant-memory slots of the prepared-weights EdgeAggregation path (include/dss2_b200.h)
 HID = _lib.HID
 # which TAG-layer kernels the runner launches (all are CUDA; there is no CPU path):
 #   "ffma": CUDA-core forward and backward (tag.cu)
@@ -124,6 +125,25 @@ class PFNRunner:
         off, _ = self.table[name]
         return ctypes.c_void_p(flat.data_ptr() + 4 * off)
 
+    # ---- EdgeAggregation weights -> constant-memory slots (thread-per-row kernels, csrc/edgeagg_row.cu) ----
+    def _ea_names(self, s):
+        pre = self.spec.prefix_fmt.format(s=s) + "edge_aggr.edge_aggr."
+        return pre + "0.weight", pre + "0.bias", pre + "2.weight", pre + "2.bias"
+
+    def ea_slots(self, graph, x_stride, ea_stride):
+        """True when every EdgeAggregation of the model can run from prepared constant-memory slots (one per sub-net)."""
+        sp = self.spec
+        if sp.L > MAX_EA_SLOTS or os.environ.get("DSS2_EA_IMPL", "row")[:1] == "w":
+            return False
+        return bool(self.lib.dss2_edgeagg_slots_ok(graph.ref, max(x_stride, sp.fn), ea_stride, sp.fe))
+
+    def ea_upload(self, flat):
+        """One layout kernel + one device-to-device copy node for all sub-nets (capturable)."""
+        sp = self.spec
+        arr = ctypes.c_void_p * sp.L
+        cols = [arr(*[self._p(flat, self._ea_names(s)[k]) for s in range(sp.L)]) for k in range(4)]
+        _lib.check(self.lib.dss2_edgeagg_upload(0, sp.L, *cols, sp.fn, sp.fe, _lib.stream()), "dss2_edgeagg_upload")
+
     # ---- forward ----
     def forward(self, graph, x, x_stride, ea, ea_stride, flat, bufs, drop_mode=1, rng_state=None, masks=None):
         """x: tensor whose data_ptr is row 0 / col 0 of the [Nt, fn] input with row stride x_stride.
@@ -132,13 +152,18 @@ class PFNRunner:
         g = graph.ref
         use_tc = TAG_IMPL == "tc" and bool(lib.dss2_tag_fwd_tc_supported(g, sp.K))
         use_tc2 = TAG_IMPL == "tc2" and bool(lib.dss2_tag_tc2_supported(g, sp.K))
+        slots = self.ea_slots(graph, x_stride, ea_stride)
+        if slots:
+            self.ea_upload(flat)
         for s in range(sp.L):
             pre = sp.prefix_fmt.format(s=s)
             xin, xs = (x, x_stride) if s == 0 else (bufs["outs"][s - 1], sp.fn)
-            _lib.check(lib.dss2_edgeagg_fwd(g, _lib.ptr(xin), xs, sp.fn, _lib.ptr(ea), ea_stride, sp.fe,
-                                            self._p(flat, pre + "edge_aggr.edge_aggr.0.weight"), self._p(flat, pre + "edge_aggr.edge_aggr.0.bias"),
-                                            self._p(flat, pre + "edge_aggr.edge_aggr.2.weight"), self._p(flat, pre + "edge_aggr.edge_aggr.2.bias"),
-                                            _lib.ptr(bufs["acts"][s, 0]), st), "dss2_edgeagg_fwd")
+            if slots:
+                _lib.check(lib.dss2_edgeagg_fwd_slot(g, _lib.ptr(xin), xs, sp.fn, _lib.ptr(ea), ea_stride, sp.fe, s, _lib.ptr(bufs["acts"][s, 0]), st),
+                           "dss2_edgeagg_fwd_slot")
+            else:
+                _lib.check(lib.dss2_edgeagg_fwd(g, _lib.ptr(xin), xs, sp.fn, _lib.ptr(ea), ea_stride, sp.fe,
+                                                *[self._p(flat, n) for n in self._ea_names(s)], _lib.ptr(bufs["acts"][s, 0]), st), "dss2_edgeagg_fwd")
             for l in range(sp.n_layers):
                 last = l == sp.n_layers - 1
                 cout = sp.out_dim(s) if last else HID
@@ -156,10 +181,14 @@ class PFNRunner:
         return bufs["outs"][-1]
 
     # ---- backward ----
-    def backward(self, graph, x, x_stride, ea, ea_stride, flat, bufs, grad_out, flat_grad, accumulate=False):
-        """grad_out [Nt, dim_out] dense.  Writes the flat parameter gradient into flat_grad."""
+    def backward(self, graph, x, x_stride, ea, ea_stride, flat, bufs, grad_out, flat_grad, accumulate=False, ea_uploaded=False):
+        """grad_out [Nt, dim_out] dense.  Writes the flat parameter gradient into flat_grad.  ea_uploaded: the constant-memory slots
+        still hold this model's EdgeAggregation weights (the captured step: forward and backward of one step, nothing in between)."""
         sp, lib, st = self.spec, self.lib, _lib.stream()
         g = graph.ref
+        slots = self.ea_slots(graph, x_stride, ea_stride)
+        if slots and not ea_uploaded:
+            self.ea_upload(flat)
         part = bufs["partials"]
         pstride = self.flat_size
 
@@ -194,11 +223,15 @@ class PFNRunner:
             need_gx = s > 0
             gprev = bufs["gsub"][s & 1] if need_gx else None
             skip_grad = g_sub if (sp.skip[s] and need_gx) else None
-            _lib.check(lib.dss2_edgeagg_bwd(g, _lib.ptr(xin), xs, sp.fn, _lib.ptr(ea), ea_stride, sp.fe,
-                                            self._p(flat, pre + "edge_aggr.edge_aggr.0.weight"), self._p(flat, pre + "edge_aggr.edge_aggr.0.bias"),
-                                            self._p(flat, pre + "edge_aggr.edge_aggr.2.weight"), self._p(flat, pre + "edge_aggr.edge_aggr.2.bias"),
-                                            _lib.ptr(gy), _lib.ptr(skip_grad), sp.fn if skip_grad is not None else 0,
-                                            _lib.ptr(gprev), pp(pre + "edge_aggr.edge_aggr.0.weight"), pstride, st), "dss2_edgeagg_bwd")
+            if slots:
+                _lib.check(lib.dss2_edgeagg_bwd_slot(g, _lib.ptr(xin), xs, sp.fn, _lib.ptr(ea), ea_stride, sp.fe, s, _lib.ptr(gy), _lib.ptr(skip_grad),
+                                                     sp.fn if skip_grad is not None else 0, _lib.ptr(gprev), pp(pre + "edge_aggr.edge_aggr.0.weight"),
+                                                     pstride, st), "dss2_edgeagg_bwd_slot")
+            else:
+                _lib.check(lib.dss2_edgeagg_bwd(g, _lib.ptr(xin), xs, sp.fn, _lib.ptr(ea), ea_stride, sp.fe,
+                                                *[self._p(flat, n) for n in self._ea_names(s)],
+                                                _lib.ptr(gy), _lib.ptr(skip_grad), sp.fn if skip_grad is not None else 0,
+                                                _lib.ptr(gprev), pp(pre + "edge_aggr.edge_aggr.0.weight"), pstride, st), "dss2_edgeagg_bwd")
             gy = gprev
         _lib.check(lib.dss2_reduce_partials(_lib.ptr(part), pstride, self.num_partials, self.flat_size, _lib.ptr(flat_grad),
                                             1 if accumulate else 0, st), "dss2_reduce_partials")

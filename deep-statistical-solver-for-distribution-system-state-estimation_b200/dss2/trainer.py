@@ -118,7 +118,7 @@ class GraphedTrainer:
         _lib.check(lib.dss2_wls_fwd_bwd(self.graph.ref, _lib.ptr(b["x"]), 11, _lib.ptr(b["edge_attr"]), 13, _lib.ptr(out),
                                         _lib.ptr(self.stats), *self.coefs, _lib.ptr(b["vminmax"]), 1, _lib.ptr(self.loss), None,
                                         _lib.ptr(self.grad_out), _lib.ptr(self.wls_ws), self.wls_ws.numel(), st), "dss2_wls_fwd_bwd")
-        self.runner.backward(self.graph, b["x"], 11, b["edge_attr"], 13, self.flat, self.bufs, self.grad_out, self.flat_grad)
+        self.runner.backward(self.graph, b["x"], 11, b["edge_attr"], 13, self.flat, self.bufs, self.grad_out, self.flat_grad, ea_uploaded=True)
         if self.world > 1:
             torch.distributed.all_reduce(self.flat_grad, group=self.pg)
         if with_optimizer:

@@ -123,6 +123,21 @@ int dss2_edgeagg_bwd(const dss2_graph_t* g, const float* x, int64_t x_stride, in
                      const float* grad_out, const float* skip_grad, int64_t skip_stride,
                      float* grad_x, float* partials, int64_t partial_stride, void* stream);
 
+/* Prepared-weights variant of (b1) for a captured step: the thread-per-row kernels (csrc/edgeagg_row.cu) read the two Linears from
+ * constant memory.  dss2_edgeagg_upload writes the weights of n modules (host arrays of n device pointers each) into slots
+ * slot0 .. slot0+n-1 (0..6) with one layout kernel and one device-to-device copy node; the _slot entry points then take a slot instead of
+ * the four weight pointers (same contracts as dss2_edgeagg_fwd / dss2_edgeagg_bwd).  dss2_edgeagg_slots_ok != 0 when the batch structure,
+ * strides (<= 16 floats) and fe (<= 6) fit those kernels; otherwise use the pointer API, which picks the kernel itself (and routes through
+ * a scratch slot when it can).  A slot's contents stay valid until the next upload into it. */
+int dss2_edgeagg_slots_ok(const dss2_graph_t* g, int64_t x_stride, int64_t ea_stride, int fe);
+int dss2_edgeagg_upload(int slot0, int n, const float* const* w1, const float* const* b1, const float* const* w2,
+                        const float* const* b2, int fn, int fe, void* stream);
+int dss2_edgeagg_fwd_slot(const dss2_graph_t* g, const float* x, int64_t x_stride, int fn, const float* edge_attr,
+                          int64_t ea_stride, int fe, int slot, float* out, void* stream);
+int dss2_edgeagg_bwd_slot(const dss2_graph_t* g, const float* x, int64_t x_stride, int fn, const float* edge_attr,
+                          int64_t ea_stride, int fe, int slot, const float* grad_out, const float* skip_grad,
+                          int64_t skip_stride, float* grad_x, float* partials, int64_t partial_stride, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * (b2) TAGConv(32 -> cout, K) [+ Dropout + ReLU] [+ residual].  Replaces PyG TAGConv.forward with
  * gcn_norm(add_self_loops=False) and the inline Dropout/ReLU of networks.py:268-269 (+ autograd):

@@ -372,14 +372,25 @@ def _kernel_gates(bufs, n_sub, n_hidden, nt):
     return [[((bits[s_, l_].unsqueeze(1) >> shifts) & 1).to(torch.float32) for l_ in range(n_hidden)] for s_ in range(n_sub)]
 
 
-def assert_gradients_vs_oracle(what, ours, golden_grads, kind, ctor, sd, xc, eac, eic, masks, st, go, bufs, noise_mult=4.0, edge_orders=0):
+def assert_gradients_vs_oracle(what, ours, golden_grads, kind, ctor, sd, xc, eac, eic, masks, st, go, bufs, noise_mult=4.0, edge_orders=2,
+                               out_ours=None):
     """Parameter gradients against the ORACLE (never against another kernel of this repo).
 
     relu' is discontinuous: a pre-activation that is +-1e-7 in one fp32 implementation and on the other side of 0 in another changes
     the gradient legitimately.  So the pass pattern our kernels recorded (sign words) is compared with the fp64 oracle's first.  No
     difference: the gradients must match the reference run's (golden file) under the usual criterion.  A difference: every differing
     entry must be a genuine tie (|fp64 pre-activation| <= 1e-6 of that layer's largest), and the gradients must match the oracle
-    evaluated WITH OUR pass pattern (fp32 run = reference value, fp64 run = arbiter).  The tie case is written to the parity log."""
+    evaluated WITH OUR pass pattern (fp32 run = reference value, fp64 run = arbiter).  The tie case is written to the parity log.
+
+    edge_orders = 2 by default: the reference's fp32 noise on a tensor is the worst of three equally valid fp32 evaluations (recorded run +
+    two edge orders).  One draw is a weak yardstick for entries that ARE rounding noise - e.g. the last layer's bias gradient for theta,
+    a column sum of the loss gradient in which every branch adds +d and -d: two independent roundings are more than 4x apart 15 % of the
+    time (ratio of two Gaussians), so a single-draw criterion flips on any change of summation order anywhere upstream.
+
+    out_ours (WLS-loss cases): that theta / V column sum IS the last layer's bias gradient, and it is ill conditioned w.r.t. the model
+    output (1e-7 on `out` moves it by 1e-5 of its scale) - so, like the GAT / GINE tests, it is checked where it is produced: against the
+    oracle's loss gradient evaluated AT the output our kernels delivered (that output itself is held to the strict criterion by the
+    caller).  Every other gradient is compared end to end."""
     n_sub = ctor.get("L", 1) if kind in ("PFN", "SkipPFN") else 1
     n_hidden = ctor["n_gnn_layers"] - 1
     nt = xc.size(0)
@@ -406,8 +417,21 @@ def assert_gradients_vs_oracle(what, ours, golden_grads, kind, ctor, sd, xc, eac
         pb = permute_edges({"edge_index": eic, "edge_attr": eac}, 100 + o_)
         refs.append(_oracle_model(kind, ctor, sd, xc, pb["edge_attr"], pb["edge_index"], masks, st, go, torch.float32,
                                   gates=gates if ties else None)[2])
+    last_bias = None
+    if out_ours is not None and ctor["dim_out"] == 2:
+        last_bias = (f"mpns.{n_sub - 1}." if kind in ("PFN", "SkipPFN") else "") + f"convs.{ctor['n_gnn_layers'] - 1}.bias"
+        assert last_bias in ours
+
+        def colsum(dtype):
+            o = out_ours.detach().cpu().to(dtype).clone().requires_grad_(True)
+            orc.wls_loss(xc.to(dtype), eac.to(dtype), o, *[t.to(dtype) for t in st], eic, REG_COEFS).backward()
+            return o.grad.sum(0)
+
+        assert_fp32_parity(ours[last_bias], colsum(torch.float32), colsum(torch.float64),
+                           f"{last_bias} ({what}; = column sums of the loss gradient at the delivered output)", noise_mult=noise_mult)
     for name, g in ours.items():
-        assert_fp32_parity(g, [r[name] for r in refs], ref64[name], f"{name} ({what})", noise_mult=noise_mult)
+        if name != last_bias:
+            assert_fp32_parity(g, [r[name] for r in refs], ref64[name], f"{name} ({what})", noise_mult=noise_mult)
 
 
 @pytest.mark.parametrize("tag", ["skippfn_cigre", "pfn_small_cigre", "mpn_cigre", "skipmpn_cigre", "skippfn_ober"])
@@ -448,7 +472,11 @@ def test_model_matches_reference_run(env, tag, where):
     for name, p in model.named_parameters():
         assert p.grad is not None and p.grad.device.type == where, name
         ours[name] = p.grad
-    assert_gradients_vs_oracle(f"{tag}/{where}", ours, g32, kind, ctor, sd, x.cpu(), ea.cpu(), ei.cpu(), masks, st, go, runner.last_bufs)
+    # edge_orders: the column sum of the loss gradient w.r.t. theta (= the last layer's bias gradient) is a near-total cancellation
+    # (every branch adds +d and -d), so 1e-7 on `out` moves it by 1e-5 of the tensor's scale: the reference's fp32 noise on it is taken
+    # over three equally valid fp32 evaluations (recorded run + two edge orders), as in the trainer-step tests
+    assert_gradients_vs_oracle(f"{tag}/{where}", ours, g32, kind, ctor, sd, x.cpu(), ea.cpu(), ei.cpu(), masks, st, go, runner.last_bufs,
+                               edge_orders=2, out_ours=out_before)
 
 
 def test_models_survive_deepcopy_and_pickle_after_a_forward(env, tmp_path):
@@ -563,7 +591,7 @@ def test_oberrhein_batch_4096_full_parity_vs_fp64_oracle(env):
     assert_fp32_parity(loss_gpu, l32, l64, "loss (B=4096)")
     ours = {name: flat_grad[off:off + n].reshape(sd0[name].shape) for name, (off, n) in tr.runner.table.items()}
     assert_gradients_vs_oracle("ober B=4096", ours, g32, "SkipPFN", ctor, sd0, batch["x"], batch["edge_attr"], batch["edge_index"], None, st,
-                               None, tr.bufs)
+                               None, tr.bufs, edge_orders=0, out_ours=out_gpu)
 
 
 def test_oberrhein_batch_4096_properties(env):
@@ -731,7 +759,7 @@ def test_tag_fwd_tensor_core_matches_cuda_core_kernel(env, case, nb, cout, act, 
             assert float(y_ref[rows].abs().min(dim=1).values.max()) < 1e-4
 
 
-def _tie_aware_model_check(env, tag, impl, noise_mult=4.0, large_graph=False, edge_orders=0):
+def _tie_aware_model_check(env, tag, impl, noise_mult=4.0, large_graph=False, edge_orders=2):
     """Whole model through the runner with TAG kernels `impl` against the reference run (same weights, same dropout masks): output
     and loss by the fp64-arbiter criterion, parameter gradients by `assert_gradients_vs_oracle` (reference run, or - at a ReLU tie -
     the oracle under the kernel's own pass pattern; never another kernel of this repo)."""
@@ -773,7 +801,8 @@ def _tie_aware_model_check(env, tag, impl, noise_mult=4.0, large_graph=False, ed
         runner.backward(graph, x, 11, ea, 13, flat, bufs, g_out, fg)
         ours = {name: fg[off:off + n].reshape(sd[name].shape) for name, (off, n) in runner.table.items()}
         assert_gradients_vs_oracle(f"{tag}/{impl}", ours, grads, kind, ctor, sd, x.cpu(), ea.cpu(), ei.cpu(), masks, st,
-                                   torch.from_numpy(z["grad_out"]), bufs, noise_mult=noise_mult, edge_orders=edge_orders)
+                                   torch.from_numpy(z["grad_out"]), bufs, noise_mult=noise_mult, edge_orders=edge_orders,
+                                   out_ours=out if ctor["dim_out"] == 2 else None)
     finally:
         ops.TAG_IMPL = saved_impl
         os.environ.pop("DSS2_DENSE_TC", None)
@@ -938,7 +967,7 @@ def test_large_graph_path_models_match_reference_run(env, tiny_tiles, tag):
     # large-graph kernels' summation order lands one weight gradient at 4.02x that noise (1.1e-5 of the scale), measured identically
     # with the exact fp32 weight-gradient pass and the tcgen05 one, i.e. inherited rounding of the inputs, not a kernel defect.
     # "cuda-core" = the large-graph path with DSS2_DENSE_TC=0 (k_dense_tag), "tc-dense" = its default (tcgen05 transform on the hop levels)
-    _tie_aware_model_check(env, tag, "tc-dense", large_graph=True, edge_orders=2 if tag == "pfn_small_cigre" else 0)
+    _tie_aware_model_check(env, tag, "tc-dense", large_graph=True)
 
 
 @pytest.mark.parametrize("tag", ["skippfn_cigre", "skippfn_ober"])
@@ -1253,8 +1282,11 @@ def test_dataset_builder_on_the_device_vs_reference_golden(env):
     assert np.array_equal(st.y.cpu().numpy()[:n], gd["y"])
     assert np.array_equal(x[:n, 8:], gd["x"][:, 8:]) and np.array_equal(ea[:e, 6:], gd["edge_attr"][:, 6:])       # raw parameter columns
     assert np.array_equal(x[:n, :8] == 0, gd["x"][:, :8] == 0) and np.array_equal(ea[:e, :6] == 0, gd["edge_attr"][:, :6] == 0)
-    for ours, ref in ((st.x_mean, gd["x_mean"]), (st.x_std, gd["x_std"]), (st.edge_mean, gd["edge_mean"]), (st.edge_std, gd["edge_std"])):
-        assert np.allclose(ours.cpu().numpy(), ref, rtol=2e-6, atol=0), (ours, ref)
+    # statistics: fp32 sums in another order (torch's CUDA reduction vs its CPU one).  A mean of signed values is a cancelling sum,
+    # so its error is measured against the column's spread (what the z-score divides by), not against the mean itself.
+    for mean, std, rmean, rstd in ((st.x_mean, st.x_std, gd["x_mean"], gd["x_std"]), (st.edge_mean, st.edge_std, gd["edge_mean"], gd["edge_std"])):
+        assert np.allclose(std.cpu().numpy(), rstd, rtol=2e-6, atol=0), (std, rstd)
+        assert np.all(np.abs(mean.cpu().numpy() - rmean) <= 2e-6 * np.maximum(np.abs(rmean), rstd)), (mean, rmean)
     assert np.allclose(x[:n, :8], gd["x"][:, :8], rtol=2e-5, atol=2e-6) and np.allclose(ea[:e, :6], gd["edge_attr"][:, :6], rtol=2e-5, atol=2e-6)
 
 
