@@ -341,18 +341,16 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) k_ea_row_fwd(EaRowArgs a) {
 constexpr int NHALF = HID / 2;   // hidden units per thread
 constexpr int BWD_THREADS = 512;
 constexpr int BWD_WARPS = BWD_THREADS / 32;
-constexpr int RED_SLOTS = 17;    // 8 packed accumulators + 1 scalar per lane and warp
-// phase C roles (warps): [0,3) W2 rows 0-15 + b2, [3,6) W2 rows 16-31, [6,10) first Linear node blocks + b1, [10,16) its edge block
-__device__ __host__ constexpr int role_first(int r) { return r == 0 ? 0 : (r == 1 ? 3 : (r == 2 ? 6 : (r == 3 ? 10 : 16))); }
-
+constexpr int RED_SLOTS = 18;    // 8 packed accumulators + 1 packed scalar per lane and warp
 struct BwdBufs {
   float *Pb, *Qb, *Gb, *Sb, *GO;   // [TR][32] swizzled: P -> grad_P, Q -> grad_Q, grad_S, S, upstream gradient
   uint32_t* gate;                  // [Z] ReLU gates of the in-edges: bit h = pre-activation of hidden unit h is positive
+  uint32_t* zrow;                  // [Z] destination row (tile-local) of every CSR entry
   float* gxp;                      // [TR][8] grad_x share of the upper half
 };
 
 __host__ __device__ inline size_t bwd_smem_bytes(int TR, int ER, int Z, int xs, int eas) {
-  size_t b = 1024 + 5 * (size_t)TR * HID * 4 + (size_t)round16u((uint32_t)(Z + 8) * 4u) + (size_t)TR * FP * 4 + 2 * (size_t)stage_layout(TR, ER, Z, xs, eas).bytes + 64;
+  size_t b = 1024 + 5 * (size_t)TR * HID * 4 + 2 * (size_t)round16u((uint32_t)(Z + 8) * 4u) + (size_t)TR * FP * 4 + 2 * (size_t)stage_layout(TR, ER, Z, xs, eas).bytes + 64;
   const size_t red = 1024 + (size_t)BWD_WARPS * RED_SLOTS * HID * 4;
   return b > red ? b : red;
 }
@@ -462,6 +460,7 @@ __device__ __forceinline__ void bwd_phase_b(const EaRowArgs& a, const TileView& 
       gQ[2 * kk + 1] = add2(gQ[2 * kk + 1], make_float2(t1.x > 0.0f ? gc.z : 0.0f, t1.y > 0.0f ? gc.w : 0.0f));
     }
     reinterpret_cast<unsigned short*>(b.gate)[2 * z + (H0 ? 1 : 0)] = (unsigned short)gate;
+    if (H0 == 0) b.zrow[z] = (uint32_t)row;
   }
   // grad_x share of this half: sum_h W1a[h][i] gP[h] + W1b[h][i] gQ[h], pairs of hidden units in the two lanes
   if (want_gx) {
@@ -496,7 +495,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_ea_row_bwd(EaRowArgs a, cons
   b.Gb = reinterpret_cast<float*>(base + 3 * BUF);
   b.Sb = reinterpret_cast<float*>(base + 4 * BUF);
   b.gate = reinterpret_cast<uint32_t*>(base + 5 * BUF);
-  b.gxp = reinterpret_cast<float*>(base + 5 * BUF + (size_t)round16u((uint32_t)(Z + 8) * 4u));
+  b.zrow = reinterpret_cast<uint32_t*>(base + 5 * BUF + (size_t)round16u((uint32_t)(Z + 8) * 4u));
+  b.gxp = reinterpret_cast<float*>(base + 5 * BUF + 2 * (size_t)round16u((uint32_t)(Z + 8) * 4u));
   char* stage0 = reinterpret_cast<char*>(b.gxp) + (size_t)TR * FP * 4;
   uint64_t* bar = reinterpret_cast<uint64_t*>(stage0 + 2 * (size_t)L.bytes);   // [0], [1]: input stages, [2]: upstream gradient tile
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, ntiles = g.num_tiles, stride = gridDim.x;
@@ -505,11 +505,13 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_ea_row_bwd(EaRowArgs a, cons
   const bool want_gx = a.gx != nullptr;
   const uint32_t go_bytes = (uint32_t)BUF;
 
-  // phase C state: 8 packed accumulators + 1 scalar, meaning by role
-  const int role = warp < role_first(1) ? 0 : (warp < role_first(2) ? 1 : (warp < role_first(3) ? 2 : 3));
-  const int slice = warp - role_first(role), nslice = role_first(role + 1) - role_first(role);
-  float2 acc[8];
-  float accs = 0.0f;
+  // phase C state: 8 packed accumulators + 1 packed scalar, meaning by role.  A warp handles TWO rows (or CSR entries) per
+  // instruction: lanes 0-15 one, lanes 16-31 the other, so every role instruction of phase C covers two rows.
+  //   warps 0-7  : W2 rows 8q .. 8q+7 (q = warp >> 1), lane = (block of 4 output rows, block of 4 hidden units), row pairs j = warp & 1 mod 2
+  //   warps 8-9  : first Linear, x_dst block + b1, lane = pair of hidden units          warps 10-11: x_src block + b2 (lane = pair of outputs)
+  //   warps 12-15: first Linear, edge block: gated grad_S of every CSR entry times its attributes, lane = pair of hidden units
+  const int rsel = lane >> 4, l16 = lane & 15;
+  float2 acc[8], accp = make_float2(0.0f, 0.0f);
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = make_float2(0.0f, 0.0f);
 
@@ -594,50 +596,46 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_ea_row_bwd(EaRowArgs a, cons
           if (i < fn) a.gx[n * fn + i] = o[i];
       }
     }
-    // ---- phase C: weight gradients, roles over warps, rows sliced inside a role
-    if (role <= 1) {
-      // W2 rows 16 role .. +16: lane = (block of 4 output rows, block of 4 hidden units); role 0 also b2 (lane = output unit)
-      const int ob = lane >> 3, hb = lane & 7;
-      for (int rr = slice; rr < nT; rr += nslice) {
-        const float4 go = lds4(b.GO + swz(rr, 4 * role + ob)), s4 = lds4(b.Sb + swz(rr, hb));
+    // ---- phase C: weight gradients (reductions over the tile's rows), roles over warps, two rows per instruction
+    if (warp < 8) {
+      const int q = warp >> 1, ob = l16 >> 3, hb = l16 & 7;
+      for (int rr = 2 * (warp & 1) + rsel; rr < nT; rr += 4) {
+        const float4 go = lds4(b.GO + swz(rr, 2 * q + ob)), s4 = lds4(b.Sb + swz(rr, hb));
         const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
 #pragma unroll
         for (int hh = 0; hh < 4; ++hh) {
           fma2(acc[hh], make_float2(go.x, go.y), sv[hh]);
           fma2(acc[4 + hh], make_float2(go.z, go.w), sv[hh]);
         }
-        if (role == 0) {
-          const float deg = (float)(v.rowptr[rr + 1] - v.rowptr[rr]);
-          accs = fmaf(deg, b.GO[rr * HID + (((lane >> 2) ^ (rr & 7)) << 2) + (lane & 3)], accs);
-        }
       }
-    } else if (role == 2) {
-      // first Linear, x_dst / x_src blocks and b1: lane = hidden unit
-      for (int rr = slice; rr < nT; rr += nslice) {
-        const int mine = rr * HID + (((lane >> 2) ^ (rr & 7)) << 2) + (lane & 3);
-        const float gp = b.Pb[mine], gq = b.Qb[mine];
+    } else if (warp < 12) {
+      const bool src_blk = warp >= 10;
+      const float* G = src_blk ? b.Qb : b.Pb;
+      for (int rr = 2 * (warp & 1) + rsel; rr < nT; rr += 4) {
+        const int off = rr * HID + (((l16 >> 1) ^ (rr & 7)) << 2) + ((l16 & 1) << 1);   // elements 2 l16, 2 l16 + 1 of a swizzled row
+        const float2 gpair = *reinterpret_cast<const float2*>(G + off);
         float xv[FP];
         load_x(v, rr, a.xs, fn, xv);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          fma2(acc[i], make_float2(xv[2 * i], xv[2 * i + 1]), gp);
-          fma2(acc[4 + i], make_float2(xv[2 * i], xv[2 * i + 1]), gq);
+        for (int i = 0; i < FP; ++i) fma2(acc[i], gpair, xv[i]);
+        if (src_blk) {   // b2[o] += deg * g[o]
+          const float deg = (float)(v.rowptr[rr + 1] - v.rowptr[rr]);
+          fma2(accp, *reinterpret_cast<const float2*>(b.GO + off), deg);
+        } else {         // b1[h] += grad_P[h]
+          accp = add2(accp, gpair);
         }
-        accs += gp;
       }
     } else {
-      // first Linear, edge block: lane = hidden unit, gated grad_S of every in-edge times its attributes
-      for (int rr = slice; rr < nT; rr += nslice) {
-        const int beg = v.rowptr[rr] - v.z0, end = v.rowptr[rr + 1] - v.z0;
-        const float gs = b.Gb[rr * HID + (((lane >> 2) ^ (rr & 7)) << 2) + (lane & 3)];
-        for (int z = beg; z < end; ++z) {
-          float av[FE];
-          load_attr(v, v.eid[z], a.eas, fe, av);
-          const float ge = ((b.gate[z] >> lane) & 1u) ? gs : 0.0f;
-          fma2(acc[0], make_float2(av[0], av[1]), ge);
-          fma2(acc[1], make_float2(av[2], av[3]), ge);
-          fma2(acc[2], make_float2(av[4], av[5]), ge);
-        }
+      const int nZ = v.rowptr[nT] - v.z0;
+      for (int z = 2 * (warp & 3) + rsel; z < nZ; z += 8) {
+        const int rr = (int)b.zrow[z];
+        const uint32_t id = v.eid[z], gate = b.gate[z] >> (2 * l16);
+        const float2 gs = *reinterpret_cast<const float2*>(b.Gb + rr * HID + (((l16 >> 1) ^ (rr & 7)) << 2) + ((l16 & 1) << 1));
+        const float2 ge = make_float2((gate & 1u) ? gs.x : 0.0f, (gate & 2u) ? gs.y : 0.0f);
+        float av[FE];
+        load_attr(v, id, a.eas, fe, av);
+#pragma unroll
+        for (int i = 0; i < FE; ++i) fma2(acc[i], ge, av[i]);
       }
     }
     __syncthreads();
@@ -647,7 +645,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_ea_row_bwd(EaRowArgs a, cons
     }
   }
 
-  // per-CTA partial: the warps' accumulators through shared memory, summed per role in warp order
+  // per-CTA partial: the warps' accumulators through shared memory, every entry summed over its role's warps and both half warps
   __syncthreads();
   float* red = reinterpret_cast<float*>(base);   // [BWD_WARPS][RED_SLOTS][32]
   {
@@ -657,39 +655,42 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_ea_row_bwd(EaRowArgs a, cons
       mine[(2 * i) * HID + lane] = acc[i].x;
       mine[(2 * i + 1) * HID + lane] = acc[i].y;
     }
-    mine[16 * HID + lane] = accs;
+    mine[16 * HID + lane] = accp.x;
+    mine[17 * HID + lane] = accp.y;
   }
   __syncthreads();
   float* part = a.partials + (size_t)blockIdx.x * a.partial_stride;
   const int n_w1 = HID * ld, off_b1 = n_w1, off_w2 = n_w1 + HID, off_b2 = off_w2 + HID * HID, total = off_b2 + HID;
   for (int i = tid; i < total; i += BWD_THREADS) {
-    int rl, slot, ln;
+    int w0, nw, slot, ln;   // warps w0 .. w0+nw-1, lanes ln and ln + 16
     if (i < n_w1) {
       const int h = i / ld, c = i - h * ld;
-      ln = h;
-      if (c < 2 * fn) {
-        rl = 2;
-        slot = c < fn ? c : FP + (c - fn);
+      ln = h >> 1;
+      if (c < fn) {
+        w0 = 8, nw = 2, slot = 2 * c + (h & 1);
+      } else if (c < 2 * fn) {
+        w0 = 10, nw = 2, slot = 2 * (c - fn) + (h & 1);
       } else {
-        rl = 3;
-        slot = c - 2 * fn;
+        w0 = 12, nw = 4, slot = 2 * (c - 2 * fn) + (h & 1);
       }
     } else if (i < off_w2) {
-      rl = 2;
-      slot = 16;
-      ln = i - off_b1;
+      const int h = i - off_b1;
+      w0 = 8, nw = 2, slot = 16 + (h & 1), ln = h >> 1;
     } else if (i < off_b2) {
       const int o = (i - off_w2) / HID, h = (i - off_w2) - o * HID, oo = o & 3;
-      rl = o >> 4;
-      ln = ((o & 15) >> 2) * 8 + (h >> 2);
+      w0 = 2 * (o >> 3), nw = 2;
+      ln = (((o & 7) >> 2) << 3) + (h >> 2);
       slot = ((oo >> 1) * 4 + (h & 3)) * 2 + (oo & 1);
     } else {
-      rl = 0;
-      slot = 16;
-      ln = i - off_b2;
+      const int o = i - off_b2;
+      w0 = 10, nw = 2, slot = 16 + (o & 1), ln = o >> 1;
     }
     float sum = 0.0f;
-    for (int w = role_first(rl); w < role_first(rl + 1); ++w) sum += red[((size_t)w * RED_SLOTS + slot) * HID + ln];
+    for (int w = w0; w < w0 + nw; ++w) {
+      const float* r = red + ((size_t)w * RED_SLOTS + slot) * HID;
+      sum += r[ln];
+      sum += r[ln + 16];
+    }
     part[i] = sum;
   }
 }
