@@ -88,13 +88,37 @@ def _masked_zscore(t, num_feat):
     return out, mean, std
 
 
+def _build_on_device(nodes, ce, labels, noise_param, meas_v, meas_pflow, zn, ze, device):
+    """The CUDA builder (csrc/dataset.cu): one launch sequence over all scenarios; no host fallback."""
+    import ctypes
+    from . import _lib
+    lib = _lib.load()
+    S, N, E = nodes.shape[0], nodes.shape[1], ce.shape[1]
+    mv = torch.zeros(N, dtype=torch.uint8, device=device)
+    mv[torch.as_tensor(np.asarray(meas_v), dtype=torch.long, device=device)] = 1
+    mp = torch.zeros(max(E, 1), dtype=torch.uint8, device=device)
+    mp[torch.as_tensor(np.asarray(meas_pflow), dtype=torch.long, device=device)] = 1
+    x = torch.empty(S * N, 11, dtype=torch.float32, device=device)
+    ea = torch.empty(S * E, 13, dtype=torch.float32, device=device)
+    stats = torch.empty(28, dtype=torch.float32, device=device)
+    ws = torch.empty(lib.dss2_build_scenarios_workspace_bytes(), dtype=torch.uint8, device=device)
+    npar = (ctypes.c_double * 6)(*[float(v) for v in noise_param])
+    nodes, ce11, zn, ze = nodes.contiguous(), ce[:, :, :11].contiguous(), zn.contiguous(), ze.contiguous()
+    with torch.cuda.device(x.device):
+        _lib.check(lib.dss2_build_scenarios(_lib.ptr(nodes), _lib.ptr(ce11), _lib.ptr(zn), _lib.ptr(ze), _lib.ptr(mv), _lib.ptr(mp), npar, S, N, E,
+                                            _lib.ptr(x), _lib.ptr(ea), _lib.ptr(stats), _lib.ptr(ws), ws.numel(), _lib.stream()), "dss2_build_scenarios")
+    return x, ea, stats[0:8], stats[14:22], stats[8:14], stats[22:28]
+
+
 def build_scenario_store(nodes, edges, labels, noise_param, meas_v, meas_pflow, noise_nodes, noise_edges,
-                         num_nfeat=8, num_efeat=6, device="cpu"):
+                         num_nfeat=8, num_efeat=6, device="cpu", impl=None):
     """nodes[S,N,7] (NODE_COLS), edges[S,E_all,>=11] (EDGE_COLS first), labels[S,N,2]: float64 arrays
     shaped like the reference pickles; noise_param: the 6 NOISE_COLS values; meas_v / meas_pflow:
     measured bus ids / measured closed-edge positions (dss2_run.py:48-53); noise_nodes[S,N,4],
     noise_edges[S,E,2]: standard-normal draws (float64).  All scenarios must share one switching
-    state (true for every grid of the reference)."""
+    state (true for every grid of the reference).  On a CUDA device the hand-written builder kernels run
+    (impl="kernel", csrc/dataset.cu); impl="torch" keeps the tensor-op restatement below (the CPU path, bit-exact
+    with the reference's np.random stream, and the measured alternative on the device)."""
     f64 = torch.float64
     nodes = torch.as_tensor(nodes, dtype=f64, device=device)
     edges = torch.as_tensor(edges, dtype=f64, device=device)
@@ -109,6 +133,19 @@ def build_scenario_store(nodes, edges, labels, noise_param, meas_v, meas_pflow, 
         raise ValueError("build_scenario_store: scenarios with different switching states are not supported")
     ce = edges[:, closed, :]                                   # data.py:144
     E = ce.shape[1]
+    if impl is None:
+        impl = "kernel" if torch.device(device).type == "cuda" else "torch"
+    if impl == "kernel":
+        if num_nfeat != 8 or num_efeat != 6:
+            raise ValueError("build_scenario_store(impl='kernel'): the reference's 8 node / 6 edge feature columns")
+        x_set, ea_set, x_mean, x_std, e_mean, e_std = _build_on_device(nodes, ce, labels, noise_param, meas_v, meas_pflow, zn, ze, device)
+        ei_local = ce[0, :, 0:2].to(torch.long).t().contiguous()
+        return ScenarioStore(
+            x=x_set, edge_attr=ea_set, y=labels.to(torch.float32).reshape(S * N, 2).contiguous(),
+            edge_index=ei_local.repeat(1, S).contiguous(),
+            node_off=torch.arange(S + 1, dtype=torch.long, device=device) * N,
+            edge_off=torch.arange(S + 1, dtype=torch.long, device=device) * E,
+            x_mean=x_mean.clone(), x_std=x_std.clone(), edge_mean=e_mean.clone(), edge_std=e_std.clone(), max_nodes=N, max_edges=E)
 
     # ---- buses (data.py:121-141) ----
     slack = nodes[:, :, 1:2]

@@ -249,6 +249,19 @@ int dss2_pflow_ex(const int64_t* edge_index, int64_t num_edges, const float* y, 
 int dss2_pflow_bwd(const dss2_graph_t* g, const float* y, int64_t y_stride, const float* edge_param, int64_t ep_stride,
                    const float* vminmax, int use_shift, const float* grad_out8, float* grad_y, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * (f-3) Dataset builder.  Replaces the feature engineering of data_from_pickles (data.py:96-206) for S scenarios of one grid:
+ * nodes [S,N,7] f64 (vn_kv, bool_slack, bool_zero_inj, vm_pu, va_rad, p_mw, q_mvar), closed_edges [S,E,11] f64 (the closed branches:
+ * from_bus, to_bus, G, B, Gs, Bs, closed line, phase shift, imax or sn, p_from_mw, q_from_mvar), noise_nodes [S,N,4] / noise_edges [S,E,2]
+ * f64 standard-normal draws (np.random.normal(0, s) = s * draw: a caller can replay the reference's stream), meas_v_mask [N] / meas_pflow_mask
+ * [E] u8 (dss2_run.py:48-53), noise_param6 = HOST array (p_noise, v_noise, i_noise, pm_noise, sgen_noise, zero_inj_coef).
+ * Out: x [S*N,11], edge_attr [S*E,13] with the first 8 / 6 columns z-scored over their non-zero entries (data.py:179-190), and
+ * stats28 = x_mean[8], edge_mean[6], x_std[8], edge_std[6].  Five launches; deterministic (fixed-order float64 reductions). */
+size_t dss2_build_scenarios_workspace_bytes(void);
+int dss2_build_scenarios(const double* nodes, const double* closed_edges, const double* noise_nodes, const double* noise_edges,
+                         const uint8_t* meas_v_mask, const uint8_t* meas_pflow_mask, const double* noise_param6, int64_t S, int N,
+                         int E, float* x, float* edge_attr, float* stats28, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Validation metrics of one batch (SURVEY.md 8f-4, dss2_run.py:183-209) in one kernel: x [Nt,>=11] (column 9 = slack flag),
  * edge_attr [Et,>=13] (columns 6.. = branch parameters), output [Nt,2] = model output (normalised V, raw theta), y [Nt,2] = labels.
  * sums19 (device, fp64): [0..3] sum (dV)^2, |dV|, (dth)^2, |dth| with V = out0*x_std0 + x_mean0 and th = out1*(1-slack);

@@ -1262,8 +1262,10 @@ def test_gnn_dsse_matches_reference_run(env, tag, where):
 
 
 # ------------------------------------------------------------------------------------------------ dataset builder on the device (scope row 8f-3)
-def test_dataset_builder_on_the_device_vs_reference_golden(env):
-    """build_scenario_store(device='cuda') on the reference's own CIGRE-14 scenarios and its np.random noise stream against the golden
+@pytest.mark.parametrize("impl", ["kernel", "torch"])
+def test_dataset_builder_on_the_device_vs_reference_golden(env, impl):
+    """impl='kernel': the hand-written builder (csrc/dataset.cu, the default on a CUDA device); impl='torch': the tensor-op restatement.
+    build_scenario_store(device='cuda') on the reference's own CIGRE-14 scenarios and its np.random noise stream against the golden
     the reference's data_from_pickles produced (golden_dataset_cigre14.npz; the CPU build is bit-exact with it, test_host_cpu).  On the
     device the element-wise pipeline (noise injection in fp64, weights 1/max(|sigma|,eps)^2 with the >= 1e12 cut, interleaving, raw
     parameter columns, edge list, labels) is bit-exact too; the masked z-score statistics are fp32 sums over 1920 rows whose
@@ -1275,9 +1277,13 @@ def test_dataset_builder_on_the_device_vs_reference_golden(env):
     S = fx["nodes"].shape[0]
     zn, ze = env["dataset"].reference_noise_stream(0, S, 15, 14)
     st = env["dataset"].build_scenario_store(fx["nodes"], fx["edges"], fx["labels"], grid["noise_param"], grid["meas_v"], grid["meas_pflow"],
-                                             zn, ze, device="cuda")
+                                             zn, ze, device="cuda", impl=impl)
     x, ea = st.x.cpu().numpy(), st.edge_attr.cpu().numpy()
     n, e = gd["x"].shape[0], gd["edge_attr"].shape[0]
+    if impl == "kernel":   # the default on the device IS the kernel, and it is deterministic
+        again = env["dataset"].build_scenario_store(fx["nodes"], fx["edges"], fx["labels"], grid["noise_param"], grid["meas_v"],
+                                                    grid["meas_pflow"], zn, ze, device="cuda")
+        assert torch.equal(again.x, st.x) and torch.equal(again.edge_attr, st.edge_attr) and torch.equal(again.x_std, st.x_std)
     assert np.array_equal(st.edge_index.cpu().numpy()[:, :14], gd["edge_index"])
     assert np.array_equal(st.y.cpu().numpy()[:n], gd["y"])
     assert np.array_equal(x[:n, 8:], gd["x"][:, 8:]) and np.array_equal(ea[:e, 6:], gd["edge_attr"][:, 6:])       # raw parameter columns
