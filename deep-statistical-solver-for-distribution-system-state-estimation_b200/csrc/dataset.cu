@@ -221,6 +221,38 @@ __global__ void __launch_bounds__(DS_THREADS) k_ds_normalise(DsArgs a) {
   }
 }
 
+// Synthetic scenario sampler (toy_network.py:83-126 + loadsampling.py:75-107), two element-wise kernels in the reference's rounding order:
+//   k_load_profiles  mu[l*H + h] = wa[l] * (base[l] * prof_a[h]) + wb[l] * (base[l] * prof_b[h])          (toy_network.py:106-107, 111-114)
+//                    and the two sampler arguments: (mu (1 - s), mu (1 + s)) for 'uniform', (mu, mu s) for 'normal' (toy_network.py:119-123)
+//   k_mc_sample      out[u, i] = A[u] + draw[u, i] * (B[u] - A[u])   (samplermontecarlo, loadsampling.py:78-91)
+//                    out[u, i] = A[u] + B[u] * draw[u, i]            (samplermontecarlo_normal = MU + SIG * gauss, loadsampling.py:105)
+__global__ void __launch_bounds__(DS_THREADS) k_load_profiles(const double* __restrict__ base, const double* __restrict__ wa,
+                                                              const double* __restrict__ wb, const double* __restrict__ prof_a,
+                                                              const double* __restrict__ prof_b, int L, int H, int dist, double spread,
+                                                              double* __restrict__ A, double* __restrict__ B) {
+  const int total = L * H;
+  for (int u = blockIdx.x * DS_THREADS + threadIdx.x; u < total; u += gridDim.x * DS_THREADS) {
+    const int l = u / H, h = u % H;
+    const double mu = __dadd_rn(__dmul_rn(wa[l], __dmul_rn(base[l], prof_a[h])), __dmul_rn(wb[l], __dmul_rn(base[l], prof_b[h])));
+    if (dist == 0) {
+      A[u] = __dmul_rn(mu, __dsub_rn(1.0, spread));
+      B[u] = __dmul_rn(mu, __dadd_rn(1.0, spread));
+    } else {
+      A[u] = mu;
+      B[u] = __dmul_rn(mu, spread);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(DS_THREADS) k_mc_sample(const double* __restrict__ A, const double* __restrict__ B, int64_t U, int iters, int dist,
+                                                          const double* __restrict__ draws, double* __restrict__ out) {
+  const int64_t total = U * iters;
+  for (int64_t i = blockIdx.x * (int64_t)DS_THREADS + threadIdx.x; i < total; i += (int64_t)gridDim.x * DS_THREADS) {
+    const int64_t u = i / iters;
+    out[i] = dist == 0 ? __dadd_rn(A[u], __dmul_rn(draws[i], __dsub_rn(B[u], A[u]))) : __dadd_rn(A[u], __dmul_rn(B[u], draws[i]));
+  }
+}
+
 int ds_grid(int64_t rows) { return (int)max((int64_t)1, min((int64_t)dss2_sm_count() * 8, (rows + DS_THREADS - 1) / DS_THREADS)); }
 
 }  // namespace
@@ -266,6 +298,26 @@ extern "C" int dss2_build_scenarios(const double* nodes, const double* closed_ed
   k_ds_finalize<<<1, 32, 0, stream>>>(a, grid, 1);
   DSS2_LAUNCH_CHECK();
   k_ds_normalise<<<grid, DS_THREADS, 0, stream>>>(a);
+  DSS2_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int dss2_load_profiles(const double* base, const double* weight_a, const double* weight_b, const double* profile_a,
+                                  const double* profile_b, int L, int H, int dist, double spread, double* arg_a, double* arg_b, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DSS2_CHECK_ARG(base && weight_a && weight_b && profile_a && profile_b && arg_a && arg_b, "dss2_load_profiles: null argument");
+  DSS2_CHECK_ARG(L >= 1 && H >= 1 && (dist == 0 || dist == 1), "dss2_load_profiles: bad sizes or distribution");
+  k_load_profiles<<<ds_grid((int64_t)L * H), DS_THREADS, 0, stream>>>(base, weight_a, weight_b, profile_a, profile_b, L, H, dist, spread, arg_a, arg_b);
+  DSS2_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int dss2_mc_sample(const double* arg_a, const double* arg_b, int64_t U, int iters, int dist, const double* draws, double* out,
+                              void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DSS2_CHECK_ARG(arg_a && arg_b && draws && out, "dss2_mc_sample: null argument");
+  DSS2_CHECK_ARG(U >= 1 && iters >= 1 && (dist == 0 || dist == 1), "dss2_mc_sample: bad sizes or distribution");
+  k_mc_sample<<<ds_grid(U * iters), DS_THREADS, 0, stream>>>(arg_a, arg_b, U, iters, dist, draws, out);
   DSS2_LAUNCH_CHECK();
   return 0;
 }

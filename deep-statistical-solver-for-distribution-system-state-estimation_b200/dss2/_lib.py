@@ -65,6 +65,8 @@ _SIGNATURES = {
     "dss2_edgeagg_bwd_slot": (c_int, [_G, _P, c_int64, c_int, _P, c_int64, c_int, c_int, _P, _P, c_int64, _P, _P, c_int64, _P]),
     "dss2_build_scenarios_workspace_bytes": (c_size_t, []),
     "dss2_build_scenarios": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, _P, _P, _P, _P, c_size_t, _P]),
+    "dss2_load_profiles": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, ctypes.c_double, _P, _P, _P]),
+    "dss2_mc_sample": (c_int, [_P, _P, c_int64, c_int, c_int, _P, _P, _P]),
     "dss2_pflow": (c_int, [_P, c_int64, _P, c_int64, _P, c_int64, _P, _P, _P]),
     "dss2_pflow_ex": (c_int, [_P, c_int64, _P, c_int64, _P, c_int64, _P, c_int, _P, _P]),
     "dss2_pflow_bwd": (c_int, [_G, _P, c_int64, _P, c_int64, _P, c_int, _P, _P, _P]),

@@ -262,6 +262,18 @@ int dss2_build_scenarios(const double* nodes, const double* closed_edges, const 
                          const uint8_t* meas_v_mask, const uint8_t* meas_pflow_mask, const double* noise_param6, int64_t S, int N,
                          int E, float* x, float* edge_attr, float* stats28, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Synthetic scenario sampler of the offline generator (toy_network.py:83-126 with loadsampling.py:75-107), bit-exact with the
+ * reference's numpy arithmetic for the same random draws.
+ * dss2_load_profiles: base [L] loads (or static generators); mu[l*H+h] = weight_a[l] * (base[l] * profile_a[h]) + weight_b[l] * (base[l] *
+ *   profile_b[h]) over the H hours of two daily profiles (toy_network.py:106-107), written as the sampler's two arguments [L*H]:
+ *   dist 0 'uniform': arg_a = mu (1 - spread), arg_b = mu (1 + spread); dist 1 'normal': arg_a = mu, arg_b = mu * spread (:119-123).
+ * dss2_mc_sample: out[u,i] = arg_a[u] + draws[u,i] * (arg_b[u] - arg_a[u]) (dist 0, samplermontecarlo, draws uniform in [0,1)) or
+ *   arg_a[u] + arg_b[u] * draws[u,i] (dist 1, samplermontecarlo_normal, standard-normal draws); draws, out [U, iters] f64. */
+int dss2_load_profiles(const double* base, const double* weight_a, const double* weight_b, const double* profile_a,
+                       const double* profile_b, int L, int H, int dist, double spread, double* arg_a, double* arg_b, void* stream);
+int dss2_mc_sample(const double* arg_a, const double* arg_b, int64_t U, int iters, int dist, const double* draws, double* out,
+                   void* stream);
+
 /* Validation metrics of one batch (SURVEY.md 8f-4, dss2_run.py:183-209) in one kernel: x [Nt,>=11] (column 9 = slack flag),
  * edge_attr [Et,>=13] (columns 6.. = branch parameters), output [Nt,2] = model output (normalised V, raw theta), y [Nt,2] = labels.
  * sums19 (device, fp64): [0..3] sum (dV)^2, |dV|, (dth)^2, |dth| with V = out0*x_std0 + x_mean0 and th = out1*(1-slack);

@@ -514,3 +514,39 @@ def train_step(sd, batch, stats, reg_coefs, p_drop, opt_state, kind="SkipPFN", g
                 opt_state[name] = (torch.zeros_like(p), torch.zeros_like(p))
             adamax_step(p, p.grad, opt_state[name][0], opt_state[name][1], opt_state["step"])
     return loss.detach()
+
+
+# --------------------------------------------------------------------------------------------
+# (f-3) synthetic scenario sampler of the offline generator: loadsampling.py:75-107, toy_network.py:83-129
+# --------------------------------------------------------------------------------------------
+def mc_uniform(lb, ub, numbersamples, draws=None):
+    """loadsampling.py:75-93 `samplermontecarlo`: LB + rand(U, n) * (UB - LB); scalars broadcast to [1, n] like the reference."""
+    import numpy as np
+    lb, ub = np.atleast_1d(np.asarray(lb, dtype=np.float64)), np.atleast_1d(np.asarray(ub, dtype=np.float64))
+    if draws is None:
+        draws = np.random.rand(lb.size, numbersamples)           # :91, legacy global stream
+    return lb[:, None] + np.multiply(draws, (ub - lb)[:, None])
+
+
+def mc_normal(mu, sig, numbersamples, draws=None):
+    """loadsampling.py:94-107 `samplermontecarlo_normal`: np.random.normal(MMU, MSIG) = MMU + MSIG * gauss on the legacy stream."""
+    import numpy as np
+    mu, sig = np.atleast_1d(np.asarray(mu, dtype=np.float64)), np.atleast_1d(np.asarray(sig, dtype=np.float64))
+    if draws is None:
+        draws = np.random.standard_normal((mu.size, numbersamples))
+    return mu[:, None] + sig[:, None] * draws
+
+
+def sample_profiles(base, weight_a, weight_b, profile_a, profile_b, iterations, dist="normal", spread=0.15, draws=None):
+    """toy_network.py:104-129: hourly profile of every load (:106-107), unrolled (:111-114), perturbed `iterations` times with the chosen
+    sampler (:118-123) and reshaped to [L, H*iterations] (:129)."""
+    import numpy as np
+    base, wa, wb = (np.asarray(t, dtype=np.float64) for t in (base, weight_a, weight_b))
+    pa, pb = np.asarray(profile_a, dtype=np.float64), np.asarray(profile_b, dtype=np.float64)
+    prof = np.stack([wa * (base * pa[i]) + wb * (base * pb[i]) for i in range(pa.size)], axis=1)
+    unroll = np.reshape(prof, prof.size)
+    if dist == "uniform":
+        mc = mc_uniform(unroll * (1 - spread), unroll * (1 + spread), iterations, draws)
+    else:
+        mc = mc_normal(unroll, unroll * spread, iterations, draws)
+    return np.reshape(mc, [prof.shape[0], prof.shape[1] * iterations])

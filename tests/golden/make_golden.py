@@ -15,6 +15,9 @@ Files written
   golden_model_<tag>.npz      reference model forward + gsp_wls_edge + backward: inputs, recorded
                               dropout masks, output (before / after the in-place slack masking), loss,
                               all parameter gradients and the gradient w.r.t. the model output
+  golden_loadsampling.npz     reference loadsampling.samplermontecarlo / samplermontecarlo_normal (vector and scalar arguments) after
+                              np.random.seed, and the load-profile step of toy_network.py:106-129 re-typed on top of them (toy_network
+                              itself imports pandapower, which the image does not have)
 """
 import os
 import pickle
@@ -195,7 +198,47 @@ def run_gine(tag, batch, stats, sd_seed, num_layers=8):
     print(tag, "out", tuple(out.shape), "loss", res["loss"])
 
 
+def run_loadsampling():
+    """The reference's own samplers (pure numpy: importable) on seeded inputs; the profile step of toy_network.py:100-129 needs pandapower
+    objects, so those few numpy lines are re-typed here verbatim over a synthetic load table and fed to the reference's samplers."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_loadsampling", "/root/reference/loadsampling.py")   # not the drop-in of the same name
+    ref_ls = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_ls)
+    rng = np.random.RandomState(7)
+    lb = rng.uniform(0.1, 2.0, 9)
+    ub = lb * (1.0 + rng.uniform(0.1, 0.9, 9))
+    mu = rng.uniform(-1.0, 3.0, 9)
+    sig = np.abs(mu) * 0.15
+    np.random.seed(21)
+    uni = ref_ls.samplermontecarlo(lb, ub, 5)
+    np.random.seed(22)
+    nor = ref_ls.samplermontecarlo_normal(mu, sig, 5)
+    np.random.seed(23)
+    uni_s = ref_ls.samplermontecarlo(0.4, 1.7, 6)
+    np.random.seed(24)
+    nor_s = ref_ls.samplermontecarlo_normal(0.9, 0.2, 6)
+    # toy_network.py:83-86, 100-129 with LOAD_DIST = 'normal' (the default) and 'uniform', ITERATIONS = 3
+    household = np.array([0.25, 0.2, 0.2, 0.2, 0.2, 0.25, 0.4, 0.65, 0.65, 0.65, 0.7, 0.6, 0.7, 0.65, 0.55, 0.5, 0.45, 0.6, 0.8, 0.9, 0.8, 0.7, 0.55, 0.3])
+    industry = np.array([0.35, 0.35, 0.3, 0.3, 0.4, 0.5, 0.6, 0.9, 1., 1., 1., 0.9, 0.85, 0.85, 0.85, 0.85, 0.8, 0.55, 0.5, 0.45, 0.4, 0.4, 0.35, 0.35])
+    p_mw = rng.uniform(0.02, 0.6, 7)
+    hh_mask = np.array([1., 1., 0., 1., 0., 0., 1.])      # load_r_mask + load_lv_mask
+    ind_mask = 1.0 - hh_mask                              # load_ind_mask + load_mv_mask
+    load_p = np.stack([hh_mask * (p_mw * household[i]) + ind_mask * (p_mw * industry[i]) for i in range(24)], axis=1)   # :106
+    unroll = np.reshape(load_p, load_p.size)                                                                             # :111
+    iters, pm_error = 3, 0.3
+    np.random.seed(25)
+    mc_n = np.reshape(ref_ls.samplermontecarlo_normal(unroll, unroll * (pm_error / 2), iters), [load_p.shape[0], load_p.shape[1] * iters])   # :122,129
+    np.random.seed(26)
+    mc_u = np.reshape(ref_ls.samplermontecarlo(unroll * (1 - pm_error), unroll * (1 + pm_error), iters), [load_p.shape[0], load_p.shape[1] * iters])
+    np.savez_compressed(os.path.join(HERE, "golden_loadsampling.npz"), lb=lb, ub=ub, mu=mu, sig=sig, uni=uni, nor=nor, uni_s=uni_s, nor_s=nor_s,
+                        p_mw=p_mw, hh_mask=hh_mask, ind_mask=ind_mask, mc_normal=mc_n, mc_uniform=mc_u, iters=np.array(iters),
+                        pm_error=np.array(pm_error), seeds=np.array([21, 22, 23, 24, 25, 26]))
+    print("loadsampling:", uni.shape, nor.shape, uni_s.shape, nor_s.shape, mc_n.shape)
+
+
 def main():
+    run_loadsampling()
     torch.set_num_threads(1)
     fix = np.load(os.path.join(HERE, "cigre14_scenarios.npz"), allow_pickle=False)
     S = fix["nodes"].shape[0]

@@ -1296,6 +1296,38 @@ def test_dataset_builder_on_the_device_vs_reference_golden(env, impl):
     assert np.allclose(x[:n, :8], gd["x"][:, :8], rtol=2e-5, atol=2e-6) and np.allclose(ea[:e, :6], gd["edge_attr"][:, :6], rtol=2e-5, atol=2e-6)
 
 
+def test_load_sampler_kernels_bit_exact_vs_reference(env):
+    """Scope row 8f-3, sampler half: dss2_load_profiles + dss2_mc_sample (csrc/dataset.cu) through dss2.sampling and the drop-in
+    `loadsampling` functions, against the outputs of the reference's own loadsampling.py (golden_loadsampling.npz): the draws come from
+    the same legacy np.random stream and every float64 product / sum is rounded once like numpy's, so the results are bit-identical."""
+    import loadsampling as dropin
+    from dss2 import sampling
+    z = load_golden("golden_loadsampling.npz")
+    sd = [int(v) for v in z["seeds"]]
+    np.random.seed(sd[0])
+    assert np.array_equal(dropin.samplermontecarlo(z["lb"], z["ub"], 5), z["uni"])
+    np.random.seed(sd[1])
+    assert np.array_equal(dropin.samplermontecarlo_normal(z["mu"], z["sig"], 5), z["nor"])
+    np.random.seed(sd[2])
+    assert np.array_equal(dropin.samplermontecarlo(0.4, 1.7, 6), z["uni_s"])
+    np.random.seed(sd[3])
+    assert np.array_equal(dropin.samplermontecarlo_normal(0.9, 0.2, 6), z["nor_s"])
+    iters, err = int(z["iters"]), float(z["pm_error"])
+    np.random.seed(sd[4])
+    got = sampling.sample_loads(z["p_mw"], z["hh_mask"], z["ind_mask"], iters, "normal", err / 2)
+    assert got.is_cuda and np.array_equal(got.cpu().numpy(), z["mc_normal"])
+    np.random.seed(sd[5])
+    assert np.array_equal(sampling.sample_loads(z["p_mw"], z["hh_mask"], z["ind_mask"], iters, "uniform", err).cpu().numpy(), z["mc_uniform"])
+    # device-side draws (the 1 M-scenario case): same kernels, oracle arithmetic on the same draws
+    g = torch.Generator(device="cuda").manual_seed(5)
+    draws = torch.randn(7 * 24, 50, dtype=torch.float64, device="cuda", generator=g)
+    got = sampling.sample_sgen(z["p_mw"], z["hh_mask"], z["ind_mask"], 50, "normal", 0.125, draws=draws)
+    ref = orc.sample_profiles(z["p_mw"], z["hh_mask"], z["ind_mask"], sampling.SUN, sampling.WIND, 50, "normal", 0.125, draws=draws.cpu().numpy())
+    assert np.array_equal(got.cpu().numpy(), ref)
+    with pytest.raises(NotImplementedError):
+        sampling.sample_loads(z["p_mw"], z["hh_mask"], z["ind_mask"], 2, "kumaraswamy")
+
+
 # ------------------------------------------------------------------------------------------------ validation metrics (scope row 8f-4)
 @pytest.mark.parametrize("case", ["cigre14", "ober_sub"])
 def test_eval_metrics_kernel_matches_script_formulas(env, case):

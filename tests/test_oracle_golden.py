@@ -173,3 +173,26 @@ def test_gnn_dsse_forward_backward_vs_reference(tag):
     assert_fp32_parity(z["loss"], loss32, loss64, "loss")
     for name, g in grads.items():
         assert_fp32_parity(g, g32[name], g64[name], name)
+
+
+def test_load_samplers_match_the_reference_bit_for_bit():
+    """oracle mc_uniform / mc_normal / sample_profiles against the reference's own loadsampling functions (golden_loadsampling.npz,
+    generated by importing /root/reference/loadsampling.py): identical np.random stream, identical float64 arithmetic -> bit-exact."""
+    z = load_golden("golden_loadsampling.npz")
+    sd = [int(v) for v in z["seeds"]]
+    np.random.seed(sd[0])
+    assert np.array_equal(orc.mc_uniform(z["lb"], z["ub"], 5), z["uni"])
+    np.random.seed(sd[1])
+    assert np.array_equal(orc.mc_normal(z["mu"], z["sig"], 5), z["nor"])
+    np.random.seed(sd[2])
+    assert np.array_equal(orc.mc_uniform(0.4, 1.7, 6), z["uni_s"])
+    np.random.seed(sd[3])
+    assert np.array_equal(orc.mc_normal(0.9, 0.2, 6), z["nor_s"])
+    from dss2 import sampling
+    iters, err = int(z["iters"]), float(z["pm_error"])
+    np.random.seed(sd[4])
+    assert np.array_equal(orc.sample_profiles(z["p_mw"], z["hh_mask"], z["ind_mask"], sampling.HOUSEHOLD, sampling.INDUSTRY, iters, "normal", err / 2),
+                          z["mc_normal"])
+    np.random.seed(sd[5])
+    assert np.array_equal(orc.sample_profiles(z["p_mw"], z["hh_mask"], z["ind_mask"], sampling.HOUSEHOLD, sampling.INDUSTRY, iters, "uniform", err),
+                          z["mc_uniform"])
