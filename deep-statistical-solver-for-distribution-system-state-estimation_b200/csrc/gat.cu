@@ -34,7 +34,8 @@ struct GatArgs {
   int fe;
   const float *wl, *bl, *wr, *br, *we, *att, *bias;
   float slope_att, slope_act;
-  int act;
+  int act;     // 0 none, 1 leaky_relu(slope_act) (relu = slope 0), 2 tanh
+  int loops;   // 1: PyG add_self_loops=True (drop input loops, append one per bus with the mean in-attribute); 0: edges as given
   float* y;           // fwd
   const float* yout;  // bwd: the layer's output (activation gate)
   const float* gy;
@@ -115,7 +116,7 @@ __device__ __forceinline__ DstStats dst_pass(const GatArgs& a, const GatW& w, in
   for (int z = beg; z < end; ++z) {
     const uint32_t id = g.eid[z];
     const int j = g.col[z];
-    if ((id >> 31) || j == i) continue;
+    if ((id >> 31) || (a.loops && j == i)) continue;
     float xj[GC], xl[GC], at[GFE], s[GC];
     load_x(a, j, xj);
     lin8(w.wl, w.bl, xj, xl);
@@ -132,16 +133,19 @@ __device__ __forceinline__ DstStats dst_pass(const GatArgs& a, const GatW& w, in
     for (int f = 0; f < GFE; ++f) abar[f] = abar[f] / c;
   }
   float s_loop[GC];
-  edge_pre(w, xr, xl_i, abar, s_loop);
-  const float sc_loop = edge_score(w, s_loop, a.slope_att);
-  m = fmaxf(m, sc_loop);
+  float sc_loop = -INFINITY;
+  if (a.loops) {
+    edge_pre(w, xr, xl_i, abar, s_loop);
+    sc_loop = edge_score(w, s_loop, a.slope_att);
+    m = fmaxf(m, sc_loop);
+  }
   float den = 0.0f, t = 0.0f;
 #pragma unroll
   for (int c = 0; c < GC; ++c) acc[c] = 0.0f;
   for (int z = beg; z < end; ++z) {
     const uint32_t id = g.eid[z];
     const int j = g.col[z];
-    if ((id >> 31) || j == i) continue;
+    if ((id >> 31) || (a.loops && j == i)) continue;
     float xj[GC], xl[GC], at[GFE], s[GC];
     load_x(a, j, xj);
     lin8(w.wl, w.bl, xj, xl);
@@ -157,7 +161,7 @@ __device__ __forceinline__ DstStats dst_pass(const GatArgs& a, const GatW& w, in
     }
     if (WITH_T) t = fmaf(ex, dot, t);
   }
-  {
+  if (a.loops) {
     const float ex = expf(sc_loop - m);
     den += ex;
     float dot = 0.0f;
@@ -168,7 +172,7 @@ __device__ __forceinline__ DstStats dst_pass(const GatArgs& a, const GatW& w, in
     }
     if (WITH_T) t = fmaf(ex, dot, t);
   }
-  den += 1e-16f;
+  den += 1e-16f;   // a bus without in-edges and without loop: acc = 0, den = 1e-16 -> out = bias, like PyG's empty softmax segment
   DstStats r;
   r.m = m;
   r.den = den;
@@ -191,7 +195,7 @@ __global__ void __launch_bounds__(GAT_THREADS) k_gat_fwd(GatArgs a) {
 #pragma unroll
     for (int c = 0; c < GC; ++c) {
       const float v = acc[c] / st.den + w.bias[c];
-      out[c] = (a.act && !(v > 0.0f)) ? v * a.slope_act : v;
+      out[c] = a.act == 2 ? tanhf(v) : ((a.act == 1 && !(v > 0.0f)) ? v * a.slope_act : v);
     }
     float4* dst = reinterpret_cast<float4*>(a.y + i * GC);
     dst[0] = make_float4(out[0], out[1], out[2], out[3]);
@@ -211,7 +215,8 @@ __global__ void __launch_bounds__(GAT_THREADS) k_gat_bwd_stats(GatArgs a) {
     lin8(w.wl, w.bl, xi, xl);
 #pragma unroll
     for (int c = 0; c < GC; ++c) {
-      const float gate = (a.act && !(a.yout[i * GC + c] > 0.0f)) ? a.slope_act : 1.0f;
+      const float yv = a.yout[i * GC + c];
+      const float gate = a.act == 2 ? 1.0f - yv * yv : ((a.act == 1 && !(yv > 0.0f)) ? a.slope_act : 1.0f);
       G[c] = a.gy[i * GC + c] * gate;
     }
     const DstStats st = dst_pass<true>(a, w, i, xr, xl, abar, acc, G);
@@ -280,7 +285,7 @@ __global__ void __launch_bounds__(GAT_THREADS) k_gat_bwd(GatArgs a) {
     for (int z = beg; z < end; ++z) {
       const uint32_t id = g.eid[z];
       const int o = g.col[z];
-      if (o == n) continue;   // self loops of the input are dropped (remove_self_loops)
+      if (a.loops && o == n) continue;   // self loops of the input are dropped (remove_self_loops, part of add_self_loops=True)
       float at[GFE], s[GC], ds[GC];
       load_attr(a, id & 0x7fffffffu, at);
       if (!(id >> 31)) {      // in-edge (o -> n): this bus is the destination
@@ -312,7 +317,7 @@ __global__ void __launch_bounds__(GAT_THREADS) k_gat_bwd(GatArgs a) {
         for (int c = 0; c < GC; ++c) dxl[c] += fmaf(alpha, Go[c], ds[c]);
       }
     }
-    {   // the appended self loop (n -> n) with the mean in-attribute
+    if (a.loops) {   // the appended self loop (n -> n) with the mean in-attribute
       if (cnt > 0) {
         const float c = (float)cnt;
 #pragma unroll
@@ -646,7 +651,7 @@ __global__ void __launch_bounds__(GAT_THREADS) k_gine_fwd(GineArgs a) {
     gine_h(a, w, i, xi, h);
     lin8(w.wn, w.bn, h, out);
 #pragma unroll
-    for (int c = 0; c < GC; ++c) out[c] = (a.act && !(out[c] > 0.0f)) ? out[c] * a.slope_act : out[c];
+    for (int c = 0; c < GC; ++c) out[c] = a.act == 2 ? tanhf(out[c]) : ((a.act == 1 && !(out[c] > 0.0f)) ? out[c] * a.slope_act : out[c]);
     float4* dst = reinterpret_cast<float4*>(a.y + i * GC);
     dst[0] = make_float4(out[0], out[1], out[2], out[3]);
     dst[1] = make_float4(out[4], out[5], out[6], out[7]);
@@ -664,7 +669,8 @@ __global__ void __launch_bounds__(GAT_THREADS) k_gine_bwd_a(GineArgs a) {
     float* o = a.ws + i * GINE_NODE_WS;
 #pragma unroll
     for (int c = 0; c < GC; ++c) {
-      const float gate = (a.act && !(a.yout[i * GC + c] > 0.0f)) ? a.slope_act : 1.0f;
+      const float yv = a.yout[i * GC + c];
+      const float gate = a.act == 2 ? 1.0f - yv * yv : ((a.act == 1 && !(yv > 0.0f)) ? a.slope_act : 1.0f);
       G[c] = a.gy[i * GC + c] * gate;
       o[c] = G[c];
       o[16 + c] = h[c];
@@ -936,7 +942,8 @@ int fill_args(const char* who, GatArgs& a, const dss2_graph_t* g, const float* x
   a.att = att;
   a.bias = bias;
   a.slope_att = slope_att;
-  a.act = act;
+  a.act = act & 0xff;
+  a.loops = (act & DSS2_GAT_NO_SELF_LOOPS) ? 0 : 1;
   a.slope_act = slope_act;
   return 0;
 }

@@ -22,7 +22,14 @@ class GATSpec:
     num_layers: int       # the reference builds num_layers - 1 GATv2 layers (networks.py:144)
     edge_dim: int
     att_slope: float = 0.2
-    act_slope: float = 0.01   # torch.nn.LeakyReLU() default (networks.py:137)
+    act_slope: float = 0.01   # torch.nn.LeakyReLU() default (networks.py:137); 0 for nonlin='relu'
+    act: str = "leaky_relu"   # nonlin of networks.py:130-137: 'leaky_relu' | 'relu' | 'tanh'
+    self_loops: bool = True   # add_self_loops of the GATv2 layers (networks.py:145)
+
+    @property
+    def act_code(self):
+        """`act` argument of dss2_gat_fwd / dss2_gat_bwd (include/dss2_b200.h)."""
+        return (2 if self.act == "tanh" else 1) | (0 if self.self_loops else 0x100)
 
     @property
     def n_conv(self):
@@ -111,7 +118,7 @@ class GATRunner:
         g = graph.ref
         for l in range(sp.n_conv):
             xin, stride = (x, xs) if l == 0 else (bufs["acts"][l - 1], GAT_C)
-            _lib.check(lib.dss2_gat_fwd(g, _lib.ptr(xin), stride, _lib.ptr(ea), eas, sp.edge_dim, *self._layer(flat, l), sp.att_slope, 1,
+            _lib.check(lib.dss2_gat_fwd(g, _lib.ptr(xin), stride, _lib.ptr(ea), eas, sp.edge_dim, *self._layer(flat, l), sp.att_slope, sp.act_code,
                                         sp.act_slope, _lib.ptr(bufs["acts"][l]), st), "dss2_gat_fwd")
         i = 2 * sp.n_conv
         _lib.check(lib.dss2_mlp2_fwd(graph.num_nodes, _lib.ptr(bufs["acts"][sp.n_conv - 1]), GAT_C, self._p(flat, f"model.module_{i}.weight"),
@@ -140,7 +147,7 @@ class GATRunner:
             xin, stride = (x, xs) if l == 0 else (bufs["acts"][l - 1], GAT_C)
             want_gx = l > 0 or need_gx
             gx = bufs["g8"][(sp.n_conv - l) & 1] if want_gx else None
-            _lib.check(lib.dss2_gat_bwd(g, _lib.ptr(xin), stride, _lib.ptr(ea), eas, sp.edge_dim, *self._layer(flat, l), sp.att_slope, 1,
+            _lib.check(lib.dss2_gat_bwd(g, _lib.ptr(xin), stride, _lib.ptr(ea), eas, sp.edge_dim, *self._layer(flat, l), sp.att_slope, sp.act_code,
                                         sp.act_slope, _lib.ptr(bufs["acts"][l]), _lib.ptr(gy), _lib.ptr(gx), _lib.ptr(bufs["ws"]),
                                         bufs["ws"].numel() * 4, pp(f"model.module_{2 * l}.lin_l.weight"), pstride, st), "dss2_gat_bwd")
             gy = gx

@@ -283,7 +283,8 @@ class GAT_DSSE(_LazyMachinery, nn.Module):
     """networks.py:113-156, the as-shipped default model of dss2_run.py:86: (num_layers - 1) x [GATv2Conv(dim_feat, dim_feat, heads,
     edge_dim, add_self_loops, fill 'mean') + LeakyReLU()], Linear(dim_feat, dim_dense), Linear(dim_dense, dim_out), wrapped in a PyG
     `Sequential` whose children are called `module_{i}` - kept, so that reference checkpoints (`model.module_0.att`, ...) load.
-    Built for the configuration the script uses (heads=1, concat, dropout 0, self loops, leaky_relu); anything else raises."""
+    heads=1 (with either `concat`: one head concatenated = one head averaged), attention dropout 0; `self_loops`, `slope` and the three
+    `nonlin` choices are free.  heads > 1 raises (with concat=True the reference's own stack cannot run: channel mismatch)."""
 
     def __init__(self, dim_feat, dim_dense, dim_out, num_layers, edge_dim, heads=1, concat=True, slope=0.2, self_loops=True, dropout=0.,
                  nonlin='leaky_relu', model='gat'):
@@ -292,13 +293,18 @@ class GAT_DSSE(_LazyMachinery, nn.Module):
             raise Exception('invalid model type')
         if nonlin not in ('relu', 'tanh', 'leaky_relu'):
             raise Exception('invalid activation type')
-        if heads != 1 or not concat or dropout != 0. or not self_loops or nonlin != 'leaky_relu':
-            raise NotImplementedError("GAT_DSSE kernels cover the configuration of dss2_run.py:86 (heads=1, concat=True, dropout=0, "
-                                      "self_loops=True, nonlin='leaky_relu')")
+        if heads != 1 and concat:
+            raise NotImplementedError("GAT_DSSE(heads > 1, concat=True): the reference's own stack cannot run this - every GATv2Conv maps "
+                                      "dim_feat -> heads * dim_feat channels while the next layer expects dim_feat (networks.py:144-147)")
+        if heads != 1:
+            raise NotImplementedError("GAT_DSSE kernels are built for heads=1 (dss2_run.py:86); multi-head averaging (concat=False) is not")
+        if dropout != 0.:
+            raise NotImplementedError("GAT_DSSE kernels are built for attention dropout 0 (dss2_run.py:86)")
         self.dim_out, self.num_layers, self.dim_feat, self.dim_dense, self.edge_dim = dim_out, num_layers, dim_feat, dim_dense, edge_dim
         self.dim_hidden = self.channels = dim_feat
         self.heads, self.concat, self.slope, self.dropout, self.loop = heads, concat, slope, dropout, self_loops
-        self.nonlin = nn.LeakyReLU()
+        self.nonlin_name = nonlin
+        self.nonlin = {'relu': nn.ReLU, 'tanh': nn.Tanh, 'leaky_relu': nn.LeakyReLU}[nonlin]()
         self.model = nn.Module()
         i = 0
         for _ in range(num_layers - 1):
@@ -313,7 +319,8 @@ class GAT_DSSE(_LazyMachinery, nn.Module):
         if m is None:
             from dss2 import gat
             spec = gat.GATSpec(dim_feat=self.dim_feat, dim_dense=self.dim_dense, dim_out=self.dim_out, num_layers=self.num_layers,
-                               edge_dim=self.edge_dim, att_slope=float(self.slope), act_slope=float(self.nonlin.negative_slope))
+                               edge_dim=self.edge_dim, att_slope=float(self.slope), act_slope=float(getattr(self.nonlin, "negative_slope", 0.0)),
+                               act=self.nonlin_name, self_loops=bool(self.loop))
             m = gat.make_machinery(spec)
             self.__dict__["_dss2_machinery"] = m
         return m

@@ -301,7 +301,8 @@ int dss2_adamax_step(float* param, const float* grad, float* exp_avg, float* exp
  * 7 x [PyG GATv2Conv(8, 8, heads=1, negative_slope=0.2, add_self_loops=True, edge_dim=6, fill_value='mean') + LeakyReLU(0.01)],
  * Linear(8, dim_dense), Linear(dim_dense, 2).
  *
- * dss2_gat_fwd: one GATv2 layer (+ optional LeakyReLU, act != 0) on the ONE-WAY edge list the script passes: x [Nt,8] (row stride
+ * dss2_gat_fwd: one GATv2 layer + activation (act: 0 none, 1 leaky_relu with act_slope - ReLU = slope 0 -, 2 tanh; or-ed with
+ * DSS2_GAT_NO_SELF_LOOPS for add_self_loops=False: edges as given, no appended loop) on the ONE-WAY edge list the script passes: x [Nt,8] (row stride
  * x_stride), edge_attr [Et,fe] (row stride ea_stride) -> y [Nt,8] dense.  Input self loops are dropped and one loop per bus is appended
  * last with the mean attribute of the edges pointing at the bus; segment softmax as PyG (max-shifted, + 1e-16).
  * Parameters with PyG's names and shapes: lin_l.weight/bias [8,8]/[8], lin_r.weight/bias, lin_edge.weight [8,fe], att [8], bias [8].
@@ -311,6 +312,7 @@ int dss2_adamax_step(float* param, const float* grad, float* exp_avg, float* exp
  * dss2_mlp2_fwd/bwd: z = W2 (W1 x + b1) + b2 per bus (no non-linearity in between, networks.py:150-151); h [Nt,dmid] is kept for the
  * backward; partial layout [w1 dmid x din | b1 dmid | w2 dout x dmid | b2 dout].
  * ---------------------------------------------------------------------------------------------- */
+#define DSS2_GAT_NO_SELF_LOOPS 0x100
 size_t dss2_gat_ws_bytes(int64_t num_nodes);
 int dss2_gat_fwd(const dss2_graph_t* g, const float* x, int64_t x_stride, const float* edge_attr, int64_t ea_stride, int fe,
                  const float* lin_l_w, const float* lin_l_b, const float* lin_r_w, const float* lin_r_b,

@@ -227,17 +227,20 @@ def init_state_dict(kind="SkipPFN", dim_featn=8, dim_feate=6, dim_out=2, dim_hid
 # --------------------------------------------------------------------------------------------
 
 
-def gatv2_layer(x, edge_index, edge_attr, w_l, b_l, w_r, b_r, w_e, att, bias, slope=0.2):
+def gatv2_layer(x, edge_index, edge_attr, w_l, b_l, w_r, b_r, w_e, att, bias, slope=0.2, self_loops=True):
     """One GATv2Conv (heads = 1) on the ONE-WAY edge list the script passes (networks.py:146 gets `data.edge_index` as is).
     Self loops of the input are dropped, then one loop per node is appended whose attribute is the mean of the attributes of the
     edges pointing at the node (0 without any).  Segment softmax as PyG: max-shifted exp / (sum + 1e-16)."""
     n = x.size(0)
-    keep = edge_index[0] != edge_index[1]
-    src, dst, ea = edge_index[0][keep], edge_index[1][keep], edge_attr[keep]
-    cnt = segment_sum(torch.ones(dst.numel(), 1, dtype=x.dtype), dst, n).clamp(min=1)
-    loop_attr = segment_sum(ea, dst, n) / cnt
-    loop = torch.arange(n)
-    src, dst, ea = torch.cat([src, loop]), torch.cat([dst, loop]), torch.cat([ea, loop_attr])
+    if self_loops:
+        keep = edge_index[0] != edge_index[1]
+        src, dst, ea = edge_index[0][keep], edge_index[1][keep], edge_attr[keep]
+        cnt = segment_sum(torch.ones(dst.numel(), 1, dtype=x.dtype), dst, n).clamp(min=1)
+        loop_attr = segment_sum(ea, dst, n) / cnt
+        loop = torch.arange(n)
+        src, dst, ea = torch.cat([src, loop]), torch.cat([dst, loop]), torch.cat([ea, loop_attr])
+    else:   # add_self_loops=False: the edge list as given (GATv2Conv.forward only touches loops under add_self_loops)
+        src, dst, ea = edge_index[0], edge_index[1], edge_attr
     x_l = x @ w_l.t() + b_l
     x_r = x @ w_r.t() + b_r
     s = torch.nn.functional.leaky_relu(x_r[dst] + x_l[src] + ea @ w_e.t(), slope)
@@ -249,14 +252,14 @@ def gatv2_layer(x, edge_index, edge_attr, w_l, b_l, w_r, b_r, w_e, att, bias, sl
     return segment_sum(x_l[src] * alpha.view(-1, 1), dst, n) + bias
 
 
-def gat_dsse_forward(sd, x, edge_index, edge_attr, num_layers=8):
+def gat_dsse_forward(sd, x, edge_index, edge_attr, num_layers=8, nonlin="leaky_relu", slope=0.2, self_loops=True):
     """GAT_DSSE.forward (networks.py:155-156) from a reference-named state_dict (`model.module_{i}.*`, PyG Sequential naming)."""
     h = x
     for l in range(num_layers - 1):
         p = f"model.module_{2 * l}."
         h = gatv2_layer(h, edge_index, edge_attr, sd[p + "lin_l.weight"], sd[p + "lin_l.bias"], sd[p + "lin_r.weight"], sd[p + "lin_r.bias"],
-                        sd[p + "lin_edge.weight"], sd[p + "att"], sd[p + "bias"])
-        h = torch.nn.functional.leaky_relu(h, 0.01)
+                        sd[p + "lin_edge.weight"], sd[p + "att"], sd[p + "bias"], slope=slope, self_loops=self_loops)
+        h = {"leaky_relu": lambda t: torch.nn.functional.leaky_relu(t, 0.01), "relu": torch.relu, "tanh": torch.tanh}[nonlin](h)   # :130-137
     i = 2 * (num_layers - 1)
     h = h @ sd[f"model.module_{i}.weight"].t() + sd[f"model.module_{i}.bias"]
     return h @ sd[f"model.module_{i + 1}.weight"].t() + sd[f"model.module_{i + 1}.bias"]

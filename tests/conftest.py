@@ -138,6 +138,7 @@ def permute_edges(batch, seed):
 def permuted_golden(z, seed):
     """dict view of a golden npz with the edge list in another order (for the oracle_*_run helpers)."""
     d = {k: z[k] for k in ("x", "edge_attr", "edge_index", "x_mean", "x_std", "edge_mean", "edge_std")}
+    d.update({k: z[k] for k in z.files if k.startswith("opt_")})
     pb = permute_edges({"edge_index": torch.from_numpy(z["edge_index"]), "edge_attr": torch.from_numpy(z["edge_attr"])}, seed)
     d["edge_index"], d["edge_attr"] = pb["edge_index"].numpy(), pb["edge_attr"].numpy()
     return d
@@ -156,10 +157,17 @@ def oracle_gat_run(orc, num_layers, sd, z, dtype):
     x, ea, ei = torch.from_numpy(z["x"]).to(dtype), torch.from_numpy(z["edge_attr"]).to(dtype), torch.from_numpy(z["edge_index"])
     st = [torch.from_numpy(z[k]).to(dtype) for k in ("x_mean", "x_std", "edge_mean", "edge_std")]
     p = {k: v.to(dtype).clone().requires_grad_(True) for k, v in sd.items()}
-    out = orc.gat_dsse_forward(p, x[:, :8], ei, ea[:, :6], num_layers)
+    out = orc.gat_dsse_forward(p, x[:, :8], ei, ea[:, :6], num_layers, **gat_options(z))
     loss = orc.wls_loss(x, ea, out, *st, ei, REG_COEFS)
     loss.backward()
     return out.detach(), loss.detach(), {k: v.grad for k, v in p.items()}
+
+
+def gat_options(z):
+    """Constructor options a GAT golden was recorded with (older files: the script's defaults)."""
+    if "opt_nonlin" not in (z.files if hasattr(z, "files") else z):
+        return {}
+    return {"nonlin": str(z["opt_nonlin"]), "slope": float(z["opt_slope"]), "self_loops": bool(z["opt_self_loops"])}
 
 
 def oracle_gine_run(orc, num_layers, sd, z, dtype):

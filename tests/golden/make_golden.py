@@ -122,10 +122,10 @@ def run_model(tag, kind, ctor, batch, stats, sd_seed, torch_seed, dtype=torch.fl
     print(tag, "out", tuple(out.shape), "loss", res.get("loss"), "masks", res["num_masks"])
 
 
-def run_gat(tag, batch, stats, sd_seed, num_layers=8):
-    """Reference GAT_DSSE (dss2_run.py:86 hyper-parameters) forward + gsp_wls_edge + backward on `batch`."""
+def run_gat(tag, batch, stats, sd_seed, num_layers=8, **opts):
+    """Reference GAT_DSSE (dss2_run.py:86 hyper-parameters; `opts`: concat / slope / self_loops / nonlin) forward + gsp_wls_edge + backward."""
     sd = orc.init_gat_state_dict(num_layers=num_layers, seed=sd_seed)
-    model = ref_net.GAT_DSSE(dim_feat=8, dim_dense=32, dim_out=2, heads=1, num_layers=num_layers, edge_dim=6)
+    model = ref_net.GAT_DSSE(dim_feat=8, dim_dense=32, dim_out=2, heads=1, num_layers=num_layers, edge_dim=6, **opts)
     missing = model.load_state_dict(sd, strict=True)
     assert not missing.missing_keys and not missing.unexpected_keys
     model.train()
@@ -133,6 +133,9 @@ def run_gat(tag, batch, stats, sd_seed, num_layers=8):
     res = {"x": batch.x.numpy(), "edge_index": batch.edge_index.numpy(), "edge_attr": batch.edge_attr.numpy(), "ptr": batch.ptr.numpy(),
            "out": out.detach().numpy().copy(), "num_layers": num_layers, "sd_seed": sd_seed,
            "x_mean": stats[0].numpy(), "x_std": stats[1].numpy(), "edge_mean": stats[2].numpy(), "edge_std": stats[3].numpy()}
+    if opts:
+        res.update(opt_nonlin=np.array(opts.get("nonlin", "leaky_relu")), opt_slope=np.array(opts.get("slope", 0.2)),
+                   opt_self_loops=np.array(opts.get("self_loops", True)), opt_concat=np.array(opts.get("concat", True)))
     got = {}
     out.register_hook(lambda g_: got.__setitem__("g", g_.clone()))
     loss = ref_loss(batch, out, stats)
@@ -237,6 +240,25 @@ def run_loadsampling():
     print("loadsampling:", uni.shape, nor.shape, uni_s.shape, nor_s.shape, mc_n.shape)
 
 
+def cigre_dataset():
+    """Reference data_from_pickles on the same 128 scenarios the fixture holds, after np.random.seed(0)."""
+    fix = np.load(os.path.join(HERE, "cigre14_scenarios.npz"), allow_pickle=False)
+    S = fix["nodes"].shape[0]
+    with tempfile.TemporaryDirectory() as tmp:
+        for name in ("nodes", "edges", "labels"):
+            with open(f"/root/reference/data/cigre14/{name}", "rb") as fh:
+                full = pickle.load(fh)
+            with open(os.path.join(tmp, name), "wb") as fh:
+                pickle.dump(full[:S], fh)
+        with open("/root/reference/data/cigre14/noise_param", "rb") as fh:
+            noise = pickle.load(fh)
+        with open(os.path.join(tmp, "noise_param"), "wb") as fh:
+            pickle.dump(noise, fh)
+        np.random.seed(0)
+        ds, xm, xs, em, es = ref_data.data_from_pickles(tmp + "/", 8, 6, 4, 2, CIGRE_MEAS_V, CIGRE_MEAS_PF)
+    return ds, (xm, xs, em, es)
+
+
 def main():
     run_loadsampling()
     torch.set_num_threads(1)
@@ -285,6 +307,10 @@ def main():
     run_model("skipmpn_cigre", "SkipMPN", skipmpn, Batch.from_data_list(ds[40:42]), stats, sd_seed=4, torch_seed=14)
 
     run_gat("gat_cigre", Batch.from_data_list(ds[50:56]), stats, sd_seed=6)
+    # the constructor's other runnable settings: no self loops + tanh + averaged single head + another attention slope; ReLU
+    run_gat("gat_noloop_tanh_cigre", Batch.from_data_list(ds[56:60]), stats, sd_seed=31, num_layers=4, self_loops=False, nonlin="tanh",
+            concat=False, slope=0.1)
+    run_gat("gat_relu_cigre", Batch.from_data_list(ds[90:93]), stats, sd_seed=32, num_layers=3, nonlin="relu")
     run_gine("gine_cigre", Batch.from_data_list(ds[60:65]), stats, sd_seed=8)
     run_gnn("gnn_gcn2_cigre", "gcn2", Batch.from_data_list(ds[70:76]), stats, sd_seed=21)
     run_gnn("gnn_tagcn_cigre", "tagcn", Batch.from_data_list(ds[80:85]), stats, sd_seed=22)

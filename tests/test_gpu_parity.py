@@ -1053,15 +1053,20 @@ def test_ragged_mixed_grid_batch_large_graph_path(env, tiny_tiles):
 
 
 # ------------------------------------------------------------------------------------------------ GAT_DSSE (scope row 8f-1)
-@pytest.mark.parametrize("tag", ["gat_cigre", "gat_ober"])
+@pytest.mark.parametrize("tag", ["gat_cigre", "gat_ober", "gat_noloop_tanh_cigre", "gat_relu_cigre"])
 @pytest.mark.parametrize("where", ["cuda", "cpu"])
 def test_gat_dsse_matches_reference_run(env, tag, where):
     """networks.GAT_DSSE (fused GATv2 kernels) with the weights of the reference run: output, loss through gsp_wls_edge and every
     parameter gradient against the reference's own GAT_DSSE executed over the shim (golden) with the fp64 oracle as arbiter.
     where='cpu' feeds CPU tensors and CPU parameters like the unmodified dss2_run.py."""
     from conftest import golden_gat, oracle_gat_run
+    from conftest import gat_options
     nl, sd, grads, z = golden_gat(tag)
-    model = env["networks"].GAT_DSSE(dim_feat=8, dim_dense=32, dim_out=2, heads=1, num_layers=nl, edge_dim=6)
+    opts = gat_options(z)          # the constructor's other runnable settings: self_loops=False, nonlin tanh / relu, slope, concat=False
+    if where == "cpu" and opts:
+        pytest.skip("CPU-tensor path covered on the default configuration")
+    ctor_opts = dict(opts, concat=bool(z["opt_concat"])) if opts else {}
+    model = env["networks"].GAT_DSSE(dim_feat=8, dim_dense=32, dim_out=2, heads=1, num_layers=nl, edge_dim=6, **ctor_opts)
     model.load_state_dict(sd, strict=True)
     model = model.to(where).train()
     x, ea, ei = torch.from_numpy(z["x"]).to(where), torch.from_numpy(z["edge_attr"]).to(where), torch.from_numpy(z["edge_index"]).to(where)
@@ -1100,7 +1105,7 @@ def test_gat_dsse_matches_reference_run(env, tag, where):
     lin = {}
     for dt in (torch.float32, torch.float64):
         pp = {k: v.to(dt).clone().requires_grad_(True) for k, v in sd.items()}
-        (orc.gat_dsse_forward(pp, x.cpu().to(dt)[:, :8], ei.cpu(), ea.cpu().to(dt)[:, :6], nl) * go.to(dt)).sum().backward()
+        (orc.gat_dsse_forward(pp, x.cpu().to(dt)[:, :8], ei.cpu(), ea.cpu().to(dt)[:, :6], nl, **opts) * go.to(dt)).sum().backward()
         lin[dt] = {k: v.grad for k, v in pp.items()}
     for name, p in model.named_parameters():
         assert_fp32_parity(p.grad, lin[torch.float32][name], lin[torch.float64][name], name + " (recorded grad_out)")
