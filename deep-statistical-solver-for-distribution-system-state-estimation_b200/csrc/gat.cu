@@ -585,6 +585,7 @@ struct GineArgs {
   int fe;
   const float *wn, *bn, *we, *be;
   float eps, slope_act;
+  const float* eps_dev;   // train_eps=True: this layer's eps parameter (device); its gradient lands behind lin.bias in the partial row
   int act;
   float* y;
   const float* yout;
@@ -638,8 +639,9 @@ __device__ __forceinline__ void gine_h(const GineArgs& a, const GineW& w, int64_
 #pragma unroll
     for (int c = 0; c < GC; ++c) agg[c] += fmaxf(pre[c], 0.0f);
   }
+  const float eps = a.eps_dev ? *a.eps_dev : a.eps;
 #pragma unroll
-  for (int c = 0; c < GC; ++c) h[c] = agg[c] + (1.0f + a.eps) * xi[c];
+  for (int c = 0; c < GC; ++c) h[c] = agg[c] + (1.0f + eps) * xi[c];
 }
 __global__ void __launch_bounds__(GAT_THREADS) k_gine_fwd(GineArgs a) {
   __shared__ GineW w;
@@ -692,7 +694,8 @@ __global__ void __launch_bounds__(GAT_THREADS) k_gine_bwd_b(GineArgs a) {
   gine_load_weights(w, a);
   __syncthreads();
   const dss2_graph_t& g = a.g;
-  float dWe[GC * GFE], dbe[GC];
+  float dWe[GC * GFE], dbe[GC], deps = 0.0f;
+  const float eps = a.eps_dev ? *a.eps_dev : a.eps;
 #pragma unroll
   for (int i = 0; i < GC * GFE; ++i) dWe[i] = 0.0f;
 #pragma unroll
@@ -704,7 +707,8 @@ __global__ void __launch_bounds__(GAT_THREADS) k_gine_bwd_b(GineArgs a) {
 #pragma unroll
     for (int c = 0; c < GC; ++c) {
       ghn[c] = sn[8 + c];
-      dx[c] = (1.0f + a.eps) * ghn[c];
+      dx[c] = (1.0f + eps) * ghn[c];
+      deps = fmaf(ghn[c], xn[c], deps);   // d/d eps of (1 + eps) x_n . gh_n
     }
     for (int z = g.rowptr[n]; z < g.rowptr[n + 1]; ++z) {
       const uint32_t id = g.eid[z];
@@ -745,6 +749,11 @@ __global__ void __launch_bounds__(GAT_THREADS) k_gine_bwd_b(GineArgs a) {
     const float v = warp_sum(dbe[c]);
     if (lane == 0) red[warp][GC * GFE + c] = v;
   }
+  __shared__ float red_eps[GAT_THREADS / 32];
+  {
+    const float v = warp_sum(deps);
+    if (lane == 0) red_eps[warp] = v;
+  }
   __syncthreads();
   float* part = a.partials + (size_t)blockIdx.x * a.partial_stride;
   for (int i = threadIdx.x; i < GC * a.fe + GC; i += blockDim.x) {
@@ -753,6 +762,12 @@ __global__ void __launch_bounds__(GAT_THREADS) k_gine_bwd_b(GineArgs a) {
 #pragma unroll
     for (int wv = 0; wv < GAT_THREADS / 32; ++wv) s += red[wv][src];
     part[i] = s;
+  }
+  if (a.eps_dev && threadIdx.x == 0) {
+    float s = 0.0f;
+#pragma unroll
+    for (int wv = 0; wv < GAT_THREADS / 32; ++wv) s += red_eps[wv];
+    part[GC * a.fe + GC] = s;
   }
 }
 
@@ -1030,12 +1045,21 @@ static int gine_fill(const char* who, GineArgs& a, const dss2_graph_t* g, const 
   return 0;
 }
 
+extern "C" int dss2_gine_fwd_ex(const dss2_graph_t* g, const float* x, int64_t x_stride, const float* edge_attr, int64_t ea_stride, int fe,
+                                const float* nn_w, const float* nn_b, const float* lin_w, const float* lin_b, float eps, const float* eps_param,
+                                int act, float act_slope, float* y, void* stream_);
 extern "C" int dss2_gine_fwd(const dss2_graph_t* g, const float* x, int64_t x_stride, const float* edge_attr, int64_t ea_stride, int fe,
                              const float* nn_w, const float* nn_b, const float* lin_w, const float* lin_b, float eps, int act,
                              float act_slope, float* y, void* stream_) {
+  return dss2_gine_fwd_ex(g, x, x_stride, edge_attr, ea_stride, fe, nn_w, nn_b, lin_w, lin_b, eps, nullptr, act, act_slope, y, stream_);
+}
+extern "C" int dss2_gine_fwd_ex(const dss2_graph_t* g, const float* x, int64_t x_stride, const float* edge_attr, int64_t ea_stride, int fe,
+                                const float* nn_w, const float* nn_b, const float* lin_w, const float* lin_b, float eps, const float* eps_param,
+                                int act, float act_slope, float* y, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   GineArgs a = {};
   if (gine_fill("dss2_gine_fwd", a, g, x, x_stride, edge_attr, ea_stride, fe, nn_w, nn_b, lin_w, lin_b, eps, act, act_slope)) return -1;
+  a.eps_dev = eps_param;
   DSS2_CHECK_ARG(y && ((uintptr_t)y & 15) == 0, "dss2_gine_fwd: y must be a 16-byte aligned [Nt, 8] buffer");
   if (g->num_nodes == 0) return 0;
   a.y = y;
@@ -1046,13 +1070,27 @@ extern "C" int dss2_gine_fwd(const dss2_graph_t* g, const float* x, int64_t x_st
 
 // partials_lin: per-CTA rows [lin.weight 8 fe | lin.bias 8]; partials_nn: per-CTA rows [nn.weight 64 | nn.bias 8] of THIS layer's share of
 // the shared Linear's gradient (the host adds the layers' shares); both with row stride partial_stride, dss2_num_partials() rows.
+extern "C" int dss2_gine_bwd_ex(const dss2_graph_t* g, const float* x, int64_t x_stride, const float* edge_attr, int64_t ea_stride, int fe,
+                                const float* nn_w, const float* nn_b, const float* lin_w, const float* lin_b, float eps, const float* eps_param,
+                                int act, float act_slope, const float* y, const float* grad_y, float* grad_x, float* node_ws,
+                                size_t node_ws_bytes, float* partials_lin, float* partials_nn, int64_t partial_stride, void* stream_);
 extern "C" int dss2_gine_bwd(const dss2_graph_t* g, const float* x, int64_t x_stride, const float* edge_attr, int64_t ea_stride, int fe,
                              const float* nn_w, const float* nn_b, const float* lin_w, const float* lin_b, float eps, int act,
                              float act_slope, const float* y, const float* grad_y, float* grad_x, float* node_ws, size_t node_ws_bytes,
                              float* partials_lin, float* partials_nn, int64_t partial_stride, void* stream_) {
+  return dss2_gine_bwd_ex(g, x, x_stride, edge_attr, ea_stride, fe, nn_w, nn_b, lin_w, lin_b, eps, nullptr, act, act_slope, y, grad_y, grad_x, node_ws,
+                          node_ws_bytes, partials_lin, partials_nn, partial_stride, stream_);
+}
+// eps_param != NULL (train_eps=True): eps is read from the device and its gradient is written as one more element of the partials_lin
+// row: [lin.weight 8 fe | lin.bias 8 | eps 1]
+extern "C" int dss2_gine_bwd_ex(const dss2_graph_t* g, const float* x, int64_t x_stride, const float* edge_attr, int64_t ea_stride, int fe,
+                                const float* nn_w, const float* nn_b, const float* lin_w, const float* lin_b, float eps, const float* eps_param,
+                                int act, float act_slope, const float* y, const float* grad_y, float* grad_x, float* node_ws,
+                                size_t node_ws_bytes, float* partials_lin, float* partials_nn, int64_t partial_stride, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   GineArgs a = {};
   if (gine_fill("dss2_gine_bwd", a, g, x, x_stride, edge_attr, ea_stride, fe, nn_w, nn_b, lin_w, lin_b, eps, act, act_slope)) return -1;
+  a.eps_dev = eps_param;
   DSS2_CHECK_ARG(grad_y && node_ws && partials_lin && partials_nn && (!act || y), "dss2_gine_bwd: null argument");
   DSS2_CHECK_ARG(g->undirected == 1, "dss2_gine_bwd: needs a graph built from the one-way edge list with undirect=1");
   DSS2_CHECK_ARG(node_ws_bytes >= dss2_gine_ws_bytes(g->num_nodes), "dss2_gine_bwd: node workspace too small");

@@ -21,6 +21,7 @@ class GINESpec:
     edge_dim: int
     eps: float = 0.0
     act_slope: float = 0.01
+    train_eps: bool = False   # eps of every GINEConv is a parameter `model.module_{2l}.eps` [1] (PyG GINEConv(train_eps=True))
 
     @property
     def n_conv(self):
@@ -42,6 +43,8 @@ class GINESpec:
         for l in range(self.n_conv):
             put(f"model.module_{2 * l}.lin.weight", c * self.edge_dim)
             put(f"model.module_{2 * l}.lin.bias", c)
+            if self.train_eps:   # directly behind lin.bias: the backward kernel writes its gradient as the next element of that partial row
+                put(f"model.module_{2 * l}.eps", 1)
             off = _align4(off)
         i = 2 * self.n_conv
         put(f"model.module_{i}.weight", self.dim_dense * c)
@@ -80,6 +83,9 @@ class GINERunner:
         return [self._p(flat, "nn.weight"), self._p(flat, "nn.bias"), self._p(flat, f"model.module_{2 * l}.lin.weight"),
                 self._p(flat, f"model.module_{2 * l}.lin.bias")]
 
+    def _eps(self, flat, l):
+        return self._p(flat, f"model.module_{2 * l}.eps") if self.spec.train_eps else None
+
     def alloc(self, num_nodes, device, need_grad=True):
         sp = self.spec
         f32 = dict(dtype=torch.float32, device=device)
@@ -96,8 +102,8 @@ class GINERunner:
         sp, lib, st = self.spec, self.lib, _lib.stream()
         for l in range(sp.n_conv):
             xin, stride = (x, xs) if l == 0 else (bufs["acts"][l - 1], GINE_C)
-            _lib.check(lib.dss2_gine_fwd(graph.ref, _lib.ptr(xin), stride, _lib.ptr(ea), eas, sp.edge_dim, *self._layer(flat, l), sp.eps, 1,
-                                         sp.act_slope, _lib.ptr(bufs["acts"][l]), st), "dss2_gine_fwd")
+            _lib.check(lib.dss2_gine_fwd_ex(graph.ref, _lib.ptr(xin), stride, _lib.ptr(ea), eas, sp.edge_dim, *self._layer(flat, l), sp.eps,
+                                            self._eps(flat, l), 1, sp.act_slope, _lib.ptr(bufs["acts"][l]), st), "dss2_gine_fwd")
         i = 2 * sp.n_conv
         _lib.check(lib.dss2_mlp2_fwd(graph.num_nodes, _lib.ptr(bufs["acts"][sp.n_conv - 1]), GINE_C, self._p(flat, f"model.module_{i}.weight"),
                                      self._p(flat, f"model.module_{i}.bias"), sp.dim_dense, self._p(flat, f"model.module_{i + 1}.weight"),
@@ -125,8 +131,8 @@ class GINERunner:
             xin, stride = (x, xs) if l == 0 else (bufs["acts"][l - 1], GINE_C)
             want_gx = l > 0 or need_gx
             gx = bufs["g8"][(sp.n_conv - l) & 1] if want_gx else None
-            _lib.check(lib.dss2_gine_bwd(graph.ref, _lib.ptr(xin), stride, _lib.ptr(ea), eas, sp.edge_dim, *self._layer(flat, l), sp.eps, 1,
-                                         sp.act_slope, _lib.ptr(bufs["acts"][l]), _lib.ptr(gy), _lib.ptr(gx), _lib.ptr(bufs["ws"]),
+            _lib.check(lib.dss2_gine_bwd_ex(graph.ref, _lib.ptr(xin), stride, _lib.ptr(ea), eas, sp.edge_dim, *self._layer(flat, l), sp.eps,
+                                            self._eps(flat, l), 1, sp.act_slope, _lib.ptr(bufs["acts"][l]), _lib.ptr(gy), _lib.ptr(gx), _lib.ptr(bufs["ws"]),
                                          bufs["ws"].numel() * 4, pp(self.table[f"model.module_{2 * l}.lin.weight"][0]),
                                          pp(sp.nn_share_offset(l)), pstride, st), "dss2_gine_bwd")
             gy = gx

@@ -207,10 +207,13 @@ class _GINEParams(nn.Module):
     """Parameter holder with PyG GINEConv's names: `nn` (the Linear handed in, shared by every layer of the model), `lin`
     (Linear(edge_dim, in_channels)), buffer `eps`.  The arithmetic is in the fused kernel (csrc/gat.cu)."""
 
-    def __init__(self, shared_nn, eps, edge_dim):
+    def __init__(self, shared_nn, eps, edge_dim, train_eps=False):
         super().__init__()
         self.nn = shared_nn
-        self.register_buffer("eps", torch.full((1,), float(eps)))
+        if train_eps:
+            self.eps = nn.Parameter(torch.full((1,), float(eps)))
+        else:
+            self.register_buffer("eps", torch.full((1,), float(eps)))
         self.lin = nn.Linear(edge_dim, shared_nn.in_features)
 
 
@@ -230,8 +233,6 @@ class GINE_DSSE(_LazyMachinery, nn.Module):
                                       "torch.nn, networks.py:72,88-91)")
         if model != 'gine':
             raise Exception('invalid model type')
-        if train_eps:
-            raise NotImplementedError("GINE_DSSE kernels cover train_eps=False (the default)")
         self.dim_out, self.num_layers, self.dim_feat, self.dim_dense = dim_out, num_layers, dim_feat, dim_dense
         self.eps, self.train_eps, self.edge_dim, self.dim_hidden = eps, train_eps, edge_dim, dim_feat
         self.nn = tnn.Linear(dim_feat, dim_feat)
@@ -239,7 +240,7 @@ class GINE_DSSE(_LazyMachinery, nn.Module):
         self.model = tnn.Module()
         i = 0
         for _ in range(num_layers - 1):
-            self.model.add_module(f"module_{i}", _GINEParams(self.nn, eps, edge_dim))
+            self.model.add_module(f"module_{i}", _GINEParams(self.nn, eps, edge_dim, train_eps))
             self.model.add_module(f"module_{i + 1}", self.nonlin)
             i += 2
         self.model.add_module(f"module_{i}", tnn.Linear(dim_feat, dim_dense))
@@ -250,7 +251,8 @@ class GINE_DSSE(_LazyMachinery, nn.Module):
         if m is None:
             from dss2 import gine
             spec = gine.GINESpec(dim_feat=self.dim_feat, dim_dense=self.dim_dense, dim_out=self.dim_out, num_layers=self.num_layers,
-                                 edge_dim=self.edge_dim, eps=float(self.eps), act_slope=float(self.nonlin.negative_slope))
+                                 edge_dim=self.edge_dim, eps=float(self.eps), act_slope=float(self.nonlin.negative_slope),
+                                 train_eps=bool(self.train_eps))
             m = gine.make_machinery(spec)
             self.__dict__["_dss2_machinery"] = m
         return m

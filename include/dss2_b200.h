@@ -335,6 +335,15 @@ int dss2_gine_bwd(const dss2_graph_t* g, const float* x, int64_t x_stride, const
                   const float* nn_w, const float* nn_b, const float* lin_w, const float* lin_b, float eps, int act, float act_slope,
                   const float* y, const float* grad_y, float* grad_x, float* node_ws, size_t node_ws_bytes, float* partials_lin,
                   float* partials_nn, int64_t partial_stride, void* stream);
+/* train_eps=True: eps_param = this layer's trainable eps on the device (NULL = the value `eps`); the backward appends its gradient to the
+ * partials_lin row: [lin.weight 8 fe | lin.bias 8 | eps 1]. */
+int dss2_gine_fwd_ex(const dss2_graph_t* g, const float* x, int64_t x_stride, const float* edge_attr, int64_t ea_stride, int fe,
+                     const float* nn_w, const float* nn_b, const float* lin_w, const float* lin_b, float eps, const float* eps_param,
+                     int act, float act_slope, float* y, void* stream);
+int dss2_gine_bwd_ex(const dss2_graph_t* g, const float* x, int64_t x_stride, const float* edge_attr, int64_t ea_stride, int fe,
+                     const float* nn_w, const float* nn_b, const float* lin_w, const float* lin_b, float eps, const float* eps_param,
+                     int act, float act_slope, const float* y, const float* grad_y, float* grad_x, float* node_ws, size_t node_ws_bytes,
+                     float* partials_lin, float* partials_nn, int64_t partial_stride, void* stream);
 int dss2_mlp2_fwd(int64_t num_nodes, const float* x, int din, const float* w1, const float* b1, int dmid, const float* w2,
                   const float* b2, int dout, float* h, float* z, void* stream);
 int dss2_mlp2_bwd(int64_t num_nodes, const float* x, int din, const float* w1, int dmid, const float* w2, int dout,

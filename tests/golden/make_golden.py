@@ -175,10 +175,15 @@ def run_gnn(tag, model, batch, stats, sd_seed, num_layers=4, K=3):
     print(tag, "out", tuple(out.shape), "loss", res["loss"])
 
 
-def run_gine(tag, batch, stats, sd_seed, num_layers=8):
-    """Reference GINE_DSSE forward + gsp_wls_edge + backward on `batch` (parameters stored under their named_parameters() names)."""
+def run_gine(tag, batch, stats, sd_seed, num_layers=8, **opts):
+    """Reference GINE_DSSE forward + gsp_wls_edge + backward on `batch` (parameters stored under their named_parameters() names).
+    opts: eps / train_eps (trainable eps parameters are drawn per layer so that every layer has its own value)."""
     sd = orc.init_gine_state_dict(num_layers=num_layers, seed=sd_seed)
-    model = ref_net.GINE_DSSE(dim_feat=8, dim_dense=32, dim_out=2, num_layers=num_layers, edge_dim=6)
+    model = ref_net.GINE_DSSE(dim_feat=8, dim_dense=32, dim_out=2, num_layers=num_layers, edge_dim=6, **opts)
+    if opts.get("train_eps"):
+        gen = torch.Generator().manual_seed(sd_seed + 1000)
+        for l in range(num_layers - 1):
+            sd[f"model.module_{2 * l}.eps"] = (torch.rand(1, generator=gen) - 0.5) * 0.6
     with torch.no_grad():
         for name, p in model.named_parameters():
             p.copy_(sd[name])
@@ -312,6 +317,7 @@ def main():
             concat=False, slope=0.1)
     run_gat("gat_relu_cigre", Batch.from_data_list(ds[90:93]), stats, sd_seed=32, num_layers=3, nonlin="relu")
     run_gine("gine_cigre", Batch.from_data_list(ds[60:65]), stats, sd_seed=8)
+    run_gine("gine_traineps_cigre", Batch.from_data_list(ds[65:69]), stats, sd_seed=33, num_layers=4, eps=0.1, train_eps=True)
     run_gnn("gnn_gcn2_cigre", "gcn2", Batch.from_data_list(ds[70:76]), stats, sd_seed=21)
     run_gnn("gnn_tagcn_cigre", "tagcn", Batch.from_data_list(ds[80:85]), stats, sd_seed=22)
 

@@ -1364,14 +1364,19 @@ def test_eval_metrics_kernel_matches_script_formulas(env, case):
 
 
 # ------------------------------------------------------------------------------------------------ GINE_DSSE (scope row 8f-1)
-@pytest.mark.parametrize("tag", ["gine_cigre", "gine_ober"])
+@pytest.mark.parametrize("tag", ["gine_cigre", "gine_ober", "gine_traineps_cigre"])
 @pytest.mark.parametrize("where", ["cuda", "cpu"])
 def test_gine_dsse_matches_reference_run(env, tag, where):
     """networks.GINE_DSSE (fused GINEConv kernels, one Linear shared by all layers) with the weights of the reference run: output, loss
     and every parameter gradient against the reference's own GINE_DSSE executed over the shim, fp64 oracle as arbiter."""
     from conftest import golden_gat, oracle_gine_run
     nl, sd, grads, z = golden_gat(tag)
-    model = env["networks"].GINE_DSSE(dim_feat=8, dim_dense=32, dim_out=2, num_layers=nl, edge_dim=6)
+    train_eps = "model.module_0.eps" in sd       # GINEConv(train_eps=True): one trainable eps per layer, with its own gradient
+    if where == "cpu" and train_eps:
+        pytest.skip("CPU-tensor path covered on the default configuration")
+    model = env["networks"].GINE_DSSE(dim_feat=8, dim_dense=32, dim_out=2, num_layers=nl, edge_dim=6, eps=0.1 if train_eps else 0.,
+                                      train_eps=train_eps)
+    assert ("model.module_0.eps" in dict(model.named_parameters())) == train_eps
     with torch.no_grad():
         for name, p in model.named_parameters():
             p.copy_(sd[name])

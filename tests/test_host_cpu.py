@@ -62,8 +62,10 @@ def test_no_cpu_fallback():
     gine = networks.GINE_DSSE(dim_feat=8, dim_dense=32, dim_out=2, num_layers=3, edge_dim=6)
     with pytest.raises(_lib.Dss2Error):
         gine(torch.zeros(4, 8), torch.tensor([[0, 1], [1, 2]]), torch.zeros(2, 6))
+    trainable = networks.GINE_DSSE(dim_feat=8, dim_dense=32, dim_out=2, num_layers=3, edge_dim=6, eps=0.2, train_eps=True)
+    assert "model.module_0.eps" in dict(trainable.named_parameters()) and float(trainable.model.module_2.eps) == pytest.approx(0.2)
     with pytest.raises(NotImplementedError):
-        networks.GINE_DSSE(dim_feat=8, dim_dense=32, dim_out=2, num_layers=3, edge_dim=6, train_eps=True)
+        networks.GINE_DSSE(dim_feat=8, dim_dense=32, dim_out=2, num_layers=3, edge_dim=6, nonlin='relu')
     gat = networks.GAT_DSSE(dim_feat=8, dim_dense=32, dim_out=2, heads=1, num_layers=3, edge_dim=6)
     with pytest.raises(_lib.Dss2Error):
         gat(torch.zeros(4, 8), torch.tensor([[0, 1], [1, 2]]), torch.zeros(2, 6))

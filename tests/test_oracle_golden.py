@@ -147,7 +147,7 @@ def test_gat_dsse_forward_backward_vs_reference(tag):
         assert_fp32_parity(g, g32[name], g64[name], name)
 
 
-@pytest.mark.parametrize("tag", ["gine_cigre", "gine_ober"])
+@pytest.mark.parametrize("tag", ["gine_cigre", "gine_ober", "gine_traineps_cigre"])
 def test_gine_dsse_forward_backward_vs_reference(tag):
     """Oracle GINE_DSSE (7 GINEConv layers sharing one Linear + 2 Linear) + loss + autograd == the reference's GINE_DSSE run over the shim."""
     from conftest import golden_gat, oracle_gine_run
