@@ -344,13 +344,14 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    if args.network != "skippfn" or args.mode != "train":
+    if args.mode != "train":
         return run_eager(args, dev, rank, world, local, K, W)
     grid = load_grid(args.config)
     shard = 0 if args.same_shards else rank
     store = synth.synthetic_store(grid, args.scenarios, seed=1234 + shard, device=dev)
     n, e = store.max_nodes, store.max_edges
-    trainer = GraphedTrainer(store, B, spec=default_spec(), reg_coefs=REG, seed=0, process_group=pg, world_size=world,
+    spec = default_spec() if args.network == "skippfn" else None      # gat / gine: the constructor arguments of dss2_run.py:73-86
+    trainer = GraphedTrainer(store, B, spec=spec, reg_coefs=REG, seed=0, process_group=pg, world_size=world, network=args.network,
                              use_cuda_graph=not args.no_graph, dropout_stream=0 if args.same_shards else None).capture()
     gen = torch.Generator().manual_seed(99 + shard)
     ids_host = torch.randint(0, args.scenarios, (W + K, B), generator=gen).pin_memory()
@@ -387,129 +388,132 @@ def main():
         sync = {"replicas_in_sync": max_over_ranks(float((trainer.flat - ref_flat).abs().max().item())) == 0.0,
                 "max_abs_param_diff_vs_rank0": max_over_ranks(float((trainer.flat - ref_flat).abs().max().item()))}
 
-    # ---- layer kernels timed live on the launching stream (hidden layer 32 -> 32, K = 2, the shapes of 35 of the 40 TAG layers) ----
-    lib, P = _lib.load(), _lib.ptr
+    roofline, tiled = None, trainer.graph.c.num_tiles > 0
     from dss2 import ops as _ops
-    sp, run, bufs = trainer.spec, trainer.runner, trainer.bufs
-    nt, et = trainer.nt, trainer.et
-    name_w, name_b = "mpns.0.convs.3.lins.0.weight", "mpns.0.convs.3.bias"
-    w_off, b_off = run.table[name_w][0], run.table[name_b][0]
-    part_w = ctypes.c_void_p(bufs["partials"].data_ptr() + 4 * w_off)
-    gref, st_ = trainer.graph.ref, _lib.stream
-    x_l, y_l, bits_l = bufs["acts"][0, 3], bufs["acts"][0, 4], bufs["bits"][0, 3]
-    gy_l, gx_l, lvl = bufs["g32"][0], bufs["g32"][1], bufs["lvl"]
-    wp, bp = run._p(trainer.flat, name_w), run._p(trainer.flat, name_b)
-    tiled = trainer.graph.c.num_tiles > 0
-    tc2 = tiled and _ops.TAG_IMPL == "tc2" and bool(lib.dss2_tag_tc2_supported(gref, sp.K))
-    kernels = {}
-    if tc2:
-        kernels["k_tag_tc3<BGX> (TAG backward-to-input, tcgen05, TMA-fed)"] = (lambda: _lib.check(lib.dss2_tag_bwd_tc2_gx(
-            gref, wp, 32, sp.K, 1, sp.p_drop, P(bits_l), P(gy_l), P(gx_l), P(lvl), lvl.numel() * 4, st_()), "gx"),
-            nt * (128 + 128 + 4 + 24), "grad_y + sign word + ELL topology in, grad_x out; excludes the 256 B/node hop-level spill it writes for k_tag_gw")
-        kernels["k_tag_tc3<FWD> (TAG forward, tcgen05, TMA-fed)"] = (lambda: _lib.check(lib.dss2_tag_fwd_tc2(
-            gref, P(x_l), wp, bp, 32, sp.K, 1, sp.p_drop, 1, P(trainer.step_state), 3, None, None, 0, P(y_l), P(bits_l), st_()), "fwd"),
-            nt * (128 + 128 + 4 + 24), "x + ELL topology in, y + sign word out")
-        in_step = " [in the step]"
-        kernels["k_tag_gw (TAG weight gradients, tcgen05 MN-major, TMA ring)" + (in_step if _ops.GW_IMPL == "tc" else " [alternative]")] = (
-            lambda: _lib.check(lib.dss2_tag_bwd_tc2_gw(
-                nt, P(x_l), 32, sp.K, 1, sp.p_drop, P(bits_l), P(gy_l), part_w, run.flat_size, b_off - w_off, P(lvl), lvl.numel() * 4, st_()), "gw"),
-            nt * (128 + 128 + 4), "x + grad_y + sign word in; excludes the 256 B/node hop levels it re-reads")
-        kernels["k_tag_gw_ffma (TAG weight gradients, exact fp32 FFMA, TMA ring)" + (in_step if _ops.GW_IMPL != "tc" else " [alternative]")] = (
-            lambda: _lib.check(lib.dss2_tag_gw_ffma(
-                nt, P(x_l), 32, sp.K, 1, sp.p_drop, P(bits_l), P(gy_l), part_w, run.flat_size, b_off - w_off, P(lvl), lvl.numel() * 4, st_()), "gwf"),
-            nt * (128 + 128 + 4), "x + grad_y + sign word in; excludes the 256 B/node hop levels it re-reads")
-    elif tiled:
-        kernels["k_tag_bwd<2,32> (TAG backward, CUDA cores)"] = (lambda: _lib.check(lib.dss2_tag_bwd(
-            gref, P(x_l), wp, 32, sp.K, 1, sp.p_drop, P(bits_l), P(gy_l), P(gx_l), part_w, run.flat_size, b_off - w_off, st_()), "bwd"),
-            nt * (3 * 128 + 4) + 4 * (nt + 1) + 16 * et, "x, grad_y in, grad_x out, sign word, CSR")
-        kernels["k_tag_fwd<2> (TAG forward, CUDA cores)"] = (lambda: _lib.check(lib.dss2_tag_fwd(
-            gref, P(x_l), wp, bp, 32, sp.K, 1, sp.p_drop, 1, P(trainer.step_state), 3, None, None, 0, P(y_l), P(bits_l), st_()), "fwd"),
-            nt * (2 * 128 + 4) + 4 * (nt + 1) + 16 * et, "x in, y out, sign word, CSR")
+    if args.network == "skippfn":   # per-kernel roofline of the SkipPFN step (GAT / GINE: thread-per-bus kernels, whole-step figure only)
+        # ---- layer kernels timed live on the launching stream (hidden layer 32 -> 32, K = 2, the shapes of 35 of the 40 TAG layers) ----
+        lib, P = _lib.load(), _lib.ptr
+        from dss2 import ops as _ops
+        sp, run, bufs = trainer.spec, trainer.runner, trainer.bufs
+        nt, et = trainer.nt, trainer.et
+        name_w, name_b = "mpns.0.convs.3.lins.0.weight", "mpns.0.convs.3.bias"
+        w_off, b_off = run.table[name_w][0], run.table[name_b][0]
+        part_w = ctypes.c_void_p(bufs["partials"].data_ptr() + 4 * w_off)
+        gref, st_ = trainer.graph.ref, _lib.stream
+        x_l, y_l, bits_l = bufs["acts"][0, 3], bufs["acts"][0, 4], bufs["bits"][0, 3]
+        gy_l, gx_l, lvl = bufs["g32"][0], bufs["g32"][1], bufs["lvl"]
+        wp, bp = run._p(trainer.flat, name_w), run._p(trainer.flat, name_b)
+        tiled = trainer.graph.c.num_tiles > 0
+        tc2 = tiled and _ops.TAG_IMPL == "tc2" and bool(lib.dss2_tag_tc2_supported(gref, sp.K))
+        kernels = {}
+        if tc2:
+            kernels["k_tag_tc3<BGX> (TAG backward-to-input, tcgen05, TMA-fed)"] = (lambda: _lib.check(lib.dss2_tag_bwd_tc2_gx(
+                gref, wp, 32, sp.K, 1, sp.p_drop, P(bits_l), P(gy_l), P(gx_l), P(lvl), lvl.numel() * 4, st_()), "gx"),
+                nt * (128 + 128 + 4 + 24), "grad_y + sign word + ELL topology in, grad_x out; excludes the 256 B/node hop-level spill it writes for k_tag_gw")
+            kernels["k_tag_tc3<FWD> (TAG forward, tcgen05, TMA-fed)"] = (lambda: _lib.check(lib.dss2_tag_fwd_tc2(
+                gref, P(x_l), wp, bp, 32, sp.K, 1, sp.p_drop, 1, P(trainer.step_state), 3, None, None, 0, P(y_l), P(bits_l), st_()), "fwd"),
+                nt * (128 + 128 + 4 + 24), "x + ELL topology in, y + sign word out")
+            in_step = " [in the step]"
+            kernels["k_tag_gw (TAG weight gradients, tcgen05 MN-major, TMA ring)" + (in_step if _ops.GW_IMPL == "tc" else " [alternative]")] = (
+                lambda: _lib.check(lib.dss2_tag_bwd_tc2_gw(
+                    nt, P(x_l), 32, sp.K, 1, sp.p_drop, P(bits_l), P(gy_l), part_w, run.flat_size, b_off - w_off, P(lvl), lvl.numel() * 4, st_()), "gw"),
+                nt * (128 + 128 + 4), "x + grad_y + sign word in; excludes the 256 B/node hop levels it re-reads")
+            kernels["k_tag_gw_ffma (TAG weight gradients, exact fp32 FFMA, TMA ring)" + (in_step if _ops.GW_IMPL != "tc" else " [alternative]")] = (
+                lambda: _lib.check(lib.dss2_tag_gw_ffma(
+                    nt, P(x_l), 32, sp.K, 1, sp.p_drop, P(bits_l), P(gy_l), part_w, run.flat_size, b_off - w_off, P(lvl), lvl.numel() * 4, st_()), "gwf"),
+                nt * (128 + 128 + 4), "x + grad_y + sign word in; excludes the 256 B/node hop levels it re-reads")
+        elif tiled:
+            kernels["k_tag_bwd<2,32> (TAG backward, CUDA cores)"] = (lambda: _lib.check(lib.dss2_tag_bwd(
+                gref, P(x_l), wp, 32, sp.K, 1, sp.p_drop, P(bits_l), P(gy_l), P(gx_l), part_w, run.flat_size, b_off - w_off, st_()), "bwd"),
+                nt * (3 * 128 + 4) + 4 * (nt + 1) + 16 * et, "x, grad_y in, grad_x out, sign word, CSR")
+            kernels["k_tag_fwd<2> (TAG forward, CUDA cores)"] = (lambda: _lib.check(lib.dss2_tag_fwd(
+                gref, P(x_l), wp, bp, 32, sp.K, 1, sp.p_drop, 1, P(trainer.step_state), 3, None, None, 0, P(y_l), P(bits_l), st_()), "fwd"),
+                nt * (2 * 128 + 4) + 4 * (nt + 1) + 16 * et, "x in, y out, sign word, CSR")
 
-    # EdgeAggregation of sub-net 1 (input = the previous sub-net's 8-wide output, gradient to the input and skip path needed)
-    pre1 = "mpns.1.edge_aggr.edge_aggr."
-    ea_w = [run._p(trainer.flat, pre1 + n_) for n_ in ("0.weight", "0.bias", "2.weight", "2.bias")]
-    ea_part = ctypes.c_void_p(bufs["partials"].data_ptr() + 4 * run.table[pre1 + "0.weight"][0])
-    x_in, eattr = bufs["outs"][0], trainer.batch["edge_attr"]
-    ea_fwd_bytes = 32 * nt + 52 * et + 16 * et + 128 * nt
-    kernels["k_edgeagg_fwd (EdgeAggregation forward)"] = (lambda: _lib.check(lib.dss2_edgeagg_fwd(
-        gref, P(x_in), sp.fn, sp.fn, P(eattr), 13, sp.fe, *ea_w, P(bufs["acts"][1, 0]), st_()), "ea_fwd"),
-        ea_fwd_bytes, "SURVEY 8(d): x row 32 + out row 128 per bus, edge_attr row 52 + edge_index 16 per branch")
-    kernels["k_edgeagg_bwd (EdgeAggregation backward: grad_x + parameter gradients)"] = (lambda: _lib.check(lib.dss2_edgeagg_bwd(
-        gref, P(x_in), sp.fn, sp.fn, P(eattr), 13, sp.fe, *ea_w, P(gy_l), P(bufs["gsub"][0]), sp.fn, P(bufs["gsub"][1]), ea_part,
-        run.flat_size, st_()), "ea_bwd"),
-        ea_fwd_bytes + 32 * nt, "SURVEY 8(d): forward bytes with grad_out in place of out, + grad_x row 32 per bus")
+        # EdgeAggregation of sub-net 1 (input = the previous sub-net's 8-wide output, gradient to the input and skip path needed)
+        pre1 = "mpns.1.edge_aggr.edge_aggr."
+        ea_w = [run._p(trainer.flat, pre1 + n_) for n_ in ("0.weight", "0.bias", "2.weight", "2.bias")]
+        ea_part = ctypes.c_void_p(bufs["partials"].data_ptr() + 4 * run.table[pre1 + "0.weight"][0])
+        x_in, eattr = bufs["outs"][0], trainer.batch["edge_attr"]
+        ea_fwd_bytes = 32 * nt + 52 * et + 16 * et + 128 * nt
+        kernels["k_edgeagg_fwd (EdgeAggregation forward)"] = (lambda: _lib.check(lib.dss2_edgeagg_fwd(
+            gref, P(x_in), sp.fn, sp.fn, P(eattr), 13, sp.fe, *ea_w, P(bufs["acts"][1, 0]), st_()), "ea_fwd"),
+            ea_fwd_bytes, "SURVEY 8(d): x row 32 + out row 128 per bus, edge_attr row 52 + edge_index 16 per branch")
+        kernels["k_edgeagg_bwd (EdgeAggregation backward: grad_x + parameter gradients)"] = (lambda: _lib.check(lib.dss2_edgeagg_bwd(
+            gref, P(x_in), sp.fn, sp.fn, P(eattr), 13, sp.fe, *ea_w, P(gy_l), P(bufs["gsub"][0]), sp.fn, P(bufs["gsub"][1]), ea_part,
+            run.flat_size, st_()), "ea_bwd"),
+            ea_fwd_bytes + 32 * nt, "SURVEY 8(d): forward bytes with grad_out in place of out, + grad_x row 32 per bus")
 
-    # the fused loss (2 kernels: reduction pass + gradient pass), on the trainer's own buffers
-    kernels["k_wls<false>+k_wls<true> (branch flows + WLS loss, forward and backward)"] = (lambda: _lib.check(lib.dss2_wls_fwd_bwd(
-        gref, P(trainer.batch["x"]), 11, P(trainer.batch["edge_attr"]), 13, P(bufs["outs"][-1]), P(trainer.stats), REG["lam_v"], REG["lam_p"],
-        REG["lam_pf"], REG["lam_reg"], P(trainer.batch["vminmax"]), 1, P(trainer.loss), None, P(trainer.grad_out), P(trainer.wls_ws),
-        trainer.wls_ws.numel(), st_()), "wls"), 60 * nt + 68 * et,
-        "SURVEY 8(d), fused forward+backward: x row 44 + out 8 + grad_out 8 per bus, edge_attr row 52 + edge_index 16 per branch, counted ONCE "
-        "(the two passes of the kernel pair re-read them; the second read mostly hits L2)")
-    # the batch packer (PyG collate): reads the selected scenarios, writes the batch
-    from dss2.batching import launch_pack as _launch_pack
-    kernels["k_pack_scan+k_pack_copy (batch packer = PyG collate)"] = (
-        lambda: _launch_pack(trainer.store, trainer.ids, trainer.batch, nt, et), 2 * (44 * nt + 52 * et + 8 * nt) + 16 * et + 8 * nt,
-        "x 44 + y 8 per bus and edge_attr 52 per branch read and written, edge_index 16 per branch and batch vector 8 per bus written")
+        # the fused loss (2 kernels: reduction pass + gradient pass), on the trainer's own buffers
+        kernels["k_wls<false>+k_wls<true> (branch flows + WLS loss, forward and backward)"] = (lambda: _lib.check(lib.dss2_wls_fwd_bwd(
+            gref, P(trainer.batch["x"]), 11, P(trainer.batch["edge_attr"]), 13, P(bufs["outs"][-1]), P(trainer.stats), REG["lam_v"], REG["lam_p"],
+            REG["lam_pf"], REG["lam_reg"], P(trainer.batch["vminmax"]), 1, P(trainer.loss), None, P(trainer.grad_out), P(trainer.wls_ws),
+            trainer.wls_ws.numel(), st_()), "wls"), 60 * nt + 68 * et,
+            "SURVEY 8(d), fused forward+backward: x row 44 + out 8 + grad_out 8 per bus, edge_attr row 52 + edge_index 16 per branch, counted ONCE "
+            "(the two passes of the kernel pair re-read them; the second read mostly hits L2)")
+        # the batch packer (PyG collate): reads the selected scenarios, writes the batch
+        from dss2.batching import launch_pack as _launch_pack
+        kernels["k_pack_scan+k_pack_copy (batch packer = PyG collate)"] = (
+            lambda: _launch_pack(trainer.store, trainer.ids, trainer.batch, nt, et), 2 * (44 * nt + 52 * et + 8 * nt) + 16 * et + 8 * nt,
+            "x 44 + y 8 per bus and edge_attr 52 per branch read and written, edge_index 16 per branch and batch vector 8 per bus written")
 
-    def time_kernel(fn, reps=30):
-        flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # 256 MB > 126 MB L2
-        durs = []
-        for _ in range(3):
-            fn()
-        for _ in range(reps):
-            flush.zero_()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            fn()
-            b.record()
-            b.synchronize()
-            durs.append(a.elapsed_time(b))
-        return statistics.mean(durs) * 1e-3
+        def time_kernel(fn, reps=30):
+            flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # 256 MB > 126 MB L2
+            durs = []
+            for _ in range(3):
+                fn()
+            for _ in range(reps):
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn()
+                b.record()
+                b.synchronize()
+                durs.append(a.elapsed_time(b))
+            return statistics.mean(durs) * 1e-3
 
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    traffic_tab = {}
-    tpath = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
-    if os.path.exists(tpath):
-        traffic_tab = json.load(open(tpath))
-    n_tag = sp.L * sp.n_layers
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        traffic_tab = {}
+        tpath = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
+        if os.path.exists(tpath):
+            traffic_tab = json.load(open(tpath))
+        n_tag = sp.L * sp.n_layers
 
-    def launches_per_step(kname):   # how often the step launches this kernel (shape of the timed launch: hidden layer / sub-net 1)
-        if kname.startswith("k_tag_"):
-            return n_tag
-        return sp.L if kname.startswith("k_edgeagg") else 1
+        def launches_per_step(kname):   # how often the step launches this kernel (shape of the timed launch: hidden layer / sub-net 1)
+            if kname.startswith("k_tag_"):
+                return n_tag
+            return sp.L if kname.startswith("k_edgeagg") else 1
 
-    timed = []
-    for kname, (fn, nbytes, what) in kernels.items():
-        t = time_kernel(fn)
-        timed.append({"kernel": kname, "us_per_launch": t * 1e6, "launches_per_step": launches_per_step(kname),
-                      "algorithmic_bytes_per_launch": nbytes, "bytes_counted": what,
-                      "achieved": nbytes / t / 1e9, "frac": nbytes / t / 1e9 / peak, "traffic": traffic_tab.get(kname.split(" ")[0])})
-    # dominant = largest share of the step (duration x launches per step)
-    dom = max((r for r in timed if "[alternative]" not in r["kernel"]), key=lambda r: r["us_per_launch"] * r["launches_per_step"])
-    roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": peak, "unit": "GB/s", "frac": dom["frac"],
-                "traffic": dom["traffic"], "peak_source": peak_src, "us_per_launch": dom["us_per_launch"],
-                "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"], "bytes_counted": dom["bytes_counted"],
-                "note": "layer kernels are bound by the per-tile dependency chain (shared-memory gathers, barriers, tcgen05 issue), not by HBM: "
-                        "see DESIGN.md section 4 and profiles/",
-                "all_layer_kernels": timed}
-    # whole-step view with SURVEY.md 8(d)'s per-layer algorithmic bytes (topology counted as 0: per-topology template)
-    hid, fn = 32, sp.fn
-    step_bytes = 60 * nt + 68 * et                                           # fused loss
-    for s_ in range(sp.L):
-        cin0 = 44 if s_ == 0 else 4 * fn                                     # EdgeAggregation reads the 11-wide x rows in sub-net 0
-        step_bytes += (cin0 * nt + 52 * et + 16 * et + 4 * hid * nt) + (cin0 * nt + 52 * et + 16 * et + 4 * hid * nt + (4 * fn * nt if s_ else 0))
-        for l_ in range(sp.n_layers):
-            cout_ = (sp.dim_out if s_ == sp.L - 1 else fn) if l_ == sp.n_layers - 1 else hid
-            step_bytes += 4 * nt * (hid + cout_) + 4 * nt * (2 * hid + cout_)  # TAG forward + recompute-style backward
-    roofline["step"] = {"algorithmic_bytes_per_step": step_bytes, "achieved": step_bytes / (ms_total / K / 1e3) / 1e9, "unit": "GB/s",
-                        "frac": step_bytes / (ms_total / K / 1e3) / 1e9 / peak,
-                        "definition": "SURVEY.md 8(d): loss 60 Nt + 68 Et; EdgeAggregation fwd+bwd; TAG 4 Nt (Cin+Cout) fwd + 4 Nt (2 Cin+Cout) bwd per layer"}
+        timed = []
+        for kname, (fn, nbytes, what) in kernels.items():
+            t = time_kernel(fn)
+            timed.append({"kernel": kname, "us_per_launch": t * 1e6, "launches_per_step": launches_per_step(kname),
+                          "algorithmic_bytes_per_launch": nbytes, "bytes_counted": what,
+                          "achieved": nbytes / t / 1e9, "frac": nbytes / t / 1e9 / peak, "traffic": traffic_tab.get(kname.split(" ")[0])})
+        # dominant = largest share of the step (duration x launches per step)
+        dom = max((r for r in timed if "[alternative]" not in r["kernel"]), key=lambda r: r["us_per_launch"] * r["launches_per_step"])
+        roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": peak, "unit": "GB/s", "frac": dom["frac"],
+                    "traffic": dom["traffic"], "peak_source": peak_src, "us_per_launch": dom["us_per_launch"],
+                    "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"], "bytes_counted": dom["bytes_counted"],
+                    "note": "layer kernels are bound by the per-tile dependency chain (shared-memory gathers, barriers, tcgen05 issue), not by HBM: "
+                            "see DESIGN.md section 4 and profiles/",
+                    "all_layer_kernels": timed}
+        # whole-step view with SURVEY.md 8(d)'s per-layer algorithmic bytes (topology counted as 0: per-topology template)
+        hid, fn = 32, sp.fn
+        step_bytes = 60 * nt + 68 * et                                           # fused loss
+        for s_ in range(sp.L):
+            cin0 = 44 if s_ == 0 else 4 * fn                                     # EdgeAggregation reads the 11-wide x rows in sub-net 0
+            step_bytes += (cin0 * nt + 52 * et + 16 * et + 4 * hid * nt) + (cin0 * nt + 52 * et + 16 * et + 4 * hid * nt + (4 * fn * nt if s_ else 0))
+            for l_ in range(sp.n_layers):
+                cout_ = (sp.dim_out if s_ == sp.L - 1 else fn) if l_ == sp.n_layers - 1 else hid
+                step_bytes += 4 * nt * (hid + cout_) + 4 * nt * (2 * hid + cout_)  # TAG forward + recompute-style backward
+        roofline["step"] = {"algorithmic_bytes_per_step": step_bytes, "achieved": step_bytes / (ms_total / K / 1e3) / 1e9, "unit": "GB/s",
+                            "frac": step_bytes / (ms_total / K / 1e3) / 1e9 / peak,
+                            "definition": "SURVEY.md 8(d): loss 60 Nt + 68 Et; EdgeAggregation fwd+bwd; TAG 4 Nt (Cin+Cout) fwd + 4 Nt (2 Cin+Cout) bwd per layer"}
 
     # ---- end to end through the host-buffer API: pinned host scenarios -> H2D -> step -> D2H loss, all inside the timed region ----
     e2e = None
@@ -525,7 +529,7 @@ def main():
                               max_nodes=n, max_edges=e)
         stage.x.copy_(store.x[:SB * n])
         stage.edge_attr.copy_(store.edge_attr[:SB * e])
-        t2 = GraphedTrainer(stage, B, spec=default_spec(), reg_coefs=REG, seed=0, process_group=pg, world_size=world,
+        t2 = GraphedTrainer(stage, B, spec=spec, reg_coefs=REG, seed=0, process_group=pg, world_size=world, network=args.network,
                             use_cuda_graph=not args.no_graph).capture()
         nbuf = max(1, min(4, args.scenarios // B))
         host_x = [store.x[i * B * n:(i + 1) * B * n].cpu().pin_memory() for i in range(nbuf)]

@@ -26,14 +26,34 @@ def default_spec(p_drop=0.3, L=5, n_layers=8, K=2, dim_out=2, fn=8, fe=6):
                    skip=tuple(s < L - 1 for s in range(L)), prefix_fmt="mpns.{s}.")
 
 
+def make_runner(network, spec=None):
+    """(runner, spec, torch module factory) of a model family: 'skippfn' (any PFNSpec: MPN / SkipMPN / PFN / SkipPFN), 'gat' = GAT_DSSE
+    (the script's as-shipped model, dss2_run.py:86), 'gine' = GINE_DSSE.  All three runners share forward / backward over static buffers
+    and a flat parameter buffer whose first `flat_size` floats are the parameters."""
+    if network == "skippfn":
+        spec = spec or default_spec()
+        return PFNRunner(spec), spec
+    if network == "gat":
+        from .gat import GATRunner, GATSpec
+        spec = spec or GATSpec(dim_feat=8, dim_dense=32, dim_out=2, num_layers=8, edge_dim=6)
+        return GATRunner(spec), spec
+    if network == "gine":
+        from .gine import GINERunner, GINESpec
+        spec = spec or GINESpec(dim_feat=8, dim_dense=32, dim_out=2, num_layers=8, edge_dim=6)
+        return GINERunner(spec), spec
+    raise ValueError(f"GraphedTrainer: unknown network {network!r}")
+
+
 class GraphedTrainer:
     def __init__(self, store, batch_graphs, spec=None, reg_coefs=None, lr=3e-3, seed=0, init_state_dict=None,
-                 process_group=None, world_size=1, use_cuda_graph=True, dropout_stream=None):
+                 process_group=None, world_size=1, use_cuda_graph=True, dropout_stream=None, network="skippfn"):
         """seed: parameter initialisation (all ranks must agree; rank 0's parameters are broadcast anyway).
         dropout_stream: index of this replica's dropout stream (default: its rank, so that every shard draws its own masks;
-        pass the same value on all ranks to reproduce a single-GPU run on identical shards)."""
+        pass the same value on all ranks to reproduce a single-GPU run on identical shards).
+        network: 'skippfn' (default, any PFNSpec), 'gat', 'gine' - see make_runner."""
         self.lib = _lib.load()
-        self.spec = spec or default_spec()
+        self.network = network
+        self.runner, self.spec = make_runner(network, spec)
         self.store = store
         self.B = int(batch_graphs)
         self.dev = store.x.device
@@ -45,7 +65,6 @@ class GraphedTrainer:
         self.lr = float(lr)
         rc = reg_coefs or {"lam_v": 1e-4, "lam_p": 1e-8, "lam_pf": 1e-6, "lam_reg": 1e2}   # dss2_run.py:104-112
         self.coefs = (float(rc["lam_v"]), float(rc["lam_p"]), float(rc["lam_pf"]), float(rc["lam_reg"]))
-        self.runner = PFNRunner(self.spec)
         n, e = store.max_nodes, store.max_edges
         self.nt, self.et = self.B * n, self.B * e
         f32 = dict(dtype=torch.float32, device=self.dev)
@@ -54,7 +73,8 @@ class GraphedTrainer:
             # parameters: same init distribution as the reference modules, one flat buffer
             self.flat = torch.zeros(self.runner.flat_size, **f32)
             self._init_params(seed, init_state_dict)
-            self.flat_grad = torch.zeros_like(self.flat)
+            # gradient buffer: the parameters' gradients first; GINE keeps per-layer shares of its shared Linear behind them
+            self.flat_grad = torch.zeros(getattr(self.runner, "grad_size", self.runner.flat_size), **f32)
             self.exp_avg = torch.zeros_like(self.flat)
             self.exp_inf = torch.zeros_like(self.flat)
             rank = torch.distributed.get_rank(process_group) if (self.world > 1 and torch.distributed.is_initialized()) else 0
@@ -88,6 +108,21 @@ class GraphedTrainer:
     # ---- parameters ----
     def _init_params(self, seed, sd):
         table = self.runner.table
+        if sd is None and self.network != "skippfn":   # the drop-in module's own initialisation (PyG's glorot / zeros, torch's Linear)
+            import sys, os
+            pkg = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+            if pkg not in sys.path:
+                sys.path.insert(0, pkg)
+            import networks
+            sp = self.spec
+            torch.manual_seed(seed)
+            if self.network == "gat":
+                m = networks.GAT_DSSE(dim_feat=sp.dim_feat, dim_dense=sp.dim_dense, dim_out=sp.dim_out, heads=1, num_layers=sp.num_layers,
+                                      edge_dim=sp.edge_dim, slope=sp.att_slope, self_loops=sp.self_loops, nonlin=sp.act)
+            else:
+                m = networks.GINE_DSSE(dim_feat=sp.dim_feat, dim_dense=sp.dim_dense, dim_out=sp.dim_out, num_layers=sp.num_layers,
+                                       edge_dim=sp.edge_dim, eps=sp.eps, train_eps=sp.train_eps)
+            sd = {k: v.detach() for k, v in m.named_parameters()}
         if sd is None:
             import math
             g = torch.Generator().manual_seed(seed)
@@ -105,6 +140,8 @@ class GraphedTrainer:
         return 2 * self.spec.fn + self.spec.fe if "edge_aggr.0" in name else self.spec.hid
 
     def state_dict(self):
+        if self.network != "skippfn":
+            return {name: self.flat[off:off + n].clone() for name, (off, n) in self.runner.table.items()}
         return {name: self.flat[off:off + n].view(shape).clone()
                 for (name, shape), (off, n) in zip(self.spec.param_names(), self.runner.table.values())}
 
@@ -113,14 +150,20 @@ class GraphedTrainer:
         lib, st = self.lib, _lib.stream()
         b = self.batch
         launch_pack(self.store, self.ids, b, self.nt, self.et)
-        out = self.runner.forward(self.graph, b["x"], 11, b["edge_attr"], 13, self.flat, self.bufs,
-                                  drop_mode=1 if self.spec.p_drop > 0 else 0, rng_state=self.step_state)
+        if self.network == "skippfn":
+            out = self.runner.forward(self.graph, b["x"], 11, b["edge_attr"], 13, self.flat, self.bufs,
+                                      drop_mode=1 if self.spec.p_drop > 0 else 0, rng_state=self.step_state)
+        else:
+            out = self.runner.forward(self.graph, b["x"], 11, b["edge_attr"], 13, self.flat, self.bufs)
         _lib.check(lib.dss2_wls_fwd_bwd(self.graph.ref, _lib.ptr(b["x"]), 11, _lib.ptr(b["edge_attr"]), 13, _lib.ptr(out),
                                         _lib.ptr(self.stats), *self.coefs, _lib.ptr(b["vminmax"]), 1, _lib.ptr(self.loss), None,
                                         _lib.ptr(self.grad_out), _lib.ptr(self.wls_ws), self.wls_ws.numel(), st), "dss2_wls_fwd_bwd")
-        self.runner.backward(self.graph, b["x"], 11, b["edge_attr"], 13, self.flat, self.bufs, self.grad_out, self.flat_grad, ea_uploaded=True)
+        if self.network == "skippfn":
+            self.runner.backward(self.graph, b["x"], 11, b["edge_attr"], 13, self.flat, self.bufs, self.grad_out, self.flat_grad, ea_uploaded=True)
+        else:
+            self.runner.backward(self.graph, b["x"], 11, b["edge_attr"], 13, self.flat, self.bufs, self.grad_out, self.flat_grad)
         if self.world > 1:
-            torch.distributed.all_reduce(self.flat_grad, group=self.pg)
+            torch.distributed.all_reduce(self.flat_grad[:self.flat.numel()], group=self.pg)
         if with_optimizer:
             _lib.check(lib.dss2_adamax_step(_lib.ptr(self.flat), _lib.ptr(self.flat_grad), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_inf),
                                             self.flat.numel(), self.lr, 0.9, 0.999, 1e-8, 1.0 / self.world, _lib.ptr(self.step_state), 1,
