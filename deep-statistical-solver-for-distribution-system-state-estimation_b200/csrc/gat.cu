@@ -458,6 +458,70 @@ __global__ void __launch_bounds__(OR_THREADS) k_outer_reduce(int64_t num_rows, c
   }
 }
 
+// The same reduction for narrow operands (ca, cb <= 8: every GATv2 / GINE / gnn_dsse layer): thread = bus row, the row's 8 x 9 outer
+// product accumulates in registers over the rows the thread owns (grid-stride), then ONE fixed-order reduction per CTA: butterfly inside
+// the warps, the 8 warp totals summed in warp order.  No shared-memory staging and two barriers per launch instead of two per 64 rows.
+__global__ void __launch_bounds__(OR_THREADS) k_outer_reduce8(int64_t num_rows, const float* __restrict__ A, int64_t as, int ca,
+                                                              const float* __restrict__ B, int64_t bs, int cb, float* partials,
+                                                              int64_t partial_stride, int64_t w_off, int64_t b_off) {
+  __shared__ float red[OR_THREADS / 32][8 * 9];
+  float acc[8][9];
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+#pragma unroll
+    for (int i = 0; i < 9; ++i) acc[c][i] = 0.0f;
+  const bool a_vec = ca == 8 && (as & 3) == 0 && (((uintptr_t)A) & 15) == 0, b_vec = cb == 8 && (bs & 3) == 0 && (((uintptr_t)B) & 15) == 0;
+  for (int64_t n = blockIdx.x * (int64_t)OR_THREADS + threadIdx.x; n < num_rows; n += (int64_t)gridDim.x * OR_THREADS) {
+    float a[8], b[8];
+    const float *pa = A + n * as, *pb = B + n * bs;
+    if (a_vec) {
+      const float4 u = *reinterpret_cast<const float4*>(pa), v = *reinterpret_cast<const float4*>(pa + 4);
+      a[0] = u.x, a[1] = u.y, a[2] = u.z, a[3] = u.w, a[4] = v.x, a[5] = v.y, a[6] = v.z, a[7] = v.w;
+    } else {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) a[c] = c < ca ? pa[c] : 0.0f;
+    }
+    if (b_vec) {
+      const float4 u = *reinterpret_cast<const float4*>(pb), v = *reinterpret_cast<const float4*>(pb + 4);
+      b[0] = u.x, b[1] = u.y, b[2] = u.z, b[3] = u.w, b[4] = v.x, b[5] = v.y, b[6] = v.z, b[7] = v.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) b[i] = i < cb ? pb[i] : 0.0f;
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[c][i] = fmaf(a[c], b[i], acc[c][i]);
+      acc[c][8] += a[c];
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c < 8; ++c)
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      const float v = warp_sum(acc[c][i]);
+      if (lane == 0) red[warp][c * 9 + i] = v;
+    }
+  __syncthreads();
+  float* part = partials + (size_t)blockIdx.x * partial_stride;
+  for (int o = threadIdx.x; o < ca * (cb + 1); o += OR_THREADS) {
+    const int c = o / (cb + 1), i = o % (cb + 1);
+    float s = 0.0f;
+#pragma unroll
+    for (int w = 0; w < OR_THREADS / 32; ++w) s += red[w][c * 9 + (i < cb ? i : 8)];
+    if (i < cb) part[w_off + (int64_t)c * cb + i] = s;
+    else part[b_off + c] = s;
+  }
+}
+
+// launches the outer-product reduction that fits the operand widths
+static void launch_outer_reduce(int np, cudaStream_t stream, int64_t num_rows, const float* A, int64_t as, int ca, const float* B, int64_t bs, int cb,
+                                float* partials, int64_t partial_stride, int64_t w_off, int64_t b_off) {
+  if (ca <= 8 && cb <= 8) k_outer_reduce8<<<np, OR_THREADS, 0, stream>>>(num_rows, A, as, ca, B, bs, cb, partials, partial_stride, w_off, b_off);
+  else k_outer_reduce<<<np, OR_THREADS, 0, stream>>>(num_rows, A, as, ca, B, bs, cb, partials, partial_stride, w_off, b_off);
+}
+
 // ---- head: z = W2 (W1 x + b1) + b2 (no non-linearity in between, networks.py:150-151) ----
 constexpr int MLP_MAX = 32;
 struct MlpArgs {
@@ -1014,10 +1078,10 @@ extern "C" int dss2_gat_bwd(const dss2_graph_t* g, const float* x, int64_t x_str
   k_gat_bwd<<<np, GAT_THREADS, 0, stream>>>(a);
   DSS2_LAUNCH_CHECK();
   // d W_l | d b_l and d W_r | d b_r from the stored node adjoints (columns 20..27 and 28..35 of the workspace)
-  k_outer_reduce<<<np, OR_THREADS, 0, stream>>>(g->num_nodes, node_ws + 20, GAT_NODE_WS, GC, x, x_stride, GC, partials, partial_stride, 0,
+  launch_outer_reduce(np, stream, g->num_nodes, node_ws + 20, GAT_NODE_WS, GC, x, x_stride, GC, partials, partial_stride, 0,
                                                 GC * GC);
   DSS2_LAUNCH_CHECK();
-  k_outer_reduce<<<np, OR_THREADS, 0, stream>>>(g->num_nodes, node_ws + 28, GAT_NODE_WS, GC, x, x_stride, GC, partials, partial_stride,
+  launch_outer_reduce(np, stream, g->num_nodes, node_ws + 28, GAT_NODE_WS, GC, x, x_stride, GC, partials, partial_stride,
                                                 GC * GC + GC, 2 * GC * GC + GC);
   DSS2_LAUNCH_CHECK();
   return 0;
@@ -1108,7 +1172,7 @@ extern "C" int dss2_gine_bwd_ex(const dss2_graph_t* g, const float* x, int64_t x
   k_gine_bwd_b<<<np, GAT_THREADS, 0, stream>>>(a);
   DSS2_LAUNCH_CHECK();
   // d W_nn | d b_nn = sum_n g[n] (x) [h[n], 1]
-  k_outer_reduce<<<np, OR_THREADS, 0, stream>>>(g->num_nodes, node_ws, GINE_NODE_WS, GC, node_ws + 16, GINE_NODE_WS, GC, partials_nn,
+  launch_outer_reduce(np, stream, g->num_nodes, node_ws, GINE_NODE_WS, GC, node_ws + 16, GINE_NODE_WS, GC, partials_nn,
                                                 partial_stride, 0, GC * GC);
   DSS2_LAUNCH_CHECK();
   return 0;
@@ -1165,9 +1229,9 @@ extern "C" int dss2_mlp2_bwd(int64_t num_nodes, const float* x, int din, const f
   DSS2_LAUNCH_CHECK();
   const int np = dss2_num_partials();
   const int64_t o_w1 = 0, o_b1 = (int64_t)dmid * din, o_w2 = o_b1 + dmid, o_b2 = o_w2 + (int64_t)dout * dmid;
-  k_outer_reduce<<<np, OR_THREADS, 0, stream>>>(num_nodes, grad_h_ws, dmid, dmid, x, din, din, partials, partial_stride, o_w1, o_b1);
+  launch_outer_reduce(np, stream, num_nodes, grad_h_ws, dmid, dmid, x, din, din, partials, partial_stride, o_w1, o_b1);
   DSS2_LAUNCH_CHECK();
-  k_outer_reduce<<<np, OR_THREADS, 0, stream>>>(num_nodes, grad_z, dout, dout, h, dmid, dmid, partials, partial_stride, o_w2, o_b2);
+  launch_outer_reduce(np, stream, num_nodes, grad_z, dout, dout, h, dmid, dmid, partials, partial_stride, o_w2, o_b2);
   DSS2_LAUNCH_CHECK();
   return 0;
 }
@@ -1267,10 +1331,10 @@ extern "C" int dss2_lin8_bwd(int64_t num_nodes, int M, int weight_is_out_by_in, 
   for (int m = 0; m < M; ++m) {
     // Linear weight [out c][in j]: sum_n gz[n][c] in[n][j];  GCN2Conv weight1 [in j][out c]: sum_n in[n][j] gz[n][c]
     if (weight_is_out_by_in)
-      k_outer_reduce<<<np, OR_THREADS, 0, stream>>>(num_nodes, grad_z, GC, GC, in[m], in_strides[m], GC, partials, partial_stride, (int64_t)m * GC * GC,
+      launch_outer_reduce(np, stream, num_nodes, grad_z, GC, GC, in[m], in_strides[m], GC, partials, partial_stride, (int64_t)m * GC * GC,
                                                     bias_offset);
     else
-      k_outer_reduce<<<np, OR_THREADS, 0, stream>>>(num_nodes, in[m], in_strides[m], GC, grad_z, GC, GC, partials, partial_stride, (int64_t)m * GC * GC,
+      launch_outer_reduce(np, stream, num_nodes, in[m], in_strides[m], GC, grad_z, GC, GC, partials, partial_stride, (int64_t)m * GC * GC,
                                                     bias_offset);
     DSS2_LAUNCH_CHECK();
   }
