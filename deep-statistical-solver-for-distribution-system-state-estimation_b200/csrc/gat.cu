@@ -458,35 +458,43 @@ __global__ void __launch_bounds__(OR_THREADS) k_outer_reduce(int64_t num_rows, c
   }
 }
 
-// The same reduction for narrow operands (ca, cb <= 8: every GATv2 / GINE / gnn_dsse layer): thread = bus row, the row's 8 x 9 outer
-// product accumulates in registers over the rows the thread owns (grid-stride), then ONE fixed-order reduction per CTA: butterfly inside
-// the warps, the 8 warp totals summed in warp order.  No shared-memory staging and two barriers per launch instead of two per 64 rows.
+// The same reduction with register accumulators: a warp owns one 8 x 8 block (ba, bb) of the [ca, cb] product (ca, cb <= 32, the number
+// of blocks a power of two <= 8: every GATv2 / GINE / gnn_dsse layer is one block, the head's two Linears are 4 blocks each) and a slice
+// of the rows; thread = bus row, the row's 8 x 9 outer product (column 8 = the bias sum, block column 0 only) accumulates in registers
+// over the rows the thread owns, then ONE fixed-order reduction per CTA: butterfly inside the warps, the warp totals of a block summed in
+// warp order.  No shared-memory staging, two barriers per launch instead of two per 64 rows.
 __global__ void __launch_bounds__(OR_THREADS) k_outer_reduce8(int64_t num_rows, const float* __restrict__ A, int64_t as, int ca,
                                                               const float* __restrict__ B, int64_t bs, int cb, float* partials,
                                                               int64_t partial_stride, int64_t w_off, int64_t b_off) {
-  __shared__ float red[OR_THREADS / 32][8 * 9];
+  constexpr int NW = OR_THREADS / 32;
+  __shared__ float red[NW][8 * 9];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nba = (ca + 7) >> 3, nbb = (cb + 7) >> 3, nblk = nba * nbb, nsl = NW / nblk;   // nblk in {1, 2, 4, 8}
+  const int blk = warp % nblk, sl = warp / nblk, ba = blk / nbb, bb = blk % nbb;
+  const int ca0 = 8 * ba, cb0 = 8 * bb, nca = min(8, ca - ca0), ncb = min(8, cb - cb0);
   float acc[8][9];
 #pragma unroll
   for (int c = 0; c < 8; ++c)
 #pragma unroll
     for (int i = 0; i < 9; ++i) acc[c][i] = 0.0f;
-  const bool a_vec = ca == 8 && (as & 3) == 0 && (((uintptr_t)A) & 15) == 0, b_vec = cb == 8 && (bs & 3) == 0 && (((uintptr_t)B) & 15) == 0;
-  for (int64_t n = blockIdx.x * (int64_t)OR_THREADS + threadIdx.x; n < num_rows; n += (int64_t)gridDim.x * OR_THREADS) {
+  const bool a_vec = nca == 8 && (as & 3) == 0 && (((uintptr_t)A) & 15) == 0, b_vec = ncb == 8 && (bs & 3) == 0 && (((uintptr_t)B) & 15) == 0;
+  const int64_t rows_per_pass = (int64_t)gridDim.x * nsl * 32;
+  for (int64_t n = ((int64_t)blockIdx.x * nsl + sl) * 32 + lane; n < num_rows; n += rows_per_pass) {
     float a[8], b[8];
-    const float *pa = A + n * as, *pb = B + n * bs;
+    const float *pa = A + n * as + ca0, *pb = B + n * bs + cb0;
     if (a_vec) {
       const float4 u = *reinterpret_cast<const float4*>(pa), v = *reinterpret_cast<const float4*>(pa + 4);
       a[0] = u.x, a[1] = u.y, a[2] = u.z, a[3] = u.w, a[4] = v.x, a[5] = v.y, a[6] = v.z, a[7] = v.w;
     } else {
 #pragma unroll
-      for (int c = 0; c < 8; ++c) a[c] = c < ca ? pa[c] : 0.0f;
+      for (int c = 0; c < 8; ++c) a[c] = c < nca ? pa[c] : 0.0f;
     }
     if (b_vec) {
       const float4 u = *reinterpret_cast<const float4*>(pb), v = *reinterpret_cast<const float4*>(pb + 4);
       b[0] = u.x, b[1] = u.y, b[2] = u.z, b[3] = u.w, b[4] = v.x, b[5] = v.y, b[6] = v.z, b[7] = v.w;
     } else {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) b[i] = i < cb ? pb[i] : 0.0f;
+      for (int i = 0; i < 8; ++i) b[i] = i < ncb ? pb[i] : 0.0f;
     }
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
@@ -495,7 +503,6 @@ __global__ void __launch_bounds__(OR_THREADS) k_outer_reduce8(int64_t num_rows, 
       acc[c][8] += a[c];
     }
   }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int c = 0; c < 8; ++c)
 #pragma unroll
@@ -507,9 +514,10 @@ __global__ void __launch_bounds__(OR_THREADS) k_outer_reduce8(int64_t num_rows, 
   float* part = partials + (size_t)blockIdx.x * partial_stride;
   for (int o = threadIdx.x; o < ca * (cb + 1); o += OR_THREADS) {
     const int c = o / (cb + 1), i = o % (cb + 1);
+    const int ib = i < cb ? i : 0;                       // the bias column lives in block column 0
+    const int b_ = (c >> 3) * nbb + (ib >> 3);
     float s = 0.0f;
-#pragma unroll
-    for (int w = 0; w < OR_THREADS / 32; ++w) s += red[w][c * 9 + (i < cb ? i : 8)];
+    for (int w = 0; w < nsl; ++w) s += red[w * nblk + b_][(c & 7) * 9 + (i < cb ? (i & 7) : 8)];
     if (i < cb) part[w_off + (int64_t)c * cb + i] = s;
     else part[b_off + c] = s;
   }
@@ -518,8 +526,11 @@ __global__ void __launch_bounds__(OR_THREADS) k_outer_reduce8(int64_t num_rows, 
 // launches the outer-product reduction that fits the operand widths
 static void launch_outer_reduce(int np, cudaStream_t stream, int64_t num_rows, const float* A, int64_t as, int ca, const float* B, int64_t bs, int cb,
                                 float* partials, int64_t partial_stride, int64_t w_off, int64_t b_off) {
-  if (ca <= 8 && cb <= 8) k_outer_reduce8<<<np, OR_THREADS, 0, stream>>>(num_rows, A, as, ca, B, bs, cb, partials, partial_stride, w_off, b_off);
-  else k_outer_reduce<<<np, OR_THREADS, 0, stream>>>(num_rows, A, as, ca, B, bs, cb, partials, partial_stride, w_off, b_off);
+  const int nblk = ((ca + 7) / 8) * ((cb + 7) / 8);
+  if (ca <= 32 && cb <= 32 && (nblk == 1 || nblk == 2 || nblk == 4 || nblk == 8))
+    k_outer_reduce8<<<np, OR_THREADS, 0, stream>>>(num_rows, A, as, ca, B, bs, cb, partials, partial_stride, w_off, b_off);
+  else
+    k_outer_reduce<<<np, OR_THREADS, 0, stream>>>(num_rows, A, as, ca, B, bs, cb, partials, partial_stride, w_off, b_off);
 }
 
 // ---- head: z = W2 (W1 x + b1) + b2 (no non-linearity in between, networks.py:150-151) ----

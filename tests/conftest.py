@@ -91,7 +91,7 @@ def split_masks(masks, ctor):
     return [masks[i * per:(i + 1) * per] for i in range(len(masks) // per)]
 
 
-def assert_fp32_parity(ours, ref32, ref64, what="", rtol=1e-5, noise_mult=4.0):
+def assert_fp32_parity(ours, ref32, ref64, what="", rtol=1e-5, noise_mult=4.0, sum_of=None):
     """The fp32 parity criterion used throughout (hard part 1).
 
     `ref32` is the reference result in fp32, `ref64` the same computation in fp64 (the arbiter).  Two
@@ -100,7 +100,11 @@ def assert_fp32_parity(ours, ref32, ref64, what="", rtol=1e-5, noise_mult=4.0):
     max(rtol * scale, noise_mult * |ref32 - ref64|_max): i.e. within `rtol` relative, or no worse than
     `noise_mult` times the reference's own fp32 rounding error on that tensor.  (noise_mult = 4: entries such as the
     last-layer theta-bias gradient are sums of +-1e3-sized terms that cancel to ~0; ours and the reference's result are two
-    draws of the same rounding noise, and a ratio of 2-3 between two draws is ordinary.)"""
+    draws of the same rounding noise, and a ratio of 2-3 between two draws is ordinary.)
+
+    sum_of: when the tensor IS a plain sum of given terms over their first axis (a bias gradient = column sum of the upstream gradient
+    over the buses), pass the terms: the scale of the rtol criterion is then max_c sum_n |term[n, c]| - the forward error bound of a
+    floating-point sum is relative to the sum of the magnitudes, not to a result the terms may cancel to."""
     ours = torch.as_tensor(ours).double().cpu()
     ref64 = torch.as_tensor(ref64).double().cpu()
     # `ref32` may be a list of fp32 evaluations of the reference that are equally valid (e.g. the same batch with its edge list in
@@ -108,6 +112,8 @@ def assert_fp32_parity(ours, ref32, ref64, what="", rtol=1e-5, noise_mult=4.0):
     refs = ref32 if isinstance(ref32, (list, tuple)) else [ref32]
     refs = [torch.as_tensor(r).double().cpu() for r in refs]
     scale = float(ref64.abs().max()) if ref64.numel() else 0.0
+    if sum_of is not None:
+        scale = max(scale, float(torch.as_tensor(sum_of).double().abs().sum(0).max()))
     noise = max(float((r - ref64).abs().max()) for r in refs) if ref64.numel() else 0.0
     err = float((ours - ref64).abs().max()) if ref64.numel() else 0.0
     # the noise term is only meaningful when the reference's fp32 result and the fp64 oracle describe the SAME computation: if they

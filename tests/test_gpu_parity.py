@@ -1160,7 +1160,9 @@ def test_gat_dsse_matches_reference_run(env, tag, where):
         (orc.gat_dsse_forward(pp, x.cpu().to(dt)[:, :8], ei.cpu(), ea.cpu().to(dt)[:, :6], nl, **opts) * go.to(dt)).sum().backward()
         lin[dt] = {k: v.grad for k, v in pp.items()}
     for name, p in model.named_parameters():
-        assert_fp32_parity(p.grad, lin[torch.float32][name], lin[torch.float64][name], name + " (recorded grad_out)")
+        # the head's last bias gradient is the plain column sum of the recorded grad_out over the buses: judged as a sum (conftest)
+        last_bias = name == f"model.module_{2 * (nl - 1) + 1}.bias"
+        assert_fp32_parity(p.grad, lin[torch.float32][name], lin[torch.float64][name], name + " (recorded grad_out)", sum_of=go if last_bias else None)
 
 
 def test_gat_layer_input_gradient_and_self_loops(env):
@@ -1314,7 +1316,9 @@ def test_gnn_dsse_matches_reference_run(env, tag, where):
         (orc.gnn_dsse_forward(pp, xr, ei.cpu(), nl, model=kind, K=K) * go.to(dt)).sum().backward()
         lin[dt] = ({k: v.grad for k, v in pp.items()}, xr.grad)
     for name, p in model.named_parameters():
-        assert_fp32_parity(p.grad, lin[torch.float32][0][name], lin[torch.float64][0][name], name + " (recorded grad_out)")
+        last_bias = name == f"model.module_{2 * (nl - 1) + 1}.bias"     # = the column sum of the recorded grad_out: judged as a sum
+        assert_fp32_parity(p.grad, lin[torch.float32][0][name], lin[torch.float64][0][name], name + " (recorded grad_out)",
+                           sum_of=go if last_bias else None)
     assert_fp32_parity(xin.grad, lin[torch.float32][1], lin[torch.float64][1], "grad_x (recorded grad_out)")
 
 
@@ -1472,7 +1476,9 @@ def test_gine_dsse_matches_reference_run(env, tag, where):
         (orc.gine_dsse_forward(pp, x.cpu().to(dt)[:, :8], ei.cpu(), ea.cpu().to(dt)[:, :6], nl) * go.to(dt)).sum().backward()
         lin[dt] = {k: v.grad for k, v in pp.items()}
     for name, p in model.named_parameters():
-        assert_fp32_parity(p.grad, lin[torch.float32][name], lin[torch.float64][name], name + " (recorded grad_out)")
+        # the head's last bias gradient is the plain column sum of the recorded grad_out over the buses: judged as a sum (conftest)
+        last_bias = name == f"model.module_{2 * (nl - 1) + 1}.bias"
+        assert_fp32_parity(p.grad, lin[torch.float32][name], lin[torch.float64][name], name + " (recorded grad_out)", sum_of=go if last_bias else None)
 
 
 def test_gine_layer_input_gradient_and_self_loops(env):
