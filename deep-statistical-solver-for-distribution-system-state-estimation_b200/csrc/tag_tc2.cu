@@ -6,7 +6,7 @@
 // non-GEMM work ~4x (gathers are LDS.128 of whole neighbour rows, the epilogue needs no ballots or broadcasts), and the three
 // 32x32 transforms stay on the tensor core (3xTF32, accumulators in TMEM).
 //
-//   k_tag_tc2<FWD>  y = sum_k (A^k x) W_k^T + b, dropout, ReLU, sign word, residual                 (replaces k_tag_fwd / k_tag_fwd_tc)
+//   k_tag_tc2<FWD>  y = sum_k (A^k x) W_k^T + b, dropout, ReLU, sign word, residual                 (replaces k_tag_fwd; the first tcgen05 version, k_tag_fwd_tc, was removed in round 2)
 //   k_tag_tc2<BGX>  grad_x = sum_k (A^k g) W_k with g = grad_y * [y>0]/(1-p): hops commute with the right-multiplication and A is
 //                   symmetric on the doubled graph, so the backward-to-input is the SAME kernel with transposed weights; it also
 //                   stores A g and A^2 g for the weight-gradient kernel

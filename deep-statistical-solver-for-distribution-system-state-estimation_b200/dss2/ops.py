@@ -15,8 +15,7 @@ MAX_EA_SLOTS = 7   # constant-memory slots of the prepared-weights EdgeAggregati
 HID = _lib.HID
 # which TAG-layer kernels the runner launches (all are CUDA; there is no CPU path):
 #   "ffma": CUDA-core forward and backward (tag.cu)
-#   "tc"  : first tcgen05 forward (tag_tc.cu), CUDA-core backward
-#   "tc2" : second-generation tcgen05 forward AND backward (tag_tc2.cu); tiles of up to 256 rows (two MMA blocks)
+#   "tc2" : tcgen05 forward AND backward (tag_tc3.cu TMA-fed, tag_tc2.cu direct loads); tiles of up to 256 rows (two MMA blocks)
 # Unsupported shapes (K = 3, oversize tiles) fall back to the CUDA-core kernels.
 TAG_IMPL = os.environ.get("DSS2_TAG_IMPL", "tc2")
 # weight-gradient pass behind the tc2 backward: "tc" = tcgen05 3xTF32 GEMM (68.7 us on the bench layer), "ffma" = exact fp32 streaming
@@ -150,7 +149,6 @@ class PFNRunner:
         masks: optional [L][n_layers-1] uint8 [Nt,32] tensors (drop_mode 2).  Returns bufs['outs'][-1]."""
         sp, lib, st = self.spec, self.lib, _lib.stream()
         g = graph.ref
-        use_tc = TAG_IMPL == "tc" and bool(lib.dss2_tag_fwd_tc_supported(g, sp.K))
         use_tc2 = TAG_IMPL == "tc2" and bool(lib.dss2_tag_tc2_supported(g, sp.K))
         slots = self.ea_slots(graph, x_stride, ea_stride)
         if slots:
@@ -173,7 +171,7 @@ class PFNRunner:
                 if not last and drop_mode == 2:
                     mask = masks[s][l]
                 res, rs = (xin, xs) if (last and sp.skip[s]) else (None, 0)
-                fwd = lib.dss2_tag_fwd_tc2 if use_tc2 else (lib.dss2_tag_fwd_tc if use_tc else lib.dss2_tag_fwd)
+                fwd = lib.dss2_tag_fwd_tc2 if use_tc2 else lib.dss2_tag_fwd
                 _lib.check(fwd(g, _lib.ptr(bufs["acts"][s, l]), self._p(flat, pre + f"convs.{l}.lins.0.weight"),
                                self._p(flat, pre + f"convs.{l}.bias"), cout, sp.K, 0 if last else 1, sp.p_drop, mode,
                                _lib.ptr(rng_state), s * sp.n_layers + l, _lib.ptr(mask), _lib.ptr(res), rs,

@@ -154,16 +154,8 @@ int dss2_tag_fwd(const dss2_graph_t* g, const float* x, const float* w, const fl
                  const uint8_t* mask, const float* res, int64_t res_stride,
                  float* y, uint32_t* act_bits, void* stream);
 
-/* Same contract as dss2_tag_fwd, with the (K+1) 32x32 transforms on the 5th-generation tensor cores (tcgen05.mma kind::tf32,
- * 3xTF32 split = fp32-equivalent accuracy, accumulators in TMEM) and a thread-per-row epilogue.  The dropout stream differs
- * from dss2_tag_fwd's (both are functions of (seed, step, layer, node) only).  dss2_tag_fwd_tc_supported() != 0 when the
- * graph is tiled, K <= 2 and a tile fits the 227 KB of shared memory; otherwise use dss2_tag_fwd. */
-int dss2_tag_fwd_tc_supported(const dss2_graph_t* g, int K);
-int dss2_tag_fwd_tc(const dss2_graph_t* g, const float* x, const float* w, const float* bias, int cout, int K,
-                    int act, float p_drop, int drop_mode, const uint64_t* rng_state, uint32_t layer_uid,
-                    const uint8_t* mask, const float* res, int64_t res_stride,
-                    float* y, uint32_t* act_bits, void* stream);
-/* Second/third-generation tensor-core layer kernels (thread = (row, half row); A operand in tensor memory; tiled graphs with
+/* Tensor-core layer kernels: the (K+1) 32x32 transforms on tcgen05 (kind::tf32, 3xTF32 split = fp32-equivalent accuracy, accumulators in
+ * TMEM), thread = (row, half row), A operand in tensor memory; tiled graphs with
  * tile_cap <= 256 and K <= 2).  Forward: same contract as dss2_tag_fwd.  Backward: same contract as dss2_tag_bwd plus a workspace of
  * dss2_tag_bwd_tc2_workspace_bytes() for the hop levels of the masked output gradient; it runs the backward-to-input as the forward
  * kernel with transposed weights (grad_x = sum_k (A^k g) W_k) and the weight gradients as one streaming MN-major GEMM

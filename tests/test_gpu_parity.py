@@ -725,13 +725,13 @@ def _tag_fwd_direct(env, fn_name, graph, x, w, bias, cout, K, act, p, mode, rng,
 
 @pytest.mark.parametrize("case,nb", [("ober_sub", 7), ("cigre14", 40), ("ober_sub", 1)])
 @pytest.mark.parametrize("cout,act,mode", [(32, 1, 2), (32, 1, 0), (8, 0, 0), (2, 0, 0), (5, 0, 0)])
-@pytest.mark.parametrize("fwd_fn", ["dss2_tag_fwd_tc2", "dss2_tag_fwd_tc"])
+@pytest.mark.parametrize("fwd_fn", ["dss2_tag_fwd_tc2"])
 def test_tag_fwd_tensor_core_matches_cuda_core_kernel(env, case, nb, cout, act, mode, fwd_fn):
     """tcgen05 forward == CUDA-core forward (same masks) within fp32 noise; identical sign words wherever |y| is not ~0."""
     b = _small_batch(env, case, nb, seed=21)
     graph = b.edge_index._dss2_graph
     K = 2
-    assert env["lib"].load().dss2_tag_fwd_tc_supported(graph.ref, K) == 1
+    assert env["lib"].load().dss2_tag_tc2_supported(graph.ref, K) == 1
     gen = torch.Generator(device="cuda").manual_seed(cout * 7 + nb)
     nt = b.x.size(0)
     x = torch.randn(nt, 32, device="cuda", generator=gen)
@@ -808,13 +808,13 @@ def _tie_aware_model_check(env, tag, impl, noise_mult=4.0, large_graph=False, ed
         os.environ.pop("DSS2_DENSE_TC", None)
 
 
-@pytest.mark.parametrize("impl", ["tc2", "tc", "ffma"])
+@pytest.mark.parametrize("impl", ["tc2", "ffma"])
 @pytest.mark.parametrize("tag", ["skippfn_cigre", "skippfn_ober", "pfn_small_cigre", "mpn_cigre", "skipmpn_cigre"])
 def test_model_kernels_match_reference_run_tie_aware(env, tag, impl):
     _tie_aware_model_check(env, tag, impl)
 
 
-@pytest.mark.parametrize("impl", ["tc", "tc2", "ffma"])
+@pytest.mark.parametrize("impl", ["tc2", "ffma"])
 def test_philox_dropout_statistics_tensor_core(env, monkeypatch, impl):
     monkeypatch.setattr(env["ops"], "TAG_IMPL", impl)
     test_philox_dropout_statistics_and_replay(env)
