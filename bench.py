@@ -69,6 +69,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="ober", choices=sorted(CONFIGS), help="BASELINE.json config (default: the headline, Oberrhein B=4096)")
+    ap.add_argument("--exact-global-batch", action="store_true",
+                    help="N > 1: train on ONE batch of N*B scenarios exactly (loss sums all-reduced between the loss passes, gradients summed) "
+                         "instead of the default DDP mean of per-shard gradients")
     ap.add_argument("--network", "--model", dest="network", default="skippfn", choices=sorted(NETWORKS))
     ap.add_argument("--mode", default="train", choices=["train", "infer"])
     ap.add_argument("--batch", type=int, default=None)
@@ -352,7 +355,8 @@ def main():
     n, e = store.max_nodes, store.max_edges
     spec = default_spec() if args.network == "skippfn" else None      # gat / gine: the constructor arguments of dss2_run.py:73-86
     trainer = GraphedTrainer(store, B, spec=spec, reg_coefs=REG, seed=0, process_group=pg, world_size=world, network=args.network,
-                             use_cuda_graph=not args.no_graph, dropout_stream=0 if args.same_shards else None).capture()
+                             use_cuda_graph=not args.no_graph, dropout_stream=0 if args.same_shards else None,
+                             exact_global_batch=args.exact_global_batch).capture()
     gen = torch.Generator().manual_seed(99 + shard)
     ids_host = torch.randint(0, args.scenarios, (W + K, B), generator=gen).pin_memory()
 
@@ -436,13 +440,23 @@ def main():
         ea_part = ctypes.c_void_p(bufs["partials"].data_ptr() + 4 * run.table[pre1 + "0.weight"][0])
         x_in, eattr = bufs["outs"][0], trainer.batch["edge_attr"]
         ea_fwd_bytes = 32 * nt + 52 * et + 16 * et + 128 * nt
-        kernels["k_edgeagg_fwd (EdgeAggregation forward)"] = (lambda: _lib.check(lib.dss2_edgeagg_fwd(
-            gref, P(x_in), sp.fn, sp.fn, P(eattr), 13, sp.fe, *ea_w, P(bufs["acts"][1, 0]), st_()), "ea_fwd"),
-            ea_fwd_bytes, "SURVEY 8(d): x row 32 + out row 128 per bus, edge_attr row 52 + edge_index 16 per branch")
-        kernels["k_edgeagg_bwd (EdgeAggregation backward: grad_x + parameter gradients)"] = (lambda: _lib.check(lib.dss2_edgeagg_bwd(
-            gref, P(x_in), sp.fn, sp.fn, P(eattr), 13, sp.fe, *ea_w, P(gy_l), P(bufs["gsub"][0]), sp.fn, P(bufs["gsub"][1]), ea_part,
-            run.flat_size, st_()), "ea_bwd"),
-            ea_fwd_bytes + 32 * nt, "SURVEY 8(d): forward bytes with grad_out in place of out, + grad_x row 32 per bus")
+        if run.ea_slots(trainer.graph, 11, 13):   # the step's path: weights prepared once per step, thread-per-row kernels read slot 1
+            run.ea_upload(trainer.flat)
+            kernels["k_ea_row_fwd (EdgeAggregation forward, thread per bus, FFMA2)"] = (lambda: _lib.check(lib.dss2_edgeagg_fwd_slot(
+                gref, P(x_in), sp.fn, sp.fn, P(eattr), 13, sp.fe, 1, P(bufs["acts"][1, 0]), st_()), "ea_fwd"),
+                ea_fwd_bytes, "SURVEY 8(d): x row 32 + out row 128 per bus, edge_attr row 52 + edge_index 16 per branch")
+            kernels["k_ea_row_bwd (EdgeAggregation backward: grad_x + parameter gradients)"] = (lambda: _lib.check(lib.dss2_edgeagg_bwd_slot(
+                gref, P(x_in), sp.fn, sp.fn, P(eattr), 13, sp.fe, 1, P(gy_l), P(bufs["gsub"][0]), sp.fn, P(bufs["gsub"][1]), ea_part,
+                run.flat_size, st_()), "ea_bwd"),
+                ea_fwd_bytes + 32 * nt, "SURVEY 8(d): forward bytes with grad_out in place of out, + grad_x row 32 per bus")
+        else:
+            kernels["k_edgeagg_fwd (EdgeAggregation forward)"] = (lambda: _lib.check(lib.dss2_edgeagg_fwd(
+                gref, P(x_in), sp.fn, sp.fn, P(eattr), 13, sp.fe, *ea_w, P(bufs["acts"][1, 0]), st_()), "ea_fwd"),
+                ea_fwd_bytes, "SURVEY 8(d): x row 32 + out row 128 per bus, edge_attr row 52 + edge_index 16 per branch")
+            kernels["k_edgeagg_bwd (EdgeAggregation backward: grad_x + parameter gradients)"] = (lambda: _lib.check(lib.dss2_edgeagg_bwd(
+                gref, P(x_in), sp.fn, sp.fn, P(eattr), 13, sp.fe, *ea_w, P(gy_l), P(bufs["gsub"][0]), sp.fn, P(bufs["gsub"][1]), ea_part,
+                run.flat_size, st_()), "ea_bwd"),
+                ea_fwd_bytes + 32 * nt, "SURVEY 8(d): forward bytes with grad_out in place of out, + grad_x row 32 per bus")
 
         # the fused loss (2 kernels: reduction pass + gradient pass), on the trainer's own buffers
         kernels["k_wls<false>+k_wls<true> (branch flows + WLS loss, forward and backward)"] = (lambda: _lib.check(lib.dss2_wls_fwd_bwd(
@@ -486,7 +500,7 @@ def main():
         def launches_per_step(kname):   # how often the step launches this kernel (shape of the timed launch: hidden layer / sub-net 1)
             if kname.startswith("k_tag_"):
                 return n_tag
-            return sp.L if kname.startswith("k_edgeagg") else 1
+            return sp.L if kname.startswith(("k_edgeagg", "k_ea_row")) else 1
 
         timed = []
         for kname, (fn, nbytes, what) in kernels.items():
@@ -530,7 +544,7 @@ def main():
         stage.x.copy_(store.x[:SB * n])
         stage.edge_attr.copy_(store.edge_attr[:SB * e])
         t2 = GraphedTrainer(stage, B, spec=spec, reg_coefs=REG, seed=0, process_group=pg, world_size=world, network=args.network,
-                            use_cuda_graph=not args.no_graph).capture()
+                            use_cuda_graph=not args.no_graph, exact_global_batch=args.exact_global_batch).capture()
         nbuf = max(1, min(4, args.scenarios // B))
         host_x = [store.x[i * B * n:(i + 1) * B * n].cpu().pin_memory() for i in range(nbuf)]
         host_ea = [store.edge_attr[i * B * e:(i + 1) * B * e].cpu().pin_memory() for i in range(nbuf)]
@@ -593,6 +607,8 @@ def main():
             "impl_detail": {"cuda_graph": not args.no_graph, "tag_impl": _ops.TAG_IMPL, "tiled": bool(tiled),
                             "tc3": os.environ.get("DSS2_TC3", "1") != "0"},
             "loss_trajectory_sha256_16": loss_sha, "data_parallel_check": sync,
+            "data_parallel_mode": ("exact global batch (loss sums all-reduced between the loss passes, gradients summed)" if args.exact_global_batch
+                                   else "mean of per-shard gradients (DDP semantics)") if world > 1 else None,
             "e2e": e2e, "gpu_launches": int(trainer.launches_per_step) * K, "launches_per_step": int(trainer.launches_per_step),
             "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.result(), "final_loss": loss_end,
         }

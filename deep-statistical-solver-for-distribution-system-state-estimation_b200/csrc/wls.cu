@@ -38,7 +38,8 @@ struct WlsArgs {
   float* grad_out;
   double* partial;     // [grid][S_N]
   unsigned* counter;
-  double* sums;        // [S_N]
+  double* sums;        // [S_N] batch sums, then [5] = bus count, [6] = branch count they were taken over
+  int global_batch;    // pass 2 only: sums[0..6] describe the GLOBAL batch (all-reduced over the data-parallel ranks between the passes)
 };
 
 __device__ __forceinline__ WlsBranchIn load_branch(const float* row, const float* s_v, const float* s_th, int i, int j) {
@@ -87,11 +88,18 @@ __global__ void __launch_bounds__(WLS_TILE_THREADS) k_wls(WlsArgs a) {
   float cN = 0.f, cE = 0.f, mv = 0.f, mth = 0.f, ml = 0.f;
   if (BWD) {
     float gl = a.grad_loss ? a.grad_loss[0] : 1.0f;
-    cN = gl / (float)Nt;
-    cE = gl / (float)Et;
-    mv = (float)(a.sums[S_V] / (double)Nt);
-    mth = (float)(a.sums[S_TH] / (double)Et);
-    ml = (float)(a.sums[S_LOAD] / (double)Et);
+    // exact-global-batch data parallelism (data.py:450-455 on the union of all ranks' batches): the means and the 1/N, 1/E factors of the
+    // gradient come from the all-reduced sums and counts; every rank then holds its buses' share of the global gradient
+    const double Ng = a.global_batch ? a.sums[5] : (double)Nt, Eg = a.global_batch ? a.sums[6] : (double)Et;
+    cN = gl / (float)Ng;
+    cE = gl / (float)Eg;
+    mv = (float)(a.sums[S_V] / Ng);
+    mth = (float)(a.sums[S_TH] / Eg);
+    ml = (float)(a.sums[S_LOAD] / Eg);
+    if (a.global_batch && blockIdx.x == 0 && tid == 0) {   // the loss of the global batch, identical on every rank
+      const double jv = a.sums[S_V] / Ng, jt = a.sums[S_TH] / Eg, jl = a.sums[S_LOAD] / Eg, lam = (double)k.lam_reg;
+      a.loss[0] = (float)(a.sums[S_JN] / Ng + a.sums[S_JE] / Eg + lam * jv * jv + lam * jt * jt + lam * jl * jl);
+    }
   }
 
   for (int t = blockIdx.x; t < g.num_tiles; t += gridDim.x) {
@@ -253,6 +261,8 @@ __global__ void __launch_bounds__(WLS_TILE_THREADS) k_wls(WlsArgs a) {
         double jv = s_red[S_V][0] / n, jt = s_red[S_TH][0] / e, jl = s_red[S_LOAD][0] / e;
         double lam = (double)k.lam_reg;
         a.loss[0] = (float)(s_red[S_JN][0] / n + s_red[S_JE][0] / e + lam * jv * jv + lam * jt * jt + lam * jl * jl);
+        a.sums[5] = n;   // the counts travel with the sums (exact-global-batch mode all-reduces all seven)
+        a.sums[6] = e;
         *a.counter = 0;  // ready for the next launch / graph replay
       }
     }
@@ -694,10 +704,37 @@ extern "C" size_t dss2_wls_workspace_bytes(const dss2_graph_t* g) {
   return (size_t)(dss2_sm_count() * WLS_TILE_CTAS_PER_SM) * S_N * sizeof(double) + 256 + 16 * sizeof(double);
 }
 
+static int wls_launch(int phase, const dss2_graph_t* g, const float* x, int64_t x_stride, const float* edge_attr, int64_t ea_stride, float* output,
+                      const float* stats, float lam_v, float lam_p, float lam_pf, float lam_reg, const float* vminmax, int mask_inplace, float* loss,
+                      const float* grad_loss, float* grad_out, void* ws, size_t ws_bytes, void* stream_);
+
 extern "C" int dss2_wls_fwd_bwd(const dss2_graph_t* g, const float* x, int64_t x_stride, const float* edge_attr,
                                 int64_t ea_stride, float* output, const float* stats, float lam_v, float lam_p, float lam_pf,
                                 float lam_reg, const float* vminmax, int mask_inplace, float* loss, const float* grad_loss,
                                 float* grad_out, void* ws, size_t ws_bytes, void* stream_) {
+  return wls_launch(0, g, x, x_stride, edge_attr, ea_stride, output, stats, lam_v, lam_p, lam_pf, lam_reg, vminmax, mask_inplace, loss, grad_loss,
+                    grad_out, ws, ws_bytes, stream_);
+}
+
+// Exact-global-batch data parallelism (data.py:450-455): phase 1 = the reduction pass only; it leaves seven doubles at
+// dss2_wls_sums(ws): the five batch sums (bus residual, branch residual, voltage-band, angle and loading penalties) and the bus / branch
+// counts.  The caller sum-all-reduces those seven over the ranks IN PLACE, then phase 2 = the gradient pass with the global means and
+// 1/N, 1/E factors (it also overwrites *loss with the loss of the global batch).  Summing the ranks' parameter gradients afterwards
+// gives the gradient of ONE batch that is the union of the ranks' batches.  Tiled batches only.
+extern "C" double* dss2_wls_sums(void* ws) { return (double*)((char*)ws + 256); }
+extern "C" int dss2_wls_pass(int phase, const dss2_graph_t* g, const float* x, int64_t x_stride, const float* edge_attr, int64_t ea_stride,
+                             float* output, const float* stats, float lam_v, float lam_p, float lam_pf, float lam_reg, const float* vminmax,
+                             int mask_inplace, float* loss, const float* grad_loss, float* grad_out, void* ws, size_t ws_bytes, void* stream_) {
+  DSS2_CHECK_ARG(phase == 1 || phase == 2, "dss2_wls_pass: phase must be 1 (reduction pass) or 2 (gradient pass on all-reduced sums)");
+  DSS2_CHECK_ARG(g && g->num_tiles > 0, "dss2_wls_pass: the split passes serve tiled batches only");
+  DSS2_CHECK_ARG(phase == 1 || grad_out, "dss2_wls_pass: phase 2 needs grad_out");
+  return wls_launch(phase, g, x, x_stride, edge_attr, ea_stride, output, stats, lam_v, lam_p, lam_pf, lam_reg, vminmax, mask_inplace, loss, grad_loss,
+                    grad_out, ws, ws_bytes, stream_);
+}
+
+static int wls_launch(int phase, const dss2_graph_t* g, const float* x, int64_t x_stride, const float* edge_attr, int64_t ea_stride, float* output,
+                      const float* stats, float lam_v, float lam_p, float lam_pf, float lam_reg, const float* vminmax, int mask_inplace, float* loss,
+                      const float* grad_loss, float* grad_out, void* ws, size_t ws_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   DSS2_CHECK_ARG(g && x && edge_attr && output && stats && vminmax && loss && ws, "dss2_wls_fwd_bwd: null argument");
   DSS2_CHECK_ARG(g->undirected == 1, "dss2_wls_fwd_bwd: needs a graph built from the one-way edge list with undirect=1");
@@ -717,6 +754,7 @@ extern "C" int dss2_wls_fwd_bwd(const dss2_graph_t* g, const float* x, int64_t x
   a.loss = loss;
   a.grad_loss = grad_loss;
   a.grad_out = grad_out;
+  a.global_batch = phase == 2;
   int grid = wls_grid_size(g);
   char* base = (char*)ws;
   a.counter = (unsigned*)base;                       // zero-initialised by the caller once; self-resetting
@@ -732,9 +770,11 @@ extern "C" int dss2_wls_fwd_bwd(const dss2_graph_t* g, const float* x, int64_t x
     DSS2_CUDA(cudaFuncSetAttribute(k_wls<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DSS2_CUDA(cudaFuncSetAttribute(k_wls<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
-  k_wls<false><<<grid, WLS_TILE_THREADS, smem, stream>>>(a);
-  DSS2_LAUNCH_CHECK();
-  if (grad_out) {
+  if (phase != 2) {
+    k_wls<false><<<grid, WLS_TILE_THREADS, smem, stream>>>(a);
+    DSS2_LAUNCH_CHECK();
+  }
+  if (grad_out && phase != 1) {
     k_wls<true><<<grid, WLS_TILE_THREADS, smem, stream>>>(a);
     DSS2_LAUNCH_CHECK();
   }

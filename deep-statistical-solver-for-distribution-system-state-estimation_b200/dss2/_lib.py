@@ -57,6 +57,9 @@ _SIGNATURES = {
     "dss2_wls_workspace_bytes": (c_size_t, [_G]),
     "dss2_wls_fwd_bwd": (c_int, [_G, _P, c_int64, _P, c_int64, _P, _P, c_float, c_float, c_float, c_float, _P, c_int, _P, _P, _P,
                                  _P, c_size_t, _P]),
+    "dss2_wls_pass": (c_int, [c_int, _G, _P, c_int64, _P, c_int64, _P, _P, c_float, c_float, c_float, c_float, _P, c_int, _P, _P, _P,
+                                 _P, c_size_t, _P]),
+    "dss2_wls_sums": (ctypes.c_void_p, [_P]),
     "dss2_edgeagg_slots_ok": (c_int, [_G, c_int64, c_int64, c_int]),
     "dss2_edgeagg_upload": (c_int, [c_int, c_int, _P, _P, _P, _P, c_int, c_int, _P]),
     "dss2_edgeagg_fwd_slot": (c_int, [_G, _P, c_int64, c_int, _P, c_int64, c_int, c_int, _P, _P]),

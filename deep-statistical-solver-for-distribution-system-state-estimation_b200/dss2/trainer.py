@@ -46,11 +46,14 @@ def make_runner(network, spec=None):
 
 class GraphedTrainer:
     def __init__(self, store, batch_graphs, spec=None, reg_coefs=None, lr=3e-3, seed=0, init_state_dict=None,
-                 process_group=None, world_size=1, use_cuda_graph=True, dropout_stream=None, network="skippfn"):
+                 process_group=None, world_size=1, use_cuda_graph=True, dropout_stream=None, network="skippfn", exact_global_batch=False):
         """seed: parameter initialisation (all ranks must agree; rank 0's parameters are broadcast anyway).
         dropout_stream: index of this replica's dropout stream (default: its rank, so that every shard draws its own masks;
         pass the same value on all ranks to reproduce a single-GPU run on identical shards).
-        network: 'skippfn' (default, any PFNSpec), 'gat', 'gine' - see make_runner."""
+        network: 'skippfn' (default, any PFNSpec), 'gat', 'gine' - see make_runner.
+        exact_global_batch (world_size > 1): the R ranks train on ONE batch of R*B scenarios exactly - the loss's batch sums and counts are
+        all-reduced between the two loss passes (7 doubles) and the parameter gradients are summed; default (False) = DDP semantics, the mean
+        of the ranks' per-shard gradients (the loss squares batch means, data.py:453-455, so the two differ)."""
         self.lib = _lib.load()
         self.network = network
         self.runner, self.spec = make_runner(network, spec)
@@ -62,6 +65,7 @@ class GraphedTrainer:
         if store.x.size(0) != store.num_scenarios * store.max_nodes:
             raise _lib.Dss2Error("GraphedTrainer needs a uniform-topology store (static batch shapes)")
         self.pg, self.world = process_group, int(world_size)
+        self.exact = bool(exact_global_batch) and self.world > 1
         self.lr = float(lr)
         rc = reg_coefs or {"lam_v": 1e-4, "lam_p": 1e-8, "lam_pf": 1e-6, "lam_reg": 1e2}   # dss2_run.py:104-112
         self.coefs = (float(rc["lam_v"]), float(rc["lam_p"]), float(rc["lam_pf"]), float(rc["lam_reg"]))
@@ -101,6 +105,10 @@ class GraphedTrainer:
             from .ops import tile_cap
             self.graph = BatchGraph(self.batch["edge_index"], self.nt, ptr=self.batch["ptr"], undirect=1, tile_cap=tile_cap())
             self.wls_ws = self.graph.wls_workspace()
+            # the seven doubles the reduction pass of the loss leaves in its workspace (5 batch sums, bus count, branch count)
+            self.wls_sums = self.wls_ws.view(torch.uint8)[256:256 + 56].view(torch.float64)
+            if self.exact and self.graph.c.num_tiles == 0:
+                raise _lib.Dss2Error("GraphedTrainer(exact_global_batch=True) serves tiled batches (graphs of up to 256 buses)")
         self.cuda_graph = None
         self.launches_per_step = None
         self.use_cuda_graph = use_cuda_graph
@@ -155,9 +163,15 @@ class GraphedTrainer:
                                       drop_mode=1 if self.spec.p_drop > 0 else 0, rng_state=self.step_state)
         else:
             out = self.runner.forward(self.graph, b["x"], 11, b["edge_attr"], 13, self.flat, self.bufs)
-        _lib.check(lib.dss2_wls_fwd_bwd(self.graph.ref, _lib.ptr(b["x"]), 11, _lib.ptr(b["edge_attr"]), 13, _lib.ptr(out),
-                                        _lib.ptr(self.stats), *self.coefs, _lib.ptr(b["vminmax"]), 1, _lib.ptr(self.loss), None,
-                                        _lib.ptr(self.grad_out), _lib.ptr(self.wls_ws), self.wls_ws.numel(), st), "dss2_wls_fwd_bwd")
+        wls_args = (self.graph.ref, _lib.ptr(b["x"]), 11, _lib.ptr(b["edge_attr"]), 13, _lib.ptr(out), _lib.ptr(self.stats), *self.coefs,
+                    _lib.ptr(b["vminmax"]), 1, _lib.ptr(self.loss), None, _lib.ptr(self.grad_out), _lib.ptr(self.wls_ws),
+                    self.wls_ws.numel() * self.wls_ws.element_size(), st)
+        if self.exact:   # reduction pass -> all-reduce of the batch sums and counts -> gradient pass on the global means
+            _lib.check(lib.dss2_wls_pass(1, *wls_args), "dss2_wls_pass(1)")
+            torch.distributed.all_reduce(self.wls_sums, group=self.pg)
+            _lib.check(lib.dss2_wls_pass(2, *wls_args), "dss2_wls_pass(2)")
+        else:
+            _lib.check(lib.dss2_wls_fwd_bwd(*wls_args), "dss2_wls_fwd_bwd")
         if self.network == "skippfn":
             self.runner.backward(self.graph, b["x"], 11, b["edge_attr"], 13, self.flat, self.bufs, self.grad_out, self.flat_grad, ea_uploaded=True)
         else:
@@ -166,7 +180,7 @@ class GraphedTrainer:
             torch.distributed.all_reduce(self.flat_grad[:self.flat.numel()], group=self.pg)
         if with_optimizer:
             _lib.check(lib.dss2_adamax_step(_lib.ptr(self.flat), _lib.ptr(self.flat_grad), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_inf),
-                                            self.flat.numel(), self.lr, 0.9, 0.999, 1e-8, 1.0 / self.world, _lib.ptr(self.step_state), 1,
+                                            self.flat.numel(), self.lr, 0.9, 0.999, 1e-8, 1.0 if self.exact else 1.0 / self.world, _lib.ptr(self.step_state), 1,
                                             st), "dss2_adamax_step")
 
     def capture(self):
@@ -180,7 +194,7 @@ class GraphedTrainer:
                 for _ in range(2):
                     before = _lib.launch_count()
                     self._enqueue()
-                    self.launches_per_step = _lib.launch_count() - before + (1 if self.world > 1 else 0)
+                    self.launches_per_step = _lib.launch_count() - before + (1 if self.world > 1 else 0) + (1 if self.exact else 0)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             for t, k in zip((self.flat, self.exp_avg, self.exp_inf, self.step_state), keep):

@@ -226,6 +226,15 @@ int dss2_wls_fwd_bwd(const dss2_graph_t* g, const float* x, int64_t x_stride, co
                      float lam_pf, float lam_reg, const float* vminmax, int mask_inplace,
                      float* loss, const float* grad_loss, float* grad_out, void* ws, size_t ws_bytes,
                      void* stream);
+/* Exact-global-batch data parallelism (the loss squares batch means, data.py:450-455, so per-rank losses do not add up):
+ * dss2_wls_pass(1, ...) runs the reduction pass only and leaves seven doubles at dss2_wls_sums(ws) - the five batch sums and the bus /
+ * branch counts; the caller sum-all-reduces them over the ranks in place; dss2_wls_pass(2, ...) runs the gradient pass with the global
+ * means and 1/N, 1/E factors and overwrites *loss with the loss of the union batch.  Summing (not averaging) the ranks' parameter
+ * gradients then gives the gradient of one batch made of all ranks' scenarios.  Same arguments as dss2_wls_fwd_bwd; tiled batches only. */
+double* dss2_wls_sums(void* ws);
+int dss2_wls_pass(int phase, const dss2_graph_t* g, const float* x, int64_t x_stride, const float* edge_attr, int64_t ea_stride,
+                  float* output, const float* stats, float lam_v, float lam_p, float lam_pf, float lam_reg, const float* vminmax,
+                  int mask_inplace, float* loss, const float* grad_loss, float* grad_out, void* ws, size_t ws_bytes, void* stream);
 
 /* get_pflow (data.py:328-390, phase_shift=True): y [Nt,2] (V pu, theta rad, row stride y_stride);
  * node vn_kv via vminmax; edge_param columns (G,B,Gs,Bs,closed,shift,imax) = edge_attr[:,6:13] given

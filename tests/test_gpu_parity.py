@@ -930,6 +930,63 @@ def test_graphed_trainer_next_row_models_equal_the_drop_in_modules(env, network)
         assert torch.allclose(tr.flat[off:off + n], p_.detach().reshape(-1), rtol=1e-3, atol=1e-5), name
 
 
+def test_exact_global_batch_loss_passes_equal_one_large_batch(env):
+    """SURVEY.md 8e, exact-global-batch data parallelism: the loss squares batch means (data.py:453-455), so the per-rank losses and
+    gradients of a sharded batch do not add up to the large batch's.  dss2_wls_pass(1) on each shard -> the seven batch sums / counts
+    added over the shards (what the ranks' all-reduce does) -> dss2_wls_pass(2) on each shard must reproduce the loss and the rows of
+    d loss / d out of ONE dss2_wls_fwd_bwd over the union batch."""
+    lib, P = env["lib"].load(), env["lib"].ptr
+    store = env["synth"].synthetic_store(env["synth"].load_grid("ober_sub"), 12, seed=8).to("cuda")
+    stats = torch.cat([store.x_mean, store.x_std, store.edge_mean, store.edge_std]).float().cuda().contiguous()
+    coefs = (REG_COEFS["lam_v"], REG_COEFS["lam_p"], REG_COEFS["lam_pf"], REG_COEFS["lam_reg"])
+    gen = torch.Generator(device="cuda").manual_seed(4)
+
+    def run(ids, phase_inputs=None):
+        b = env["batching"].pack_batch(store, torch.tensor(ids, device="cuda"))
+        g = env["ops"].resolve_graph(b.edge_index, b.x.size(0))
+        return b, g
+
+    ids_all = [0, 5, 2, 9, 7, 3, 11, 1]
+    shards = [ids_all[:3], ids_all[3:]]              # ragged on purpose: 3 + 5 scenarios
+    b_all, g_all = run(ids_all)
+    out_all = torch.stack([torch.randn(b_all.x.size(0), device="cuda", generator=gen) * 2.0,
+                           torch.randn(b_all.x.size(0), device="cuda", generator=gen) * 0.6], 1).contiguous()
+    n_per = store.max_nodes
+
+    def call(fn, phase, b, g, out, loss, gout, ws):
+        args = (g.ref, P(b.x), 11, P(b.edge_attr), 13, P(out), P(stats), *coefs, P(b.vminmax), 0, P(loss), None, P(gout), P(ws), ws.numel(),
+                env["lib"].stream())
+        env["lib"].check(fn(*args) if phase is None else fn(phase, *args), "wls")
+
+    loss_all, gout_all = torch.zeros((), device="cuda"), torch.empty_like(out_all)
+    call(lib.dss2_wls_fwd_bwd, None, b_all, g_all, out_all.clone(), loss_all, gout_all, g_all.wls_workspace())
+    parts, off = [], 0
+    for ids in shards:
+        b, g = run(ids)
+        n = len(ids) * n_per
+        parts.append(dict(b=b, g=g, out=out_all[off:off + n].clone().contiguous(), loss=torch.zeros((), device="cuda"),
+                          gout=torch.empty(n, 2, device="cuda"), ws=g.wls_workspace()))
+        off += n
+    for p_ in parts:
+        call(lib.dss2_wls_pass, 1, p_["b"], p_["g"], p_["out"], p_["loss"], p_["gout"], p_["ws"])
+    sums = [p_["ws"][256:256 + 56].view(torch.float64) for p_ in parts]
+    total = sums[0] + sums[1]                          # = all_reduce(SUM) over two ranks
+    assert float(total[5]) == b_all.x.size(0) and float(total[6]) == b_all.edge_attr.size(0)
+    for sv in sums:
+        sv.copy_(total)
+    for p_ in parts:
+        call(lib.dss2_wls_pass, 2, p_["b"], p_["g"], p_["out"], p_["loss"], p_["gout"], p_["ws"])
+    torch.cuda.synchronize()
+    for p_ in parts:
+        assert torch.allclose(p_["loss"], loss_all, rtol=1e-6, atol=0), (float(p_["loss"]), float(loss_all))
+    got = torch.cat([p_["gout"] for p_ in parts])
+    assert torch.allclose(got, gout_all, rtol=2e-6, atol=1e-7 * float(gout_all.abs().max()))
+    # and the per-shard (DDP) gradients are NOT the large batch's: the mode changes the result
+    p0 = parts[0]
+    call(lib.dss2_wls_fwd_bwd, None, p0["b"], p0["g"], p0["out"], p0["loss"], p0["gout"], p0["ws"])
+    assert not torch.allclose(p0["gout"], gout_all[:p0["gout"].size(0)], rtol=1e-3, atol=0)
+
+
 # ------------------------------------------------------------------------------------------------ whole training step (throughput tier)
 @pytest.mark.parametrize("case,nb", [("cigre14", 64), ("ober_sub", 6), ("ober_sub_x5", 3), ("ober_sub_x143", 2)])
 def test_graphed_trainer_step_matches_oracle(env, case, nb):
