@@ -294,13 +294,19 @@ def _small_batch(env, case="ober_sub", nb=5, seed=7):
     return env["batching"].pack_batch(st, list(range(nb)))
 
 
-@pytest.mark.parametrize("case,nb", [("cigre14", 20), ("ober_sub", 5), ("cigre14_reswitched", 1)])
-def test_edge_aggregation_forward_backward(env, case, nb):
+@pytest.mark.parametrize("impl", ["row", "warp"])
+@pytest.mark.parametrize("case,nb,fn,fe", [("cigre14", 20, 8, 6), ("ober_sub", 5, 8, 6), ("cigre14_reswitched", 1, 8, 6), ("ober_sub", 4, 5, 4),
+                                           ("cigre14", 17, 3, 6), ("ober_sub", 3, 8, 8)])
+def test_edge_aggregation_forward_backward(env, monkeypatch, case, nb, fn, fe, impl):
+    """impl='row': the thread-per-row FFMA2 kernels (csrc/edgeagg_row.cu; the default), impl='warp': the round-1 warp-per-row kernels
+    (DSS2_EA_IMPL=warp; also what 8 edge features fall back to).  Narrow feature counts exercise the zero-padded weight layouts, a strided
+    attribute view the raw-row bulk copies (row stride 13, rows not 16-byte aligned), 17 CIGRE graphs a full 255-row tile."""
+    monkeypatch.setenv("DSS2_EA_IMPL", impl)
     b = _small_batch(env, case, nb)
     torch.manual_seed(1)
-    m = env["networks"].EdgeAggregation(8, 6, 32, 32).cuda()
-    x = (torch.randn(b.x.size(0), 8, device="cuda")).requires_grad_(True)
-    ea = b.edge_attr[:, :6]
+    m = env["networks"].EdgeAggregation(fn, fe, 32, 32).cuda()
+    x = (torch.randn(b.x.size(0), fn, device="cuda")).requires_grad_(True)
+    ea = b.edge_attr[:, :fe]
     out = m(x, b.edge_index, ea)
     gw = torch.randn_like(out)
     (out * gw).sum().backward()
@@ -1085,9 +1091,9 @@ def test_large_graph_path_wls_loss(env, tiny_tiles, tag):
     test_wls_loss_all_penalties_active(env)
 
 
-def test_large_graph_path_layers(env, tiny_tiles):
-    test_edge_aggregation_forward_backward(env, "ober_sub", 5)
-    test_edge_aggregation_forward_backward(env, "cigre14_reswitched", 1)
+def test_large_graph_path_layers(env, tiny_tiles, monkeypatch):
+    test_edge_aggregation_forward_backward(env, monkeypatch, "ober_sub", 5, 8, 6, "row")
+    test_edge_aggregation_forward_backward(env, monkeypatch, "cigre14_reswitched", 1, 8, 6, "row")
     for cout, K in [(32, 2), (8, 2), (2, 2), (32, 1)]:
         test_tag_conv_forward_backward(env, cout, K)
 
