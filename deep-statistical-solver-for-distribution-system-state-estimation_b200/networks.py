@@ -31,7 +31,24 @@ class _LazyMachinery:
     def __getstate__(self):
         state = self.__dict__.copy()
         state.pop("_dss2_machinery", None)
+        state.pop("_dss2_param_slots", None)
         return state
+
+    def _named_params(self):
+        """dict(self.named_parameters()) without walking the module tree on every forward (181 parameters for the default SkipPFN: 0.85 ms of
+        a 8 ms script-scale step): the (name, owning module, attribute) triples are cached, the Parameter objects are looked up fresh, so
+        .to() / load_state_dict / parameter replacement keep working."""
+        slots = self.__dict__.get("_dss2_param_slots")
+        if slots is None:
+            slots = []
+            seen = set()
+            for prefix, mod in self.named_modules():
+                for attr, p in mod._parameters.items():
+                    if p is not None and id(p) not in seen:          # shared parameters once, under their first name (named_parameters' rule)
+                        seen.add(id(p))
+                        slots.append((prefix + "." + attr if prefix else attr, mod, attr))
+            self.__dict__["_dss2_param_slots"] = slots
+        return {name: mod._parameters[attr] for name, mod, attr in slots}
 
 
 class TAGConv(nn.Module):
@@ -83,7 +100,7 @@ class _Stack(_LazyMachinery, nn.Module):
     def forward(self, x, edge_index, edge_attr):
         runner, pack = self._machinery()
         masks, self._dss2_masks = self._dss2_masks, None
-        return ops.pfn_apply(runner, pack, dict(self.named_parameters()), x, edge_index, edge_attr, masks=masks,
+        return ops.pfn_apply(runner, pack, self._named_params(), x, edge_index, edge_attr, masks=masks,
                              rng_state=self._dss2_rng_state)
 
 
@@ -200,7 +217,7 @@ class gnn_dsse(_LazyMachinery, nn.Module):
     def forward(self, x, edge_index):
         from dss2 import gnn
         runner, pack = self._machinery()
-        return gnn.gnn_apply(runner, pack, dict(self.named_parameters()), x, edge_index)
+        return gnn.gnn_apply(runner, pack, self._named_params(), x, edge_index)
 
 
 class _GINEParams(nn.Module):
@@ -260,7 +277,7 @@ class GINE_DSSE(_LazyMachinery, nn.Module):
     def forward(self, x, edge_index, edge_attr):
         from dss2 import gine
         runner, pack = self._machinery()
-        return gine.gine_apply(runner, pack, dict(self.named_parameters()), x, edge_index, edge_attr)
+        return gine.gine_apply(runner, pack, self._named_params(), x, edge_index, edge_attr)
 
 
 class _GATv2Params(nn.Module):
@@ -330,4 +347,4 @@ class GAT_DSSE(_LazyMachinery, nn.Module):
     def forward(self, x, edge_index, edge_attr):
         from dss2 import gat
         runner, pack = self._machinery()
-        return gat.gat_apply(runner, pack, dict(self.named_parameters()), x, edge_index, edge_attr)
+        return gat.gat_apply(runner, pack, self._named_params(), x, edge_index, edge_attr)
