@@ -925,10 +925,33 @@ int dss2_tc2_dense_bgx(const dss2_graph_t* g, const float* grad_y, const uint32_
   return K == 1 ? launch_tc2_inst<MODE_BGX, 1, 8, true>(a, stream) : launch_tc2_inst<MODE_BGX, 2, 8, true>(a, stream);
 }
 
+// every tile of a launch that did not go through the chained kernel is complete at its end: mark them all
+__global__ void k_fill_marks(uint32_t* marks, int n, const uint64_t* seq) {
+  const uint32_t v = (uint32_t)seq[1] + 1u;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) marks[i] = v;
+}
+
+extern "C" int dss2_tag_fwd_tc2_chain(const dss2_graph_t* g, const float* x, const float* w, const float* bias, int cout, int K, int act,
+                                      float p_drop, int drop_mode, const uint64_t* rng_state, uint32_t layer_uid, const uint8_t* mask,
+                                      const float* res, int64_t res_stride, float* y, uint32_t* act_bits, uint32_t* done_flags,
+                                      const uint32_t* wait_flags, void* stream_);
 extern "C" int dss2_tag_fwd_tc2(const dss2_graph_t* g, const float* x, const float* w, const float* bias, int cout, int K, int act,
                                 float p_drop, int drop_mode, const uint64_t* rng_state, uint32_t layer_uid, const uint8_t* mask,
                                 const float* res, int64_t res_stride, float* y, uint32_t* act_bits, void* stream_) {
+  return dss2_tag_fwd_tc2_chain(g, x, w, bias, cout, K, act, p_drop, drop_mode, rng_state, layer_uid, mask, res, res_stride, y, act_bits, nullptr,
+                                nullptr, stream_);
+}
+
+// Chained variant for a stack of layers inside one captured step (see Tc2Args): done_flags [num_tiles] receives this launch's per-tile
+// completion marks, wait_flags = the done_flags of the launch that produced x.  Either may be NULL.  Both need rng_state (the device
+// {seed, step} pair: the marks carry step + 1, so a replayed graph needs no reset).  When the TMA-fed kernel cannot serve the shape the
+// flags are ignored and the launch is an ordinary one (correct, just not overlapped) - then done_flags is filled by a plain kernel.
+extern "C" int dss2_tag_fwd_tc2_chain(const dss2_graph_t* g, const float* x, const float* w, const float* bias, int cout, int K, int act,
+                                      float p_drop, int drop_mode, const uint64_t* rng_state, uint32_t layer_uid, const uint8_t* mask,
+                                      const float* res, int64_t res_stride, float* y, uint32_t* act_bits, uint32_t* done_flags,
+                                      const uint32_t* wait_flags, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  DSS2_CHECK_ARG(!(done_flags || wait_flags) || rng_state, "dss2_tag_fwd_tc2_chain: the tile marks need rng_state (device {seed, step})");
   DSS2_CHECK_ARG(g && x && w && bias && y, "dss2_tag_fwd_tc2: null argument");
   DSS2_CHECK_ARG(cout >= 1 && cout <= HID, "dss2_tag_fwd_tc2: cout %d outside 1..%d", cout, HID);
   DSS2_CHECK_ARG(tc2_supported(g, K), "dss2_tag_fwd_tc2: needs a tiled graph (tile_cap <= 256) and K in 1..2");
@@ -955,9 +978,19 @@ extern "C" int dss2_tag_fwd_tc2(const dss2_graph_t* g, const float* x, const flo
   a.res_stride = res_stride;
   a.out = y;
   a.out_bits = act_bits;
+  a.done_flags = done_flags;
+  a.wait_flags = wait_flags;
+  a.chain_seq = rng_state;
   const int rc3 = dss2_tc3_launch(MODE_FWD, a, K, stream);   // the TMA-fed kernel when it serves the shape
   if (rc3 <= 0) return rc3;
-  return launch_tc2<MODE_FWD>(a, K, stream);
+  a.done_flags = nullptr;
+  a.wait_flags = nullptr;
+  const int rc2 = launch_tc2<MODE_FWD>(a, K, stream);        // ordinary launch: ordered after the producer, complete before any consumer
+  if (rc2 == 0 && done_flags) {
+    k_fill_marks<<<max(1, min(g->num_tiles, 1024) / 256 + 1), 256, 0, stream>>>(done_flags, g->num_tiles, rng_state);
+    DSS2_LAUNCH_CHECK();
+  }
+  return rc2;
 }
 
 extern "C" size_t dss2_tag_bwd_tc2_workspace_bytes(int64_t num_nodes, int K) { return (size_t)K * num_nodes * HID * sizeof(float) + 256; }

@@ -25,6 +25,14 @@ struct Tc2Args {
   float* lvl_out;           // BGX: [K][Nt,32] hop levels 1..K of g (for k_tag_gw)
   const float* dense_lvl;   // large-graph path: hop levels 1..K precomputed in global memory ([K][Nt,32]); tiles are plain row chunks
   int flags;                // measurement switches (DSS2_TC2_FLAGS): 1 = BGX prefetches the next tile behind the last publish like FWD
+  // Layer chaining (k_tag_tc3 only): a tile of layer l+1 needs nothing but the SAME tile of layer l (message passing never leaves a tile),
+  // so consecutive layer launches are linked per tile instead of per grid.  done_flags[t] is set to the chain sequence number (device
+  // step counter + 1) once tile t's outputs are in global memory; a launch given wait_flags reads tile t's input only after the
+  // producer's flag carries this step's number, and is launched with programmatic stream serialization WITHOUT a grid-wide wait: its
+  // CTAs start on the SMs the producer's CTAs leave and run ahead (no empty last round, prologue hidden behind the producer's tail).
+  uint32_t* done_flags;
+  const uint32_t* wait_flags;
+  const uint64_t* chain_seq;   // device {seed, step}: sequence number = (uint32)step + 1
 };
 
 namespace {

@@ -21,6 +21,8 @@ TAG_IMPL = os.environ.get("DSS2_TAG_IMPL", "tc2")
 # weight-gradient pass behind the tc2 backward: "tc" = tcgen05 3xTF32 GEMM (68.7 us on the bench layer), "ffma" = exact fp32 streaming
 # kernel on the CUDA cores (82.5 us; profiles/r1k_bench.json) - the tensor cores are used because they measure faster
 GW_IMPL = os.environ.get("DSS2_GW_IMPL", "tc")
+# consecutive TAG layers of a sub-net linked per tile (programmatic dependent launch + tile marks) instead of per grid: DSS2_CHAIN=0 disables
+CHAIN = os.environ.get("DSS2_CHAIN", "1") != "0"
 
 
 def tile_cap():
@@ -112,6 +114,8 @@ class PFNRunner:
             # one sign word per node; rows padded to 64 words so every [s, l] slice starts 256-byte aligned (bulk-copy source)
             "bits": torch.empty(sp.L, max(sp.n_layers - 1, 1), (num_nodes + 63) // 64 * 64, dtype=torch.int32, device=device),
             "outs": [torch.empty(num_nodes, sp.out_dim(s), **f32) for s in range(sp.L)],
+            # per-tile completion marks of every forward layer launch (layer chaining; one 32-bit word per tile, 256-tile upper bound per row)
+            "marks": torch.zeros(sp.L, sp.n_layers, (num_nodes + 255) // 256 * 256 + 256, dtype=torch.int32, device=device),
         }
         if need_grad:
             b["g32"] = [torch.empty(num_nodes, HID, **f32) for _ in range(2)]
@@ -153,6 +157,7 @@ class PFNRunner:
         slots = self.ea_slots(graph, x_stride, ea_stride)
         if slots:
             self.ea_upload(flat)
+        chain = use_tc2 and CHAIN and rng_state is not None and "marks" in bufs
         for s in range(sp.L):
             pre = sp.prefix_fmt.format(s=s)
             xin, xs = (x, x_stride) if s == 0 else (bufs["outs"][s - 1], sp.fn)
@@ -171,11 +176,16 @@ class PFNRunner:
                 if not last and drop_mode == 2:
                     mask = masks[s][l]
                 res, rs = (xin, xs) if (last and sp.skip[s]) else (None, 0)
-                fwd = lib.dss2_tag_fwd_tc2 if use_tc2 else lib.dss2_tag_fwd
-                _lib.check(fwd(g, _lib.ptr(bufs["acts"][s, l]), self._p(flat, pre + f"convs.{l}.lins.0.weight"),
-                               self._p(flat, pre + f"convs.{l}.bias"), cout, sp.K, 0 if last else 1, sp.p_drop, mode,
-                               _lib.ptr(rng_state), s * sp.n_layers + l, _lib.ptr(mask), _lib.ptr(res), rs,
-                               _lib.ptr(y), None if last else _lib.ptr(bufs["bits"][s, l]), st), "dss2_tag_fwd")
+                args = (g, _lib.ptr(bufs["acts"][s, l]), self._p(flat, pre + f"convs.{l}.lins.0.weight"),
+                        self._p(flat, pre + f"convs.{l}.bias"), cout, sp.K, 0 if last else 1, sp.p_drop, mode,
+                        _lib.ptr(rng_state), s * sp.n_layers + l, _lib.ptr(mask), _lib.ptr(res), rs,
+                        _lib.ptr(y), None if last else _lib.ptr(bufs["bits"][s, l]))
+                if chain:   # layers of a sub-net linked per tile: layer l+1 starts on the SMs layer l's CTAs leave (csrc/tc2_shared.cuh)
+                    marks = bufs["marks"]
+                    _lib.check(lib.dss2_tag_fwd_tc2_chain(*args, None if last else _lib.ptr(marks[s, l]), _lib.ptr(marks[s, l - 1]) if l > 0 else None,
+                                                          st), "dss2_tag_fwd_tc2_chain")
+                else:
+                    _lib.check((lib.dss2_tag_fwd_tc2 if use_tc2 else lib.dss2_tag_fwd)(*args, st), "dss2_tag_fwd")
         return bufs["outs"][-1]
 
     # ---- backward ----

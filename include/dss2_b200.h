@@ -170,6 +170,15 @@ int dss2_tag_fwd_tc2(const dss2_graph_t* g, const float* x, const float* w, cons
                      int act, float p_drop, int drop_mode, const uint64_t* rng_state, uint32_t layer_uid,
                      const uint8_t* mask, const float* res, int64_t res_stride,
                      float* y, uint32_t* act_bits, void* stream);
+/* Chained variant for a stack of layers inside one step: a tile of layer l+1 needs only the SAME tile of layer l (message passing never
+ * leaves a tile), so the launches are linked per tile instead of per grid.  done_flags [num_tiles] (u32) receives step+1 for every tile
+ * whose outputs are in global memory; wait_flags = the done_flags of the launch that produced x: this launch then starts (programmatic
+ * stream serialization, no grid-wide wait) on the SMs the producer's CTAs leave and reads a tile once its mark carries this step's number.
+ * rng_state (device {seed, step}) supplies the step; marks need no reset between steps.  Either pointer may be NULL. */
+int dss2_tag_fwd_tc2_chain(const dss2_graph_t* g, const float* x, const float* w, const float* bias, int cout, int K,
+                           int act, float p_drop, int drop_mode, const uint64_t* rng_state, uint32_t layer_uid,
+                           const uint8_t* mask, const float* res, int64_t res_stride, float* y, uint32_t* act_bits,
+                           uint32_t* done_flags, const uint32_t* wait_flags, void* stream);
 size_t dss2_tag_bwd_tc2_workspace_bytes(int64_t num_nodes, int K);
 int dss2_tag_bwd_tc2(const dss2_graph_t* g, const float* x, const float* w, int cout, int K,
                      int act, float p_drop, const uint32_t* act_bits, const float* grad_y,
