@@ -936,6 +936,28 @@ def test_graphed_trainer_next_row_models_equal_the_drop_in_modules(env, network)
         assert torch.allclose(tr.flat[off:off + n], p_.detach().reshape(-1), rtol=1e-3, atol=1e-5), name
 
 
+def test_chained_forward_layers_equal_ordinary_launches(env, monkeypatch):
+    """Layer chaining (tile marks + programmatic dependent launch, csrc/tc2_shared.cuh): the layers of a sub-net linked per tile instead of
+    per grid must produce bit-identical activations, sign words and outputs - same kernels, same arithmetic, only the launch order of
+    the CTAs changes - over several steps of a replayed CUDA graph (the marks carry step + 1 and are never reset)."""
+    from dss2.trainer import GraphedTrainer, default_spec
+    store = env["synth"].synthetic_store(env["synth"].load_grid("ober_sub"), 64, seed=12).to("cuda")
+    ids = [torch.randperm(64, generator=torch.Generator().manual_seed(s_))[:48].cuda() for s_ in range(4)]
+    runs = {}
+    for chain in (True, False):
+        monkeypatch.setattr(env["ops"], "CHAIN", chain)
+        tr = GraphedTrainer(store, 48, spec=default_spec(p_drop=0.3, L=2, n_layers=5), reg_coefs=REG_COEFS, seed=4, use_cuda_graph=True).capture()
+        assert ("marks" in tr.bufs)
+        losses = [float(tr.step(i_)) for i_ in ids]
+        runs[chain] = (losses, tr.flat.clone(), tr.bufs["acts"].clone(), tr.bufs["bits"].clone(), tr.bufs["marks"][:, :, :tr.graph.c.num_tiles].clone())
+    assert runs[True][0] == runs[False][0]
+    for a_, b_ in zip(runs[True][1:4], runs[False][1:4]):
+        assert torch.equal(a_, b_)
+    marks = runs[True][4]
+    # every chained producer layer (all but the last of a sub-net) marked every tile with the last step's number: step counter 4 -> mark 4
+    assert bool((marks[:, :-1] == marks[0, 0, 0]).all()) and int(marks[0, 0, 0]) > 0 and bool((runs[False][4] == 0).all())
+
+
 def test_exact_global_batch_loss_passes_equal_one_large_batch(env):
     """SURVEY.md 8e, exact-global-batch data parallelism: the loss squares batch means (data.py:453-455), so the per-rank losses and
     gradients of a sharded batch do not add up to the large batch's.  dss2_wls_pass(1) on each shard -> the seven batch sums / counts
