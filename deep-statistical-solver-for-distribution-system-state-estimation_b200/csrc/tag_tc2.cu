@@ -996,9 +996,22 @@ extern "C" int dss2_tag_fwd_tc2_chain(const dss2_graph_t* g, const float* x, con
 extern "C" size_t dss2_tag_bwd_tc2_workspace_bytes(int64_t num_nodes, int K) { return (size_t)K * num_nodes * HID * sizeof(float) + 256; }
 
 // the two halves of the backward, individually launchable (bench.py times them separately; dss2_tag_bwd_tc2 = both)
+extern "C" int dss2_tag_bwd_tc2_gx_chain(const dss2_graph_t* g, const float* w, int cout, int K, int act, float p_drop, const uint32_t* act_bits,
+                                         const float* grad_y, float* grad_x, void* ws, size_t ws_bytes, const uint64_t* rng_state,
+                                         uint32_t* done_flags, const uint32_t* wait_flags, void* stream_);
 extern "C" int dss2_tag_bwd_tc2_gx(const dss2_graph_t* g, const float* w, int cout, int K, int act, float p_drop, const uint32_t* act_bits,
                                    const float* grad_y, float* grad_x, void* ws, size_t ws_bytes, void* stream_) {
+  return dss2_tag_bwd_tc2_gx_chain(g, w, cout, K, act, p_drop, act_bits, grad_y, grad_x, ws, ws_bytes, nullptr, nullptr, nullptr, stream_);
+}
+
+// Chained variant (see dss2_tag_fwd_tc2_chain): the backward-to-input of layer l-1 needs only the same tile of layer l's grad_x, so a
+// stack of these launches links per tile.  The weight-gradient pass of a layer (dss2_tag_bwd_tc2_gw) needs the WHOLE launch (it streams
+// 64-row chunks across tiles and reads the spilled levels): run it behind an event on a second stream with its own workspace per layer.
+extern "C" int dss2_tag_bwd_tc2_gx_chain(const dss2_graph_t* g, const float* w, int cout, int K, int act, float p_drop, const uint32_t* act_bits,
+                                         const float* grad_y, float* grad_x, void* ws, size_t ws_bytes, const uint64_t* rng_state,
+                                         uint32_t* done_flags, const uint32_t* wait_flags, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  DSS2_CHECK_ARG(!(done_flags || wait_flags) || rng_state, "dss2_tag_bwd_tc2_gx_chain: the tile marks need rng_state (device {seed, step})");
   DSS2_CHECK_ARG(g && w && grad_y && grad_x && ws, "dss2_tag_bwd_tc2_gx: null argument");
   DSS2_CHECK_ARG(cout >= 1 && cout <= HID, "dss2_tag_bwd_tc2_gx: cout %d outside 1..%d", cout, HID);
   DSS2_CHECK_ARG(tc2_supported(g, K), "dss2_tag_bwd_tc2_gx: needs a tiled graph (tile_cap <= 256) and K in 1..2");
@@ -1015,9 +1028,19 @@ extern "C" int dss2_tag_bwd_tc2_gx(const dss2_graph_t* g, const float* w, int co
   a.scale = 1.0f / (float)(1.0 - (double)p_drop);
   a.out = grad_x;
   a.lvl_out = (float*)ws;
+  a.done_flags = done_flags;
+  a.wait_flags = wait_flags;
+  a.chain_seq = rng_state;
   const int rc3 = dss2_tc3_launch(MODE_BGX, a, K, stream);
   if (rc3 <= 0) return rc3;
-  return launch_tc2<MODE_BGX>(a, K, stream);
+  a.done_flags = nullptr;
+  a.wait_flags = nullptr;
+  const int rc2 = launch_tc2<MODE_BGX>(a, K, stream);
+  if (rc2 == 0 && done_flags) {
+    k_fill_marks<<<max(1, min(g->num_tiles, 1024) / 256 + 1), 256, 0, stream>>>(done_flags, g->num_tiles, rng_state);
+    DSS2_LAUNCH_CHECK();
+  }
+  return rc2;
 }
 
 extern "C" int dss2_tag_bwd_tc2_gw(int64_t num_nodes, const float* x, int cout, int K, int act, float p_drop, const uint32_t* act_bits,

@@ -48,6 +48,7 @@ _SIGNATURES = {
     "dss2_tag_bwd_tc2_workspace_bytes": (c_size_t, [c_int64, c_int]),
     "dss2_tag_bwd_tc2": (c_int, [_G, _P, _P, c_int, c_int, c_int, c_float, _P, _P, _P, _P, c_int64, c_int64, _P, c_size_t, _P]),
     "dss2_tag_bwd_tc2_gx": (c_int, [_G, _P, c_int, c_int, c_int, c_float, _P, _P, _P, _P, c_size_t, _P]),
+    "dss2_tag_bwd_tc2_gx_chain": (c_int, [_G, _P, c_int, c_int, c_int, c_float, _P, _P, _P, _P, c_size_t, _P, _P, _P, _P]),
     "dss2_tag_bwd_tc2_gw": (c_int, [c_int64, _P, c_int, c_int, c_int, c_float, _P, _P, _P, c_int64, c_int64, _P, c_size_t, _P]),
     "dss2_tag_gw_ffma": (c_int, [c_int64, _P, c_int, c_int, c_int, c_float, _P, _P, _P, c_int64, c_int64, _P, c_size_t, _P]),
     "dss2_tc_selftest": (c_int, [_P, _P, _P, _P]),

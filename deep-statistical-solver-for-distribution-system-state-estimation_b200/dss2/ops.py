@@ -23,6 +23,8 @@ TAG_IMPL = os.environ.get("DSS2_TAG_IMPL", "tc2")
 GW_IMPL = os.environ.get("DSS2_GW_IMPL", "tc")
 # consecutive TAG layers of a sub-net linked per tile (programmatic dependent launch + tile marks) instead of per grid: DSS2_CHAIN=0 disables
 CHAIN = os.environ.get("DSS2_CHAIN", "1") != "0"
+# backward: chained backward-to-input launches on the current stream, weight-gradient passes on a second one (DSS2_CHAIN_BWD=0 disables)
+CHAIN_BWD = CHAIN and os.environ.get("DSS2_CHAIN_BWD", "0") != "0"
 
 
 def tile_cap():
@@ -106,7 +108,7 @@ class PFNRunner:
         self.num_partials = self.lib.dss2_num_partials()
 
     # ---- buffers ----
-    def alloc(self, num_nodes, device, need_grad=True):
+    def alloc(self, num_nodes, device, need_grad=True, pipelined=False):
         sp = self.spec
         f32 = dict(dtype=torch.float32, device=device)
         b = {
@@ -122,6 +124,12 @@ class PFNRunner:
             b["gsub"] = [torch.empty(num_nodes, sp.fn, **f32) for _ in range(2)]
             b["partials"] = torch.zeros(self.num_partials, self.flat_size, **f32)
             b["lvl"] = torch.empty(self.lib.dss2_tag_bwd_tc2_workspace_bytes(num_nodes, sp.K) // 4, **f32)
+            if pipelined:
+                # two-stream backward (see backward()): the gradient of every layer input and the spilled hop levels of every layer stay
+                # alive until that layer's weight-gradient pass has read them on the second stream
+                b["gchain"] = torch.empty(sp.n_layers, num_nodes, HID, **f32)
+                b["lvls"] = torch.empty(sp.n_layers, b["lvl"].numel(), **f32)
+                b["marks_b"] = torch.zeros_like(b["marks"])
         return b
 
     def _p(self, flat, name):
@@ -189,10 +197,14 @@ class PFNRunner:
         return bufs["outs"][-1]
 
     # ---- backward ----
-    def backward(self, graph, x, x_stride, ea, ea_stride, flat, bufs, grad_out, flat_grad, accumulate=False, ea_uploaded=False):
+    def backward(self, graph, x, x_stride, ea, ea_stride, flat, bufs, grad_out, flat_grad, accumulate=False, ea_uploaded=False, rng_state=None):
         """grad_out [Nt, dim_out] dense.  Writes the flat parameter gradient into flat_grad.  ea_uploaded: the constant-memory slots
-        still hold this model's EdgeAggregation weights (the captured step: forward and backward of one step, nothing in between)."""
+        still hold this model's EdgeAggregation weights (the captured step: forward and backward of one step, nothing in between).
+        rng_state (device {seed, step}) with buffers from alloc(pipelined=True) selects the two-stream schedule (_backward_pipelined)."""
         sp, lib, st = self.spec, self.lib, _lib.stream()
+        if (CHAIN_BWD and rng_state is not None and "gchain" in bufs and TAG_IMPL == "tc2" and GW_IMPL == "tc"
+                and bool(lib.dss2_tag_tc2_supported(graph.ref, sp.K))):
+            return self._backward_pipelined(graph, x, x_stride, ea, ea_stride, flat, bufs, grad_out, flat_grad, accumulate, ea_uploaded, rng_state)
         g = graph.ref
         slots = self.ea_slots(graph, x_stride, ea_stride)
         if slots and not ea_uploaded:
@@ -241,6 +253,74 @@ class PFNRunner:
                                                 _lib.ptr(gy), _lib.ptr(skip_grad), sp.fn if skip_grad is not None else 0,
                                                 _lib.ptr(gprev), pp(pre + "edge_aggr.edge_aggr.0.weight"), pstride, st), "dss2_edgeagg_bwd")
             gy = gprev
+        _lib.check(lib.dss2_reduce_partials(_lib.ptr(part), pstride, self.num_partials, self.flat_size, _lib.ptr(flat_grad),
+                                            1 if accumulate else 0, st), "dss2_reduce_partials")
+        return flat_grad
+
+    def _backward_pipelined(self, graph, x, x_stride, ea, ea_stride, flat, bufs, grad_out, flat_grad, accumulate, ea_uploaded, rng_state):
+        """Same arithmetic as backward(), scheduled on two streams.  The backward-to-input launches of a sub-net form a per-tile chain on
+        the current stream (layer l-1 needs only the same tile of layer l's output: dss2_tag_bwd_tc2_gx_chain); the weight-gradient pass
+        of each layer needs that layer's whole launch (its spilled hop levels), so it runs behind an event on a second stream and fills
+        the SMs the chain leaves idle.  Every layer keeps its own input gradient and level workspace until its pass has run; the streams
+        join before the next sub-net reuses them.  Each kernel still writes only its own columns of the per-CTA partials."""
+        sp, lib = self.spec, self.lib
+        g = graph.ref
+        main = torch.cuda.current_stream()
+        if getattr(self, "_side", None) is None or self._side.device != main.device:
+            self._side = torch.cuda.Stream(device=main.device)
+        side = self._side
+        st, st2 = ctypes.c_void_p(main.cuda_stream), ctypes.c_void_p(side.cuda_stream)
+        slots = self.ea_slots(graph, x_stride, ea_stride)
+        if slots and not ea_uploaded:
+            self.ea_upload(flat)
+        part, pstride = bufs["partials"], self.flat_size
+
+        def pp(name):
+            return ctypes.c_void_p(part.data_ptr() + 4 * self.table[name][0])
+
+        G, LV, marks = bufs["gchain"], bufs["lvls"], bufs["marks_b"]
+        nws = LV[0].numel() * 4
+        gy = grad_out
+        forked = False
+        for s in reversed(range(sp.L)):
+            pre = sp.prefix_fmt.format(s=s)
+            xin, xs = (x, x_stride) if s == 0 else (bufs["outs"][s - 1], sp.fn)
+            g_sub = gy
+            if forked:
+                main.wait_stream(side)      # the previous sub-net's weight-gradient passes have read G / LV / g_sub
+            for l in reversed(range(sp.n_layers)):
+                last = l == sp.n_layers - 1
+                cout = sp.out_dim(s) if last else HID
+                act = 0 if last else 1
+                bits = None if last else _lib.ptr(bufs["bits"][s, l])
+                w_off, b_off = self.table[pre + f"convs.{l}.lins.0.weight"][0], self.table[pre + f"convs.{l}.bias"][0]
+                _lib.check(lib.dss2_tag_bwd_tc2_gx_chain(g, self._p(flat, pre + f"convs.{l}.lins.0.weight"), cout, sp.K, act, sp.p_drop, bits,
+                                                         _lib.ptr(gy), _lib.ptr(G[l]), _lib.ptr(LV[l]), nws, _lib.ptr(rng_state),
+                                                         _lib.ptr(marks[s, l]) if l > 0 else None, None if last else _lib.ptr(marks[s, l + 1]), st),
+                           "dss2_tag_bwd_tc2_gx_chain")
+                ev = torch.cuda.Event()
+                ev.record(main)
+                side.wait_event(ev)
+                forked = True
+                _lib.check(lib.dss2_tag_bwd_tc2_gw(graph.num_nodes, _lib.ptr(bufs["acts"][s, l]), cout, sp.K, act, sp.p_drop, bits, _lib.ptr(gy),
+                                                   pp(pre + f"convs.{l}.lins.0.weight"), pstride, b_off - w_off, _lib.ptr(LV[l]), nws, st2),
+                           "dss2_tag_bwd_tc2_gw")
+                gy = G[l]
+            need_gx = s > 0
+            gprev = bufs["gsub"][s & 1] if need_gx else None
+            skip_grad = g_sub if (sp.skip[s] and need_gx) else None
+            if slots:
+                _lib.check(lib.dss2_edgeagg_bwd_slot(g, _lib.ptr(xin), xs, sp.fn, _lib.ptr(ea), ea_stride, sp.fe, s, _lib.ptr(gy), _lib.ptr(skip_grad),
+                                                     sp.fn if skip_grad is not None else 0, _lib.ptr(gprev), pp(pre + "edge_aggr.edge_aggr.0.weight"),
+                                                     pstride, st), "dss2_edgeagg_bwd_slot")
+            else:
+                _lib.check(lib.dss2_edgeagg_bwd(g, _lib.ptr(xin), xs, sp.fn, _lib.ptr(ea), ea_stride, sp.fe,
+                                                *[self._p(flat, n) for n in self._ea_names(s)],
+                                                _lib.ptr(gy), _lib.ptr(skip_grad), sp.fn if skip_grad is not None else 0,
+                                                _lib.ptr(gprev), pp(pre + "edge_aggr.edge_aggr.0.weight"), pstride, st), "dss2_edgeagg_bwd")
+            gy = gprev
+        if forked:
+            main.wait_stream(side)
         _lib.check(lib.dss2_reduce_partials(_lib.ptr(part), pstride, self.num_partials, self.flat_size, _lib.ptr(flat_grad),
                                             1 if accumulate else 0, st), "dss2_reduce_partials")
         return flat_grad

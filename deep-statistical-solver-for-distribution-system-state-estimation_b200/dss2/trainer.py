@@ -98,7 +98,7 @@ class GraphedTrainer:
             self.stats = torch.cat([store.x_mean, store.x_std, store.edge_mean, store.edge_std]).to(**f32).contiguous()
             self.loss = torch.zeros((), **f32)
             self.grad_out = torch.empty(self.nt, 2, **f32)
-            self.bufs = self.runner.alloc(self.nt, self.dev, need_grad=True)
+            self.bufs = self.runner.alloc(self.nt, self.dev, need_grad=True, **({'pipelined': True} if self.network == 'skippfn' else {}))
             # structure: one eager pack, then build once (uniform topology: identical for every batch)
             self.ids.copy_(torch.arange(self.B, device=self.dev) % store.num_scenarios)
             launch_pack(store, self.ids, self.batch, self.nt, self.et)
@@ -157,6 +157,10 @@ class GraphedTrainer:
     def _enqueue(self, with_optimizer=True):
         lib, st = self.lib, _lib.stream()
         b = self.batch
+        if not with_optimizer:   # the step counter (= the sequence number of the tile marks of the chained layers) will not advance
+            for k in ("marks", "marks_b"):
+                if k in self.bufs:
+                    self.bufs[k].zero_()
         launch_pack(self.store, self.ids, b, self.nt, self.et)
         if self.network == "skippfn":
             out = self.runner.forward(self.graph, b["x"], 11, b["edge_attr"], 13, self.flat, self.bufs,
@@ -173,7 +177,8 @@ class GraphedTrainer:
         else:
             _lib.check(lib.dss2_wls_fwd_bwd(*wls_args), "dss2_wls_fwd_bwd")
         if self.network == "skippfn":
-            self.runner.backward(self.graph, b["x"], 11, b["edge_attr"], 13, self.flat, self.bufs, self.grad_out, self.flat_grad, ea_uploaded=True)
+            self.runner.backward(self.graph, b["x"], 11, b["edge_attr"], 13, self.flat, self.bufs, self.grad_out, self.flat_grad, ea_uploaded=True,
+                                 rng_state=self.step_state)
         else:
             self.runner.backward(self.graph, b["x"], 11, b["edge_attr"], 13, self.flat, self.bufs, self.grad_out, self.flat_grad)
         if self.world > 1:

@@ -179,6 +179,12 @@ int dss2_tag_fwd_tc2_chain(const dss2_graph_t* g, const float* x, const float* w
                            int act, float p_drop, int drop_mode, const uint64_t* rng_state, uint32_t layer_uid,
                            const uint8_t* mask, const float* res, int64_t res_stride, float* y, uint32_t* act_bits,
                            uint32_t* done_flags, const uint32_t* wait_flags, void* stream);
+/* The same for a stack of backward-to-input launches (dss2_tag_bwd_tc2_gx): layer l-1 needs only the same tile of layer l's grad_x.  The
+ * weight-gradient pass of a layer (dss2_tag_bwd_tc2_gw) needs the whole launch: run it behind an event on a second stream, with a
+ * workspace per layer (it then fills the SMs the chained launches leave idle). */
+int dss2_tag_bwd_tc2_gx_chain(const dss2_graph_t* g, const float* w, int cout, int K, int act, float p_drop,
+                              const uint32_t* act_bits, const float* grad_y, float* grad_x, void* ws, size_t ws_bytes,
+                              const uint64_t* rng_state, uint32_t* done_flags, const uint32_t* wait_flags, void* stream);
 size_t dss2_tag_bwd_tc2_workspace_bytes(int64_t num_nodes, int K);
 int dss2_tag_bwd_tc2(const dss2_graph_t* g, const float* x, const float* w, int cout, int K,
                      int act, float p_drop, const uint32_t* act_bits, const float* grad_y,

@@ -958,6 +958,34 @@ def test_chained_forward_layers_equal_ordinary_launches(env, monkeypatch):
     assert bool((marks[:, :-1] == marks[0, 0, 0]).all()) and int(marks[0, 0, 0]) > 0 and bool((runs[False][4] == 0).all())
 
 
+def test_two_stream_backward_equals_ordinary_backward(env, monkeypatch):
+    """The pipelined backward (PFNRunner._backward_pipelined: chained backward-to-input launches on the step's stream, weight-gradient
+    passes behind events on a second one, per-layer gradient / level buffers) is the ordinary backward re-scheduled: the flat gradient
+    of one step and the parameters after several replayed steps must be bit-identical, with dropout on and on a ragged last tile."""
+    from dss2.trainer import GraphedTrainer, default_spec
+    store = env["synth"].synthetic_store(env["synth"].load_grid("ober_sub"), 64, seed=13).to("cuda")
+    ids = [torch.randperm(64, generator=torch.Generator().manual_seed(10 + s_))[:48].cuda() for s_ in range(4)]
+    runs = {}
+    for piped in (True, False):
+        monkeypatch.setattr(env["ops"], "CHAIN_BWD", piped)
+        tr = GraphedTrainer(store, 48, spec=default_spec(p_drop=0.3, L=2, n_layers=5), reg_coefs=REG_COEFS, seed=4, use_cuda_graph=False)
+        assert "gchain" in tr.bufs
+        tr.ids.copy_(ids[0])
+        tr._enqueue(with_optimizer=False)
+        tr._enqueue(with_optimizer=False)     # same step number twice: the marks are reset, not trusted
+        torch.cuda.synchronize()
+        g1 = tr.flat_grad.clone()
+        tr = GraphedTrainer(store, 48, spec=default_spec(p_drop=0.3, L=2, n_layers=5), reg_coefs=REG_COEFS, seed=4, use_cuda_graph=True).capture()
+        losses = [float(tr.step(i_)) for i_ in ids]
+        runs[piped] = (losses, g1, tr.flat.clone(), tr.flat_grad.clone(), tr.bufs["marks_b"][:, :, :tr.graph.c.num_tiles].clone())
+    assert runs[True][0] == runs[False][0]
+    for a_, b_ in zip(runs[True][1:4], runs[False][1:4]):
+        assert torch.equal(a_, b_)
+    marks = runs[True][4]
+    # layers 1 .. n-1 of every sub-net published every tile with the last step's number; layer 0 has no consumer
+    assert int(marks[0, 1, 0]) > 0 and bool((marks[:, 1:] == marks[0, 1, 0]).all()) and bool((runs[False][4] == 0).all())
+
+
 def test_exact_global_batch_loss_passes_equal_one_large_batch(env):
     """SURVEY.md 8e, exact-global-batch data parallelism: the loss squares batch means (data.py:453-455), so the per-rank losses and
     gradients of a sharded batch do not add up to the large batch's.  dss2_wls_pass(1) on each shard -> the seven batch sums / counts
