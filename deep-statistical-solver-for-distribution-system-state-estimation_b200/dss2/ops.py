@@ -24,7 +24,7 @@ GW_IMPL = os.environ.get("DSS2_GW_IMPL", "tc")
 # consecutive TAG layers of a sub-net linked per tile (programmatic dependent launch + tile marks) instead of per grid: DSS2_CHAIN=0 disables
 CHAIN = os.environ.get("DSS2_CHAIN", "1") != "0"
 # backward: chained backward-to-input launches on the current stream, weight-gradient passes on a second one (DSS2_CHAIN_BWD=0 disables)
-CHAIN_BWD = CHAIN and os.environ.get("DSS2_CHAIN_BWD", "0") != "0"
+CHAIN_BWD = CHAIN and os.environ.get("DSS2_CHAIN_BWD", "1") != "0"
 
 
 def tile_cap():
