@@ -129,6 +129,10 @@ __global__ void __launch_bounds__(Tc2Shape<RW>::THREADS + 32, RW == 8 ? 1 : 2) k
   const int cout = a.cout;
   const bool spill = MODE == MODE_BGX && a.lvl_out != nullptr;
   const bool has_bits = MODE == MODE_BGX && a.in_bits != nullptr;
+  // narrow grad_y rows (the last layer of a sub-net: cout 2, 4, 8 or 16 floats): the stage takes them as ONE dense 1-D bulk copy
+  // (16-byte-aligned superset of the tile's rows, like the topology words) and the upper feature half of level 0 is zero
+  const bool narrow = MODE == MODE_BGX && cout != HID;
+  const int nalign = narrow && cout * 4 < 16 ? 16 / (cout * 4) : 1;   // rows per 16 bytes
 
   // ---- layer chaining: let the next layer launch now (it links to this one per tile through done_flags, see Tc2Args) ----
   if (a.done_flags) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -167,8 +171,11 @@ __global__ void __launch_bounds__(Tc2Shape<RW>::THREADS + 32, RW == 8 ? 1 : 2) k
     const uint32_t bit_bytes = has_bits ? (uint32_t)(((tn.n0 - r4 + nT) * 4 + 15) & ~15) : 0u;
     tinfo[2 * s] = tn.n0;
     tinfo[2 * s + 1] = tn.n1;
-    mbar_expect_tx(&in_full[s], LV_TILE + (uint32_t)nT * 16u + ci_bytes + bit_bytes);
-    tma_load_rows(st, &in_map, tn.n0, &in_full[s]);
+    const int rn = tn.n0 & ~(nalign - 1);
+    const uint32_t in_bytes = narrow ? (uint32_t)(((tn.n0 - rn + nT) * cout * 4 + 15) & ~15) : LV_TILE;
+    mbar_expect_tx(&in_full[s], in_bytes + (uint32_t)nT * 16u + ci_bytes + bit_bytes);
+    if (narrow) bulk_g2s(st, reinterpret_cast<const char*>(a.in) + (size_t)rn * cout * 4, in_bytes, &in_full[s]);
+    else tma_load_rows(st, &in_map, tn.n0, &in_full[s]);
     bulk_g2s(st + Sm::ST_W, reinterpret_cast<const char*>(g.ell_w) + (size_t)tn.n0 * 16, (uint32_t)nT * 16u, &in_full[s]);
     bulk_g2s(st + Sm::ST_CI, reinterpret_cast<const char*>(g.ell_ci) + (size_t)r2 * 8, ci_bytes, &in_full[s]);
     if (has_bits) bulk_g2s(st + Sm::ST_BITS, reinterpret_cast<const char*>(a.in_bits) + (size_t)r4 * 4, bit_bytes, &in_full[s]);
@@ -331,14 +338,33 @@ __global__ void __launch_bounds__(Tc2Shape<RW>::THREADS + 32, RW == 8 ? 1 : 2) k
       float xr[HF];
       RowTopo tp;
       {
-        const uint32_t code = tc::row_code(row);
+        if (narrow) {
+          const float* p = reinterpret_cast<const float*>(st) + ((uint32_t)(n0 & (nalign - 1)) + row) * (uint32_t)cout;
 #pragma unroll
-        for (uint32_t q = 0; q < 4; ++q) {
-          const float4 v = *reinterpret_cast<const float4*>(st + (code ^ ((half * 4 + q) << 4)));
-          xr[4 * q] = v.x;
-          xr[4 * q + 1] = v.y;
-          xr[4 * q + 2] = v.z;
-          xr[4 * q + 3] = v.w;
+          for (int c = 0; c < HF; ++c) xr[c] = 0.0f;
+          if (half == 0) {
+            if (cout == 8) {
+              const float4 v0 = *reinterpret_cast<const float4*>(p), v1 = *reinterpret_cast<const float4*>(p + 4);
+              xr[0] = v0.x, xr[1] = v0.y, xr[2] = v0.z, xr[3] = v0.w, xr[4] = v1.x, xr[5] = v1.y, xr[6] = v1.z, xr[7] = v1.w;
+            } else if (cout == 2) {
+              const float2 v0 = *reinterpret_cast<const float2*>(p);
+              xr[0] = v0.x, xr[1] = v0.y;
+            } else {
+#pragma unroll
+              for (int c = 0; c < HF; ++c)
+                if (c < cout) xr[c] = p[c];
+            }
+          }
+        } else {
+          const uint32_t code = tc::row_code(row);
+#pragma unroll
+          for (uint32_t q = 0; q < 4; ++q) {
+            const float4 v = *reinterpret_cast<const float4*>(st + (code ^ ((half * 4 + q) << 4)));
+            xr[4 * q] = v.x;
+            xr[4 * q + 1] = v.y;
+            xr[4 * q + 2] = v.z;
+            xr[4 * q + 3] = v.w;
+          }
         }
         tp.w = *reinterpret_cast<const float4*>(st + Sm::ST_W + row * 16);
         const uint2 ci = *reinterpret_cast<const uint2*>(st + Sm::ST_CI + ((uint32_t)(n0 & 1) + row) * 8);
@@ -549,7 +575,12 @@ int dss2_tc3_launch(int mode, const Tc2Args& a, int K, cudaStream_t stream) {
   }();
   const dss2_graph_t& g = a.g;
   if (!enabled || g.num_tiles <= 0 || g.max_tile_nodes > T2_MAX || K < 1 || K > 2 || !g.ell_w || !g.ell_ci) return 1;
-  if (mode == MODE_BGX && a.cout != 32) return 1;                         // narrow grad_y rows: k_tag_tc2 loads them directly
+  static const bool narrow_ok = [] {
+    const char* e = getenv("DSS2_TC3_NARROW");
+    return !(e && e[0] == '0');
+  }();
+  // narrow grad_y rows: dense bulk copy of 2 / 4 / 8 / 16-float rows (other widths: k_tag_tc2 loads them directly)
+  if (mode == MODE_BGX && a.cout != 32 && !(narrow_ok && (a.cout == 2 || a.cout == 4 || a.cout == 8 || a.cout == 16))) return 1;
   if ((((uintptr_t)a.in | (uintptr_t)a.in_bits | (uintptr_t)a.lvl_out) & 15) != 0) return 1;   // TMA / bulk-copy alignment
   if (mode == MODE_FWD) return K == 1 ? launch_tc3_k<MODE_FWD, 1>(a, stream) : launch_tc3_k<MODE_FWD, 2>(a, stream);
   return K == 1 ? launch_tc3_k<MODE_BGX, 1>(a, stream) : launch_tc3_k<MODE_BGX, 2>(a, stream);
