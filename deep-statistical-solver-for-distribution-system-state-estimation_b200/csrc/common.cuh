@@ -15,6 +15,10 @@
 void dss2_set_error(const char* fmt, ...);
 void dss2_count_launch(int n);
 int dss2_sm_count();
+// launch priority of the kernels on the step's critical path when a second stream competes for the SMs (the two-stream backward:
+// the weight-gradient passes are fillers).  level 1: per-tile chained launches, level 2: + every TMA-fed TAG launch and the
+// EdgeAggregation backward.  0 = no attribute.  DSS2_CHAIN_PRIO selects the highest level that gets the attribute (default 1).
+int dss2_launch_priority(int level);
 
 #define DSS2_CHECK_ARG(cond, ...)            \
   do {                                       \

@@ -731,7 +731,20 @@ int launch_fwd(const EaRowArgs& a, int grid, size_t smem, cudaStream_t stream) {
 template <int SLOT>
 int launch_bwd(const EaRowArgs& a, const CUtensorMap& map, int grid, size_t smem, cudaStream_t stream) {
   DSS2_CUDA(cudaFuncSetAttribute(k_ea_row_bwd<SLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_ea_row_bwd<SLOT><<<grid, BWD_THREADS, smem, stream>>>(a, map);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(BWD_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  const int prio = dss2_launch_priority(2);   // on the step's critical path; the weight-gradient passes of the TAG layers fill in behind
+  if (prio != 0) {
+    attr[0].id = cudaLaunchAttributePriority;
+    attr[0].val.priority = prio;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+  DSS2_CUDA(cudaLaunchKernelEx(&cfg, k_ea_row_bwd<SLOT>, a, map));
   DSS2_LAUNCH_CHECK();
   return 0;
 }

@@ -1,3 +1,4 @@
+#include <cstdlib>
 // Library runtime (errors, launch counter) + batch structure kernels:
 //   dss2_graph_build  - doubled-graph CSR by destination, gcn degree norm, tiling   (networks.py:236-258, PyG gcn_norm)
 //   dss2_pack_batch   - PyG Batch.from_data_list as a gather kernel                   (dss2_run.py:68-69,134)
@@ -30,6 +31,17 @@ int dss2_sm_count() {
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
   }
   return sms;
+}
+int dss2_launch_priority(int level) {
+  static const int max_level = [] {
+    const char* e = getenv("DSS2_CHAIN_PRIO");
+    return e ? atoi(e) : 1;
+  }();
+  static const int greatest = [] {
+    int least = 0, g = 0;
+    return cudaDeviceGetStreamPriorityRange(&least, &g) == cudaSuccess ? g : 0;
+  }();
+  return level <= max_level ? greatest : 0;
 }
 extern "C" const char* dss2_last_error(void) { return g_err; }
 extern "C" int dss2_version(void) { return 100; }

@@ -543,20 +543,29 @@ int launch_tc3(const Tc2Args& a, cudaStream_t stream) {
   const size_t smem = Tc3Smem<RW>::bytes(K);
   const int grid = max(1, min(a.g.num_tiles, (RW == 8 ? 1 : 2) * dss2_sm_count()));
   DSS2_CUDA(cudaFuncSetAttribute(k_tag_tc3<MODE, K, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (a.wait_flags) {   // chained to the previous layer per tile: may start while that launch still runs (see Tc2Args)
+  {
+    // chained to the previous layer per tile (wait_flags): may start while that launch still runs (see Tc2Args)
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3((unsigned)Shape::THREADS + 32);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (a.wait_flags) {
+      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
+    const int prio = dss2_launch_priority(a.wait_flags ? 1 : 2);
+    if (prio != 0) {
+      attr[na].id = cudaLaunchAttributePriority;
+      attr[na].val.priority = prio;
+      ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = (unsigned)na;
     DSS2_CUDA(cudaLaunchKernelEx(&cfg, k_tag_tc3<MODE, K, RW>, a, map));
-  } else {
-    k_tag_tc3<MODE, K, RW><<<grid, Shape::THREADS + 32, smem, stream>>>(a, map);
   }
   DSS2_LAUNCH_CHECK();
   return 0;
