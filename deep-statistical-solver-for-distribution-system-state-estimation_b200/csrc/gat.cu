@@ -1351,3 +1351,222 @@ extern "C" int dss2_lin8_bwd(int64_t num_nodes, int M, int weight_is_out_by_in, 
   }
   return 0;
 }
+
+// -------------------------------------------------------------------------------------------------
+// gnn_dsse(model='fagcn'): FAConv (networks.py:44-50; torch_geometric.nn.conv.FAConv) at width 8 on the one-way edge list:
+//   out[i] = sum_{j -> i} tanh(att_l . x[j] + att_r . x[i]) * dinv[j] dinv[i] * x[j]  (+ the self loop, appended last)  + eps * x_0[i]
+// followed by the model's non-linearity (fused here).  Thread per bus; the attention logits of the neighbours are recomputed from their
+// rows (8 FMAs) instead of stored.  FAConv's own dropout acts on the attention coefficients; the kernels cover dropout = 0 (the default).
+// -------------------------------------------------------------------------------------------------
+namespace {
+struct FaArgs {
+  dss2_graph_t g;
+  const float* dinv;
+  int self_loops;
+  const float* x;        // [Nt, >= 8], row stride xs
+  int64_t xs;
+  const float* x0;       // [Nt, >= 8], row stride x0s
+  int64_t x0s;
+  const float *att_l, *att_r;   // [8] each
+  float eps;
+  int act;
+  float slope;
+  float* y;              // fwd: [Nt, 8]
+  const float* yout;     // bwd: the forward's y
+  const float* gy;       // bwd
+  float* gx;             // bwd: [Nt, 8] adjoint of x
+  float* acc;            // bwd, optional: acc[n] += eps * gz[n]  (the x_0 path)
+  float* partials;       // bwd: per-CTA partial sums: [0, 8) att_l, [8, 16) att_r
+  int64_t partial_stride;
+};
+__device__ __forceinline__ void fa_row(const float* p, float (&v)[GC]) {
+#pragma unroll
+  for (int c = 0; c < GC; ++c) v[c] = p[c];
+}
+__device__ __forceinline__ float fa_dot(const float (&a)[GC], const float (&b)[GC]) {
+  float d = 0.0f;
+#pragma unroll
+  for (int c = 0; c < GC; ++c) d = fmaf(a[c], b[c], d);
+  return d;
+}
+__device__ __forceinline__ float fa_act_grad(int act, float slope, float y) {
+  if (act == 1) return y > 0.0f ? 1.0f : slope;
+  if (act == 2) return y > 0.0f ? 1.0f : 0.0f;
+  if (act == 3) return 1.0f - y * y;
+  return 1.0f;
+}
+
+__global__ void __launch_bounds__(GAT_THREADS) k_fa_fwd(FaArgs a) {
+  const dss2_graph_t& g = a.g;
+  float wl[GC], wr[GC];
+  fa_row(a.att_l, wl);
+  fa_row(a.att_r, wr);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < g.num_nodes; i += (int64_t)gridDim.x * blockDim.x) {
+    const float di = a.dinv[i];
+    float xi[GC], acc[GC];
+    fa_row(a.x + i * a.xs, xi);
+    const float ar = fa_dot(xi, wr);
+#pragma unroll
+    for (int c = 0; c < GC; ++c) acc[c] = 0.0f;
+    for (int z = g.rowptr[i]; z < g.rowptr[i + 1]; ++z) {
+      if (g.eid[z] >> 31) continue;           // out-edge of i
+      const int64_t j = g.col[z];
+      float xj[GC];
+      fa_row(a.x + j * a.xs, xj);
+      const float coef = tanhf(fa_dot(xj, wl) + ar) * (a.dinv[j] * di);
+#pragma unroll
+      for (int c = 0; c < GC; ++c) acc[c] = fmaf(coef, xj[c], acc[c]);
+    }
+    if (a.self_loops) {
+      const float coef = tanhf(fa_dot(xi, wl) + ar) * (di * di);
+#pragma unroll
+      for (int c = 0; c < GC; ++c) acc[c] = fmaf(coef, xi[c], acc[c]);
+    }
+    float o[GC];
+#pragma unroll
+    for (int c = 0; c < GC; ++c) {
+      float v = a.eps != 0.0f ? fmaf(a.eps, a.x0[i * a.x0s + c], acc[c]) : acc[c];
+      if (a.act == 1) v = v > 0.0f ? v : v * a.slope;
+      else if (a.act == 2) v = fmaxf(v, 0.0f);
+      else if (a.act == 3) v = tanhf(v);
+      o[c] = v;
+    }
+    float4* dst = reinterpret_cast<float4*>(a.y + i * GC);
+    dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+    dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+  }
+}
+
+// adjoint: with gz = grad_y * act'(y) and, per edge j -> i, t = tanh(al[j] + ar[i]), c = dinv[j] dinv[i], q = (1 - t^2) c (gz[i] . x[j]):
+//   grad_x[j] += t c gz[i] + q att_l,   grad_x[i] += q att_r,   grad_att_l += q x[j],   grad_att_r += q x[i].
+// A thread owns bus n: its in-edges give the att_r terms, its out-edges (same CSR row, flagged) the att_l terms and the message adjoint.
+__global__ void __launch_bounds__(GAT_THREADS) k_fa_bwd(FaArgs a) {
+  const dss2_graph_t& g = a.g;
+  __shared__ float red[GAT_THREADS / 32][2 * GC];
+  float wl[GC], wr[GC], dwl[GC], dwr[GC];
+  fa_row(a.att_l, wl);
+  fa_row(a.att_r, wr);
+#pragma unroll
+  for (int c = 0; c < GC; ++c) dwl[c] = dwr[c] = 0.0f;
+  for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < g.num_nodes; n += (int64_t)gridDim.x * blockDim.x) {
+    const float dn = a.dinv[n];
+    float xn[GC], gzn[GC], gx[GC];
+    fa_row(a.x + n * a.xs, xn);
+#pragma unroll
+    for (int c = 0; c < GC; ++c) {
+      gzn[c] = a.gy[n * GC + c] * fa_act_grad(a.act, a.slope, a.yout ? a.yout[n * GC + c] : 0.0f);
+      gx[c] = 0.0f;
+    }
+    if (a.acc) {
+#pragma unroll
+      for (int c = 0; c < GC; ++c) a.acc[n * GC + c] += a.eps * gzn[c];
+    }
+    const float al_n = fa_dot(xn, wl), ar_n = fa_dot(xn, wr);
+    float q_l = 0.0f, q_r = 0.0f;   // sums of q over the out-edges (n is the source) and the in-edges (n is the target)
+    for (int z = g.rowptr[n]; z < g.rowptr[n + 1]; ++z) {
+      const int64_t m = g.col[z];
+      float xm[GC];
+      fa_row(a.x + m * a.xs, xm);
+      const float c = a.dinv[m] * dn;
+      if (g.eid[z] >> 31) {   // n -> m
+        float gzm[GC];
+#pragma unroll
+        for (int k = 0; k < GC; ++k) gzm[k] = a.gy[m * GC + k] * fa_act_grad(a.act, a.slope, a.yout ? a.yout[m * GC + k] : 0.0f);
+        const float t = tanhf(al_n + fa_dot(xm, wr));
+        const float tc = t * c;
+#pragma unroll
+        for (int k = 0; k < GC; ++k) gx[k] = fmaf(tc, gzm[k], gx[k]);
+        q_l += (1.0f - t * t) * c * fa_dot(gzm, xn);
+      } else {                // m -> n
+        const float t = tanhf(fa_dot(xm, wl) + ar_n);
+        q_r += (1.0f - t * t) * c * fa_dot(gzn, xm);
+      }
+    }
+    if (a.self_loops) {
+      const float t = tanhf(al_n + ar_n), c = dn * dn;
+      const float tc = t * c, q = (1.0f - t * t) * c * fa_dot(gzn, xn);
+#pragma unroll
+      for (int k = 0; k < GC; ++k) gx[k] = fmaf(tc, gzn[k], gx[k]);
+      q_l += q;
+      q_r += q;
+    }
+#pragma unroll
+    for (int k = 0; k < GC; ++k) {
+      gx[k] = fmaf(q_l, wl[k], fmaf(q_r, wr[k], gx[k]));
+      dwl[k] = fmaf(q_l, xn[k], dwl[k]);
+      dwr[k] = fmaf(q_r, xn[k], dwr[k]);
+    }
+    float4* dst = reinterpret_cast<float4*>(a.gx + n * GC);
+    dst[0] = make_float4(gx[0], gx[1], gx[2], gx[3]);
+    dst[1] = make_float4(gx[4], gx[5], gx[6], gx[7]);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < GC; ++k) {
+    const float v1 = warp_sum(dwl[k]), v2 = warp_sum(dwr[k]);
+    if (lane == 0) {
+      red[warp][k] = v1;
+      red[warp][GC + k] = v2;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * GC) {
+    float s = 0.0f;
+#pragma unroll
+    for (int w = 0; w < GAT_THREADS / 32; ++w) s += red[w][threadIdx.x];
+    a.partials[(size_t)blockIdx.x * a.partial_stride + threadIdx.x] = s;
+  }
+}
+
+int fa_fill(const char* who, FaArgs& a, const dss2_graph_t* g, const float* dinv, int self_loops, const float* x, int64_t xs, const float* x0,
+            int64_t x0s, const float* att_l, const float* att_r, float eps, int act, float slope) {
+  DSS2_CHECK_ARG(g && dinv && x && att_l && att_r && (eps == 0.0f || x0), "%s: null argument", who);
+  DSS2_CHECK_ARG(xs >= GC && (eps == 0.0f || x0s >= GC), "%s: row strides below %d", who, GC);
+  DSS2_CHECK_ARG(act >= 0 && act <= 3, "%s: act %d outside 0..3", who, act);
+  a.g = *g;
+  a.dinv = dinv;
+  a.self_loops = self_loops;
+  a.x = x;
+  a.xs = xs;
+  a.x0 = x0;
+  a.x0s = x0s;
+  a.att_l = att_l;
+  a.att_r = att_r;
+  a.eps = eps;
+  a.act = act;
+  a.slope = slope;
+  return 0;
+}
+}  // namespace
+
+extern "C" int dss2_fa_fwd(const dss2_graph_t* g, const float* dinv, int self_loops, const float* x, int64_t x_stride, const float* x0,
+                           int64_t x0_stride, const float* att_l, const float* att_r, float eps, int act, float slope, float* y,
+                           void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  FaArgs a = {};
+  if (fa_fill("dss2_fa_fwd", a, g, dinv, self_loops, x, x_stride, x0, x0_stride, att_l, att_r, eps, act, slope)) return -1;
+  DSS2_CHECK_ARG(y && ((uintptr_t)y & 15) == 0, "dss2_fa_fwd: y missing or unaligned");
+  if (g->num_nodes == 0) return 0;
+  a.y = y;
+  k_fa_fwd<<<grid_for(g->num_nodes, GAT_THREADS), GAT_THREADS, 0, stream>>>(a);
+  DSS2_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int dss2_fa_bwd(const dss2_graph_t* g, const float* dinv, int self_loops, const float* x, int64_t x_stride, const float* att_l,
+                           const float* att_r, float eps, int act, float slope, const float* y, const float* grad_y, float* grad_x,
+                           float* acc_x0, float* partials, int64_t partial_stride, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  FaArgs a = {};
+  if (fa_fill("dss2_fa_bwd", a, g, dinv, self_loops, x, x_stride, x, x_stride, att_l, att_r, eps, act, slope)) return -1;
+  DSS2_CHECK_ARG(grad_y && grad_x && partials && (!act || y) && ((uintptr_t)grad_x & 15) == 0, "dss2_fa_bwd: null or unaligned argument");
+  a.yout = y;
+  a.gy = grad_y;
+  a.gx = grad_x;
+  a.acc = acc_x0;
+  a.partials = partials;
+  a.partial_stride = partial_stride;
+  k_fa_bwd<<<dss2_num_partials(), GAT_THREADS, 0, stream>>>(a);   // every partial row is written (idle CTAs write zeros)
+  DSS2_LAUNCH_CHECK();
+  return 0;
+}

@@ -92,6 +92,8 @@ _SIGNATURES = {
     "dss2_gcn_prop8": (c_int, [_G, _P, c_int, c_int, _P, c_int64, c_float, _P, c_int64, c_float, _P, _P]),
     "dss2_lin8_fwd": (c_int, [c_int64, c_int, c_int, _P, _P, _P, _P, c_int, c_float, _P, _P]),
     "dss2_lin8_bwd": (c_int, [c_int64, c_int, c_int, _P, _P, _P, c_int, c_float, _P, _P, _P, _P, _P, c_float, _P, c_int64, c_int64, _P]),
+    "dss2_fa_fwd": (c_int, [_G, _P, c_int, _P, c_int64, _P, c_int64, _P, _P, c_float, c_int, c_float, _P, _P]),
+    "dss2_fa_bwd": (c_int, [_G, _P, c_int, _P, c_int64, _P, _P, c_float, c_int, c_float, _P, _P, _P, _P, _P, c_int64, _P]),
     "dss2_mlp2_fwd": (c_int, [c_int64, _P, c_int, _P, _P, c_int, _P, _P, c_int, _P, _P, _P]),
     "dss2_mlp2_bwd": (c_int, [c_int64, _P, c_int, _P, c_int, _P, c_int, _P, _P, _P, _P, _P, c_int64, _P]),
 }

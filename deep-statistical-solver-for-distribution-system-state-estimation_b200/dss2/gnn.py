@@ -1,8 +1,8 @@
-"""Host side of gnn_dsse (reference networks.py:11-69, the rest of SURVEY.md 8f-1): `model='gcn2'` (GCN2Conv stack, the default)
-and `model='tagcn'` (TAGConv stack) at width dim_feat == 8, followed by Linear(dim_feat, dim_dense), Linear(dim_dense, dim_out).
-Spec, flat parameter layout under the names named_parameters() reports (`model.module_{2l}.weight1`, `model.module_{2l}.lins.{k}.weight`,
+"""Host side of gnn_dsse (reference networks.py:11-69, the rest of SURVEY.md 8f-1): `model='gcn2'` (GCN2Conv stack, the default),
+`model='fagcn'` (FAConv stack, dropout 0) and `model='tagcn'` (TAGConv stack) at width dim_feat == 8, followed by Linear(dim_feat, dim_dense), Linear(dim_dense, dim_out).
+Spec, flat parameter layout under the names named_parameters() reports (`model.module_{2l}.weight1`, `.att_l.weight`, `.att_r.weight`, `.lins.{k}.weight`,
 `model.module_{2l}.bias`, the head), launch sequence, autograd bridge.  All arithmetic is in csrc/gat.cu (k_gcn_dinv, k_prop8,
-k_lin8_fwd/bwd, k_outer_reduce, the mlp2 head); there is no CPU fallback.
+k_lin8_fwd/bwd, k_fa_fwd/bwd, k_outer_reduce, the mlp2 head); there is no CPU fallback.
 
 Reference behaviours kept: the model takes the edge list AS GIVEN (one-way for the reference's data: no un-directing, networks.py:67-69),
 so the propagation is not symmetric and the backward walks the out-edges; `x_0` is the model input (networks.py:68).  Not reproduced:
@@ -22,12 +22,12 @@ ACTS = {"none": 0, "leaky_relu": 1, "relu": 2, "tanh": 3}
 
 @dataclass(frozen=True)
 class GNNSpec:
-    model: str            # 'gcn2' | 'tagcn'
+    model: str            # 'gcn2' | 'fagcn' | 'tagcn'
     dim_feat: int
     dim_dense: int
     dim_out: int
     num_layers: int
-    alpha: float = 0.1    # GCN2Conv: main_param
+    alpha: float = 0.1    # main_param: GCN2Conv's alpha, FAConv's eps
     K: int = 3            # TAGConv
     bias: bool = True     # TAGConv
     self_loops: bool = True
@@ -56,6 +56,9 @@ class GNNSpec:
             p = f"model.module_{2 * l}."
             if self.model == "gcn2":
                 put(p + "weight1", c * c)
+            elif self.model == "fagcn":
+                put(p + "att_l.weight", c)      # Linear(channels, 1, bias=False) x 2, contiguous: one 16-float gradient slot
+                put(p + "att_r.weight", c)
             else:
                 if self.bias:
                     put(p + "bias", c)
@@ -73,8 +76,8 @@ class GNNSpec:
 
 
 def validate(sp):
-    if sp.model not in ("gcn2", "tagcn"):
-        raise NotImplementedError(f"gnn_dsse kernels cover model='gcn2' and model='tagcn' (networks.py:37-53); '{sp.model}' (FAConv) is not built")
+    if sp.model not in ("gcn2", "fagcn", "tagcn"):
+        raise Exception("invalid model type")
     if sp.dim_feat != C:
         raise NotImplementedError(f"gnn_dsse kernels are built for dim_feat == {C}, got {sp.dim_feat}")
     if not (1 <= sp.dim_dense <= 32 and 1 <= sp.dim_out <= 8 and sp.num_layers >= 2):
@@ -110,7 +113,7 @@ class GNNRunner:
     def alloc(self, num_nodes, device, need_grad=True):
         sp = self.spec
         f32 = dict(dtype=torch.float32, device=device)
-        nlev = 1 if sp.model == "gcn2" else sp.K          # per layer: h (gcn2) or hop levels 1..K (tagcn)
+        nlev = sp.K if sp.model == "tagcn" else 1         # per layer: h (gcn2), hop levels 1..K (tagcn); fagcn keeps none
         b = {"dinv": torch.empty(num_nodes, **f32), "acts": torch.empty(sp.n_conv, num_nodes, C, **f32),
              "lev": torch.empty(sp.n_conv, nlev, num_nodes, C, **f32), "h": torch.empty(num_nodes, sp.dim_dense, **f32),
              "out": torch.empty(num_nodes, sp.dim_out, **f32)}
@@ -143,10 +146,16 @@ class GNNRunner:
 
     def forward(self, graph, x, xs, flat, bufs):
         sp, lib, st, g = self.spec, self.lib, _lib.stream(), graph.ref
-        loops = 1 if (sp.self_loops and sp.model == "gcn2") else 0      # TAGConv: gcn_norm(add_self_loops=False)
+        loops = 1 if (sp.self_loops and sp.model != "tagcn") else 0      # TAGConv: gcn_norm(add_self_loops=False)
         _lib.check(lib.dss2_gcn_dinv(g, loops, _lib.ptr(bufs["dinv"]), st), "dss2_gcn_dinv")
         for l in range(sp.n_conv):
             xin, stride = (x, xs) if l == 0 else (bufs["acts"][l - 1], C)
+            if sp.model == "fagcn":
+                p = f"model.module_{2 * l}."
+                _lib.check(lib.dss2_fa_fwd(g, _lib.ptr(bufs["dinv"]), loops, _lib.ptr(xin), stride, _lib.ptr(x), xs, self._p(flat, p + "att_l.weight"),
+                                           self._p(flat, p + "att_r.weight"), sp.alpha, ACTS[sp.act], sp.act_slope, _lib.ptr(bufs["acts"][l]), st),
+                           "dss2_fa_fwd")
+                continue
             if sp.model == "gcn2":
                 # h = (1 - alpha) A x + alpha x_0   (GCN2Conv.forward: x.mul_(1 - alpha); x_0 = alpha * x_0; out = x.add_(x_0))
                 _lib.check(lib.dss2_gcn_prop8(g, _lib.ptr(bufs["dinv"]), loops, 0, _lib.ptr(xin), stride, 1.0 - sp.alpha, _lib.ptr(x), xs, sp.alpha,
@@ -172,7 +181,7 @@ class GNNRunner:
         """grad_out [Nt, dim_out] dense -> flat parameter gradient; returns grad wrt x [Nt, 8]."""
         sp, lib, st, g = self.spec, self.lib, _lib.stream(), graph.ref
         part, pstride = bufs["partials"], self.flat_size
-        loops = 1 if (sp.self_loops and sp.model == "gcn2") else 0
+        loops = 1 if (sp.self_loops and sp.model != "tagcn") else 0
 
         def pp(off):
             return ctypes.c_void_p(part.data_ptr() + 4 * off)
@@ -185,6 +194,18 @@ class GNNRunner:
                    "dss2_mlp2_bwd")
         bufs["gx0"].zero_()
         for l in reversed(range(sp.n_conv)):
+            if sp.model == "fagcn":
+                p = f"model.module_{2 * l}."
+                xin, stride = (x, xs) if l == 0 else (bufs["acts"][l - 1], C)
+                gx = bufs["g8"][(sp.n_conv - l) & 1]
+                _lib.check(lib.dss2_fa_bwd(g, _lib.ptr(bufs["dinv"]), loops, _lib.ptr(xin), stride, self._p(flat, p + "att_l.weight"),
+                                           self._p(flat, p + "att_r.weight"), sp.alpha, ACTS[sp.act], sp.act_slope, _lib.ptr(bufs["acts"][l]),
+                                           _lib.ptr(gy), _lib.ptr(gx), _lib.ptr(bufs["gx0"]) if sp.alpha != 0.0 else None,
+                                           pp(self.table[p + "att_l.weight"][0]), pstride, st), "dss2_fa_bwd")
+                if l == 0 and sp.alpha != 0.0:
+                    gx.add_(bufs["gx0"])          # the x_0 path (eps * sum_l grad_z_l) joins the gradient of the model input
+                gy = gx
+                continue
             ins, strides = self._layer_inputs(bufs, l, x, xs)
             gins = [bufs["gin"][m] for m in range(sp.M)]
             w_off = self._w_off(l)

@@ -12,7 +12,7 @@ EdgeAggregation.forward (networks.py:196-200) never reaches `message` and is not
 PFN receive the same raw edge attributes; reversed edges negate attribute columns 0 and 2 (networks.py:252).
 There is no CPU fallback: without a CUDA device or the built library, forward raises.
 GAT_DSSE (networks.py:113-156, the as-shipped default of dss2_run.py:86) runs on its own fused GATv2 kernels
-(csrc/gat.cu), and so do GINE_DSSE (networks.py:71-111) and gnn_dsse (networks.py:11-69; model='gcn2' and 'tagcn').
+(csrc/gat.cu), and so do GINE_DSSE (networks.py:71-111) and gnn_dsse (networks.py:11-69; model='gcn2', 'fagcn' and 'tagcn').
 """
 import math
 
@@ -171,12 +171,22 @@ class _GCN2Params(nn.Module):
         nn.init.xavier_uniform_(self.weight1)
 
 
+class _FAParams(nn.Module):
+    """Parameter holder with PyG FAConv's names / shapes / initialisation: `att_l`, `att_r` = Linear(channels, 1, bias=False)."""
+
+    def __init__(self, channels):
+        super().__init__()
+        self.att_l = nn.Linear(channels, 1, bias=False)
+        self.att_r = nn.Linear(channels, 1, bias=False)
+
+
 class gnn_dsse(_LazyMachinery, nn.Module):
     """networks.py:11-69: (num_layers - 1) x [conv + nonlin], Linear(dim_feat, dim_dense), Linear(dim_dense, dim_out) in a PyG `Sequential`
     (children `module_{i}`), `forward(x, edge_index)` with x_0 = x.  conv = GCN2Conv(channels, alpha=main_param, theta, shared_weights,
-    cached, normalize, add_self_loops) for model='gcn2' (the default) or TAGConv(channels, channels, K, bias, normalize) for
-    model='tagcn'.  Built for what the reference's defaults select (theta=None, shared_weights=True, normalize=True, dropout 0);
-    model='fagcn' and the other settings raise.  `cached=True` is accepted and ignored: the normalisation is recomputed per batch."""
+    cached, normalize, add_self_loops) for model='gcn2' (the default), FAConv(channels, eps=main_param, dropout, cached, normalize,
+    add_self_loops) for model='fagcn', or TAGConv(channels, channels, K, bias, normalize) for model='tagcn'.  Built for what the
+    reference's defaults select (theta=None, shared_weights=True, normalize=True, dropout 0); the other settings raise.
+    `cached=True` is accepted and ignored: the normalisation is recomputed per batch."""
 
     def __init__(self, dim_feat, dim_dense, dim_out, num_layers, nonlin='leaky_relu', main_param=0.1, K=3, bias=True, dropout=0., theta=None,
                  shared_weights=True, cached=True, add_self_loops=True, normalize=True, model='gcn2'):
@@ -185,8 +195,9 @@ class gnn_dsse(_LazyMachinery, nn.Module):
             raise Exception('invalid activation type')
         if model not in ('gcn2', 'fagcn', 'tagcn'):
             raise Exception('invalid model type')
-        if model == 'fagcn':
-            raise NotImplementedError("gnn_dsse(model='fagcn') (FAConv, networks.py:44-50) is not built; 'gcn2' and 'tagcn' are")
+        if model == 'fagcn' and dropout != 0.:
+            raise NotImplementedError("gnn_dsse(model='fagcn') kernels cover dropout=0 (FAConv's dropout acts on the attention coefficients, "
+                                      "networks.py:46; the reference default is 0)")
         if theta is not None or not shared_weights or not normalize:
             raise NotImplementedError("gnn_dsse kernels cover theta=None, shared_weights=True, normalize=True (the reference's defaults)")
         self.channels, self.main_param, self.dim_out, self.K, self.dropout, self.bias = dim_feat, main_param, dim_out, K, dropout, bias
@@ -196,7 +207,8 @@ class gnn_dsse(_LazyMachinery, nn.Module):
         self.model = nn.Module()
         i = 0
         for _ in range(num_layers - 1):
-            self.model.add_module(f"module_{i}", _GCN2Params(dim_feat) if model == 'gcn2' else TAGConv(dim_feat, dim_feat, K=K, bias=bias))
+            conv = _GCN2Params(dim_feat) if model == 'gcn2' else _FAParams(dim_feat) if model == 'fagcn' else TAGConv(dim_feat, dim_feat, K=K, bias=bias)
+            self.model.add_module(f"module_{i}", conv)
             self.model.add_module(f"module_{i + 1}", self.nonlin)
             i += 2
         self.model.add_module(f"module_{i}", nn.Linear(dim_feat, dim_dense))

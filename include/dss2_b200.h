@@ -367,7 +367,7 @@ int dss2_mlp2_bwd(int64_t num_nodes, const float* x, int din, const float* w1, i
                   void* stream);
 
 /* ------------------------------------------------------------------------------------------------
- * gnn_dsse building blocks (networks.py:11-69: GCN2Conv / TAGConv stacks at width dim_feat <= 8 on the one-way edge list as given).
+ * gnn_dsse building blocks (networks.py:11-69: GCN2Conv / TAGConv / FAConv stacks at width dim_feat <= 8 on the one-way edge list as given).
  * dss2_gcn_dinv: gcn_norm's deg^-1/2 per bus (in-degree, + 1 with add_self_loops; inf -> 0).
  * dss2_gcn_prop8: out = scale * (A_hat x) + add_scale * add with A_hat = D^-1/2 (A [+ I]) D^-1/2 over the in-edges in PyG's scatter
  *   order (self loop last), or - transposed != 0 - over the out-edges (adjoint).  Rows are 8 floats (zero padded), x with row stride.
@@ -384,6 +384,16 @@ int dss2_lin8_fwd(int64_t num_nodes, int M, int weight_is_out_by_in, const float
 int dss2_lin8_bwd(int64_t num_nodes, int M, int weight_is_out_by_in, const float* const* in, const int64_t* in_strides, const float* w,
                   int act, float slope, const float* y, const float* grad_y, float* grad_z, float* const* grad_in, float* acc,
                   float acc_scale, float* partials, int64_t partial_stride, int64_t bias_offset, void* stream);
+
+/* gnn_dsse(model='fagcn') (networks.py:44-50, torch_geometric FAConv with dropout = 0) at width 8 on the one-way edge list:
+ *   y[i] = act( sum_{j -> i} tanh(att_l . x[j] + att_r . x[i]) dinv[j] dinv[i] x[j]  (+ self loop, last)  + eps x0[i] ).
+ * dss2_fa_bwd: grad_x (adjoint of x, message and attention paths), optionally acc_x0 += eps * grad_z (the x_0 path), and per-CTA
+ * partial sums of the attention gradients at partials[0..8) (att_l) and partials[8..16) (att_r), dss2_num_partials() rows. */
+int dss2_fa_fwd(const dss2_graph_t* g, const float* dinv, int self_loops, const float* x, int64_t x_stride, const float* x0,
+                int64_t x0_stride, const float* att_l, const float* att_r, float eps, int act, float slope, float* y, void* stream);
+int dss2_fa_bwd(const dss2_graph_t* g, const float* dinv, int self_loops, const float* x, int64_t x_stride, const float* att_l,
+                const float* att_r, float eps, int act, float slope, const float* y, const float* grad_y, float* grad_x,
+                float* acc_x0, float* partials, int64_t partial_stride, void* stream);
 
 #ifdef __cplusplus
 }

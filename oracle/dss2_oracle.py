@@ -337,7 +337,8 @@ def init_gine_state_dict(dim_feat=8, dim_dense=32, dim_out=2, num_layers=8, edge
 # --------------------------------------------------------------------------------------------
 # gnn_dsse (networks.py:11-69): (num_layers - 1) x [conv + nonlin], Linear(dim_feat, dim_dense), Linear(dim_dense, dim_out);
 # forward(x, edge_index) with x_0 = x, on the edge list AS GIVEN (no un-directing).  model='gcn2': GCN2Conv(channels, alpha,
-# shared_weights=True, add_self_loops, normalize); model='tagcn': TAGConv(channels, channels, K, bias, normalize).
+# shared_weights=True, add_self_loops, normalize); model='fagcn': FAConv(channels, eps, dropout, add_self_loops, normalize);
+# model='tagcn': TAGConv(channels, channels, K, bias, normalize).
 # --------------------------------------------------------------------------------------------
 
 
@@ -363,6 +364,17 @@ def gnn_dsse_forward(sd, x, edge_index, num_layers, model="gcn2", alpha=0.1, K=3
             prop = segment_sum(w.view(-1, 1) * h[ei[0]], ei[1], n)          # GCN2Conv.message / aggr='add'
             out = prop * (1 - alpha) + alpha * x0                           # x.mul_(1 - alpha); x_0 = alpha * x_0; x.add_(x_0)
             h = out @ sd[p + "weight1"]                                     # addmm(out, out, weight1, beta=0, alpha=1)
+        elif model == "fagcn":
+            # FAConv (PyG): out_i = sum_{j -> i} tanh(att_l x_j + att_r x_i) w_ji x_j + eps x_0_i; `alpha` is FAConv's eps (networks.py:46)
+            if add_self_loops:
+                ei, w = gcn_norm_self_loops(edge_index, n, x.dtype)
+            else:
+                ei, w = edge_index, gcn_weights(edge_index, n, x.dtype)
+            al, ar = h @ sd[p + "att_l.weight"].t(), h @ sd[p + "att_r.weight"].t()
+            coef = torch.tanh(al[ei[0]] + ar[ei[1]]).squeeze(-1) * w
+            h = segment_sum(coef.view(-1, 1) * h[ei[0]], ei[1], n)
+            if alpha != 0.0:
+                h = h + alpha * x0
         elif model == "tagcn":
             ws = []
             k = 0
@@ -391,6 +403,9 @@ def init_gnn_state_dict(model="gcn2", dim_feat=8, dim_dense=32, dim_out=2, num_l
         p = f"model.module_{2 * l}."
         if model == "gcn2":
             sd[p + "weight1"] = u(c, c, bound=math.sqrt(6.0 / (2 * c)))
+        elif model == "fagcn":
+            sd[p + "att_l.weight"] = u(1, c, bound=1.0 / math.sqrt(c))
+            sd[p + "att_r.weight"] = u(1, c, bound=1.0 / math.sqrt(c))
         else:
             sd[p + "bias"] = u(c, bound=0.1)
             for k in range(K + 1):

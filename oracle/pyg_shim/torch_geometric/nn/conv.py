@@ -39,6 +39,8 @@ class MessagePassing(nn.Module):
         for name in self._msg_args:
             if name.endswith("_j") or name.endswith("_i"):
                 base = kwargs[name[:-2]]
+                if isinstance(base, (tuple, list)):      # PyG: a pair (source-side tensor, target-side tensor)
+                    base = base[0] if name.endswith("_j") else base[1]
                 if num_nodes is None:
                     num_nodes = base.size(self.node_dim)
                 call[name] = base.index_select(self.node_dim, src if name.endswith("_j") else dst)
@@ -177,7 +179,44 @@ class GCN2Conv(MessagePassing):
         return x_j if edge_weight is None else edge_weight.view(-1, 1) * x_j
 
 
-FAConv = _outside_hot_path("FAConv")
+class FAConv(MessagePassing):
+    """PyG FAConv(channels, eps=0.1, dropout=0.0, cached=False, add_self_loops=True, normalize=True), as used at reference
+    networks.py:44-50: att_l, att_r = Linear(channels, 1, bias=False);
+      forward(x, x_0, edge_index): gcn_norm(add_self_loops) (cached after the first call when cached=True);
+      out = propagate(x=x, alpha=(att_l(x), att_r(x)), edge_weight);  out = out + eps * x_0  (when eps != 0);
+      message: x_j * (dropout(tanh(alpha_j + alpha_i)) * edge_weight)  with alpha_j = att_l(x)[source], alpha_i = att_r(x)[target]."""
+
+    def __init__(self, channels, eps=0.1, dropout=0.0, cached=False, add_self_loops=True, normalize=True, **kwargs):
+        kwargs.setdefault("aggr", "add")
+        super().__init__(**kwargs)
+        self.channels, self.eps, self.dropout = channels, eps, dropout
+        self.cached, self.normalize, self.add_self_loops_ = cached, normalize, add_self_loops
+        self._cached_edge_index = None
+        self.att_l = torch.nn.Linear(channels, 1, bias=False)
+        self.att_r = torch.nn.Linear(channels, 1, bias=False)
+
+    def forward(self, x, x_0, edge_index, edge_weight=None):
+        if self.normalize:
+            assert edge_weight is None
+            cache = self._cached_edge_index
+            if cache is None:
+                edge_index, edge_weight = gcn_norm(edge_index, None, x.size(self.node_dim), False, self.add_self_loops_, self.flow, dtype=x.dtype)
+                if self.cached:
+                    self._cached_edge_index = (edge_index, edge_weight)
+            else:
+                edge_index, edge_weight = cache
+        else:
+            assert edge_weight is not None
+        out = self.propagate(edge_index, x=x, alpha=(self.att_l(x), self.att_r(x)), edge_weight=edge_weight)
+        if self.eps != 0.0:
+            out = out + self.eps * x_0
+        return out
+
+    def message(self, x_j, alpha_j, alpha_i, edge_weight):
+        alpha = (alpha_j + alpha_i).squeeze(-1).tanh()
+        alpha = torch.nn.functional.dropout(alpha, p=self.dropout, training=self.training)
+        return x_j * (alpha * edge_weight).view(-1, 1)
+
 
 class GINEConv(MessagePassing):
     """PyG GINEConv(nn, eps=0., train_eps=False, edge_dim=None), as used at reference networks.py:100:

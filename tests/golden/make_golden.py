@@ -151,7 +151,7 @@ def run_gat(tag, batch, stats, sd_seed, num_layers=8, **opts):
 
 
 def run_gnn(tag, model, batch, stats, sd_seed, num_layers=4, K=3):
-    """Reference gnn_dsse (networks.py:11-69; model='gcn2' or 'tagcn', defaults otherwise; cached=False so that the run does not depend
+    """Reference gnn_dsse (networks.py:11-69; model='gcn2', 'fagcn' or 'tagcn', defaults otherwise; cached=False so that the run does not depend
     on call history) forward + gsp_wls_edge + backward on `batch`.  forward(x, edge_index): the one-way edge list as the script has it."""
     sd = orc.init_gnn_state_dict(model=model, num_layers=num_layers, K=K, seed=sd_seed)
     net = ref_net.gnn_dsse(dim_feat=8, dim_dense=32, dim_out=2, num_layers=num_layers, K=K, cached=False, model=model)
@@ -320,6 +320,7 @@ def main():
     run_gine("gine_traineps_cigre", Batch.from_data_list(ds[65:69]), stats, sd_seed=33, num_layers=4, eps=0.1, train_eps=True)
     run_gnn("gnn_gcn2_cigre", "gcn2", Batch.from_data_list(ds[70:76]), stats, sd_seed=21)
     run_gnn("gnn_tagcn_cigre", "tagcn", Batch.from_data_list(ds[80:85]), stats, sd_seed=22)
+    run_gnn("gnn_fagcn_cigre", "fagcn", Batch.from_data_list(ds[94:100]), stats, sd_seed=24)
 
     # ---- Oberrhein: synthetic scenarios from the product generator, reference model + loss on top ----
     grid = synth.load_grid("ober_sub")
@@ -331,6 +332,7 @@ def main():
     run_gat("gat_ober", ob, ostats, sd_seed=7)
     run_gine("gine_ober", ob, ostats, sd_seed=9)
     run_gnn("gnn_gcn2_ober", "gcn2", ob, ostats, sd_seed=23, num_layers=8)
+    run_gnn("gnn_fagcn_ober", "fagcn", ob, ostats, sd_seed=25, num_layers=5)
     # a far-from-solution output so that all three soft-constraint penalties are active
     torch.manual_seed(99)
     wild = torch.stack([torch.randn(ob.x.shape[0]) * 3.0, torch.randn(ob.x.shape[0]) * 0.8], 1).requires_grad_(True)

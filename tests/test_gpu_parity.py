@@ -1386,10 +1386,10 @@ def test_dss2_run_flow_with_default_gat_model(env):
 
 
 # ------------------------------------------------------------------------------------------------ gnn_dsse (rest of scope row 8f-1)
-@pytest.mark.parametrize("tag", ["gnn_gcn2_cigre", "gnn_tagcn_cigre", "gnn_gcn2_ober"])
+@pytest.mark.parametrize("tag", ["gnn_gcn2_cigre", "gnn_tagcn_cigre", "gnn_gcn2_ober", "gnn_fagcn_cigre", "gnn_fagcn_ober"])
 @pytest.mark.parametrize("where", ["cuda", "cpu"])
 def test_gnn_dsse_matches_reference_run(env, tag, where):
-    """networks.gnn_dsse (model='gcn2' / 'tagcn'; thread-per-bus propagation and 8x8 transform kernels) with the weights of the reference
+    """networks.gnn_dsse (model='gcn2' / 'tagcn' / 'fagcn'; thread-per-bus propagation, attention and 8x8 transform kernels) with the weights of the reference
     run: model output against the reference's own gnn_dsse executed over the shim (golden), the loss kernel on the output it received,
     every parameter gradient on the upstream gradient the reference run recorded (strict) and end to end through the loss, and the
     gradient w.r.t. x (x feeds both the first layer and, as x_0, every GCN2Conv).  fp64 oracle as arbiter."""

@@ -58,7 +58,7 @@ def test_no_cpu_fallback():
     with pytest.raises(_lib.Dss2Error):
         gnn(torch.zeros(4, 8), torch.tensor([[0, 1], [1, 2]]))
     with pytest.raises(NotImplementedError):
-        networks.gnn_dsse(dim_feat=8, dim_dense=32, dim_out=2, num_layers=3, model='fagcn')
+        networks.gnn_dsse(dim_feat=8, dim_dense=32, dim_out=2, num_layers=3, model='fagcn', dropout=0.1)
     gine = networks.GINE_DSSE(dim_feat=8, dim_dense=32, dim_out=2, num_layers=3, edge_dim=6)
     with pytest.raises(_lib.Dss2Error):
         gine(torch.zeros(4, 8), torch.tensor([[0, 1], [1, 2]]), torch.zeros(2, 6))
@@ -138,12 +138,12 @@ def test_data_parallel_plumbing_gloo_world2():
 
 
 def test_gnn_dsse_state_dict_names_match_reference_layout():
-    """Parameter names / shapes of gnn_dsse ('gcn2', 'tagcn') equal the reference's (PyG Sequential naming; the goldens hold the
+    """Parameter names / shapes of gnn_dsse ('gcn2', 'tagcn', 'fagcn') equal the reference's (PyG Sequential naming; the goldens hold the
     reference's own named_parameters()), and the flat layout covers all of them."""
     import dss2_oracle as orc
     from conftest import golden_gat
     from dss2 import gnn
-    for tag in ("gnn_gcn2_cigre", "gnn_tagcn_cigre"):
+    for tag in ("gnn_gcn2_cigre", "gnn_tagcn_cigre", "gnn_fagcn_cigre"):
         nl, sd, _, z = golden_gat(tag)
         m = networks.gnn_dsse(dim_feat=8, dim_dense=32, dim_out=2, num_layers=nl, K=int(z["K"]), model=str(z["model"]))
         ours = {k: tuple(v.shape) for k, v in m.named_parameters()}

@@ -161,7 +161,7 @@ def test_gine_dsse_forward_backward_vs_reference(tag):
         assert_fp32_parity(g, g32[name], g64[name], name)
 
 
-@pytest.mark.parametrize("tag", ["gnn_gcn2_cigre", "gnn_tagcn_cigre", "gnn_gcn2_ober"])
+@pytest.mark.parametrize("tag", ["gnn_gcn2_cigre", "gnn_tagcn_cigre", "gnn_gcn2_ober", "gnn_fagcn_cigre", "gnn_fagcn_ober"])
 def test_gnn_dsse_forward_backward_vs_reference(tag):
     """Oracle gnn_dsse (GCN2Conv / TAGConv stacks on the one-way edge list + 2 Linear) + loss + autograd == the reference's gnn_dsse run
     over the shim (same weights): the reference's recorded run must sit within fp32 noise of the fp64 oracle."""
