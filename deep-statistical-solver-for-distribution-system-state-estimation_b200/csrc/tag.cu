@@ -566,20 +566,38 @@ int launch_hop(const dss2_graph_t* g, const float* X, float* Y, cudaStream_t s) 
   return 0;
 }
 
-__global__ void k_reduce_partials(const float* __restrict__ partials, int64_t stride, int num, int64_t count, float* grad, int accumulate) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+// grad[i] = sum over the per-CTA partial rows, in a fixed order: 8 row groups per column (row r in group r % 8) summed in parallel,
+// then the 8 group sums in group order.  148 dependent loads per thread made the one-group version latency bound (~20 us per launch
+// whatever the column count); the per-sub-net launches of the two-stream backward are short.
+constexpr int RP_COLS = 32, RP_GROUPS = 8;
+__global__ void __launch_bounds__(RP_COLS* RP_GROUPS) k_reduce_partials(const float* __restrict__ partials, int64_t stride, int num, int64_t count,
+                                                                        float* grad, int accumulate) {
+  __shared__ float red[RP_GROUPS][RP_COLS];
+  const int cx = threadIdx.x & (RP_COLS - 1), gy = threadIdx.x / RP_COLS;
+  for (int64_t base = (int64_t)blockIdx.x * RP_COLS; base < count; base += (int64_t)gridDim.x * RP_COLS) {
+    const int64_t i = base + cx;
     float s = 0.0f;
-    int c = 0;
-    for (; c + 4 <= num; c += 4) {
-      float v0 = partials[(size_t)c * stride + i], v1 = partials[(size_t)(c + 1) * stride + i];
-      float v2 = partials[(size_t)(c + 2) * stride + i], v3 = partials[(size_t)(c + 3) * stride + i];
-      s += v0;
-      s += v1;
-      s += v2;
-      s += v3;
+    if (i < count) {
+      int c = gy;
+      for (; c + 3 * RP_GROUPS < num; c += 4 * RP_GROUPS) {
+        const float v0 = partials[(size_t)c * stride + i], v1 = partials[(size_t)(c + RP_GROUPS) * stride + i];
+        const float v2 = partials[(size_t)(c + 2 * RP_GROUPS) * stride + i], v3 = partials[(size_t)(c + 3 * RP_GROUPS) * stride + i];
+        s += v0;
+        s += v1;
+        s += v2;
+        s += v3;
+      }
+      for (; c < num; c += RP_GROUPS) s += partials[(size_t)c * stride + i];
     }
-    for (; c < num; ++c) s += partials[(size_t)c * stride + i];
-    grad[i] = accumulate ? grad[i] + s : s;
+    red[gy][cx] = s;
+    __syncthreads();
+    if (gy == 0 && i < count) {
+      float t = red[0][cx];
+#pragma unroll
+      for (int q = 1; q < RP_GROUPS; ++q) t += red[q][cx];
+      grad[i] = accumulate ? grad[i] + t : t;
+    }
+    __syncthreads();
   }
 }
 
@@ -782,8 +800,8 @@ extern "C" int dss2_reduce_partials(const float* partials, int64_t partial_strid
   cudaStream_t stream = (cudaStream_t)stream_;
   DSS2_CHECK_ARG(partials && grad && num_partials >= 1 && count >= 0, "dss2_reduce_partials: bad argument");
   if (count == 0) return 0;
-  int grid = (int)max((int64_t)1, min((int64_t)148 * 8, (count + 127) / 128));
-  k_reduce_partials<<<grid, 128, 0, stream>>>(partials, partial_stride, num_partials, count, grad, accumulate);
+  int grid = (int)max((int64_t)1, min((int64_t)148 * 8, (count + RP_COLS - 1) / RP_COLS));
+  k_reduce_partials<<<grid, RP_COLS * RP_GROUPS, 0, stream>>>(partials, partial_stride, num_partials, count, grad, accumulate);
   DSS2_LAUNCH_CHECK();
   return 0;
 }

@@ -197,14 +197,19 @@ class PFNRunner:
         return bufs["outs"][-1]
 
     # ---- backward ----
-    def backward(self, graph, x, x_stride, ea, ea_stride, flat, bufs, grad_out, flat_grad, accumulate=False, ea_uploaded=False, rng_state=None):
+    def backward(self, graph, x, x_stride, ea, ea_stride, flat, bufs, grad_out, flat_grad, accumulate=False, ea_uploaded=False, rng_state=None,
+                 bucket_hook=None):
         """grad_out [Nt, dim_out] dense.  Writes the flat parameter gradient into flat_grad.  ea_uploaded: the constant-memory slots
         still hold this model's EdgeAggregation weights (the captured step: forward and backward of one step, nothing in between).
-        rng_state (device {seed, step}) with buffers from alloc(pipelined=True) selects the two-stream schedule (_backward_pipelined)."""
+        rng_state (device {seed, step}) with buffers from alloc(pipelined=True) selects the two-stream schedule (_backward_pipelined).
+        bucket_hook(lo, hi): two-stream schedule only - called on the second stream once flat_grad[lo:hi] (one sub-net) is final, e.g. to
+        all-reduce it while the next sub-net's backward runs; self.bucketed tells whether the hook was used."""
         sp, lib, st = self.spec, self.lib, _lib.stream()
+        self.bucketed = False
         if (CHAIN_BWD and rng_state is not None and "gchain" in bufs and TAG_IMPL == "tc2" and GW_IMPL == "tc"
                 and bool(lib.dss2_tag_tc2_supported(graph.ref, sp.K))):
-            return self._backward_pipelined(graph, x, x_stride, ea, ea_stride, flat, bufs, grad_out, flat_grad, accumulate, ea_uploaded, rng_state)
+            return self._backward_pipelined(graph, x, x_stride, ea, ea_stride, flat, bufs, grad_out, flat_grad, accumulate, ea_uploaded, rng_state,
+                                            bucket_hook)
         g = graph.ref
         slots = self.ea_slots(graph, x_stride, ea_stride)
         if slots and not ea_uploaded:
@@ -257,12 +262,24 @@ class PFNRunner:
                                             1 if accumulate else 0, st), "dss2_reduce_partials")
         return flat_grad
 
-    def _backward_pipelined(self, graph, x, x_stride, ea, ea_stride, flat, bufs, grad_out, flat_grad, accumulate, ea_uploaded, rng_state):
+    def _subnet_range(self, s):
+        """[lo, hi) of sub-net s in the flat parameter buffer (the layout is ordered by sub-net)."""
+        sp = self.spec
+        lo = min(off for name, (off, _) in self.table.items() if name.startswith(sp.prefix_fmt.format(s=s)))
+        if s + 1 < sp.L:
+            hi = min(off for name, (off, _) in self.table.items() if name.startswith(sp.prefix_fmt.format(s=s + 1)))
+        else:
+            hi = self.flat_size
+        return (0 if s == 0 else lo), hi
+
+    def _backward_pipelined(self, graph, x, x_stride, ea, ea_stride, flat, bufs, grad_out, flat_grad, accumulate, ea_uploaded, rng_state,
+                            bucket_hook=None):
         """Same arithmetic as backward(), scheduled on two streams.  The backward-to-input launches of a sub-net form a per-tile chain on
         the current stream (layer l-1 needs only the same tile of layer l's output: dss2_tag_bwd_tc2_gx_chain); the weight-gradient pass
         of each layer needs that layer's whole launch (its spilled hop levels), so it runs behind an event on a second stream and fills
         the SMs the chain leaves idle.  Every layer keeps its own input gradient and level workspace until its pass has run; the streams
-        join before the next sub-net reuses them.  Each kernel still writes only its own columns of the per-CTA partials."""
+        join before the next sub-net reuses them.  Each kernel still writes only its own columns of the per-CTA partials, and the
+        partial reduction of a sub-net's columns (+ bucket_hook: its all-reduce) runs on the second stream under the next sub-net."""
         sp, lib = self.spec, self.lib
         g = graph.ref
         main = torch.cuda.current_stream()
@@ -281,13 +298,13 @@ class PFNRunner:
         G, LV, marks = bufs["gchain"], bufs["lvls"], bufs["marks_b"]
         nws = LV[0].numel() * 4
         gy = grad_out
-        forked = False
+        ev_gw = None
         for s in reversed(range(sp.L)):
             pre = sp.prefix_fmt.format(s=s)
             xin, xs = (x, x_stride) if s == 0 else (bufs["outs"][s - 1], sp.fn)
             g_sub = gy
-            if forked:
-                main.wait_stream(side)      # the previous sub-net's weight-gradient passes have read G / LV / g_sub
+            if ev_gw is not None:
+                main.wait_event(ev_gw)      # the previous sub-net's weight-gradient passes have read G / LV / g_sub
             for l in reversed(range(sp.n_layers)):
                 last = l == sp.n_layers - 1
                 cout = sp.out_dim(s) if last else HID
@@ -301,7 +318,6 @@ class PFNRunner:
                 ev = torch.cuda.Event()
                 ev.record(main)
                 side.wait_event(ev)
-                forked = True
                 _lib.check(lib.dss2_tag_bwd_tc2_gw(graph.num_nodes, _lib.ptr(bufs["acts"][s, l]), cout, sp.K, act, sp.p_drop, bits, _lib.ptr(gy),
                                                    pp(pre + f"convs.{l}.lins.0.weight"), pstride, b_off - w_off, _lib.ptr(LV[l]), nws, st2),
                            "dss2_tag_bwd_tc2_gw")
@@ -319,10 +335,20 @@ class PFNRunner:
                                                 _lib.ptr(gy), _lib.ptr(skip_grad), sp.fn if skip_grad is not None else 0,
                                                 _lib.ptr(gprev), pp(pre + "edge_aggr.edge_aggr.0.weight"), pstride, st), "dss2_edgeagg_bwd")
             gy = gprev
-        if forked:
-            main.wait_stream(side)
-        _lib.check(lib.dss2_reduce_partials(_lib.ptr(part), pstride, self.num_partials, self.flat_size, _lib.ptr(flat_grad),
-                                            1 if accumulate else 0, st), "dss2_reduce_partials")
+            ev_gw = torch.cuda.Event()
+            ev_gw.record(side)
+            # this sub-net's columns are final once its EdgeAggregation backward (this stream) and weight-gradient passes (second stream) are
+            ev = torch.cuda.Event()
+            ev.record(main)
+            side.wait_event(ev)
+            lo, hi = self._subnet_range(s)
+            _lib.check(lib.dss2_reduce_partials(ctypes.c_void_p(part.data_ptr() + 4 * lo), pstride, self.num_partials, hi - lo,
+                                                ctypes.c_void_p(flat_grad.data_ptr() + 4 * lo), 1 if accumulate else 0, st2), "dss2_reduce_partials")
+            if bucket_hook is not None:
+                with torch.cuda.stream(side):
+                    bucket_hook(lo, hi)
+        main.wait_stream(side)
+        self.bucketed = bucket_hook is not None
         return flat_grad
 
 
