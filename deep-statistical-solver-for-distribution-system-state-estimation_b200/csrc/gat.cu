@@ -41,8 +41,9 @@ struct GatArgs {
   const float* gy;
   float* ws;          // [Nt][GAT_NODE_WS]
   float* gx;
-  float* partials;
+  float* partials;     // k_gat_bwd: the lin_edge.w block of the partial row
   int64_t partial_stride;
+  int64_t off_att, off_bias;   // k_gat_bwd: att and bias blocks relative to `partials`
 };
 
 __device__ __forceinline__ void load_weights(GatW& w, const GatArgs& a) {
@@ -378,7 +379,8 @@ __global__ void __launch_bounds__(GAT_THREADS) k_gat_bwd(GatArgs a) {
     float s = 0.0f;
 #pragma unroll
     for (int wv = 0; wv < GAT_THREADS / 32; ++wv) s += red[wv][src];
-    part[i] = s;
+    const int j = i - GC * a.fe;
+    part[j < 0 ? (int64_t)i : j < GC ? a.off_att + j : a.off_bias + (j - GC)] = s;
   }
 }
 
@@ -1059,21 +1061,26 @@ extern "C" int dss2_gat_fwd(const dss2_graph_t* g, const float* x, int64_t x_str
   return 0;
 }
 
-extern "C" int dss2_gat_bwd(const dss2_graph_t* g, const float* x, int64_t x_stride, const float* edge_attr, int64_t ea_stride, int fe,
-                            const float* lin_l_w, const float* lin_l_b, const float* lin_r_w, const float* lin_r_b,
-                            const float* lin_edge_w, const float* att, const float* bias, float att_slope, int act, float act_slope,
-                            const float* y, const float* grad_y, float* grad_x, float* node_ws, size_t node_ws_bytes, float* partials,
-                            int64_t partial_stride, void* stream_) {
+// part_off[7]: offsets (floats, relative to `partials`) of the blocks [lin_l.w 64, lin_l.b 8, lin_r.w 64, lin_r.b 8, lin_edge.w 8 fe, att 8,
+// bias 8] inside a partial row: one head of a multi-head layer writes into that head's slice of every parameter.
+extern "C" int dss2_gat_bwd_ex(const dss2_graph_t* g, const float* x, int64_t x_stride, const float* edge_attr, int64_t ea_stride, int fe,
+                               const float* lin_l_w, const float* lin_l_b, const float* lin_r_w, const float* lin_r_b,
+                               const float* lin_edge_w, const float* att, const float* bias, float att_slope, int act, float act_slope,
+                               const float* y, const float* grad_y, float* grad_x, float* node_ws, size_t node_ws_bytes, float* partials,
+                               int64_t partial_stride, const int64_t* part_off, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   GatArgs a = {};
   if (fill_args("dss2_gat_bwd", a, g, x, x_stride, edge_attr, ea_stride, fe, lin_l_w, lin_l_b, lin_r_w, lin_r_b, lin_edge_w, att, bias,
                 att_slope, act, act_slope))
     return -1;
-  DSS2_CHECK_ARG(grad_y && node_ws && partials && (!act || y), "dss2_gat_bwd: null argument");
+  DSS2_CHECK_ARG(grad_y && node_ws && partials && part_off && (!(act & 0xff) || y), "dss2_gat_bwd: null argument");
   DSS2_CHECK_ARG(g->undirected == 1, "dss2_gat_bwd: needs a graph built from the one-way edge list with undirect=1 (out-edges of a bus are "
                  "found through the reversed entries)");
   DSS2_CHECK_ARG(node_ws_bytes >= dss2_gat_ws_bytes(g->num_nodes), "dss2_gat_bwd: node workspace too small");
-  DSS2_CHECK_ARG(partial_stride >= 2 * (GC * GC + GC) + GC * fe + 2 * GC, "dss2_gat_bwd: partial_stride too small");
+  for (int i = 0; i < 7; ++i) {
+    const int64_t n = i == 0 || i == 2 ? GC * GC : i == 4 ? GC * fe : GC;
+    DSS2_CHECK_ARG(part_off[i] >= 0 && part_off[i] + n <= partial_stride, "dss2_gat_bwd: partial block %d outside the partial row", i);
+  }
   DSS2_CHECK_ARG(!grad_x || ((uintptr_t)grad_x & 15) == 0, "dss2_gat_bwd: grad_x must be 16-byte aligned");
   if (g->num_nodes == 0) return 0;
   a.yout = y;
@@ -1082,20 +1089,31 @@ extern "C" int dss2_gat_bwd(const dss2_graph_t* g, const float* x, int64_t x_str
   a.gx = grad_x;
   k_gat_bwd_stats<<<grid_for(g->num_nodes, GAT_THREADS), GAT_THREADS, 0, stream>>>(a);
   DSS2_LAUNCH_CHECK();
-  // partial row: [lin_l.w 64 | lin_l.b 8 | lin_r.w 64 | lin_r.b 8 | lin_edge.w 8 fe | att 8 | bias 8]
   const int np = dss2_num_partials();
-  a.partials = partials + 2 * (GC * GC + GC);
+  a.partials = partials + part_off[4];
+  a.off_att = part_off[5] - part_off[4];
+  a.off_bias = part_off[6] - part_off[4];
   a.partial_stride = partial_stride;
   k_gat_bwd<<<np, GAT_THREADS, 0, stream>>>(a);
   DSS2_LAUNCH_CHECK();
   // d W_l | d b_l and d W_r | d b_r from the stored node adjoints (columns 20..27 and 28..35 of the workspace)
-  launch_outer_reduce(np, stream, g->num_nodes, node_ws + 20, GAT_NODE_WS, GC, x, x_stride, GC, partials, partial_stride, 0,
-                                                GC * GC);
+  launch_outer_reduce(np, stream, g->num_nodes, node_ws + 20, GAT_NODE_WS, GC, x, x_stride, GC, partials, partial_stride, part_off[0], part_off[1]);
   DSS2_LAUNCH_CHECK();
-  launch_outer_reduce(np, stream, g->num_nodes, node_ws + 28, GAT_NODE_WS, GC, x, x_stride, GC, partials, partial_stride,
-                                                GC * GC + GC, 2 * GC * GC + GC);
+  launch_outer_reduce(np, stream, g->num_nodes, node_ws + 28, GAT_NODE_WS, GC, x, x_stride, GC, partials, partial_stride, part_off[2], part_off[3]);
   DSS2_LAUNCH_CHECK();
   return 0;
+}
+
+// partial row: [lin_l.w 64 | lin_l.b 8 | lin_r.w 64 | lin_r.b 8 | lin_edge.w 8 fe | att 8 | bias 8]
+extern "C" int dss2_gat_bwd(const dss2_graph_t* g, const float* x, int64_t x_stride, const float* edge_attr, int64_t ea_stride, int fe,
+                            const float* lin_l_w, const float* lin_l_b, const float* lin_r_w, const float* lin_r_b,
+                            const float* lin_edge_w, const float* att, const float* bias, float att_slope, int act, float act_slope,
+                            const float* y, const float* grad_y, float* grad_x, float* node_ws, size_t node_ws_bytes, float* partials,
+                            int64_t partial_stride, void* stream_) {
+  const int64_t w = GC * GC, e0 = 2 * (w + GC);
+  const int64_t off[7] = {0, w, w + GC, 2 * w + GC, e0, e0 + (int64_t)GC * fe, e0 + (int64_t)GC * fe + GC};
+  return dss2_gat_bwd_ex(g, x, x_stride, edge_attr, ea_stride, fe, lin_l_w, lin_l_b, lin_r_w, lin_r_b, lin_edge_w, att, bias, att_slope, act,
+                         act_slope, y, grad_y, grad_x, node_ws, node_ws_bytes, partials, partial_stride, off, stream_);
 }
 
 extern "C" size_t dss2_gine_ws_bytes(int64_t num_nodes) { return (size_t)num_nodes * GINE_NODE_WS * sizeof(float); }

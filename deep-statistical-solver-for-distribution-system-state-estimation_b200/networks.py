@@ -296,13 +296,13 @@ class _GATv2Params(nn.Module):
     """Parameter holder with PyG GATv2Conv's names / shapes / initialisation (glorot weights, zero biases); the arithmetic is in the
     fused kernel (csrc/gat.cu), so this module has no forward of its own."""
 
-    def __init__(self, channels, edge_dim):
+    def __init__(self, channels, edge_dim, heads=1):
         super().__init__()
-        self.att = nn.Parameter(torch.empty(1, 1, channels))
-        self.bias = nn.Parameter(torch.zeros(channels))
-        self.lin_l = nn.Linear(channels, channels, bias=True)
-        self.lin_r = nn.Linear(channels, channels, bias=True)
-        self.lin_edge = nn.Linear(edge_dim, channels, bias=False)
+        self.att = nn.Parameter(torch.empty(1, heads, channels))
+        self.bias = nn.Parameter(torch.zeros(channels))          # concat=False (or one head): [channels]
+        self.lin_l = nn.Linear(channels, heads * channels, bias=True)
+        self.lin_r = nn.Linear(channels, heads * channels, bias=True)
+        self.lin_edge = nn.Linear(edge_dim, heads * channels, bias=False)
         for lin in (self.lin_l, self.lin_r, self.lin_edge):
             nn.init.xavier_uniform_(lin.weight)
             if lin.bias is not None:
@@ -314,8 +314,9 @@ class GAT_DSSE(_LazyMachinery, nn.Module):
     """networks.py:113-156, the as-shipped default model of dss2_run.py:86: (num_layers - 1) x [GATv2Conv(dim_feat, dim_feat, heads,
     edge_dim, add_self_loops, fill 'mean') + LeakyReLU()], Linear(dim_feat, dim_dense), Linear(dim_dense, dim_out), wrapped in a PyG
     `Sequential` whose children are called `module_{i}` - kept, so that reference checkpoints (`model.module_0.att`, ...) load.
-    heads=1 (with either `concat`: one head concatenated = one head averaged), attention dropout 0; `self_loops`, `slope` and the three
-    `nonlin` choices are free.  heads > 1 raises (with concat=True the reference's own stack cannot run: channel mismatch)."""
+    heads=1 (with either `concat`: one head concatenated = one head averaged) or heads 2..4 with concat=False (averaged heads),
+    attention dropout 0; `self_loops`, `slope` and the three `nonlin` choices are free.  heads > 1 with concat=True raises (the
+    reference's own stack cannot run it: channel mismatch)."""
 
     def __init__(self, dim_feat, dim_dense, dim_out, num_layers, edge_dim, heads=1, concat=True, slope=0.2, self_loops=True, dropout=0.,
                  nonlin='leaky_relu', model='gat'):
@@ -327,8 +328,8 @@ class GAT_DSSE(_LazyMachinery, nn.Module):
         if heads != 1 and concat:
             raise NotImplementedError("GAT_DSSE(heads > 1, concat=True): the reference's own stack cannot run this - every GATv2Conv maps "
                                       "dim_feat -> heads * dim_feat channels while the next layer expects dim_feat (networks.py:144-147)")
-        if heads != 1:
-            raise NotImplementedError("GAT_DSSE kernels are built for heads=1 (dss2_run.py:86); multi-head averaging (concat=False) is not")
+        if not 1 <= heads <= 4:
+            raise NotImplementedError("GAT_DSSE kernels support heads in 1..4 (dss2_run.py:79 uses 1)")
         if dropout != 0.:
             raise NotImplementedError("GAT_DSSE kernels are built for attention dropout 0 (dss2_run.py:86)")
         self.dim_out, self.num_layers, self.dim_feat, self.dim_dense, self.edge_dim = dim_out, num_layers, dim_feat, dim_dense, edge_dim
@@ -339,7 +340,7 @@ class GAT_DSSE(_LazyMachinery, nn.Module):
         self.model = nn.Module()
         i = 0
         for _ in range(num_layers - 1):
-            self.model.add_module(f"module_{i}", _GATv2Params(dim_feat, edge_dim))
+            self.model.add_module(f"module_{i}", _GATv2Params(dim_feat, edge_dim, heads))
             self.model.add_module(f"module_{i + 1}", self.nonlin)
             i += 2
         self.model.add_module(f"module_{i}", nn.Linear(dim_feat, dim_dense))
@@ -351,7 +352,7 @@ class GAT_DSSE(_LazyMachinery, nn.Module):
             from dss2 import gat
             spec = gat.GATSpec(dim_feat=self.dim_feat, dim_dense=self.dim_dense, dim_out=self.dim_out, num_layers=self.num_layers,
                                edge_dim=self.edge_dim, att_slope=float(self.slope), act_slope=float(getattr(self.nonlin, "negative_slope", 0.0)),
-                               act=self.nonlin_name, self_loops=bool(self.loop))
+                               act=self.nonlin_name, self_loops=bool(self.loop), heads=int(self.heads))
             m = gat.make_machinery(spec)
             self.__dict__["_dss2_machinery"] = m
         return m

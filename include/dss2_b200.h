@@ -339,6 +339,15 @@ int dss2_gat_bwd(const dss2_graph_t* g, const float* x, int64_t x_stride, const 
                  const float* lin_edge_w, const float* att, const float* bias, float att_slope, int act, float act_slope,
                  const float* y, const float* grad_y, float* grad_x, float* node_ws, size_t node_ws_bytes, float* partials,
                  int64_t partial_stride, void* stream);
+/* One head of a multi-head layer (GATv2Conv(heads = H, concat = False), networks.py:145-146: the heads' outputs are averaged): the same
+ * backward with the seven blocks of the partial row at explicit offsets part_off[7] (floats, relative to `partials`, order as above), so
+ * that head h writes into its slice of every parameter.  The host side (dss2/gat.py) runs the heads with act = 0 and a zero bias and
+ * combines them with dss2_lin8_fwd / dss2_lin8_bwd (M = H inputs, weight blocks I / H, the layer's bias and activation). */
+int dss2_gat_bwd_ex(const dss2_graph_t* g, const float* x, int64_t x_stride, const float* edge_attr, int64_t ea_stride, int fe,
+                    const float* lin_l_w, const float* lin_l_b, const float* lin_r_w, const float* lin_r_b,
+                    const float* lin_edge_w, const float* att, const float* bias, float att_slope, int act, float act_slope,
+                    const float* y, const float* grad_y, float* grad_x, float* node_ws, size_t node_ws_bytes, float* partials,
+                    int64_t partial_stride, const int64_t* part_off, void* stream);
 /* GINE_DSSE layer (networks.py:71-111, PyG GINEConv + LeakyReLU): y_i = leaky(nn((1 + eps) x_i + sum_{j->i} relu(x_j + lin(a_ji)))) with
  * nn = the model's ONE shared Linear(8,8) and lin = this layer's Linear(edge_dim, 8); one-way edge list.  Backward: node_ws of
  * dss2_gine_ws_bytes(Nt); per-CTA partial rows [lin.weight 8 fe | lin.bias 8] at partials_lin and [nn.weight 64 | nn.bias 8] (this

@@ -257,15 +257,26 @@ def gat_dsse_forward(sd, x, edge_index, edge_attr, num_layers=8, nonlin="leaky_r
     h = x
     for l in range(num_layers - 1):
         p = f"model.module_{2 * l}."
-        h = gatv2_layer(h, edge_index, edge_attr, sd[p + "lin_l.weight"], sd[p + "lin_l.bias"], sd[p + "lin_r.weight"], sd[p + "lin_r.bias"],
-                        sd[p + "lin_edge.weight"], sd[p + "att"], sd[p + "bias"], slope=slope, self_loops=self_loops)
+        H = sd[p + "att"].shape[1]
+        if H == 1:
+            h = gatv2_layer(h, edge_index, edge_attr, sd[p + "lin_l.weight"], sd[p + "lin_l.bias"], sd[p + "lin_r.weight"], sd[p + "lin_r.bias"],
+                            sd[p + "lin_edge.weight"], sd[p + "att"], sd[p + "bias"], slope=slope, self_loops=self_loops)
+        else:
+            # heads > 1, concat=False (GATv2Conv: out.mean(dim=1) + bias): head k owns rows [k C, (k+1) C) of lin_l / lin_r / lin_edge
+            # and att[0, k]; the heads do not interact before the mean
+            c = h.size(1)
+            heads = [gatv2_layer(h, edge_index, edge_attr, sd[p + "lin_l.weight"][k * c:(k + 1) * c], sd[p + "lin_l.bias"][k * c:(k + 1) * c],
+                                 sd[p + "lin_r.weight"][k * c:(k + 1) * c], sd[p + "lin_r.bias"][k * c:(k + 1) * c],
+                                 sd[p + "lin_edge.weight"][k * c:(k + 1) * c], sd[p + "att"][0, k], 0.0, slope=slope, self_loops=self_loops)
+                     for k in range(H)]
+            h = torch.stack(heads, 1).mean(dim=1) + sd[p + "bias"]
         h = {"leaky_relu": lambda t: torch.nn.functional.leaky_relu(t, 0.01), "relu": torch.relu, "tanh": torch.tanh}[nonlin](h)   # :130-137
     i = 2 * (num_layers - 1)
     h = h @ sd[f"model.module_{i}.weight"].t() + sd[f"model.module_{i}.bias"]
     return h @ sd[f"model.module_{i + 1}.weight"].t() + sd[f"model.module_{i + 1}.bias"]
 
 
-def init_gat_state_dict(dim_feat=8, dim_dense=32, dim_out=2, num_layers=8, edge_dim=6, seed=0, dtype=torch.float32):
+def init_gat_state_dict(dim_feat=8, dim_dense=32, dim_out=2, num_layers=8, edge_dim=6, seed=0, dtype=torch.float32, heads=1):
     """Random GAT_DSSE parameters with the reference's names/shapes; all biases non-zero so every path is exercised."""
     g = torch.Generator().manual_seed(seed)
 
@@ -275,13 +286,13 @@ def init_gat_state_dict(dim_feat=8, dim_dense=32, dim_out=2, num_layers=8, edge_
     sd = {}
     for l in range(num_layers - 1):
         p = f"model.module_{2 * l}."
-        sd[p + "att"] = u(1, 1, dim_feat, bound=0.8)
+        sd[p + "att"] = u(1, heads, dim_feat, bound=0.8)
         sd[p + "bias"] = u(dim_feat, bound=0.1)
-        sd[p + "lin_l.weight"] = u(dim_feat, dim_feat, bound=0.6)
-        sd[p + "lin_l.bias"] = u(dim_feat, bound=0.1)
-        sd[p + "lin_r.weight"] = u(dim_feat, dim_feat, bound=0.6)
-        sd[p + "lin_r.bias"] = u(dim_feat, bound=0.1)
-        sd[p + "lin_edge.weight"] = u(dim_feat, edge_dim, bound=0.6)
+        sd[p + "lin_l.weight"] = u(heads * dim_feat, dim_feat, bound=0.6)
+        sd[p + "lin_l.bias"] = u(heads * dim_feat, bound=0.1)
+        sd[p + "lin_r.weight"] = u(heads * dim_feat, dim_feat, bound=0.6)
+        sd[p + "lin_r.bias"] = u(heads * dim_feat, bound=0.1)
+        sd[p + "lin_edge.weight"] = u(heads * dim_feat, edge_dim, bound=0.6)
     i = 2 * (num_layers - 1)
     sd[f"model.module_{i}.weight"] = u(dim_dense, dim_feat, bound=1.0 / math.sqrt(dim_feat))
     sd[f"model.module_{i}.bias"] = u(dim_dense, bound=1.0 / math.sqrt(dim_feat))

@@ -176,6 +176,10 @@ def gat_options(z):
     return {"nonlin": str(z["opt_nonlin"]), "slope": float(z["opt_slope"]), "self_loops": bool(z["opt_self_loops"])}
 
 
+def gat_heads(z):
+    return int(z["opt_heads"]) if "opt_heads" in (z.files if hasattr(z, "files") else z) else 1
+
+
 def oracle_gine_run(orc, num_layers, sd, z, dtype):
     """Oracle GINE_DSSE forward + WLS loss + autograd on the inputs of a golden file."""
     x, ea, ei = torch.from_numpy(z["x"]).to(dtype), torch.from_numpy(z["edge_attr"]).to(dtype), torch.from_numpy(z["edge_index"])

@@ -124,8 +124,9 @@ def run_model(tag, kind, ctor, batch, stats, sd_seed, torch_seed, dtype=torch.fl
 
 def run_gat(tag, batch, stats, sd_seed, num_layers=8, **opts):
     """Reference GAT_DSSE (dss2_run.py:86 hyper-parameters; `opts`: concat / slope / self_loops / nonlin) forward + gsp_wls_edge + backward."""
-    sd = orc.init_gat_state_dict(num_layers=num_layers, seed=sd_seed)
-    model = ref_net.GAT_DSSE(dim_feat=8, dim_dense=32, dim_out=2, heads=1, num_layers=num_layers, edge_dim=6, **opts)
+    heads = opts.pop("heads", 1)
+    sd = orc.init_gat_state_dict(num_layers=num_layers, seed=sd_seed, heads=heads)
+    model = ref_net.GAT_DSSE(dim_feat=8, dim_dense=32, dim_out=2, heads=heads, num_layers=num_layers, edge_dim=6, **opts)
     missing = model.load_state_dict(sd, strict=True)
     assert not missing.missing_keys and not missing.unexpected_keys
     model.train()
@@ -135,7 +136,8 @@ def run_gat(tag, batch, stats, sd_seed, num_layers=8, **opts):
            "x_mean": stats[0].numpy(), "x_std": stats[1].numpy(), "edge_mean": stats[2].numpy(), "edge_std": stats[3].numpy()}
     if opts:
         res.update(opt_nonlin=np.array(opts.get("nonlin", "leaky_relu")), opt_slope=np.array(opts.get("slope", 0.2)),
-                   opt_self_loops=np.array(opts.get("self_loops", True)), opt_concat=np.array(opts.get("concat", True)))
+                   opt_self_loops=np.array(opts.get("self_loops", True)), opt_concat=np.array(opts.get("concat", True)),
+                   opt_heads=np.array(heads))
     got = {}
     out.register_hook(lambda g_: got.__setitem__("g", g_.clone()))
     loss = ref_loss(batch, out, stats)
@@ -316,6 +318,10 @@ def main():
     run_gat("gat_noloop_tanh_cigre", Batch.from_data_list(ds[56:60]), stats, sd_seed=31, num_layers=4, self_loops=False, nonlin="tanh",
             concat=False, slope=0.1)
     run_gat("gat_relu_cigre", Batch.from_data_list(ds[90:93]), stats, sd_seed=32, num_layers=3, nonlin="relu")
+    # multi-head: only concat=False can run in the reference (concat=True changes the channel count between layers)
+    run_gat("gat_heads2_cigre", Batch.from_data_list(ds[100:105]), stats, sd_seed=34, num_layers=4, heads=2, concat=False)
+    run_gat("gat_heads3_tanh_cigre", Batch.from_data_list(ds[105:108]), stats, sd_seed=35, num_layers=3, heads=3, concat=False, nonlin="tanh",
+            self_loops=False)
     run_gine("gine_cigre", Batch.from_data_list(ds[60:65]), stats, sd_seed=8)
     run_gine("gine_traineps_cigre", Batch.from_data_list(ds[65:69]), stats, sd_seed=33, num_layers=4, eps=0.1, train_eps=True)
     run_gnn("gnn_gcn2_cigre", "gcn2", Batch.from_data_list(ds[70:76]), stats, sd_seed=21)

@@ -1219,20 +1219,20 @@ def test_ragged_mixed_grid_batch_large_graph_path(env, tiny_tiles):
 
 
 # ------------------------------------------------------------------------------------------------ GAT_DSSE (scope row 8f-1)
-@pytest.mark.parametrize("tag", ["gat_cigre", "gat_ober", "gat_noloop_tanh_cigre", "gat_relu_cigre"])
+@pytest.mark.parametrize("tag", ["gat_cigre", "gat_ober", "gat_noloop_tanh_cigre", "gat_relu_cigre", "gat_heads2_cigre", "gat_heads3_tanh_cigre"])
 @pytest.mark.parametrize("where", ["cuda", "cpu"])
 def test_gat_dsse_matches_reference_run(env, tag, where):
     """networks.GAT_DSSE (fused GATv2 kernels) with the weights of the reference run: output, loss through gsp_wls_edge and every
     parameter gradient against the reference's own GAT_DSSE executed over the shim (golden) with the fp64 oracle as arbiter.
     where='cpu' feeds CPU tensors and CPU parameters like the unmodified dss2_run.py."""
     from conftest import golden_gat, oracle_gat_run
-    from conftest import gat_options
+    from conftest import gat_options, gat_heads
     nl, sd, grads, z = golden_gat(tag)
     opts = gat_options(z)          # the constructor's other runnable settings: self_loops=False, nonlin tanh / relu, slope, concat=False
     if where == "cpu" and opts:
         pytest.skip("CPU-tensor path covered on the default configuration")
     ctor_opts = dict(opts, concat=bool(z["opt_concat"])) if opts else {}
-    model = env["networks"].GAT_DSSE(dim_feat=8, dim_dense=32, dim_out=2, heads=1, num_layers=nl, edge_dim=6, **ctor_opts)
+    model = env["networks"].GAT_DSSE(dim_feat=8, dim_dense=32, dim_out=2, heads=gat_heads(z), num_layers=nl, edge_dim=6, **ctor_opts)
     model.load_state_dict(sd, strict=True)
     model = model.to(where).train()
     x, ea, ei = torch.from_numpy(z["x"]).to(where), torch.from_numpy(z["edge_attr"]).to(where), torch.from_numpy(z["edge_index"]).to(where)

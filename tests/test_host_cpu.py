@@ -69,8 +69,10 @@ def test_no_cpu_fallback():
     gat = networks.GAT_DSSE(dim_feat=8, dim_dense=32, dim_out=2, heads=1, num_layers=3, edge_dim=6)
     with pytest.raises(_lib.Dss2Error):
         gat(torch.zeros(4, 8), torch.tensor([[0, 1], [1, 2]]), torch.zeros(2, 6))
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(NotImplementedError):      # the reference's own stack cannot run heads > 1 with concat=True
         networks.GAT_DSSE(dim_feat=8, dim_dense=32, dim_out=2, heads=2, num_layers=3, edge_dim=6)
+    multi = networks.GAT_DSSE(dim_feat=8, dim_dense=32, dim_out=2, heads=2, concat=False, num_layers=3, edge_dim=6)
+    assert tuple(multi.model.module_0.lin_l.weight.shape) == (16, 8) and tuple(multi.model.module_0.att.shape) == (1, 2, 8)
 
 
 def test_gat_dsse_state_dict_names_match_reference_layout():

@@ -133,7 +133,7 @@ def test_model_forward_backward_vs_reference(tag):
         assert_fp32_parity(g32[name], g, g64[name], name)
 
 
-@pytest.mark.parametrize("tag", ["gat_cigre", "gat_ober", "gat_noloop_tanh_cigre", "gat_relu_cigre"])
+@pytest.mark.parametrize("tag", ["gat_cigre", "gat_ober", "gat_noloop_tanh_cigre", "gat_relu_cigre", "gat_heads2_cigre", "gat_heads3_tanh_cigre"])
 def test_gat_dsse_forward_backward_vs_reference(tag):
     """Oracle GAT_DSSE (7 GATv2 layers + 2 Linear) + loss + autograd == the reference's GAT_DSSE run over the shim (same weights)."""
     from conftest import golden_gat, oracle_gat_run
