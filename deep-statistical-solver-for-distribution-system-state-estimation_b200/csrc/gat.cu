@@ -24,6 +24,12 @@ constexpr int GAT_NODE_WS = 36;   // floats per bus of backward scratch: m, den,
 struct GatW {
   float wl[GC * GC], bl[GC], wr[GC * GC], br[GC], we[GC * GFE], att[GC], bias[GC];
 };
+// Prepared weights in constant memory, one slot per layer (dss2_gat_upload): with SLOT a template parameter every weight is an
+// immediate constant-bank operand of its FMA - no shared-memory load and no register holds a weight (the shared-memory variant made ptxas
+// park ~200 weights in registers: 255 registers, 8 warps per SM).  SLOT = -1: weights from the launch's pointers through shared memory.
+constexpr int GAT_SLOTS = 8;
+__constant__ GatW c_gat[GAT_SLOTS];
+__device__ GatW g_gat_stage[GAT_SLOTS];
 
 struct GatArgs {
   dss2_graph_t g;
@@ -60,6 +66,17 @@ __device__ __forceinline__ void load_weights(GatW& w, const GatArgs& a) {
     w.br[threadIdx.x] = a.br[threadIdx.x];
     w.att[threadIdx.x] = a.att[threadIdx.x];
     w.bias[threadIdx.x] = a.bias[threadIdx.x];
+  }
+}
+
+template <int SLOT>
+__device__ __forceinline__ const GatW& gat_weights(GatW& sh, const GatArgs& a) {
+  if constexpr (SLOT >= 0) {
+    return c_gat[SLOT];
+  } else {
+    load_weights(sh, a);
+    __syncthreads();
+    return sh;
   }
 }
 
@@ -181,10 +198,10 @@ __device__ __forceinline__ DstStats dst_pass(const GatArgs& a, const GatW& w, in
   return r;
 }
 
+template <int SLOT>
 __global__ void __launch_bounds__(GAT_THREADS) k_gat_fwd(GatArgs a) {
-  __shared__ GatW w;
-  load_weights(w, a);
-  __syncthreads();
+  __shared__ GatW w_sh;
+  const GatW& w = gat_weights<SLOT>(w_sh, a);
   const float zero[GC] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.g.num_nodes; i += (int64_t)gridDim.x * blockDim.x) {
     float xi[GC], xr[GC], xl[GC], abar[GFE], acc[GC];
@@ -205,10 +222,10 @@ __global__ void __launch_bounds__(GAT_THREADS) k_gat_fwd(GatArgs a) {
 }
 
 // backward pass A: per bus g = grad_y * gate, x_r, softmax statistics (m, den, t)
+template <int SLOT>
 __global__ void __launch_bounds__(GAT_THREADS) k_gat_bwd_stats(GatArgs a) {
-  __shared__ GatW w;
-  load_weights(w, a);
-  __syncthreads();
+  __shared__ GatW w_sh;
+  const GatW& w = gat_weights<SLOT>(w_sh, a);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.g.num_nodes; i += (int64_t)gridDim.x * blockDim.x) {
     float xi[GC], xr[GC], xl[GC], abar[GFE], acc[GC], G[GC];
     load_x(a, i, xi);
@@ -252,11 +269,11 @@ __device__ __forceinline__ float edge_adjoint(const GatArgs& a, const GatW& w, c
 
 // backward pass B: thread = bus n.  As destination it owns d x_r[n], d W_e, d att of its in-edges and loop; as source it gathers d x_l[n]
 // from its out-edges.  partial layout per CTA: [W_e 8 x fe | att 8 | bias 8] at the offsets the host passes via partials pointer.
+template <int SLOT>
 __global__ void __launch_bounds__(GAT_THREADS) k_gat_bwd(GatArgs a) {
-  __shared__ GatW w;
+  __shared__ GatW w_sh;
   __shared__ float red[GAT_THREADS / 32][GC * GFE + 2 * GC];
-  load_weights(w, a);
-  __syncthreads();
+  const GatW& w = gat_weights<SLOT>(w_sh, a);
   const dss2_graph_t& g = a.g;
   float dWe[GC * GFE], datt[GC], dbias[GC];
 #pragma unroll
@@ -1012,12 +1029,56 @@ __global__ void __launch_bounds__(GAT_THREADS) k_lin8_bwd(Lin8Args a) {
   }
 }
 
+struct GatPrepArgs {
+  const float *wl[GAT_SLOTS], *bl[GAT_SLOTS], *wr[GAT_SLOTS], *br[GAT_SLOTS], *we[GAT_SLOTS], *att[GAT_SLOTS], *bias[GAT_SLOTS];
+  int fe, first;
+};
+__global__ void k_gat_prep(GatPrepArgs p) {
+  const int s = p.first + blockIdx.x, q = blockIdx.x;
+  GatW& w = g_gat_stage[s];
+  for (int i = threadIdx.x; i < GC * GC; i += blockDim.x) {
+    w.wl[i] = p.wl[q][i];
+    w.wr[i] = p.wr[q][i];
+  }
+  for (int i = threadIdx.x; i < GC * GFE; i += blockDim.x) {
+    const int c = i / GFE, f = i % GFE;
+    w.we[i] = f < p.fe ? p.we[q][c * p.fe + f] : 0.0f;
+  }
+  if (threadIdx.x < GC) {
+    w.bl[threadIdx.x] = p.bl[q][threadIdx.x];
+    w.br[threadIdx.x] = p.br[q][threadIdx.x];
+    w.att[threadIdx.x] = p.att[q][threadIdx.x];
+    w.bias[threadIdx.x] = p.bias[q][threadIdx.x];
+  }
+}
+
+#define GAT_SLOT_CASE(S, KERN, GRID) \
+  case S:                            \
+    KERN<S><<<GRID, GAT_THREADS, 0, stream>>>(a); \
+    break;
+#define GAT_SLOT_LAUNCH(slot, KERN, GRID)   \
+  switch (slot) {                           \
+    GAT_SLOT_CASE(-1, KERN, GRID)           \
+    GAT_SLOT_CASE(0, KERN, GRID)            \
+    GAT_SLOT_CASE(1, KERN, GRID)            \
+    GAT_SLOT_CASE(2, KERN, GRID)            \
+    GAT_SLOT_CASE(3, KERN, GRID)            \
+    GAT_SLOT_CASE(4, KERN, GRID)            \
+    GAT_SLOT_CASE(5, KERN, GRID)            \
+    GAT_SLOT_CASE(6, KERN, GRID)            \
+    GAT_SLOT_CASE(7, KERN, GRID)            \
+    default:                                \
+      dss2_set_error("GAT weight slot %d outside -1..%d", slot, GAT_SLOTS - 1); \
+      return -1;                            \
+  }
+
 int grid_for(int64_t n, int threads) { return (int)max((int64_t)1, min((int64_t)dss2_sm_count() * 8, (n + threads - 1) / threads)); }
 
 int fill_args(const char* who, GatArgs& a, const dss2_graph_t* g, const float* x, int64_t xs, const float* ea, int64_t eas, int fe,
               const float* wl, const float* bl, const float* wr, const float* br, const float* we, const float* att, const float* bias,
-              float slope_att, int act, float slope_act) {
-  DSS2_CHECK_ARG(g && x && ea && wl && bl && wr && br && we && att && bias, "%s: null argument", who);
+              float slope_att, int act, float slope_act, int slot = -1) {
+  DSS2_CHECK_ARG(g && x && ea, "%s: null argument", who);
+  DSS2_CHECK_ARG(slot >= 0 || (wl && bl && wr && br && we && att && bias), "%s: null weight pointer", who);
   DSS2_CHECK_ARG(fe >= 1 && fe <= GFE, "%s: edge_dim %d outside 1..%d", who, fe, GFE);
   DSS2_CHECK_ARG(xs >= GC && eas >= fe, "%s: row strides too small", who);
   a.g = *g;
@@ -1044,34 +1105,75 @@ int fill_args(const char* who, GatArgs& a, const dss2_graph_t* g, const float* x
 
 extern "C" size_t dss2_gat_ws_bytes(int64_t num_nodes) { return (size_t)num_nodes * GAT_NODE_WS * sizeof(float); }
 
-extern "C" int dss2_gat_fwd(const dss2_graph_t* g, const float* x, int64_t x_stride, const float* edge_attr, int64_t ea_stride, int fe,
-                            const float* lin_l_w, const float* lin_l_b, const float* lin_r_w, const float* lin_r_b,
-                            const float* lin_edge_w, const float* att, const float* bias, float att_slope, int act, float act_slope,
-                            float* y, void* stream_) {
+static int gat_fwd_impl(int slot, const dss2_graph_t* g, const float* x, int64_t x_stride, const float* edge_attr, int64_t ea_stride, int fe,
+                        const float* lin_l_w, const float* lin_l_b, const float* lin_r_w, const float* lin_r_b,
+                        const float* lin_edge_w, const float* att, const float* bias, float att_slope, int act, float act_slope,
+                        float* y, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   GatArgs a = {};
   if (fill_args("dss2_gat_fwd", a, g, x, x_stride, edge_attr, ea_stride, fe, lin_l_w, lin_l_b, lin_r_w, lin_r_b, lin_edge_w, att, bias,
-                att_slope, act, act_slope))
+                att_slope, act, act_slope, slot))
     return -1;
   DSS2_CHECK_ARG(y && ((uintptr_t)y & 15) == 0, "dss2_gat_fwd: y must be a 16-byte aligned [Nt, 8] buffer");
   if (g->num_nodes == 0) return 0;
   a.y = y;
-  k_gat_fwd<<<grid_for(g->num_nodes, GAT_THREADS), GAT_THREADS, 0, stream>>>(a);
+  GAT_SLOT_LAUNCH(slot, k_gat_fwd, grid_for(g->num_nodes, GAT_THREADS));
   DSS2_LAUNCH_CHECK();
   return 0;
 }
 
+extern "C" int dss2_gat_fwd(const dss2_graph_t* g, const float* x, int64_t x_stride, const float* edge_attr, int64_t ea_stride, int fe,
+                            const float* lin_l_w, const float* lin_l_b, const float* lin_r_w, const float* lin_r_b,
+                            const float* lin_edge_w, const float* att, const float* bias, float att_slope, int act, float act_slope,
+                            float* y, void* stream_) {
+  return gat_fwd_impl(-1, g, x, x_stride, edge_attr, ea_stride, fe, lin_l_w, lin_l_b, lin_r_w, lin_r_b, lin_edge_w, att, bias, att_slope, act,
+                      act_slope, y, stream_);
+}
+
+// Weights of `count` layers -> constant-memory slots first .. first + count - 1: one layout kernel + one device-to-device copy (both
+// capturable).  The slot variants of the layer kernels then read every weight as an immediate constant operand.
+extern "C" int dss2_gat_upload(int first, int count, const float* const* lin_l_w, const float* const* lin_l_b, const float* const* lin_r_w,
+                               const float* const* lin_r_b, const float* const* lin_edge_w, const float* const* att, const float* const* bias,
+                               int fe, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DSS2_CHECK_ARG(first >= 0 && count >= 1 && first + count <= GAT_SLOTS, "dss2_gat_upload: slots %d..%d outside 0..%d", first, first + count - 1,
+                 GAT_SLOTS - 1);
+  DSS2_CHECK_ARG(fe >= 1 && fe <= GFE, "dss2_gat_upload: edge_dim %d outside 1..%d", fe, GFE);
+  GatPrepArgs p = {};
+  for (int q = 0; q < count; ++q) {
+    DSS2_CHECK_ARG(lin_l_w[q] && lin_l_b[q] && lin_r_w[q] && lin_r_b[q] && lin_edge_w[q] && att[q] && bias[q], "dss2_gat_upload: null pointer");
+    p.wl[q] = lin_l_w[q], p.bl[q] = lin_l_b[q], p.wr[q] = lin_r_w[q], p.br[q] = lin_r_b[q], p.we[q] = lin_edge_w[q], p.att[q] = att[q];
+    p.bias[q] = bias[q];
+  }
+  p.fe = fe;
+  p.first = first;
+  k_gat_prep<<<count, 64, 0, stream>>>(p);
+  DSS2_LAUNCH_CHECK();
+  void* stage = nullptr;
+  DSS2_CUDA(cudaGetSymbolAddress(&stage, g_gat_stage));
+  DSS2_CUDA(cudaMemcpyToSymbolAsync(c_gat, (const char*)stage + (size_t)first * sizeof(GatW), (size_t)count * sizeof(GatW),
+                                    (size_t)first * sizeof(GatW), cudaMemcpyDeviceToDevice, stream));
+  return 0;
+}
+
+extern "C" int dss2_gat_fwd_slot(const dss2_graph_t* g, const float* x, int64_t x_stride, const float* edge_attr, int64_t ea_stride, int fe,
+                                 int slot, float att_slope, int act, float act_slope, float* y, void* stream_) {
+  DSS2_CHECK_ARG(slot >= 0 && slot < GAT_SLOTS, "dss2_gat_fwd_slot: slot %d outside 0..%d", slot, GAT_SLOTS - 1);
+  return gat_fwd_impl(slot, g, x, x_stride, edge_attr, ea_stride, fe, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, att_slope,
+                      act, act_slope, y, stream_);
+}
+
 // part_off[7]: offsets (floats, relative to `partials`) of the blocks [lin_l.w 64, lin_l.b 8, lin_r.w 64, lin_r.b 8, lin_edge.w 8 fe, att 8,
 // bias 8] inside a partial row: one head of a multi-head layer writes into that head's slice of every parameter.
-extern "C" int dss2_gat_bwd_ex(const dss2_graph_t* g, const float* x, int64_t x_stride, const float* edge_attr, int64_t ea_stride, int fe,
-                               const float* lin_l_w, const float* lin_l_b, const float* lin_r_w, const float* lin_r_b,
-                               const float* lin_edge_w, const float* att, const float* bias, float att_slope, int act, float act_slope,
-                               const float* y, const float* grad_y, float* grad_x, float* node_ws, size_t node_ws_bytes, float* partials,
-                               int64_t partial_stride, const int64_t* part_off, void* stream_) {
+static int gat_bwd_impl(int slot, const dss2_graph_t* g, const float* x, int64_t x_stride, const float* edge_attr, int64_t ea_stride, int fe,
+                        const float* lin_l_w, const float* lin_l_b, const float* lin_r_w, const float* lin_r_b,
+                        const float* lin_edge_w, const float* att, const float* bias, float att_slope, int act, float act_slope,
+                        const float* y, const float* grad_y, float* grad_x, float* node_ws, size_t node_ws_bytes, float* partials,
+                        int64_t partial_stride, const int64_t* part_off, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   GatArgs a = {};
   if (fill_args("dss2_gat_bwd", a, g, x, x_stride, edge_attr, ea_stride, fe, lin_l_w, lin_l_b, lin_r_w, lin_r_b, lin_edge_w, att, bias,
-                att_slope, act, act_slope))
+                att_slope, act, act_slope, slot))
     return -1;
   DSS2_CHECK_ARG(grad_y && node_ws && partials && part_off && (!(act & 0xff) || y), "dss2_gat_bwd: null argument");
   DSS2_CHECK_ARG(g->undirected == 1, "dss2_gat_bwd: needs a graph built from the one-way edge list with undirect=1 (out-edges of a bus are "
@@ -1087,14 +1189,14 @@ extern "C" int dss2_gat_bwd_ex(const dss2_graph_t* g, const float* x, int64_t x_
   a.gy = grad_y;
   a.ws = node_ws;
   a.gx = grad_x;
-  k_gat_bwd_stats<<<grid_for(g->num_nodes, GAT_THREADS), GAT_THREADS, 0, stream>>>(a);
+  GAT_SLOT_LAUNCH(slot, k_gat_bwd_stats, grid_for(g->num_nodes, GAT_THREADS));
   DSS2_LAUNCH_CHECK();
   const int np = dss2_num_partials();
   a.partials = partials + part_off[4];
   a.off_att = part_off[5] - part_off[4];
   a.off_bias = part_off[6] - part_off[4];
   a.partial_stride = partial_stride;
-  k_gat_bwd<<<np, GAT_THREADS, 0, stream>>>(a);
+  GAT_SLOT_LAUNCH(slot, k_gat_bwd, np);
   DSS2_LAUNCH_CHECK();
   // d W_l | d b_l and d W_r | d b_r from the stored node adjoints (columns 20..27 and 28..35 of the workspace)
   launch_outer_reduce(np, stream, g->num_nodes, node_ws + 20, GAT_NODE_WS, GC, x, x_stride, GC, partials, partial_stride, part_off[0], part_off[1]);
@@ -1102,6 +1204,26 @@ extern "C" int dss2_gat_bwd_ex(const dss2_graph_t* g, const float* x, int64_t x_
   launch_outer_reduce(np, stream, g->num_nodes, node_ws + 28, GAT_NODE_WS, GC, x, x_stride, GC, partials, partial_stride, part_off[2], part_off[3]);
   DSS2_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int dss2_gat_bwd_ex(const dss2_graph_t* g, const float* x, int64_t x_stride, const float* edge_attr, int64_t ea_stride, int fe,
+                               const float* lin_l_w, const float* lin_l_b, const float* lin_r_w, const float* lin_r_b,
+                               const float* lin_edge_w, const float* att, const float* bias, float att_slope, int act, float act_slope,
+                               const float* y, const float* grad_y, float* grad_x, float* node_ws, size_t node_ws_bytes, float* partials,
+                               int64_t partial_stride, const int64_t* part_off, void* stream_) {
+  return gat_bwd_impl(-1, g, x, x_stride, edge_attr, ea_stride, fe, lin_l_w, lin_l_b, lin_r_w, lin_r_b, lin_edge_w, att, bias, att_slope, act,
+                      act_slope, y, grad_y, grad_x, node_ws, node_ws_bytes, partials, partial_stride, part_off, stream_);
+}
+
+// the backward of a layer whose weights sit in constant-memory slot `slot` (standard partial row)
+extern "C" int dss2_gat_bwd_slot(const dss2_graph_t* g, const float* x, int64_t x_stride, const float* edge_attr, int64_t ea_stride, int fe,
+                                 int slot, float att_slope, int act, float act_slope, const float* y, const float* grad_y, float* grad_x,
+                                 float* node_ws, size_t node_ws_bytes, float* partials, int64_t partial_stride, void* stream_) {
+  DSS2_CHECK_ARG(slot >= 0 && slot < GAT_SLOTS, "dss2_gat_bwd_slot: slot %d outside 0..%d", slot, GAT_SLOTS - 1);
+  const int64_t w = GC * GC, e0 = 2 * (w + GC);
+  const int64_t off[7] = {0, w, w + GC, 2 * w + GC, e0, e0 + (int64_t)GC * fe, e0 + (int64_t)GC * fe + GC};
+  return gat_bwd_impl(slot, g, x, x_stride, edge_attr, ea_stride, fe, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, att_slope,
+                      act, act_slope, y, grad_y, grad_x, node_ws, node_ws_bytes, partials, partial_stride, off, stream_);
 }
 
 // partial row: [lin_l.w 64 | lin_l.b 8 | lin_r.w 64 | lin_r.b 8 | lin_edge.w 8 fe | att 8 | bias 8]

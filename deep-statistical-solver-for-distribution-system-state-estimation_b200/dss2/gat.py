@@ -7,6 +7,7 @@ in_channels no longer match, networks.py:145): every head runs the single-head k
 activation, and the per-bus 8x8 kernels (dss2_lin8_fwd/bwd with weight blocks I / H) average the heads, add the bias and apply the
 non-linearity.  All arithmetic is in csrc/gat.cu; there is no CPU fallback."""
 import ctypes
+import os
 from dataclasses import dataclass
 
 import torch
@@ -15,6 +16,7 @@ from . import _lib
 from .ops import ParamPack, _align4, require_cuda, resolve_graph, stage_rows
 
 GAT_C = 8   # channels the kernels are built for (dim_feat of dss2_run.py:73)
+GAT_SLOTS = 8   # constant-memory weight slots of csrc/gat.cu
 
 
 @dataclass(frozen=True)
@@ -114,6 +116,16 @@ class GATRunner:
         p = f"model.module_{2 * l}."
         return [self._p(flat, p + k) for k in ("lin_l.weight", "lin_l.bias", "lin_r.weight", "lin_r.bias", "lin_edge.weight", "att", "bias")]
 
+    # ---- single-head layers: weights in constant-memory slots (csrc/gat.cu, dss2_gat_upload) ----
+    def use_slots(self):
+        return self.spec.heads == 1 and self.spec.n_conv <= GAT_SLOTS and os.environ.get("DSS2_GAT_SLOTS", "1") != "0"
+
+    def upload(self, flat):
+        sp = self.spec
+        arr = ctypes.c_void_p * sp.n_conv
+        cols = [arr(*[self._layer(flat, l)[k] for l in range(sp.n_conv)]) for k in range(7)]
+        _lib.check(self.lib.dss2_gat_upload(0, sp.n_conv, *cols, sp.edge_dim, _lib.stream()), "dss2_gat_upload")
+
     _HEAD_BLOCKS = (("lin_l.weight", GAT_C * GAT_C), ("lin_l.bias", GAT_C), ("lin_r.weight", GAT_C * GAT_C), ("lin_r.bias", GAT_C),
                     ("lin_edge.weight", None), ("att", GAT_C))
 
@@ -171,8 +183,15 @@ class GATRunner:
         H = sp.heads
         if H > 1:
             self.prepare(flat)
+        slots = self.use_slots()
+        if slots:
+            self.upload(flat)
         for l in range(sp.n_conv):
             xin, stride = (x, xs) if l == 0 else (bufs["acts"][l - 1], GAT_C)
+            if slots:
+                _lib.check(lib.dss2_gat_fwd_slot(g, _lib.ptr(xin), stride, _lib.ptr(ea), eas, sp.edge_dim, l, sp.att_slope, sp.act_code,
+                                                 sp.act_slope, _lib.ptr(bufs["acts"][l]), st), "dss2_gat_fwd_slot")
+                continue
             if H > 1:
                 raw = bufs["raw"][l]
                 for h in range(H):
@@ -192,10 +211,14 @@ class GATRunner:
                    "dss2_mlp2_fwd")
         return bufs["out"]
 
-    def backward(self, graph, x, xs, ea, eas, flat, bufs, grad_out, flat_grad, need_gx=False):
-        """grad_out [Nt, dim_out] dense -> flat parameter gradient (and grad wrt x when need_gx)."""
+    def backward(self, graph, x, xs, ea, eas, flat, bufs, grad_out, flat_grad, need_gx=False, uploaded=False):
+        """grad_out [Nt, dim_out] dense -> flat parameter gradient (and grad wrt x when need_gx).  uploaded: the constant-memory slots
+        still hold this model's weights (the captured step: forward and backward of one step, nothing in between)."""
         sp, lib, st = self.spec, self.lib, _lib.stream()
         g = graph.ref
+        slots = self.use_slots()
+        if slots and not uploaded:
+            self.upload(flat)
         part, pstride = bufs["partials"], self.flat_size
 
         def pp(name):
@@ -233,6 +256,13 @@ class GATRunner:
                     _lib.check(lib.dss2_lin8_fwd(graph.num_nodes, H, 1, self._arr([gxh[h] for h in range(H)]), self._strides(H),
                                                  self._p(flat, "_mean_blocks"), None, 0, 0.0, _lib.ptr(gx), st), "dss2_lin8_fwd")
                     gx.mul_(float(H))
+                gy = gx
+                gx_out = gx
+                continue
+            if slots:
+                _lib.check(lib.dss2_gat_bwd_slot(g, _lib.ptr(xin), stride, _lib.ptr(ea), eas, sp.edge_dim, l, sp.att_slope, sp.act_code, sp.act_slope,
+                                                 _lib.ptr(bufs["acts"][l]), _lib.ptr(gy), _lib.ptr(gx), _lib.ptr(bufs["ws"]), bufs["ws"].numel() * 4,
+                                                 pp(f"model.module_{2 * l}.lin_l.weight"), pstride, st), "dss2_gat_bwd_slot")
                 gy = gx
                 gx_out = gx
                 continue

@@ -192,7 +192,8 @@ class GraphedTrainer:
                                  rng_state=self.step_state, bucket_hook=hook)
             reduced = self.runner.bucketed
         else:
-            self.runner.backward(self.graph, b["x"], 11, b["edge_attr"], 13, self.flat, self.bufs, self.grad_out, self.flat_grad)
+            kw = {"uploaded": True} if self.network == "gat" else {}      # GAT: the forward's constant-memory weight slots are still valid
+            self.runner.backward(self.graph, b["x"], 11, b["edge_attr"], 13, self.flat, self.bufs, self.grad_out, self.flat_grad, **kw)
             reduced = False
         if self.world > 1 and not reduced:
             torch.distributed.all_reduce(self.flat_grad[:self.flat.numel()], group=self.pg)
