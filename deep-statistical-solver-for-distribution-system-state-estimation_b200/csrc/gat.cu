@@ -19,6 +19,7 @@ namespace {
 constexpr int GC = 8;       // channels = dim_feat (heads = 1)
 constexpr int GFE = 8;      // edge_dim <= 8
 constexpr int GAT_THREADS = 128;
+constexpr int GAT_BWD_THREADS = 256;   // k_gat_bwd runs one CTA per partial row (= per SM): 8 warps instead of 4 hide its gather latency
 constexpr int GAT_NODE_WS = 36;   // floats per bus of backward scratch: m, den, t, pad, g[8], x_r[8], d x_l[8], d x_r[8]
 
 struct GatW {
@@ -270,9 +271,9 @@ __device__ __forceinline__ float edge_adjoint(const GatArgs& a, const GatW& w, c
 // backward pass B: thread = bus n.  As destination it owns d x_r[n], d W_e, d att of its in-edges and loop; as source it gathers d x_l[n]
 // from its out-edges.  partial layout per CTA: [W_e 8 x fe | att 8 | bias 8] at the offsets the host passes via partials pointer.
 template <int SLOT>
-__global__ void __launch_bounds__(GAT_THREADS) k_gat_bwd(GatArgs a) {
+__global__ void __launch_bounds__(GAT_BWD_THREADS) k_gat_bwd(GatArgs a) {
   __shared__ GatW w_sh;
-  __shared__ float red[GAT_THREADS / 32][GC * GFE + 2 * GC];
+  __shared__ float red[GAT_BWD_THREADS / 32][GC * GFE + 2 * GC];
   const GatW& w = gat_weights<SLOT>(w_sh, a);
   const dss2_graph_t& g = a.g;
   float dWe[GC * GFE], datt[GC], dbias[GC];
@@ -395,7 +396,7 @@ __global__ void __launch_bounds__(GAT_THREADS) k_gat_bwd(GatArgs a) {
     else src = GC * GFE + (i - GC * a.fe);
     float s = 0.0f;
 #pragma unroll
-    for (int wv = 0; wv < GAT_THREADS / 32; ++wv) s += red[wv][src];
+    for (int wv = 0; wv < GAT_BWD_THREADS / 32; ++wv) s += red[wv][src];
     const int j = i - GC * a.fe;
     part[j < 0 ? (int64_t)i : j < GC ? a.off_att + j : a.off_bias + (j - GC)] = s;
   }
@@ -782,9 +783,9 @@ __global__ void __launch_bounds__(GAT_THREADS) k_gine_bwd_a(GineArgs a) {
 }
 // backward pass B: thread = bus n: d W_e / d b_e of its in-edges, d x[n] from its own term and its out-edges.
 // partial layout per CTA at a.partials: [lin.weight 8 x fe | lin.bias 8]
-__global__ void __launch_bounds__(GAT_THREADS) k_gine_bwd_b(GineArgs a) {
+__global__ void __launch_bounds__(GAT_BWD_THREADS) k_gine_bwd_b(GineArgs a) {
   __shared__ GineW w;
-  __shared__ float red[GAT_THREADS / 32][GC * GFE + GC];
+  __shared__ float red[GAT_BWD_THREADS / 32][GC * GFE + GC];
   gine_load_weights(w, a);
   __syncthreads();
   const dss2_graph_t& g = a.g;
@@ -843,7 +844,7 @@ __global__ void __launch_bounds__(GAT_THREADS) k_gine_bwd_b(GineArgs a) {
     const float v = warp_sum(dbe[c]);
     if (lane == 0) red[warp][GC * GFE + c] = v;
   }
-  __shared__ float red_eps[GAT_THREADS / 32];
+  __shared__ float red_eps[GAT_BWD_THREADS / 32];
   {
     const float v = warp_sum(deps);
     if (lane == 0) red_eps[warp] = v;
@@ -854,13 +855,13 @@ __global__ void __launch_bounds__(GAT_THREADS) k_gine_bwd_b(GineArgs a) {
     const int src = i < GC * a.fe ? (i / a.fe) * GFE + (i % a.fe) : GC * GFE + (i - GC * a.fe);
     float s = 0.0f;
 #pragma unroll
-    for (int wv = 0; wv < GAT_THREADS / 32; ++wv) s += red[wv][src];
+    for (int wv = 0; wv < GAT_BWD_THREADS / 32; ++wv) s += red[wv][src];
     part[i] = s;
   }
   if (a.eps_dev && threadIdx.x == 0) {
     float s = 0.0f;
 #pragma unroll
-    for (int wv = 0; wv < GAT_THREADS / 32; ++wv) s += red_eps[wv];
+    for (int wv = 0; wv < GAT_BWD_THREADS / 32; ++wv) s += red_eps[wv];
     part[GC * a.fe + GC] = s;
   }
 }
@@ -1052,21 +1053,21 @@ __global__ void k_gat_prep(GatPrepArgs p) {
   }
 }
 
-#define GAT_SLOT_CASE(S, KERN, GRID) \
-  case S:                            \
-    KERN<S><<<GRID, GAT_THREADS, 0, stream>>>(a); \
+#define GAT_SLOT_CASE(S, KERN, GRID, THREADS) \
+  case S:                                     \
+    KERN<S><<<GRID, THREADS, 0, stream>>>(a); \
     break;
-#define GAT_SLOT_LAUNCH(slot, KERN, GRID)   \
-  switch (slot) {                           \
-    GAT_SLOT_CASE(-1, KERN, GRID)           \
-    GAT_SLOT_CASE(0, KERN, GRID)            \
-    GAT_SLOT_CASE(1, KERN, GRID)            \
-    GAT_SLOT_CASE(2, KERN, GRID)            \
-    GAT_SLOT_CASE(3, KERN, GRID)            \
-    GAT_SLOT_CASE(4, KERN, GRID)            \
-    GAT_SLOT_CASE(5, KERN, GRID)            \
-    GAT_SLOT_CASE(6, KERN, GRID)            \
-    GAT_SLOT_CASE(7, KERN, GRID)            \
+#define GAT_SLOT_LAUNCH(slot, KERN, GRID, THREADS) \
+  switch (slot) {                                  \
+    GAT_SLOT_CASE(-1, KERN, GRID, THREADS)         \
+    GAT_SLOT_CASE(0, KERN, GRID, THREADS)          \
+    GAT_SLOT_CASE(1, KERN, GRID, THREADS)          \
+    GAT_SLOT_CASE(2, KERN, GRID, THREADS)          \
+    GAT_SLOT_CASE(3, KERN, GRID, THREADS)          \
+    GAT_SLOT_CASE(4, KERN, GRID, THREADS)          \
+    GAT_SLOT_CASE(5, KERN, GRID, THREADS)          \
+    GAT_SLOT_CASE(6, KERN, GRID, THREADS)          \
+    GAT_SLOT_CASE(7, KERN, GRID, THREADS)          \
     default:                                \
       dss2_set_error("GAT weight slot %d outside -1..%d", slot, GAT_SLOTS - 1); \
       return -1;                            \
@@ -1117,7 +1118,7 @@ static int gat_fwd_impl(int slot, const dss2_graph_t* g, const float* x, int64_t
   DSS2_CHECK_ARG(y && ((uintptr_t)y & 15) == 0, "dss2_gat_fwd: y must be a 16-byte aligned [Nt, 8] buffer");
   if (g->num_nodes == 0) return 0;
   a.y = y;
-  GAT_SLOT_LAUNCH(slot, k_gat_fwd, grid_for(g->num_nodes, GAT_THREADS));
+  GAT_SLOT_LAUNCH(slot, k_gat_fwd, grid_for(g->num_nodes, GAT_THREADS), GAT_THREADS);
   DSS2_LAUNCH_CHECK();
   return 0;
 }
@@ -1189,14 +1190,14 @@ static int gat_bwd_impl(int slot, const dss2_graph_t* g, const float* x, int64_t
   a.gy = grad_y;
   a.ws = node_ws;
   a.gx = grad_x;
-  GAT_SLOT_LAUNCH(slot, k_gat_bwd_stats, grid_for(g->num_nodes, GAT_THREADS));
+  GAT_SLOT_LAUNCH(slot, k_gat_bwd_stats, grid_for(g->num_nodes, GAT_THREADS), GAT_THREADS);
   DSS2_LAUNCH_CHECK();
   const int np = dss2_num_partials();
   a.partials = partials + part_off[4];
   a.off_att = part_off[5] - part_off[4];
   a.off_bias = part_off[6] - part_off[4];
   a.partial_stride = partial_stride;
-  GAT_SLOT_LAUNCH(slot, k_gat_bwd, np);
+  GAT_SLOT_LAUNCH(slot, k_gat_bwd, np, GAT_BWD_THREADS);
   DSS2_LAUNCH_CHECK();
   // d W_l | d b_l and d W_r | d b_r from the stored node adjoints (columns 20..27 and 28..35 of the workspace)
   launch_outer_reduce(np, stream, g->num_nodes, node_ws + 20, GAT_NODE_WS, GC, x, x_stride, GC, partials, partial_stride, part_off[0], part_off[1]);
@@ -1320,7 +1321,7 @@ extern "C" int dss2_gine_bwd_ex(const dss2_graph_t* g, const float* x, int64_t x
   const int np = dss2_num_partials();
   a.partials = partials_lin;
   a.partial_stride = partial_stride;
-  k_gine_bwd_b<<<np, GAT_THREADS, 0, stream>>>(a);
+  k_gine_bwd_b<<<np, GAT_BWD_THREADS, 0, stream>>>(a);
   DSS2_LAUNCH_CHECK();
   // d W_nn | d b_nn = sum_n g[n] (x) [h[n], 1]
   launch_outer_reduce(np, stream, g->num_nodes, node_ws, GINE_NODE_WS, GC, node_ws + 16, GINE_NODE_WS, GC, partials_nn,

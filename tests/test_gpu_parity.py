@@ -888,8 +888,8 @@ def test_tag_bwd_tensor_core_matches_cuda_core_kernel(env, case, nb, cout, act):
 def test_graphed_trainer_next_row_models_equal_the_drop_in_modules(env, network):
     """GraphedTrainer(network='gat' | 'gine'): the captured step (packer -> model forward -> fused WLS loss -> backward -> flat Adamax)
     issues the same kernels as the drop-in modules under autograd (which the reference-run tests above hold to the oracle): same loss,
-    same parameter gradients bit for bit, and a CUDA-graph replay that reproduces the eager step; then three steps of training against
-    torch.optim.Adamax driving the drop-in module."""
+    same parameter gradients bit for bit, and a CUDA-graph replay that reproduces the eager step; then three replayed steps against
+    torch.optim.Adamax fed with the same gradients, and the module's loss on the trained parameters."""
     from dss2.trainer import GraphedTrainer
     store = env["synth"].synthetic_store(env["synth"].load_grid("ober_sub"), 8, seed=6).to("cuda")
     nb = 5
@@ -924,16 +924,30 @@ def test_graphed_trainer_next_row_models_equal_the_drop_in_modules(env, network)
     for name, p_ in model.named_parameters():
         off, n = tr.runner.table[name]
         assert torch.equal(tr.flat_grad[off:off + n], p_.grad.reshape(-1)), name
+    loss_first = tr.loss.clone()
     tr.capture()
+    # Replayed steps against torch.optim.Adamax.  Both optimizers get the SAME gradient every step (the captured step's), so the comparison
+    # is not at the mercy of Adamax's normalisation (update = lr * m / max-norm: a rounding-level difference in a near-zero gradient
+    # becomes a full-size update, and two equally valid trainings drift apart by 1e-4 .. 1e-3 within three steps).
     for step in range(3):
         loss_g = tr.step(ids).clone()
-        loss_m = module_step()
+        torch.cuda.synchronize()
+        if step == 0:
+            assert torch.equal(loss_g, loss_first), "the first replayed step is the eager step"
+        for name, p_ in model.named_parameters():
+            off, n = tr.runner.table[name]
+            p_.grad = tr.flat_grad[off:off + n].view_as(p_).clone()
         opt.step()
-        # step 1 is bit-identical (checked above); afterwards our flat Adamax and torch.optim.Adamax round their updates differently
-        assert torch.allclose(loss_g, loss_m, rtol=1e-4, atol=0), (step, float(loss_g), float(loss_m))
-    for name, p_ in model.named_parameters():
-        off, n = tr.runner.table[name]
-        assert torch.allclose(tr.flat[off:off + n], p_.detach().reshape(-1), rtol=1e-3, atol=1e-5), name
+        for name, p_ in model.named_parameters():
+            off, n = tr.runner.table[name]
+            assert torch.allclose(tr.flat[off:off + n], p_.detach().reshape(-1), rtol=1e-5, atol=1e-6), (step, name)
+        with torch.no_grad():      # keep the module on the trainer's trajectory (the two updates differ in the last bit)
+            for name, p_ in model.named_parameters():
+                off, n = tr.runner.table[name]
+                p_.copy_(tr.flat[off:off + n].view_as(p_))
+    # and the module's own forward + loss on the trained parameters is the trainer's next loss
+    loss_m = module_step()
+    assert torch.equal(tr.step(ids), loss_m)
 
 
 def test_chained_forward_layers_equal_ordinary_launches(env, monkeypatch):
