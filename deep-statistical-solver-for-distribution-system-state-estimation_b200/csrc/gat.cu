@@ -1200,6 +1200,13 @@ static int gat_bwd_impl(int slot, const dss2_graph_t* g, const float* x, int64_t
   GAT_SLOT_LAUNCH(slot, k_gat_bwd, np, GAT_BWD_THREADS);
   DSS2_LAUNCH_CHECK();
   // d W_l | d b_l and d W_r | d b_r from the stored node adjoints (columns 20..27 and 28..35 of the workspace)
+  if (part_off[2] == part_off[0] + GC * GC && part_off[3] == part_off[1] + GC) {
+    // [lin_l.w | lin_r.w] and [lin_l.b | lin_r.b] adjacent in the partial row: ONE reduction over the 16 adjoint columns
+    launch_outer_reduce(np, stream, g->num_nodes, node_ws + 20, GAT_NODE_WS, 2 * GC, x, x_stride, GC, partials, partial_stride, part_off[0],
+                        part_off[1]);
+    DSS2_LAUNCH_CHECK();
+    return 0;
+  }
   launch_outer_reduce(np, stream, g->num_nodes, node_ws + 20, GAT_NODE_WS, GC, x, x_stride, GC, partials, partial_stride, part_off[0], part_off[1]);
   DSS2_LAUNCH_CHECK();
   launch_outer_reduce(np, stream, g->num_nodes, node_ws + 28, GAT_NODE_WS, GC, x, x_stride, GC, partials, partial_stride, part_off[2], part_off[3]);
@@ -1216,15 +1223,16 @@ extern "C" int dss2_gat_bwd_ex(const dss2_graph_t* g, const float* x, int64_t x_
                       act_slope, y, grad_y, grad_x, node_ws, node_ws_bytes, partials, partial_stride, part_off, stream_);
 }
 
-// the backward of a layer whose weights sit in constant-memory slot `slot` (standard partial row)
+// the backward of a layer whose weights sit in constant-memory slot `slot` (part_off as in dss2_gat_bwd_ex; NULL: the standard partial row)
 extern "C" int dss2_gat_bwd_slot(const dss2_graph_t* g, const float* x, int64_t x_stride, const float* edge_attr, int64_t ea_stride, int fe,
                                  int slot, float att_slope, int act, float act_slope, const float* y, const float* grad_y, float* grad_x,
-                                 float* node_ws, size_t node_ws_bytes, float* partials, int64_t partial_stride, void* stream_) {
+                                 float* node_ws, size_t node_ws_bytes, float* partials, int64_t partial_stride, const int64_t* part_off,
+                                 void* stream_) {
   DSS2_CHECK_ARG(slot >= 0 && slot < GAT_SLOTS, "dss2_gat_bwd_slot: slot %d outside 0..%d", slot, GAT_SLOTS - 1);
   const int64_t w = GC * GC, e0 = 2 * (w + GC);
   const int64_t off[7] = {0, w, w + GC, 2 * w + GC, e0, e0 + (int64_t)GC * fe, e0 + (int64_t)GC * fe + GC};
   return gat_bwd_impl(slot, g, x, x_stride, edge_attr, ea_stride, fe, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, att_slope,
-                      act, act_slope, y, grad_y, grad_x, node_ws, node_ws_bytes, partials, partial_stride, off, stream_);
+                      act, act_slope, y, grad_y, grad_x, node_ws, node_ws_bytes, partials, partial_stride, part_off ? part_off : off, stream_);
 }
 
 // partial row: [lin_l.w 64 | lin_l.b 8 | lin_r.w 64 | lin_r.b 8 | lin_edge.w 8 fe | att 8 | bias 8]

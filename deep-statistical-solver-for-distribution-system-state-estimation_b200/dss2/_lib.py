@@ -84,7 +84,7 @@ _SIGNATURES = {
     "dss2_gat_upload": (c_int, [c_int, c_int, _P, _P, _P, _P, _P, _P, _P, c_int, _P]),
     "dss2_gat_fwd_slot": (c_int, [_G, _P, c_int64, _P, c_int64, c_int, c_int, c_float, c_int, c_float, _P, _P]),
     "dss2_gat_bwd_slot": (c_int, [_G, _P, c_int64, _P, c_int64, c_int, c_int, c_float, c_int, c_float, _P, _P, _P, _P, c_size_t, _P,
-                                  c_int64, _P]),
+                                  c_int64, _P, _P]),
     "dss2_gat_bwd_ex": (c_int, [_G, _P, c_int64, _P, c_int64, c_int, _P, _P, _P, _P, _P, _P, _P, c_float, c_int, c_float,
                                 _P, _P, _P, _P, c_size_t, _P, c_int64, _P, _P]),
     "dss2_gine_ws_bytes": (c_size_t, [c_int64]),

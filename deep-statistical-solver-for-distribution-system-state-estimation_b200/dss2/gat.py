@@ -57,9 +57,9 @@ class GATSpec:
         return out
 
     def layout(self):
-        """name -> (offset, numel) in the flat fp32 buffer.  Per GATv2 layer the tensors sit in the order of the kernel's partial
-        gradient row [lin_l.w | lin_l.b | lin_r.w | lin_r.b | lin_edge.w | att | bias] (all sizes are multiples of 4 floats for
-        dim_feat = 8 and even edge_dim), the head as [w1 | b1 | w2 | b2]."""
+        """name -> (offset, numel) in the flat fp32 buffer.  Per GATv2 layer [lin_l.w | lin_r.w | lin_l.b | lin_r.b | lin_edge.w | att |
+        bias] (all sizes are multiples of 4 floats for dim_feat = 8 and even edge_dim); the backward gets the blocks' offsets
+        (`part_off`), the head is [w1 | b1 | w2 | b2]."""
         off, table = 0, {}
 
         def put(name, n):
@@ -71,8 +71,8 @@ class GATSpec:
         for l in range(self.n_conv):
             p = f"model.module_{2 * l}."
             put(p + "lin_l.weight", H * c * c)     # H > 1: every parameter holds its heads one after the other (PyG's [H * C, ...] rows)
+            put(p + "lin_r.weight", H * c * c)     # the two Linears' weights, then their biases, adjacent: one gradient reduction for both
             put(p + "lin_l.bias", H * c)
-            put(p + "lin_r.weight", H * c * c)
             put(p + "lin_r.bias", H * c)
             put(p + "lin_edge.weight", H * c * fe)
             put(p + "att", H * c)
@@ -128,6 +128,13 @@ class GATRunner:
 
     _HEAD_BLOCKS = (("lin_l.weight", GAT_C * GAT_C), ("lin_l.bias", GAT_C), ("lin_r.weight", GAT_C * GAT_C), ("lin_r.bias", GAT_C),
                     ("lin_edge.weight", None), ("att", GAT_C))
+
+    def _layer_offsets(self, l):
+        """part_off of layer l relative to its lin_l.weight (single head)."""
+        p = f"model.module_{2 * l}."
+        base = self.table[p + "lin_l.weight"][0]
+        return (ctypes.c_int64 * 7)(*[self.table[p + k][0] - base for k in ("lin_l.weight", "lin_l.bias", "lin_r.weight", "lin_r.bias",
+                                                                              "lin_edge.weight", "att", "bias")])
 
     def _head_offsets(self, l, h):
         """Flat offsets of head h's slice of the six per-head parameters of layer l, then of the unused bias slot."""
@@ -262,13 +269,14 @@ class GATRunner:
             if slots:
                 _lib.check(lib.dss2_gat_bwd_slot(g, _lib.ptr(xin), stride, _lib.ptr(ea), eas, sp.edge_dim, l, sp.att_slope, sp.act_code, sp.act_slope,
                                                  _lib.ptr(bufs["acts"][l]), _lib.ptr(gy), _lib.ptr(gx), _lib.ptr(bufs["ws"]), bufs["ws"].numel() * 4,
-                                                 pp(f"model.module_{2 * l}.lin_l.weight"), pstride, st), "dss2_gat_bwd_slot")
+                                                 pp(f"model.module_{2 * l}.lin_l.weight"), pstride, self._layer_offsets(l), st), "dss2_gat_bwd_slot")
                 gy = gx
                 gx_out = gx
                 continue
-            _lib.check(lib.dss2_gat_bwd(g, _lib.ptr(xin), stride, _lib.ptr(ea), eas, sp.edge_dim, *self._layer(flat, l), sp.att_slope, sp.act_code,
-                                        sp.act_slope, _lib.ptr(bufs["acts"][l]), _lib.ptr(gy), _lib.ptr(gx), _lib.ptr(bufs["ws"]),
-                                        bufs["ws"].numel() * 4, pp(f"model.module_{2 * l}.lin_l.weight"), pstride, st), "dss2_gat_bwd")
+            _lib.check(lib.dss2_gat_bwd_ex(g, _lib.ptr(xin), stride, _lib.ptr(ea), eas, sp.edge_dim, *self._layer(flat, l), sp.att_slope, sp.act_code,
+                                           sp.act_slope, _lib.ptr(bufs["acts"][l]), _lib.ptr(gy), _lib.ptr(gx), _lib.ptr(bufs["ws"]),
+                                           bufs["ws"].numel() * 4, pp(f"model.module_{2 * l}.lin_l.weight"), pstride, self._layer_offsets(l), st),
+                       "dss2_gat_bwd_ex")
             gy = gx
             gx_out = gx
         _lib.check(lib.dss2_reduce_partials(_lib.ptr(part), pstride, self.num_partials, self.flat_size, _lib.ptr(flat_grad), 0, st),

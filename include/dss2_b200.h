@@ -342,7 +342,9 @@ int dss2_gat_bwd(const dss2_graph_t* g, const float* x, int64_t x_stride, const 
 /* Prepared weights: dss2_gat_upload puts the seven tensors of `count` layers into constant-memory slots first .. first + count - 1 (8
  * slots; one layout kernel + one device-to-device copy, both capturable); dss2_gat_fwd_slot / dss2_gat_bwd_slot are the layer kernels
  * reading slot `slot` - every weight an immediate constant operand, 92-96 registers per thread instead of 255 (the pointer variants
- * stage the weights in shared memory).  Slots are process-wide state: upload, then launch, on one stream. */
+ * stage the weights in shared memory).  Slots are process-wide state: upload, then launch, on one stream.  part_off: as for
+ * dss2_gat_bwd_ex below, or NULL for the standard partial row; with [lin_l.w | lin_r.w] and [lin_l.b | lin_r.b] adjacent the two Linear
+ * gradients come from ONE outer-product reduction. */
 int dss2_gat_upload(int first, int count, const float* const* lin_l_w, const float* const* lin_l_b, const float* const* lin_r_w,
                     const float* const* lin_r_b, const float* const* lin_edge_w, const float* const* att, const float* const* bias, int fe,
                     void* stream);
@@ -350,7 +352,7 @@ int dss2_gat_fwd_slot(const dss2_graph_t* g, const float* x, int64_t x_stride, c
                       float att_slope, int act, float act_slope, float* y, void* stream);
 int dss2_gat_bwd_slot(const dss2_graph_t* g, const float* x, int64_t x_stride, const float* edge_attr, int64_t ea_stride, int fe, int slot,
                       float att_slope, int act, float act_slope, const float* y, const float* grad_y, float* grad_x, float* node_ws,
-                      size_t node_ws_bytes, float* partials, int64_t partial_stride, void* stream);
+                      size_t node_ws_bytes, float* partials, int64_t partial_stride, const int64_t* part_off, void* stream);
 /* One head of a multi-head layer (GATv2Conv(heads = H, concat = False), networks.py:145-146: the heads' outputs are averaged): the same
  * backward with the seven blocks of the partial row at explicit offsets part_off[7] (floats, relative to `partials`, order as above), so
  * that head h writes into its slice of every parameter.  The host side (dss2/gat.py) runs the heads with act = 0 and a zero bias and
