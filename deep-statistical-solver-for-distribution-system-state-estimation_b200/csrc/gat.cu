@@ -628,7 +628,7 @@ __global__ void __launch_bounds__(128) k_mlp2_fwd_fixed(MlpArgs a) {
       float h = b1[c];
 #pragma unroll
       for (int i = 0; i < DIN; ++i) h = fmaf(w1[c * DIN + i], x[i], h);
-      a.h[n * DMID + c] = h;
+      if (a.h) a.h[n * DMID + c] = h;      // NULL: the backward is dss2_mlp2_bwd_nh, which never reads it
 #pragma unroll
       for (int o = 0; o < DOUT; ++o) z[o] = fmaf(w2[o * DMID + c], h, z[o]);
     }
@@ -636,6 +636,93 @@ __global__ void __launch_bounds__(128) k_mlp2_fwd_fixed(MlpArgs a) {
     for (int o = 0; o < DOUT; ++o) a.z[n * DOUT + o] = z[o];
   }
 }
+// The head has no non-linearity between its two Linears (networks.py:150-151), so every weight gradient is linear in the two small
+// sums S = sum_n grad_z[n] (x) x[n] (DOUT x DIN) and s = sum_n grad_z[n]:
+//   d W1 = W2^T S,  d b1 = W2^T s,  d W2 = S W1^T + s b1^T,  d b2 = s.
+// One pass: grad_x per bus, S and s in registers, one fixed-order reduction per CTA, then the CTA expands ITS S, s into its partial row
+// (the expansion is linear, so the sum over the CTA rows is the gradient).  Neither h nor grad_h ever touch memory (the stored-h
+// version moved 2 x 128 B per bus for them and ran two more outer-product reductions).
+constexpr int MLP_NH_THREADS = 256;
+template <int DIN, int DMID, int DOUT>
+__global__ void __launch_bounds__(MLP_NH_THREADS) k_mlp2_bwd_nh(MlpArgs a, float* partials, int64_t partial_stride) {
+  constexpr int NS = DOUT * (DIN + 1), NW = MLP_NH_THREADS / 32;
+  __shared__ float w1[DMID * DIN], w2[DOUT * DMID], b1[DMID], red[NW][NS], tot[NS];
+  for (int i = threadIdx.x; i < DMID * DIN; i += blockDim.x) w1[i] = a.w1[i];
+  for (int i = threadIdx.x; i < DOUT * DMID; i += blockDim.x) w2[i] = a.w2[i];
+  if (threadIdx.x < DMID) b1[threadIdx.x] = a.b1[threadIdx.x];
+  __syncthreads();
+  float S[DOUT][DIN + 1];
+#pragma unroll
+  for (int o = 0; o < DOUT; ++o)
+#pragma unroll
+    for (int i = 0; i <= DIN; ++i) S[o][i] = 0.0f;
+  for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < a.n; n += (int64_t)gridDim.x * blockDim.x) {
+    float gz[DOUT], x[DIN], gx[DIN];
+#pragma unroll
+    for (int o = 0; o < DOUT; ++o) gz[o] = a.gz[n * DOUT + o];
+#pragma unroll
+    for (int i = 0; i < DIN; ++i) {
+      x[i] = a.x[n * DIN + i];
+      gx[i] = 0.0f;
+    }
+#pragma unroll
+    for (int c = 0; c < DMID; ++c) {
+      float gh = 0.0f;
+#pragma unroll
+      for (int o = 0; o < DOUT; ++o) gh = fmaf(w2[o * DMID + c], gz[o], gh);
+#pragma unroll
+      for (int i = 0; i < DIN; ++i) gx[i] = fmaf(w1[c * DIN + i], gh, gx[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < DIN; ++i) a.gx[n * DIN + i] = gx[i];
+#pragma unroll
+    for (int o = 0; o < DOUT; ++o) {
+#pragma unroll
+      for (int i = 0; i < DIN; ++i) S[o][i] = fmaf(gz[o], x[i], S[o][i]);
+      S[o][DIN] += gz[o];
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 0; o < DOUT; ++o)
+#pragma unroll
+    for (int i = 0; i <= DIN; ++i) {
+      const float v = warp_sum(S[o][i]);
+      if (lane == 0) red[warp][o * (DIN + 1) + i] = v;
+    }
+  __syncthreads();
+  if (threadIdx.x < NS) {
+    float s = 0.0f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) s += red[w][threadIdx.x];
+    tot[threadIdx.x] = s;
+  }
+  __syncthreads();
+  // partial row layout: [w1 dmid x din | b1 dmid | w2 dout x dmid | b2 dout]
+  float* part = partials + (size_t)blockIdx.x * partial_stride;
+  constexpr int O_B1 = DMID * DIN, O_W2 = O_B1 + DMID, O_B2 = O_W2 + DOUT * DMID, TOTAL = O_B2 + DOUT;
+  for (int idx = threadIdx.x; idx < TOTAL; idx += blockDim.x) {
+    float v = 0.0f;
+    if (idx < O_B1) {
+      const int c = idx / DIN, i = idx % DIN;
+#pragma unroll
+      for (int o = 0; o < DOUT; ++o) v = fmaf(w2[o * DMID + c], tot[o * (DIN + 1) + i], v);
+    } else if (idx < O_W2) {
+      const int c = idx - O_B1;
+#pragma unroll
+      for (int o = 0; o < DOUT; ++o) v = fmaf(w2[o * DMID + c], tot[o * (DIN + 1) + DIN], v);
+    } else if (idx < O_B2) {
+      const int o = (idx - O_W2) / DMID, c = (idx - O_W2) % DMID;
+      v = tot[o * (DIN + 1) + DIN] * b1[c];
+#pragma unroll
+      for (int i = 0; i < DIN; ++i) v = fmaf(tot[o * (DIN + 1) + i], w1[c * DIN + i], v);
+    } else {
+      v = tot[(idx - O_B2) * (DIN + 1) + DIN];
+    }
+    part[idx] = v;
+  }
+}
+
 template <int DIN, int DMID, int DOUT>
 __global__ void __launch_bounds__(128) k_mlp2_bwd_fixed(MlpArgs a) {
   __shared__ float w1[DMID * DIN], w2[DOUT * DMID];
@@ -1341,7 +1428,7 @@ extern "C" int dss2_gine_bwd_ex(const dss2_graph_t* g, const float* x, int64_t x
 extern "C" int dss2_mlp2_fwd(int64_t num_nodes, const float* x, int din, const float* w1, const float* b1, int dmid, const float* w2,
                              const float* b2, int dout, float* h, float* z, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  DSS2_CHECK_ARG(x && w1 && b1 && w2 && b2 && h && z, "dss2_mlp2_fwd: null argument");
+  DSS2_CHECK_ARG(x && w1 && b1 && w2 && b2 && z, "dss2_mlp2_fwd: null argument");
   DSS2_CHECK_ARG(din >= 1 && din <= MLP_MAX && dmid >= 1 && dmid <= MLP_MAX && dout >= 1 && dout <= 8, "dss2_mlp2_fwd: sizes %d -> %d -> %d unsupported",
                  din, dmid, dout);
   if (num_nodes == 0) return 0;
@@ -1357,6 +1444,7 @@ extern "C" int dss2_mlp2_fwd(int64_t num_nodes, const float* x, int din, const f
   a.dout = dout;
   a.h = h;
   a.z = z;
+  DSS2_CHECK_ARG(h || (din == 8 && dmid == 32 && dout == 2), "dss2_mlp2_fwd: h may be NULL only where dss2_mlp2_nh_supported()");
   if (din == 8 && dmid == 32 && dout == 2) k_mlp2_fwd_fixed<8, 32, 2><<<grid_for(num_nodes, 128), 128, 0, stream>>>(a);
   else k_mlp2_fwd<<<grid_for(num_nodes, 128), 128, 0, stream>>>(a);
   DSS2_LAUNCH_CHECK();
@@ -1392,6 +1480,31 @@ extern "C" int dss2_mlp2_bwd(int64_t num_nodes, const float* x, int din, const f
   launch_outer_reduce(np, stream, num_nodes, grad_h_ws, dmid, dmid, x, din, din, partials, partial_stride, o_w1, o_b1);
   DSS2_LAUNCH_CHECK();
   launch_outer_reduce(np, stream, num_nodes, grad_z, dout, dout, h, dmid, dmid, partials, partial_stride, o_w2, o_b2);
+  DSS2_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int dss2_mlp2_nh_supported(int din, int dmid, int dout) { return din == 8 && dmid == 32 && dout == 2; }
+
+// the same gradients without h / grad_h in memory (k_mlp2_bwd_nh); sizes: dss2_mlp2_nh_supported
+extern "C" int dss2_mlp2_bwd_nh(int64_t num_nodes, const float* x, int din, const float* w1, const float* b1, int dmid, const float* w2, int dout,
+                                const float* grad_z, float* grad_x, float* partials, int64_t partial_stride, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DSS2_CHECK_ARG(x && w1 && b1 && w2 && grad_z && grad_x && partials, "dss2_mlp2_bwd_nh: null argument");
+  DSS2_CHECK_ARG(dss2_mlp2_nh_supported(din, dmid, dout), "dss2_mlp2_bwd_nh: sizes %d -> %d -> %d unsupported", din, dmid, dout);
+  DSS2_CHECK_ARG(partial_stride >= (int64_t)dmid * din + dmid + dout * dmid + dout, "dss2_mlp2_bwd_nh: partial_stride too small");
+  MlpArgs a = {};
+  a.n = num_nodes;
+  a.x = x;
+  a.din = din;
+  a.w1 = w1;
+  a.b1 = b1;
+  a.dmid = dmid;
+  a.w2 = w2;
+  a.dout = dout;
+  a.gz = grad_z;
+  a.gx = grad_x;
+  k_mlp2_bwd_nh<8, 32, 2><<<dss2_num_partials(), MLP_NH_THREADS, 0, stream>>>(a, partials, partial_stride);   // idle CTAs write zeros
   DSS2_LAUNCH_CHECK();
   return 0;
 }

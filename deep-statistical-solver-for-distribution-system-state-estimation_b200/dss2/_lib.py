@@ -102,6 +102,8 @@ _SIGNATURES = {
     "dss2_fa_bwd": (c_int, [_G, _P, c_int, _P, c_int64, _P, _P, c_float, c_int, c_float, _P, _P, _P, _P, _P, c_int64, _P]),
     "dss2_mlp2_fwd": (c_int, [c_int64, _P, c_int, _P, _P, c_int, _P, _P, c_int, _P, _P, _P]),
     "dss2_mlp2_bwd": (c_int, [c_int64, _P, c_int, _P, c_int, _P, c_int, _P, _P, _P, _P, _P, c_int64, _P]),
+    "dss2_mlp2_nh_supported": (c_int, [c_int, c_int, c_int]),
+    "dss2_mlp2_bwd_nh": (c_int, [c_int64, _P, c_int, _P, _P, c_int, _P, c_int, _P, _P, _P, c_int64, _P]),
 }
 
 _lib = None

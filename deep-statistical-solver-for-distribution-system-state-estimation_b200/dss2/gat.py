@@ -13,6 +13,7 @@ from dataclasses import dataclass
 import torch
 
 from . import _lib
+from .head import head_bwd, head_fwd
 from .ops import ParamPack, _align4, require_cuda, resolve_graph, stage_rows
 
 GAT_C = 8   # channels the kernels are built for (dim_feat of dss2_run.py:73)
@@ -212,10 +213,9 @@ class GATRunner:
             _lib.check(lib.dss2_gat_fwd(g, _lib.ptr(xin), stride, _lib.ptr(ea), eas, sp.edge_dim, *self._layer(flat, l), sp.att_slope, sp.act_code,
                                         sp.act_slope, _lib.ptr(bufs["acts"][l]), st), "dss2_gat_fwd")
         i = 2 * sp.n_conv
-        _lib.check(lib.dss2_mlp2_fwd(graph.num_nodes, _lib.ptr(bufs["acts"][sp.n_conv - 1]), GAT_C, self._p(flat, f"model.module_{i}.weight"),
-                                     self._p(flat, f"model.module_{i}.bias"), sp.dim_dense, self._p(flat, f"model.module_{i + 1}.weight"),
-                                     self._p(flat, f"model.module_{i + 1}.bias"), sp.dim_out, _lib.ptr(bufs["h"]), _lib.ptr(bufs["out"]), st),
-                   "dss2_mlp2_fwd")
+        head_fwd(lib, graph.num_nodes, _lib.ptr(bufs["acts"][sp.n_conv - 1]), GAT_C, self._p(flat, f"model.module_{i}.weight"),
+                 self._p(flat, f"model.module_{i}.bias"), sp.dim_dense, self._p(flat, f"model.module_{i + 1}.weight"),
+                 self._p(flat, f"model.module_{i + 1}.bias"), sp.dim_out, _lib.ptr(bufs["h"]), _lib.ptr(bufs["out"]), st)
         return bufs["out"]
 
     def backward(self, graph, x, xs, ea, eas, flat, bufs, grad_out, flat_grad, need_gx=False, uploaded=False):
@@ -233,10 +233,9 @@ class GATRunner:
 
         i = 2 * sp.n_conv
         gy = bufs["g8"][0]
-        _lib.check(lib.dss2_mlp2_bwd(graph.num_nodes, _lib.ptr(bufs["acts"][sp.n_conv - 1]), GAT_C, self._p(flat, f"model.module_{i}.weight"),
-                                     sp.dim_dense, self._p(flat, f"model.module_{i + 1}.weight"), sp.dim_out, _lib.ptr(bufs["h"]),
-                                     _lib.ptr(grad_out), _lib.ptr(bufs["gh"]), _lib.ptr(gy), pp(f"model.module_{i}.weight"), pstride, st),
-                   "dss2_mlp2_bwd")
+        head_bwd(lib, graph.num_nodes, _lib.ptr(bufs["acts"][sp.n_conv - 1]), GAT_C, self._p(flat, f"model.module_{i}.weight"),
+                 self._p(flat, f"model.module_{i}.bias"), sp.dim_dense, self._p(flat, f"model.module_{i + 1}.weight"), sp.dim_out,
+                 _lib.ptr(bufs["h"]), _lib.ptr(grad_out), _lib.ptr(bufs["gh"]), _lib.ptr(gy), pp(f"model.module_{i}.weight"), pstride, st)
         gx_out = None
         for l in reversed(range(sp.n_conv)):
             xin, stride = (x, xs) if l == 0 else (bufs["acts"][l - 1], GAT_C)

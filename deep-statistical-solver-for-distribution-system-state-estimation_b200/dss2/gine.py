@@ -7,6 +7,7 @@ from dataclasses import dataclass
 import torch
 
 from . import _lib
+from .head import head_bwd, head_fwd
 from .ops import ParamPack, _align4, require_cuda, resolve_graph, stage_rows
 
 GINE_C = 8
@@ -105,10 +106,9 @@ class GINERunner:
             _lib.check(lib.dss2_gine_fwd_ex(graph.ref, _lib.ptr(xin), stride, _lib.ptr(ea), eas, sp.edge_dim, *self._layer(flat, l), sp.eps,
                                             self._eps(flat, l), 1, sp.act_slope, _lib.ptr(bufs["acts"][l]), st), "dss2_gine_fwd")
         i = 2 * sp.n_conv
-        _lib.check(lib.dss2_mlp2_fwd(graph.num_nodes, _lib.ptr(bufs["acts"][sp.n_conv - 1]), GINE_C, self._p(flat, f"model.module_{i}.weight"),
-                                     self._p(flat, f"model.module_{i}.bias"), sp.dim_dense, self._p(flat, f"model.module_{i + 1}.weight"),
-                                     self._p(flat, f"model.module_{i + 1}.bias"), sp.dim_out, _lib.ptr(bufs["h"]), _lib.ptr(bufs["out"]), st),
-                   "dss2_mlp2_fwd")
+        head_fwd(lib, graph.num_nodes, _lib.ptr(bufs["acts"][sp.n_conv - 1]), GINE_C, self._p(flat, f"model.module_{i}.weight"),
+                 self._p(flat, f"model.module_{i}.bias"), sp.dim_dense, self._p(flat, f"model.module_{i + 1}.weight"),
+                 self._p(flat, f"model.module_{i + 1}.bias"), sp.dim_out, _lib.ptr(bufs["h"]), _lib.ptr(bufs["out"]), st)
         return bufs["out"]
 
     def backward(self, graph, x, xs, ea, eas, flat, bufs, grad_out, flat_grad, need_gx=False):
@@ -122,10 +122,9 @@ class GINERunner:
 
         i = 2 * sp.n_conv
         gy = bufs["g8"][0]
-        _lib.check(lib.dss2_mlp2_bwd(graph.num_nodes, _lib.ptr(bufs["acts"][sp.n_conv - 1]), GINE_C, self._p(flat, f"model.module_{i}.weight"),
-                                     sp.dim_dense, self._p(flat, f"model.module_{i + 1}.weight"), sp.dim_out, _lib.ptr(bufs["h"]),
-                                     _lib.ptr(grad_out), _lib.ptr(bufs["gh"]), _lib.ptr(gy), pp(self.table[f"model.module_{i}.weight"][0]),
-                                     pstride, st), "dss2_mlp2_bwd")
+        head_bwd(lib, graph.num_nodes, _lib.ptr(bufs["acts"][sp.n_conv - 1]), GINE_C, self._p(flat, f"model.module_{i}.weight"),
+                 self._p(flat, f"model.module_{i}.bias"), sp.dim_dense, self._p(flat, f"model.module_{i + 1}.weight"), sp.dim_out,
+                 _lib.ptr(bufs["h"]), _lib.ptr(grad_out), _lib.ptr(bufs["gh"]), _lib.ptr(gy), pp(self.table[f"model.module_{i}.weight"][0]), pstride, st)
         gx_out = None
         for l in reversed(range(sp.n_conv)):
             xin, stride = (x, xs) if l == 0 else (bufs["acts"][l - 1], GINE_C)

@@ -14,6 +14,7 @@ from dataclasses import dataclass
 import torch
 
 from . import _lib
+from .head import head_bwd, head_fwd
 from .ops import ParamPack, _align4, require_cuda, resolve_graph, stage_rows
 
 C = 8
@@ -171,10 +172,9 @@ class GNNRunner:
             _lib.check(lib.dss2_lin8_fwd(graph.num_nodes, sp.M, 0 if sp.model == "gcn2" else 1, self._ptr_array(ins), self._stride_array(strides),
                                          self._w(flat, l), bias, ACTS[sp.act], sp.act_slope, _lib.ptr(bufs["acts"][l]), st), "dss2_lin8_fwd")
         i = 2 * sp.n_conv
-        _lib.check(lib.dss2_mlp2_fwd(graph.num_nodes, _lib.ptr(bufs["acts"][sp.n_conv - 1]), C, self._p(flat, f"model.module_{i}.weight"),
-                                     self._p(flat, f"model.module_{i}.bias"), sp.dim_dense, self._p(flat, f"model.module_{i + 1}.weight"),
-                                     self._p(flat, f"model.module_{i + 1}.bias"), sp.dim_out, _lib.ptr(bufs["h"]), _lib.ptr(bufs["out"]), st),
-                   "dss2_mlp2_fwd")
+        head_fwd(lib, graph.num_nodes, _lib.ptr(bufs["acts"][sp.n_conv - 1]), C, self._p(flat, f"model.module_{i}.weight"),
+                 self._p(flat, f"model.module_{i}.bias"), sp.dim_dense, self._p(flat, f"model.module_{i + 1}.weight"),
+                 self._p(flat, f"model.module_{i + 1}.bias"), sp.dim_out, _lib.ptr(bufs["h"]), _lib.ptr(bufs["out"]), st)
         return bufs["out"]
 
     def backward(self, graph, x, xs, flat, bufs, grad_out, flat_grad):
@@ -188,10 +188,9 @@ class GNNRunner:
 
         i = 2 * sp.n_conv
         gy = bufs["g8"][0]
-        _lib.check(lib.dss2_mlp2_bwd(graph.num_nodes, _lib.ptr(bufs["acts"][sp.n_conv - 1]), C, self._p(flat, f"model.module_{i}.weight"),
-                                     sp.dim_dense, self._p(flat, f"model.module_{i + 1}.weight"), sp.dim_out, _lib.ptr(bufs["h"]),
-                                     _lib.ptr(grad_out), _lib.ptr(bufs["gh"]), _lib.ptr(gy), pp(self.table[f"model.module_{i}.weight"][0]), pstride, st),
-                   "dss2_mlp2_bwd")
+        head_bwd(lib, graph.num_nodes, _lib.ptr(bufs["acts"][sp.n_conv - 1]), C, self._p(flat, f"model.module_{i}.weight"),
+                 self._p(flat, f"model.module_{i}.bias"), sp.dim_dense, self._p(flat, f"model.module_{i + 1}.weight"), sp.dim_out,
+                 _lib.ptr(bufs["h"]), _lib.ptr(grad_out), _lib.ptr(bufs["gh"]), _lib.ptr(gy), pp(self.table[f"model.module_{i}.weight"][0]), pstride, st)
         bufs["gx0"].zero_()
         for l in reversed(range(sp.n_conv)):
             if sp.model == "fagcn":

@@ -388,6 +388,12 @@ int dss2_mlp2_fwd(int64_t num_nodes, const float* x, int din, const float* w1, c
 int dss2_mlp2_bwd(int64_t num_nodes, const float* x, int din, const float* w1, int dmid, const float* w2, int dout,
                   const float* h, const float* grad_z, float* grad_h_ws, float* grad_x, float* partials, int64_t partial_stride,
                   void* stream);
+/* The head without h or grad_h in memory, for the sizes dss2_mlp2_nh_supported() accepts (8 -> 32 -> 2, dss2_run.py:73-76): there is no
+ * non-linearity between the two Linears, so all four gradients are linear in S = sum_n grad_z[n] (x) x[n] and s = sum_n grad_z[n]; one
+ * pass over the buses, same partial-row layout.  dss2_mlp2_fwd takes h = NULL for these sizes. */
+int dss2_mlp2_nh_supported(int din, int dmid, int dout);
+int dss2_mlp2_bwd_nh(int64_t num_nodes, const float* x, int din, const float* w1, const float* b1, int dmid, const float* w2, int dout,
+                     const float* grad_z, float* grad_x, float* partials, int64_t partial_stride, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * gnn_dsse building blocks (networks.py:11-69: GCN2Conv / TAGConv / FAConv stacks at width dim_feat <= 8 on the one-way edge list as given).
