@@ -156,14 +156,15 @@ class PFNRunner:
         _lib.check(self.lib.dss2_edgeagg_upload(0, sp.L, *cols, sp.fn, sp.fe, _lib.stream()), "dss2_edgeagg_upload")
 
     # ---- forward ----
-    def forward(self, graph, x, x_stride, ea, ea_stride, flat, bufs, drop_mode=1, rng_state=None, masks=None):
+    def forward(self, graph, x, x_stride, ea, ea_stride, flat, bufs, drop_mode=1, rng_state=None, masks=None, ea_uploaded=False):
         """x: tensor whose data_ptr is row 0 / col 0 of the [Nt, fn] input with row stride x_stride.
-        masks: optional [L][n_layers-1] uint8 [Nt,32] tensors (drop_mode 2).  Returns bufs['outs'][-1]."""
+        masks: optional [L][n_layers-1] uint8 [Nt,32] tensors (drop_mode 2).  ea_uploaded: the caller has already run ea_upload(flat)
+        for this step (the trainer does, beside the batch packer).  Returns bufs['outs'][-1]."""
         sp, lib, st = self.spec, self.lib, _lib.stream()
         g = graph.ref
         use_tc2 = TAG_IMPL == "tc2" and bool(lib.dss2_tag_tc2_supported(g, sp.K))
         slots = self.ea_slots(graph, x_stride, ea_stride)
-        if slots:
+        if slots and not ea_uploaded:
             self.ea_upload(flat)
         chain = use_tc2 and CHAIN and rng_state is not None and "marks" in bufs
         for s in range(sp.L):

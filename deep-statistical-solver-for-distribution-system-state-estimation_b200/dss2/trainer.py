@@ -167,10 +167,20 @@ class GraphedTrainer:
             for k in ("marks", "marks_b"):
                 if k in self.bufs:
                     self.bufs[k].zero_()
+        pre = self.network == "skippfn" and self.runner.ea_slots(self.graph, 11, 13)
+        if pre:      # the EdgeAggregation weights go to their constant-memory slots on a second stream, beside the batch packer
+            main = torch.cuda.current_stream()
+            if getattr(self, "_prep_stream", None) is None:
+                self._prep_stream = torch.cuda.Stream(device=self.dev)
+            self._prep_stream.wait_stream(main)
+            with torch.cuda.stream(self._prep_stream):
+                self.runner.ea_upload(self.flat)
         launch_pack(self.store, self.ids, b, self.nt, self.et)
+        if pre:
+            main.wait_stream(self._prep_stream)
         if self.network == "skippfn":
             out = self.runner.forward(self.graph, b["x"], 11, b["edge_attr"], 13, self.flat, self.bufs,
-                                      drop_mode=1 if self.spec.p_drop > 0 else 0, rng_state=self.step_state)
+                                      drop_mode=1 if self.spec.p_drop > 0 else 0, rng_state=self.step_state, ea_uploaded=bool(pre))
         else:
             out = self.runner.forward(self.graph, b["x"], 11, b["edge_attr"], 13, self.flat, self.bufs)
         wls_args = (self.graph.ref, _lib.ptr(b["x"]), 11, _lib.ptr(b["edge_attr"]), 13, _lib.ptr(out), _lib.ptr(self.stats), *self.coefs,
