@@ -397,9 +397,24 @@ __global__ void k_pack_copy(const float* __restrict__ x_all, const float* __rest
       vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
       vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
     }
-    if ((threadIdx.x & 31) == 0) {  // vn_kv > 0: IEEE order == integer order
-      atomicMin((int*)&vminmax[0], __float_as_int(vmin));
-      atomicMax((int*)&vminmax[1], __float_as_int(vmax));
+    // one atomic pair per CTA (all launches hit the same two words: per-warp atomics queued 32 k deep at B = 4096)
+    __shared__ float s_mm[2][32];
+    const int warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    if ((threadIdx.x & 31) == 0) {
+      s_mm[0][warp] = vmin;
+      s_mm[1][warp] = vmax;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < nw; ++w) {
+        vmin = fminf(vmin, s_mm[0][w]);
+        vmax = fmaxf(vmax, s_mm[1][w]);
+      }
+      // vn_kv > 0: IEEE order == integer order; CTAs that saw no bus row (slices beyond the graph) hold the neutral elements
+      if (vmin <= vmax) {
+        atomicMin((int*)&vminmax[0], __float_as_int(vmin));
+        atomicMax((int*)&vminmax[1], __float_as_int(vmax));
+      }
     }
   }
 }
