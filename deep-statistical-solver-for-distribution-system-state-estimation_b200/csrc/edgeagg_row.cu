@@ -347,10 +347,13 @@ struct BwdBufs {
   uint32_t* gate;                  // [Z] ReLU gates of the in-edges: bit h = pre-activation of hidden unit h is positive
   uint32_t* zrow;                  // [Z] destination row (tile-local) of every CSR entry
   float* gxp;                      // [TR][8] grad_x share of the upper half
+  float* avz;                      // [Z][8] attributes of every CSR entry as phase B used them (sign-flipped for reversed entries; 6 used):
+                                   // phase C's edge role reads them with two vector loads instead of re-deriving them per entry
 };
 
 __host__ __device__ inline size_t bwd_smem_bytes(int TR, int ER, int Z, int xs, int eas) {
-  size_t b = 1024 + 5 * (size_t)TR * HID * 4 + 2 * (size_t)round16u((uint32_t)(Z + 8) * 4u) + (size_t)TR * FP * 4 + 2 * (size_t)stage_layout(TR, ER, Z, xs, eas).bytes + 64;
+  size_t b = 1024 + 5 * (size_t)TR * HID * 4 + 2 * (size_t)round16u((uint32_t)(Z + 8) * 4u) + (size_t)TR * FP * 4 + (size_t)Z * 32 +
+             2 * (size_t)stage_layout(TR, ER, Z, xs, eas).bytes + 64;
   const size_t red = 1024 + (size_t)BWD_WARPS * RED_SLOTS * HID * 4;
   return b > red ? b : red;
 }
@@ -426,6 +429,11 @@ __device__ __forceinline__ void bwd_phase_b(const EaRowArgs& a, const TileView& 
     const int c = v.col[z] - v.n0;
     float av[FE];
     load_attr(v, v.eid[z], a.eas, a.fe, av);
+    if (H0 == 0) {   // keep them for phase C (FE = 6: one 16-byte and one 8-byte store)
+      static_assert(FE == 6, "avz layout");
+      sts4(b.avz + 8 * z, make_float2(av[0], av[1]), make_float2(av[2], av[3]));
+      *reinterpret_cast<float2*>(b.avz + 8 * z + 4) = make_float2(av[4], av[5]);
+    }
     const float m0 = -2.0f * av[0], m2 = -2.0f * av[2];   // the twin's attributes: columns 0 and 2 flipped once more
     uint32_t gate = 0u;
 #pragma unroll
@@ -497,7 +505,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_ea_row_bwd(EaRowArgs a, cons
   b.gate = reinterpret_cast<uint32_t*>(base + 5 * BUF);
   b.zrow = reinterpret_cast<uint32_t*>(base + 5 * BUF + (size_t)round16u((uint32_t)(Z + 8) * 4u));
   b.gxp = reinterpret_cast<float*>(base + 5 * BUF + 2 * (size_t)round16u((uint32_t)(Z + 8) * 4u));
-  char* stage0 = reinterpret_cast<char*>(b.gxp) + (size_t)TR * FP * 4;
+  b.avz = b.gxp + (size_t)TR * FP;
+  char* stage0 = reinterpret_cast<char*>(b.avz) + (size_t)Z * 32;
   uint64_t* bar = reinterpret_cast<uint64_t*>(stage0 + 2 * (size_t)L.bytes);   // [0], [1]: input stages, [2]: upstream gradient tile
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, ntiles = g.num_tiles, stride = gridDim.x;
   const int row = tid & 255, half = tid >> 8, K0 = half * 4;   // the half is warp-uniform
@@ -629,11 +638,12 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_ea_row_bwd(EaRowArgs a, cons
       const int nZ = v.rowptr[nT] - v.z0;
       for (int z = 2 * (warp & 3) + rsel; z < nZ; z += 8) {
         const int rr = (int)b.zrow[z];
-        const uint32_t id = v.eid[z], gate = b.gate[z] >> (2 * l16);
+        const uint32_t gate = b.gate[z] >> (2 * l16);
         const float2 gs = *reinterpret_cast<const float2*>(b.Gb + rr * HID + (((l16 >> 1) ^ (rr & 7)) << 2) + ((l16 & 1) << 1));
         const float2 ge = make_float2((gate & 1u) ? gs.x : 0.0f, (gate & 2u) ? gs.y : 0.0f);
-        float av[FE];
-        load_attr(v, id, a.eas, fe, av);
+        const float4 a0 = lds4(b.avz + 8 * z);
+        const float2 a1 = *reinterpret_cast<const float2*>(b.avz + 8 * z + 4);
+        const float av[FE] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y};
 #pragma unroll
         for (int i = 0; i < FE; ++i) fma2(acc[i], ge, av[i]);
       }
