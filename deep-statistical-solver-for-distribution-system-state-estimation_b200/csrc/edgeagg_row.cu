@@ -344,15 +344,14 @@ constexpr int BWD_WARPS = BWD_THREADS / 32;
 constexpr int RED_SLOTS = 18;    // 8 packed accumulators + 1 packed scalar per lane and warp
 struct BwdBufs {
   float *Pb, *Qb, *Gb, *Sb, *GO;   // [TR][32] swizzled: P -> grad_P, Q -> grad_Q, grad_S, S, upstream gradient
-  uint32_t* gate;                  // [Z] ReLU gates of the in-edges: bit h = pre-activation of hidden unit h is positive
-  uint32_t* zrow;                  // [Z] destination row (tile-local) of every CSR entry
   float* gxp;                      // [TR][8] grad_x share of the upper half
-  float* avz;                      // [Z][8] attributes of every CSR entry as phase B used them (sign-flipped for reversed entries; 6 used):
-                                   // phase C's edge role reads them with two vector loads instead of re-deriving them per entry
+  float* avz;                      // [Z][8] one record per CSR entry for phase C's edge role: the 6 attributes as phase B used them
+                                   // (sign-flipped for reversed entries), the destination row (tile-local), the ReLU gate word of the
+                                   // in-edge (bit h = pre-activation of hidden unit h is positive; one 16-bit half per thread half)
 };
 
 __host__ __device__ inline size_t bwd_smem_bytes(int TR, int ER, int Z, int xs, int eas) {
-  size_t b = 1024 + 5 * (size_t)TR * HID * 4 + 2 * (size_t)round16u((uint32_t)(Z + 8) * 4u) + (size_t)TR * FP * 4 + (size_t)Z * 32 +
+  size_t b = 1024 + 5 * (size_t)TR * HID * 4 + (size_t)TR * FP * 4 + (size_t)Z * 32 +
              2 * (size_t)stage_layout(TR, ER, Z, xs, eas).bytes + 64;
   const size_t red = 1024 + (size_t)BWD_WARPS * RED_SLOTS * HID * 4;
   return b > red ? b : red;
@@ -467,8 +466,9 @@ __device__ __forceinline__ void bwd_phase_b(const EaRowArgs& a, const TileView& 
       gQ[2 * kk] = add2(gQ[2 * kk], make_float2(t0.x > 0.0f ? gc.x : 0.0f, t0.y > 0.0f ? gc.y : 0.0f));
       gQ[2 * kk + 1] = add2(gQ[2 * kk + 1], make_float2(t1.x > 0.0f ? gc.z : 0.0f, t1.y > 0.0f ? gc.w : 0.0f));
     }
-    reinterpret_cast<unsigned short*>(b.gate)[2 * z + (H0 ? 1 : 0)] = (unsigned short)gate;
-    if (H0 == 0) b.zrow[z] = (uint32_t)row;
+    // the entry's record for phase C: [6 attributes | destination row | gate word] = 32 bytes, read back with two vector loads
+    reinterpret_cast<unsigned short*>(b.avz + 8 * z + 7)[H0 ? 1 : 0] = (unsigned short)gate;
+    if (H0 == 0) reinterpret_cast<uint32_t*>(b.avz)[8 * z + 6] = (uint32_t)row;
   }
   // grad_x share of this half: sum_h W1a[h][i] gP[h] + W1b[h][i] gQ[h], pairs of hidden units in the two lanes
   if (want_gx) {
@@ -502,9 +502,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_ea_row_bwd(EaRowArgs a, cons
   b.Qb = reinterpret_cast<float*>(base + 2 * BUF);
   b.Gb = reinterpret_cast<float*>(base + 3 * BUF);
   b.Sb = reinterpret_cast<float*>(base + 4 * BUF);
-  b.gate = reinterpret_cast<uint32_t*>(base + 5 * BUF);
-  b.zrow = reinterpret_cast<uint32_t*>(base + 5 * BUF + (size_t)round16u((uint32_t)(Z + 8) * 4u));
-  b.gxp = reinterpret_cast<float*>(base + 5 * BUF + 2 * (size_t)round16u((uint32_t)(Z + 8) * 4u));
+  b.gxp = reinterpret_cast<float*>(base + 5 * BUF);
   b.avz = b.gxp + (size_t)TR * FP;
   char* stage0 = reinterpret_cast<char*>(b.avz) + (size_t)Z * 32;
   uint64_t* bar = reinterpret_cast<uint64_t*>(stage0 + 2 * (size_t)L.bytes);   // [0], [1]: input stages, [2]: upstream gradient tile
@@ -637,12 +635,11 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_ea_row_bwd(EaRowArgs a, cons
     } else {
       const int nZ = v.rowptr[nT] - v.z0;
       for (int z = 2 * (warp & 3) + rsel; z < nZ; z += 8) {
-        const int rr = (int)b.zrow[z];
-        const uint32_t gate = b.gate[z] >> (2 * l16);
+        const float4 a0 = lds4(b.avz + 8 * z), a1 = lds4(b.avz + 8 * z + 4);
+        const int rr = (int)__float_as_uint(a1.z);
+        const uint32_t gate = __float_as_uint(a1.w) >> (2 * l16);
         const float2 gs = *reinterpret_cast<const float2*>(b.Gb + rr * HID + (((l16 >> 1) ^ (rr & 7)) << 2) + ((l16 & 1) << 1));
         const float2 ge = make_float2((gate & 1u) ? gs.x : 0.0f, (gate & 2u) ? gs.y : 0.0f);
-        const float4 a0 = lds4(b.avz + 8 * z);
-        const float2 a1 = *reinterpret_cast<const float2*>(b.avz + 8 * z + 4);
         const float av[FE] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y};
 #pragma unroll
         for (int i = 0; i < FE; ++i) fma2(acc[i], ge, av[i]);
