@@ -345,13 +345,15 @@ constexpr int RED_SLOTS = 18;    // 8 packed accumulators + 1 packed scalar per 
 struct BwdBufs {
   float *Pb, *Qb, *Gb, *Sb, *GO;   // [TR][32] swizzled: P -> grad_P, Q -> grad_Q, grad_S, S, upstream gradient
   float* gxp;                      // [TR][8] grad_x share of the upper half
+  float* x8;                       // [TR][8] the tile's node features as aligned 32-byte rows (phase A1 has them in registers; the raw
+                                   // stage rows are 44 bytes apart, so phase C's x roles would need 8 scalar loads per row)
   float* avz;                      // [Z][8] one record per CSR entry for phase C's edge role: the 6 attributes as phase B used them
                                    // (sign-flipped for reversed entries), the destination row (tile-local), the ReLU gate word of the
                                    // in-edge (bit h = pre-activation of hidden unit h is positive; one 16-bit half per thread half)
 };
 
 __host__ __device__ inline size_t bwd_smem_bytes(int TR, int ER, int Z, int xs, int eas) {
-  size_t b = 1024 + 5 * (size_t)TR * HID * 4 + (size_t)TR * FP * 4 + (size_t)Z * 32 +
+  size_t b = 1024 + 5 * (size_t)TR * HID * 4 + 2 * (size_t)TR * FP * 4 + (size_t)Z * 32 +
              2 * (size_t)stage_layout(TR, ER, Z, xs, eas).bytes + 64;
   const size_t red = 1024 + (size_t)BWD_WARPS * RED_SLOTS * HID * 4;
   return b > red ? b : red;
@@ -371,6 +373,10 @@ __device__ __forceinline__ void bwd_phase_a1(const EaRowArgs& a, const TileView&
   constexpr int K0 = H0 / 4;
   float xv[FP];
   load_x(v, row, a.xs, a.fn, xv);
+  if (H0 == 0) {
+    sts4(b.x8 + row * FP, make_float2(xv[0], xv[1]), make_float2(xv[2], xv[3]));
+    sts4(b.x8 + row * FP + 4, make_float2(xv[4], xv[5]), make_float2(xv[6], xv[7]));
+  }
   float2 P[NHALF / 2], Q[NHALF / 2];
 #pragma unroll
   for (int j = 0; j < NHALF / 2; ++j) {
@@ -503,7 +509,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_ea_row_bwd(EaRowArgs a, cons
   b.Gb = reinterpret_cast<float*>(base + 3 * BUF);
   b.Sb = reinterpret_cast<float*>(base + 4 * BUF);
   b.gxp = reinterpret_cast<float*>(base + 5 * BUF);
-  b.avz = b.gxp + (size_t)TR * FP;
+  b.x8 = b.gxp + (size_t)TR * FP;
+  b.avz = b.x8 + (size_t)TR * FP;
   char* stage0 = reinterpret_cast<char*>(b.avz) + (size_t)Z * 32;
   uint64_t* bar = reinterpret_cast<uint64_t*>(stage0 + 2 * (size_t)L.bytes);   // [0], [1]: input stages, [2]: upstream gradient tile
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, ntiles = g.num_tiles, stride = gridDim.x;
@@ -621,8 +628,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) k_ea_row_bwd(EaRowArgs a, cons
       for (int rr = 2 * (warp & 1) + rsel; rr < nT; rr += 4) {
         const int off = rr * HID + (((l16 >> 1) ^ (rr & 7)) << 2) + ((l16 & 1) << 1);   // elements 2 l16, 2 l16 + 1 of a swizzled row
         const float2 gpair = *reinterpret_cast<const float2*>(G + off);
-        float xv[FP];
-        load_x(v, rr, a.xs, fn, xv);
+        const float4 x0 = lds4(b.x8 + rr * FP), x1 = lds4(b.x8 + rr * FP + 4);
+        const float xv[FP] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
         for (int i = 0; i < FP; ++i) fma2(acc[i], gpair, xv[i]);
         if (src_blk) {   // b2[o] += deg * g[o]
